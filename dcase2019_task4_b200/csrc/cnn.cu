@@ -1,0 +1,792 @@
+// CNN stack of the CRNN: 3 x { conv3x3 + bias -> BatchNorm2d(eps 1e-3, momentum 0.99) -> GLU
+// (Linear64->64 over channels, times sigmoid of the un-projected input) -> Dropout(0.5) -> AvgPool (2,4) }.
+//
+// Replaces (reference file:line):  baseline/models/CNN.py:5-16 (GLU), :42-67 (block), :85-89 (forward),
+// and their autograd backward.  Activations are channels-last fp32: [B, T, F, 64].
+//
+// Layer 0 never materialises its [B,64,864,64] conv output (340 MB): BN batch statistics come from the 9x9
+// tap moments of the input (conv0 is linear in the 9 taps), BN is folded into the conv weights, and
+// conv0 -> BN -> GLU -> dropout -> pool is recomputed per 128-pixel tile in both passes.
+#include "cnn.cuh"
+
+namespace {
+
+constexpr int kC = 64;
+constexpr int kPitch = 68;   // smem row pitch (floats): conflict-free 128-bit row access
+constexpr int kTile = 128;   // pixels per tile = threads per CTA
+constexpr float kBnEps = 1e-3f;
+constexpr float kBnMomentum = 0.99f;
+
+// acc[n] += sum_k a_row[k] * W[k * 64 + n];  a_row (own smem row) and W (smem, broadcast reads).
+template <int K>
+__device__ __forceinline__ void rowmat64(const float* __restrict__ a_row, const float* __restrict__ W,
+                                         float (&acc)[64]) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(a_row + k0);
+        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float4* wrow = reinterpret_cast<const float4*>(W + (k0 + kk) * 64);
+#pragma unroll
+            for (int n4 = 0; n4 < 16; ++n4) {
+                const float4 w = wrow[n4];
+                acc[4 * n4 + 0] = fmaf(av[kk], w.x, acc[4 * n4 + 0]);
+                acc[4 * n4 + 1] = fmaf(av[kk], w.y, acc[4 * n4 + 1]);
+                acc[4 * n4 + 2] = fmaf(av[kk], w.z, acc[4 * n4 + 2]);
+                acc[4 * n4 + 3] = fmaf(av[kk], w.w, acc[4 * n4 + 3]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void resolve_rng(const DropoutCfg& d, uint64_t& seed, uint32_t& step) {
+    seed = d.seed; step = d.step;
+    if (d.sc) { seed = d.sc->seed; step = d.sc->step; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layer 0: tap moments  sum x_k (9) and sum x_k x_l (45, k <= l) over all output pixels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cnn0_moments_kernel(const float* __restrict__ x, long long n_pix, int T, double* __restrict__ mom) {
+    __shared__ float red[8][54];
+    float acc[54];
+#pragma unroll
+    for (int i = 0; i < 54; ++i) acc[i] = 0.f;
+    for (long long p = blockIdx.x * 256ll + threadIdx.x; p < n_pix; p += (long long)gridDim.x * 256) {
+        const int f = (int)(p & 63);
+        const int t = (int)((p >> 6) % T);
+        float tap[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int dy = k / 3 - 1, dx = k % 3 - 1;
+            const bool ok = (t + dy >= 0) && (t + dy < T) && (f + dx >= 0) && (f + dx < 64);
+            tap[k] = ok ? __ldg(x + p + dy * 64 + dx) : 0.f;
+        }
+        int i = 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            acc[k] += tap[k];
+#pragma unroll
+            for (int l = k; l < 9; ++l) { acc[i] = fmaf(tap[k], tap[l], acc[i]); ++i; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 54; ++i) {
+        const float v = warp_sum(acc[i]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 54) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
+        atomicAdd(mom + threadIdx.x, s);
+    }
+}
+
+__device__ __forceinline__ int tri_index(int k, int l) {  // k <= l, order of cnn0_moments_kernel
+    return 9 + k * 9 - (k * (k - 1)) / 2 + (l - k);
+}
+
+// One block of 64 threads: batch (or running) statistics of conv0's output from the tap moments, BN folded
+// into the conv weights, running-stat update (momentum 0.99, unbiased variance), CNN.py:49.
+__global__ void bn0_finalize_kernel(const double* __restrict__ mom, long long n_pix, const float* __restrict__ w,
+                                    const float* __restrict__ b, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float* __restrict__ running, int training,
+                                    float* __restrict__ fold0) {
+    const int c = threadIdx.x;
+    double mean, var;
+    if (training) {
+        const double inv_n = 1.0 / (double)n_pix;
+        double m[9];
+        for (int k = 0; k < 9; ++k) m[k] = mom[k] * inv_n;
+        mean = b[c];
+        for (int k = 0; k < 9; ++k) mean += (double)w[c * 9 + k] * m[k];
+        var = 0.0;
+        for (int k = 0; k < 9; ++k)
+            for (int l = 0; l < 9; ++l) {
+                const double M = mom[k <= l ? tri_index(k, l) : tri_index(l, k)] * inv_n;
+                var += (double)w[c * 9 + k] * (double)w[c * 9 + l] * (M - m[k] * m[l]);
+            }
+        if (var < 0.0) var = 0.0;
+        if (running) {
+            running[c] = (1.f - kBnMomentum) * running[c] + kBnMomentum * (float)mean;
+            const double unbiased = var * (double)n_pix / (double)(n_pix - 1);
+            running[64 + c] = (1.f - kBnMomentum) * running[64 + c] + kBnMomentum * (float)unbiased;
+        }
+    } else {
+        mean = running[c];
+        var = running[64 + c];
+    }
+    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+    const float a = gamma[c] * invstd;
+    for (int k = 0; k < 9; ++k) fold0[kFold0Wf + k * 64 + c] = a * w[c * 9 + k];
+    fold0[kFold0Bf + c] = a * (b[c] - (float)mean) + beta[c];
+    fold0[kFold0Mean + c] = (float)mean;
+    fold0[kFold0Invstd + c] = invstd;
+    fold0[kFold0A + c] = a;
+}
+
+// BN statistics of layers 1,2 from the conv epilogue's per-channel sum / sum of squares.
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, long long n_pix, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running, int training,
+                                   float* __restrict__ bn) {
+    const int c = threadIdx.x;
+    double mean, var;
+    if (training) {
+        mean = stats[c] / (double)n_pix;
+        var = stats[64 + c] / (double)n_pix - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (running) {
+            running[c] = (1.f - kBnMomentum) * running[c] + kBnMomentum * (float)mean;
+            const double unbiased = var * (double)n_pix / (double)(n_pix - 1);
+            running[64 + c] = (1.f - kBnMomentum) * running[64 + c] + kBnMomentum * (float)unbiased;
+        }
+    } else {
+        mean = running[c];
+        var = running[64 + c];
+    }
+    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+    const float a = gamma[c] * invstd;
+    bn[kBnScale + c] = a;
+    bn[kBnShift + c] = beta[c] - a * (float)mean;
+    bn[kBnMean + c] = (float)mean;
+    bn[kBnInvstd + c] = invstd;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared pieces of the GLU / pool kernels
+// ---------------------------------------------------------------------------------------------
+struct GluArgs {
+    const float* src;      // L0: x [B][T][64]; else ypre [P][64]
+    long long n_pix;       // P
+    int T;                 // L0 only: frames per clip
+    int F;                 // 64 / 16 / 4
+    const float* aff;      // L0: fold0; else bn
+    const float* gamma;    // bwd, layers 1,2
+    const float* beta;     // bwd, layers 1,2
+    const float* glu_w;
+    const float* glu_b;
+    DropoutCfg drop;
+    float* out;            // fwd: pooled output [P/8][64]
+    const float* d_out;    // bwd: grad of pooled output
+    float* d_y;            // bwd layers 1,2: grad wrt BN output [P][64]
+    float* stat_acc;       // bwd: layers 1,2 -> s12 [2][64]; L0 -> acc0 {S1[64], G[64][9]}
+    float* g_glu_w;
+    float* g_glu_b;
+};
+
+// y row (BN output) of this thread's pixel into its smem row; L0 recomputes conv0 from the 9 taps.
+template <bool L0>
+__device__ __forceinline__ void produce_y_row(const GluArgs& a, long long p, bool valid, const float* aff_s,
+                                              const float* xs, float* a_row, float (&tap)[9]) {
+    if (L0) {
+        const int tr = threadIdx.x >> 6, f = threadIdx.x & 63;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) tap[k] = xs[(tr + k / 3) * 66 + f + (k % 3)];
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+            float4 y = *reinterpret_cast<const float4*>(aff_s + kFold0Bf + 4 * c4);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(aff_s + kFold0Wf + k * 64 + 4 * c4);
+                y.x = fmaf(w.x, tap[k], y.x); y.y = fmaf(w.y, tap[k], y.y);
+                y.z = fmaf(w.z, tap[k], y.z); y.w = fmaf(w.w, tap[k], y.w);
+            }
+            *reinterpret_cast<float4*>(a_row + 4 * c4) = y;
+        }
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(a.src + p * 64);
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float4 v = __ldg(src + c4);
+                const float4 sc = *reinterpret_cast<const float4*>(aff_s + kBnScale + 4 * c4);
+                const float4 sh = *reinterpret_cast<const float4*>(aff_s + kBnShift + 4 * c4);
+                y.x = fmaf(sc.x, v.x, sh.x); y.y = fmaf(sc.y, v.y, sh.y);
+                y.z = fmaf(sc.z, v.z, sh.z); y.w = fmaf(sc.w, v.w, sh.w);
+            }
+            *reinterpret_cast<float4*>(a_row + 4 * c4) = y;
+        }
+    }
+}
+
+// stage x rows t0-1 .. t0+2 (zero padded) of clip b for a layer-0 tile (2 rows x 64 mel bins)
+__device__ __forceinline__ void load_xs(const float* __restrict__ x, long long tile, int T, float* xs) {
+    const long long r0 = 2 * tile;
+    const long long b = r0 / T;
+    const int t0 = (int)(r0 % T);
+    for (int i = threadIdx.x; i < 4 * 66; i += kTile) {
+        const int hr = i / 66, hc = i % 66;
+        const int tt = t0 - 1 + hr, ff = hc - 1;
+        const bool ok = tt >= 0 && tt < T && ff >= 0 && ff < 64;
+        xs[i] = ok ? __ldg(x + (b * T + tt) * 64 + ff) : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: [conv0 | BN apply] -> GLU -> dropout -> avg-pool (2,4)
+// ---------------------------------------------------------------------------------------------
+template <bool L0>
+__global__ void __launch_bounds__(kTile)
+glu_pool_fwd_kernel(GluArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wt = smem;                 // [64 k][64 n]
+    float* bg = Wt + 4096;            // [64]
+    float* aff_s = bg + 64;           // fold0 (832) or bn (256)
+    float* A = aff_s + 832;           // [128][68]
+    float* xs = A + kTile * kPitch;   // [4][66] (L0)
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < 4096; i += kTile) Wt[(i & 63) * 64 + (i >> 6)] = __ldg(a.glu_w + i);
+    if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
+    for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kTile) aff_s[i] = a.aff[i];
+    uint64_t seed; uint32_t step;
+    resolve_rng(a.drop, seed, step);
+    __syncthreads();
+
+    const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
+    const long long n_out = a.n_pix >> 3;
+    const int wpr = a.F >> 2;
+    float* a_row = A + tid * kPitch;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long p = tile * kTile + tid;
+        const bool valid = p < a.n_pix;
+        if (L0) { load_xs(a.src, tile, a.T, xs); __syncthreads(); }
+        float tap[9];
+        produce_y_row<L0>(a, p, valid, aff_s, xs, a_row, tap);
+        float acc[64];
+#pragma unroll
+        for (int n = 0; n < 64; ++n) acc[n] = bg[n];
+        rowmat64<64>(a_row, Wt, acc);
+        uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+        float scale = 1.f;
+        if (a.drop.enabled) {
+            const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
+            keep_lo = r.x; keep_hi = r.y; scale = 2.f;
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+            const float4 y = *reinterpret_cast<const float4*>(a_row + 4 * c4);
+            const uint32_t bits = (c4 < 8 ? keep_lo : keep_hi) >> ((4 * c4) & 31);
+            float4 z;
+            z.x = (bits & 1u) ? acc[4 * c4 + 0] * sigmoid_fast(y.x) * scale : 0.f;
+            z.y = (bits & 2u) ? acc[4 * c4 + 1] * sigmoid_fast(y.y) * scale : 0.f;
+            z.z = (bits & 4u) ? acc[4 * c4 + 2] * sigmoid_fast(y.z) * scale : 0.f;
+            z.w = (bits & 8u) ? acc[4 * c4 + 3] * sigmoid_fast(y.w) * scale : 0.f;
+            if (!valid) z = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(a_row + 4 * c4) = z;
+        }
+        __syncthreads();
+        {   // pooling: 16 windows x 8 channel groups
+            const int w = tid >> 3, cg = tid & 7;
+            const int wr = w / wpr, wc = w - wr * wpr;
+            const int r0 = (2 * wr) * a.F + 4 * wc;
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* row = A + (r0 + i * a.F + j) * kPitch + 8 * cg;
+                    const float4 u = *reinterpret_cast<const float4*>(row);
+                    const float4 v = *reinterpret_cast<const float4*>(row + 4);
+                    s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+                    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+                }
+            const long long op = tile * 16 + w;
+            if (op < n_out) {
+                float4* dst = reinterpret_cast<float4*>(a.out + op * 64 + 8 * cg);
+                dst[0] = make_float4(0.125f * s0.x, 0.125f * s0.y, 0.125f * s0.z, 0.125f * s0.w);
+                dst[1] = make_float4(0.125f * s1.x, 0.125f * s1.y, 0.125f * s1.z, 0.125f * s1.w);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of [conv0 | BN apply] -> GLU -> dropout -> pool, recomputing the forward per tile
+// ---------------------------------------------------------------------------------------------
+template <bool L0>
+__global__ void __launch_bounds__(kTile)
+glu_pool_bwd_kernel(GluArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wt = smem;                 // [64 k][64 n]  Wt[k][n] = Wg[n][k]  (lin = Wg y)
+    float* Wn = Wt + 4096;            // [64 n][64 k]  natural            (d_y += Wg^T d_lin)
+    float* bg = Wn + 4096;            // [64]
+    float* aff_s = bg + 64;           // fold0 (832) or bn (256)
+    float* gb = aff_s + 832;          // [2][64]: 1/gamma, beta (layers 1,2)
+    float* A = gb + 128;              // y        [128][68]
+    float* D = A + kTile * kPitch;    // d_lin    [128][68]
+    float* E = D + kTile * kPitch;    // d_y      [128][68]
+    float* xs = E + kTile * kPitch;   // [4][66] (L0)
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < 4096; i += kTile) {
+        const float w = __ldg(a.glu_w + i);
+        Wn[i] = w;
+        Wt[(i & 63) * 64 + (i >> 6)] = w;
+    }
+    if (tid < 64) {
+        bg[tid] = __ldg(a.glu_b + tid);
+        if (!L0) {
+            const float g = __ldg(a.gamma + tid);
+            gb[tid] = fabsf(g) > 1e-20f ? 1.f / g : 0.f;
+            gb[64 + tid] = __ldg(a.beta + tid);
+        }
+    }
+    for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kTile) aff_s[i] = a.aff[i];
+    uint64_t seed; uint32_t step;
+    resolve_rng(a.drop, seed, step);
+    __syncthreads();
+
+    const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
+    const int wpr = a.F >> 2;
+    float* a_row = A + tid * kPitch;
+    float* d_row = D + tid * kPitch;
+    float* e_row = E + tid * kPitch;
+
+    // persistent partial sums
+    float accW[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) accW[i] = 0.f;
+    float cs0 = 0.f, cs1 = 0.f;   // tid < 64: db_glu, S1 ; tid >= 64: S2 (layers 1,2)
+    float cg[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // L0: G[c][taps]
+    const int nb = tid >> 3, kb = tid & 7;
+    const int cc = tid & 63;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long p = tile * kTile + tid;
+        const bool valid = p < a.n_pix;
+        if (L0) { load_xs(a.src, tile, a.T, xs); __syncthreads(); }
+        float tap[9];
+        produce_y_row<L0>(a, p, valid, aff_s, xs, a_row, tap);
+        float acc[64];
+#pragma unroll
+        for (int n = 0; n < 64; ++n) acc[n] = bg[n];
+        rowmat64<64>(a_row, Wt, acc);                 // lin
+        uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+        float scale = 0.125f;
+        if (a.drop.enabled) {
+            const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
+            keep_lo = r.x; keep_hi = r.y; scale = 0.25f;
+        }
+        {   // window of this pixel inside the tile -> pooled pixel index
+            const int tr = tid / a.F, f = tid - tr * a.F;
+            const long long op = tile * 16 + (tr >> 1) * wpr + (f >> 2);
+            const float4* dsrc = reinterpret_cast<const float4*>(a.d_out + op * 64);
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                float4 dz = valid ? __ldg(dsrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t bits = (c4 < 8 ? keep_lo : keep_hi) >> ((4 * c4) & 31);
+                dz.x = (bits & 1u) ? dz.x * scale : 0.f;
+                dz.y = (bits & 2u) ? dz.y * scale : 0.f;
+                dz.z = (bits & 4u) ? dz.z * scale : 0.f;
+                dz.w = (bits & 8u) ? dz.w * scale : 0.f;
+                const float4 y = *reinterpret_cast<const float4*>(a_row + 4 * c4);
+                const float gx = sigmoid_fast(y.x), gy = sigmoid_fast(y.y), gz = sigmoid_fast(y.z), gw = sigmoid_fast(y.w);
+                *reinterpret_cast<float4*>(d_row + 4 * c4) = make_float4(dz.x * gx, dz.y * gy, dz.z * gz, dz.w * gw);
+                // direct path through the gate: dz * lin * g * (1 - g)
+                acc[4 * c4 + 0] = dz.x * acc[4 * c4 + 0] * gx * (1.f - gx);
+                acc[4 * c4 + 1] = dz.y * acc[4 * c4 + 1] * gy * (1.f - gy);
+                acc[4 * c4 + 2] = dz.z * acc[4 * c4 + 2] * gz * (1.f - gz);
+                acc[4 * c4 + 3] = dz.w * acc[4 * c4 + 3] * gw * (1.f - gw);
+            }
+        }
+        rowmat64<64>(d_row, Wn, acc);                 // + Wg^T d_lin  -> d_y
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+            const float4 v = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+            *reinterpret_cast<float4*>(e_row + 4 * c4) = v;
+            if (!L0 && valid) reinterpret_cast<float4*>(a.d_y + p * 64)[c4] = v;
+        }
+        __syncthreads();
+        // dWg[n][k] += sum_p d_lin[p][n] * y[p][k]
+#pragma unroll 4
+        for (int q = 0; q < kTile; ++q) {
+            const float4 d4 = *reinterpret_cast<const float4*>(D + q * kPitch + 4 * nb);
+            const float4 y0 = *reinterpret_cast<const float4*>(A + q * kPitch + 8 * kb);
+            const float4 y1 = *reinterpret_cast<const float4*>(A + q * kPitch + 8 * kb + 4);
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) accW[i * 8 + j] = fmaf(dv[i], yv[j], accW[i * 8 + j]);
+        }
+        // column sums
+        if (tid < 64) {
+            for (int q = 0; q < kTile; ++q) {
+                cs0 += D[q * kPitch + cc];
+                const float e = E[q * kPitch + cc];
+                cs1 += e;
+                if (L0) {
+                    const float* xr = xs + (q >> 6) * 66 + (q & 63);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) cg[k] = fmaf(e, xr[(k / 3) * 66 + (k % 3)], cg[k]);
+                }
+            }
+        } else {
+            for (int q = 0; q < kTile; ++q) {
+                const float e = E[q * kPitch + cc];
+                if (L0) {
+                    const float* xr = xs + (q >> 6) * 66 + (q & 63);
+#pragma unroll
+                    for (int k = 5; k < 9; ++k) cg[k - 5] = fmaf(e, xr[(k / 3) * 66 + (k % 3)], cg[k - 5]);
+                } else {
+                    cs0 = fmaf(e, (A[q * kPitch + cc] - gb[64 + cc]) * gb[cc], cs0);   // d_y * xhat
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(a.g_glu_w + (4 * nb + i) * 64 + 8 * kb + j, accW[i * 8 + j]);
+    if (tid < 64) {
+        atomicAdd(a.g_glu_b + cc, cs0);
+        atomicAdd(a.stat_acc + cc, cs1);                       // S1
+        if (L0) for (int k = 0; k < 5; ++k) atomicAdd(a.stat_acc + 64 + cc * 9 + k, cg[k]);
+    } else {
+        if (L0) { for (int k = 5; k < 9; ++k) atomicAdd(a.stat_acc + 64 + cc * 9 + k, cg[k - 5]); }
+        else atomicAdd(a.stat_acc + 64 + cc, cs0);             // S2
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv3x3, 64 -> 64 channels, stride 1, pad 1 (CNN.py:46-47), implicit GEMM on the tile's halo.
+// Also used as the data-gradient pass with mirrored / transposed weights.
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_w_prep_kernel(const float* __restrict__ w, float* __restrict__ w_fwd,
+                                   float* __restrict__ w_dgrad) {
+    // w [n][c][tap]; w_fwd [tap][c][n]; w_dgrad [tap'][n][c] with tap' = 8 - tap
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * 64 * 9; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9, c = (i / 9) & 63, n = i / 576;
+        const float v = __ldg(w + i);
+        w_fwd[tap * 4096 + c * 64 + n] = v;
+        w_dgrad[(8 - tap) * 4096 + n * 64 + c] = v;
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kTile, 1)
+conv3x3_kernel(const float* __restrict__ in, int n_rows, int T_l, int F, const float* __restrict__ w_prep,
+               const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wc = smem;                   // [9][64][64]
+    float* halo = Wc + 9 * 4096;        // [(TR+2)*(F+2)][68]
+    const int tid = threadIdx.x;
+    const int TR = kTile / F;
+    const int HW = F + 2;
+    const int HP = (TR + 2) * HW;
+    for (int i = tid; i < 9 * 1024; i += kTile)
+        reinterpret_cast<float4*>(Wc)[i] = __ldg(reinterpret_cast<const float4*>(w_prep) + i);
+    const int tr = tid / F, f = tid - tr * F;
+    double stat_acc = 0.0;
+    const int n_tiles = (n_rows + TR - 1) / TR;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int R0 = tile * TR;
+        for (int i = tid; i < HP * 16; i += kTile) {
+            const int hp = i >> 4, q = i & 15;
+            const int hr = hp / HW, hc = hp - hr * HW;
+            const int R = R0 - 1 + hr, ff = hc - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (R >= 0 && R < n_rows && ff >= 0 && ff < F)
+                v = __ldg(reinterpret_cast<const float4*>(in) + ((long long)R * F + ff) * 16 + q);
+            reinterpret_cast<float4*>(halo)[hp * 17 + q] = v;
+        }
+        __syncthreads();
+        const int R = R0 + tr;
+        const bool rvalid = R < n_rows;
+        const int t = R % T_l;
+        float acc[64];
+#pragma unroll
+        for (int n = 0; n < 64; ++n) acc[n] = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const bool ok = rvalid && (dy == 0 || (dy < 0 ? t > 0 : t < T_l - 1));
+            if (ok) rowmat64<64>(halo + ((tr + 1 + dy) * HW + f + 1 + dx) * kPitch, Wc + tap * 4096, acc);
+        }
+        if (rvalid) {
+            float4* dst = reinterpret_cast<float4*>(out + ((long long)R * F + f) * 64);
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4)
+                dst[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        }
+        __syncthreads();
+        if (STATS) {
+            float* tile_s = halo;   // [128][68], reuses the halo buffer
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4)
+                *reinterpret_cast<float4*>(tile_s + tid * kPitch + 4 * c4) =
+                    rvalid ? make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3])
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            float s = 0.f;
+            const int c = tid & 63;
+            if (tid < 64) { for (int q = 0; q < kTile; ++q) s += tile_s[q * kPitch + c]; }
+            else { for (int q = 0; q < kTile; ++q) { const float v = tile_s[q * kPitch + c]; s = fmaf(v, v, s); } }
+            stat_acc += (double)s;
+            __syncthreads();
+        }
+    }
+    if (STATS) atomicAdd(stats + tid, stat_acc);   // [0,64): sum, [64,128): sum of squares
+}
+
+// d_pre = a * (d_y - S1/N - xhat * S2/N)   (BatchNorm backward, batch statistics), in place.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, long long n_pix,
+                    const float* __restrict__ bn, const float* __restrict__ s12, float* __restrict__ g_gamma,
+                    float* __restrict__ g_beta, float* __restrict__ g_conv_b) {
+    __shared__ float sa[64], sm[64], si[64], s1[64], s2[64];
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        const float inv_n = 1.f / (float)n_pix;
+        sa[c] = bn[kBnScale + c]; sm[c] = bn[kBnMean + c]; si[c] = bn[kBnInvstd + c];
+        s1[c] = s12[c] * inv_n; s2[c] = s12[64 + c] * inv_n;
+        if (blockIdx.x == 0) { g_gamma[c] = s12[64 + c]; g_beta[c] = s12[c]; g_conv_b[c] = 0.f; }
+    }
+    __syncthreads();
+    const long long total = n_pix * 16;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i & 15) * 4;
+        float4 d = reinterpret_cast<float4*>(d_y)[i];
+        const float4 y = __ldg(reinterpret_cast<const float4*>(ypre) + i);
+        d.x = sa[c + 0] * (d.x - s1[c + 0] - (y.x - sm[c + 0]) * si[c + 0] * s2[c + 0]);
+        d.y = sa[c + 1] * (d.y - s1[c + 1] - (y.y - sm[c + 1]) * si[c + 1] * s2[c + 1]);
+        d.z = sa[c + 2] * (d.z - s1[c + 2] - (y.z - sm[c + 2]) * si[c + 2] * s2[c + 2]);
+        d.w = sa[c + 3] * (d.w - s1[c + 3] - (y.w - sm[c + 3]) * si[c + 3] * s2[c + 3]);
+        reinterpret_cast<float4*>(d_y)[i] = d;
+    }
+}
+
+// dW[n][c][tap] = sum_p d_pre[p][n] * in[p + tap][c];  grid = (chunks, 9 taps)
+__global__ void __launch_bounds__(kTile)
+conv_wgrad_kernel(const float* __restrict__ d_pre, const float* __restrict__ in, int n_rows, int T_l, int F,
+                  float* __restrict__ g_w) {
+    extern __shared__ __align__(16) float smem[];
+    float* Dp = smem;                    // [128][68]
+    float* In = Dp + kTile * kPitch;     // [128][68]
+    const int tid = threadIdx.x;
+    const int tap = blockIdx.y;
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    const int TR = kTile / F;
+    const int tr = tid / F, f = tid - tr * F;
+    const int nb = tid >> 3, kb = tid & 7;
+    const int n_tiles = (n_rows + TR - 1) / TR;
+    float accW[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) accW[i] = 0.f;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int R = tile * TR + tr;
+        const bool rvalid = R < n_rows;
+        const int t = R % T_l;
+        const bool ivalid = rvalid && (t + dy >= 0) && (t + dy < T_l) && (f + dx >= 0) && (f + dx < F);
+        const float4* dsrc = reinterpret_cast<const float4*>(d_pre) + ((long long)R * F + f) * 16;
+        const float4* isrc = reinterpret_cast<const float4*>(in) + ((long long)(R + dy) * F + f + dx) * 16;
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+            reinterpret_cast<float4*>(Dp + tid * kPitch)[c4] = rvalid ? __ldg(dsrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(In + tid * kPitch)[c4] = ivalid ? __ldg(isrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int q = 0; q < kTile; ++q) {
+            const float4 d4 = *reinterpret_cast<const float4*>(Dp + q * kPitch + 4 * nb);
+            const float4 y0 = *reinterpret_cast<const float4*>(In + q * kPitch + 8 * kb);
+            const float4 y1 = *reinterpret_cast<const float4*>(In + q * kPitch + 8 * kb + 4);
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) accW[i * 8 + j] = fmaf(dv[i], yv[j], accW[i * 8 + j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            atomicAdd(g_w + (4 * nb + i) * 576 + (8 * kb + j) * 9 + tap, accW[i * 8 + j]);
+}
+
+// Layer-0 parameter gradients from {S1, G} and the tap moments (one block of 64 threads).
+__global__ void cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix,
+                                         const float* __restrict__ w, const float* __restrict__ b,
+                                         const float* __restrict__ fold0, const float* __restrict__ acc0,
+                                         float* __restrict__ g_w, float* __restrict__ g_b,
+                                         float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+    const int c = threadIdx.x;
+    const double n = (double)n_pix;
+    const double mean = fold0[kFold0Mean + c], invstd = fold0[kFold0Invstd + c], a = fold0[kFold0A + c];
+    const double S1 = acc0[c];
+    double G[9], wG = 0.0;
+    for (int k = 0; k < 9; ++k) { G[k] = acc0[64 + c * 9 + k]; wG += (double)w[c * 9 + k] * G[k]; }
+    const double bm = (double)b[c] - mean;
+    const double S2 = invstd * (wG + bm * S1);          // sum d_y * xhat
+    g_gamma[c] = (float)S2;
+    g_beta[c] = (float)S1;
+    g_b[c] = 0.f;                                       // BN cancels the conv bias
+    for (int k = 0; k < 9; ++k) {
+        double sxx = 0.0;                               // sum_p xhat_c * x_k
+        for (int l = 0; l < 9; ++l)
+            sxx += (double)w[c * 9 + l] * mom[l <= k ? tri_index(l, k) : tri_index(k, l)];
+        sxx = invstd * (sxx + bm * mom[k]);
+        g_w[c * 9 + k] = (float)(a * (G[k] - (S1 / n) * mom[k] - (S2 / n) * sxx));
+    }
+}
+
+constexpr size_t kGluFwdSmem = (4096 + 64 + 832 + kTile * kPitch + 4 * 66) * sizeof(float);
+constexpr size_t kGluBwdSmem = (2 * 4096 + 64 + 832 + 128 + 3 * kTile * kPitch + 4 * 66) * sizeof(float);
+constexpr size_t kWgradSmem = 2 * kTile * kPitch * sizeof(float);
+size_t conv_smem_bytes(int F) { return (size_t)(9 * 4096 + (kTile / F + 2) * (F + 2) * kPitch) * sizeof(float); }
+
+}  // namespace
+
+int cnn_kernels_init() {
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluFwdSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluFwdSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluBwdSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluBwdSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(4)));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(4)));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmem));
+    return DCASE_OK;
+}
+
+int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, cudaStream_t s) {
+    DCASE_CUDA_CHECK(cudaMemsetAsync(mom, 0, 54 * sizeof(double), s));
+    const long long n_pix = (long long)B * T * 64;
+    long long blocks = (n_pix + 255) / 256;
+    if (blocks > num_sms * 4) blocks = num_sms * 4;
+    cnn0_moments_kernel<<<(int)blocks, 256, 0, s>>>(x, n_pix, T, mom);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
+                        const float* gamma, const float* beta, float* running, int training, float* fold0,
+                        cudaStream_t s) {
+    bn0_finalize_kernel<<<1, 64, 0, s>>>(mom, n_pix, conv_w, conv_b, gamma, beta, running, training, fold0);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+static int grid_for(long long n_tiles, int num_sms, int per_sm) {
+    long long g = (long long)num_sms * per_sm;
+    return (int)(n_tiles < g ? n_tiles : g);
+}
+
+int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
+                         DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
+    GluArgs a{};
+    a.src = x; a.n_pix = (long long)B * T * 64; a.T = T; a.F = 64; a.aff = fold0;
+    a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
+    const long long n_tiles = a.n_pix / kTile;
+    glu_pool_fwd_kernel<true><<<grid_for(n_tiles, num_sms, 4), kTile, kGluFwdSmem, s>>>(a);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
+                        const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
+    GluArgs a{};
+    a.src = ypre; a.n_pix = n_pix; a.F = F; a.aff = bn; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
+    const long long n_tiles = (n_pix + kTile - 1) / kTile;
+    glu_pool_fwd_kernel<false><<<grid_for(n_tiles, num_sms, 4), kTile, kGluFwdSmem, s>>>(a);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_conv_w_prep(const float* w, float* w_fwd, float* w_dgrad, cudaStream_t s) {
+    conv_w_prep_kernel<<<36, 256, 0, s>>>(w, w_fwd, w_dgrad);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_conv3x3(const float* in, int n_rows, int T_l, int F, const float* w_prep, const float* bias, float* out,
+                   double* stats, int num_sms, cudaStream_t s) {
+    const int TR = kTile / F;
+    const int n_tiles = (n_rows + TR - 1) / TR;
+    const int grid = grid_for(n_tiles, num_sms, 1);
+    if (stats) {
+        DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
+        conv3x3_kernel<true><<<grid, kTile, conv_smem_bytes(F), s>>>(in, n_rows, T_l, F, w_prep, bias, out, stats);
+    } else {
+        conv3x3_kernel<false><<<grid, kTile, conv_smem_bytes(F), s>>>(in, n_rows, T_l, F, w_prep, bias, out, nullptr);
+    }
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta, float* running,
+                       int training, float* bn, cudaStream_t s) {
+    bn_finalize_kernel<<<1, 64, 0, s>>>(stats, n_pix, gamma, beta, running, training, bn);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_glu_pool_bwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
+                         DropoutCfg drop, const float* d_out, float* acc0, float* g_glu_w, float* g_glu_b,
+                         int num_sms, cudaStream_t s) {
+    GluArgs a{};
+    a.src = x; a.n_pix = (long long)B * T * 64; a.T = T; a.F = 64; a.aff = fold0;
+    a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.stat_acc = acc0;
+    a.g_glu_w = g_glu_w; a.g_glu_b = g_glu_b;
+    const long long n_tiles = a.n_pix / kTile;
+    glu_pool_bwd_kernel<true><<<grid_for(n_tiles, num_sms, 1), kTile, kGluBwdSmem, s>>>(a);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* bn, const float* gamma,
+                        const float* beta, const float* glu_w, const float* glu_b, DropoutCfg drop,
+                        const float* d_out, float* d_y, float* s12, float* g_glu_w, float* g_glu_b, int num_sms,
+                        cudaStream_t s) {
+    GluArgs a{};
+    a.src = ypre; a.n_pix = n_pix; a.F = F; a.aff = bn; a.gamma = gamma; a.beta = beta;
+    a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.d_y = d_y; a.stat_acc = s12;
+    a.g_glu_w = g_glu_w; a.g_glu_b = g_glu_b;
+    const long long n_tiles = (n_pix + kTile - 1) / kTile;
+    glu_pool_bwd_kernel<false><<<grid_for(n_tiles, num_sms, 1), kTile, kGluBwdSmem, s>>>(a);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const float* bn, const float* gamma,
+                        const float* s12, float* g_gamma, float* g_beta, float* g_conv_b, int num_sms,
+                        cudaStream_t s) {
+    (void)gamma;
+    long long blocks = (n_pix * 16 + 255) / 256;
+    if (blocks > num_sms * 8) blocks = num_sms * 8;
+    bn_bwd_apply_kernel<<<(int)blocks, 256, 0, s>>>(d_y, ypre, n_pix, bn, s12, g_gamma, g_beta, g_conv_b);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_conv_wgrad(const float* d_pre, const float* in, int n_rows, int T_l, int F, float* g_w, int num_sms,
+                      cudaStream_t s) {
+    const int TR = kTile / F;
+    const int n_tiles = (n_rows + TR - 1) / TR;
+    int chunks = (num_sms * 2 + 8) / 9;
+    if (chunks > n_tiles) chunks = n_tiles;
+    if (chunks < 1) chunks = 1;
+    conv_wgrad_kernel<<<dim3(chunks, 9), kTile, kWgradSmem, s>>>(d_pre, in, n_rows, T_l, F, g_w);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
+                             const float* gamma, const float* fold0, const float* acc0, float* g_conv_w,
+                             float* g_conv_b, float* g_gamma, float* g_beta, cudaStream_t s) {
+    (void)gamma;
+    cnn0_bwd_finalize_kernel<<<1, 64, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, acc0, g_conv_w, g_conv_b, g_gamma,
+                                            g_beta);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}

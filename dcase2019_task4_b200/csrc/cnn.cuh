@@ -1,0 +1,60 @@
+// CNN stack kernels (host launchers) -- see cnn.cu for the reference citations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+// Folded layer-0 parameters produced by bn0_finalize (floats):
+//   wf[9][64] (tap-major), bf[64], mean[64], invstd[64], a[64]
+constexpr int kFold0Wf = 0;
+constexpr int kFold0Bf = 576;
+constexpr int kFold0Mean = 640;
+constexpr int kFold0Invstd = 704;
+constexpr int kFold0A = 768;
+constexpr int kFold0Size = 832;
+
+// BN affine of layers 1,2 produced by bn_finalize (floats): scale[64], shift[64], mean[64], invstd[64]
+constexpr int kBnScale = 0;
+constexpr int kBnShift = 64;
+constexpr int kBnMean = 128;
+constexpr int kBnInvstd = 192;
+constexpr int kBnSize = 256;
+
+struct DropoutCfg {
+    int enabled;            // 0: identity; 1: p = 0.5 (keep-bit from Philox, scale 2)
+    uint64_t seed;
+    uint32_t step;
+    uint32_t stream;        // model_id * 8 + layer
+    const DcaseStepScalars* sc;  // if non-null overrides seed/step (CUDA-graph replay)
+};
+
+int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, cudaStream_t s);
+int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
+                        const float* gamma, const float* beta, float* running /*[2][64]*/, int training,
+                        float* fold0, cudaStream_t s);
+int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
+                         DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
+int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
+                        const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
+int launch_conv_w_prep(const float* w /*[64][64][3][3]*/, float* w_fwd /*[9][64c][64n]*/,
+                       float* w_dgrad /*[9][64n][64c]*/, cudaStream_t s);
+int launch_conv3x3(const float* in, int n_rows, int T_l, int F, const float* w_prep, const float* bias,
+                   float* out, double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
+int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta,
+                       float* running, int training, float* bn, cudaStream_t s);
+int launch_glu_pool_bwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
+                         DropoutCfg drop, const float* d_out, float* acc0 /*see cnn.cu*/, float* g_glu_w,
+                         float* g_glu_b, int num_sms, cudaStream_t s);
+int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* bn, const float* gamma,
+                        const float* beta, const float* glu_w, const float* glu_b, DropoutCfg drop,
+                        const float* d_out, float* d_y, float* s12 /*[2][64]*/, float* g_glu_w, float* g_glu_b,
+                        int num_sms, cudaStream_t s);
+int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const float* bn, const float* gamma,
+                        const float* s12, float* g_gamma, float* g_beta, float* g_conv_b, int num_sms,
+                        cudaStream_t s);
+int launch_conv_wgrad(const float* d_pre, const float* in, int n_rows, int T_l, int F, float* g_w, int num_sms,
+                      cudaStream_t s);
+int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
+                             const float* gamma, const float* fold0, const float* acc0, float* g_conv_w,
+                             float* g_conv_b, float* g_gamma, float* g_beta, cudaStream_t s);
+int cnn_kernels_init();

@@ -1,0 +1,19 @@
+// Internal definition of the opaque dcase_ctx handle.
+#pragma once
+#include <cuda_runtime.h>
+#include "fft2048.cuh"
+
+struct dcase_ctx {
+    int device;
+    int num_sms;
+    // log-mel constant tables (device)
+    float* d_window;     // [2048] symmetric Hamming
+    cf32* d_twiddle;     // [2048] exp(-2 pi i m / 2048)
+    float* d_mel_w;      // packed non-zero Slaney weights
+    int* d_mel_start;    // [64] first non-zero bin
+    int* d_mel_len;      // [64] band length
+    int* d_mel_off;      // [64] offset into d_mel_w
+    int mel_nnz;
+    // host copy of the dense filterbank for dcase_mel_filterbank()
+    float* h_mel_dense;  // [64 * 1025]
+};

@@ -1,0 +1,36 @@
+// BiGRU + small GEMM helpers (host launchers) -- see gru.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+struct GruFwdArgs {
+    const float* gi;         // [2][B*T][3H] input projections incl. b_ih
+    const float* w_hh[2];    // [3H][H]
+    const float* b_hh[2];    // [3H]
+    float* out;              // [B*T][2H]
+    float* save_r;           // [2][B*T][H] each, nullable (no backward)
+    float* save_z;
+    float* save_n;
+    float* save_hn;          // W_hn h + b_hn
+    float* save_hp;          // h_{prev}
+    int B, T;
+};
+
+struct GruBwdArgs {
+    const float* d_out;      // [B*T][2H]
+    const float* w_hh[2];
+    const float* save_r;
+    const float* save_z;
+    const float* save_n;
+    const float* save_hn;
+    const float* save_hp;
+    float* dgi;              // [2][B*T][3H]
+    float* dgh;              // [2][B*T][3H]
+    int B, T;
+};
+
+int launch_sgemm(int M, int N, int K, const float* A, long long sam, long long sak, const float* B, long long sbk,
+                 long long sbn, float* C, int ldc, const float* bias, int beta, int split_k, cudaStream_t s);
+int launch_colsum(const float* A, int M, int N, float* out, cudaStream_t s);
+int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t s);
+int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s);

@@ -1,0 +1,352 @@
+// Head (dropout -> sigmoid dense + class-softmax attention pooling), mean-teacher losses, Adam + EMA.
+//
+// Replaces (reference file:line):
+//   baseline/models/CRNN.py:74-81                         head forward (+ autograd backward)
+//   baseline/main.py:95-145                               weak / strong BCE, 2x MSE consistency, teacher meters
+//   baseline/main.py:152-157, :45-49 + torch.optim.Adam   optimizer step and teacher EMA
+#include "head_loss.cuh"
+
+namespace {
+
+constexpr int kD = 128;        // 2 * hidden
+constexpr int kMaxC = 16;      // class slots
+
+__device__ __forceinline__ void head_row_forward(const float* __restrict__ x, const uint4 keep, int drop,
+                                                 const float* __restrict__ Wd, const float* __restrict__ Ws,
+                                                 const float* __restrict__ bd, const float* __restrict__ bs, int NC,
+                                                 float (&ld)[kMaxC], float (&ls)[kMaxC], float* xm_row) {
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) { ld[c] = bd[c]; ls[c] = bs[c]; }
+    const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
+#pragma unroll 4
+    for (int k4 = 0; k4 < kD / 4; ++k4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(x) + k4);
+        if (drop) {
+            const uint32_t bits = kw[k4 >> 3] >> ((4 * k4) & 31);
+            v.x = (bits & 1u) ? 2.f * v.x : 0.f;
+            v.y = (bits & 2u) ? 2.f * v.y : 0.f;
+            v.z = (bits & 4u) ? 2.f * v.z : 0.f;
+            v.w = (bits & 8u) ? 2.f * v.w : 0.f;
+        }
+        if (xm_row) *reinterpret_cast<float4*>(xm_row + 4 * k4) = v;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+            if (c < NC) {
+                const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
+                const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
+                ld[c] = fmaf(v.x, wd.x, fmaf(v.y, wd.y, fmaf(v.z, wd.z, fmaf(v.w, wd.w, ld[c]))));
+                ls[c] = fmaf(v.x, ws.x, fmaf(v.y, ws.y, fmaf(v.z, ws.z, fmaf(v.w, ws.w, ls[c]))));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void softmax_classes(const float (&ls)[kMaxC], int NC, float (&a_raw)[kMaxC]) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) if (c < NC) mx = fmaxf(mx, ls[c]);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) { a_raw[c] = c < NC ? __expf(ls[c] - mx) : 0.f; sum += a_raw[c]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) a_raw[c] *= inv;
+}
+
+__device__ __forceinline__ void load_head_weights(const HeadArgs& a, float* Wd, float* Ws, float* bd, float* bs) {
+    for (int i = threadIdx.x; i < kMaxC * kD; i += blockDim.x) {
+        const bool ok = i < a.NC * kD;
+        Wd[i] = ok ? __ldg(a.w_dense + i) : 0.f;
+        Ws[i] = ok ? __ldg(a.w_soft + i) : 0.f;
+    }
+    if (threadIdx.x < kMaxC) {
+        bd[threadIdx.x] = threadIdx.x < a.NC ? __ldg(a.b_dense + threadIdx.x) : 0.f;
+        bs[threadIdx.x] = threadIdx.x < a.NC ? __ldg(a.b_soft + threadIdx.x) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+head_fwd_kernel(HeadArgs a) {
+    __shared__ __align__(16) float Wd[kMaxC * kD];
+    __shared__ __align__(16) float Ws[kMaxC * kD];
+    __shared__ float bd[kMaxC], bs[kMaxC];
+    __shared__ float red[4][2 * kMaxC];
+    const int tid = threadIdx.x, b = blockIdx.x;
+    load_head_weights(a, Wd, Ws, bd, bs);
+    uint64_t seed = a.seed; uint32_t step = a.step;
+    if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
+    __syncthreads();
+    float num[kMaxC], den[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) { num[c] = 0.f; den[c] = 0.f; }
+    for (int t = tid; t < a.To; t += 128) {
+        const long long row = (long long)b * a.To + t;
+        uint4 keep = make_uint4(0, 0, 0, 0);
+        if (a.drop) keep = philox4x32_10((uint64_t)row, a.stream, step, seed);
+        float ld[kMaxC], ls[kMaxC], ar[kMaxC];
+        head_row_forward(a.x + row * kD, keep, a.drop, Wd, Ws, bd, bs, a.NC, ld, ls, nullptr);
+        softmax_classes(ls, a.NC, ar);
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+            if (c < a.NC) {
+                const float s = sigmoid_fast(ld[c]);
+                const float at = fminf(fmaxf(ar[c], 1e-7f), 1.f);
+                a.strong[row * a.NC + c] = s;
+                num[c] = fmaf(s, at, num[c]);
+                den[c] += at;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+        const float n = warp_sum(num[c]), d = warp_sum(den[c]);
+        if ((tid & 31) == 0) { red[tid >> 5][c] = n; red[tid >> 5][kMaxC + c] = d; }
+    }
+    __syncthreads();
+    if (tid < a.NC) {
+        const float n = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+        const float d = red[0][kMaxC + tid] + red[1][kMaxC + tid] + red[2][kMaxC + tid] + red[3][kMaxC + tid];
+        a.weak[b * a.NC + tid] = n / d;
+        if (a.den) a.den[b * a.NC + tid] = d;
+    }
+}
+
+// Backward of the head for one clip per CTA; forward recomputed from x.  dynamic smem:
+//   Wd,Ws [16][128] | bd,bs [16] | xm [128][132] | dl [128][33]
+__global__ void __launch_bounds__(128)
+head_bwd_kernel(HeadArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wd = smem;
+    float* Ws = Wd + kMaxC * kD;
+    float* bd = Ws + kMaxC * kD;
+    float* bs = bd + kMaxC;
+    float* xm = bs + kMaxC;            // [128][132]
+    float* dl = xm + 128 * 132;        // [128][33]  (0..15 dense logits grad, 16..31 softmax logits grad)
+    const int tid = threadIdx.x, b = blockIdx.x;
+    load_head_weights(a, Wd, Ws, bd, bs);
+    uint64_t seed = a.seed; uint32_t step = a.step;
+    if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
+    __syncthreads();
+    float gw[2 * kMaxC];
+#pragma unroll
+    for (int c = 0; c < 2 * kMaxC; ++c) gw[c] = 0.f;
+    float gb = 0.f;
+    for (int t0 = 0; t0 < a.To; t0 += 128) {
+        const int t = t0 + tid;
+        const bool valid = t < a.To;
+        float* xm_row = xm + tid * 132;
+        float* dl_row = dl + tid * 33;
+        if (valid) {
+            const long long row = (long long)b * a.To + t;
+            uint4 keep = make_uint4(0, 0, 0, 0);
+            if (a.drop) keep = philox4x32_10((uint64_t)row, a.stream, step, seed);
+            float ld[kMaxC], ls[kMaxC], ar[kMaxC];
+            head_row_forward(a.x + row * kD, keep, a.drop, Wd, Ws, bd, bs, a.NC, ld, ls, xm_row);
+            softmax_classes(ls, a.NC, ar);
+            float da[kMaxC];
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < kMaxC; ++c) {
+                da[c] = 0.f;
+                float dld = 0.f;
+                if (c < a.NC) {
+                    const float s = sigmoid_fast(ld[c]);
+                    const float at = fminf(fmaxf(ar[c], 1e-7f), 1.f);
+                    const float dwk = __ldg(a.d_weak + b * a.NC + c);
+                    const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
+                    const float wk = __ldg(a.weak + b * a.NC + c);
+                    const float ds = __ldg(a.d_strong + row * a.NC + c) + dwk * at * inv_den;
+                    dld = ds * s * (1.f - s);
+                    const bool pass = ar[c] >= 1e-7f && ar[c] <= 1.f;   // clamp passes gradient inside [min, max]
+                    da[c] = pass ? dwk * (s - wk) * inv_den : 0.f;
+                    dot = fmaf(da[c], ar[c], dot);
+                }
+                dl_row[c] = dld;
+            }
+#pragma unroll
+            for (int c = 0; c < kMaxC; ++c) dl_row[kMaxC + c] = c < a.NC ? ar[c] * (da[c] - dot) : 0.f;
+            // d x = mask * 2 * (Wd^T dl_d + Ws^T dl_s)
+            const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
+            float4* dx = reinterpret_cast<float4*>(a.d_x + row * kD);
+#pragma unroll 4
+            for (int k4 = 0; k4 < kD / 4; ++k4) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) {
+                    if (c < a.NC) {
+                        const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
+                        const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
+                        const float gd = dl_row[c], gs = dl_row[kMaxC + c];
+                        acc.x = fmaf(gd, wd.x, fmaf(gs, ws.x, acc.x));
+                        acc.y = fmaf(gd, wd.y, fmaf(gs, ws.y, acc.y));
+                        acc.z = fmaf(gd, wd.z, fmaf(gs, ws.z, acc.z));
+                        acc.w = fmaf(gd, wd.w, fmaf(gs, ws.w, acc.w));
+                    }
+                }
+                if (a.drop) {
+                    const uint32_t bits = kw[k4 >> 3] >> ((4 * k4) & 31);
+                    acc.x = (bits & 1u) ? 2.f * acc.x : 0.f;
+                    acc.y = (bits & 2u) ? 2.f * acc.y : 0.f;
+                    acc.z = (bits & 4u) ? 2.f * acc.z : 0.f;
+                    acc.w = (bits & 8u) ? 2.f * acc.w : 0.f;
+                }
+                dx[k4] = acc;
+            }
+        } else {
+            for (int k = 0; k < kD; ++k) xm_row[k] = 0.f;
+            for (int c = 0; c < 2 * kMaxC; ++c) dl_row[c] = 0.f;
+        }
+        __syncthreads();
+        // thread k owns column k of both weight gradients; threads 0..31 also own one bias slot
+        for (int q = 0; q < 128; ++q) {
+            const float xv = xm[q * 132 + tid];
+#pragma unroll
+            for (int c = 0; c < 2 * kMaxC; ++c) gw[c] = fmaf(dl[q * 33 + c], xv, gw[c]);
+            if (tid < 2 * kMaxC) gb += dl[q * 33 + tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+        if (c < a.NC) {
+            atomicAdd(a.g_w_dense + c * kD + tid, gw[c]);
+            atomicAdd(a.g_w_soft + c * kD + tid, gw[kMaxC + c]);
+        }
+    }
+    if (tid < kMaxC) { if (tid < a.NC) atomicAdd(a.g_b_dense + tid, gb); }
+    else if (tid < 2 * kMaxC) { if (tid - kMaxC < a.NC) atomicAdd(a.g_b_soft + tid - kMaxC, gb); }
+}
+
+__device__ __forceinline__ float bce_term(float p, float y) {
+    return -(y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(log1pf(-p), -100.f));
+}
+__device__ __forceinline__ float bce_grad(float p, float y) { return (p - y) / fmaxf((1.f - p) * p, 1e-12f); }
+
+__global__ void __launch_bounds__(1024)
+mt_loss_kernel(LossArgs a) {
+    __shared__ float red[32][6];
+    const int tid = threadIdx.x;
+    const float cw = a.sc ? a.sc->cons_weight : a.cons_weight;
+    const bool has_t = a.strong_t != nullptr;
+    const int per_clip = a.To * a.NC;
+    const long long n_all_s = (long long)a.B * per_clip;
+    const int n_all_w = a.B * a.NC;
+    const float inv_ns = a.strong_hi > a.strong_lo ? 1.f / ((float)(a.strong_hi - a.strong_lo) * per_clip) : 0.f;
+    const float inv_nw = a.weak_hi > a.weak_lo ? 1.f / ((float)(a.weak_hi - a.weak_lo) * a.NC) : 0.f;
+    const float cs_scale = has_t ? cw * 2.f / (float)n_all_s : 0.f;
+    const float cwk_scale = has_t ? cw * 2.f / (float)n_all_w : 0.f;
+    float s_bce = 0.f, s_bce_t = 0.f, s_cons = 0.f, w_bce = 0.f, w_bce_t = 0.f, w_cons = 0.f;
+    for (long long e = tid; e < n_all_s; e += 1024) {
+        const int b = (int)(e / per_clip);
+        const float p = a.strong_s[e];
+        float d = 0.f;
+        if (b >= a.strong_lo && b < a.strong_hi) {
+            const float y = a.target[e];
+            s_bce += bce_term(p, y);
+            if (has_t) s_bce_t += bce_term(a.strong_t[e], y);
+            d = bce_grad(p, y) * inv_ns;
+        }
+        if (has_t) {
+            const float diff = p - a.strong_t[e];
+            s_cons = fmaf(diff, diff, s_cons);
+            d = fmaf(cs_scale, diff, d);
+        }
+        a.d_strong[e] = d;
+    }
+    for (int e = tid; e < n_all_w; e += 1024) {
+        const int b = e / a.NC, c = e - b * a.NC;
+        const float p = a.weak_s[e];
+        float d = 0.f;
+        if (b >= a.weak_lo && b < a.weak_hi) {
+            float y = -INFINITY;   // target.max(-2), main.py:95
+            for (int t = 0; t < a.To; ++t) y = fmaxf(y, a.target[((long long)b * a.To + t) * a.NC + c]);
+            w_bce += bce_term(p, y);
+            if (has_t) w_bce_t += bce_term(a.weak_t[e], y);
+            d = bce_grad(p, y) * inv_nw;
+        }
+        if (has_t) {
+            const float diff = p - a.weak_t[e];
+            w_cons = fmaf(diff, diff, w_cons);
+            d = fmaf(cwk_scale, diff, d);
+        }
+        a.d_weak[e] = d;
+    }
+    float v[6] = {w_bce, w_bce_t, s_bce, s_bce_t, s_cons, w_cons};
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        v[i] = warp_sum(v[i]);
+        if ((tid & 31) == 0) red[tid >> 5][i] = v[i];
+    }
+    __syncthreads();
+    if (tid < 32) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = warp_sum(red[tid][i]);
+        if (tid == 0) {
+            const float weak_loss = v[0] * inv_nw, weak_ema = v[1] * inv_nw;
+            const float strong_loss = v[2] * inv_ns, strong_ema = v[3] * inv_ns;
+            const float cons_s = has_t ? cw * v[4] / (float)n_all_s : 0.f;
+            const float cons_w = has_t ? cw * v[5] / (float)n_all_w : 0.f;
+            a.meters[0] = weak_loss; a.meters[1] = weak_ema; a.meters[2] = strong_loss; a.meters[3] = strong_ema;
+            a.meters[4] = cons_s; a.meters[5] = cons_w;
+            a.meters[6] = weak_loss + strong_loss + cons_s + cons_w;
+            a.meters[7] = cw;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                float* __restrict__ p_ema, long long n, float lr, float beta1, float beta2, float eps, float bc1,
+                float bc2, float alpha, float grad_scale, const DcaseStepScalars* __restrict__ sc) {
+    if (sc) { lr = sc->lr; bc1 = sc->bias_corr1; bc2 = sc->bias_corr2; alpha = sc->ema_alpha; grad_scale = sc->grad_scale; }
+    const float step_size = lr / bc1;
+    const float inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float gi = g[i] * grad_scale;
+        const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+        const float pi = p[i] - step_size * (mi / denom);
+        p[i] = pi;
+        if (p_ema) p_ema[i] = alpha * p_ema[i] + (1.f - alpha) * pi;
+    }
+}
+
+constexpr size_t kHeadBwdSmem = (2 * kMaxC * kD + 2 * kMaxC + 128 * 132 + 128 * 33) * sizeof(float);
+
+}  // namespace
+
+int head_kernels_init() {
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadBwdSmem));
+    return DCASE_OK;
+}
+
+int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
+    head_fwd_kernel<<<a.B, 128, 0, s>>>(a);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
+    head_bwd_kernel<<<a.B, 128, kHeadBwdSmem, s>>>(a);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_mt_loss(const LossArgs& a, cudaStream_t s) {
+    mt_loss_kernel<<<1, 1024, 0, s>>>(a);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_adam_ema(float* p, const float* g, float* m, float* v, float* p_ema, long long n, float lr, float beta1,
+                    float beta2, float eps, float bc1, float bc2, float alpha, float grad_scale,
+                    const DcaseStepScalars* sc, int num_sms, cudaStream_t s) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > num_sms * 8) blocks = num_sms * 8;
+    adam_ema_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, p_ema, n, lr, beta1, beta2, eps, bc1, bc2, alpha,
+                                               grad_scale, sc);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}

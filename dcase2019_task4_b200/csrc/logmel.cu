@@ -1,0 +1,349 @@
+// K1/K2: waveform -> Hamming STFT magnitude -> Slaney mel (amplitude) -> noise / dB / top_db / z-score.
+//
+// Replaces (reference file:line):
+//   baseline/DatasetDcase2019Task4.py:197-231   calculate_mel_spec            -> dcase_logmel_fwd
+//   baseline/DataLoad.py:274-287,192-207,210-259,302-321 + utils/Scaler.py:99-105
+//   (order: utils/utils.py:397-412 get_transforms)                            -> dcase_logmel_finish
+//
+// K1 layout: one CTA = 16 consecutive frames of one clip. The contiguous waveform span
+// (15*511 + 2048 samples, reflect-padded at the clip ends) is staged once in shared memory, so the
+// 4x frame overlap (2048/511) is served on-chip and HBM sees each sample ~1.2x. Two real frames are
+// packed into one complex 2048-point Stockham FFT (radix 8,8,8,4) held in shared memory.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/dcase_b200.h"
+#include "common.cuh"
+#include "ctx.h"
+#include "fft2048.cuh"
+
+namespace {
+
+constexpr int kNfft = 2048;
+constexpr int kHop = 511;
+constexpr int kBins = 1025;
+constexpr int kMel = 64;
+constexpr int kFramesPerCta = 16;
+constexpr int kSpan = (kFramesPerCta - 1) * kHop + kNfft;  // 9713
+constexpr int kMagPitch = 1032;
+
+struct MelTables {
+    const float* window;
+    const cf32* twiddle;
+    const float* mel_w;
+    const int* mel_start;
+    const int* mel_len;
+    const int* mel_off;
+};
+
+__device__ __forceinline__ int reflect_index(int s, int L) {
+    if (s < 0) s = -s;
+    if (s >= L) s = 2 * (L - 1) - s;
+    return s;
+}
+
+template <typename WaveT>
+__device__ __forceinline__ float load_sample(const WaveT* p, int i);
+template <>
+__device__ __forceinline__ float load_sample<float>(const float* p, int i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ float load_sample<int16_t>(const int16_t* p, int i) {
+    return (float)__ldg(p + i) * (1.0f / 32768.0f);  // soundfile's int16 -> float scaling
+}
+
+template <typename WaveT>
+__global__ void __launch_bounds__(256, 2)
+stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, float* __restrict__ mel_amp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* span = reinterpret_cast<float*>(smem_raw);                 // [kSpan] (+pad)
+    cf32* bufA = reinterpret_cast<cf32*>(span + 9728);                // [2048]
+    cf32* bufB = bufA + kNfft;                                        // [2048]
+    cf32* tw = bufB + kNfft;                                          // [2048]
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * kFramesPerCta;
+    const WaveT* clip = wave + (size_t)b * L;
+
+    const int s0 = t0 * kHop - kNfft / 2;
+    for (int i = tid; i < kSpan; i += 256) {
+        int s = reflect_index(s0 + i, L);
+        span[i] = (s >= 0 && s < L) ? load_sample<WaveT>(clip, s) : 0.f;
+    }
+    for (int i = tid; i < kNfft; i += 256) tw[i] = tab.twiddle[i];
+    __syncthreads();
+
+    const int n_pairs = min(kFramesPerCta, T - t0 + 1) / 2;  // frames [t0, T) in pairs (odd tail rounds up)
+    for (int p = 0; p < n_pairs; ++p) {
+        // pass 1 (Ns = 1): windowed load straight from the span, two real frames -> one complex signal
+        {
+            const float* fa = span + (2 * p) * kHop;
+            const float* fb = fa + kHop;
+            cf32 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int n = tid + r * 256;
+                const float w = __ldg(tab.window + n);
+                v[r] = cf32{fa[n] * w, fb[n] * w};
+            }
+            fft8(v);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) bufA[tid * 8 + r] = v[r];
+        }
+        __syncthreads();
+        stockham_pass<8>(tid, 8, bufA, bufB, tw);
+        __syncthreads();
+        stockham_pass<8>(tid, 64, bufB, bufA, tw);
+        __syncthreads();
+        stockham_pass<4>(tid, 512, bufA, bufB, tw);
+        stockham_pass<4>(tid + 256, 512, bufA, bufB, tw);
+        __syncthreads();
+        // separate the two real spectra and take magnitudes (bins 0..1024)
+        float* mag = reinterpret_cast<float*>(bufA);  // [2][kMagPitch]
+        for (int k = tid; k < kBins; k += 256) {
+            const cf32 zk = bufB[k];
+            const cf32 zn = bufB[(kNfft - k) & (kNfft - 1)];
+            const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+            const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
+            mag[k] = sqrtf(ar * ar + ai * ai);
+            mag[kMagPitch + k] = sqrtf(br * br + bi * bi);
+        }
+        __syncthreads();
+        // sparse Slaney mel projection: 2 frames x 64 mels x 2 lanes
+        {
+            const int fr = tid >> 7;
+            const int m = (tid & 127) >> 1;
+            const int hf = tid & 1;
+            const int start = __ldg(tab.mel_start + m), len = __ldg(tab.mel_len + m);
+            const float* w = tab.mel_w + __ldg(tab.mel_off + m);
+            const float* mg = mag + fr * kMagPitch + start;
+            float acc = 0.f;
+            for (int i = hf; i < len; i += 2) acc = fmaf(__ldg(w + i), mg[i], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            const int t = t0 + 2 * p + fr;
+            if (hf == 0 && t < T) mel_amp[((size_t)b * T + t) * kMel + m] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K2a: per-clip max of the clean and of the noisy amplitude mel ------------------------------
+__device__ __forceinline__ float4 noise_quad(uint64_t quad_index, uint32_t step, uint64_t seed) {
+    const uint4 r = philox4x32_10(quad_index, DCASE_STREAM_NOISE, step, seed);
+    const float k = 2.3283064365386963e-10f;  // 2^-32
+    const float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
+    const float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
+    // (float)r + 0.5f can round to 2^32 -> u = 1 -> log 0 = radius 0: harmless.
+    const float ra = sqrtf(-2.f * logf(fminf(u0, 0.99999994f))), rb = sqrtf(-2.f * logf(fminf(u2, 0.99999994f)));
+    float sa, ca, sb, cb;
+    sincospif(2.f * u1, &sa, &ca);
+    sincospif(2.f * u3, &sb, &cb);
+    return make_float4(0.25f * fabsf(ra * ca), 0.25f * fabsf(ra * sa), 0.25f * fabsf(rb * cb),
+                       0.25f * fabsf(rb * sb));
+}
+
+__global__ void __launch_bounds__(256)
+clip_max_kernel(const float* __restrict__ mel_amp, int T_in, const float* __restrict__ noise, int want_noisy,
+                uint64_t seed, uint32_t step, const DcaseStepScalars* __restrict__ sc,
+                float* __restrict__ clip_max, int B) {
+    __shared__ float red[2][8];
+    if (sc) { seed = sc->seed; step = sc->step; }
+    const int b = blockIdx.x;
+    const int n_quads = T_in * (kMel / 4);
+    const float4* src = reinterpret_cast<const float4*>(mel_amp + (size_t)b * T_in * kMel);
+    const float4* nz = noise ? reinterpret_cast<const float4*>(noise + (size_t)b * T_in * kMel) : nullptr;
+    float mc = 0.f, mn = 0.f;
+    for (int q = threadIdx.x; q < n_quads; q += 256) {
+        const float4 x = __ldg(src + q);
+        mc = fmaxf(mc, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+        if (want_noisy) {
+            const float4 e = nz ? __ldg(nz + q) : noise_quad((uint64_t)b * n_quads + q, step, seed);
+            mn = fmaxf(mn, fmaxf(fmaxf(x.x + e.x, x.y + e.y), fmaxf(x.z + e.z, x.w + e.w)));
+        }
+    }
+    mc = warp_max(mc);
+    mn = warp_max(mn);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = mc; red[1][threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        mc = threadIdx.x < 8 ? red[0][threadIdx.x] : 0.f;
+        mn = threadIdx.x < 8 ? red[1][threadIdx.x] : 0.f;
+        mc = warp_max(mc);
+        mn = warp_max(mn);
+        if (threadIdx.x == 0) { clip_max[b] = mc; clip_max[B + b] = mn; }
+    }
+}
+
+__device__ __forceinline__ float amp_to_db(float x) { return 20.f * log10f(fmaxf(x, 1e-5f)); }
+
+// ---- K2b: dB, top_db floor, pad/trunc, z-score -> clean (+ noisy) ---------------------------------
+__global__ void __launch_bounds__(256)
+finish_kernel(const float* __restrict__ mel_amp, int B, int T_in, int T_out, const float* __restrict__ mean,
+              const float* __restrict__ stdv, const float* __restrict__ noise, uint64_t seed, uint32_t step,
+              const DcaseStepScalars* __restrict__ sc, const float* __restrict__ clip_max,
+              float* __restrict__ clean, float* __restrict__ noisy) {
+    if (sc) { seed = sc->seed; step = sc->step; }
+    const size_t total = (size_t)B * T_out * (kMel / 4);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i & 15);
+        const size_t row = i >> 4;
+        const int t = (int)(row % T_out);
+        const int b = (int)(row / T_out);
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + q);
+        const float4 sd = __ldg(reinterpret_cast<const float4*>(stdv) + q);
+        float4 lc = make_float4(0.f, 0.f, 0.f, 0.f), ln = lc;  // pad rows are 0.0 dB (DataLoad.py:222-226)
+        if (t < T_in) {
+            const size_t src_q = ((size_t)b * T_in + t) * 16 + q;
+            const float4 x = __ldg(reinterpret_cast<const float4*>(mel_amp) + src_q);
+            const float floor_c = amp_to_db(clip_max[b]) - 80.f;
+            lc.x = fmaxf(amp_to_db(x.x), floor_c);
+            lc.y = fmaxf(amp_to_db(x.y), floor_c);
+            lc.z = fmaxf(amp_to_db(x.z), floor_c);
+            lc.w = fmaxf(amp_to_db(x.w), floor_c);
+            if (noisy) {
+                const float4 e = noise ? __ldg(reinterpret_cast<const float4*>(noise) + src_q)
+                                       : noise_quad(src_q, step, seed);
+                const float floor_n = amp_to_db(clip_max[B + b]) - 80.f;
+                ln.x = fmaxf(amp_to_db(x.x + e.x), floor_n);
+                ln.y = fmaxf(amp_to_db(x.y + e.y), floor_n);
+                ln.z = fmaxf(amp_to_db(x.z + e.z), floor_n);
+                ln.w = fmaxf(amp_to_db(x.w + e.w), floor_n);
+            }
+        }
+        float4 o;
+        o.x = (lc.x - mu.x) / sd.x; o.y = (lc.y - mu.y) / sd.y; o.z = (lc.z - mu.z) / sd.z; o.w = (lc.w - mu.w) / sd.w;
+        reinterpret_cast<float4*>(clean)[i] = o;
+        if (noisy) {
+            o.x = (ln.x - mu.x) / sd.x; o.y = (ln.y - mu.y) / sd.y; o.z = (ln.z - mu.z) / sd.z; o.w = (ln.w - mu.w) / sd.w;
+            reinterpret_cast<float4*>(noisy)[i] = o;
+        }
+    }
+}
+
+// ---- host-side constant tables -----------------------------------------------------------------
+double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+constexpr size_t kStftSmemBytes = 9728 * sizeof(float) + 3 * kNfft * sizeof(cf32);
+
+}  // namespace
+
+int dcase_logmel_tables_create(dcase_ctx* ctx) {
+    const double sr = 44100.0, f_lo = 0.0, f_hi = 22050.0;
+    std::vector<float> win(kNfft);
+    for (int n = 0; n < kNfft; ++n) win[n] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * n / (kNfft - 1)));
+    std::vector<cf32> tw(kNfft);
+    for (int m = 0; m < kNfft; ++m) {
+        const double a = -2.0 * M_PI * m / kNfft;
+        tw[m] = cf32{(float)cos(a), (float)sin(a)};
+    }
+    // Slaney filterbank, librosa.filters.mel(sr, n_fft, n_mels=64, fmin, fmax, htk=False, norm=None)
+    std::vector<double> mel_f(kMel + 2);
+    const double m_lo = hz_to_mel(f_lo), m_hi = hz_to_mel(f_hi);
+    for (int i = 0; i < kMel + 2; ++i) mel_f[i] = mel_to_hz(m_lo + (m_hi - m_lo) * i / (kMel + 1));
+    ctx->h_mel_dense = (float*)calloc((size_t)kMel * kBins, sizeof(float));
+    std::vector<float> packed;
+    std::vector<int> start(kMel), len(kMel), off(kMel);
+    for (int i = 0; i < kMel; ++i) {
+        int first = -1, last = -1;
+        for (int k = 0; k < kBins; ++k) {
+            const double f = (sr / 2) * k / (kBins - 1);
+            const double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
+            const double upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
+            const double w = lower < upper ? (lower > 0.0 ? lower : 0.0) : (upper > 0.0 ? upper : 0.0);
+            ctx->h_mel_dense[(size_t)i * kBins + k] = (float)w;
+            if ((float)w != 0.f) { if (first < 0) first = k; last = k; }
+        }
+        start[i] = first < 0 ? 0 : first;
+        len[i] = first < 0 ? 0 : last - first + 1;
+        off[i] = (int)packed.size();
+        for (int k = 0; k < len[i]; ++k) packed.push_back(ctx->h_mel_dense[(size_t)i * kBins + start[i] + k]);
+    }
+    ctx->mel_nnz = (int)packed.size();
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_window, kNfft * sizeof(float)));
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_twiddle, kNfft * sizeof(cf32)));
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_w, packed.size() * sizeof(float)));
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_start, kMel * sizeof(int)));
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_len, kMel * sizeof(int)));
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_off, kMel * sizeof(int)));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_window, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_twiddle, tw.data(), kNfft * sizeof(cf32), cudaMemcpyHostToDevice));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_start, start.data(), kMel * sizeof(int), cudaMemcpyHostToDevice));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_len, len.data(), kMel * sizeof(int), cudaMemcpyHostToDevice));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_off, off.data(), kMel * sizeof(int), cudaMemcpyHostToDevice));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kStftSmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kStftSmemBytes));
+    return DCASE_OK;
+}
+
+void dcase_logmel_tables_destroy(dcase_ctx* ctx) {
+    cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_w);
+    cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len); cudaFree(ctx->d_mel_off);
+    free(ctx->h_mel_dense);
+}
+
+extern "C" {
+
+int dcase_logmel_num_frames(int n_samples) { return 1 + n_samples / kHop; }
+
+int dcase_mel_filterbank(dcase_ctx* ctx, float* out_host) {
+    DCASE_REQUIRE(ctx && out_host, "null argument");
+    memcpy(out_host, ctx->h_mel_dense, (size_t)kMel * kBins * sizeof(float));
+    return DCASE_OK;
+}
+
+static int logmel_fwd_impl(dcase_ctx* ctx, const void* wave, int is_pcm16, int B, int L, float* mel_amp,
+                           cudaStream_t stream) {
+    DCASE_REQUIRE(ctx && wave && mel_amp, "null argument");
+    DCASE_REQUIRE(B >= 0 && L > kNfft / 2, "need L > 1024 samples (single reflection)");
+    if (B == 0) return DCASE_OK;
+    const int T = 1 + L / kHop;
+    MelTables tab{ctx->d_window, ctx->d_twiddle, ctx->d_mel_w, ctx->d_mel_start, ctx->d_mel_len, ctx->d_mel_off};
+    dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
+    if (is_pcm16)
+        stft_mel_kernel<int16_t><<<grid, 256, kStftSmemBytes, stream>>>((const int16_t*)wave, L, T, tab, mel_amp);
+    else
+        stft_mel_kernel<float><<<grid, 256, kStftSmemBytes, stream>>>((const float*)wave, L, T, tab, mel_amp);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int dcase_logmel_fwd(dcase_ctx* ctx, const float* wave, int B, int L, float* mel_amp, void* stream) {
+    return logmel_fwd_impl(ctx, wave, 0, B, L, mel_amp, (cudaStream_t)stream);
+}
+
+int dcase_logmel_fwd_pcm16(dcase_ctx* ctx, const int16_t* wave, int B, int L, float* mel_amp, void* stream) {
+    return logmel_fwd_impl(ctx, wave, 1, B, L, mel_amp, (cudaStream_t)stream);
+}
+
+int dcase_logmel_finish(dcase_ctx* ctx, const float* mel_amp, int B, int T_in, int T_out, const float* mean,
+                        const float* stdv, const float* noise, uint64_t seed, uint32_t step, const void* scalars,
+                        float* clip_max_ws, float* clean, float* noisy, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCASE_REQUIRE(ctx && mel_amp && mean && stdv && clip_max_ws && clean, "null argument");
+    DCASE_REQUIRE(B >= 0 && T_in > 0 && T_out > 0, "bad shape");
+    if (B == 0) return DCASE_OK;
+    const DcaseStepScalars* sc = (const DcaseStepScalars*)scalars;
+    clip_max_kernel<<<B, 256, 0, stream>>>(mel_amp, T_in, noise, noisy != nullptr, seed, step, sc, clip_max_ws, B);
+    DCASE_LAUNCH_CHECK();
+    const size_t total = (size_t)B * T_out * 16;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
+    finish_kernel<<<blocks, 256, 0, stream>>>(mel_amp, B, T_in, T_out, mean, stdv, noise, seed, step, sc, clip_max_ws,
+                                             clean, noisy);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+}  // extern "C"

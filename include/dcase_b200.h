@@ -1,0 +1,165 @@
+/* dcase_b200 -- C ABI of the B200-native DCASE2019-task4 hot path.
+ *
+ * One shared library (libdcase_b200.so, sm_100a) behind the reference's Python surface.  The reference
+ * (turpaultn/DCASE2019_task4) is pure Python and has no FFI layer of its own; each entry point below names
+ * the reference interface (file:line under /root/reference) whose work it replaces.  INTEGRATION.md shows
+ * the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 or a negative DCASE_ERR_* code; dcase_last_error() gives the text
+ *     (thread-local);
+ *   - all tensor pointers are DEVICE pointers owned by the caller (torch tensors: tensor.data_ptr()),
+ *     including workspaces (sizes from the *_bytes / *_count helpers); the library never allocates
+ *     per call, never synchronises, and launches on the given stream (cudaStream_t passed as void*);
+ *   - activations are channels-last fp32; features are [B, T, 64] (the reference's [B,1,T,64] NCHW
+ *     with C = 1 is the same memory);
+ *   - parameters are ONE flat fp32 slab in the order of CRNN(**cfg.crnn_kwargs).named_parameters()
+ *     (SURVEY.md section 10): cnn.cnn.{conv,batchnorm,glu}{0,1,2}, rnn.rnn.*_l{0,1}[_reverse], dense,
+ *     dense_softmax.  Gradients use the same layout.  BN running stats are [3][2][64] =
+ *     {layer}{running_mean, running_var}{channel}.
+ *
+ * RNG contract (restated in numpy by oracle/philox.py)
+ *   Philox4x32-10, key = (seed_lo, seed_hi), counter = (row_lo, row_hi, stream, step).
+ *   Dropout(0.5) keep bit of element (row, col) = bit (col & 31) of output word (col >> 5), where row is
+ *   the channels-last pixel index ((b*T + t)*F + f) for CNN block i (stream = 8*model_id + i) and the
+ *   frame index (b*To + t) for the head (stream = 8*model_id + 3).  Teacher noise: counter row =
+ *   (b*T + t)*16 + q for mel bins 4q..4q+3, stream 4; u = (w + 0.5) * 2^-32; Box-Muller pairs (u0,u1),
+ *   (u2,u3); noise = 0.25 * |n|  (AugmentGaussianNoise, DataLoad.py:285: std = 0.5 ** 2).
+ */
+#ifndef DCASE_B200_H_
+#define DCASE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCASE_B200_VERSION 100
+
+#define DCASE_FLAG_BN_BATCH_STATS 1   /* module.train(): BatchNorm uses + updates batch statistics */
+#define DCASE_FLAG_DROPOUT 2          /* Dropout(0.5) active (CNN blocks and head) */
+
+typedef struct dcase_ctx dcase_ctx;
+
+int dcase_version(void);
+const char* dcase_last_error(void);
+int dcase_ctx_create(dcase_ctx** out, int device);
+int dcase_ctx_destroy(dcase_ctx* ctx);
+
+/* Per-step scalars in device memory (so a captured CUDA graph replays with new values).
+ * Layout must match DcaseStepScalars in csrc/common.cuh. */
+typedef struct dcase_step_scalars {
+    uint64_t seed;
+    uint32_t step;
+    float cons_weight;
+    float ema_alpha;
+    float lr;
+    float bias_corr1;
+    float bias_corr2;
+    float grad_scale;
+    float pad_;
+} dcase_step_scalars;
+
+/* ---- log-mel -------------------------------------------------------------------------------------- */
+
+/* librosa.stft(center=True) frame count: 1 + n_samples / 511.  DatasetDcase2019Task4.py:211-218 */
+int dcase_logmel_num_frames(int n_samples);
+
+/* The Slaney filterbank the kernel uses (librosa.filters.mel(44100, 2048, 64, 0, 22050, htk=False,
+ * norm=None)), dense float32 [64][1025] into HOST memory.  DatasetDcase2019Task4.py:220-225 */
+int dcase_mel_filterbank(dcase_ctx* ctx, float* out_host);
+
+/* DatasetDcase2019Task4.calculate_mel_spec (DatasetDcase2019Task4.py:197-231, save_log_feature=False):
+ * wave [B][L] -> amplitude mel [B][T][64], T = 1 + L/511.  Hamming(2048) STFT, hop 511, reflect pad. */
+int dcase_logmel_fwd(dcase_ctx* ctx, const float* wave, int B, int L, float* mel_amp, void* stream);
+/* Same from 16-bit PCM as stored in the wav files (soundfile scaling 1/32768, utils/utils.py:187). */
+int dcase_logmel_fwd_pcm16(dcase_ctx* ctx, const int16_t* wave, int B, int L, float* mel_amp, void* stream);
+
+/* get_transforms(frames, scaler, augment_type="noise") (utils/utils.py:397-412) on a batch:
+ * AugmentGaussianNoise (DataLoad.py:274-287) -> ApplyLog / librosa.amplitude_to_db (DataLoad.py:192-207)
+ * -> PadOrTrunc (DataLoad.py:210-259) -> ToTensor -> Normalize / Scaler.normalize (Scaler.py:99-105).
+ * mel_amp [B][T_in][64] -> clean [B][T_out][64] and, if noisy != NULL, noisy [B][T_out][64].
+ * noise: explicit |N(0,0.25)| sample [B][T_in][64] or NULL (Philox, see RNG contract; scalars overrides
+ * seed/step when non-NULL).  clip_max_ws: [2*B] floats of scratch. */
+int dcase_logmel_finish(dcase_ctx* ctx, const float* mel_amp, int B, int T_in, int T_out, const float* mean,
+                        const float* stdv, const float* noise, uint64_t seed, uint32_t step, const void* scalars,
+                        float* clip_max_ws, float* clean, float* noisy, void* stream);
+
+/* ---- CRNN ------------------------------------------------------------------------------------------ */
+
+/* Number of fp32 elements of the flat parameter slab (214,356 for n_class = 10). */
+size_t dcase_crnn_param_count(int n_class);
+/* Offset (in elements) of a named parameter inside the slab, or -1.  Names as in named_parameters(). */
+long long dcase_crnn_param_offset(int n_class, const char* name);
+
+size_t dcase_crnn_workspace_bytes(int B, int T, int n_class);
+/* Location of a named intermediate inside the workspace (tests / debugging); returns 0 or DCASE_ERR_ARG.
+ * Names: out0 ypre1 out1 ypre2 out2 rnn0 rnn1 fold0 bn1 bn2 d_out0 d_out1 d_out2 d_rnn0 d_rnn1 */
+int dcase_crnn_ws_tensor(int B, int T, int n_class, const char* name, size_t* offset_bytes, size_t* n_elems);
+
+/* CRNN.forward (models/CRNN.py:59-84; CNN.py:85-89; RNN.py:14-16).
+ * x [B][T][64], T % 8 == 0 -> strong [B][T/8][n_class], weak [B][n_class].
+ * flags: DCASE_FLAG_*; without BN_BATCH_STATS this is module.eval().  bn_running [3][2][64] is updated
+ * in train mode.  model_id selects the dropout streams (0 student, 1 teacher). */
+int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int n_class, const float* params,
+                       float* bn_running, int flags, uint64_t seed, uint32_t step, int model_id,
+                       const void* scalars, float* strong, float* weak, void* workspace, void* stream);
+
+/* Backward of the forward pass that filled `workspace` (same x, params, flags, seed, step, model_id).
+ * grads (param_count elements) is overwritten with d loss / d params  (loss.backward(), main.py:153). */
+int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int n_class, const float* params, int flags,
+                        uint64_t seed, uint32_t step, int model_id, const void* scalars, const float* d_strong,
+                        const float* d_weak, const float* weak, void* workspace, float* grads, void* stream);
+
+/* ---- mean-teacher losses (main.py:95-145; main_simple_CRNN.py:46-66 when strong_t == NULL) ---------- */
+/* meters[8] = {weak_class_loss, Weak EMA loss, Strong loss, Strong EMA loss, Consistency strong,
+ *              Consistency weak, Loss, Consistency weight};  d_strong / d_weak = d Loss / d student outputs.
+ * weak_mask = slice(weak_lo, weak_hi), strong_mask = slice(strong_lo, strong_hi); empty slice = None. */
+int dcase_mt_loss(dcase_ctx* ctx, const float* strong_s, const float* weak_s, const float* strong_t,
+                  const float* weak_t, const float* target, int B, int To, int n_class, int weak_lo, int weak_hi,
+                  int strong_lo, int strong_hi, float cons_weight, const void* scalars, float* meters,
+                  float* d_strong, float* d_weak, void* stream);
+
+/* ---- optimizer.step() + update_ema_variables (main.py:154-157, :45-49) ------------------------------ */
+/* torch.optim.Adam (no amsgrad / weight decay) on flat slabs, then p_ema = alpha*p_ema + (1-alpha)*p.
+ * step_t is Adam's step count AFTER the increment; g is multiplied by grad_scale first (1/world_size). */
+int dcase_adam_ema_step(dcase_ctx* ctx, float* p, const float* g, float* m, float* v, float* p_ema, size_t n,
+                        float lr, float beta1, float beta2, float eps, int step_t, float ema_alpha,
+                        float grad_scale, const void* scalars, void* stream);
+
+/* ---- one mean-teacher iteration, main.py:84-153 (forward x2, losses, backward) ----------------------- */
+typedef struct dcase_mt_args {
+    const float* x_student;   /* [B][T][64] clean */
+    const float* x_teacher;   /* [B][T][64] noisy; NULL = no teacher (main_simple_CRNN.py) */
+    const float* target;      /* [B][T/8][n_class], -1 rows for unlabeled clips */
+    int B, T, n_class;
+    int weak_lo, weak_hi, strong_lo, strong_hi;
+    const float* params_s;
+    const float* params_t;
+    float* bn_s;
+    float* bn_t;
+    int flags;
+    uint64_t seed;
+    uint32_t step;
+    float cons_weight;
+    const void* scalars;      /* device dcase_step_scalars or NULL */
+    float* strong_s;          /* outputs */
+    float* weak_s;
+    float* strong_t;
+    float* weak_t;
+    float* meters;            /* [8] */
+    float* d_strong;          /* scratch [B][T/8][n_class] */
+    float* d_weak;            /* scratch [B][n_class] */
+    void* ws_s;
+    void* ws_t;
+    float* grads;             /* [param_count] out */
+} dcase_mt_args;
+
+int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCASE_B200_H_ */

@@ -1,0 +1,220 @@
+"""CRNN / loss / optimizer parity: CUDA kernels (through the C ABI) vs the plain-torch fp32 oracle.
+
+Tolerance (north star): frame posteriors within 1e-3 abs of the reference path.  The kernels compute in
+fp32 (FMA, fast-exp sigmoid); observed errors are printed so regressions are visible.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn as ocrnn
+from oracle import train_step as otrain
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+POSTERIOR_TOL = 1e-3
+FLAGS_EVAL = 0
+FLAGS_TRAIN_NODROP = 1
+FLAGS_TRAIN = 3
+
+
+@pytest.fixture(scope="module")
+def K(cuda_device):
+    from dcase2019_task4_b200 import kernels
+    return kernels
+
+
+def _inputs(B, T, seed=0):
+    g = torch.Generator().manual_seed(100 + seed)
+    return torch.randn(B, 1, T, 64, generator=g) * 1.2 + 0.1
+
+
+def _buffers(seed=0):
+    g = torch.Generator().manual_seed(7 + seed)
+    buf = ocrnn.init_buffers()
+    for i in range(3):
+        buf[f"cnn.cnn.batchnorm{i}.running_mean"] = 0.2 * torch.randn(64, generator=g)
+        buf[f"cnn.cnn.batchnorm{i}.running_var"] = 0.5 + torch.rand(64, generator=g)
+    return buf
+
+
+def test_param_layout_matches_named_parameters(K):
+    off = 0
+    for name, shp in ocrnn.param_shapes(10).items():
+        assert K.param_offset(name) == off, name
+        off += int(np.prod(shp))
+    assert K.param_count(10) == off == 214356
+
+
+@pytest.mark.parametrize("B,T", [(2, 64), (1, 864), (3, 136)])
+def test_forward_eval(K, cuda_device, B, T):
+    p = ocrnn.init_params(seed=1)
+    buf = _buffers()
+    x = _inputs(B, T)
+    with torch.no_grad():
+        s_ref, w_ref, inter = ocrnn.crnn_forward(x, p, buf, training=False, return_intermediates=True)
+    ws = K.new_workspace(B, T, 10, cuda_device)
+    bn = H.bn_running_flat(buf).to(cuda_device)
+    bn0 = bn.clone()
+    s, w = K.crnn_forward(x.to(cuda_device), H.flat_params(p).to(cuda_device), bn, FLAGS_EVAL, ws)
+    for name in ("cnn0", "cnn1", "cnn2", "rnn"):
+        got = K.ws_tensor(ws, B, T, 10, {"cnn0": "out0", "cnn1": "out1", "cnn2": "out2", "rnn": "rnn1"}[name]).cpu()
+        ref = H.nchw_to_cl(inter[name]).reshape(-1) if name != "rnn" else inter[name].reshape(-1)
+        print(f"{name}: max|err| {H.maxerr(got, ref):.3e} (max|ref| {float(ref.abs().max()):.3e})")
+        assert H.maxerr(got, ref) <= 2e-4 * max(1.0, float(ref.abs().max()))
+    es, ew = H.maxerr(s.cpu(), s_ref), H.maxerr(w.cpu(), w_ref)
+    print(f"eval B={B} T={T}: strong Linf {es:.3e} weak Linf {ew:.3e}")
+    assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
+    assert torch.equal(bn, bn0)               # eval mode must not touch running stats
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_forward_train_and_running_stats(K, cuda_device, dropout):
+    B, T = 4, 72
+    seed, step = 0xC0FFEE1234, 5
+    p = ocrnn.init_params(seed=2)
+    buf = _buffers(1)
+    buf_ref = copy.deepcopy(buf)
+    x = _inputs(B, T, 1)
+    masks = H.oracle_masks(B, T, seed, step, model_id=1) if dropout else None
+    with torch.no_grad():
+        s_ref, w_ref = ocrnn.crnn_forward(x, p, buf_ref, training=True, masks=masks)
+    ws = K.new_workspace(B, T, 10, cuda_device)
+    bn = H.bn_running_flat(buf).to(cuda_device)
+    s, w = K.crnn_forward(x.to(cuda_device), H.flat_params(p).to(cuda_device), bn,
+                          FLAGS_TRAIN if dropout else FLAGS_TRAIN_NODROP, ws, seed=seed, step=step, model_id=1)
+    es, ew = H.maxerr(s.cpu(), s_ref), H.maxerr(w.cpu(), w_ref)
+    print(f"train dropout={dropout}: strong Linf {es:.3e} weak Linf {ew:.3e}")
+    assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
+    ebn = H.maxerr(bn.cpu(), H.bn_running_flat(buf_ref))
+    print(f"running stats err {ebn:.3e}")
+    assert ebn <= 1e-4
+
+
+def _loss_inputs(B, To, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    strong_t = torch.rand(B, To, 10, generator=g)
+    weak_t = torch.rand(B, 10, generator=g)
+    target = (torch.rand(B, To, 10, generator=g) < 0.2).float()
+    return strong_t, weak_t, target
+
+
+@pytest.mark.parametrize("with_teacher", [True, False])
+def test_mt_loss(K, cuda_device, with_teacher):
+    B, To = 8, 9
+    g = torch.Generator().manual_seed(3)
+    strong = torch.rand(B, To, 10, generator=g).requires_grad_(True)
+    weak = torch.rand(B, 10, generator=g).requires_grad_(True)
+    strong_t, weak_t, target = _loss_inputs(B, To)
+    target[2:6] = -1                           # unlabeled rows (utils.py:82-85)
+    wm, sm = slice(0, 2), slice(6, 8)
+    loss, meters = otrain.mean_teacher_losses(strong, weak, strong_t if with_teacher else None,
+                                              weak_t if with_teacher else None, target, wm, sm, 1.37)
+    loss.backward()
+    dev = cuda_device
+    m, ds, dw = K.mt_loss(strong.detach().to(dev), weak.detach().to(dev),
+                          strong_t.to(dev) if with_teacher else None, weak_t.to(dev) if with_teacher else None,
+                          target.to(dev), wm, sm, 1.37)
+    m = m.cpu().numpy()
+    names = ["weak_class_loss", "Weak EMA loss", "Strong loss", "Strong EMA loss", "Consistency strong",
+             "Consistency weak", "Loss"]
+    for i, n in enumerate(names):
+        if n in meters:
+            assert abs(m[i] - meters[n]) <= 1e-5 * max(1.0, abs(meters[n])), (n, m[i], meters[n])
+    assert H.maxerr(ds.cpu(), strong.grad) <= 1e-5 * float(strong.grad.abs().max())
+    assert H.maxerr(dw.cpu(), weak.grad) <= 1e-5 * float(weak.grad.abs().max())
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_backward_all_gradients(K, cuda_device, dropout):
+    B, T = 4, 72
+    To = T // 8
+    seed, step = 99, 3
+    dev = cuda_device
+    p = ocrnn.init_params(seed=4)
+    buf = _buffers(2)
+    x = _inputs(B, T, 2)
+    strong_t, weak_t, target = _loss_inputs(B, To, 9)
+    target[1:3] = -1
+    wm, sm = slice(0, 1), slice(3, 4)
+    masks = H.oracle_masks(B, T, seed, step, model_id=0) if dropout else None
+    sp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    s_ref, w_ref = ocrnn.crnn_forward(x, sp, copy.deepcopy(buf), training=True, masks=masks)
+    loss, _ = otrain.mean_teacher_losses(s_ref, w_ref, strong_t, weak_t, target, wm, sm, 0.8)
+    gref = dict(zip(sp.keys(), torch.autograd.grad(loss, list(sp.values()))))
+
+    flags = FLAGS_TRAIN if dropout else FLAGS_TRAIN_NODROP
+    ws = K.new_workspace(B, T, 10, dev)
+    pf = H.flat_params(p).to(dev)
+    xd = x.to(dev)
+    s, w = K.crnn_forward(xd, pf, H.bn_running_flat(buf).to(dev), flags, ws, seed=seed, step=step)
+    _, ds, dw = K.mt_loss(s, w, strong_t.to(dev), weak_t.to(dev), target.to(dev), wm, sm, 0.8)
+    grads = K.crnn_backward(xd, pf, flags, ws, ds, dw, w, seed=seed, step=step).cpu()
+    got = H.unflat_params(grads)
+    worst = 0.0
+    for k, gr in gref.items():
+        scale = float(gr.abs().max())
+        err = H.maxerr(got[k], gr)
+        rel = err / max(scale, 1e-12)
+        print(f"{k:40s} max|g| {scale:.3e} err {err:.3e} rel {rel:.2e}")
+        if k.endswith("conv0.bias") or k.endswith("conv1.bias") or k.endswith("conv2.bias"):
+            assert err <= 1e-6                 # BN cancels the conv bias: gradient is rounding noise in torch
+            continue
+        worst = max(worst, rel)
+        assert rel <= 2e-3, k
+    print(f"worst relative gradient error {worst:.2e}")
+
+
+def test_adam_ema_matches_torch_adam(K, cuda_device):
+    n = 214356
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(n, generator=g)
+    pe = torch.randn(n, generator=g)
+    ref_p = {"w": p.clone()}
+    ref_pe = pe.clone()
+    st = otrain.new_adam_state(ref_p)
+    dp, dpe = p.to(cuda_device), pe.to(cuda_device)
+    m = torch.zeros(n, device=cuda_device)
+    v = torch.zeros(n, device=cuda_device)
+    for t in range(1, 4):
+        grad = torch.randn(n, generator=g) * 10 ** float(torch.randn((), generator=g))
+        otrain.adam_update(ref_p, {"w": grad}, st)
+        a = otrain.ema_alpha(t)
+        ref_pe.mul_(a).add_(ref_p["w"], alpha=1 - a)
+        K.adam_ema_step(dp, grad.to(cuda_device), m, v, dpe, t, ema_alpha=a)
+        assert H.maxerr(dp.cpu(), ref_p["w"]) <= 2e-6
+        assert H.maxerr(dpe.cpu(), ref_pe) <= 2e-6
+    assert otrain.ema_alpha(1) == 0.5          # first step: alpha = min(1 - 1/2, 0.999), main.py:47,155
+
+
+def test_full_size_eval_and_train_step_properties(K, cuda_device):
+    """BASELINE config: B=24, T=864.  Eval forward vs oracle + size-independent properties."""
+    B, T = 24, 864
+    dev = cuda_device
+    p = ocrnn.init_params(seed=5)
+    buf = _buffers(3)
+    x = _inputs(B, T, 3)
+    with torch.no_grad():
+        s_ref, w_ref = ocrnn.crnn_forward(x, p, buf, training=False)
+    ws = K.new_workspace(B, T, 10, dev)
+    pf = H.flat_params(p).to(dev)
+    bn = H.bn_running_flat(buf).to(dev)
+    s, w = K.crnn_forward(x.to(dev), pf, bn, FLAGS_EVAL, ws)
+    es, ew = H.maxerr(s.cpu(), s_ref), H.maxerr(w.cpu(), w_ref)
+    print(f"full-size eval: strong Linf {es:.3e} weak Linf {ew:.3e}")
+    assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
+    # batch independence in eval mode: clip 5 alone gives the same posteriors
+    s1, _ = K.crnn_forward(x[5:6].to(dev), pf, bn, FLAGS_EVAL, K.new_workspace(1, T, 10, dev))
+    assert H.maxerr(s1[0], s[5]) <= 1e-6
+    # weak is a convex combination of strong over time
+    assert bool((w <= s.max(1)[0] + 1e-6).all()) and bool((w >= s.min(1)[0] - 1e-6).all())
+    # train-mode step: same seed/step -> bitwise identical forward; different step -> different dropout
+    a1, _ = K.crnn_forward(x.to(dev), pf, bn.clone(), FLAGS_TRAIN, ws, seed=1, step=1)
+    a1 = a1.clone()
+    a2, _ = K.crnn_forward(x.to(dev), pf, bn.clone(), FLAGS_TRAIN, ws, seed=1, step=1)
+    assert torch.equal(a1, a2)
+    a3, _ = K.crnn_forward(x.to(dev), pf, bn.clone(), FLAGS_TRAIN, ws, seed=1, step=2)
+    assert not torch.equal(a1, a3)

@@ -1,0 +1,131 @@
+"""Pins the torch oracle (oracle/crnn.py, oracle/train_step.py) against the reference's own
+``baseline/models/CRNN.py`` imported UNMODIFIED from /root/reference.  Runs only where the reference tree is
+mounted (the build container); the GPU box relies on the committed fixtures in tests/golden/."""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn as ocrnn
+from oracle import train_step as otrain
+
+REF = "/root/reference/baseline"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+
+CRNN_KWARGS = {"n_in_channel": 1, "nclass": 10, "attention": True, "n_RNN_cell": 64, "n_layers_RNN": 2,
+               "activation": "glu", "dropout": 0.5, "kernel_size": 3 * [3], "padding": 3 * [1], "stride": 3 * [1],
+               "nb_filters": [64, 64, 64], "pooling": list(3 * ((2, 4),))}   # config.py:53-58
+
+
+def ref_crnn(**over):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from models.CRNN import CRNN
+    kw = dict(CRNN_KWARGS)
+    kw.update(over)
+    return CRNN(**kw)
+
+
+def load_oracle_params(model, p, buf):
+    sd = dict(model.named_parameters())
+    with torch.no_grad():
+        for k, v in p.items():
+            sd[k].copy_(v)
+        for k, v in buf.items():
+            dict(model.named_buffers())[k].copy_(v)
+
+
+def test_named_parameters_order_and_count():
+    m = ref_crnn()
+    names = [k for k, _ in m.named_parameters()]
+    shapes = ocrnn.param_shapes(10)
+    assert names == list(shapes.keys())
+    for k, v in m.named_parameters():
+        assert tuple(v.shape) == tuple(shapes[k])
+    assert sum(v.numel() for v in m.parameters()) == 214356
+
+
+def test_eval_forward_matches_reference():
+    p = ocrnn.init_params(seed=1)
+    buf = ocrnn.init_buffers()
+    buf["cnn.cnn.batchnorm1.running_mean"] += 0.3
+    buf["cnn.cnn.batchnorm2.running_var"] *= 1.7
+    m = ref_crnn().eval()
+    load_oracle_params(m, p, buf)
+    x = torch.randn(3, 1, 64, 64)
+    with torch.no_grad():
+        s_ref, w_ref = m(x)
+        s, w = ocrnn.crnn_forward(x, p, buf, training=False)
+    assert float((s - s_ref).abs().max()) < 2e-6
+    assert float((w - w_ref).abs().max()) < 2e-6
+
+
+def test_train_forward_backward_matches_reference_without_dropout():
+    p = ocrnn.init_params(seed=2)
+    buf = ocrnn.init_buffers()
+    m = ref_crnn(dropout=0).train()
+    load_oracle_params(m, p, buf)
+    x = torch.randn(4, 1, 72, 64)
+    g = torch.Generator().manual_seed(0)
+    strong_t, weak_t = torch.rand(4, 9, 10, generator=g), torch.rand(4, 10, generator=g)
+    target = (torch.rand(4, 9, 10, generator=g) < 0.3).float()
+    wm, sm = slice(0, 1), slice(3, 4)
+    s_ref, w_ref = m(x)
+    # main.py:95-145 verbatim structure with torch criteria
+    bce, mse = torch.nn.BCELoss(), torch.nn.MSELoss()
+    tw = target.max(-2)[0]
+    loss_ref = bce(w_ref[wm], tw[wm]) + bce(s_ref[sm], target[sm]) + 0.8 * mse(s_ref, strong_t) + 0.8 * mse(w_ref, weak_t)
+    loss_ref.backward()
+    sp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    buf2 = copy.deepcopy(buf)
+    s, w = ocrnn.crnn_forward(x, sp, buf2, training=True, masks=None)
+    loss, meters = otrain.mean_teacher_losses(s, w, strong_t, weak_t, target, wm, sm, 0.8)
+    assert abs(float(loss) - float(loss_ref)) < 1e-6
+    grads = torch.autograd.grad(loss, list(sp.values()))
+    for (k, v), gmine in zip(m.named_parameters(), grads):
+        scale = max(float(v.grad.abs().max()), 1e-8)
+        if ".conv" in k and k.endswith("bias"):
+            continue                          # analytically zero behind BatchNorm; rounding noise on both sides
+        assert float((gmine - v.grad).abs().max()) <= 1e-4 * scale + 1e-9, k
+    for k, v in m.named_buffers():            # running stats: momentum 0.99, unbiased variance
+        assert float((buf2[k].float() - v.float()).abs().max()) < 1e-5, k
+
+
+def test_adam_and_ema_match_torch_optim():
+    torch.manual_seed(0)
+    p = {"a": torch.randn(50), "b": torch.randn(3, 7)}
+    ref = [torch.nn.Parameter(v.clone()) for v in p.values()]
+    opt = torch.optim.Adam(ref, lr=0.001, betas=(0.9, 0.999))   # main.py:289-290
+    st = otrain.new_adam_state(p)
+    for _ in range(5):
+        g = {k: torch.randn_like(v) for k, v in p.items()}
+        for r, gg in zip(ref, g.values()):
+            r.grad = gg.clone()
+        opt.step()
+        otrain.adam_update(p, g, st)
+        for r, v in zip(ref, p.values()):
+            assert float((r.detach() - v).abs().max()) < 1e-6
+
+
+def test_rampup_matches_reference_ramps():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from utils import ramps
+    for cur, length in [(0, 10500), (1, 10500), (5000, 10500), (10500, 10500), (20000, 10500), (3, 0)]:
+        assert otrain.sigmoid_rampup(cur, length) == pytest.approx(ramps.sigmoid_rampup(cur, length), abs=1e-15)
+    assert otrain.consistency_weight(0, 210) == pytest.approx(2 * np.exp(-5.0))
+    assert otrain.consistency_weight(10500, 210) == 2.0
+
+
+def test_state_dict_format_roundtrip():
+    p = ocrnn.init_params(seed=3)
+    buf = ocrnn.init_buffers()
+    m = ref_crnn()
+    m.load(parameters=ocrnn.to_reference_state_dict(p, buf))
+    sd = m.state_dict()
+    assert set(sd.keys()) == {"cnn", "rnn", "dense"}
+    assert torch.equal(sd["cnn"]["conv1.weight"], p["cnn.cnn.conv1.weight"])
+    assert torch.equal(sd["rnn"]["rnn.weight_hh_l1_reverse"], p["rnn.rnn.weight_hh_l1_reverse"])
