@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the DCASE2019-task4 hot path:  10-s clips/s of the CRNN mean-teacher train step.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[1]): batch 24 = 6 weak + 12 unlabeled + 6 synthetic 10-s clips per GPU; one step
+= waveform -> log-mel (clean + noisy) -> teacher fwd -> student fwd -> BCE + consistency losses -> student bwd ->
+Adam + EMA.  Synthetic clips (dcase2019_task4_b200/synth.py), random-init weights (utils.weights_init).
+Prints ONE JSON line on rank 0 (contract in the task prompt).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_PER_GPU = 24
+BATCH_SIZES = [6, 12, 6]                 # main.py:238: [bs//4, bs//2, bs//4]
+FRAMES = 864
+N_SAMPLES = 441000
+STEPS_PER_EPOCH = 210                    # len(loader) with the full dataset
+# algorithmic GEMM/conv FLOPs per clip (2*MACs), SURVEY.md section 8d / BASELINE.md section 4
+FWD_FLOPS_PER_CLIP = 1.1808e9
+STEP_FLOPS_PER_CLIP = 4.7232e9
+LAYER_FLOPS_PER_CLIP = {"conv0": 63.70e6, "glu0": 452.98e6, "conv1": 509.61e6, "glu1": 56.62e6,
+                        "conv2": 63.70e6, "glu2": 7.08e6}
+MEL_BYTES_PER_CLIP = 441000 * 4 + 864 * 64 * 4
+
+
+def kernel_flops_per_launch(name, B):
+    """Algorithmic FLOPs one launch of a named kernel performs at per-GPU batch B (GEMM/conv work only)."""
+    L = LAYER_FLOPS_PER_CLIP
+    table = {
+        "cnn0_fused_fwd": L["conv0"] + L["glu0"],
+        "cnn0_fused_bwd": L["conv0"] + 3 * L["glu0"] + L["conv0"],   # recompute + dgate GEMM + GLU wgrad + conv wgrad
+        "conv3x3_fwd_l1": L["conv1"], "conv3x3_dgrad_l1": L["conv1"], "conv3x3_wgrad_l1": L["conv1"],
+        "conv3x3_fwd_l2": L["conv2"], "conv3x3_dgrad_l2": L["conv2"], "conv3x3_wgrad_l2": L["conv2"],
+        "glu_pool_fwd_l1": L["glu1"], "glu_pool_bwd_l1": 3 * L["glu1"],
+        "glu_pool_fwd_l2": L["glu2"], "glu_pool_bwd_l2": 3 * L["glu2"],
+    }
+    return table.get(name, 0.0) * B
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_batches(n_batches, seed):
+    from dcase2019_task4_b200 import synth
+    waves, events = synth.make_clips(n_batches * B_PER_GPU, seed=seed, n_samples=N_SAMPLES)
+    targets = np.stack([synth.make_targets(events[i * B_PER_GPU:(i + 1) * B_PER_GPU], BATCH_SIZES, FRAMES // 8)
+                        for i in range(n_batches)])
+    return waves.reshape(n_batches, B_PER_GPU, N_SAMPLES), targets
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(n_steps, n_warmup, clips_per_step, seed=0):
+    """Times `n_steps` mean-teacher iterations of the CPU port on `clips_per_step` clips each: restated float64
+    numpy log-mel (librosa is not installed) + plain-torch CRNN oracle + Adam + EMA.  Returns clips/s, details."""
+    import torch
+    from dcase2019_task4_b200 import synth
+    from oracle import crnn as ocrnn, mel as omel, train_step as otrain
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nb = clips_per_step
+    sizes = [nb // 4, nb // 2, nb - nb // 4 - nb // 2]
+    waves, events = synth.make_clips(nb, seed=seed, n_samples=N_SAMPLES)
+    target = torch.from_numpy(synth.make_targets(events, sizes, FRAMES // 8))
+    basis = omel.mel_filterbank()
+    rng = np.random.default_rng(seed)
+    sp, tp = ocrnn.init_params(seed=1), ocrnn.init_params(seed=2)
+    sbuf, tbuf = ocrnn.init_buffers(), ocrnn.init_buffers()
+    adam = otrain.new_adam_state(sp)
+    mean, std = np.full(64, -30.0), np.full(64, 12.0)
+    times = []
+    for it in range(n_warmup + n_steps):
+        t0 = time.perf_counter()
+        xs, xn = [], []
+        for w in waves:                                  # per-sample, as the reference's Dataset does
+            amp = omel.calculate_mel_spec(w.astype(np.float64), basis)
+            noise = np.abs(rng.normal(0, 0.25, amp.shape))
+            c, n = omel.transform_chain(amp, mean, std, noise=noise, frames=FRAMES)
+            xs.append(c); xn.append(n)
+        x = torch.from_numpy(np.stack(xs))
+        x_ema = torch.from_numpy(np.stack(xn))
+        g = torch.Generator().manual_seed(it)
+        masks = [{f"cnn{i}": torch.rand(nb, 64, FRAMES >> i, 64 >> (2 * i), generator=g) < 0.5 for i in range(3)}
+                 for _ in range(2)]
+        for m in masks:
+            m["head"] = torch.rand(nb, FRAMES // 8, 128, generator=g) < 0.5
+        otrain.train_batch(sp, sbuf, adam, x, target, it, STEPS_PER_EPOCH, teacher_p=tp, teacher_buf=tbuf, x_ema=x_ema,
+                           weak_mask=slice(0, sizes[0]), strong_mask=slice(sizes[0] + sizes[1], nb),
+                           masks_student=masks[0], masks_teacher=masks[1])
+        dt = time.perf_counter() - t0
+        if it >= n_warmup:
+            times.append(dt)
+    mean_t = float(np.mean(times))
+    return nb / mean_t, {"cores": cores, "s_per_step": mean_t, "clips_per_step": nb}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import torch  # noqa: F401
+    # bound the run: probe one small step, then size the per-step sample so K+W steps end within ~150 s
+    _, probe = cpu_reference_steps(1, 0, 4)
+    per_clip = probe["s_per_step"] / 4
+    total_steps = args.steps + args.warmup
+    nb = int(max(4, min(B_PER_GPU, (150.0 / max(total_steps, 1)) / per_clip // 4 * 4)))
+    value, info = cpu_reference_steps(args.steps, args.warmup, nb)
+    sample = (f"{args.steps} timed steps of {nb} clips each (reference batch is 24; bounded so the run ends in minutes); "
+              "restated float64 numpy log-mel (librosa absent) + plain-torch CRNN oracle + Adam + EMA")
+    line = {"impl": "reference", "metric": "mean_teacher_train_clips_per_sec", "value": value, "unit": "clips/s",
+            "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["s_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(), "global_batch": nb, "frames": FRAMES},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": info["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name():
+    return ("configs[1]: batch=24/GPU weak+synthetic CRNN mean-teacher (6 weak | 12 unlabeled | 6 strong 10-s clips), "
+            "waveform -> log-mel (clean+noisy) -> teacher fwd + student fwd -> BCE + consistency -> bwd -> Adam + EMA")
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from dcase2019_task4_b200 import config as cfg
+    from dcase2019_task4_b200 import kernels as K
+    from dcase2019_task4_b200.main import MeanTeacherEngine
+    from dcase2019_task4_b200.models.CRNN import CRNN
+    from dcase2019_task4_b200.utils import ramps
+    from dcase2019_task4_b200.utils.utils import weights_init
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    # ---- data: pool of distinct batches resident in HBM (larger than the 126 MB L2) + pinned host copies ----
+    n_pool = 6
+    waves, targets = synthetic_batches(n_pool, seed=1000 + rank)
+    wave_dev = torch.from_numpy(waves).to(dev)                      # [6, 24, 441000] f32 = 254 MB
+    target_dev = torch.from_numpy(targets).to(dev)
+    wave_host = torch.from_numpy(waves).pin_memory()
+    target_host = torch.from_numpy(targets).pin_memory()
+
+    # ---- scaler statistics from the first batch (Scaler.calculate_scaler semantics, untimed set-up) ----
+    amp0 = K.logmel_fwd(wave_dev[0])
+    db0 = K.logmel_finish(amp0, torch.zeros(64, device=dev), torch.ones(64, device=dev), FRAMES)
+    mean = db0.mean(dim=(0, 1)).contiguous()
+    std = (db0.pow(2).mean(dim=(0, 1)) - mean ** 2).sqrt().contiguous()
+
+    # ---- models exactly as main.py:279-290 ----
+    torch.manual_seed(1234)
+    crnn = CRNN(**cfg.crnn_kwargs)
+    crnn_ema = CRNN(**cfg.crnn_kwargs)
+    crnn.apply(weights_init)
+    crnn_ema.apply(weights_init)
+    for p in crnn_ema.parameters():
+        p.detach_()
+    crnn, crnn_ema = crnn.train().cuda(), crnn_ema.train().cuda()
+    if world > 1:                                                   # identical weights on every rank
+        dist.broadcast(crnn.flat_parameters(), 0)
+        dist.broadcast(crnn_ema.flat_parameters(), 0)
+    optimizer = torch.optim.Adam(filter(lambda p: p.requires_grad, crnn.parameters()), lr=0.001, betas=(0.9, 0.999))
+    weak_mask = slice(BATCH_SIZES[0])
+    strong_mask = slice(BATCH_SIZES[0] + BATCH_SIZES[1], B_PER_GPU)
+    engine = MeanTeacherEngine(crnn, optimizer, crnn_ema, weak_mask, strong_mask, B_PER_GPU, FRAMES)
+    rampup_length = STEPS_PER_EPOCH * cfg.n_epoch // 2
+
+    state = {"gs": 0}
+
+    def cons_weight():
+        gs = state["gs"]
+        r = ramps.sigmoid_rampup(gs, rampup_length) if gs < rampup_length else 1.0
+        return cfg.max_consistency_cost * r
+
+    def resident_step(i):
+        engine.step_from_waveforms(wave_dev[i % n_pool], target_dev[i % n_pool], mean, std, cons_weight(),
+                                   state["gs"] + 1, check=False)
+        state["gs"] += 1
+
+    stage_w = torch.empty(B_PER_GPU, N_SAMPLES, device=dev)
+    stage_t = torch.empty(B_PER_GPU, FRAMES // 8, 10, device=dev)
+
+    def e2e_step(i):
+        """Public-API call with HOST buffers: H2D of the clips and targets, the step, D2H of the meters."""
+        stage_w.copy_(wave_host[i % n_pool], non_blocking=True)
+        stage_t.copy_(target_host[i % n_pool], non_blocking=True)
+        engine.step_from_waveforms(stage_w, stage_t, mean, std, cons_weight(), state["gs"] + 1, check=False)
+        state["gs"] += 1
+        return engine.check_loss()                                  # syncs on the 32-byte meter copy
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the timed device-resident region ----
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = K.launch_count()
+    ms_total = timed(resident_step, args.steps)
+    launches = K.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * B_PER_GPU * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers ----
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B_PER_GPU * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launching stream, separate pass) ----
+    K.profile_begin()
+    n_prof = 5
+    for i in range(n_prof):
+        resident_step(i)
+    prof = K.profile_end()
+    total_prof = sum(ms for _, ms in prof.values())
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dom_name, (dom_cnt, dom_ms) = dom
+    dom_avg_s = dom_ms / dom_cnt * 1e-3
+    dom_flops = kernel_flops_per_launch(dom_name, B_PER_GPU)
+    if dom_name == "stft_mel":
+        roof = {"bound": "hbm", "achieved": MEL_BYTES_PER_CLIP * B_PER_GPU / dom_avg_s / 1e9, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s"}
+    else:
+        roof = {"bound": "tensor", "achieved": dom_flops / dom_avg_s / 1e12, "peak": peaks["tf_sustained"],
+                "unit": "TFLOP/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof.update({"traffic": None, "kernel": dom_name, "kernel_ms": dom_ms / dom_cnt,
+                 "kernel_share_of_step": dom_ms / total_prof, "peak_source": peaks["source"] + " (sustained bf16 dense)",
+                 "step_tensor_frac": (value / world) * STEP_FLOPS_PER_CLIP / 1e12 / peaks["tf_sustained"],
+                 "per_kernel_ms": {k: round(ms / n_prof, 4) for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}})
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, info = cpu_reference_steps(1, 0, B_PER_GPU)
+        cpu = {"value": v, "unit": "clips/s", "cores": info["cores"], "kind": "port",
+               "sample": "1 mean-teacher step on 24 clips (%.1f s): restated float64 numpy log-mel (librosa absent) + "
+                         "plain-torch CRNN oracle + Adam + EMA, all host threads" % info["s_per_step"]}
+
+    if rank == 0:
+        line = {"metric": "mean_teacher_train_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(), "global_batch": world * B_PER_GPU, "frames": FRAMES,
+                           "parallelism": "dp%d" % world,
+                           "l2": "inputs larger than L2: rotating pool of 6 waveform batches (254 MB) per GPU, "
+                                 "plus ~400 MB of activations rewritten every step"},
+                "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": B_PER_GPU * N_SAMPLES * 4 + B_PER_GPU * (FRAMES // 8) * 10 * 4,
+                        "d2h_bytes_per_step": 32},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,9 @@ SIGNATURES = {
     "dcase_last_error": (ctypes.c_char_p, []),
     "dcase_ctx_create": (c_i, [ctypes.POINTER(c_p), c_i]),
     "dcase_ctx_destroy": (c_i, [c_p]),
+    "dcase_launch_count": (ctypes.c_ulonglong, []),
+    "dcase_profile_begin": (c_i, []),
+    "dcase_profile_end": (c_i, [ctypes.c_char_p, c_sz]),
     "dcase_logmel_num_frames": (c_i, [c_i]),
     "dcase_mel_filterbank": (c_i, [c_p, c_p]),
     "dcase_logmel_fwd": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),

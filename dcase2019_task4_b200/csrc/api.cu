@@ -15,6 +15,25 @@ int dcase_logmel_tables_create(dcase_ctx* ctx);
 void dcase_logmel_tables_destroy(dcase_ctx* ctx);
 
 static thread_local char g_err[512] = "";
+unsigned long long g_dcase_launches = 0;
+
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+DcaseProfScope::DcaseProfScope(const char* name, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_prof_on) return;
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+DcaseProfScope::~DcaseProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
 
 void dcase_set_error(const char* fmt, ...) {
     va_list ap;
@@ -147,6 +166,41 @@ int check_shape(int B, int T, int NC) {
 extern "C" {
 
 int dcase_version(void) { return DCASE_B200_VERSION; }
+
+unsigned long long dcase_launch_count(void) { return g_dcase_launches; }
+
+int dcase_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+    return DCASE_OK;
+}
+
+int dcase_profile_end(char* buf, size_t cap) {
+    g_prof_on = false;
+    DCASE_REQUIRE(buf && cap > 0, "null buffer");
+    DCASE_CUDA_CHECK(cudaDeviceSynchronize());
+    struct Agg { std::string name; int count; double ms; };
+    std::vector<Agg> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        bool found = false;
+        for (auto& a : agg) if (a.name == r.name) { a.count++; a.ms += ms; found = true; break; }
+        if (!found) agg.push_back({r.name, 1, ms});
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    std::string out;
+    for (auto& a : agg) {
+        char line[160];
+        snprintf(line, sizeof(line), "%s,%d,%.6f\n", a.name.c_str(), a.count, a.ms);
+        out += line;
+    }
+    if (out.size() + 1 > cap) { dcase_set_error("profile buffer too small"); return DCASE_ERR_ARG; }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return DCASE_OK;
+}
 const char* dcase_last_error(void) { return g_err; }
 
 int dcase_ctx_create(dcase_ctx** out, int device) {

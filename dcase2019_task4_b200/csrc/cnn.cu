@@ -660,6 +660,7 @@ int cnn_kernels_init() {
 }
 
 int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, cudaStream_t s) {
+    DCASE_PROF("cnn0_moments", s);
     DCASE_CUDA_CHECK(cudaMemsetAsync(mom, 0, 54 * sizeof(double), s));
     const long long n_pix = (long long)B * T * 64;
     long long blocks = (n_pix + 255) / 256;
@@ -672,6 +673,7 @@ int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, 
 int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running, int training, float* fold0,
                         cudaStream_t s) {
+    DCASE_PROF("bn0_finalize", s);
     bn0_finalize_kernel<<<1, 64, 0, s>>>(mom, n_pix, conv_w, conv_b, gamma, beta, running, training, fold0);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
@@ -684,6 +686,7 @@ static int grid_for(long long n_tiles, int num_sms, int per_sm) {
 
 int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
                          DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
+    DCASE_PROF("cnn0_fused_fwd", s);
     GluArgs a{};
     a.src = x; a.n_pix = (long long)B * T * 64; a.T = T; a.F = 64; a.aff = fold0;
     a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
@@ -695,6 +698,7 @@ int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const
 
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
                         const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
+    DCASE_PROF(F == 16 ? "glu_pool_fwd_l1" : "glu_pool_fwd_l2", s);
     GluArgs a{};
     a.src = ypre; a.n_pix = n_pix; a.F = F; a.aff = bn; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
     const long long n_tiles = (n_pix + kTile - 1) / kTile;
@@ -704,6 +708,7 @@ int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* 
 }
 
 int launch_conv_w_prep(const float* w, float* w_fwd, float* w_dgrad, cudaStream_t s) {
+    DCASE_PROF("conv_w_prep", s);
     conv_w_prep_kernel<<<36, 256, 0, s>>>(w, w_fwd, w_dgrad);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
@@ -711,6 +716,7 @@ int launch_conv_w_prep(const float* w, float* w_fwd, float* w_dgrad, cudaStream_
 
 int launch_conv3x3(const float* in, int n_rows, int T_l, int F, const float* w_prep, const float* bias, float* out,
                    double* stats, int num_sms, cudaStream_t s) {
+    DCASE_PROF(bias ? (F == 16 ? "conv3x3_fwd_l1" : "conv3x3_fwd_l2") : (F == 16 ? "conv3x3_dgrad_l1" : "conv3x3_dgrad_l2"), s);
     const int TR = kTile / F;
     const int n_tiles = (n_rows + TR - 1) / TR;
     const int grid = grid_for(n_tiles, num_sms, 1);
@@ -726,6 +732,7 @@ int launch_conv3x3(const float* in, int n_rows, int T_l, int F, const float* w_p
 
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta, float* running,
                        int training, float* bn, cudaStream_t s) {
+    DCASE_PROF("bn_finalize", s);
     bn_finalize_kernel<<<1, 64, 0, s>>>(stats, n_pix, gamma, beta, running, training, bn);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
@@ -734,6 +741,7 @@ int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma,
 int launch_glu_pool_bwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
                          DropoutCfg drop, const float* d_out, float* acc0, float* g_glu_w, float* g_glu_b,
                          int num_sms, cudaStream_t s) {
+    DCASE_PROF("cnn0_fused_bwd", s);
     GluArgs a{};
     a.src = x; a.n_pix = (long long)B * T * 64; a.T = T; a.F = 64; a.aff = fold0;
     a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.stat_acc = acc0;
@@ -748,6 +756,7 @@ int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* 
                         const float* beta, const float* glu_w, const float* glu_b, DropoutCfg drop,
                         const float* d_out, float* d_y, float* s12, float* g_glu_w, float* g_glu_b, int num_sms,
                         cudaStream_t s) {
+    DCASE_PROF(F == 16 ? "glu_pool_bwd_l1" : "glu_pool_bwd_l2", s);
     GluArgs a{};
     a.src = ypre; a.n_pix = n_pix; a.F = F; a.aff = bn; a.gamma = gamma; a.beta = beta;
     a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.d_y = d_y; a.stat_acc = s12;
@@ -761,6 +770,7 @@ int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* 
 int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const float* bn, const float* gamma,
                         const float* s12, float* g_gamma, float* g_beta, float* g_conv_b, int num_sms,
                         cudaStream_t s) {
+    DCASE_PROF("bn_bwd_apply", s);
     (void)gamma;
     long long blocks = (n_pix * 16 + 255) / 256;
     if (blocks > num_sms * 8) blocks = num_sms * 8;
@@ -771,6 +781,7 @@ int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const fl
 
 int launch_conv_wgrad(const float* d_pre, const float* in, int n_rows, int T_l, int F, float* g_w, int num_sms,
                       cudaStream_t s) {
+    DCASE_PROF(F == 16 ? "conv3x3_wgrad_l1" : "conv3x3_wgrad_l2", s);
     const int TR = kTile / F;
     const int n_tiles = (n_rows + TR - 1) / TR;
     int chunks = (num_sms * 2 + 8) / 9;
@@ -784,6 +795,7 @@ int launch_conv_wgrad(const float* d_pre, const float* in, int n_rows, int T_l, 
 int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                              const float* gamma, const float* fold0, const float* acc0, float* g_conv_w,
                              float* g_conv_b, float* g_gamma, float* g_beta, cudaStream_t s) {
+    DCASE_PROF("cnn0_bwd_finalize", s);
     (void)gamma;
     cnn0_bwd_finalize_kernel<<<1, 64, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, acc0, g_conv_w, g_conv_b, g_gamma,
                                             g_beta);

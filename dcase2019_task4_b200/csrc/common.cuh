@@ -21,7 +21,22 @@ void dcase_set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
-#define DCASE_LAUNCH_CHECK() DCASE_CUDA_CHECK(cudaGetLastError())
+// every kernel launch goes through this: counts launches (bench.py's gpu_launches) and checks the launch
+extern unsigned long long g_dcase_launches;
+#define DCASE_LAUNCH_CHECK()                 \
+    do {                                     \
+        ++g_dcase_launches;                  \
+        DCASE_CUDA_CHECK(cudaGetLastError()); \
+    } while (0)
+
+// Optional per-kernel CUDA-event timing on the launching stream (dcase_profile_begin / _end).
+struct DcaseProfScope {
+    int slot;
+    cudaStream_t stream;
+    DcaseProfScope(const char* name, cudaStream_t s);
+    ~DcaseProfScope();
+};
+#define DCASE_PROF(name, stream) DcaseProfScope prof_scope__(name, stream)
 
 #define DCASE_REQUIRE(cond, msg)                                                            \
     do {                                                                                    \

@@ -219,6 +219,7 @@ gru_bwd_kernel(GruBwdArgs a) {
 
 int launch_sgemm(int M, int N, int K, const float* A, long long sam, long long sak, const float* B, long long sbk,
                  long long sbn, float* C, int ldc, const float* bias, int beta, int split_k, cudaStream_t s) {
+    DCASE_PROF("sgemm", s);
     if (M <= 0 || N <= 0 || K <= 0) return DCASE_OK;
     dim3 grid((N + 63) / 64, (M + 63) / 64, split_k < 1 ? 1 : split_k);
     sgemm_kernel<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, ldc, bias, beta);
@@ -227,18 +228,21 @@ int launch_sgemm(int M, int N, int K, const float* A, long long sam, long long s
 }
 
 int launch_colsum(const float* A, int M, int N, float* out, cudaStream_t s) {
+    DCASE_PROF("colsum", s);
     colsum_kernel<<<(N + 63) / 64, 256, 0, s>>>(A, M, N, out);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 
 int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t s) {
+    DCASE_PROF("gru_fwd", s);
     gru_fwd_kernel<<<dim3(a.B, 2), 4 * H, 0, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 
 int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s) {
+    DCASE_PROF("gru_bwd", s);
     gru_bwd_kernel<<<dim3(a.B, 2), 4 * H, 0, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;

@@ -323,18 +323,21 @@ int head_kernels_init() {
 }
 
 int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
+    DCASE_PROF("head_fwd", s);
     head_fwd_kernel<<<a.B, 128, 0, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 
 int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
+    DCASE_PROF("head_bwd", s);
     head_bwd_kernel<<<a.B, 128, kHeadBwdSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 
 int launch_mt_loss(const LossArgs& a, cudaStream_t s) {
+    DCASE_PROF("mt_loss", s);
     mt_loss_kernel<<<1, 1024, 0, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
@@ -343,6 +346,7 @@ int launch_mt_loss(const LossArgs& a, cudaStream_t s) {
 int launch_adam_ema(float* p, const float* g, float* m, float* v, float* p_ema, long long n, float lr, float beta1,
                     float beta2, float eps, float bc1, float bc2, float alpha, float grad_scale,
                     const DcaseStepScalars* sc, int num_sms, cudaStream_t s) {
+    DCASE_PROF("adam_ema", s);
     long long blocks = (n + 255) / 256;
     if (blocks > num_sms * 8) blocks = num_sms * 8;
     adam_ema_kernel<<<(int)blocks, 256, 0, s>>>(p, g, m, v, p_ema, n, lr, beta1, beta2, eps, bc1, bc2, alpha,

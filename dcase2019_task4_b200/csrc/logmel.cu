@@ -309,6 +309,7 @@ static int logmel_fwd_impl(dcase_ctx* ctx, const void* wave, int is_pcm16, int B
     DCASE_REQUIRE(B >= 0 && L > kNfft / 2, "need L > 1024 samples (single reflection)");
     if (B == 0) return DCASE_OK;
     const int T = 1 + L / kHop;
+    DCASE_PROF("stft_mel", stream);
     MelTables tab{ctx->d_window, ctx->d_twiddle, ctx->d_mel_w, ctx->d_mel_start, ctx->d_mel_len, ctx->d_mel_off};
     dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
     if (is_pcm16)
@@ -335,6 +336,7 @@ int dcase_logmel_finish(dcase_ctx* ctx, const float* mel_amp, int B, int T_in, i
     DCASE_REQUIRE(B >= 0 && T_in > 0 && T_out > 0, "bad shape");
     if (B == 0) return DCASE_OK;
     const DcaseStepScalars* sc = (const DcaseStepScalars*)scalars;
+    DCASE_PROF("logmel_finish", stream);
     clip_max_kernel<<<B, 256, 0, stream>>>(mel_amp, T_in, noise, noisy != nullptr, seed, step, sc, clip_max_ws, B);
     DCASE_LAUNCH_CHECK();
     const size_t total = (size_t)B * T_out * 16;

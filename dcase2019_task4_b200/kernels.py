@@ -172,6 +172,25 @@ def adam_ema_step(p, g, m, v, p_ema, step_t, lr=1e-3, beta1=0.9, beta2=0.999, ep
                                         int(step_t), float(ema_alpha), float(grad_scale), ptr(scalars), stream_ptr()))
 
 
+def launch_count():
+    return int(lib().dcase_launch_count())
+
+
+def profile_begin():
+    check(lib().dcase_profile_begin())
+
+
+def profile_end():
+    """-> {kernel name: (launch count, total ms)} measured with CUDA events on the launching stream."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().dcase_profile_end(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split(",")
+        out[name] = (int(cnt), float(ms))
+    return out
+
+
 def mt_fwd_bwd(args):
     """One call for teacher fwd + student fwd + losses + student bwd (``args`` is a filled _lib.MtArgs)."""
     dev = torch.cuda.current_device()

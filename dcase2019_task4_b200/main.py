@@ -1,0 +1,234 @@
+"""Mean-teacher training step of the reference (``baseline/main.py:45-165``) on the B200-native kernels.
+
+``train(train_loader, model, optimizer, epoch, ema_model=None, weak_mask=None, strong_mask=None)`` keeps the
+reference signature and semantics (consistency ramp-up, weak / strong BCE on slice masks, 2x MSE consistency,
+teacher in train mode on the noisy input, Adam, EMA with alpha = min(1 - 1/(step+1), 0.999), per-batch loss
+assertions, meters).  One iteration is: ONE C-ABI call for teacher forward + student forward + losses + student
+backward (``dcase_mt_fwd_bwd``), an optional NCCL all-reduce of the flat gradient slab (data parallel), and ONE
+fused Adam + EMA launch (``dcase_adam_ema_step``) that updates ``torch.optim.Adam``'s own state tensors in place,
+so ``optimizer.state_dict()`` (saved at main.py:339) stays valid.  The reference's >= 9 ``.item()`` host syncs per
+batch become one asynchronous 32-byte copy whose assertion is checked one batch later.
+
+``main_simple_CRNN.train`` (main_simple_CRNN.py:31-82) is the same body with ``ema_model=None``.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from . import config as cfg
+from . import kernels as K
+from ._lib import MtArgs, StepScalars
+from .utils import ramps
+from .utils.utils import AverageMeterSet
+
+METER_NAMES = ["weak_class_loss", "Weak EMA loss", "Strong loss", "Strong EMA loss", "Consistency strong",
+               "Consistency weak", "Loss", "Consistency weight"]
+
+
+def update_ema_variables(model, ema_model, alpha, global_step):
+    """main.py:45-49 as one launch over the flat slabs (kept for API parity; the fused step does this itself)."""
+    alpha = min(1 - 1 / (global_step + 1), alpha)
+    with torch.no_grad():
+        ema_model.flat_parameters().mul_(alpha).add_(model.flat_parameters(), alpha=1 - alpha)
+
+
+def _bounds(mask, B):
+    if mask is None:
+        return 0, 0
+    lo, hi, st = mask.indices(B)
+    assert st == 1
+    return lo, max(lo, hi)
+
+
+class MeanTeacherEngine(object):
+    """Device-resident buffers + launch sequence of one mean-teacher iteration for a fixed batch shape."""
+
+    def __init__(self, model, optimizer, ema_model=None, weak_mask=None, strong_mask=None, batch_size=None,
+                 frames=cfg.max_frames, process_group=None):
+        self.model, self.ema_model, self.optimizer = model, ema_model, optimizer
+        self.B, self.T, self.NC = batch_size, frames, model.nclass
+        self.To = frames // cfg.pooling_time_ratio
+        self.weak_mask, self.strong_mask = weak_mask, strong_mask
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        dev = model.flat_parameters().device
+        if dev.type != "cuda":
+            raise RuntimeError("MeanTeacherEngine needs the models on a CUDA device (no CPU fallback)")
+        self.dev = dev
+        f32 = dict(device=dev, dtype=torch.float32)
+        B, To, NC = self.B, self.To, self.NC
+        self.strong_s = torch.empty(B, To, NC, **f32)
+        self.weak_s = torch.empty(B, NC, **f32)
+        self.strong_t = torch.empty(B, To, NC, **f32)
+        self.weak_t = torch.empty(B, NC, **f32)
+        self.d_strong = torch.empty(B, To, NC, **f32)
+        self.d_weak = torch.empty(B, NC, **f32)
+        self.meters = torch.zeros(8, **f32)
+        self.meters_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.meters_event = torch.cuda.Event()
+        self._pending = False
+        self.ws_s = K.new_workspace(B, frames, NC, dev)
+        self.ws_t = K.new_workspace(B, frames, NC, dev) if ema_model is not None else None
+        n = model.flat_parameters().numel()
+        self.grads = torch.zeros(n, **f32)
+        self._bind_adam_state(n)
+        self._x = torch.empty(B, frames, 64, **f32)
+        self._x_ema = torch.empty(B, frames, 64, **f32) if ema_model is not None else None
+
+    # torch.optim.Adam bookkeeping -----------------------------------------------------------------------
+    def _bind_adam_state(self, n):
+        opt = self.optimizer
+        if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
+            raise NotImplementedError("the fused step implements torch.optim.Adam with one param group (main.py:290)")
+        g = opt.param_groups[0]
+        if g.get("amsgrad") or g.get("weight_decay", 0) != 0 or g.get("maximize"):
+            raise NotImplementedError("amsgrad / weight_decay / maximize are not on the reference's path")
+        plist = self.model._param_list
+        if [id(p) for p in g["params"]] != [id(p) for p in plist]:
+            raise NotImplementedError("the optimizer must hold exactly model.parameters() in order (main.py:290)")
+        self.m = torch.zeros(n, device=self.dev)
+        self.v = torch.zeros(n, device=self.dev)
+        self._steps = []
+        for p, (off, cnt) in zip(plist, self.model._param_slices):
+            st = opt.state[p]
+            if "exp_avg" in st:
+                self.m[off:off + cnt].copy_(st["exp_avg"].reshape(-1))
+                self.v[off:off + cnt].copy_(st["exp_avg_sq"].reshape(-1))
+            if "step" not in st:
+                st["step"] = torch.tensor(0.0)
+            st["exp_avg"] = self.m[off:off + cnt].view(p.shape)
+            st["exp_avg_sq"] = self.v[off:off + cnt].view(p.shape)
+            self._steps.append(st["step"])
+
+    def _adam_step_count(self):
+        return int(self._steps[0].item()) if self._steps else 0
+
+    # one iteration ------------------------------------------------------------------------------------------
+    def step(self, batch_input, ema_batch_input, target, cons_weight, global_step_after, check=True):
+        """main.py:84-157 for one batch already on the device.  Returns nothing; meters are read asynchronously
+        (``read_meters``).  ``global_step_after`` is the reference's ``global_step`` after its increment."""
+        model, ema = self.model, self.ema_model
+        x = batch_input.contiguous()
+        xt = ema_batch_input.contiguous() if ema is not None else None
+        assert x.shape[0] == self.B and x.shape[-2] == self.T
+        wl, wh = _bounds(self.weak_mask, self.B)
+        sl, sh = _bounds(self.strong_mask, self.B)
+        flags = model.forward_flags()
+        seed, step = model.next_rng()
+        a = MtArgs()
+        a.x_student = x.data_ptr()
+        a.x_teacher = xt.data_ptr() if xt is not None else None
+        a.target = target.contiguous().data_ptr()
+        a.B, a.T, a.n_class = self.B, self.T, self.NC
+        a.weak_lo, a.weak_hi, a.strong_lo, a.strong_hi = wl, wh, sl, sh
+        a.params_s = model.flat_parameters().data_ptr()
+        a.bn_s = model.flat_bn_running().data_ptr()
+        if ema is not None:
+            a.params_t = ema.flat_parameters().data_ptr()
+            a.bn_t = ema.flat_bn_running().data_ptr()
+            a.strong_t, a.weak_t = self.strong_t.data_ptr(), self.weak_t.data_ptr()
+            a.ws_t = self.ws_t.data_ptr()
+            ema._nbt_pending += 1
+        model._nbt_pending += 1
+        a.flags, a.seed, a.step, a.cons_weight, a.scalars = flags, seed, step, float(cons_weight), None
+        a.strong_s, a.weak_s = self.strong_s.data_ptr(), self.weak_s.data_ptr()
+        a.meters, a.d_strong, a.d_weak = self.meters.data_ptr(), self.d_strong.data_ptr(), self.d_weak.data_ptr()
+        a.ws_s, a.grads = self.ws_s.data_ptr(), self.grads.data_ptr()
+        if check and self._pending:
+            self.check_loss()
+        with torch.cuda.device(self.dev):
+            K.mt_fwd_bwd(a)
+            if self.world > 1:
+                torch.distributed.all_reduce(self.grads, group=self.pg)      # flat slab, SUM; 1/N folded below
+            g = self.optimizer.param_groups[0]
+            torch._foreach_add_(self._steps, 1.0)
+            alpha = min(1 - 1 / (global_step_after + 1), 0.999)
+            K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
+                            ema.flat_parameters() if ema is not None else None, self._adam_step_count(),
+                            lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], ema_alpha=alpha,
+                            grad_scale=1.0 / self.world)
+            self.meters_host.copy_(self.meters, non_blocking=True)
+            self.meters_event.record()
+        self._pending = True
+
+    def step_from_waveforms(self, wave, target, mean, std, cons_weight, global_step_after, check=True):
+        """The whole hot path for one batch of raw clips already on the device: wave [B, L] (float32 or int16
+        PCM) -> calculate_mel_spec -> noise / dB / pad / z-score (clean + noisy) -> mean-teacher iteration."""
+        amp = K.logmel_fwd(wave)
+        seed, _ = self.model._rng_seed, 0
+        if self.ema_model is not None:
+            x, x_ema = K.logmel_finish(amp, mean, std, self.T, noisy=True, seed=seed ^ 0x5DEECE66D,
+                                       step=self.model._rng_step & 0xFFFFFFFF, out_clean=self._x, out_noisy=self._x_ema)
+        else:
+            x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None
+        self.step(x, x_ema, target, cons_weight, global_step_after, check=check)
+
+    def read_meters(self):
+        """Synchronise on the last step's 32-byte meter copy and return {name: float}."""
+        self.meters_event.synchronize()
+        vals = self.meters_host.tolist()
+        return dict(zip(METER_NAMES, vals))
+
+    def check_loss(self):
+        """The reference's per-batch assertions (main.py:147-148), applied to the last finished step."""
+        loss = self.read_meters()["Loss"]
+        self._pending = False
+        assert not (np.isnan(loss) or loss > 1e5), 'Loss explosion: {}'.format(loss)
+        assert not loss < 0, 'Loss problem, cannot be negative'
+        return loss
+
+
+def _engine_for(model, optimizer, ema_model, weak_mask, strong_mask, B, T):
+    key = (id(optimizer), id(ema_model), B, T, repr(weak_mask), repr(strong_mask))
+    cache = model.__dict__.setdefault("_mt_engines", {})
+    if key not in cache:
+        cache[key] = MeanTeacherEngine(model, optimizer, ema_model, weak_mask, strong_mask, B, T)
+    return cache[key]
+
+
+def train(train_loader, model, optimizer, epoch, ema_model=None, weak_mask=None, strong_mask=None, log=None):
+    """One epoch of a Mean Teacher model (or of the plain CRNN when ``ema_model`` is None).
+
+    train_loader yields (teacher input, student input... ) exactly as the reference: ``(batch_input,
+    ema_batch_input, target)`` with a teacher, ``(batch_input, target)`` without."""
+    meters = AverageMeterSet()
+    start = time.time()
+    rampup_length = len(train_loader) * cfg.n_epoch // 2
+    engine = None
+    for i, batch in enumerate(train_loader):
+        if ema_model is not None:
+            batch_input, ema_batch_input, target = batch
+        else:
+            (batch_input, target), ema_batch_input = batch, None
+        global_step = epoch * len(train_loader) + i
+        rampup_value = ramps.sigmoid_rampup(global_step, rampup_length) if global_step < rampup_length else 1.0
+        meters.update('lr', optimizer.param_groups[0]['lr'])
+        dev = model.flat_parameters().device
+        batch_input = batch_input.to(dev, non_blocking=True)
+        target = target.to(dev, non_blocking=True).float()
+        if ema_batch_input is not None:
+            ema_batch_input = ema_batch_input.to(dev, non_blocking=True)
+        if engine is None or engine.B != batch_input.shape[0] or engine.T != batch_input.shape[-2]:
+            engine = _engine_for(model, optimizer, ema_model, weak_mask, strong_mask, batch_input.shape[0],
+                                 batch_input.shape[-2])
+        consistency_cost = cfg.max_consistency_cost * rampup_value
+        engine.step(batch_input, ema_batch_input, target, consistency_cost, global_step + 1)
+        vals = engine.read_meters() if i == len(train_loader) - 1 else None
+        if vals is not None:
+            engine.check_loss()
+            for name in METER_NAMES:
+                if ema_model is None and ("EMA" in name or "Consistency" in name):
+                    continue
+                if weak_mask is None and name in ("weak_class_loss", "Weak EMA loss"):
+                    continue
+                if strong_mask is None and name in ("Strong loss", "Strong EMA loss"):
+                    continue
+                meters.update(name, vals[name])
+    epoch_time = time.time() - start
+    msg = 'Epoch: {}\tTime {:.2f}\t{meters}'.format(epoch, epoch_time, meters=meters)
+    (log.info if log is not None else print)(msg)
+    return meters

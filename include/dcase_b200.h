@@ -48,6 +48,14 @@ const char* dcase_last_error(void);
 int dcase_ctx_create(dcase_ctx** out, int device);
 int dcase_ctx_destroy(dcase_ctx* ctx);
 
+/* ---- measurement helpers (bench.py) -------------------------------------------------------------- */
+/* Kernel launches issued by this library since load (bench.py's "gpu_launches"). */
+unsigned long long dcase_launch_count(void);
+/* Per-kernel CUDA-event timing on the launching stream: begin, run some steps, end -> "name,count,total_ms\n"
+ * lines into buf (synchronises the device). */
+int dcase_profile_begin(void);
+int dcase_profile_end(char* buf, size_t cap);
+
 /* Per-step scalars in device memory (so a captured CUDA graph replays with new values).
  * Layout must match DcaseStepScalars in csrc/common.cuh. */
 typedef struct dcase_step_scalars {
