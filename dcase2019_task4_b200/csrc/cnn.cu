@@ -8,6 +8,7 @@
 // tap moments of the input (conv0 is linear in the 9 taps), BN is folded into the conv weights, and
 // conv0 -> BN -> GLU -> dropout -> pool is recomputed per 128-pixel tile in both passes.
 #include "cnn.cuh"
+#include "tc.cuh"
 
 namespace {
 
@@ -178,9 +179,22 @@ struct GluArgs {
 };
 
 // y row (BN output) of this thread's pixel into its smem row; L0 recomputes conv0 from the 9 taps.
-template <bool L0>
+// Row accessors: 16-byte chunk c4 (channels 4*c4 .. 4*c4+3) of a tile row.
+struct PadRow {      // [128][68] fp32, CUDA-core tiles
+    float* row;
+    __device__ __forceinline__ float4* chunk(int c4) const { return reinterpret_cast<float4*>(row + 4 * c4); }
+};
+struct Sw128Row {    // two SW128 blocks of 128 rows (tc.cuh): K-major tcgen05 operand, rows = pixels
+    unsigned char* base;
+    int r;
+    __device__ __forceinline__ float4* chunk(int c4) const {
+        return reinterpret_cast<float4*>(base + (c4 >> 3) * 16384 + tc::sw128_chunk(r, c4 & 7));
+    }
+};
+
+template <bool L0, typename RowT>
 __device__ __forceinline__ void produce_y_row(const GluArgs& a, long long p, bool valid, const float* aff_s,
-                                              const float* xs, float* a_row, float (&tap)[9]) {
+                                              const float* xs, RowT a_row, float (&tap)[9]) {
     if (L0) {
         const int tr = threadIdx.x >> 6, f = threadIdx.x & 63;
 #pragma unroll
@@ -194,7 +208,7 @@ __device__ __forceinline__ void produce_y_row(const GluArgs& a, long long p, boo
                 y.x = fmaf(w.x, tap[k], y.x); y.y = fmaf(w.y, tap[k], y.y);
                 y.z = fmaf(w.z, tap[k], y.z); y.w = fmaf(w.w, tap[k], y.w);
             }
-            *reinterpret_cast<float4*>(a_row + 4 * c4) = y;
+            *a_row.chunk(c4) = y;
         }
     } else {
         const float4* src = reinterpret_cast<const float4*>(a.src + p * 64);
@@ -208,7 +222,7 @@ __device__ __forceinline__ void produce_y_row(const GluArgs& a, long long p, boo
                 y.x = fmaf(sc.x, v.x, sh.x); y.y = fmaf(sc.y, v.y, sh.y);
                 y.z = fmaf(sc.z, v.z, sh.z); y.w = fmaf(sc.w, v.w, sh.w);
             }
-            *reinterpret_cast<float4*>(a_row + 4 * c4) = y;
+            *a_row.chunk(c4) = y;
         }
     }
 }
@@ -229,55 +243,88 @@ __device__ __forceinline__ void load_xs(const float* __restrict__ x, long long t
 // ---------------------------------------------------------------------------------------------
 // forward: [conv0 | BN apply] -> GLU -> dropout -> avg-pool (2,4)
 // ---------------------------------------------------------------------------------------------
+// smem (1024-B aligned): Wb  K-major B operand  Wg[n][k]     2 x [64][128 B]   16 KB
+//                        A   K-major A operand  y[p][k]      2 x [128][128 B]  32 KB (reused for z)
+//                        bg[64] | aff (fold0 / bn) | xs[4][66]
+// The 64x64 channel GEMM  lin = y Wg^T  runs on the tensor core (tcgen05.mma kind::tf32, fp32 accumulate in
+// TMEM, 64 columns); CUDA cores do conv0 / BN, the gate, dropout and the pooling.  Several CTAs per SM overlap
+// one CTA's MMA with the others' CUDA-core phases.
+constexpr int kGluFwdSmemBytes = 1024 + 16384 + 32768 + (64 + 832 + 4 * 66) * 4;
+
 template <bool L0>
 __global__ void __launch_bounds__(kTile)
 glu_pool_fwd_kernel(GluArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    float* Wt = smem;                 // [64 k][64 n]
-    float* bg = Wt + 4096;            // [64]
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Wb = smem;
+    unsigned char* A = smem + 16384;
+    float* bg = reinterpret_cast<float*>(smem + 16384 + 32768);
     float* aff_s = bg + 64;           // fold0 (832) or bn (256)
-    float* A = aff_s + 832;           // [128][68]
-    float* xs = A + kTile * kPitch;   // [4][66] (L0)
-    const int tid = threadIdx.x;
+    float* xs = aff_s + 832;          // [4][66] (L0)
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
 
-    for (int i = tid; i < 4096; i += kTile) Wt[(i & 63) * 64 + (i >> 6)] = __ldg(a.glu_w + i);
+    for (int i = tid; i < 4096; i += kTile) {      // Wg[n][k] -> block k/32, row n, swizzled
+        const int n = i >> 6, k = i & 63;
+        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = __ldg(a.glu_w + i);
+    }
     if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
     for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kTile) aff_s[i] = a.aff[i];
+    if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
     uint64_t seed; uint32_t step;
     resolve_rng(a.drop, seed, step);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
     __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t a_addr = tc::smem_u32(A), b_addr = tc::smem_u32(Wb);
+    uint32_t phase = 0;
 
     const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
     const long long n_out = a.n_pix >> 3;
     const int wpr = a.F >> 2;
-    float* a_row = A + tid * kPitch;
+    const Sw128Row a_row{A, tid};
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long p = tile * kTile + tid;
         const bool valid = p < a.n_pix;
         if (L0) { load_xs(a.src, tile, a.T, xs); __syncthreads(); }
         float tap[9];
         produce_y_row<L0>(a, p, valid, aff_s, xs, a_row, tap);
-        float acc[64];
-#pragma unroll
-        for (int n = 0; n < 64; ++n) acc[n] = bg[n];
-        rowmat64<64>(a_row, Wt, acc);
+        tc::fence_proxy_async();                 // y tile -> visible to the tensor core
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            tc::umma_128x64x64_kmajor(tmem, a_addr, b_addr, false);
+            tc::umma_commit(&mma_bar);
+        }
         uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
         float scale = 1.f;
-        if (a.drop.enabled) {
+        if (a.drop.enabled) {                    // overlaps the MMA
             const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
             keep_lo = r.x; keep_hi = r.y; scale = 2.f;
         }
+        tc::mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+        float acc[64];
+        tc::tmem_ld_row64(tmem, warp, 0, acc);
+        tc::fence_before_sync();
 #pragma unroll
         for (int c4 = 0; c4 < 16; ++c4) {
-            const float4 y = *reinterpret_cast<const float4*>(a_row + 4 * c4);
+            float4* slot = a_row.chunk(c4);
+            const float4 y = *slot;
+            const float4 b4 = *reinterpret_cast<const float4*>(bg + 4 * c4);
             const uint32_t bits = (c4 < 8 ? keep_lo : keep_hi) >> ((4 * c4) & 31);
             float4 z;
-            z.x = (bits & 1u) ? acc[4 * c4 + 0] * sigmoid_fast(y.x) * scale : 0.f;
-            z.y = (bits & 2u) ? acc[4 * c4 + 1] * sigmoid_fast(y.y) * scale : 0.f;
-            z.z = (bits & 4u) ? acc[4 * c4 + 2] * sigmoid_fast(y.z) * scale : 0.f;
-            z.w = (bits & 8u) ? acc[4 * c4 + 3] * sigmoid_fast(y.w) * scale : 0.f;
+            z.x = (bits & 1u) ? (acc[4 * c4 + 0] + b4.x) * sigmoid_fast(y.x) * scale : 0.f;
+            z.y = (bits & 2u) ? (acc[4 * c4 + 1] + b4.y) * sigmoid_fast(y.y) * scale : 0.f;
+            z.z = (bits & 4u) ? (acc[4 * c4 + 2] + b4.z) * sigmoid_fast(y.z) * scale : 0.f;
+            z.w = (bits & 8u) ? (acc[4 * c4 + 3] + b4.w) * sigmoid_fast(y.w) * scale : 0.f;
             if (!valid) z = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(a_row + 4 * c4) = z;
+            *slot = z;
         }
         __syncthreads();
         {   // pooling: 16 windows x 8 channel groups
@@ -289,9 +336,9 @@ glu_pool_fwd_kernel(GluArgs a) {
             for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float* row = A + (r0 + i * a.F + j) * kPitch + 8 * cg;
-                    const float4 u = *reinterpret_cast<const float4*>(row);
-                    const float4 v = *reinterpret_cast<const float4*>(row + 4);
+                    const Sw128Row row{A, r0 + i * a.F + j};
+                    const float4 u = *row.chunk(2 * cg);
+                    const float4 v = *row.chunk(2 * cg + 1);
                     s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
                     s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
                 }
@@ -304,30 +351,58 @@ glu_pool_fwd_kernel(GluArgs a) {
         }
         __syncthreads();
     }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward of [conv0 | BN apply] -> GLU -> dropout -> pool, recomputing the forward per tile
 // ---------------------------------------------------------------------------------------------
+// All five contractions of this pass run on the tensor core (tcgen05.mma kind::tf32, fp32 accumulators in TMEM):
+//   G1  lin  [p][n]  = sum_k Y[p][k]  Wg[n][k]            (recompute)            D1: cols   0.. 63, M=128
+//   G2  dY   [p][k] += sum_n DL[p][n] Wg[n][k]            (through the linear)   D2: cols  64..127, M=128
+//   G3  dWg' [n][j]  = sum_p DL[p][n] [Y | 1][p][j]       (dWg and db_g)         D3: cols 128..207, M=64, N=80
+//   G4  S    [c][j]  = sum_p dY[p][c] [1 | taps][p][j]    (dbeta; L0: conv0 dW)  D4: cols 208..223, M=64, N=16
+//   G5  C    [c][k]  = sum_p dY[p][c] Y[p][k]             (diag -> dgamma)       D5: cols 224..287, M=64 (layers 1,2)
+// G3..G5 accumulate in TMEM over all tiles of the persistent CTA and are read once at the end.  Reductions over
+// pixels need MN-major operands (SWIZZLE_128B_BASE32B for fp32), so Y / DL / dY are staged in both layouts.
+struct B32Row {      // MN-major operand blocks of 128 rows: rows = pixels (the K index), 32 channels per block
+    unsigned char* base;
+    int r;
+    __device__ __forceinline__ float4* chunk(int c4) const {
+        return reinterpret_cast<float4*>(base + (c4 >> 3) * 16384 + tc::sw128b32_chunk(r, c4 & 7));
+    }
+};
+
+constexpr int kBwdWb = 0, kBwdWm = 16384, kBwdP = 32768, kBwdQ1 = 65536, kBwdExt = 65536 + 32768, kBwdQ2 = 114688,
+              kBwdMisc = 147456;
+constexpr int kGluBwdSmemBytes = 1024 + kBwdMisc + (64 + 832 + 128 + 4 * 66) * 4;
+
 template <bool L0>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, 1)
 glu_pool_bwd_kernel(GluArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    float* Wt = smem;                 // [64 k][64 n]  Wt[k][n] = Wg[n][k]  (lin = Wg y)
-    float* Wn = Wt + 4096;            // [64 n][64 k]  natural            (d_y += Wg^T d_lin)
-    float* bg = Wn + 4096;            // [64]
-    float* aff_s = bg + 64;           // fold0 (832) or bn (256)
-    float* gb = aff_s + 832;          // [2][64]: 1/gamma, beta (layers 1,2)
-    float* A = gb + 128;              // y        [128][68]
-    float* D = A + kTile * kPitch;    // d_lin    [128][68]
-    float* E = D + kTile * kPitch;    // d_y      [128][68]
-    float* xs = E + kTile * kPitch;   // [4][66] (L0)
-    const int tid = threadIdx.x;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Wb = smem + kBwdWb;     // Wg[n][k], K-major SW128 (rows n)
+    unsigned char* Wm = smem + kBwdWm;     // Wg[n][k], MN-major B32 (rows n = K index of G2, k contiguous)
+    unsigned char* P = smem + kBwdP;       // K-major: Y, then DL
+    unsigned char* Q1 = smem + kBwdQ1;     // MN-major: Y (2 blocks) | EXT block
+    unsigned char* EXT = smem + kBwdExt;
+    unsigned char* Q2 = smem + kBwdQ2;     // MN-major: DL, then dY
+    float* bg = reinterpret_cast<float*>(smem + kBwdMisc);
+    float* aff_s = bg + 64;                // fold0 (832) or bn (256)
+    float* gb = aff_s + 832;               // [2][64]: 1/gamma, beta (layers 1,2)
+    float* xs = gb + 128;                  // [4][66] (L0)
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     for (int i = tid; i < 4096; i += kTile) {
+        const int n = i >> 6, k = i & 63;
         const float w = __ldg(a.glu_w + i);
-        Wn[i] = w;
-        Wt[(i & 63) * 64 + (i >> 6)] = w;
+        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = w;
+        *reinterpret_cast<float*>(Wm + (k >> 5) * 8192 + tc::sw128b32_chunk(n, (k & 31) >> 2) + (k & 3) * 4) = w;
     }
     if (tid < 64) {
         bg[tid] = __ldg(a.glu_b + tid);
@@ -338,122 +413,202 @@ glu_pool_bwd_kernel(GluArgs a) {
         }
     }
     for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kTile) aff_s[i] = a.aff[i];
+    {   // EXT row of this thread: [1, 0...] (L0 rewrites it with the taps every tile)
+        const B32Row ext{EXT, tid};
+        *ext.chunk(0) = make_float4(1.f, 0.f, 0.f, 0.f);
+        *ext.chunk(1) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *ext.chunk(2) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *ext.chunk(3) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     uint64_t seed; uint32_t step;
     resolve_rng(a.drop, seed, step);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
     __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t wb_a = tc::smem_u32(Wb), wm_a = tc::smem_u32(Wm), p_a = tc::smem_u32(P), q1_a = tc::smem_u32(Q1),
+                   ext_a = tc::smem_u32(EXT), q2_a = tc::smem_u32(Q2);
+    uint32_t phase = 0;
+    bool pending = false;      // G4/G5 of the previous tile still reading Q1 / Q2
+    bool first = true;
 
     const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
     const int wpr = a.F >> 2;
-    float* a_row = A + tid * kPitch;
-    float* d_row = D + tid * kPitch;
-    float* e_row = E + tid * kPitch;
-
-    // persistent partial sums
-    float accW[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) accW[i] = 0.f;
-    float cs0 = 0.f, cs1 = 0.f;   // tid < 64: db_glu, S1 ; tid >= 64: S2 (layers 1,2)
-    float cg[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // L0: G[c][taps]
-    const int nb = tid >> 3, kb = tid & 7;
-    const int cc = tid & 63;
+    const Sw128Row p_row{P, tid};
+    const B32Row y32_row{Q1, tid}, q2_row{Q2, tid}, ext_row{EXT, tid};
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long p = tile * kTile + tid;
         const bool valid = p < a.n_pix;
-        if (L0) { load_xs(a.src, tile, a.T, xs); __syncthreads(); }
+        if (L0) { load_xs(a.src, tile, a.T, xs); }
+        if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; pending = false; }
+        if (L0) __syncthreads();
         float tap[9];
-        produce_y_row<L0>(a, p, valid, aff_s, xs, a_row, tap);
-        float acc[64];
+        produce_y_row<L0>(a, p, valid, aff_s, xs, p_row, tap);
 #pragma unroll
-        for (int n = 0; n < 64; ++n) acc[n] = bg[n];
-        rowmat64<64>(a_row, Wt, acc);                 // lin
-        uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
-        float scale = 0.125f;
-        if (a.drop.enabled) {
-            const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
-            keep_lo = r.x; keep_hi = r.y; scale = 0.25f;
+        for (int c4 = 0; c4 < 16; ++c4) *y32_row.chunk(c4) = *p_row.chunk(c4);
+        if (L0) {
+            *ext_row.chunk(0) = make_float4(1.f, tap[0], tap[1], tap[2]);
+            *ext_row.chunk(1) = make_float4(tap[3], tap[4], tap[5], tap[6]);
+            *ext_row.chunk(2) = make_float4(tap[7], tap[8], 0.f, 0.f);
         }
-        {   // window of this pixel inside the tile -> pooled pixel index
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            tc::umma_128x64x64_kmajor(tmem, p_a, wb_a, false);            // G1
+            tc::umma_commit(&mma_bar);
+        }
+        // pooled-output gradient of this pixel's window, dropout mask and 1/8 folded in (overlaps G1)
+        float dz[64];
+        {
+            uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+            float scale = 0.125f;
+            if (a.drop.enabled) {
+                const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
+                keep_lo = r.x; keep_hi = r.y; scale = 0.25f;
+            }
             const int tr = tid / a.F, f = tid - tr * a.F;
             const long long op = tile * 16 + (tr >> 1) * wpr + (f >> 2);
             const float4* dsrc = reinterpret_cast<const float4*>(a.d_out + op * 64);
 #pragma unroll
             for (int c4 = 0; c4 < 16; ++c4) {
-                float4 dz = valid ? __ldg(dsrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 d = valid ? __ldg(dsrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const uint32_t bits = (c4 < 8 ? keep_lo : keep_hi) >> ((4 * c4) & 31);
-                dz.x = (bits & 1u) ? dz.x * scale : 0.f;
-                dz.y = (bits & 2u) ? dz.y * scale : 0.f;
-                dz.z = (bits & 4u) ? dz.z * scale : 0.f;
-                dz.w = (bits & 8u) ? dz.w * scale : 0.f;
-                const float4 y = *reinterpret_cast<const float4*>(a_row + 4 * c4);
-                const float gx = sigmoid_fast(y.x), gy = sigmoid_fast(y.y), gz = sigmoid_fast(y.z), gw = sigmoid_fast(y.w);
-                *reinterpret_cast<float4*>(d_row + 4 * c4) = make_float4(dz.x * gx, dz.y * gy, dz.z * gz, dz.w * gw);
-                // direct path through the gate: dz * lin * g * (1 - g)
-                acc[4 * c4 + 0] = dz.x * acc[4 * c4 + 0] * gx * (1.f - gx);
-                acc[4 * c4 + 1] = dz.y * acc[4 * c4 + 1] * gy * (1.f - gy);
-                acc[4 * c4 + 2] = dz.z * acc[4 * c4 + 2] * gz * (1.f - gz);
-                acc[4 * c4 + 3] = dz.w * acc[4 * c4 + 3] * gw * (1.f - gw);
+                dz[4 * c4 + 0] = (bits & 1u) ? d.x * scale : 0.f;
+                dz[4 * c4 + 1] = (bits & 2u) ? d.y * scale : 0.f;
+                dz[4 * c4 + 2] = (bits & 4u) ? d.z * scale : 0.f;
+                dz[4 * c4 + 3] = (bits & 8u) ? d.w * scale : 0.f;
             }
         }
-        rowmat64<64>(d_row, Wn, acc);                 // + Wg^T d_lin  -> d_y
+        tc::mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+        float acc[64];
+        tc::tmem_ld_row64(tmem, warp, 0, acc);                                // lin (without bias)
 #pragma unroll
         for (int c4 = 0; c4 < 16; ++c4) {
-            const float4 v = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-            *reinterpret_cast<float4*>(e_row + 4 * c4) = v;
-            if (!L0 && valid) reinterpret_cast<float4*>(a.d_y + p * 64)[c4] = v;
+            float4* slot = p_row.chunk(c4);
+            const float4 y = *slot;
+            const float4 b4 = *reinterpret_cast<const float4*>(bg + 4 * c4);
+            const float gx = sigmoid_fast(y.x), gy = sigmoid_fast(y.y), gz = sigmoid_fast(y.z), gw = sigmoid_fast(y.w);
+            const float4 dl = make_float4(dz[4 * c4] * gx, dz[4 * c4 + 1] * gy, dz[4 * c4 + 2] * gz, dz[4 * c4 + 3] * gw);
+            *slot = dl;                       // P: Y -> DL (G1 has completed)
+            *q2_row.chunk(c4) = dl;
+            // direct path through the gate: dz * lin * g * (1 - g)
+            acc[4 * c4 + 0] = dz[4 * c4 + 0] * (acc[4 * c4 + 0] + b4.x) * gx * (1.f - gx);
+            acc[4 * c4 + 1] = dz[4 * c4 + 1] * (acc[4 * c4 + 1] + b4.y) * gy * (1.f - gy);
+            acc[4 * c4 + 2] = dz[4 * c4 + 2] * (acc[4 * c4 + 2] + b4.z) * gz * (1.f - gz);
+            acc[4 * c4 + 3] = dz[4 * c4 + 3] * (acc[4 * c4 + 3] + b4.w) * gw * (1.f - gw);
         }
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
         __syncthreads();
-        // dWg[n][k] += sum_p d_lin[p][n] * y[p][k]
-#pragma unroll 4
-        for (int q = 0; q < kTile; ++q) {
-            const float4 d4 = *reinterpret_cast<const float4*>(D + q * kPitch + 4 * nb);
-            const float4 y0 = *reinterpret_cast<const float4*>(A + q * kPitch + 8 * kb);
-            const float4 y1 = *reinterpret_cast<const float4*>(A + q * kPitch + 8 * kb + 4);
-            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-            const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+        if (tid == 0) {
+            tc::fence_after_sync();
+            {   // G2: D2[p][k] = sum_n DL[p][n] Wg[n][k];  A K-major (P), B MN-major (Wm)
+                constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 1);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) accW[i * 8 + j] = fmaf(dv[i], yv[j], accW[i * 8 + j]);
-        }
-        // column sums
-        if (tid < 64) {
-            for (int q = 0; q < kTile; ++q) {
-                cs0 += D[q * kPitch + cc];
-                const float e = E[q * kPitch + cc];
-                cs1 += e;
-                if (L0) {
-                    const float* xr = xs + (q >> 6) * 66 + (q & 63);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) cg[k] = fmaf(e, xr[(k / 3) * 66 + (k % 3)], cg[k]);
-                }
+                for (int j = 0; j < 8; ++j)
+                    tc::umma_tf32(tmem + 64, tc::smem_desc_sw128(p_a + (j >> 2) * 16384 + (j & 3) * 32, 16, 1024),
+                                  tc::smem_desc(wm_a + j * 1024, 8192, 512, 1), idesc, j > 0 ? 1u : 0u);
             }
-        } else {
-            for (int q = 0; q < kTile; ++q) {
-                const float e = E[q * kPitch + cc];
-                if (L0) {
-                    const float* xr = xs + (q >> 6) * 66 + (q & 63);
+            {   // G3: D3[n][j] (+)= sum_p DL[p][n] [Y | EXT][p][j]
+                constexpr uint32_t idesc = tc::idesc_tf32(64, 80, 1, 1);
 #pragma unroll
-                    for (int k = 5; k < 9; ++k) cg[k - 5] = fmaf(e, xr[(k / 3) * 66 + (k % 3)], cg[k - 5]);
+                for (int j = 0; j < 16; ++j)
+                    tc::umma_tf32(tmem + 128, tc::smem_desc(q2_a + j * 1024, 16384, 512, 1),
+                                  tc::smem_desc(q1_a + j * 1024, 16384, 512, 1), idesc, (!first || j > 0) ? 1u : 0u);
+            }
+            tc::umma_commit(&mma_bar);
+        }
+        tc::mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+        {
+            float d2[64];
+            tc::tmem_ld_row64(tmem, warp, 64, d2);
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const float4 v = make_float4(acc[4 * c4] + d2[4 * c4], acc[4 * c4 + 1] + d2[4 * c4 + 1],
+                                             acc[4 * c4 + 2] + d2[4 * c4 + 2], acc[4 * c4 + 3] + d2[4 * c4 + 3]);
+                *q2_row.chunk(c4) = v;        // Q2: DL -> dY (G3 has completed)
+                if (!L0 && valid) reinterpret_cast<float4*>(a.d_y + p * 64)[c4] = v;
+            }
+        }
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            {   // G4: D4[c][j] (+)= sum_p dY[p][c] EXT[p][j]
+                constexpr uint32_t idesc = tc::idesc_tf32(64, 16, 1, 1);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    tc::umma_tf32(tmem + 208, tc::smem_desc(q2_a + j * 1024, 16384, 512, 1),
+                                  tc::smem_desc(ext_a + j * 1024, 16384, 512, 1), idesc, (!first || j > 0) ? 1u : 0u);
+            }
+            if (!L0) {   // G5: D5[c][k] (+)= sum_p dY[p][c] Y[p][k]
+                constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 1, 1);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    tc::umma_tf32(tmem + 224, tc::smem_desc(q2_a + j * 1024, 16384, 512, 1),
+                                  tc::smem_desc(q1_a + j * 1024, 16384, 512, 1), idesc, (!first || j > 0) ? 1u : 0u);
+            }
+            tc::umma_commit(&mma_bar);
+        }
+        pending = true;
+        first = false;
+    }
+    if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; }
+    tc::fence_after_sync();
+    if (!first) {
+        // accumulator row m of an M=64 MMA lives in TMEM lane 32*(m/16) + m%16: warp w, lanes 0..15 -> m = 16w + lane
+        const int m = 16 * warp + lane;
+        const bool own = lane < 16;
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+        float v[16];
+#pragma unroll 1
+        for (int j0 = 0; j0 < 80; j0 += 16) {
+            tc::tmem_ld16(tbase + 128 + j0, v);
+            tc::tmem_ld_wait();
+            if (own) {
+                if (j0 < 64) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(a.g_glu_w + m * 64 + j0 + j, v[j]);
                 } else {
-                    cs0 = fmaf(e, (A[q * kPitch + cc] - gb[64 + cc]) * gb[cc], cs0);   // d_y * xhat
+                    atomicAdd(a.g_glu_b + m, v[0]);
                 }
             }
         }
-        __syncthreads();
-    }
+        tc::tmem_ld16(tbase + 208, v);
+        tc::tmem_ld_wait();
+        const float s1 = v[0];
+        if (own) {
+            atomicAdd(a.stat_acc + m, s1);                                   // S1 = sum dY
+            if (L0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+                for (int k = 0; k < 9; ++k) atomicAdd(a.stat_acc + 64 + m * 9 + k, v[1 + k]);
+            }
+        }
+        if (!L0) {
+            float diag = 0.f;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 64; j0 += 16) {
+                tc::tmem_ld16(tbase + 224 + j0, v);
+                tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(a.g_glu_w + (4 * nb + i) * 64 + 8 * kb + j, accW[i * 8 + j]);
-    if (tid < 64) {
-        atomicAdd(a.g_glu_b + cc, cs0);
-        atomicAdd(a.stat_acc + cc, cs1);                       // S1
-        if (L0) for (int k = 0; k < 5; ++k) atomicAdd(a.stat_acc + 64 + cc * 9 + k, cg[k]);
-    } else {
-        if (L0) { for (int k = 5; k < 9; ++k) atomicAdd(a.stat_acc + 64 + cc * 9 + k, cg[k - 5]); }
-        else atomicAdd(a.stat_acc + 64 + cc, cs0);             // S2
+                for (int j = 0; j < 16; ++j) diag = (j0 + j == m) ? v[j] : diag;
+            }
+            if (own) atomicAdd(a.stat_acc + 64 + m, (diag - gb[64 + m] * s1) * gb[m]);   // S2 = sum dY * xhat
+        }
     }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -641,8 +796,8 @@ __global__ void cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long lo
     }
 }
 
-constexpr size_t kGluFwdSmem = (4096 + 64 + 832 + kTile * kPitch + 4 * 66) * sizeof(float);
-constexpr size_t kGluBwdSmem = (2 * 4096 + 64 + 832 + 128 + 3 * kTile * kPitch + 4 * 66) * sizeof(float);
+constexpr size_t kGluFwdSmem = kGluFwdSmemBytes;
+constexpr size_t kGluBwdSmem = kGluBwdSmemBytes;
 constexpr size_t kWgradSmem = 2 * kTile * kPitch * sizeof(float);
 size_t conv_smem_bytes(int F) { return (size_t)(9 * 4096 + (kTile / F + 2) * (F + 2) * kPitch) * sizeof(float); }
 

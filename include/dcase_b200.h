@@ -56,6 +56,11 @@ unsigned long long dcase_launch_count(void);
 int dcase_profile_begin(void);
 int dcase_profile_end(char* buf, size_t cap);
 
+/* Self-test of the tcgen05 / TMEM primitives (csrc/tc.cuh).  mode 0: D[128][64] = A[128][64] * B[64][64]^T with
+ * K-major operands; mode 1: raw TMEM dump [128 lanes][64 columns] of D[m][n] = sum_p A[p][m] * B[p][n], p < 128,
+ * with MN-major operands and M = 64. */
+int dcase_selftest_umma(dcase_ctx* ctx, int mode, const float* A, const float* B, float* D, void* stream);
+
 /* Per-step scalars in device memory (so a captured CUDA graph replays with new values).
  * Layout must match DcaseStepScalars in csrc/common.cuh. */
 typedef struct dcase_step_scalars {

@@ -1,0 +1,155 @@
+"""Drop-in boundary on the GPU: the reference's Python surface (models.CRNN.CRNN, utils.get_transforms,
+main.train, torch.optim.Adam state) driven the way baseline/main.py drives it, checked against the oracle."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn as ocrnn
+from oracle import mel as omel
+from oracle import philox
+from oracle import train_step as otrain
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg(cuda_device):
+    import dcase2019_task4_b200.config as cfg
+    from dcase2019_task4_b200 import main as bmain
+    from dcase2019_task4_b200.models.CRNN import CRNN
+    from dcase2019_task4_b200.utils.utils import get_transforms, weights_init
+    from dcase2019_task4_b200.utils.Scaler import Scaler
+    return dict(cfg=cfg, main=bmain, CRNN=CRNN, get_transforms=get_transforms, weights_init=weights_init,
+                Scaler=Scaler)
+
+
+def _load(model, p):
+    with torch.no_grad():
+        for k, v in model.named_parameters():
+            v.copy_(p[k].to(v.device))
+
+
+def test_module_surface_and_autograd(pkg, cuda_device):
+    cfg, CRNN = pkg["cfg"], pkg["CRNN"]
+    model = CRNN(**cfg.crnn_kwargs)
+    model.apply(pkg["weights_init"])                       # main.py:282
+    assert [k for k, _ in model.named_parameters()] == list(ocrnn.param_shapes(10).keys())
+    model = model.cuda()
+    flat = model.flat_parameters()
+    assert all(p.is_cuda and p.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+               for p in model.parameters())
+    p = ocrnn.init_params(seed=21)
+    _load(model, p)
+    x = torch.randn(3, 1, 64, 64)
+    # eval mode, batch 1 as evaluation_measures.py:207
+    model.eval()
+    with torch.no_grad():
+        s1, _ = model(x[:1].cuda())
+        s_ref, _ = ocrnn.crnn_forward(x[:1], p, ocrnn.init_buffers(), training=False)
+    assert H.maxerr(s1.cpu(), s_ref) <= 1e-3
+    # train mode with dropout=0 kwargs: autograd through the fused Function vs torch autograd on the oracle
+    kw = dict(cfg.crnn_kwargs)
+    kw["dropout"] = 0
+    m2 = CRNN(**kw).cuda().train()
+    _load(m2, p)
+    strong, weak = m2(x.cuda())
+    loss = (strong ** 2).mean() + weak.sum()
+    loss.backward()
+    sp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    s_ref, w_ref = ocrnn.crnn_forward(x, sp, ocrnn.init_buffers(), training=True)
+    gref = torch.autograd.grad((s_ref ** 2).mean() + w_ref.sum(), list(sp.values()))
+    for (k, v), gr in zip(m2.named_parameters(), gref):
+        if ".conv" in k and k.endswith("bias"):
+            continue
+        assert H.maxerr(v.grad.cpu(), gr) <= 2e-3 * max(float(gr.abs().max()), 1e-12), k
+    # torch's own optimizer works on the views, checkpoint keeps the nested reference format
+    opt = torch.optim.Adam(filter(lambda q: q.requires_grad, m2.parameters()), lr=0.001, betas=(0.9, 0.999))
+    before = m2.flat_parameters().clone()
+    opt.step()
+    assert not torch.equal(before, m2.flat_parameters())
+    sd = m2.state_dict()
+    assert set(sd.keys()) == {"cnn", "rnn", "dense"} and len(sd["cnn"]) == 27 and len(sd["rnn"]) == 16
+    assert int(sd["cnn"]["batchnorm0.num_batches_tracked"]) == 1
+    m3 = CRNN(**kw).cuda()
+    m3.load(parameters=sd)
+    assert torch.equal(m3.cnn.cnn.conv1.weight, m2.cnn.cnn.conv1.weight)
+
+
+def test_get_transforms_per_sample_matches_oracle(pkg, cuda_device):
+    Scaler = pkg["Scaler"]
+    rng = np.random.default_rng(0)
+    feats = np.abs(rng.normal(0, 1, (87, 64))).astype(np.float32) * 30
+    sc = Scaler()
+    sc.load_state_dict({"mean_": rng.normal(-5, 2, 64).tolist(),
+                        "mean_of_square_": (rng.uniform(150, 300, 64)).tolist()})
+    label = np.zeros((108, 10))
+    label[3:9, 2] = 1
+    tf = pkg["get_transforms"](864, sc, augment_type="noise")
+    x, x_noisy, y = tf((feats, label))
+    assert tuple(x.shape) == (1, 864, 64) and tuple(x_noisy.shape) == (1, 864, 64) and y.dtype == torch.float32
+    ref = omel.transform_chain(feats, sc.mean_, sc.std_, frames=864)[0]
+    assert np.abs(x.cpu().numpy() - ref).max() <= 2e-5
+    nz = philox.teacher_noise(87, tf._seed, 0)
+    refn = omel.transform_chain(feats, sc.mean_, sc.std_, noise=nz.astype(np.float64), frames=864)[1]
+    assert np.abs(x_noisy.cpu().numpy() - refn).max() <= 1e-4
+    # validation transform (no noise, no scaler) returns [x, label]
+    out = pkg["get_transforms"](864)((feats, label))
+    assert len(out) == 2 and tuple(out[0].shape) == (1, 864, 64)
+
+
+class _Loader(list):
+    pass
+
+
+def test_train_three_steps_match_oracle(pkg, cuda_device):
+    """main.train on a 3-batch loader vs the restated loop body: Adam state, EMA alpha schedule (0.5 first),
+    BN running statistics and the meters.  dropout=0 so no mask injection is needed here."""
+    cfg, CRNN, bmain = pkg["cfg"], pkg["CRNN"], pkg["main"]
+    kw = dict(cfg.crnn_kwargs)
+    kw["dropout"] = 0
+    B, T = 8, 64
+    ps, pt = ocrnn.init_params(seed=31), ocrnn.init_params(seed=32)
+    student, teacher = CRNN(**kw), CRNN(**kw)
+    _load(student, ps)
+    _load(teacher, pt)
+    for q in teacher.parameters():
+        q.detach_()
+    student, teacher = student.train().cuda(), teacher.train().cuda()
+    opt = torch.optim.Adam(filter(lambda q: q.requires_grad, student.parameters()), lr=0.001, betas=(0.9, 0.999))
+    g = torch.Generator().manual_seed(5)
+    batches = _Loader()
+    for _ in range(3):
+        x = torch.randn(B, 1, T, 64, generator=g)
+        xe = x + 0.1 * torch.randn(B, 1, T, 64, generator=g)
+        tgt = (torch.rand(B, T // 8, 10, generator=g) < 0.2).float()
+        tgt[2:6] = -1
+        batches.append((x, xe, tgt))
+    wm, sm = slice(2), slice(6, 8)
+    meters = bmain.train(batches, student, opt, 0, ema_model=teacher, weak_mask=wm, strong_mask=sm)
+
+    sbuf, tbuf = ocrnn.init_buffers(), ocrnn.init_buffers()
+    adam = otrain.new_adam_state(ps)
+    last = None
+    for i, (x, xe, tgt) in enumerate(batches):
+        last, _ = otrain.train_batch(ps, sbuf, adam, x, tgt, i, len(batches), teacher_p=pt, teacher_buf=tbuf,
+                                     x_ema=xe, weak_mask=wm, strong_mask=sm)
+    got_s = {k: v.detach().cpu() for k, v in student.named_parameters()}
+    got_t = {k: v.detach().cpu() for k, v in teacher.named_parameters()}
+    for k in ps:
+        if ".conv" in k and k.endswith("bias"):
+            continue      # zero gradient behind BatchNorm: torch feeds Adam rounding noise, we feed exact zeros
+        assert H.maxerr(got_s[k], ps[k]) <= 2e-5, k          # 3 Adam steps of lr 1e-3
+        assert H.maxerr(got_t[k], pt[k]) <= 2e-5, k
+    for i in range(3):
+        for nm in ("running_mean", "running_var"):
+            a = getattr(getattr(student.cnn.cnn, f"batchnorm{i}"), nm).cpu()
+            assert H.maxerr(a, sbuf[f"cnn.cnn.batchnorm{i}.{nm}"]) <= 1e-4
+    st = opt.state_dict()["state"]
+    assert len(st) == 38 and float(st[0]["step"]) == 3.0
+    assert H.maxerr(st[0]["exp_avg"].cpu(), adam["exp_avg"]["cnn.cnn.conv0.weight"]) <= 1e-6
+    for name in ("Loss", "Strong loss", "weak_class_loss", "Consistency strong", "Consistency weak"):
+        assert abs(meters[name].val - last[name]) <= 1e-4 * max(1.0, abs(last[name])), name
+    assert int(student.state_dict()["cnn"]["batchnorm2.num_batches_tracked"]) == 3

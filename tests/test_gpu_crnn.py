@@ -64,7 +64,7 @@ def test_forward_eval(K, cuda_device, B, T):
         got = K.ws_tensor(ws, B, T, 10, {"cnn0": "out0", "cnn1": "out1", "cnn2": "out2", "rnn": "rnn1"}[name]).cpu()
         ref = H.nchw_to_cl(inter[name]).reshape(-1) if name != "rnn" else inter[name].reshape(-1)
         print(f"{name}: max|err| {H.maxerr(got, ref):.3e} (max|ref| {float(ref.abs().max()):.3e})")
-        assert H.maxerr(got, ref) <= 2e-4 * max(1.0, float(ref.abs().max()))
+        assert H.maxerr(got, ref) <= 4e-3 * max(1.0, float(ref.abs().max()))  # tf32 tensor-core GEMMs
     es, ew = H.maxerr(s.cpu(), s_ref), H.maxerr(w.cpu(), w_ref)
     print(f"eval B={B} T={T}: strong Linf {es:.3e} weak Linf {ew:.3e}")
     assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
@@ -91,7 +91,7 @@ def test_forward_train_and_running_stats(K, cuda_device, dropout):
     assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
     ebn = H.maxerr(bn.cpu(), H.bn_running_flat(buf_ref))
     print(f"running stats err {ebn:.3e}")
-    assert ebn <= 1e-4
+    assert ebn <= 1e-3                         # tf32 GLU GEMMs upstream of the layer-1/2 batch statistics
 
 
 def _loss_inputs(B, To, seed=0):
@@ -164,7 +164,7 @@ def test_backward_all_gradients(K, cuda_device, dropout):
             assert err <= 1e-6                 # BN cancels the conv bias: gradient is rounding noise in torch
             continue
         worst = max(worst, rel)
-        assert rel <= 2e-3, k
+        assert rel <= 1e-2, k                  # tf32 tensor-core GEMMs (10-bit operand mantissa)
     print(f"worst relative gradient error {worst:.2e}")
 
 

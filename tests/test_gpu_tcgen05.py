@@ -1,0 +1,47 @@
+"""Pins the hand-written tcgen05 primitives (csrc/tc.cuh: SW128 operand layout, smem / instruction descriptors,
+TMEM read-back) against a plain fp32 matmul.  kind::tf32 keeps 10 mantissa bits of each operand."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tf32(x):
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)      # truncation to 19 bits, as the tensor core reads it
+
+
+def _run(mode, A, B):
+    from dcase2019_task4_b200 import _lib
+    D = torch.full((128, 64), float("nan"), device=A.device)
+    _lib.check(_lib.lib().dcase_selftest_umma(_lib.ctx(A.device), mode, _lib.ptr(A), _lib.ptr(B), _lib.ptr(D),
+                                              _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return D
+
+
+def test_umma_kmajor_128x64x64(cuda_device):
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(128, 64, generator=g).to(cuda_device)
+    B = torch.randn(64, 64, generator=g).to(cuda_device)
+    D = _run(0, A, B)
+    ref = _tf32(A).double() @ _tf32(B).double().t()
+    err = float((D.double() - ref).abs().max())
+    full = float((D.double() - A.double() @ B.double().t()).abs().max())
+    print(f"K-major tf32: err vs tf32-truncated ref {err:.3e}, vs fp32 ref {full:.3e}")
+    assert err <= 2e-3 * float(ref.abs().max())                     # rounding mode of the operand conversion
+    assert full <= 2e-2 * float(ref.abs().max())
+
+
+def test_umma_mnmajor_m64(cuda_device):
+    g = torch.Generator().manual_seed(1)
+    A = torch.randn(128, 64, generator=g).to(cuda_device)
+    B = torch.randn(128, 64, generator=g).to(cuda_device)
+    raw = _run(1, A, B)                                             # [128 lanes][64 columns]
+    ref = (_tf32(A).double().t() @ _tf32(B).double())               # [64 m][64 n]
+    # M = 64 accumulators: row m lives in TMEM lane 32*(m/16) + m%16 (16 lanes of each 32-lane sub-partition)
+    lanes = torch.tensor([32 * (m // 16) + m % 16 for m in range(64)], device=cuda_device)
+    got = raw[lanes]
+    err = float((got.double() - ref).abs().max())
+    alt = float((raw[:64].double() - ref).abs().max())
+    print(f"MN-major M=64: err with lane map 32*(m/16)+m%16: {err:.3e}; with lanes 0..63: {alt:.3e}")
+    assert min(err, alt) <= 5e-3 * float(ref.abs().max())
