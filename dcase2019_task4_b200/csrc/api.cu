@@ -221,6 +221,7 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     ctx->num_sms = prop.multiProcessorCount;
     int rc = dcase_logmel_tables_create(ctx);
     if (rc == DCASE_OK) rc = cnn_kernels_init();
+    if (rc == DCASE_OK) rc = conv_tc_kernels_init();
     if (rc == DCASE_OK) rc = head_kernels_init();
     if (rc != DCASE_OK) { delete ctx; return rc; }
     *out = ctx;
@@ -295,7 +296,7 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
         float* bn = wsp<float>(ws, L, names[l][4]);
         float* out = wsp<float>(ws, L, names[l][5]);
         DCASE_TRY(launch_conv_w_prep(params + o.conv_w[l], wf, wd, s));
-        DCASE_TRY(launch_conv3x3(in, n_rows, T_l, F_l, wf, params + o.conv_b[l], ypre, training ? stats : nullptr, sms, s));
+        DCASE_TRY(launch_conv3x3(in, B, T_l, F_l, wf, params + o.conv_b[l], ypre, training ? stats : nullptr, sms, s));
         DCASE_TRY(launch_bn_finalize(stats, n_pix, params + o.bn_w[l], params + o.bn_b[l], bn_running + l * 128,
                                      training, bn, s));
         DCASE_TRY(launch_glu_pool_fwd(ypre, n_pix, F_l, bn, params + o.glu_w[l], params + o.glu_b[l], drop(l), out, sms, s));
@@ -421,8 +422,8 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
                                       grads + o.glu_b[l], sms, s));
         DCASE_TRY(launch_bn_bwd_apply(dy, ypre, n_pix, bn, params + o.bn_w[l], s12, grads + o.bn_w[l],
                                       grads + o.bn_b[l], grads + o.conv_b[l], sms, s));
-        DCASE_TRY(launch_conv_wgrad(dy, lin, n_rows, T_l, F_l, grads + o.conv_w[l], sms, s));
-        DCASE_TRY(launch_conv3x3(dy, n_rows, T_l, F_l, wd, nullptr, d_in, nullptr, sms, s));
+        DCASE_TRY(launch_conv_wgrad(dy, lin, B, T_l, F_l, grads + o.conv_w[l], sms, s));
+        DCASE_TRY(launch_conv3x3(dy, B, T_l, F_l, wd, nullptr, d_in, nullptr, sms, s));
     }
 
     // ---- CNN block 0 ----

@@ -12,34 +12,9 @@
 
 namespace {
 
-constexpr int kC = 64;
-constexpr int kPitch = 68;   // smem row pitch (floats): conflict-free 128-bit row access
 constexpr int kTile = 128;   // pixels per tile = threads per CTA
 constexpr float kBnEps = 1e-3f;
 constexpr float kBnMomentum = 0.99f;
-
-// acc[n] += sum_k a_row[k] * W[k * 64 + n];  a_row (own smem row) and W (smem, broadcast reads).
-template <int K>
-__device__ __forceinline__ void rowmat64(const float* __restrict__ a_row, const float* __restrict__ W,
-                                         float (&acc)[64]) {
-#pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += 4) {
-        const float4 a4 = *reinterpret_cast<const float4*>(a_row + k0);
-        const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const float4* wrow = reinterpret_cast<const float4*>(W + (k0 + kk) * 64);
-#pragma unroll
-            for (int n4 = 0; n4 < 16; ++n4) {
-                const float4 w = wrow[n4];
-                acc[4 * n4 + 0] = fmaf(av[kk], w.x, acc[4 * n4 + 0]);
-                acc[4 * n4 + 1] = fmaf(av[kk], w.y, acc[4 * n4 + 1]);
-                acc[4 * n4 + 2] = fmaf(av[kk], w.z, acc[4 * n4 + 2]);
-                acc[4 * n4 + 3] = fmaf(av[kk], w.w, acc[4 * n4 + 3]);
-            }
-        }
-    }
-}
 
 __device__ __forceinline__ void resolve_rng(const DropoutCfg& d, uint64_t& seed, uint32_t& step) {
     seed = d.seed; step = d.step;
@@ -180,10 +155,6 @@ struct GluArgs {
 
 // y row (BN output) of this thread's pixel into its smem row; L0 recomputes conv0 from the 9 taps.
 // Row accessors: 16-byte chunk c4 (channels 4*c4 .. 4*c4+3) of a tile row.
-struct PadRow {      // [128][68] fp32, CUDA-core tiles
-    float* row;
-    __device__ __forceinline__ float4* chunk(int c4) const { return reinterpret_cast<float4*>(row + 4 * c4); }
-};
 struct Sw128Row {    // two SW128 blocks of 128 rows (tc.cuh): K-major tcgen05 operand, rows = pixels
     unsigned char* base;
     int r;
@@ -611,87 +582,6 @@ glu_pool_bwd_kernel(GluArgs a) {
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
-// ---------------------------------------------------------------------------------------------
-// conv3x3, 64 -> 64 channels, stride 1, pad 1 (CNN.py:46-47), implicit GEMM on the tile's halo.
-// Also used as the data-gradient pass with mirrored / transposed weights.
-// ---------------------------------------------------------------------------------------------
-__global__ void conv_w_prep_kernel(const float* __restrict__ w, float* __restrict__ w_fwd,
-                                   float* __restrict__ w_dgrad) {
-    // w [n][c][tap]; w_fwd [tap][c][n]; w_dgrad [tap'][n][c] with tap' = 8 - tap
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * 64 * 9; i += gridDim.x * blockDim.x) {
-        const int tap = i % 9, c = (i / 9) & 63, n = i / 576;
-        const float v = __ldg(w + i);
-        w_fwd[tap * 4096 + c * 64 + n] = v;
-        w_dgrad[(8 - tap) * 4096 + n * 64 + c] = v;
-    }
-}
-
-template <bool STATS>
-__global__ void __launch_bounds__(kTile, 1)
-conv3x3_kernel(const float* __restrict__ in, int n_rows, int T_l, int F, const float* __restrict__ w_prep,
-               const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats) {
-    extern __shared__ __align__(16) float smem[];
-    float* Wc = smem;                   // [9][64][64]
-    float* halo = Wc + 9 * 4096;        // [(TR+2)*(F+2)][68]
-    const int tid = threadIdx.x;
-    const int TR = kTile / F;
-    const int HW = F + 2;
-    const int HP = (TR + 2) * HW;
-    for (int i = tid; i < 9 * 1024; i += kTile)
-        reinterpret_cast<float4*>(Wc)[i] = __ldg(reinterpret_cast<const float4*>(w_prep) + i);
-    const int tr = tid / F, f = tid - tr * F;
-    double stat_acc = 0.0;
-    const int n_tiles = (n_rows + TR - 1) / TR;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int R0 = tile * TR;
-        for (int i = tid; i < HP * 16; i += kTile) {
-            const int hp = i >> 4, q = i & 15;
-            const int hr = hp / HW, hc = hp - hr * HW;
-            const int R = R0 - 1 + hr, ff = hc - 1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (R >= 0 && R < n_rows && ff >= 0 && ff < F)
-                v = __ldg(reinterpret_cast<const float4*>(in) + ((long long)R * F + ff) * 16 + q);
-            reinterpret_cast<float4*>(halo)[hp * 17 + q] = v;
-        }
-        __syncthreads();
-        const int R = R0 + tr;
-        const bool rvalid = R < n_rows;
-        const int t = R % T_l;
-        float acc[64];
-#pragma unroll
-        for (int n = 0; n < 64; ++n) acc[n] = bias ? __ldg(bias + n) : 0.f;
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const bool ok = rvalid && (dy == 0 || (dy < 0 ? t > 0 : t < T_l - 1));
-            if (ok) rowmat64<64>(halo + ((tr + 1 + dy) * HW + f + 1 + dx) * kPitch, Wc + tap * 4096, acc);
-        }
-        if (rvalid) {
-            float4* dst = reinterpret_cast<float4*>(out + ((long long)R * F + f) * 64);
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4)
-                dst[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-        }
-        __syncthreads();
-        if (STATS) {
-            float* tile_s = halo;   // [128][68], reuses the halo buffer
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4)
-                *reinterpret_cast<float4*>(tile_s + tid * kPitch + 4 * c4) =
-                    rvalid ? make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3])
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
-            float s = 0.f;
-            const int c = tid & 63;
-            if (tid < 64) { for (int q = 0; q < kTile; ++q) s += tile_s[q * kPitch + c]; }
-            else { for (int q = 0; q < kTile; ++q) { const float v = tile_s[q * kPitch + c]; s = fmaf(v, v, s); } }
-            stat_acc += (double)s;
-            __syncthreads();
-        }
-    }
-    if (STATS) atomicAdd(stats + tid, stat_acc);   // [0,64): sum, [64,128): sum of squares
-}
-
 // d_pre = a * (d_y - S1/N - xhat * S2/N)   (BatchNorm backward, batch statistics), in place.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, long long n_pix,
@@ -717,57 +607,6 @@ bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, lon
         d.w = sa[c + 3] * (d.w - s1[c + 3] - (y.w - sm[c + 3]) * si[c + 3] * s2[c + 3]);
         reinterpret_cast<float4*>(d_y)[i] = d;
     }
-}
-
-// dW[n][c][tap] = sum_p d_pre[p][n] * in[p + tap][c];  grid = (chunks, 9 taps)
-__global__ void __launch_bounds__(kTile)
-conv_wgrad_kernel(const float* __restrict__ d_pre, const float* __restrict__ in, int n_rows, int T_l, int F,
-                  float* __restrict__ g_w) {
-    extern __shared__ __align__(16) float smem[];
-    float* Dp = smem;                    // [128][68]
-    float* In = Dp + kTile * kPitch;     // [128][68]
-    const int tid = threadIdx.x;
-    const int tap = blockIdx.y;
-    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    const int TR = kTile / F;
-    const int tr = tid / F, f = tid - tr * F;
-    const int nb = tid >> 3, kb = tid & 7;
-    const int n_tiles = (n_rows + TR - 1) / TR;
-    float accW[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) accW[i] = 0.f;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int R = tile * TR + tr;
-        const bool rvalid = R < n_rows;
-        const int t = R % T_l;
-        const bool ivalid = rvalid && (t + dy >= 0) && (t + dy < T_l) && (f + dx >= 0) && (f + dx < F);
-        const float4* dsrc = reinterpret_cast<const float4*>(d_pre) + ((long long)R * F + f) * 16;
-        const float4* isrc = reinterpret_cast<const float4*>(in) + ((long long)(R + dy) * F + f + dx) * 16;
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-            reinterpret_cast<float4*>(Dp + tid * kPitch)[c4] = rvalid ? __ldg(dsrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            reinterpret_cast<float4*>(In + tid * kPitch)[c4] = ivalid ? __ldg(isrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int q = 0; q < kTile; ++q) {
-            const float4 d4 = *reinterpret_cast<const float4*>(Dp + q * kPitch + 4 * nb);
-            const float4 y0 = *reinterpret_cast<const float4*>(In + q * kPitch + 8 * kb);
-            const float4 y1 = *reinterpret_cast<const float4*>(In + q * kPitch + 8 * kb + 4);
-            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-            const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) accW[i * 8 + j] = fmaf(dv[i], yv[j], accW[i * 8 + j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            atomicAdd(g_w + (4 * nb + i) * 576 + (8 * kb + j) * 9 + tap, accW[i * 8 + j]);
 }
 
 // Layer-0 parameter gradients from {S1, G} and the tap moments (one block of 64 threads).
@@ -798,8 +637,6 @@ __global__ void cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long lo
 
 constexpr size_t kGluFwdSmem = kGluFwdSmemBytes;
 constexpr size_t kGluBwdSmem = kGluBwdSmemBytes;
-constexpr size_t kWgradSmem = 2 * kTile * kPitch * sizeof(float);
-size_t conv_smem_bytes(int F) { return (size_t)(9 * 4096 + (kTile / F + 2) * (F + 2) * kPitch) * sizeof(float); }
 
 }  // namespace
 
@@ -808,9 +645,6 @@ int cnn_kernels_init() {
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluFwdSmem));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluBwdSmem));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluBwdSmem));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(4)));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(4)));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmem));
     return DCASE_OK;
 }
 
@@ -862,29 +696,6 @@ int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* 
     return DCASE_OK;
 }
 
-int launch_conv_w_prep(const float* w, float* w_fwd, float* w_dgrad, cudaStream_t s) {
-    DCASE_PROF("conv_w_prep", s);
-    conv_w_prep_kernel<<<36, 256, 0, s>>>(w, w_fwd, w_dgrad);
-    DCASE_LAUNCH_CHECK();
-    return DCASE_OK;
-}
-
-int launch_conv3x3(const float* in, int n_rows, int T_l, int F, const float* w_prep, const float* bias, float* out,
-                   double* stats, int num_sms, cudaStream_t s) {
-    DCASE_PROF(bias ? (F == 16 ? "conv3x3_fwd_l1" : "conv3x3_fwd_l2") : (F == 16 ? "conv3x3_dgrad_l1" : "conv3x3_dgrad_l2"), s);
-    const int TR = kTile / F;
-    const int n_tiles = (n_rows + TR - 1) / TR;
-    const int grid = grid_for(n_tiles, num_sms, 1);
-    if (stats) {
-        DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
-        conv3x3_kernel<true><<<grid, kTile, conv_smem_bytes(F), s>>>(in, n_rows, T_l, F, w_prep, bias, out, stats);
-    } else {
-        conv3x3_kernel<false><<<grid, kTile, conv_smem_bytes(F), s>>>(in, n_rows, T_l, F, w_prep, bias, out, nullptr);
-    }
-    DCASE_LAUNCH_CHECK();
-    return DCASE_OK;
-}
-
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta, float* running,
                        int training, float* bn, cudaStream_t s) {
     DCASE_PROF("bn_finalize", s);
@@ -930,19 +741,6 @@ int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const fl
     long long blocks = (n_pix * 16 + 255) / 256;
     if (blocks > num_sms * 8) blocks = num_sms * 8;
     bn_bwd_apply_kernel<<<(int)blocks, 256, 0, s>>>(d_y, ypre, n_pix, bn, s12, g_gamma, g_beta, g_conv_b);
-    DCASE_LAUNCH_CHECK();
-    return DCASE_OK;
-}
-
-int launch_conv_wgrad(const float* d_pre, const float* in, int n_rows, int T_l, int F, float* g_w, int num_sms,
-                      cudaStream_t s) {
-    DCASE_PROF(F == 16 ? "conv3x3_wgrad_l1" : "conv3x3_wgrad_l2", s);
-    const int TR = kTile / F;
-    const int n_tiles = (n_rows + TR - 1) / TR;
-    int chunks = (num_sms * 2 + 8) / 9;
-    if (chunks > n_tiles) chunks = n_tiles;
-    if (chunks < 1) chunks = 1;
-    conv_wgrad_kernel<<<dim3(chunks, 9), kTile, kWgradSmem, s>>>(d_pre, in, n_rows, T_l, F, g_w);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

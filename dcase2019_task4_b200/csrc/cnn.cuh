@@ -36,9 +36,9 @@ int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const
                          DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
                         const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
-int launch_conv_w_prep(const float* w /*[64][64][3][3]*/, float* w_fwd /*[9][64c][64n]*/,
-                       float* w_dgrad /*[9][64n][64c]*/, cudaStream_t s);
-int launch_conv3x3(const float* in, int n_rows, int T_l, int F, const float* w_prep, const float* bias,
+// conv_tc.cu: weight images are the swizzled shared-memory layout of the tcgen05 B operand (36864 floats each)
+int launch_conv_w_prep(const float* w /*[64][64][3][3]*/, float* img_fwd, float* img_dgrad, cudaStream_t s);
+int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, const float* bias,
                    float* out, double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta,
                        float* running, int training, float* bn, cudaStream_t s);
@@ -52,9 +52,10 @@ int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* 
 int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const float* bn, const float* gamma,
                         const float* s12, float* g_gamma, float* g_beta, float* g_conv_b, int num_sms,
                         cudaStream_t s);
-int launch_conv_wgrad(const float* d_pre, const float* in, int n_rows, int T_l, int F, float* g_w, int num_sms,
+int launch_conv_wgrad(const float* d_pre, const float* in, int B, int T_l, int F, float* g_w, int num_sms,
                       cudaStream_t s);
 int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                              const float* gamma, const float* fold0, const float* acc0, float* g_conv_w,
                              float* g_conv_b, float* g_gamma, float* g_beta, cudaStream_t s);
 int cnn_kernels_init();
+int conv_tc_kernels_init();

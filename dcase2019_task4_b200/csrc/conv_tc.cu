@@ -1,0 +1,314 @@
+// conv3x3 (64 -> 64 channels, stride 1, pad 1; CNN.py:46-47) on the 5th-gen tensor cores: forward, data
+// gradient and weight gradient as implicit GEMMs (tcgen05.mma kind::tf32, fp32 accumulators in TMEM).
+//
+// Tile = 16 frames x 8 mel slots = 128 output pixels of one clip.  The 18 x PITCH input halo (zero filled
+// outside the clip) is staged ONCE in shared memory in the tensor core's swizzled operand layout; the 9 taps are
+// the SAME buffer at 9 start addresses (the swizzle is a function of the absolute shared-memory address, so row
+// shifts need no re-layout; pinned by tests/test_gpu_tcgen05.py).  Layer 1 (F = 16) covers the mel axis with two
+// 8-wide halves (PITCH = 10); layer 2 (F = 4) uses PITCH = 8 with 4 valid slots.
+//
+//   forward / dgrad : D[pixel][n] = sum_tap sum_c halo[pixel + tap][c] * W[tap][n][c]     M=128, N=64, K=9*64
+//                     the 144 KB weight image arrives by ONE bulk-async copy group (cp.async.bulk, mbarrier tx)
+//   wgrad           : D[n][c]    += sum_pixel d_pre[pixel][n] * halo[pixel + tap][c]      M=64, N=64, K=pixels
+//                     (MN-major operands, SWIZZLE_128B_BASE32B), 3 taps (one dy) per CTA, accumulated in TMEM over
+//                     all tiles of the persistent CTA
+#include "cnn.cuh"
+#include "tc.cuh"
+
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kHaloRows = 192;                    // >= 18 * 10 + 2, multiple of 8
+constexpr int kHaloBlk = kHaloRows * 128;         // bytes per 32-channel block
+constexpr int kWImgBytes = 9 * 16384;             // [9 taps][2 k-blocks][64 rows][128 B]
+constexpr int kConvSmemBytes = 1024 + kWImgBytes + 2 * kHaloBlk + 256;
+constexpr int kWgradSmemBytes = 1024 + 2 * 16384 + 2 * kHaloBlk;
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc::smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+
+// W [n][c][tap] -> shared-memory images (K-major SW128 B operands, rows = output channel of the pass)
+//   forward: image[tap ][c / 32][row n][c % 32] = W[n][c][tap]
+//   dgrad  : image[8-tap][n / 32][row c][n % 32] = W[n][c][tap]      (mirrored taps, transposed channels)
+__global__ void conv_w_image_kernel(const float* __restrict__ w, float* __restrict__ img_fwd, float* __restrict__ img_dgrad) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * 64 * 9; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9, c = (i / 9) & 63, n = i / 576;
+        const float v = __ldg(w + i);
+        img_fwd[(tap * 16384 + (c >> 5) * 8192 + tc::sw128_off(n, c & 31)) >> 2] = v;
+        img_dgrad[((8 - tap) * 16384 + (n >> 5) * 8192 + tc::sw128_off(c, n & 31)) >> 2] = v;
+    }
+}
+
+struct TileGeom {
+    int b, t0, f0;
+};
+__device__ __forceinline__ TileGeom decode_tile(int tile, int halves, int tblocks) {
+    TileGeom g;
+    const int h = tile % halves;
+    const int r = tile / halves;
+    g.f0 = h * 8;
+    g.t0 = (r % tblocks) * 16;
+    g.b = r / tblocks;
+    return g;
+}
+
+// stage halo rows [row_lo, row_hi) (18 x PITCH pixels; row 0 = frame t0 - 1, slot 0 = mel f0 - 1), zero outside the clip
+template <bool B32>
+__device__ __forceinline__ void load_halo(const float* __restrict__ in, const TileGeom& g, int T_l, int F, int pitch,
+                                          int row_lo, int row_hi, unsigned char* halo) {
+    const int n_items = (row_hi - row_lo) * pitch * 16;
+    for (int idx = threadIdx.x; idx < n_items; idx += kTile) {
+        const int q = idx & 15;
+        const int hp = row_lo * pitch + (idx >> 4);
+        const int hr = hp / pitch, hs = hp - hr * pitch;
+        const int t = g.t0 - 1 + hr, f = g.f0 - 1 + hs;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T_l && f >= 0 && f < F)
+            v = __ldg(reinterpret_cast<const float4*>(in) + (((long long)g.b * T_l + t) * F + f) * 16 + q);
+        const uint32_t off = (q >> 3) * kHaloBlk + (B32 ? tc::sw128b32_chunk(hp, q & 7) : tc::sw128_chunk(hp, q & 7));
+        *reinterpret_cast<float4*>(halo + off) = v;
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(kTile, 1)
+conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const float* __restrict__ w_img,
+                  const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Wi = smem;                          // weight image, 144 KB
+    unsigned char* halo = smem + kWImgBytes;           // 2 blocks x 192 rows x 128 B
+    float* bias_s = reinterpret_cast<float*>(halo + 2 * kHaloBlk);
+    __shared__ uint64_t w_bar, mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pitch = F == 16 ? 10 : 8;
+    const int halves = F == 16 ? 2 : 1;
+    const int tblocks = (T_l + 15) / 16;
+    const int n_tiles = B * tblocks * halves;
+
+    if (tid == 0) {
+        tc::mbar_init(&w_bar, 1);
+        tc::mbar_init(&mma_bar, 1);
+        tc::fence_mbar_init();
+        mbar_expect_tx(&w_bar, kWImgBytes);
+        for (int i = 0; i < 9; ++i) bulk_g2s(Wi + i * 16384, reinterpret_cast<const unsigned char*>(w_img) + i * 16384, 16384, &w_bar);
+    }
+    if (tid < 64) bias_s[tid] = bias ? __ldg(bias + tid) : 0.f;
+    for (int i = tid; i < 2 * kHaloBlk / 16; i += kTile) reinterpret_cast<float4*>(halo)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t w_a = tc::smem_u32(Wi), h_a = tc::smem_u32(halo);
+    uint32_t phase = 0;
+    double stat_acc = 0.0;
+    const int ti = tid >> 3, j = tid & 7;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileGeom g = decode_tile(tile, halves, tblocks);
+        load_halo<false>(in, g, T_l, F, pitch, 0, 18, halo);
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::mbar_wait(&w_bar, 0);                  // weight image landed (no-op after the first tile)
+            tc::fence_after_sync();
+            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                const uint32_t a0 = h_a + ((1 + dy) * pitch + 1 + dx) * 128;
+                const uint32_t b0 = w_a + tap * 16384;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    tc::umma_tf32(tmem, tc::smem_desc_sw128(a0 + (k >> 2) * kHaloBlk + (k & 3) * 32, 16, pitch * 128),
+                                  tc::smem_desc_sw128(b0 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc,
+                                  (tap > 0 || k > 0) ? 1u : 0u);
+            }
+            tc::umma_commit(&mma_bar);
+        }
+        tc::mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+        float acc[64];
+        tc::tmem_ld_row64(tmem, warp, 0, acc);
+        tc::fence_before_sync();
+        const int t = g.t0 + ti, f = g.f0 + j;
+        const bool valid = t < T_l && f < F;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) acc[c] += bias_s[c];
+        if (valid) {
+            float4* dst = reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64);
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) dst[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        }
+        if (STATS) {                                   // per-channel sum / sum of squares for the batch statistics
+            float* tile_s = reinterpret_cast<float*>(halo);     // [128][68]; all MMAs reading the halo have completed
+            __syncthreads();
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4)
+                *reinterpret_cast<float4*>(tile_s + tid * 68 + 4 * c4) =
+                    valid ? make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3])
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            float s = 0.f;
+            const int c = tid & 63;
+            if (tid < 64) { for (int q = 0; q < kTile; ++q) s += tile_s[q * 68 + c]; }
+            else { for (int q = 0; q < kTile; ++q) { const float v = tile_s[q * 68 + c]; s = fmaf(v, v, s); } }
+            stat_acc += (double)s;
+        }
+        __syncthreads();
+    }
+    if (STATS) atomicAdd(stats + tid, stat_acc);       // [0,64): sum, [64,128): sum of squares
+    if (tid == 0 && n_tiles <= (int)blockIdx.x) tc::mbar_wait(&w_bar, 0);   // never leave with a bulk copy in flight
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
+// grid = (chunks, 3): blockIdx.y selects dy; TMEM holds the three [64 n][64 c] accumulators of dx = -1, 0, +1.
+__global__ void __launch_bounds__(kTile, 2)
+conv_wgrad_tc_kernel(const float* __restrict__ d_pre, const float* __restrict__ in, int B, int T_l, int F,
+                     float* __restrict__ g_w) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* DP = smem;                          // d_pre tile, MN-major B32: 2 blocks x 128 rows
+    unsigned char* halo = smem + 32768;                // input halo, MN-major B32: 2 blocks x 192 rows
+    __shared__ uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dy = (int)blockIdx.y - 1;
+    const int pitch = F == 16 ? 10 : 8;
+    const int halves = F == 16 ? 2 : 1;
+    const int tblocks = (T_l + 15) / 16;
+    const int n_tiles = B * tblocks * halves;
+
+    if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
+    for (int i = tid; i < 2 * kHaloBlk / 16; i += kTile) reinterpret_cast<float4*>(halo)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t dp_a = tc::smem_u32(DP), h_a = tc::smem_u32(halo);
+    uint32_t phase = 0;
+    bool pending = false, first = true;
+    const int ti = tid >> 3, j = tid & 7;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileGeom g = decode_tile(tile, halves, tblocks);
+        if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; pending = false; }
+        {   // d_pre row of this thread's pixel (zero for pixels outside the clip / mel range)
+            const int t = g.t0 + ti, f = g.f0 + j;
+            const bool valid = t < T_l && f < F;
+            const float4* src = reinterpret_cast<const float4*>(d_pre) + (((long long)g.b * T_l + t) * F + f) * 16;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4)
+                *reinterpret_cast<float4*>(DP + (c4 >> 3) * 16384 + tc::sw128b32_chunk(tid, c4 & 7)) =
+                    valid ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        load_halo<true>(in, g, T_l, F, pitch, 1 + dy, 17 + dy, halo);
+        // the two slack pixels past row 17+dy read by the dx = +1 tap of the last frame stay zero / stale-but-finite:
+        // they only meet d_pre rows of slots j >= 6 of ... (see below) -> keep them exact: slots beyond the row are
+        // the next row's first slots, which the loop above has just rewritten or which are still zero.
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 1, 1);
+#pragma unroll 1
+            for (int dxi = 0; dxi < 3; ++dxi) {
+#pragma unroll 4
+                for (int r = 0; r < 16; ++r)           // K step = the 8 pixels of frame row r of the tile
+                    tc::umma_tf32(tmem + dxi * 64, tc::smem_desc(dp_a + r * 1024, 16384, 512, 1),
+                                  tc::smem_desc(h_a + ((1 + dy + r) * pitch + dxi) * 128, kHaloBlk, 512, 1), idesc,
+                                  (!first || r > 0) ? 1u : 0u);
+            }
+            tc::umma_commit(&mma_bar);
+        }
+        pending = true;
+        first = false;
+    }
+    if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; }
+    tc::fence_after_sync();
+    if (!first) {
+        const int n = 16 * warp + lane;                // M = 64 accumulators: row m in TMEM lane 32*(m/16) + m%16
+        const bool own = lane < 16;
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
+        float v[16];
+#pragma unroll 1
+        for (int dxi = 0; dxi < 3; ++dxi) {
+            const int tap = (dy + 1) * 3 + dxi;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                tc::tmem_ld16(tbase + dxi * 64 + c0, v);
+                tc::tmem_ld_wait();
+                if (own) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) atomicAdd(g_w + n * 576 + (c0 + c) * 9 + tap, v[c]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+int grid_for(int n_tiles, int num_sms, int per_sm) {
+    const int g = num_sms * per_sm;
+    return n_tiles < g ? n_tiles : g;
+}
+
+}  // namespace
+
+int conv_tc_kernels_init() {
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBytes));
+    return DCASE_OK;
+}
+
+int launch_conv_w_prep(const float* w, float* w_fwd, float* w_dgrad, cudaStream_t s) {
+    DCASE_PROF("conv_w_prep", s);
+    conv_w_image_kernel<<<36, 256, 0, s>>>(w, w_fwd, w_dgrad);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, const float* bias, float* out,
+                   double* stats, int num_sms, cudaStream_t s) {
+    DCASE_PROF(bias ? (F == 16 ? "conv3x3_fwd_l1" : "conv3x3_fwd_l2") : (F == 16 ? "conv3x3_dgrad_l1" : "conv3x3_dgrad_l2"), s);
+    DCASE_REQUIRE(F == 16 || F == 4, "conv3x3 is built for the 16- and 4-bin layers of cfg.crnn_kwargs");
+    const int n_tiles = B * ((T_l + 15) / 16) * (F == 16 ? 2 : 1);
+    const int grid = grid_for(n_tiles, num_sms, 1);
+    if (stats) {
+        DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
+        conv3x3_tc_kernel<true><<<grid, kTile, kConvSmemBytes, s>>>(in, B, T_l, F, w_img, bias, out, stats);
+    } else {
+        conv3x3_tc_kernel<false><<<grid, kTile, kConvSmemBytes, s>>>(in, B, T_l, F, w_img, bias, out, nullptr);
+    }
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int launch_conv_wgrad(const float* d_pre, const float* in, int B, int T_l, int F, float* g_w, int num_sms,
+                      cudaStream_t s) {
+    DCASE_PROF(F == 16 ? "conv3x3_wgrad_l1" : "conv3x3_wgrad_l2", s);
+    DCASE_REQUIRE(F == 16 || F == 4, "conv wgrad is built for the 16- and 4-bin layers of cfg.crnn_kwargs");
+    const int n_tiles = B * ((T_l + 15) / 16) * (F == 16 ? 2 : 1);
+    int chunks = (2 * num_sms) / 3;
+    if (chunks > n_tiles) chunks = n_tiles;
+    if (chunks < 1) chunks = 1;
+    conv_wgrad_tc_kernel<<<dim3(chunks, 3), kTile, kWgradSmemBytes, s>>>(d_pre, in, B, T_l, F, g_w);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
