@@ -65,6 +65,9 @@ SIGNATURES = {
                             c_p, c_p]),
     "dcase_adam_ema_step": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_p, c_p]),
     "dcase_mt_fwd_bwd": (c_i, [c_p, ctypes.POINTER(MtArgs), c_p]),
+    "dcase_sizeof_mt_args": (c_sz, []),
+    "dcase_sizeof_step_scalars": (c_sz, []),
+    "dcase_selftest_umma_shift": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
 }
 
 _lib = None
@@ -91,6 +94,9 @@ def lib():
                     fn = getattr(handle, name)
                     fn.restype = res
                     fn.argtypes = args
+                if handle.dcase_sizeof_mt_args() != ctypes.sizeof(MtArgs) or \
+                        handle.dcase_sizeof_step_scalars() != ctypes.sizeof(StepScalars):
+                    raise DcaseError("ctypes struct mirrors do not match include/dcase_b200.h as compiled")
                 _lib = handle
     return _lib
 

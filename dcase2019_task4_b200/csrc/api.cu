@@ -166,6 +166,11 @@ int check_shape(int B, int T, int NC) {
 extern "C" {
 
 int dcase_version(void) { return DCASE_B200_VERSION; }
+size_t dcase_sizeof_mt_args(void) { return sizeof(dcase_mt_args); }
+size_t dcase_sizeof_step_scalars(void) {
+    static_assert(sizeof(dcase_step_scalars) == sizeof(DcaseStepScalars), "scalar struct mirrors diverged");
+    return sizeof(dcase_step_scalars);
+}
 
 unsigned long long dcase_launch_count(void) { return g_dcase_launches; }
 

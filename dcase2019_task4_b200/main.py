@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import config as cfg
+from . import dp
 from . import kernels as K
 from ._lib import MtArgs, StepScalars
 from .utils import ramps
@@ -142,15 +143,14 @@ class MeanTeacherEngine(object):
             self.check_loss()
         with torch.cuda.device(self.dev):
             K.mt_fwd_bwd(a)
-            if self.world > 1:
-                torch.distributed.all_reduce(self.grads, group=self.pg)      # flat slab, SUM; 1/N folded below
+            grad_scale = dp.allreduce_grads_(self.grads, self.pg) if self.world > 1 else 1.0   # flat slab, SUM
             g = self.optimizer.param_groups[0]
             torch._foreach_add_(self._steps, 1.0)
             alpha = min(1 - 1 / (global_step_after + 1), 0.999)
             K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
                             ema.flat_parameters() if ema is not None else None, self._adam_step_count(),
                             lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], ema_alpha=alpha,
-                            grad_scale=1.0 / self.world)
+                            grad_scale=grad_scale)
             self.meters_host.copy_(self.meters, non_blocking=True)
             self.meters_event.record()
         self._pending = True

@@ -60,6 +60,11 @@ int dcase_profile_end(char* buf, size_t cap);
  * K-major operands; mode 1: raw TMEM dump [128 lanes][64 columns] of D[m][n] = sum_p A[p][m] * B[p][n], p < 128,
  * with MN-major operands and M = 64. */
 int dcase_selftest_umma(dcase_ctx* ctx, int mode, const float* A, const float* B, float* D, void* stream);
+/* D[128][64] = Arows * B^T where the K-major A operand starts `shift` rows into a 256-row swizzled buffer with its
+ * 8-row groups `pitch` rows apart (how the conv kernels address the 9 taps of one staged halo). base_mode 0 is the
+ * encoding the kernels use (descriptor base_offset = 0: the swizzle follows absolute shared-memory addresses). */
+int dcase_selftest_umma_shift(dcase_ctx* ctx, int shift, int pitch, int base_mode, const float* A, const float* B,
+                              float* D, void* stream);
 
 /* Per-step scalars in device memory (so a captured CUDA graph replays with new values).
  * Layout must match DcaseStepScalars in csrc/common.cuh. */
@@ -171,6 +176,10 @@ typedef struct dcase_mt_args {
 } dcase_mt_args;
 
 int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* args, void* stream);
+
+/* sizeof(dcase_mt_args) / sizeof(dcase_step_scalars) as compiled, so FFI struct mirrors can be checked at load. */
+size_t dcase_sizeof_mt_args(void);
+size_t dcase_sizeof_step_scalars(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dcase_b200.h declares; shape / layout helpers
+answer without a GPU; compute entry points fail loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dcase_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcase_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dcase2019_task4_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    handle = lib.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for name in syms:
+        assert hasattr(handle, name), f"{name} declared in include/dcase_b200.h but not exported"
+        assert name in lib.SIGNATURES, f"{name} has no ctypes signature in _lib.SIGNATURES"
+    assert set(lib.SIGNATURES) == set(syms)
+
+
+def test_layout_helpers_without_gpu(lib):
+    h = lib.lib()
+    assert h.dcase_version() == 100
+    assert h.dcase_logmel_num_frames(441000) == 864            # config.py:22 max_frames
+    assert h.dcase_crnn_param_count(10) == 214356
+    assert h.dcase_crnn_param_offset(10, b"cnn.cnn.conv0.weight") == 0
+    assert h.dcase_crnn_param_offset(10, b"dense_softmax.bias") == 214356 - 10
+    assert h.dcase_crnn_param_offset(10, b"no.such.param") == -1
+    assert h.dcase_crnn_workspace_bytes(24, 864, 10) > 24 * 432 * 16 * 64 * 4 * 4
+    off, n = ctypes.c_size_t(), ctypes.c_size_t()
+    assert h.dcase_crnn_ws_tensor(24, 864, 10, b"out0", ctypes.byref(off), ctypes.byref(n)) == 0
+    assert n.value == 24 * 432 * 16 * 64
+    assert h.dcase_crnn_ws_tensor(24, 864, 10, b"bogus", ctypes.byref(off), ctypes.byref(n)) < 0
+    assert b"bogus" in h.dcase_last_error()
+
+
+def test_struct_mirrors_match_header(lib):
+    h = lib.lib()
+    assert ctypes.sizeof(lib.StepScalars) == h.dcase_sizeof_step_scalars() == 40      # 8 + 4 + 7 * 4
+    assert ctypes.sizeof(lib.MtArgs) == h.dcase_sizeof_mt_args()
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lib.DcaseError):
+        lib.ctx()
+    h = ctypes.c_void_p()
+    assert lib.lib().dcase_ctx_create(ctypes.byref(h), 0) < 0  # no device -> error code, not a silent CPU path
+    from dcase2019_task4_b200.models.CRNN import CRNN
+    from dcase2019_task4_b200 import config as cfg
+    m = CRNN(**cfg.crnn_kwargs)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 864, 64))

@@ -1,0 +1,147 @@
+"""CPU: host-side mirror of the reference interface (no kernels involved)."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from dcase2019_task4_b200 import DataLoad, config as cfg, dp
+from dcase2019_task4_b200.models.CRNN import CRNN
+from dcase2019_task4_b200.utils import ramps
+from dcase2019_task4_b200.utils.Scaler import Scaler
+from dcase2019_task4_b200.utils.utils import (AverageMeterSet, ManyHotEncoder, SaveBest, find_contiguous_regions,
+                                              get_transforms, weights_init)
+from oracle import crnn as ocrnn
+from oracle import mel as omel
+
+
+def _df(n, kind):
+    names = ["f%d_%s.wav" % (i, kind) for i in range(n)]
+    if kind == "weak":
+        return pd.DataFrame({"filename": names, "event_labels": ["Dog,Cat" if i % 2 else "Speech" for i in range(n)]})
+    if kind == "unl":
+        return pd.DataFrame({"filename": names})
+    rows = []
+    for i, f in enumerate(names):
+        rows.append({"filename": f, "onset": 1.0, "offset": 5.0, "event_label": "Dog"})
+        rows.append({"filename": f, "onset": 2.0 + i, "offset": 9.0 + i, "event_label": "Speech"})
+    return pd.DataFrame(rows)
+
+
+def _datasets(enc):
+    feats = lambda name: np.full((4, 64), float(len(name)), dtype=np.float32)
+    return [DataLoad.DataLoadDf(_df(13, "weak"), feats, enc.encode_strong_df),
+            DataLoad.DataLoadDf(_df(31, "unl"), feats, enc.encode_strong_df),
+            DataLoad.DataLoadDf(_df(14, "syn"), feats, enc.encode_strong_df)]
+
+
+def test_dataset_labels_and_target_layout():
+    enc = ManyHotEncoder(cfg.classes, n_frames=cfg.max_frames // cfg.pooling_time_ratio)
+    weak, unl, syn = _datasets(enc)
+    assert len(weak) == 13 and len(unl) == 31 and len(syn) == 14     # strong frame has 2 rows per file
+    _, y = weak[1]
+    assert y.shape == (108, 10) and y[:, cfg.classes.index("Dog")].all() and y.sum() == 2 * 108
+    _, y = unl[0]
+    assert (y == -1).all()                                            # utils.py:82-85
+    _, y = syn[3]
+    assert y[1:5, cfg.classes.index("Dog")].all() and y[5, cfg.classes.index("Dog")] == 0
+    assert y[5:12, cfg.classes.index("Speech")].all()
+
+
+def test_multistream_sampler_matches_reference_semantics():
+    enc = ManyHotEncoder(cfg.classes, n_frames=108)
+    concat = DataLoad.ConcatDataset(_datasets(enc))
+    assert [len(r) for r in concat.cluster_indices] == [13, 31, 14] and len(concat) == 58
+    s = DataLoad.MultiStreamBatchSampler(concat, batch_sizes=[2, 4, 2], seed=0)
+    assert len(s) == min(13 // 2, 31 // 4, 14 // 2) == 6
+    batches = list(s)
+    assert len(batches) == 6
+    for b in batches:
+        assert len(b) == 8
+        assert all(i < 13 for i in b[:2]) and all(13 <= i < 44 for i in b[2:6]) and all(44 <= i < 58 for i in b[6:])
+    flat = [i for b in batches for i in b]
+    assert len(set(flat)) == len(flat)                                # without replacement within an epoch
+    with pytest.raises(AssertionError):
+        DataLoad.MultiStreamBatchSampler(concat, batch_sizes=[2, 4])
+
+
+def test_multistream_sampler_rank_sharding():
+    enc = ManyHotEncoder(cfg.classes, n_frames=108)
+    concat = DataLoad.ConcatDataset(_datasets(enc))
+    per_rank = dp.per_rank_batch_sizes([4, 8, 4], 2)
+    assert per_rank == [2, 4, 2]
+    with pytest.raises(ValueError):
+        dp.per_rank_batch_sizes([6, 12, 6], 4)
+    seen = []
+    for rank in range(2):
+        s = DataLoad.MultiStreamBatchSampler(concat, per_rank, rank=rank, world_size=2, seed=5)
+        batches = list(s)
+        assert len(batches) == len(s) == min(13 // 2 // 2, 31 // 2 // 4, 14 // 2 // 2)
+        seen.append({i for b in batches for i in b})
+    assert not (seen[0] & seen[1])                                    # ranks see disjoint clips
+
+
+def test_many_hot_encoder_roundtrip_and_regions():
+    enc = ManyHotEncoder(np.array(cfg.classes), n_frames=20)
+    y = enc.encode_strong_df([["Dog", 2, 6], ["Cat", 0, 20], ["Dog", 10, 12]])
+    dec = enc.decode_strong(y)
+    assert ["Dog", 2, 6] in [[a, int(b), int(c)] for a, b, c in dec] and ["Cat", 0, 20] in [[a, int(b), int(c)] for a, b, c in dec]
+    assert find_contiguous_regions([0, 1, 1, 0, 1]).tolist() == [[1, 3], [4, 5]]
+    assert enc.decode_weak(enc.encode_weak(["Dog", "Speech"])) == ["Dog", "Speech"]
+    assert ManyHotEncoder.load_state_dict(enc.state_dict()).labels == cfg.classes
+
+
+def test_scaler_matches_oracle_and_wire_format(tmp_path):
+    rng = np.random.default_rng(0)
+    data = [(torch.from_numpy(rng.normal(-20, 8, (1, 50, 64)).astype(np.float32)), None) for _ in range(5)]
+    sc = Scaler()
+    mean, std = sc.calculate_scaler(data)
+    m, m2 = omel.scaler_means([d[0].numpy() for d in data])
+    assert np.allclose(mean, m) and np.allclose(std, omel.scaler_std(m, m2))
+    sd = sc.state_dict()
+    assert set(sd) == {"mean_", "mean_of_square_"} and isinstance(sd["mean_"], list)
+    sc.save(tmp_path / "s.json")
+    sc2 = Scaler()
+    sc2.load(tmp_path / "s.json")
+    assert np.allclose(sc2.std_, sc.std_)
+    x = data[0][0]
+    assert np.allclose(sc.normalize(x).numpy(), (x.numpy() - mean) / std, atol=1e-5)
+
+
+def test_transform_chain_structure_and_small_utils():
+    t = get_transforms(864, Scaler(), augment_type="noise")
+    assert [type(s).__name__ for s in t.transforms] == ["AugmentGaussianNoise", "ApplyLog", "PadOrTrunc", "ToTensor", "Normalize"]
+    assert t._build_plan()["frames"] == 864 and t._build_plan()["noise"]
+    assert [type(s).__name__ for s in get_transforms(100).transforms] == ["ApplyLog", "PadOrTrunc", "ToTensor"]
+    with pytest.raises(NotImplementedError):
+        DataLoad.Compose([DataLoad.ToTensor()])._build_plan()
+    assert ramps.sigmoid_rampup(0, 10) == pytest.approx(np.exp(-5)) and ramps.sigmoid_rampup(3, 0) == 1.0
+    sb = SaveBest("sup")
+    assert [sb.apply(v) for v in (0.1, 0.05, 0.3)] == [True, False, True] and sb.best_epoch == 2
+    ms = AverageMeterSet()
+    ms.update("Loss", 2.0)
+    ms.update("Loss", 4.0)
+    assert ms["Loss"].avg == 3.0 and "Loss 4.0000" in str(ms)
+
+
+def test_crnn_module_surface_on_cpu():
+    torch.manual_seed(0)
+    m = CRNN(**cfg.crnn_kwargs)
+    m.apply(weights_init)
+    names = [k for k, _ in m.named_parameters()]
+    assert names == list(ocrnn.param_shapes(10).keys())
+    flat = m.flat_parameters()
+    assert flat.numel() == 214356
+    assert abs(float(m.cnn.cnn.batchnorm1.weight.mean()) - 1.0) < 0.02 and float(m.dense.bias.abs().max()) == 0.0
+    with torch.no_grad():
+        m.dense.weight.fill_(3.0)
+    off = sum(int(np.prod(s)) for k, s in ocrnn.param_shapes(10).items() if k < "dense" and not k.startswith("dense"))
+    assert float(flat[214356 - 2 * 1290: 214356 - 2 * 1290 + 1280].min()) == 3.0   # parameters are views of the slab
+    sd = m.state_dict()
+    assert set(sd) == {"cnn", "rnn", "dense"} and "dense_softmax" not in sd      # CRNN.py:49-53 quirk kept
+    m2 = CRNN(**cfg.crnn_kwargs)
+    m2.load(parameters=sd)
+    assert torch.equal(m2.rnn.rnn.weight_hh_l1_reverse, m.rnn.rnn.weight_hh_l1_reverse)
+    for p in m2.parameters():
+        p.detach_()                                                               # main.py:286-287
+    with pytest.raises(NotImplementedError):
+        CRNN(**dict(cfg.crnn_kwargs, activation="relu"))

@@ -1,0 +1,105 @@
+"""CPU: the oracle against the committed golden fixtures (made from the unmodified reference by
+tests/golden/make_golden.py) and against independent implementations (torch.stft, torchaudio filterbank)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn as ocrnn
+from oracle import mel as omel
+from oracle import philox
+from oracle import train_step as otrain
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _crnn_fixture():
+    z = np.load(os.path.join(GOLD, "crnn_reference.npz"))
+    p = {k[len("param/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    buf = ocrnn.init_buffers()
+    for k in z.files:
+        if k.startswith("buf/"):
+            buf[k[len("buf/"):]] = torch.from_numpy(z[k]).clone()
+    return z, p, buf
+
+
+def test_oracle_crnn_matches_reference_fixture_eval():
+    z, p, buf = _crnn_fixture()
+    with torch.no_grad():
+        s, w = ocrnn.crnn_forward(torch.from_numpy(z["x"]), p, buf, training=False)
+    assert np.abs(s.numpy() - z["strong_eval"]).max() < 2e-6
+    assert np.abs(w.numpy() - z["weak_eval"]).max() < 2e-6
+
+
+def test_oracle_crnn_matches_reference_fixture_train_and_grads():
+    z, p, buf = _crnn_fixture()
+    sp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    s, w = ocrnn.crnn_forward(torch.from_numpy(z["x"]), sp, buf, training=True)
+    assert np.abs(s.detach().numpy() - z["strong_train"]).max() < 2e-6
+    assert np.abs(w.detach().numpy() - z["weak_train"]).max() < 2e-6
+    target = torch.from_numpy(z["target"])
+    loss, _ = otrain.mean_teacher_losses(s, w, None, None, target, slice(0, 2), slice(0, 2), 0.0)
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-6
+    grads = torch.autograd.grad(loss, list(sp.values()))
+    for k, g in zip(sp.keys(), grads):
+        ref_abs = float(z["gradabs/" + k])
+        assert abs(float(g.double().abs().sum()) - ref_abs) <= 1e-4 * ref_abs + 1e-7, k
+    for k in z.files:
+        if k.startswith("buf_after_train/"):
+            assert np.abs(buf[k[len("buf_after_train/"):]].numpy() - z[k]).max() < 1e-5, k
+
+
+def test_oracle_mel_matches_fixture():
+    z = np.load(os.path.join(GOLD, "mel_oracle.npz"))
+    fb = omel.mel_filterbank()
+    assert int(z["fb_nnz"]) == np.count_nonzero(fb) == 1983        # SURVEY: 1,983 of 65,600 weights non-zero
+    assert abs(float(z["fb_sum"]) - fb.astype(np.float64).sum()) < 1e-9
+    for i in range(3):
+        amp = omel.calculate_mel_spec(z["wave"][i].astype(np.float64))
+        assert np.array_equal(amp, z["mel_amp"][i])
+        c, n = omel.transform_chain(amp, z["mean"], z["std"], noise=z["noise"][i].astype(np.float64), frames=48)
+        assert np.array_equal(c, z["clean"][i]) and np.array_equal(n, z["noisy"][i])
+
+
+def test_oracle_stft_matches_torch_stft():
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(20000)
+    S = omel.stft_magnitude(y)
+    win = torch.hamming_window(2048, periodic=False, dtype=torch.float64)
+    ref = torch.stft(torch.from_numpy(y), n_fft=2048, hop_length=511, window=win, center=True, pad_mode="reflect",
+                     return_complex=True).abs().numpy()
+    assert S.shape == ref.shape == (1025, 1 + 20000 // 511)
+    assert np.abs(S - ref).max() < 1e-10
+
+
+def test_oracle_filterbank_matches_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    ref = ta.functional.melscale_fbanks(1025, 0.0, 22050.0, 64, 44100, norm=None, mel_scale="slaney").numpy().T
+    assert np.abs(omel.mel_filterbank() - ref).max() < 1e-5       # torchaudio computes it in float32
+
+
+def test_amplitude_to_db_top_db_and_amin():
+    S = np.array([[1.0, 1e-7, 0.0], [10.0, 1e-3, 1e-5]])
+    L = omel.amplitude_to_db(S)
+    assert L.max() == pytest.approx(20.0)
+    assert L.min() == pytest.approx(20.0 - 80.0)                  # floored at max - top_db
+    assert omel.amplitude_to_db(np.zeros((2, 2)))[0, 0] == pytest.approx(-100.0)   # amin = 1e-5
+    assert omel.pad_trunc_seq(np.ones((3, 2)), 5).shape == (5, 2) and omel.pad_trunc_seq(np.ones((7, 2)), 5).shape == (5, 2)
+
+
+def test_philox_known_answer_and_mask_statistics():
+    # Random123 known-answer test for philox4x32-10: counter = key = 0
+    out = philox.philox4x32(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    out = philox.philox4x32(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff)
+    assert [int(v) for v in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    m = philox.dropout_mask(4096, 64, seed=123, stream=1, step=7)
+    assert 0.49 < m.mean() < 0.51
+    assert not np.array_equal(m, philox.dropout_mask(4096, 64, seed=123, stream=1, step=8))
+
+
+def test_ramp_and_ema_schedule():
+    assert otrain.ema_alpha(1) == 0.5 and otrain.ema_alpha(999) == pytest.approx(0.999) and otrain.ema_alpha(5000) == 0.999
+    assert otrain.consistency_weight(0, 210) == pytest.approx(2 * np.exp(-5.0))
+    assert otrain.consistency_weight(10499, 210) < 2.0 and otrain.consistency_weight(10500, 210) == 2.0
