@@ -315,9 +315,14 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     for (int l = 0; l < 2; ++l) {
         const int nin = l == 0 ? kC : 2 * kH;
         float* rout = wsp<float>(ws, L, l == 0 ? "rnn0" : "rnn1");
-        for (int d = 0; d < 2; ++d)
-            DCASE_TRY(launch_sgemm(BT, 3 * kH, nin, rin, nin, 1, params + o.w_ih[l][d], 1, nin,
-                                   gi + (size_t)d * BT * 3 * kH, 3 * kH, params + o.b_ih[l][d], 0, 1, s));
+        {   // input projections of both directions in one launch: gi[d] = X W_ih[d]^T + b_ih[d]
+            GemmBatch gb{};
+            for (int d = 0; d < 2; ++d)
+                gb.p[d] = GemmProblem{BT, 3 * kH, nin, rin, nin, 1, params + o.w_ih[l][d], 1, nin,
+                                      gi + (size_t)d * BT * 3 * kH, 3 * kH, params + o.b_ih[l][d]};
+            gb.n = 2; gb.split = 1; gb.mode = 0;
+            DCASE_TRY(launch_sgemm_batch(gb, s));
+        }
         GruFwdArgs g{};
         g.gi = gi;
         for (int d = 0; d < 2; ++d) { g.w_hh[d] = params + o.w_hh[l][d]; g.b_hh[d] = params + o.b_hh[l][d]; }
@@ -391,19 +396,25 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
         g.save_hp = wsp<float>(ws, L, sv[l][4]);
         g.dgi = dgi; g.dgh = dgh; g.B = B; g.T = To;
         DCASE_TRY(launch_gru_bwd(g, s));
-        const int split = BT >= 512 ? 16 : 1;
+        // weight / bias / input gradients of both directions: 6 GEMMs in one launch + 4 column sums in one launch
+        DCASE_CUDA_CHECK(cudaMemsetAsync(d_in, 0, (size_t)BT * nin * sizeof(float), s));
+        GemmBatch gb{};
+        ColsumBatch cb{};
         for (int d = 0; d < 2; ++d) {
             const float* dgi_d = dgi + (size_t)d * BT * 3 * kH;
             const float* dgh_d = dgh + (size_t)d * BT * 3 * kH;
             const float* hp_d = g.save_hp + (size_t)d * BT * kH;
-            // dW_ih [3H][nin] = dgi^T X ;  dW_hh [3H][H] = dgh^T Hprev   (split-K, atomics into zeroed grads)
-            DCASE_TRY(launch_sgemm(3 * kH, nin, BT, dgi_d, 1, 3 * kH, xin, nin, 1, grads + o.w_ih[l][d], nin, nullptr, 1, split, s));
-            DCASE_TRY(launch_sgemm(3 * kH, kH, BT, dgh_d, 1, 3 * kH, hp_d, kH, 1, grads + o.w_hh[l][d], kH, nullptr, 1, split, s));
-            DCASE_TRY(launch_colsum(dgi_d, BT, 3 * kH, grads + o.b_ih[l][d], s));
-            DCASE_TRY(launch_colsum(dgh_d, BT, 3 * kH, grads + o.b_hh[l][d], s));
-            // d_in [BT][nin] (+)= dgi [BT][3H] W_ih [3H][nin]
-            DCASE_TRY(launch_sgemm(BT, nin, 3 * kH, dgi_d, 3 * kH, 1, params + o.w_ih[l][d], nin, 1, d_in, nin, nullptr, d, 1, s));
+            // dW_ih [3H][nin] = dgi^T X ;  dW_hh [3H][H] = dgh^T Hprev ;  d_in [BT][nin] += dgi W_ih
+            gb.p[3 * d + 0] = GemmProblem{3 * kH, nin, BT, dgi_d, 1, 3 * kH, xin, nin, 1, grads + o.w_ih[l][d], nin, nullptr};
+            gb.p[3 * d + 1] = GemmProblem{3 * kH, kH, BT, dgh_d, 1, 3 * kH, hp_d, kH, 1, grads + o.w_hh[l][d], kH, nullptr};
+            gb.p[3 * d + 2] = GemmProblem{BT, nin, 3 * kH, dgi_d, 3 * kH, 1, params + o.w_ih[l][d], nin, 1, d_in, nin, nullptr};
+            cb.A[2 * d] = dgi_d; cb.out[2 * d] = grads + o.b_ih[l][d];
+            cb.A[2 * d + 1] = dgh_d; cb.out[2 * d + 1] = grads + o.b_hh[l][d];
         }
+        gb.n = 6; gb.split = BT >= 512 ? 4 : 1; gb.mode = 1;
+        cb.n = 4; cb.M = BT; cb.N = 3 * kH;
+        DCASE_TRY(launch_sgemm_batch(gb, s));
+        DCASE_TRY(launch_colsum_batch(cb, s));
     }
 
     // ---- CNN blocks 2, 1 ----

@@ -29,8 +29,26 @@ struct GruBwdArgs {
     int B, T;
 };
 
-int launch_sgemm(int M, int N, int K, const float* A, long long sam, long long sak, const float* B, long long sbk,
-                 long long sbn, float* C, int ldc, const float* bias, int beta, int split_k, cudaStream_t s);
-int launch_colsum(const float* A, int M, int N, float* out, cudaStream_t s);
+struct GemmProblem {
+    int M, N, K;
+    const float* A; long long sam, sak;     // A(m,k) = A[m*sam + k*sak]
+    const float* B; long long sbk, sbn;     // B(k,n) = B[k*sbk + n*sbn]
+    float* C; int ldc;
+    const float* bias;                       // nullable, added once
+};
+struct GemmBatch {
+    GemmProblem p[8];
+    int n;          // problems in this launch
+    int split;      // K slices per problem
+    int mode;       // 0: C = result (split must be 1); 1: atomicAdd into C
+};
+struct ColsumBatch {
+    const float* A[4];   // [M][N] each
+    float* out[4];       // [N] each, accumulated with atomics
+    int n, M, N;
+};
+
+int launch_sgemm_batch(const GemmBatch& g, cudaStream_t s);
+int launch_colsum_batch(const ColsumBatch& c, cudaStream_t s);
 int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t s);
 int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s);
