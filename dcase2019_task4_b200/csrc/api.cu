@@ -224,6 +224,9 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    DCASE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     int rc = dcase_logmel_tables_create(ctx);
     if (rc == DCASE_OK) rc = cnn_kernels_init();
     if (rc == DCASE_OK) rc = conv_tc_kernels_init();
@@ -236,6 +239,9 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
 int dcase_ctx_destroy(dcase_ctx* ctx) {
     if (!ctx) return DCASE_OK;
     dcase_logmel_tables_destroy(ctx);
+    cudaStreamDestroy(ctx->aux_stream);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
     delete ctx;
     return DCASE_OK;
 }
@@ -486,13 +492,20 @@ int dcase_adam_ema_step(dcase_ctx* ctx, float* p, const float* g, float* m, floa
 int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* a, void* stream) {
     DCASE_REQUIRE(ctx && a, "null argument");
     const int To = a->T / 8;
+    cudaStream_t s = (cudaStream_t)stream;
     if (a->x_teacher) {
+        // the teacher forward (no grad, main.py:87-89) is independent of the student forward until the losses:
+        // fork it onto the context's second stream so the two overlap (latency-bound GRU / single-CTA kernels)
         DCASE_REQUIRE(a->params_t && a->bn_t && a->strong_t && a->weak_t && a->ws_t, "teacher buffers missing");
+        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
+        DCASE_CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
         DCASE_TRY(dcase_crnn_forward(ctx, a->x_teacher, a->B, a->T, a->n_class, a->params_t, a->bn_t, a->flags, a->seed,
-                                     a->step, 1, a->scalars, a->strong_t, a->weak_t, a->ws_t, stream));
+                                     a->step, 1, a->scalars, a->strong_t, a->weak_t, a->ws_t, ctx->aux_stream));
+        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     }
     DCASE_TRY(dcase_crnn_forward(ctx, a->x_student, a->B, a->T, a->n_class, a->params_s, a->bn_s, a->flags, a->seed,
                                  a->step, 0, a->scalars, a->strong_s, a->weak_s, a->ws_s, stream));
+    if (a->x_teacher) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     DCASE_TRY(dcase_mt_loss(ctx, a->strong_s, a->weak_s, a->x_teacher ? a->strong_t : nullptr,
                             a->x_teacher ? a->weak_t : nullptr, a->target, a->B, To, a->n_class, a->weak_lo, a->weak_hi,
                             a->strong_lo, a->strong_hi, a->cons_weight, a->scalars, a->meters, a->d_strong, a->d_weak,

@@ -14,6 +14,9 @@ struct dcase_ctx {
     int* d_mel_len;      // [64] band length
     int* d_mel_off;      // [64] offset into d_mel_w
     int mel_nnz;
+    // second stream + events: the teacher forward runs concurrently with the student forward (dcase_mt_fwd_bwd)
+    cudaStream_t aux_stream;
+    cudaEvent_t ev_fork, ev_join;
     // host copy of the dense filterbank for dcase_mel_filterbank()
     float* h_mel_dense;  // [64 * 1025]
 };
