@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int kTile = 128;   // pixels per tile = threads per CTA
+constexpr int kTile = 128;   // pixels per tile
 constexpr float kBnEps = 1e-3f;
 constexpr float kBnMomentum = 0.99f;
 
@@ -163,15 +163,22 @@ struct Sw128Row {    // two SW128 blocks of 128 rows (tc.cuh): K-major tcgen05 o
     }
 };
 
+// Thread mapping of the GLU kernels: 256 threads per 128-pixel tile, two threads per pixel row.
+//   row  = tid & 127   (warp w reads TMEM lanes 32*(w & 3) .. +31, the lanes of its row)
+//   half = tid >> 7    (channels 32*half .. 32*half + 31  = chunks 8*half .. 8*half + 7)
+constexpr int kThreads = 256;
+
+// y (BN output) of this thread's 32 channels into its smem row; L0 recomputes conv0 from the 9 taps.
 template <bool L0, typename RowT>
-__device__ __forceinline__ void produce_y_row(const GluArgs& a, long long p, bool valid, const float* aff_s,
-                                              const float* xs, RowT a_row, float (&tap)[9]) {
+__device__ __forceinline__ void produce_y_half(const GluArgs& a, long long p, bool valid, const float* aff_s,
+                                               const float* xs, RowT a_row, int row, int half, float (&tap)[9]) {
     if (L0) {
-        const int tr = threadIdx.x >> 6, f = threadIdx.x & 63;
+        const int tr = row >> 6, f = row & 63;
 #pragma unroll
         for (int k = 0; k < 9; ++k) tap[k] = xs[(tr + k / 3) * 66 + f + (k % 3)];
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
+        for (int q = 0; q < 8; ++q) {
+            const int c4 = 8 * half + q;
             float4 y = *reinterpret_cast<const float4*>(aff_s + kFold0Bf + 4 * c4);
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
@@ -184,7 +191,8 @@ __device__ __forceinline__ void produce_y_row(const GluArgs& a, long long p, boo
     } else {
         const float4* src = reinterpret_cast<const float4*>(a.src + p * 64);
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
+        for (int q = 0; q < 8; ++q) {
+            const int c4 = 8 * half + q;
             float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 const float4 v = __ldg(src + c4);
@@ -203,12 +211,20 @@ __device__ __forceinline__ void load_xs(const float* __restrict__ x, long long t
     const long long r0 = 2 * tile;
     const long long b = r0 / T;
     const int t0 = (int)(r0 % T);
-    for (int i = threadIdx.x; i < 4 * 66; i += kTile) {
+    for (int i = threadIdx.x; i < 4 * 66; i += kThreads) {
         const int hr = i / 66, hc = i % 66;
         const int tt = t0 - 1 + hr, ff = hc - 1;
         const bool ok = tt >= 0 && tt < T && ff >= 0 && ff < 64;
         xs[i] = ok ? __ldg(x + (b * T + tt) * 64 + ff) : 0.f;
     }
+}
+
+// 32 accumulator columns [col, col + 32) of this thread's row
+__device__ __forceinline__ void tmem_ld_row32(uint32_t tmem_base, int warp, int col, float (&v)[32]) {
+    const uint32_t t = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
+    tc::tmem_ld16(t, v);
+    tc::tmem_ld16(t + 16, v + 16);
+    tc::tmem_ld_wait();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -218,12 +234,12 @@ __device__ __forceinline__ void load_xs(const float* __restrict__ x, long long t
 //                        A   K-major A operand  y[p][k]      2 x [128][128 B]  32 KB (reused for z)
 //                        bg[64] | aff (fold0 / bn) | xs[4][66]
 // The 64x64 channel GEMM  lin = y Wg^T  runs on the tensor core (tcgen05.mma kind::tf32, fp32 accumulate in
-// TMEM, 64 columns); CUDA cores do conv0 / BN, the gate, dropout and the pooling.  Several CTAs per SM overlap
-// one CTA's MMA with the others' CUDA-core phases.
+// TMEM, 64 columns); CUDA cores do conv0 / BN, the gate, dropout and the pooling.  Four CTAs (32 warps) per SM
+// overlap one CTA's MMA with the others' CUDA-core phases.
 constexpr int kGluFwdSmemBytes = 1024 + 16384 + 32768 + (64 + 832 + 4 * 66) * 4;
 
 template <bool L0>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kThreads, 4)
 glu_pool_fwd_kernel(GluArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -235,13 +251,14 @@ glu_pool_fwd_kernel(GluArgs a) {
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, half = tid >> 7;
 
-    for (int i = tid; i < 4096; i += kTile) {      // Wg[n][k] -> block k/32, row n, swizzled
+    for (int i = tid; i < 4096; i += kThreads) {      // Wg[n][k] -> block k/32, row n, swizzled
         const int n = i >> 6, k = i & 63;
         *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = __ldg(a.glu_w + i);
     }
     if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
-    for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kTile) aff_s[i] = a.aff[i];
+    for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kThreads) aff_s[i] = a.aff[i];
     if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
     uint64_t seed; uint32_t step;
@@ -257,13 +274,13 @@ glu_pool_fwd_kernel(GluArgs a) {
     const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
     const long long n_out = a.n_pix >> 3;
     const int wpr = a.F >> 2;
-    const Sw128Row a_row{A, tid};
+    const Sw128Row a_row{A, row};
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long p = tile * kTile + tid;
+        const long long p = tile * kTile + row;
         const bool valid = p < a.n_pix;
         if (L0) { load_xs(a.src, tile, a.T, xs); __syncthreads(); }
         float tap[9];
-        produce_y_row<L0>(a, p, valid, aff_s, xs, a_row, tap);
+        produce_y_half<L0>(a, p, valid, aff_s, xs, a_row, row, half, tap);
         tc::fence_proxy_async();                 // y tile -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
@@ -271,54 +288,50 @@ glu_pool_fwd_kernel(GluArgs a) {
             tc::umma_128x64x64_kmajor(tmem, a_addr, b_addr, false);
             tc::umma_commit(&mma_bar);
         }
-        uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+        uint32_t keep = 0xffffffffu;             // keep bits of channels 32*half .. +31 (overlaps the MMA)
         float scale = 1.f;
-        if (a.drop.enabled) {                    // overlaps the MMA
+        if (a.drop.enabled) {
             const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
-            keep_lo = r.x; keep_hi = r.y; scale = 2.f;
+            keep = half ? r.y : r.x; scale = 2.f;
         }
         tc::mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc::fence_after_sync();
-        float acc[64];
-        tc::tmem_ld_row64(tmem, warp, 0, acc);
+        float acc[32];
+        tmem_ld_row32(tmem, warp, 32 * half, acc);
         tc::fence_before_sync();
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-            float4* slot = a_row.chunk(c4);
+        for (int q = 0; q < 8; ++q) {
+            float4* slot = a_row.chunk(8 * half + q);
             const float4 y = *slot;
-            const float4 b4 = *reinterpret_cast<const float4*>(bg + 4 * c4);
-            const uint32_t bits = (c4 < 8 ? keep_lo : keep_hi) >> ((4 * c4) & 31);
+            const float4 b4 = *reinterpret_cast<const float4*>(bg + 32 * half + 4 * q);
+            const uint32_t bits = keep >> (4 * q);
             float4 z;
-            z.x = (bits & 1u) ? (acc[4 * c4 + 0] + b4.x) * sigmoid_fast(y.x) * scale : 0.f;
-            z.y = (bits & 2u) ? (acc[4 * c4 + 1] + b4.y) * sigmoid_fast(y.y) * scale : 0.f;
-            z.z = (bits & 4u) ? (acc[4 * c4 + 2] + b4.z) * sigmoid_fast(y.z) * scale : 0.f;
-            z.w = (bits & 8u) ? (acc[4 * c4 + 3] + b4.w) * sigmoid_fast(y.w) * scale : 0.f;
+            z.x = (bits & 1u) ? (acc[4 * q + 0] + b4.x) * sigmoid_fast(y.x) * scale : 0.f;
+            z.y = (bits & 2u) ? (acc[4 * q + 1] + b4.y) * sigmoid_fast(y.y) * scale : 0.f;
+            z.z = (bits & 4u) ? (acc[4 * q + 2] + b4.z) * sigmoid_fast(y.z) * scale : 0.f;
+            z.w = (bits & 8u) ? (acc[4 * q + 3] + b4.w) * sigmoid_fast(y.w) * scale : 0.f;
             if (!valid) z = make_float4(0.f, 0.f, 0.f, 0.f);
             *slot = z;
         }
         __syncthreads();
-        {   // pooling: 16 windows x 8 channel groups
-            const int w = tid >> 3, cg = tid & 7;
+        {   // pooling: 16 windows x 16 channel quads
+            const int w = tid >> 4, cq = tid & 15;
             const int wr = w / wpr, wc = w - wr * wpr;
             const int r0 = (2 * wr) * a.F + 4 * wc;
-            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const Sw128Row row{A, r0 + i * a.F + j};
-                    const float4 u = *row.chunk(2 * cg);
-                    const float4 v = *row.chunk(2 * cg + 1);
+                    const Sw128Row rr{A, r0 + i * a.F + j};
+                    const float4 u = *rr.chunk(cq);
                     s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
-                    s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
                 }
             const long long op = tile * 16 + w;
-            if (op < n_out) {
-                float4* dst = reinterpret_cast<float4*>(a.out + op * 64 + 8 * cg);
-                dst[0] = make_float4(0.125f * s0.x, 0.125f * s0.y, 0.125f * s0.z, 0.125f * s0.w);
-                dst[1] = make_float4(0.125f * s1.x, 0.125f * s1.y, 0.125f * s1.z, 0.125f * s1.w);
-            }
+            if (op < n_out)
+                *reinterpret_cast<float4*>(a.out + op * 64 + 4 * cq) =
+                    make_float4(0.125f * s0.x, 0.125f * s0.y, 0.125f * s0.z, 0.125f * s0.w);
         }
         __syncthreads();
     }
@@ -351,7 +364,7 @@ constexpr int kBwdWb = 0, kBwdWm = 16384, kBwdP = 32768, kBwdQ1 = 65536, kBwdExt
 constexpr int kGluBwdSmemBytes = 1024 + kBwdMisc + (64 + 832 + 128 + 4 * 66) * 4;
 
 template <bool L0>
-__global__ void __launch_bounds__(kTile, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 glu_pool_bwd_kernel(GluArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -368,8 +381,9 @@ glu_pool_bwd_kernel(GluArgs a) {
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & 127, half = tid >> 7;
 
-    for (int i = tid; i < 4096; i += kTile) {
+    for (int i = tid; i < 4096; i += kThreads) {
         const int n = i >> 6, k = i & 63;
         const float w = __ldg(a.glu_w + i);
         *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = w;
@@ -383,9 +397,9 @@ glu_pool_bwd_kernel(GluArgs a) {
             gb[64 + tid] = __ldg(a.beta + tid);
         }
     }
-    for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kTile) aff_s[i] = a.aff[i];
-    {   // EXT row of this thread: [1, 0...] (L0 rewrites it with the taps every tile)
-        const B32Row ext{EXT, tid};
+    for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kThreads) aff_s[i] = a.aff[i];
+    if (half == 0) {   // EXT row of this pixel: [1, 0...] (L0 rewrites it with the taps every tile)
+        const B32Row ext{EXT, row};
         *ext.chunk(0) = make_float4(1.f, 0.f, 0.f, 0.f);
         *ext.chunk(1) = make_float4(0.f, 0.f, 0.f, 0.f);
         *ext.chunk(2) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -408,20 +422,20 @@ glu_pool_bwd_kernel(GluArgs a) {
 
     const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
     const int wpr = a.F >> 2;
-    const Sw128Row p_row{P, tid};
-    const B32Row y32_row{Q1, tid}, q2_row{Q2, tid}, ext_row{EXT, tid};
+    const Sw128Row p_row{P, row};
+    const B32Row y32_row{Q1, row}, q2_row{Q2, row}, ext_row{EXT, row};
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long p = tile * kTile + tid;
+        const long long p = tile * kTile + row;
         const bool valid = p < a.n_pix;
         if (L0) { load_xs(a.src, tile, a.T, xs); }
         if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; pending = false; }
         if (L0) __syncthreads();
         float tap[9];
-        produce_y_row<L0>(a, p, valid, aff_s, xs, p_row, tap);
+        produce_y_half<L0>(a, p, valid, aff_s, xs, p_row, row, half, tap);
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) *y32_row.chunk(c4) = *p_row.chunk(c4);
-        if (L0) {
+        for (int q = 0; q < 8; ++q) *y32_row.chunk(8 * half + q) = *p_row.chunk(8 * half + q);
+        if (L0 && half == 0) {
             *ext_row.chunk(0) = make_float4(1.f, tap[0], tap[1], tap[2]);
             *ext_row.chunk(1) = make_float4(tap[3], tap[4], tap[5], tap[6]);
             *ext_row.chunk(2) = make_float4(tap[7], tap[8], 0.f, 0.f);
@@ -434,46 +448,46 @@ glu_pool_bwd_kernel(GluArgs a) {
             tc::umma_commit(&mma_bar);
         }
         // pooled-output gradient of this pixel's window, dropout mask and 1/8 folded in (overlaps G1)
-        float dz[64];
+        float dz[32];
         {
-            uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+            uint32_t keep = 0xffffffffu;
             float scale = 0.125f;
             if (a.drop.enabled) {
                 const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
-                keep_lo = r.x; keep_hi = r.y; scale = 0.25f;
+                keep = half ? r.y : r.x; scale = 0.25f;
             }
-            const int tr = tid / a.F, f = tid - tr * a.F;
+            const int tr = row / a.F, f = row - tr * a.F;
             const long long op = tile * 16 + (tr >> 1) * wpr + (f >> 2);
-            const float4* dsrc = reinterpret_cast<const float4*>(a.d_out + op * 64);
+            const float4* dsrc = reinterpret_cast<const float4*>(a.d_out + op * 64) + 8 * half;
 #pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) {
-                const float4 d = valid ? __ldg(dsrc + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const uint32_t bits = (c4 < 8 ? keep_lo : keep_hi) >> ((4 * c4) & 31);
-                dz[4 * c4 + 0] = (bits & 1u) ? d.x * scale : 0.f;
-                dz[4 * c4 + 1] = (bits & 2u) ? d.y * scale : 0.f;
-                dz[4 * c4 + 2] = (bits & 4u) ? d.z * scale : 0.f;
-                dz[4 * c4 + 3] = (bits & 8u) ? d.w * scale : 0.f;
+            for (int q = 0; q < 8; ++q) {
+                const float4 d = valid ? __ldg(dsrc + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const uint32_t bits = keep >> (4 * q);
+                dz[4 * q + 0] = (bits & 1u) ? d.x * scale : 0.f;
+                dz[4 * q + 1] = (bits & 2u) ? d.y * scale : 0.f;
+                dz[4 * q + 2] = (bits & 4u) ? d.z * scale : 0.f;
+                dz[4 * q + 3] = (bits & 8u) ? d.w * scale : 0.f;
             }
         }
         tc::mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc::fence_after_sync();
-        float acc[64];
-        tc::tmem_ld_row64(tmem, warp, 0, acc);                                // lin (without bias)
+        float acc[32];
+        tmem_ld_row32(tmem, warp, 32 * half, acc);                            // lin (without bias)
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-            float4* slot = p_row.chunk(c4);
+        for (int q = 0; q < 8; ++q) {
+            float4* slot = p_row.chunk(8 * half + q);
             const float4 y = *slot;
-            const float4 b4 = *reinterpret_cast<const float4*>(bg + 4 * c4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bg + 32 * half + 4 * q);
             const float gx = sigmoid_fast(y.x), gy = sigmoid_fast(y.y), gz = sigmoid_fast(y.z), gw = sigmoid_fast(y.w);
-            const float4 dl = make_float4(dz[4 * c4] * gx, dz[4 * c4 + 1] * gy, dz[4 * c4 + 2] * gz, dz[4 * c4 + 3] * gw);
+            const float4 dl = make_float4(dz[4 * q] * gx, dz[4 * q + 1] * gy, dz[4 * q + 2] * gz, dz[4 * q + 3] * gw);
             *slot = dl;                       // P: Y -> DL (G1 has completed)
-            *q2_row.chunk(c4) = dl;
+            *q2_row.chunk(8 * half + q) = dl;
             // direct path through the gate: dz * lin * g * (1 - g)
-            acc[4 * c4 + 0] = dz[4 * c4 + 0] * (acc[4 * c4 + 0] + b4.x) * gx * (1.f - gx);
-            acc[4 * c4 + 1] = dz[4 * c4 + 1] * (acc[4 * c4 + 1] + b4.y) * gy * (1.f - gy);
-            acc[4 * c4 + 2] = dz[4 * c4 + 2] * (acc[4 * c4 + 2] + b4.z) * gz * (1.f - gz);
-            acc[4 * c4 + 3] = dz[4 * c4 + 3] * (acc[4 * c4 + 3] + b4.w) * gw * (1.f - gw);
+            acc[4 * q + 0] = dz[4 * q + 0] * (acc[4 * q + 0] + b4.x) * gx * (1.f - gx);
+            acc[4 * q + 1] = dz[4 * q + 1] * (acc[4 * q + 1] + b4.y) * gy * (1.f - gy);
+            acc[4 * q + 2] = dz[4 * q + 2] * (acc[4 * q + 2] + b4.z) * gz * (1.f - gz);
+            acc[4 * q + 3] = dz[4 * q + 3] * (acc[4 * q + 3] + b4.w) * gw * (1.f - gw);
         }
         tc::fence_proxy_async();
         tc::fence_before_sync();
@@ -500,14 +514,14 @@ glu_pool_bwd_kernel(GluArgs a) {
         phase ^= 1;
         tc::fence_after_sync();
         {
-            float d2[64];
-            tc::tmem_ld_row64(tmem, warp, 64, d2);
+            float d2[32];
+            tmem_ld_row32(tmem, warp, 64 + 32 * half, d2);
 #pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) {
-                const float4 v = make_float4(acc[4 * c4] + d2[4 * c4], acc[4 * c4 + 1] + d2[4 * c4 + 1],
-                                             acc[4 * c4 + 2] + d2[4 * c4 + 2], acc[4 * c4 + 3] + d2[4 * c4 + 3]);
-                *q2_row.chunk(c4) = v;        // Q2: DL -> dY (G3 has completed)
-                if (!L0 && valid) reinterpret_cast<float4*>(a.d_y + p * 64)[c4] = v;
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = make_float4(acc[4 * q] + d2[4 * q], acc[4 * q + 1] + d2[4 * q + 1],
+                                             acc[4 * q + 2] + d2[4 * q + 2], acc[4 * q + 3] + d2[4 * q + 3]);
+                *q2_row.chunk(8 * half + q) = v;        // Q2: DL -> dY (G3 has completed)
+                if (!L0 && valid) reinterpret_cast<float4*>(a.d_y + p * 64)[8 * half + q] = v;
             }
         }
         tc::fence_proxy_async();
@@ -536,7 +550,7 @@ glu_pool_bwd_kernel(GluArgs a) {
     }
     if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; }
     tc::fence_after_sync();
-    if (!first) {
+    if (!first && warp < 4) {
         // accumulator row m of an M=64 MMA lives in TMEM lane 32*(m/16) + m%16: warp w, lanes 0..15 -> m = 16w + lane
         const int m = 16 * warp + lane;
         const bool own = lane < 16;
@@ -680,7 +694,7 @@ int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const
     a.src = x; a.n_pix = (long long)B * T * 64; a.T = T; a.F = 64; a.aff = fold0;
     a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
     const long long n_tiles = a.n_pix / kTile;
-    glu_pool_fwd_kernel<true><<<grid_for(n_tiles, num_sms, 4), kTile, kGluFwdSmem, s>>>(a);
+    glu_pool_fwd_kernel<true><<<grid_for(n_tiles, num_sms, 4), kThreads, kGluFwdSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
@@ -691,7 +705,7 @@ int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* 
     GluArgs a{};
     a.src = ypre; a.n_pix = n_pix; a.F = F; a.aff = bn; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
     const long long n_tiles = (n_pix + kTile - 1) / kTile;
-    glu_pool_fwd_kernel<false><<<grid_for(n_tiles, num_sms, 4), kTile, kGluFwdSmem, s>>>(a);
+    glu_pool_fwd_kernel<false><<<grid_for(n_tiles, num_sms, 4), kThreads, kGluFwdSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
@@ -713,7 +727,7 @@ int launch_glu_pool_bwd0(const float* x, int B, int T, const float* fold0, const
     a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.stat_acc = acc0;
     a.g_glu_w = g_glu_w; a.g_glu_b = g_glu_b;
     const long long n_tiles = a.n_pix / kTile;
-    glu_pool_bwd_kernel<true><<<grid_for(n_tiles, num_sms, 1), kTile, kGluBwdSmem, s>>>(a);
+    glu_pool_bwd_kernel<true><<<grid_for(n_tiles, num_sms, 1), kThreads, kGluBwdSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
@@ -728,7 +742,7 @@ int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* 
     a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.d_y = d_y; a.stat_acc = s12;
     a.g_glu_w = g_glu_w; a.g_glu_b = g_glu_b;
     const long long n_tiles = (n_pix + kTile - 1) / kTile;
-    glu_pool_bwd_kernel<false><<<grid_for(n_tiles, num_sms, 1), kTile, kGluBwdSmem, s>>>(a);
+    glu_pool_bwd_kernel<false><<<grid_for(n_tiles, num_sms, 1), kThreads, kGluBwdSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

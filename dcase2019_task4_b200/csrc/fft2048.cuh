@@ -48,6 +48,11 @@ __host__ __device__ __forceinline__ void fft8(cf32* v) {
     }
 }
 
+// Shared-memory index padding: one extra slot per 8 complex values makes the stride-8 writes of the first two
+// passes (index 8 j + r across the lanes j) conflict-free while stride-1 accesses stay conflict-free.
+__host__ __device__ __forceinline__ int fft_pad(int i) { return i + (i >> 3); }
+constexpr int kFftPaddedSize = 2048 + 256;
+
 // One Stockham pass of radix R for "thread" j (0 <= j < 2048 / R). Ns = product of the radices
 // of the passes already done. tw[m] = exp(-2 pi i m / 2048).
 template <int R>
@@ -59,11 +64,11 @@ __host__ __device__ __forceinline__ void stockham_pass(int j, int Ns, const cf32
     const int tw_stride = N / (Ns * R);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        v[r] = src[j + r * (N / R)];
+        v[r] = src[fft_pad(j + r * (N / R))];
         if (r > 0) v[r] = cmul(v[r], tw[r * k * tw_stride]);
     }
     if (R == 8) fft8(v); else fft4(v);
     const int d = (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[d + r * Ns] = v[r];
+    for (int r = 0; r < R; ++r) dst[fft_pad(d + r * Ns)] = v[r];
 }

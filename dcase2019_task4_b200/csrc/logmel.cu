@@ -58,9 +58,9 @@ __global__ void __launch_bounds__(256, 2)
 stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, float* __restrict__ mel_amp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* span = reinterpret_cast<float*>(smem_raw);                 // [kSpan] (+pad)
-    cf32* bufA = reinterpret_cast<cf32*>(span + 9728);                // [2048]
-    cf32* bufB = bufA + kNfft;                                        // [2048]
-    cf32* tw = bufB + kNfft;                                          // [2048]
+    cf32* bufA = reinterpret_cast<cf32*>(span + 9728);                // [2304] (padded, fft_pad)
+    cf32* bufB = bufA + kFftPaddedSize;                               // [2304]
+    cf32* tw = bufB + kFftPaddedSize;                                 // [2048]
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
@@ -90,7 +90,7 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, flo
             }
             fft8(v);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) bufA[tid * 8 + r] = v[r];
+            for (int r = 0; r < 8; ++r) bufA[fft_pad(tid * 8 + r)] = v[r];
         }
         __syncthreads();
         stockham_pass<8>(tid, 8, bufA, bufB, tw);
@@ -103,8 +103,8 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, flo
         // separate the two real spectra and take magnitudes (bins 0..1024)
         float* mag = reinterpret_cast<float*>(bufA);  // [2][kMagPitch]
         for (int k = tid; k < kBins; k += 256) {
-            const cf32 zk = bufB[k];
-            const cf32 zn = bufB[(kNfft - k) & (kNfft - 1)];
+            const cf32 zk = bufB[fft_pad(k)];
+            const cf32 zn = bufB[fft_pad((kNfft - k) & (kNfft - 1))];
             const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
             const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
             mag[k] = sqrtf(ar * ar + ai * ai);
@@ -232,7 +232,7 @@ double mel_to_hz(double m) {
     return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
 }
 
-constexpr size_t kStftSmemBytes = 9728 * sizeof(float) + 3 * kNfft * sizeof(cf32);
+constexpr size_t kStftSmemBytes = 9728 * sizeof(float) + (2 * kFftPaddedSize + kNfft) * sizeof(cf32);
 
 }  // namespace
 

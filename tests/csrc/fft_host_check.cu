@@ -8,7 +8,7 @@
 
 int main() {
     const int N = 2048;
-    std::vector<cf32> tw(N), a(N), b(N);
+    std::vector<cf32> tw(N), a(kFftPaddedSize), b(kFftPaddedSize);
     for (int m = 0; m < N; ++m) {
         double ang = -2.0 * M_PI * m / N;
         tw[m] = cf32{(float)cos(ang), (float)sin(ang)};
@@ -18,7 +18,7 @@ int main() {
     for (int i = 0; i < N; ++i) {
         xr[i] = rand() / (double)RAND_MAX - 0.5;
         xi[i] = rand() / (double)RAND_MAX - 0.5;
-        a[i] = cf32{(float)xr[i], (float)xi[i]};
+        a[fft_pad(i)] = cf32{(float)xr[i], (float)xi[i]};
     }
     for (int j = 0; j < 256; ++j) stockham_pass<8>(j, 1, a.data(), b.data(), tw.data());
     for (int j = 0; j < 256; ++j) stockham_pass<8>(j, 8, b.data(), a.data(), tw.data());
@@ -32,7 +32,7 @@ int main() {
             sr += xr[n] * cos(ang) - xi[n] * sin(ang);
             si += xr[n] * sin(ang) + xi[n] * cos(ang);
         }
-        maxerr = fmax(maxerr, hypot(sr - a[k].x, si - a[k].y));
+        maxerr = fmax(maxerr, hypot(sr - a[fft_pad(k)].x, si - a[fft_pad(k)].y));
         maxmag = fmax(maxmag, hypot(sr, si));
     }
     printf("max_abs_err %.3e max_mag %.3e\n", maxerr, maxmag);
