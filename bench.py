@@ -191,7 +191,7 @@ def run_b200(args, rank, local_rank, world):
     import torch.distributed as dist
     from dcase2019_task4_b200 import config as cfg
     from dcase2019_task4_b200 import kernels as K
-    from dcase2019_task4_b200.main import MeanTeacherEngine
+    from dcase2019_task4_b200.main import HostBatchPrefetcher, MeanTeacherEngine
     from dcase2019_task4_b200.models.CRNN import CRNN
     from dcase2019_task4_b200.utils import ramps
     from dcase2019_task4_b200.utils.utils import weights_init
@@ -248,14 +248,18 @@ def run_b200(args, rank, local_rank, world):
                                    state["gs"] + 1, check=False)
         state["gs"] += 1
 
-    stage_w = torch.empty(B_PER_GPU, N_SAMPLES, device=dev)
-    stage_t = torch.empty(B_PER_GPU, FRAMES // 8, 10, device=dev)
+    prefetch = HostBatchPrefetcher(dev, (B_PER_GPU, N_SAMPLES), (B_PER_GPU, FRAMES // 8, 10))
 
     def e2e_step(i):
-        """Public-API call with HOST buffers: H2D of the clips and targets, the step, D2H of the meters."""
-        stage_w.copy_(wave_host[i % n_pool], non_blocking=True)
-        stage_t.copy_(target_host[i % n_pool], non_blocking=True)
-        engine.step_from_waveforms(stage_w, stage_t, mean, std, cons_weight(), state["gs"] + 1, check=False)
+        """Public-API call with HOST buffers: every step copies its clips and targets from pinned host memory
+        (double-buffered on a copy stream, overlapping the previous step's kernels), runs the step and reads the
+        meters back (the loss assertion of main.py:147-148)."""
+        if i == 0:
+            prefetch.submit(wave_host[0], target_host[0])
+        prefetch.submit(wave_host[(i + 1) % n_pool], target_host[(i + 1) % n_pool])
+        w, t = prefetch.next()
+        engine.step_from_waveforms(w, t, mean, std, cons_weight(), state["gs"] + 1, check=False)
+        prefetch.release()
         state["gs"] += 1
         return engine.check_loss()                                  # syncs on the 32-byte meter copy
 
@@ -289,9 +293,7 @@ def run_b200(args, rank, local_rank, world):
     value = world * B_PER_GPU * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ----
-    for i in range(2):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = timed(e2e_step, args.steps)          # (pipeline primed by the first step; no separate warm-up needed)
     e2e_value = world * B_PER_GPU * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel durations (CUDA events on the launching stream, separate pass) ----

@@ -417,7 +417,7 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
             cb.A[2 * d] = dgi_d; cb.out[2 * d] = grads + o.b_ih[l][d];
             cb.A[2 * d + 1] = dgh_d; cb.out[2 * d + 1] = grads + o.b_hh[l][d];
         }
-        gb.n = 6; gb.split = BT >= 512 ? 4 : 1; gb.mode = 1;
+        gb.n = 6; gb.split = BT >= 512 ? 16 : 1; gb.mode = 1;
         cb.n = 4; cb.M = BT; cb.N = 3 * kH;
         DCASE_TRY(launch_sgemm_batch(gb, s));
         DCASE_TRY(launch_colsum_batch(cb, s));

@@ -110,7 +110,7 @@ conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const flo
     const uint32_t tmem = tmem_base_s;
     const uint32_t w_a = tc::smem_u32(Wi), h_a = tc::smem_u32(halo);
     uint32_t phase = 0;
-    double stat_acc = 0.0;
+    double stat_sum = 0.0, stat_sq = 0.0;
     const int ti = tid >> 3, j = tid & 7;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -159,15 +159,24 @@ conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const flo
                     valid ? make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3])
                           : make_float4(0.f, 0.f, 0.f, 0.f);
             __syncthreads();
-            float s = 0.f;
-            const int c = tid & 63;
-            if (tid < 64) { for (int q = 0; q < kTile; ++q) s += tile_s[q * 68 + c]; }
-            else { for (int q = 0; q < kTile; ++q) { const float v = tile_s[q * 68 + c]; s = fmaf(v, v, s); } }
-            stat_acc += (double)s;
+            // thread (c, h) reduces rows 64h .. 64h+63 of channel c: sum and sum of squares in one pass
+            const int c = tid & 63, h = tid >> 6;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 16
+            for (int q = 0; q < 64; ++q) {
+                const float v = tile_s[(64 * h + q) * 68 + c];
+                s1 += v;
+                s2 = fmaf(v, v, s2);
+            }
+            stat_sum += (double)s1;
+            stat_sq += (double)s2;
         }
         __syncthreads();
     }
-    if (STATS) atomicAdd(stats + tid, stat_acc);       // [0,64): sum, [64,128): sum of squares
+    if (STATS) {                                       // [0,64): sum, [64,128): sum of squares
+        atomicAdd(stats + (tid & 63), stat_sum);
+        atomicAdd(stats + 64 + (tid & 63), stat_sq);
+    }
     if (tid == 0 && n_tiles <= (int)blockIdx.x) tc::mbar_wait(&w_bar, 0);   // never leave with a bulk copy in flight
     tc::fence_before_sync();
     __syncthreads();

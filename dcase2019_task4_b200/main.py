@@ -182,6 +182,44 @@ class MeanTeacherEngine(object):
         return loss
 
 
+class HostBatchPrefetcher(object):
+    """Double-buffered host -> device staging of (waveform, target) batches on a copy stream, so the H2D copy of
+    batch i+1 overlaps the kernels of batch i.  Host tensors should be pinned (``tensor.pin_memory()``)."""
+
+    def __init__(self, device, wave_shape, target_shape, wave_dtype=torch.float32, slots=2):
+        self.dev = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.wave = [torch.empty(wave_shape, dtype=wave_dtype, device=self.dev) for _ in range(slots)]
+        self.target = [torch.empty(target_shape, dtype=torch.float32, device=self.dev) for _ in range(slots)]
+        self.copied = [torch.cuda.Event() for _ in range(slots)]
+        self.consumed = [torch.cuda.Event() for _ in range(slots)]
+        self.slots, self.head, self.tail, self.used = slots, 0, 0, [False] * slots
+
+    def submit(self, wave_host, target_host):
+        """Enqueue the copy of one host batch into the next free slot (waits for that slot's last consumer)."""
+        k = self.head % self.slots
+        self.head += 1
+        with torch.cuda.stream(self.copy_stream):
+            if self.used[k]:
+                self.copy_stream.wait_event(self.consumed[k])
+            self.wave[k].copy_(wave_host, non_blocking=True)
+            self.target[k].copy_(target_host, non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+        self.used[k] = True
+
+    def next(self):
+        """Device tensors of the oldest submitted batch; the current stream waits for its copy."""
+        k = self.tail % self.slots
+        torch.cuda.current_stream(self.dev).wait_event(self.copied[k])
+        return self.wave[k], self.target[k]
+
+    def release(self):
+        """Call after the kernels consuming the batch returned by ``next`` have been enqueued."""
+        k = self.tail % self.slots
+        self.tail += 1
+        self.consumed[k].record(torch.cuda.current_stream(self.dev))
+
+
 def _engine_for(model, optimizer, ema_model, weak_mask, strong_mask, B, T):
     key = (id(optimizer), id(ema_model), B, T, repr(weak_mask), repr(strong_mask))
     cache = model.__dict__.setdefault("_mt_engines", {})
