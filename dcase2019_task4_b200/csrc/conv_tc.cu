@@ -77,10 +77,33 @@ __device__ __forceinline__ void load_halo(const float* __restrict__ in, const Ti
     }
 }
 
-template <bool STATS>
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;     // src-size 0: nothing is read, 16 zero bytes are written
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
+}
+
+// asynchronous (register-free) staging of the 18 x PITCH halo of a tile, K-major SW128 layout, zero fill outside the clip
+__device__ __forceinline__ void prefetch_halo(const float* __restrict__ in, const TileGeom& g, int T_l, int F, int pitch,
+                                              unsigned char* halo) {
+    const int n_items = 18 * pitch * 16;
+    for (int idx = threadIdx.x; idx < n_items; idx += kTile) {
+        const int q = idx & 15;
+        const int hp = idx >> 4;
+        const int hr = hp / pitch, hs = hp - hr * pitch;
+        const int t = g.t0 - 1 + hr, f = g.f0 - 1 + hs;
+        const bool ok = t >= 0 && t < T_l && f >= 0 && f < F;
+        const float4* src = reinterpret_cast<const float4*>(in) + (ok ? (((long long)g.b * T_l + t) * F + f) * 16 + q : 0);
+        cp_async16_zfill(halo + (q >> 3) * kHaloBlk + tc::sw128_chunk(hp, q & 7), src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Software pipeline per CTA (persistent over its tiles, single halo buffer, two TMEM accumulators):
+//   wait halo(i) | issue MMA(i) -> TMEM[i & 1] | epilogue(i-1) from TMEM[(i-1) & 1] overlaps MMA(i) |
+//   wait MMA(i) | cp.async halo(i+1) (the buffer is free once MMA(i) has completed)
 __global__ void __launch_bounds__(kTile, 1)
 conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const float* __restrict__ w_img,
-                  const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats) {
+                  const float* __restrict__ bias, float* __restrict__ out) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* Wi = smem;                          // weight image, 144 KB
@@ -103,25 +126,44 @@ conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const flo
     }
     if (tid < 64) bias_s[tid] = bias ? __ldg(bias + tid) : 0.f;
     for (int i = tid; i < 2 * kHaloBlk / 16; i += kTile) reinterpret_cast<float4*>(halo)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
     const uint32_t w_a = tc::smem_u32(Wi), h_a = tc::smem_u32(halo);
     uint32_t phase = 0;
-    double stat_sum = 0.0, stat_sq = 0.0;
     const int ti = tid >> 3, j = tid & 7;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    auto epilogue = [&](const TileGeom& g, int buf) {
+        float acc[64];
+        tc::tmem_ld_row64(tmem, warp, buf * 64, acc);
+        tc::fence_before_sync();
+        const int t = g.t0 + ti, f = g.f0 + j;
+        if (t < T_l && f < F) {
+            float4* dst = reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64);
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 4 * c4);
+                dst[c4] = make_float4(acc[4 * c4] + b4.x, acc[4 * c4 + 1] + b4.y, acc[4 * c4 + 2] + b4.z, acc[4 * c4 + 3] + b4.w);
+            }
+        }
+    };
+
+    int tile = blockIdx.x;
+    if (tile < n_tiles) prefetch_halo(in, decode_tile(tile, halves, tblocks), T_l, F, pitch, halo);
+    TileGeom prev{};
+    int it = 0;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
         const TileGeom g = decode_tile(tile, halves, tblocks);
-        load_halo<false>(in, g, T_l, F, pitch, 0, 18, halo);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         tc::fence_proxy_async();
-        __syncthreads();
+        __syncthreads();                               // halo(i) complete and visible; epilogue(i-2) has drained TMEM[i & 1]
         if (tid == 0) {
             tc::mbar_wait(&w_bar, 0);                  // weight image landed (no-op after the first tile)
             tc::fence_after_sync();
             constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+            const uint32_t d = tmem + (it & 1) * 64;
 #pragma unroll 1
             for (int tap = 0; tap < 9; ++tap) {
                 const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -129,58 +171,46 @@ conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const flo
                 const uint32_t b0 = w_a + tap * 16384;
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    tc::umma_tf32(tmem, tc::smem_desc_sw128(a0 + (k >> 2) * kHaloBlk + (k & 3) * 32, 16, pitch * 128),
+                    tc::umma_tf32(d, tc::smem_desc_sw128(a0 + (k >> 2) * kHaloBlk + (k & 3) * 32, 16, pitch * 128),
                                   tc::smem_desc_sw128(b0 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc,
                                   (tap > 0 || k > 0) ? 1u : 0u);
             }
             tc::umma_commit(&mma_bar);
         }
+        if (it > 0) epilogue(prev, (it - 1) & 1);      // overlaps MMA(i)
         tc::mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc::fence_after_sync();
-        float acc[64];
-        tc::tmem_ld_row64(tmem, warp, 0, acc);
-        tc::fence_before_sync();
-        const int t = g.t0 + ti, f = g.f0 + j;
-        const bool valid = t < T_l && f < F;
-#pragma unroll
-        for (int c = 0; c < 64; ++c) acc[c] += bias_s[c];
-        if (valid) {
-            float4* dst = reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64);
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) dst[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-        }
-        if (STATS) {                                   // per-channel sum / sum of squares for the batch statistics
-            float* tile_s = reinterpret_cast<float*>(halo);     // [128][68]; all MMAs reading the halo have completed
-            __syncthreads();
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4)
-                *reinterpret_cast<float4*>(tile_s + tid * 68 + 4 * c4) =
-                    valid ? make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3])
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
-            // thread (c, h) reduces rows 64h .. 64h+63 of channel c: sum and sum of squares in one pass
-            const int c = tid & 63, h = tid >> 6;
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 16
-            for (int q = 0; q < 64; ++q) {
-                const float v = tile_s[(64 * h + q) * 68 + c];
-                s1 += v;
-                s2 = fmaf(v, v, s2);
-            }
-            stat_sum += (double)s1;
-            stat_sq += (double)s2;
-        }
-        __syncthreads();
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) prefetch_halo(in, decode_tile(next, halves, tblocks), T_l, F, pitch, halo);
+        prev = g;
     }
-    if (STATS) {                                       // [0,64): sum, [64,128): sum of squares
-        atomicAdd(stats + (tid & 63), stat_sum);
-        atomicAdd(stats + 64 + (tid & 63), stat_sq);
-    }
-    if (tid == 0 && n_tiles <= (int)blockIdx.x) tc::mbar_wait(&w_bar, 0);   // never leave with a bulk copy in flight
+    if (it > 0) epilogue(prev, (it - 1) & 1);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+// per-channel sum and sum of squares of a [n_pix][64] tensor (BatchNorm batch statistics, fp64 accumulation)
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ y, long long n_pix, double* __restrict__ stats) {
+    __shared__ float red[16][128];
+    const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (long long r = (long long)blockIdx.x * 16 + rl; r < n_pix; r += (long long)gridDim.x * 16) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y) + r * 16 + cq);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    float* row = red[rl];
+    row[4 * cq] = s.x; row[4 * cq + 1] = s.y; row[4 * cq + 2] = s.z; row[4 * cq + 3] = s.w;
+    row[64 + 4 * cq] = q.x; row[64 + 4 * cq + 1] = q.y; row[64 + 4 * cq + 2] = q.z; row[64 + 4 * cq + 3] = q.w;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        double t = 0.0;
+        for (int i = 0; i < 16; ++i) t += (double)red[i][threadIdx.x];
+        atomicAdd(stats + threadIdx.x, t);             // [0,64): sum, [64,128): sum of squares
+    }
 }
 
 // grid = (chunks, 3): blockIdx.y selects dy; TMEM holds the three [64 n][64 c] accumulators of dx = -1, 0, +1.
@@ -280,15 +310,14 @@ int grid_for(int n_tiles, int num_sms, int per_sm) {
 }  // namespace
 
 int conv_tc_kernels_init() {
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBytes));
     return DCASE_OK;
 }
 
 int launch_conv_w_prep(const float* w, float* w_fwd, float* w_dgrad, cudaStream_t s) {
     DCASE_PROF("conv_w_prep", s);
-    conv_w_image_kernel<<<36, 256, 0, s>>>(w, w_fwd, w_dgrad);
+    conv_w_image_kernel<<<144, 256, 0, s>>>(w, w_fwd, w_dgrad);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
@@ -299,13 +328,16 @@ int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, c
     DCASE_REQUIRE(F == 16 || F == 4, "conv3x3 is built for the 16- and 4-bin layers of cfg.crnn_kwargs");
     const int n_tiles = B * ((T_l + 15) / 16) * (F == 16 ? 2 : 1);
     const int grid = grid_for(n_tiles, num_sms, 1);
+    conv3x3_tc_kernel<<<grid, kTile, kConvSmemBytes, s>>>(in, B, T_l, F, w_img, bias, out);
+    DCASE_LAUNCH_CHECK();
     if (stats) {
         DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
-        conv3x3_tc_kernel<true><<<grid, kTile, kConvSmemBytes, s>>>(in, B, T_l, F, w_img, bias, out, stats);
-    } else {
-        conv3x3_tc_kernel<false><<<grid, kTile, kConvSmemBytes, s>>>(in, B, T_l, F, w_img, bias, out, nullptr);
+        const long long n_pix = (long long)B * T_l * F;
+        long long blocks = (n_pix + 16 * 32 - 1) / (16 * 32);
+        if (blocks > num_sms * 4) blocks = num_sms * 4;
+        bn_stats_kernel<<<(int)blocks, 256, 0, s>>>(out, n_pix, stats);
+        DCASE_LAUNCH_CHECK();
     }
-    DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 

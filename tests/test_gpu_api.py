@@ -157,7 +157,8 @@ def test_train_three_steps_match_oracle(pkg, cuda_device):
         # random-walk by +-lr per step on rounding noise, ours stay put: compare bias-corrected
         rm = bn.running_mean.cpu() - got_s[f"cnn.cnn.conv{i}.bias"]
         rm_ref = sbuf[f"cnn.cnn.batchnorm{i}.running_mean"] - ps[f"cnn.cnn.conv{i}.bias"]
-        assert H.maxerr(rm, rm_ref) <= 3e-4
+        # (the reference's last forward used the bias BEFORE its final +-lr update, hence the 1e-3 slack)
+        assert H.maxerr(rm, rm_ref) <= 1e-3 + 3e-4
         assert H.maxerr(bn.running_var.cpu(), sbuf[f"cnn.cnn.batchnorm{i}.running_var"]) <= 3e-4
     st = opt.state_dict()["state"]
     assert len(st) == 38 and float(st[0]["step"]) == 3.0
