@@ -10,9 +10,8 @@ struct dcase_ctx {
     float* d_window;     // [2048] symmetric Hamming
     cf32* d_twiddle;     // [2048] exp(-2 pi i m / 2048)
     float* d_mel_w;      // packed non-zero Slaney weights
-    int* d_mel_start;    // [64] first non-zero bin
-    int* d_mel_len;      // [64] band length
-    int* d_mel_off;      // [64] offset into d_mel_w
+    int* d_mel_work;     // [128][4] balanced work items of the mel projection
+    int* d_mel_owner;    // [64][2]  slots of each band
     int mel_nnz;
     // second stream + events: the teacher forward runs concurrently with the student forward (dcase_mt_fwd_bwd)
     cudaStream_t aux_stream;

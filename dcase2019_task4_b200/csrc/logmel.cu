@@ -35,9 +35,8 @@ struct MelTables {
     const float* window;
     const cf32* twiddle;
     const float* mel_w;
-    const int* mel_start;
-    const int* mel_len;
-    const int* mel_off;
+    const int4* mel_work;    // [128] per-thread work items {bin start, weight offset, count, band}
+    const int2* mel_owner;   // [64]  {first slot, slot count} per band
 };
 
 __device__ __forceinline__ int reflect_index(int s, int L) {
@@ -62,6 +61,7 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, flo
     float* span = reinterpret_cast<float*>(smem_raw);                 // [kSpan] (+pad)
     cf32* bufA = reinterpret_cast<cf32*>(span + kSpanPad);            // [2304] (padded, fft_pad)
     cf32* bufB = bufA + kFftPaddedSize;                               // [2304]
+    __shared__ float part[256];
     const cf32* __restrict__ tw = tab.twiddle;                        // [2048], read through L1 (16 KB, hot)
 
     const int tid = threadIdx.x;
@@ -112,19 +112,32 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, flo
             mag[kMagPitch + k] = sqrtf(br * br + bi * bi);
         }
         __syncthreads();
-        // sparse Slaney mel projection: 2 frames x 64 mels x 2 lanes
+        // sparse Slaney mel projection (1,983 non-zeros per frame), load balanced: 128 threads per frame, each owns
+        // a contiguous run of <= 16 weights inside one band (host-built table); band owners combine the partials
         {
-            const int fr = tid >> 7;
-            const int m = (tid & 127) >> 1;
-            const int hf = tid & 1;
-            const int start = __ldg(tab.mel_start + m), len = __ldg(tab.mel_len + m);
-            const float* w = tab.mel_w + __ldg(tab.mel_off + m);
-            const float* mg = mag + fr * kMagPitch + start;
+            const int fr = tid >> 7, slot = tid & 127;
+            const int4 e = __ldg(tab.mel_work + slot);          // {bin start, weight offset, count, -}
+            const float* w = tab.mel_w + e.y;
+            const float* mg = mag + fr * kMagPitch + e.x;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int i = 0;
+            for (; i + 3 < e.z; i += 4) {
+                a0 = fmaf(__ldg(w + i), mg[i], a0);
+                a1 = fmaf(__ldg(w + i + 1), mg[i + 1], a1);
+                a2 = fmaf(__ldg(w + i + 2), mg[i + 2], a2);
+                a3 = fmaf(__ldg(w + i + 3), mg[i + 3], a3);
+            }
+            for (; i < e.z; ++i) a0 = fmaf(__ldg(w + i), mg[i], a0);
+            part[tid] = (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
+        if ((tid & 127) < kMel) {
+            const int fr = tid >> 7, m = tid & 127;
+            const int2 o = __ldg(tab.mel_owner + m);            // {first slot, slot count} of band m
             float acc = 0.f;
-            for (int i = hf; i < len; i += 2) acc = fmaf(__ldg(w + i), mg[i], acc);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            for (int q = 0; q < o.y; ++q) acc += part[fr * 128 + o.x + q];
             const int t = t0 + 2 * p + fr;
-            if (hf == 0 && t < T) mel_amp[((size_t)b * T + t) * kMel + m] = acc;
+            if (t < T) mel_amp[((size_t)b * T + t) * kMel + m] = acc;
         }
         __syncthreads();
     }
@@ -272,15 +285,41 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
     DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_window, kNfft * sizeof(float)));
     DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_twiddle, kNfft * sizeof(cf32)));
     DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_w, packed.size() * sizeof(float)));
-    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_start, kMel * sizeof(int)));
-    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_len, kMel * sizeof(int)));
-    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_off, kMel * sizeof(int)));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
     DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_window, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
     DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_twiddle, tw.data(), kNfft * sizeof(cf32), cudaMemcpyHostToDevice));
-    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
-    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_start, start.data(), kMel * sizeof(int), cudaMemcpyHostToDevice));
-    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_len, len.data(), kMel * sizeof(int), cudaMemcpyHostToDevice));
-    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_off, off.data(), kMel * sizeof(int), cudaMemcpyHostToDevice));
+    // balanced work split: band m gets n_m of the 128 slots (proportional to its length, at least one)
+    {
+        std::vector<int> n_slots(kMel, 1);
+        int used = kMel;
+        while (used < 128) {            // give the next slot to the band with the largest per-slot load
+            int best = 0;
+            double best_load = -1.0;
+            for (int m = 0; m < kMel; ++m) {
+                const double load = (double)len[m] / n_slots[m];
+                if (load > best_load) { best_load = load; best = m; }
+            }
+            ++n_slots[best];
+            ++used;
+        }
+        std::vector<int> work(128 * 4), owner(kMel * 2);
+        int slot = 0;
+        for (int m = 0; m < kMel; ++m) {
+            owner[2 * m] = slot;
+            owner[2 * m + 1] = n_slots[m];
+            for (int q = 0; q < n_slots[m]; ++q, ++slot) {
+                const int beg = (int)((long long)len[m] * q / n_slots[m]), end = (int)((long long)len[m] * (q + 1) / n_slots[m]);
+                work[4 * slot] = start[m] + beg;
+                work[4 * slot + 1] = off[m] + beg;
+                work[4 * slot + 2] = end - beg;
+                work[4 * slot + 3] = m;
+            }
+        }
+        DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_work, work.size() * sizeof(int)));
+        DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_owner, owner.size() * sizeof(int)));
+        DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_work, work.data(), work.size() * sizeof(int), cudaMemcpyHostToDevice));
+        DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_owner, owner.data(), owner.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kStftSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -290,7 +329,7 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
 
 void dcase_logmel_tables_destroy(dcase_ctx* ctx) {
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_w);
-    cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len); cudaFree(ctx->d_mel_off);
+    cudaFree(ctx->d_mel_work); cudaFree(ctx->d_mel_owner);
     free(ctx->h_mel_dense);
 }
 
@@ -311,7 +350,7 @@ static int logmel_fwd_impl(dcase_ctx* ctx, const void* wave, int is_pcm16, int B
     if (B == 0) return DCASE_OK;
     const int T = 1 + L / kHop;
     DCASE_PROF("stft_mel", stream);
-    MelTables tab{ctx->d_window, ctx->d_twiddle, ctx->d_mel_w, ctx->d_mel_start, ctx->d_mel_len, ctx->d_mel_off};
+    MelTables tab{ctx->d_window, ctx->d_twiddle, ctx->d_mel_w, (const int4*)ctx->d_mel_work, (const int2*)ctx->d_mel_owner};
     dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
     if (is_pcm16)
         stft_mel_kernel<int16_t><<<grid, 256, kStftSmemBytes, stream>>>((const int16_t*)wave, L, T, tab, mel_amp);
