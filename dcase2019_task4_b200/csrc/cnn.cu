@@ -186,7 +186,7 @@ __device__ __forceinline__ void produce_y_half(const GluArgs& a, long long p, bo
                 y.x = fmaf(w.x, tap[k], y.x); y.y = fmaf(w.y, tap[k], y.y);
                 y.z = fmaf(w.z, tap[k], y.z); y.w = fmaf(w.w, tap[k], y.w);
             }
-            *a_row.chunk(c4) = y;
+            *a_row.chunk(c4) = tc::tf32_rn4(y);
         }
     } else {
         const float4* src = reinterpret_cast<const float4*>(a.src + p * 64);
@@ -201,7 +201,7 @@ __device__ __forceinline__ void produce_y_half(const GluArgs& a, long long p, bo
                 y.x = fmaf(sc.x, v.x, sh.x); y.y = fmaf(sc.y, v.y, sh.y);
                 y.z = fmaf(sc.z, v.z, sh.z); y.w = fmaf(sc.w, v.w, sh.w);
             }
-            *a_row.chunk(c4) = y;
+            *a_row.chunk(c4) = tc::tf32_rn4(y);
         }
     }
 }
@@ -238,6 +238,10 @@ __device__ __forceinline__ void tmem_ld_row32(uint32_t tmem_base, int warp, int 
 // overlap one CTA's MMA with the others' CUDA-core phases.
 constexpr int kGluFwdSmemBytes = 1024 + 16384 + 32768 + (64 + 832 + 4 * 66) * 4;
 
+// Layer 0 also runs conv0 (+ folded BN) on the tensor core: per tile the 9 taps of every pixel (+ a constant 1 for
+// the bias) form a [128][16] operand T0, the folded weights a [64][16] operand W0; both live in the second 16 KB
+// block of A (T0 = logical columns 0..15, W0 = logical columns 16..31 of rows 0..63, same swizzle) until y = T0 W0^T
+// has been read back from TMEM and written over them as the A operand of the GLU GEMM.
 template <bool L0>
 __global__ void __launch_bounds__(kThreads, 4)
 glu_pool_fwd_kernel(GluArgs a) {
@@ -250,17 +254,18 @@ glu_pool_fwd_kernel(GluArgs a) {
     float* xs = aff_s + 832;          // [4][66] (L0)
     __shared__ uint64_t mma_bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint2 keep_s[kTile];   // dropout keep words of the tile's pixels (computed once per pixel)
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127, half = tid >> 7;
 
     for (int i = tid; i < 4096; i += kThreads) {      // Wg[n][k] -> block k/32, row n, swizzled
         const int n = i >> 6, k = i & 63;
-        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = __ldg(a.glu_w + i);
+        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(__ldg(a.glu_w + i));
     }
     if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
     for (int i = tid; i < (L0 ? kFold0Size : kBnSize); i += kThreads) aff_s[i] = a.aff[i];
     if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
     uint64_t seed; uint32_t step;
     resolve_rng(a.drop, seed, step);
     tc::fence_proxy_async();
@@ -271,16 +276,74 @@ glu_pool_fwd_kernel(GluArgs a) {
     const uint32_t a_addr = tc::smem_u32(A), b_addr = tc::smem_u32(Wb);
     uint32_t phase = 0;
 
+    // W0 chunk owned by this thread (row n = tid >> 2, logical chunk 4 + (tid & 3)): folded conv0 weights + bias
+    float4 w0_chunk = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (L0) {
+        const int n = tid >> 2, c = tid & 3;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = 4 * c + e;
+            v[e] = k < 9 ? aff_s[kFold0Wf + k * 64 + n] : (k == 9 ? aff_s[kFold0Bf + n] : 0.f);
+        }
+        w0_chunk = tc::tf32_rn4(make_float4(v[0], v[1], v[2], v[3]));
+    }
+    unsigned char* T0 = A + 16384;                    // block 1 of A
+
     const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
     const long long n_out = a.n_pix >> 3;
     const int wpr = a.F >> 2;
+    const float pool_scale = a.drop.enabled ? 0.25f : 0.125f;   // 1/8 window, x2 inverted dropout
     const Sw128Row a_row{A, row};
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long p = tile * kTile + row;
         const bool valid = p < a.n_pix;
-        if (L0) { load_xs(a.src, tile, a.T, xs); __syncthreads(); }
-        float tap[9];
-        produce_y_half<L0>(a, p, valid, aff_s, xs, a_row, row, half, tap);
+        if (L0) {
+            load_xs(a.src, tile, a.T, xs);
+            __syncthreads();
+            // operands of y = T0 W0^T
+            *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(tid >> 2, 4 + (tid & 3))) = w0_chunk;
+            if (half == 0) {
+                const int tr = row >> 6, f = row & 63;
+                float tap[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) tap[k] = tc::tf32_rn(xs[(tr + k / 3) * 66 + f + (k % 3)]);
+                *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 0)) = make_float4(tap[0], tap[1], tap[2], tap[3]);
+                *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 1)) = make_float4(tap[4], tap[5], tap[6], tap[7]);
+                *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 2)) = make_float4(tap[8], 1.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 3)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tc::fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after_sync();
+                constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+                const uint32_t t0a = a_addr + 16384;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    tc::umma_tf32(tmem + 64, tc::smem_desc_sw128(t0a + k * 32, 16, 1024),
+                                  tc::smem_desc_sw128(t0a + 64 + k * 32, 16, 1024), idesc, k);
+                tc::umma_commit(&mma_bar);
+            }
+        }
+        if (a.drop.enabled && half == 0) {            // one Philox call per pixel (overlaps the conv0 MMA)
+            const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
+            keep_s[row] = make_uint2(r.x, r.y);
+        }
+        if (L0) {
+            tc::mbar_wait(&mma_bar, phase);
+            phase ^= 1;
+            tc::fence_after_sync();
+            float y[32];
+            tmem_ld_row32(tmem, warp, 64 + 32 * half, y);
+            tc::fence_before_sync();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                *a_row.chunk(8 * half + q) = tc::tf32_rn4(make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]));
+        } else {
+            float tap[9];
+            produce_y_half<false>(a, p, valid, aff_s, xs, a_row, row, half, tap);
+        }
         tc::fence_proxy_async();                 // y tile -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
@@ -288,12 +351,8 @@ glu_pool_fwd_kernel(GluArgs a) {
             tc::umma_128x64x64_kmajor(tmem, a_addr, b_addr, false);
             tc::umma_commit(&mma_bar);
         }
-        uint32_t keep = 0xffffffffu;             // keep bits of channels 32*half .. +31 (overlaps the MMA)
-        float scale = 1.f;
-        if (a.drop.enabled) {
-            const uint4 r = philox4x32_10((uint64_t)p, a.drop.stream, step, seed);
-            keep = half ? r.y : r.x; scale = 2.f;
-        }
+        uint32_t keep = 0xffffffffu;             // keep bits of channels 32*half .. +31
+        if (a.drop.enabled) { const uint2 kw = keep_s[row]; keep = half ? kw.y : kw.x; }
         tc::mbar_wait(&mma_bar, phase);
         phase ^= 1;
         tc::fence_after_sync();
@@ -307,10 +366,10 @@ glu_pool_fwd_kernel(GluArgs a) {
             const float4 b4 = *reinterpret_cast<const float4*>(bg + 32 * half + 4 * q);
             const uint32_t bits = keep >> (4 * q);
             float4 z;
-            z.x = (bits & 1u) ? (acc[4 * q + 0] + b4.x) * sigmoid_fast(y.x) * scale : 0.f;
-            z.y = (bits & 2u) ? (acc[4 * q + 1] + b4.y) * sigmoid_fast(y.y) * scale : 0.f;
-            z.z = (bits & 4u) ? (acc[4 * q + 2] + b4.z) * sigmoid_fast(y.z) * scale : 0.f;
-            z.w = (bits & 8u) ? (acc[4 * q + 3] + b4.w) * sigmoid_fast(y.w) * scale : 0.f;
+            z.x = (bits & 1u) ? (acc[4 * q + 0] + b4.x) * sigmoid_fast(y.x) : 0.f;
+            z.y = (bits & 2u) ? (acc[4 * q + 1] + b4.y) * sigmoid_fast(y.y) : 0.f;
+            z.z = (bits & 4u) ? (acc[4 * q + 2] + b4.z) * sigmoid_fast(y.z) : 0.f;
+            z.w = (bits & 8u) ? (acc[4 * q + 3] + b4.w) * sigmoid_fast(y.w) : 0.f;
             if (!valid) z = make_float4(0.f, 0.f, 0.f, 0.f);
             *slot = z;
         }
@@ -329,15 +388,17 @@ glu_pool_fwd_kernel(GluArgs a) {
                     s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
                 }
             const long long op = tile * 16 + w;
-            if (op < n_out)
-                *reinterpret_cast<float4*>(a.out + op * 64 + 4 * cq) =
-                    make_float4(0.125f * s0.x, 0.125f * s0.y, 0.125f * s0.z, 0.125f * s0.w);
+            if (op < n_out) {
+                float4 o = make_float4(pool_scale * s0.x, pool_scale * s0.y, pool_scale * s0.z, pool_scale * s0.w);
+                if (a.F != 4) o = tc::tf32_rn4(o);            // input of the next block's tensor-core conv
+                *reinterpret_cast<float4*>(a.out + op * 64 + 4 * cq) = o;
+            }
         }
         __syncthreads();
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -385,7 +446,7 @@ glu_pool_bwd_kernel(GluArgs a) {
 
     for (int i = tid; i < 4096; i += kThreads) {
         const int n = i >> 6, k = i & 63;
-        const float w = __ldg(a.glu_w + i);
+        const float w = tc::tf32_rn(__ldg(a.glu_w + i));
         *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = w;
         *reinterpret_cast<float*>(Wm + (k >> 5) * 8192 + tc::sw128b32_chunk(n, (k & 31) >> 2) + (k & 3) * 4) = w;
     }
@@ -436,9 +497,9 @@ glu_pool_bwd_kernel(GluArgs a) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) *y32_row.chunk(8 * half + q) = *p_row.chunk(8 * half + q);
         if (L0 && half == 0) {
-            *ext_row.chunk(0) = make_float4(1.f, tap[0], tap[1], tap[2]);
-            *ext_row.chunk(1) = make_float4(tap[3], tap[4], tap[5], tap[6]);
-            *ext_row.chunk(2) = make_float4(tap[7], tap[8], 0.f, 0.f);
+            *ext_row.chunk(0) = tc::tf32_rn4(make_float4(1.f, tap[0], tap[1], tap[2]));
+            *ext_row.chunk(1) = tc::tf32_rn4(make_float4(tap[3], tap[4], tap[5], tap[6]));
+            *ext_row.chunk(2) = tc::tf32_rn4(make_float4(tap[7], tap[8], 0.f, 0.f));
         }
         tc::fence_proxy_async();
         __syncthreads();
@@ -480,7 +541,7 @@ glu_pool_bwd_kernel(GluArgs a) {
             const float4 y = *slot;
             const float4 b4 = *reinterpret_cast<const float4*>(bg + 32 * half + 4 * q);
             const float gx = sigmoid_fast(y.x), gy = sigmoid_fast(y.y), gz = sigmoid_fast(y.z), gw = sigmoid_fast(y.w);
-            const float4 dl = make_float4(dz[4 * q] * gx, dz[4 * q + 1] * gy, dz[4 * q + 2] * gz, dz[4 * q + 3] * gw);
+            const float4 dl = tc::tf32_rn4(make_float4(dz[4 * q] * gx, dz[4 * q + 1] * gy, dz[4 * q + 2] * gz, dz[4 * q + 3] * gw));
             *slot = dl;                       // P: Y -> DL (G1 has completed)
             *q2_row.chunk(8 * half + q) = dl;
             // direct path through the gate: dz * lin * g * (1 - g)
@@ -520,7 +581,7 @@ glu_pool_bwd_kernel(GluArgs a) {
             for (int q = 0; q < 8; ++q) {
                 const float4 v = make_float4(acc[4 * q] + d2[4 * q], acc[4 * q + 1] + d2[4 * q + 1],
                                              acc[4 * q + 2] + d2[4 * q + 2], acc[4 * q + 3] + d2[4 * q + 3]);
-                *q2_row.chunk(8 * half + q) = v;        // Q2: DL -> dY (G3 has completed)
+                *q2_row.chunk(8 * half + q) = tc::tf32_rn4(v);        // Q2: DL -> dY (G3 has completed)
                 if (!L0 && valid) reinterpret_cast<float4*>(a.d_y + p * 64)[8 * half + q] = v;
             }
         }
@@ -619,7 +680,7 @@ bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, lon
         d.y = sa[c + 1] * (d.y - s1[c + 1] - (y.y - sm[c + 1]) * si[c + 1] * s2[c + 1]);
         d.z = sa[c + 2] * (d.z - s1[c + 2] - (y.z - sm[c + 2]) * si[c + 2] * s2[c + 2]);
         d.w = sa[c + 3] * (d.w - s1[c + 3] - (y.w - sm[c + 3]) * si[c + 3] * s2[c + 3]);
-        reinterpret_cast<float4*>(d_y)[i] = d;
+        reinterpret_cast<float4*>(d_y)[i] = tc::tf32_rn4(d);       // operand of the conv dgrad / wgrad MMAs
     }
 }
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __global__ void conv_w_image_kernel(const float* __restrict__ w, float* __restrict__ img_fwd, float* __restrict__ img_dgrad) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * 64 * 9; i += gridDim.x * blockDim.x) {
         const int tap = i % 9, c = (i / 9) & 63, n = i / 576;
-        const float v = __ldg(w + i);
+        const float v = tc::tf32_rn(__ldg(w + i));
         img_fwd[(tap * 16384 + (c >> 5) * 8192 + tc::sw128_off(n, c & 31)) >> 2] = v;
         img_dgrad[((8 - tap) * 16384 + (n >> 5) * 8192 + tc::sw128_off(c, n & 31)) >> 2] = v;
     }

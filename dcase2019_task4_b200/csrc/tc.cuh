@@ -26,6 +26,16 @@ __device__ __forceinline__ uint32_t sw128_chunk(int r, int c) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((c ^ r) & 7) << 4));
 }
 
+// kind::tf32 TRUNCATES fp32 operands to 19 bits; truncation shrinks every product by ~2^-11 and the bias compounds
+// layer after layer (measured: -0.4 % on the layer-1 batch variance).  Every value that feeds an MMA is therefore
+// rounded to nearest tf32 when it is produced (unbiased), by the thread that writes the operand tile / tensor.
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+
 // ---- mbarrier ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
