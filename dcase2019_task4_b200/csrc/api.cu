@@ -227,6 +227,8 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     DCASE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_loss_scratch, kLossScratchBytes));
+    DCASE_CUDA_CHECK(cudaMemset(ctx->d_loss_scratch, 0, kLossScratchBytes));
     int rc = dcase_logmel_tables_create(ctx);
     if (rc == DCASE_OK) rc = cnn_kernels_init();
     if (rc == DCASE_OK) rc = conv_tc_kernels_init();
@@ -239,6 +241,7 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
 int dcase_ctx_destroy(dcase_ctx* ctx) {
     if (!ctx) return DCASE_OK;
     dcase_logmel_tables_destroy(ctx);
+    cudaFree(ctx->d_loss_scratch);
     cudaStreamDestroy(ctx->aux_stream);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
@@ -472,6 +475,8 @@ int dcase_mt_loss(dcase_ctx* ctx, const float* strong_s, const float* weak_s, co
     a.B = B; a.To = To; a.NC = NC; a.weak_lo = weak_lo; a.weak_hi = weak_hi; a.strong_lo = strong_lo; a.strong_hi = strong_hi;
     a.cons_weight = cons_weight; a.sc = (const DcaseStepScalars*)scalars; a.meters = meters;
     a.d_strong = d_strong; a.d_weak = d_weak;
+    a.partials = ctx->d_loss_scratch;
+    a.ticket = reinterpret_cast<unsigned int*>(ctx->d_loss_scratch + kLossMaxCtas * 8);
     return launch_mt_loss(a, (cudaStream_t)stream_);
 }
 

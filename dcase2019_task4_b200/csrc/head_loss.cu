@@ -222,9 +222,12 @@ __device__ __forceinline__ float bce_term(float p, float y) {
 }
 __device__ __forceinline__ float bce_grad(float p, float y) { return (p - y) / fmaxf((1.f - p) * p, 1e-12f); }
 
-__global__ void __launch_bounds__(1024)
+// One CTA per clip (grid-stride over clips): element-wise gradients + per-CTA partial sums; the last CTA to
+// finish (atomic ticket) adds the partials in CTA order, so the meters do not depend on the schedule.
+__global__ void __launch_bounds__(256)
 mt_loss_kernel(LossArgs a) {
-    __shared__ float red[32][6];
+    __shared__ float red[8][6];
+    __shared__ bool is_last;
     const int tid = threadIdx.x;
     const float cw = a.sc ? a.sc->cons_weight : a.cons_weight;
     const bool has_t = a.strong_t != nullptr;
@@ -236,40 +239,52 @@ mt_loss_kernel(LossArgs a) {
     const float cs_scale = has_t ? cw * 2.f / (float)n_all_s : 0.f;
     const float cwk_scale = has_t ? cw * 2.f / (float)n_all_w : 0.f;
     float s_bce = 0.f, s_bce_t = 0.f, s_cons = 0.f, w_bce = 0.f, w_bce_t = 0.f, w_cons = 0.f;
-    for (long long e = tid; e < n_all_s; e += 1024) {
-        const int b = (int)(e / per_clip);
-        const float p = a.strong_s[e];
-        float d = 0.f;
-        if (b >= a.strong_lo && b < a.strong_hi) {
-            const float y = a.target[e];
-            s_bce += bce_term(p, y);
-            if (has_t) s_bce_t += bce_term(a.strong_t[e], y);
-            d = bce_grad(p, y) * inv_ns;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const bool in_strong = b >= a.strong_lo && b < a.strong_hi;
+        const bool in_weak = b >= a.weak_lo && b < a.weak_hi;
+        const long long base = (long long)b * per_clip;
+        for (int i = tid; i < per_clip; i += 256) {
+            const long long e = base + i;
+            const float p = a.strong_s[e];
+            float d = 0.f;
+            if (in_strong) {
+                const float y = a.target[e];
+                s_bce += bce_term(p, y);
+                if (has_t) s_bce_t += bce_term(a.strong_t[e], y);
+                d = bce_grad(p, y) * inv_ns;
+            }
+            if (has_t) {
+                const float diff = p - a.strong_t[e];
+                s_cons = fmaf(diff, diff, s_cons);
+                d = fmaf(cs_scale, diff, d);
+            }
+            a.d_strong[e] = d;
         }
-        if (has_t) {
-            const float diff = p - a.strong_t[e];
-            s_cons = fmaf(diff, diff, s_cons);
-            d = fmaf(cs_scale, diff, d);
+        // weak outputs of the clip: 16 lanes per class scan the clip's targets (target.max(-2), main.py:95)
+        const int c = tid >> 4, l = tid & 15;
+        if (c < a.NC) {
+            const int e = b * a.NC + c;
+            float y = -INFINITY;
+            if (in_weak)
+                for (int t = l; t < a.To; t += 16) y = fmaxf(y, a.target[base + (long long)t * a.NC + c]);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, o));
+            if (l == 0) {
+                const float p = a.weak_s[e];
+                float d = 0.f;
+                if (in_weak) {
+                    w_bce += bce_term(p, y);
+                    if (has_t) w_bce_t += bce_term(a.weak_t[e], y);
+                    d = bce_grad(p, y) * inv_nw;
+                }
+                if (has_t) {
+                    const float diff = p - a.weak_t[e];
+                    w_cons = fmaf(diff, diff, w_cons);
+                    d = fmaf(cwk_scale, diff, d);
+                }
+                a.d_weak[e] = d;
+            }
         }
-        a.d_strong[e] = d;
-    }
-    for (int e = tid; e < n_all_w; e += 1024) {
-        const int b = e / a.NC, c = e - b * a.NC;
-        const float p = a.weak_s[e];
-        float d = 0.f;
-        if (b >= a.weak_lo && b < a.weak_hi) {
-            float y = -INFINITY;   // target.max(-2), main.py:95
-            for (int t = 0; t < a.To; ++t) y = fmaxf(y, a.target[((long long)b * a.To + t) * a.NC + c]);
-            w_bce += bce_term(p, y);
-            if (has_t) w_bce_t += bce_term(a.weak_t[e], y);
-            d = bce_grad(p, y) * inv_nw;
-        }
-        if (has_t) {
-            const float diff = p - a.weak_t[e];
-            w_cons = fmaf(diff, diff, w_cons);
-            d = fmaf(cwk_scale, diff, d);
-        }
-        a.d_weak[e] = d;
     }
     float v[6] = {w_bce, w_bce_t, s_bce, s_bce_t, s_cons, w_cons};
 #pragma unroll
@@ -278,9 +293,24 @@ mt_loss_kernel(LossArgs a) {
         if ((tid & 31) == 0) red[tid >> 5][i] = v[i];
     }
     __syncthreads();
-    if (tid < 32) {
+    if (tid < 6) {
+        float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) v[i] = warp_sum(red[tid][i]);
+        for (int w = 0; w < 8; ++w) s += red[w][tid];
+        a.partials[blockIdx.x * 8 + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid < 32) {
+        float s = 0.f;
+        if (tid < 6)
+            for (unsigned g = 0; g < gridDim.x; ++g) s += __ldcg(a.partials + g * 8 + tid);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = __shfl_sync(0xffffffffu, s, i);
         if (tid == 0) {
             const float weak_loss = v[0] * inv_nw, weak_ema = v[1] * inv_nw;
             const float strong_loss = v[2] * inv_ns, strong_ema = v[3] * inv_ns;
@@ -290,6 +320,7 @@ mt_loss_kernel(LossArgs a) {
             a.meters[4] = cons_s; a.meters[5] = cons_w;
             a.meters[6] = weak_loss + strong_loss + cons_s + cons_w;
             a.meters[7] = cw;
+            *a.ticket = 0u;                                  // ready for the next launch
         }
     }
 }
@@ -338,7 +369,8 @@ int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
 
 int launch_mt_loss(const LossArgs& a, cudaStream_t s) {
     DCASE_PROF("mt_loss", s);
-    mt_loss_kernel<<<1, 1024, 0, s>>>(a);
+    const int grid = a.B < kLossMaxCtas ? a.B : kLossMaxCtas;
+    mt_loss_kernel<<<grid, 256, 0, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

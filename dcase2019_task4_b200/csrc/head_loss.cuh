@@ -40,9 +40,14 @@ struct LossArgs {
     float cons_weight;
     const DcaseStepScalars* sc;
     float* meters;           // [8]
+    float* partials;         // [kLossMaxCtas][8] per-CTA partial sums (context scratch)
+    unsigned int* ticket;    // completion counter (context scratch, zero between launches)
     float* d_strong;
     float* d_weak;
 };
+
+constexpr int kLossMaxCtas = 1024;
+constexpr size_t kLossScratchBytes = (kLossMaxCtas * 8 + 8) * sizeof(float);
 
 int head_kernels_init();
 int launch_head_fwd(const HeadArgs& a, cudaStream_t s);

@@ -158,18 +158,20 @@ __device__ __forceinline__ float4 noise_quad(uint64_t quad_index, uint32_t step,
                        0.25f * fabsf(rb * sb));
 }
 
+// grid (slices, B): every CTA reduces a slice of the clip and folds it in with atomicMax on the float bits
+// (amplitudes are >= 0, so the unsigned order is the float order; clip_max is zeroed by the launcher)
 __global__ void __launch_bounds__(256)
 clip_max_kernel(const float* __restrict__ mel_amp, int T_in, const float* __restrict__ noise, int want_noisy,
                 uint64_t seed, uint32_t step, const DcaseStepScalars* __restrict__ sc,
                 float* __restrict__ clip_max, int B) {
     __shared__ float red[2][8];
     if (sc) { seed = sc->seed; step = sc->step; }
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const int n_quads = T_in * (kMel / 4);
     const float4* src = reinterpret_cast<const float4*>(mel_amp + (size_t)b * T_in * kMel);
     const float4* nz = noise ? reinterpret_cast<const float4*>(noise + (size_t)b * T_in * kMel) : nullptr;
     float mc = 0.f, mn = 0.f;
-    for (int q = threadIdx.x; q < n_quads; q += 256) {
+    for (int q = blockIdx.x * 256 + threadIdx.x; q < n_quads; q += gridDim.x * 256) {
         const float4 x = __ldg(src + q);
         mc = fmaxf(mc, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
         if (want_noisy) {
@@ -186,7 +188,10 @@ clip_max_kernel(const float* __restrict__ mel_amp, int T_in, const float* __rest
         mn = threadIdx.x < 8 ? red[1][threadIdx.x] : 0.f;
         mc = warp_max(mc);
         mn = warp_max(mn);
-        if (threadIdx.x == 0) { clip_max[b] = mc; clip_max[B + b] = mn; }
+        if (threadIdx.x == 0) {
+            atomicMax(reinterpret_cast<unsigned int*>(clip_max) + b, __float_as_uint(fmaxf(mc, 0.f)));
+            if (want_noisy) atomicMax(reinterpret_cast<unsigned int*>(clip_max) + B + b, __float_as_uint(fmaxf(mn, 0.f)));
+        }
     }
 }
 
@@ -377,7 +382,14 @@ int dcase_logmel_finish(dcase_ctx* ctx, const float* mel_amp, int B, int T_in, i
     if (B == 0) return DCASE_OK;
     const DcaseStepScalars* sc = (const DcaseStepScalars*)scalars;
     DCASE_PROF("logmel_finish", stream);
-    clip_max_kernel<<<B, 256, 0, stream>>>(mel_amp, T_in, noise, noisy != nullptr, seed, step, sc, clip_max_ws, B);
+    DCASE_CUDA_CHECK(cudaMemsetAsync(clip_max_ws, 0, 2 * (size_t)B * sizeof(float), stream));
+    const int n_quads = T_in * (kMel / 4);
+    int slices = (n_quads + 1023) / 1024;                       // >= 4 quads per thread
+    const int want = (ctx->num_sms * 8 + B - 1) / B;
+    if (slices > want) slices = want;
+    if (slices < 1) slices = 1;
+    clip_max_kernel<<<dim3(slices, B), 256, 0, stream>>>(mel_amp, T_in, noise, noisy != nullptr, seed, step, sc,
+                                                         clip_max_ws, B);
     DCASE_LAUNCH_CHECK();
     const size_t total = (size_t)B * T_out * 16;
     int blocks = (int)((total + 255) / 256);
