@@ -138,7 +138,7 @@ WsLayout ws_layout(int B, int T, int NC) {
     add("rnn0", BT * 128); add("rnn1", BT * 128);
     add("den", (size_t)B * 16);
     L.acc_off = L.total;
-    add("acc0", 640); add("s12_1", 128); add("s12_2", 128);
+    add("acc0", kCnn0AccFloats); add("s12_1", 128); add("s12_2", 128);
     L.acc_bytes = L.total - L.acc_off;
     add("d_rnn1", BT * 128); add("d_rnn0", BT * 128);
     add("dgi", 2 * BT * 192); add("dgh", 2 * BT * 192);
@@ -231,6 +231,7 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     DCASE_CUDA_CHECK(cudaMemset(ctx->d_loss_scratch, 0, kLossScratchBytes));
     int rc = dcase_logmel_tables_create(ctx);
     if (rc == DCASE_OK) rc = cnn_kernels_init();
+    if (rc == DCASE_OK) rc = cnn0_kernels_init();
     if (rc == DCASE_OK) rc = conv_tc_kernels_init();
     if (rc == DCASE_OK) rc = head_kernels_init();
     if (rc != DCASE_OK) { delete ctx; return rc; }
@@ -292,7 +293,7 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
                                   params + o.bn_b[0], bn_running, training, fold0, s));
     float* out0 = wsp<float>(ws, L, "out0");
-    DCASE_TRY(launch_glu_pool_fwd0(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), out0, sms, s));
+    DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), out0, sms, s));
 
     // ---- CNN blocks 1, 2 ----
     const char* names[3][6] = {{}, {"wprep1_f", "wprep1_d", "ypre1", "stats1", "bn1", "out1"},
@@ -454,11 +455,12 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
     // ---- CNN block 0 ----
     float* acc0 = wsp<float>(ws, L, "acc0");
     const float* fold0 = wsp<float>(ws, L, "fold0");
-    DCASE_TRY(launch_glu_pool_bwd0(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0),
-                                   wsp<float>(ws, L, "d_out0"), acc0, grads + o.glu_w[0], grads + o.glu_b[0], sms, s));
+    DCASE_TRY(launch_cnn0_bwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0),
+                              wsp<float>(ws, L, "d_out0"), acc0, sms, s));
     DCASE_TRY(launch_cnn0_bwd_finalize(wsp<double>(ws, L, "mom0"), (long long)B * T * 64, params + o.conv_w[0],
-                                       params + o.conv_b[0], params + o.bn_w[0], fold0, acc0, grads + o.conv_w[0],
-                                       grads + o.conv_b[0], grads + o.bn_w[0], grads + o.bn_b[0], s));
+                                       params + o.conv_b[0], fold0, params + o.glu_w[0], acc0, grads + o.conv_w[0],
+                                       grads + o.conv_b[0], grads + o.bn_w[0], grads + o.bn_b[0], grads + o.glu_w[0],
+                                       grads + o.glu_b[0], s));
     return DCASE_OK;
 }
 

@@ -684,41 +684,13 @@ bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, lon
     }
 }
 
-// Layer-0 parameter gradients from {S1, G} and the tap moments (one block of 64 threads).
-__global__ void cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix,
-                                         const float* __restrict__ w, const float* __restrict__ b,
-                                         const float* __restrict__ fold0, const float* __restrict__ acc0,
-                                         float* __restrict__ g_w, float* __restrict__ g_b,
-                                         float* __restrict__ g_gamma, float* __restrict__ g_beta) {
-    const int c = threadIdx.x;
-    const double n = (double)n_pix;
-    const double mean = fold0[kFold0Mean + c], invstd = fold0[kFold0Invstd + c], a = fold0[kFold0A + c];
-    const double S1 = acc0[c];
-    double G[9], wG = 0.0;
-    for (int k = 0; k < 9; ++k) { G[k] = acc0[64 + c * 9 + k]; wG += (double)w[c * 9 + k] * G[k]; }
-    const double bm = (double)b[c] - mean;
-    const double S2 = invstd * (wG + bm * S1);          // sum d_y * xhat
-    g_gamma[c] = (float)S2;
-    g_beta[c] = (float)S1;
-    g_b[c] = 0.f;                                       // BN cancels the conv bias
-    for (int k = 0; k < 9; ++k) {
-        double sxx = 0.0;                               // sum_p xhat_c * x_k
-        for (int l = 0; l < 9; ++l)
-            sxx += (double)w[c * 9 + l] * mom[l <= k ? tri_index(l, k) : tri_index(k, l)];
-        sxx = invstd * (sxx + bm * mom[k]);
-        g_w[c * 9 + k] = (float)(a * (G[k] - (S1 / n) * mom[k] - (S2 / n) * sxx));
-    }
-}
-
 constexpr size_t kGluFwdSmem = kGluFwdSmemBytes;
 constexpr size_t kGluBwdSmem = kGluBwdSmemBytes;
 
 }  // namespace
 
 int cnn_kernels_init() {
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluFwdSmem));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluFwdSmem));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluBwdSmem));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluBwdSmem));
     return DCASE_OK;
 }
@@ -748,18 +720,6 @@ static int grid_for(long long n_tiles, int num_sms, int per_sm) {
     return (int)(n_tiles < g ? n_tiles : g);
 }
 
-int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                         DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
-    DCASE_PROF("cnn0_fused_fwd", s);
-    GluArgs a{};
-    a.src = x; a.n_pix = (long long)B * T * 64; a.T = T; a.F = 64; a.aff = fold0;
-    a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
-    const long long n_tiles = a.n_pix / kTile;
-    glu_pool_fwd_kernel<true><<<grid_for(n_tiles, num_sms, 4), kThreads, kGluFwdSmem, s>>>(a);
-    DCASE_LAUNCH_CHECK();
-    return DCASE_OK;
-}
-
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
                         const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
     DCASE_PROF(F == 16 ? "glu_pool_fwd_l1" : "glu_pool_fwd_l2", s);
@@ -775,20 +735,6 @@ int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma,
                        int training, float* bn, cudaStream_t s) {
     DCASE_PROF("bn_finalize", s);
     bn_finalize_kernel<<<1, 64, 0, s>>>(stats, n_pix, gamma, beta, running, training, bn);
-    DCASE_LAUNCH_CHECK();
-    return DCASE_OK;
-}
-
-int launch_glu_pool_bwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                         DropoutCfg drop, const float* d_out, float* acc0, float* g_glu_w, float* g_glu_b,
-                         int num_sms, cudaStream_t s) {
-    DCASE_PROF("cnn0_fused_bwd", s);
-    GluArgs a{};
-    a.src = x; a.n_pix = (long long)B * T * 64; a.T = T; a.F = 64; a.aff = fold0;
-    a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.stat_acc = acc0;
-    a.g_glu_w = g_glu_w; a.g_glu_b = g_glu_b;
-    const long long n_tiles = a.n_pix / kTile;
-    glu_pool_bwd_kernel<true><<<grid_for(n_tiles, num_sms, 1), kThreads, kGluBwdSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
@@ -816,17 +762,6 @@ int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const fl
     long long blocks = (n_pix * 16 + 255) / 256;
     if (blocks > num_sms * 8) blocks = num_sms * 8;
     bn_bwd_apply_kernel<<<(int)blocks, 256, 0, s>>>(d_y, ypre, n_pix, bn, s12, g_gamma, g_beta, g_conv_b);
-    DCASE_LAUNCH_CHECK();
-    return DCASE_OK;
-}
-
-int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
-                             const float* gamma, const float* fold0, const float* acc0, float* g_conv_w,
-                             float* g_conv_b, float* g_gamma, float* g_beta, cudaStream_t s) {
-    DCASE_PROF("cnn0_bwd_finalize", s);
-    (void)gamma;
-    cnn0_bwd_finalize_kernel<<<1, 64, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, acc0, g_conv_w, g_conv_b, g_gamma,
-                                            g_beta);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

@@ -32,8 +32,16 @@ int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, 
 int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running /*[2][64]*/, int training,
                         float* fold0, cudaStream_t s);
-int launch_glu_pool_fwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                         DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
+// cnn0.cu: fused block 0 (conv0 + BN + GLU + dropout + pool), forward / backward / parameter gradients
+int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
+                    DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
+constexpr int kCnn0AccFloats = 128 * 16;   // {U[64][16], S2[64][16]}, zeroed before launch_cnn0_bwd
+int launch_cnn0_bwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
+                    DropoutCfg drop, const float* d_out, float* us, int num_sms, cudaStream_t s);
+int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
+                             const float* fold0, const float* glu_w, const float* us, float* g_conv_w, float* g_conv_b,
+                             float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b, cudaStream_t s);
+int cnn0_kernels_init();
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
                         const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
 // conv_tc.cu: weight images are the swizzled shared-memory layout of the tcgen05 B operand (36864 floats each)
@@ -42,9 +50,6 @@ int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, c
                    float* out, double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta,
                        float* running, int training, float* bn, cudaStream_t s);
-int launch_glu_pool_bwd0(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                         DropoutCfg drop, const float* d_out, float* acc0 /*see cnn.cu*/, float* g_glu_w,
-                         float* g_glu_b, int num_sms, cudaStream_t s);
 int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* bn, const float* gamma,
                         const float* beta, const float* glu_w, const float* glu_b, DropoutCfg drop,
                         const float* d_out, float* d_y, float* s12 /*[2][64]*/, float* g_glu_w, float* g_glu_b,
@@ -54,8 +59,5 @@ int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const fl
                         cudaStream_t s);
 int launch_conv_wgrad(const float* d_pre, const float* in, int B, int T_l, int F, float* g_w, int num_sms,
                       cudaStream_t s);
-int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
-                             const float* gamma, const float* fold0, const float* acc0, float* g_conv_w,
-                             float* g_conv_b, float* g_gamma, float* g_beta, cudaStream_t s);
 int cnn_kernels_init();
 int conv_tc_kernels_init();
