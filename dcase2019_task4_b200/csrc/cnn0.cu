@@ -54,32 +54,64 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 }
 __device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-struct KRow {    // K-major SW128 operand: two blocks of 128 rows x 32 channels
-    unsigned char* base;
-    int r;
-    __device__ __forceinline__ float4* chunk(int c4) const {
-        return reinterpret_cast<float4*>(base + (c4 >> 3) * 16384 + tc::sw128_chunk(r, c4 & 7));
-    }
-};
-struct MnRow {   // MN-major (SWIZZLE_128B_BASE32B) operand: blocks of 128 rows (= K index) x 32 channels
-    unsigned char* base;
-    int r;
-    __device__ __forceinline__ float4* chunk(int c4) const {
-        return reinterpret_cast<float4*>(base + (c4 >> 3) * 16384 + tc::sw128b32_chunk(r, c4 & 7));
-    }
-};
+// ---- shared-memory operand tiles, addressed with 32-bit shared-space addresses ----------------------------
+// Both tcgen05 layouts used here are XOR swizzles of the 16-byte chunk index inside a 128-byte row, so the address
+// of chunk c4 (channels 4 c4 .. 4 c4 + 3) of a thread's row is  (row_base ^ ((c4 & 7) << 4)) + (c4 >> 3) * 16 KB
+// with the row's own swizzle bits folded into row_base (region bases are 1024-byte aligned).
+__device__ __forceinline__ uint32_t krow_base(uint32_t region, int r) {    // K-major SWIZZLE_128B (tc::sw128_chunk)
+    return region + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((r & 7) << 4));
+}
+__device__ __forceinline__ uint32_t mnrow_base(uint32_t region, int r) {   // MN-major SWIZZLE_128B_BASE32B
+    return region + (uint32_t)(r * 128 + ((r & 3) << 5));
+}
+__device__ __forceinline__ uint32_t chunk_addr(uint32_t row_base, int c4) {
+    return (row_base ^ (uint32_t)((c4 & 7) << 4)) + (uint32_t)(c4 >> 3) * 16384u;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
-// stage x rows t0-1 .. t0+2 (zero padded) of the tile's clip: xs[4][66]
-__device__ __forceinline__ void load_xs(const float* __restrict__ x, long long tile, int T, float* xs, int t, int nt) {
+// x rows t0-1 .. t0+2 (zero padded) of a tile = xs[4][66]; thread t of nt owns elements t, t + nt (nt >= 132)
+struct XsRegs { float v0, v1; };
+__device__ __forceinline__ float xs_value(const float* __restrict__ x, long long tile, int T, int i) {
     const long long r0 = 2 * tile;
     const long long b = r0 / T;
-    const int t0 = (int)(r0 % T);
-    for (int i = t; i < 4 * 66; i += nt) {
-        const int hr = i / 66, hc = i - hr * 66;
-        const int tt = t0 - 1 + hr, ff = hc - 1;
-        const bool ok = tt >= 0 && tt < T && ff >= 0 && ff < 64;
-        xs[i] = ok ? __ldg(x + (b * T + tt) * 64 + ff) : 0.f;
-    }
+    const int t0 = (int)(r0 - b * T);
+    const int hr = i / 66, hc = i - hr * 66;
+    const int tt = t0 - 1 + hr, ff = hc - 1;
+    const bool ok = tt >= 0 && tt < T && ff >= 0 && ff < 64;
+    return ok ? __ldg(x + (b * T + tt) * 64 + ff) : 0.f;
+}
+__device__ __forceinline__ XsRegs xs_prefetch(const float* __restrict__ x, long long tile, int T, int t) {
+    XsRegs r;
+    r.v0 = xs_value(x, tile, T, t);
+    r.v1 = t + 256 < 4 * 66 ? xs_value(x, tile, T, t + 256) : 0.f;
+    return r;
+}
+__device__ __forceinline__ void xs_commit(const XsRegs& r, float* xs, int t) {
+    xs[t] = r.v0;
+    if (t + 256 < 4 * 66) xs[t + 256] = r.v1;
+}
+
+// rounds to the nearest tf32 (ties away), finite inputs only: 2 instructions instead of cvt.rna's 3
+__device__ __forceinline__ float tf32_round_fast(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+// operand rows of MMA0 for pixel `row` of a tile: [tap0..8, 1, 0, 0] -> chunks 0..2 of its row
+__device__ __forceinline__ void write_taps(const float* xs, int row, uint32_t t0_rowbase) {
+    const int tr = row >> 6, f = row & 63;
+    float tap[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) tap[k] = tf32_round_fast(xs[(tr + k / 3) * 66 + f + (k % 3)]);
+    sts128(chunk_addr(t0_rowbase, 0), tap[0], tap[1], tap[2], tap[3]);
+    sts128(chunk_addr(t0_rowbase, 1), tap[4], tap[5], tap[6], tap[7]);
+    sts128(chunk_addr(t0_rowbase, 2), tap[8], 1.f, 0.f, 0.f);
 }
 
 // Wg[n][k] -> K-major SW128 B operand (two blocks of 64 rows), rounded to tf32 after the truncation compensation
@@ -127,28 +159,36 @@ __device__ __forceinline__ void sigmoid32(const float (&y)[32], float (&g)[32]) 
     for (int i = 0; i < 32; ++i) g[i] = rcp_ftz(1.f + g[i]);
 }
 
+__device__ __forceinline__ void require_aligned_smem(const void* p) {
+    if (tc::smem_u32(p) & 1023u) __trap();      // the operand swizzles assume 1024-byte aligned regions
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-// smem (1024-B aligned): Wb 16 KB | T0 16 KB | A 32 KB (y K-major, then z MN-major) | P 8 KB | bg, xs, keep
-// TMEM (128 columns): [0,64) y then lin, [64,80) pooled output (M = 64 channels, N = 16 windows)
+// Software pipeline per CTA (3 CTAs / SM): MMA0 of the NEXT tile is issued together with MMA1 of the current one
+// and the next tile's x rows are prefetched into registers, so the only tensor-core round trip a tile waits for
+// is MMA1; the pooled result of tile i is drained while tile i + 1 computes.
+// smem (1024-B aligned, all dynamic): Wb 16 KB | T0 16 KB | A 32 KB (y K-major, then z MN-major) | P 8 KB |
+//                                     bg[64] | xs[4][66] | keep_lo[128] | 3 mbarriers | tmem base
+// TMEM (128 columns): [0,64) y (next tile's y while the current tile is in its GLU phase),
+//                     [64,128) lin, then [64,80) the pooled output (M = 64 channels, N = 16 windows)
 constexpr int kFwdWb = 0, kFwdT0 = 16384, kFwdA = 32768, kFwdP = 65536, kFwdMisc = 73728;
-constexpr int kFwdSmemBytes = 1024 + kFwdMisc + 64 * 4 + 4 * 66 * 4 + 128 * 8;
+constexpr int kFwdSmemBytes = kFwdMisc + 64 * 4 + 4 * 66 * 4 + 128 * 4 + 3 * 8 + 8;
 constexpr int kFwdThreads = 256;
 
 __global__ void __launch_bounds__(kFwdThreads, 3)
 cnn0_fwd_kernel(Cnn0Args a) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    extern __shared__ __align__(1024) unsigned char smem[];
+    require_aligned_smem(smem);
     unsigned char* Wb = smem + kFwdWb;
     unsigned char* T0 = smem + kFwdT0;
-    unsigned char* A = smem + kFwdA;
     unsigned char* Pm = smem + kFwdP;
     float* bg = reinterpret_cast<float*>(smem + kFwdMisc);
     float* xs = bg + 64;
-    uint2* keep_s = reinterpret_cast<uint2*>(xs + 4 * 66);
-    __shared__ uint64_t bar_s, bar_pool_s;
-    __shared__ uint32_t tmem_base_s;
+    uint32_t* keep_lo = reinterpret_cast<uint32_t*>(xs + 4 * 66);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(keep_lo + 128);     // [0] MMA0, [1] MMA1, [2] MMA2 (pool)
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 3);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & 127, half = tid >> 7;
 
@@ -159,69 +199,79 @@ cnn0_fwd_kernel(Cnn0Args a) {
         *reinterpret_cast<float*>(Pm + (p >> 5) * 2048 + tc::sw128_off(w, p & 31)) = (((p & 63) >> 2) == w) ? 1.f : 0.f;
     }
     if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
-    if (tid == 0) { tc::mbar_init(&bar_s, 1); tc::mbar_init(&bar_pool_s, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
+    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(tmem_base_s, 128);
     uint64_t seed = a.drop.seed; uint32_t step = a.drop.step;
     if (a.drop.sc) { seed = a.drop.sc->seed; step = a.drop.sc->step; }
+    const long long n_tiles = (long long)a.B * a.T / 2;
+    const long long stride = gridDim.x;
+    long long cur = blockIdx.x;
+    const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), a_a = tc::smem_u32(smem + kFwdA), p_a = tc::smem_u32(Pm);
+    const uint32_t t0_rb = krow_base(t0_a, row), y_rb = krow_base(a_a, row), z_rb = mnrow_base(a_a, row);
+    const bool drop = a.drop.enabled != 0;
+
+    // prologue: operands of the first tile, its MMA0, and the x rows of the second tile in registers
+    uint32_t keep_next = 0xffffffffu;       // keep bits (this thread's 32 channels) of the tile whose MMA0 is in flight
+    {
+        XsRegs xr = xs_prefetch(a.x, cur, a.T, tid);
+        xs_commit(xr, xs, tid);
+    }
+    __syncthreads();
+    const uint32_t tmem = *tmem_base_s;
+    if (half == 0) write_taps(xs, row, t0_rb);
+    else if (drop) {
+        const uint4 r = philox4x32_10((uint64_t)(cur * kTile + row), a.drop.stream, step, seed);
+        keep_lo[row] = r.x;
+        keep_next = r.y;
+    }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = tmem_base_s;
-    const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), a_a = tc::smem_u32(A), p_a = tc::smem_u32(Pm);
+    if (tid == 0) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
+    if (drop && half == 0) keep_next = keep_lo[row];
+    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, cur + stride, a.T, tid) : XsRegs{0.f, 0.f};
+
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t phase = 0, phase_pool = 0;
-
-    const long long n_tiles = (long long)a.B * a.T / 2;
+    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
     // 1/8 window, x2 inverted dropout, truncation of z undone here (P is exactly 1)
-    const float pool_scale = (a.drop.enabled ? 0.25f : 0.125f) * kTruncComp;
-    const KRow y_row{A, row};
-    const MnRow z_row{A, row};
-    long long prev_tile = -1;
+    const float pool_scale = (drop ? 0.25f : 0.125f) * kTruncComp;
+    long long prev = -1;
 
-    auto pooled_epilogue = [&]() {     // pooled tile `prev_tile`: TMEM -> out; also frees the z buffer
-        tc::mbar_wait(&bar_pool_s, phase_pool);
-        phase_pool ^= 1;
+    for (; cur < n_tiles; cur += stride) {
+        const long long nxt = cur + stride;
+        const bool has_next = nxt < n_tiles;
+        const uint32_t keep = keep_next;
+        tc::mbar_wait(&bars[0], ph0);            // y of `cur` is in TMEM; T0 may be rewritten
+        ph0 ^= 1;
         tc::fence_after_sync();
-        if (warp < 4) {
-            float v[16];
-            tc::tmem_ld16(tmem + 64 + lane_base, v);
-            tc::tmem_ld_wait();
-            if (lane < 16) {               // accumulator row m of an M=64 MMA lives in lane 32*(m/16) + m%16
-                float* dst = a.out + prev_tile * 16 * 64 + 16 * warp + lane;
+        uint32_t keep_hi_next = 0xffffffffu;
+        if (has_next) {
+            xs_commit(xr, xs, tid);
+            __syncthreads();
+            if (half == 0) write_taps(xs, row, t0_rb);
+            else if (drop) {
+                const uint4 r = philox4x32_10((uint64_t)(nxt * kTile + row), a.drop.stream, step, seed);
+                keep_lo[row] = r.x;
+                keep_hi_next = r.y;
+            }
+            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, nxt + stride, a.T, tid);
+        }
+        if (prev >= 0) {                          // pooled tile `prev`: TMEM -> out; also frees the z buffer
+            tc::mbar_wait(&bars[2], ph2);
+            ph2 ^= 1;
+            tc::fence_after_sync();
+            if (warp < 4) {
+                float v[16];
+                tc::tmem_ld16(tmem + 64 + lane_base, v);
+                tc::tmem_ld_wait();
+                if (lane < 16) {                  // accumulator row m of an M=64 MMA lives in lane 32*(m/16) + m%16
+                    float* dst = a.out + prev * 16 * 64 + 16 * warp + lane;
 #pragma unroll
-                for (int w = 0; w < 16; ++w) dst[w * 64] = tc::tf32_rn(pool_scale * v[w]);   // conv1 MMA operand
+                    for (int w = 0; w < 16; ++w) dst[w * 64] = tc::tf32_rn(pool_scale * v[w]);   // conv1 MMA operand
+                }
             }
         }
-        tc::fence_before_sync();
-    };
-
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        load_xs(a.x, tile, a.T, xs, tid, kFwdThreads);
-        __syncthreads();
-        if (half == 0) {                   // operand rows of MMA0: [tap0..8, 1, 0...]
-            const int tr = row >> 6, f = row & 63;
-            float tap[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) tap[k] = tc::tf32_rn(xs[(tr + k / 3) * 66 + f + (k % 3)]);
-            *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 0)) = make_float4(tap[0], tap[1], tap[2], tap[3]);
-            *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 1)) = make_float4(tap[4], tap[5], tap[6], tap[7]);
-            *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 2)) = make_float4(tap[8], 1.f, 0.f, 0.f);
-        } else if (a.drop.enabled) {       // dropout keep bits of the pixel (64 channels)
-            const uint4 r = philox4x32_10((uint64_t)(tile * kTile + row), a.drop.stream, step, seed);
-            keep_s[row] = make_uint2(r.x, r.y);
-        }
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            issue_mma0(tmem, t0_a);
-            tc::umma_commit(&bar_s);
-        }
-        if (prev_tile >= 0) pooled_epilogue();          // overlaps MMA0
-        tc::mbar_wait(&bar_s, phase);
-        phase ^= 1;
-        tc::fence_after_sync();
         float g[32];
         {
             float y[32];
@@ -229,38 +279,35 @@ cnn0_fwd_kernel(Cnn0Args a) {
             tc::fence_before_sync();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                *y_row.chunk(8 * half + q) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                sts128(chunk_addr(y_rb, 8 * half + q), y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
             sigmoid32(y, g);
         }
         tc::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
-            tc::umma_128x64x64_kmajor(tmem, a_a, wb_a, false);
-            tc::umma_commit(&bar_s);
+            tc::umma_128x64x64_kmajor(tmem + 64, a_a, wb_a, false);
+            tc::umma_commit(&bars[1]);
+            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
         }
-        if (a.drop.enabled) {
-            const uint2 kw = keep_s[row];
-            const uint32_t keep = half ? kw.y : kw.x;
+        if (drop) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) g[i] = (keep & (1u << i)) ? g[i] : 0.f;
+            keep_next = half ? keep_hi_next : keep_lo[row];
         }
-        tc::mbar_wait(&bar_s, phase);
-        phase ^= 1;
+        tc::mbar_wait(&bars[1], ph1);
+        ph1 ^= 1;
         tc::fence_after_sync();
         {
             float lin[32];
-            tmem_ld32(tmem + lane_base + 32 * half, lin);
+            tmem_ld32(tmem + 64 + lane_base + 32 * half, lin);
             tc::fence_before_sync();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bg + 32 * half + 4 * q);
-                float4 z;
-                z.x = (lin[4 * q + 0] + b4.x) * g[4 * q + 0];
-                z.y = (lin[4 * q + 1] + b4.y) * g[4 * q + 1];
-                z.z = (lin[4 * q + 2] + b4.z) * g[4 * q + 2];
-                z.w = (lin[4 * q + 3] + b4.w) * g[4 * q + 3];
-                *z_row.chunk(8 * half + q) = z;          // overwrites y (MMA1 has completed)
+                sts128(chunk_addr(z_rb, 8 * half + q),           // overwrites y (MMA1 has completed)
+                       (lin[4 * q + 0] + b4.x) * g[4 * q + 0], (lin[4 * q + 1] + b4.y) * g[4 * q + 1],
+                       (lin[4 * q + 2] + b4.z) * g[4 * q + 2], (lin[4 * q + 3] + b4.w) * g[4 * q + 3]);
             }
         }
         tc::fence_proxy_async();
@@ -272,11 +319,25 @@ cnn0_fwd_kernel(Cnn0Args a) {
             for (int j = 0; j < 16; ++j)
                 tc::umma_tf32(tmem + 64, tc::smem_desc(a_a + j * 1024, 16384, 512, 1),
                               tc::smem_desc_sw128(p_a + (j >> 2) * 2048 + (j & 3) * 32, 16, 1024), idesc, j > 0 ? 1u : 0u);
-            tc::umma_commit(&bar_pool_s);
+            tc::umma_commit(&bars[2]);
         }
-        prev_tile = tile;
+        prev = cur;
     }
-    if (prev_tile >= 0) pooled_epilogue();
+    if (prev >= 0) {
+        tc::mbar_wait(&bars[2], ph2);
+        tc::fence_after_sync();
+        if (warp < 4) {
+            float v[16];
+            tc::tmem_ld16(tmem + 64 + lane_base, v);
+            tc::tmem_ld_wait();
+            if (lane < 16) {
+                float* dst = a.out + prev * 16 * 64 + 16 * warp + lane;
+#pragma unroll
+                for (int w = 0; w < 16; ++w) dst[w * 64] = tc::tf32_rn(pool_scale * v[w]);
+            }
+        }
+    }
+    tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
@@ -284,21 +345,22 @@ cnn0_fwd_kernel(Cnn0Args a) {
 // ---------------------------------------------------------------------------------------------
 // backward (recomputes the forward per tile)
 // ---------------------------------------------------------------------------------------------
-// One CTA per SM, 512 threads = two independent groups of 256 (named barriers), each streaming its own tiles so
-// one group's CUDA-core phase overlaps the other's tensor-core round trips.
-// smem (1024-B aligned): Wb 16 KB | per group: T0 16 KB | E 16 KB (MN-major [taps | 1]) | DL 32 KB (first y,
-//                        K-major) | D2 32 KB (DL and D2 contiguous: one M = 128 MN-major A operand) | misc
-// TMEM (512 columns): group g at 256 g: [0,64) y then lin, [64,80) accumulator {U | S2}[128][16]
+// One CTA per SM, 512 threads = two independent groups of 256 (named barriers), each streaming its own tiles with
+// the same software pipeline as the forward (MMA0 of the next tile rides with MMA1 of the current one), so one
+// group's CUDA-core phases overlap the other's tensor-core round trips.
+// smem (1024-B aligned, all dynamic): Wb 16 KB | per group: T0 16 KB | E 16 KB (MN-major [taps | 1]) | DL 32 KB
+//                        (first y, K-major) | D2 32 KB (DL and D2 contiguous: one M = 128 MN-major A operand) | misc
+// TMEM (512 columns): group g at 256 g: [0,64) y, [64,128) lin, [128,144) accumulator {U | S2}[128][16]
 constexpr int kBwdThreads = 512;
 constexpr int kBwdGroupBytes = 16384 + 16384 + 32768 + 32768;
 constexpr int kBwdMiscOff = 16384 + 2 * kBwdGroupBytes;
-constexpr int kBwdMiscGroupFloats = 4 * 66 + 2 * 128;      // xs | keep (uint2 [128])
-constexpr int kBwdSmemBytes = 1024 + kBwdMiscOff + (64 + 2 * kBwdMiscGroupFloats) * 4;
+constexpr int kBwdMiscGroupFloats = 4 * 66 + 128;          // xs | keep_lo
+constexpr int kBwdSmemBytes = kBwdMiscOff + (64 + 2 * kBwdMiscGroupFloats) * 4 + 6 * 8 + 8;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 cnn0_bwd_kernel(Cnn0Args a) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    extern __shared__ __align__(1024) unsigned char smem[];
+    require_aligned_smem(smem);
     const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255;
     const int warp = tid >> 5, lane = tid & 31;
     const int row = gt & 127, half = gt >> 7;
@@ -306,72 +368,87 @@ cnn0_bwd_kernel(Cnn0Args a) {
     unsigned char* gbase = smem + 16384 + grp * kBwdGroupBytes;
     unsigned char* T0 = gbase;
     unsigned char* E = gbase + 16384;
-    unsigned char* DL = gbase + 32768;
-    unsigned char* D2 = gbase + 65536;
     float* bg = reinterpret_cast<float*>(smem + kBwdMiscOff);
     float* xs = bg + 64 + grp * kBwdMiscGroupFloats;
-    uint2* keep_s = reinterpret_cast<uint2*>(xs + 4 * 66);
-    __shared__ uint64_t bar_s[2], bar_acc_s[2];
-    __shared__ uint32_t tmem_base_s;
+    uint32_t* keep_lo = reinterpret_cast<uint32_t*>(xs + 4 * 66);
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(bg + 64 + 2 * kBwdMiscGroupFloats);
+    uint64_t* bars = bars_all + 3 * grp;                 // [0] MMA0, [1] MMA1, [2] MMA3 (accumulate)
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars_all + 6);
 
     stage_wg(a.glu_w, Wb, tid, kBwdThreads);
     stage_w0(a.fold0, T0, gt, 256);
     for (int r = gt; r < 128; r += 256)                    // E chunk 3 (columns 12..15) stays zero
         *reinterpret_cast<float4*>(E + tc::sw128b32_chunk(r, 3)) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
-    if (gt == 0) { tc::mbar_init(&bar_s[grp], 1); tc::mbar_init(&bar_acc_s[grp], 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    if (gt == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1); tc::fence_mbar_init(); }
+    if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     uint64_t seed = a.drop.seed; uint32_t step = a.drop.step;
     if (a.drop.sc) { seed = a.drop.sc->seed; step = a.drop.sc->step; }
+    const long long n_tiles = (long long)a.B * a.T / 2;
+    const long long stride = (long long)gridDim.x * 2;
+    long long cur = (long long)blockIdx.x * 2 + grp;
+    const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), e_a = tc::smem_u32(E), dl_a = tc::smem_u32(gbase + 32768);
+    const uint32_t t0_rb = krow_base(t0_a, row), e_rb = mnrow_base(e_a, row), y_rb = krow_base(dl_a, row),
+                   dl_rb = mnrow_base(dl_a, row);       // D2 rows: dl_rb + 32768 (chunk_addr's block stride continues)
+    const bool drop = a.drop.enabled != 0;
+    const bool active = cur < n_tiles;
+    const int bar_id = 1 + grp;
+
+    uint32_t keep_next = 0xffffffffu;
+    if (active) {
+        XsRegs xr0 = xs_prefetch(a.x, cur, a.T, gt);
+        xs_commit(xr0, xs, gt);
+    }
+    __syncthreads();
+    const uint32_t tmem = *tmem_base_s + 256u * grp;
+    if (active) {
+        if (half == 0) write_taps(xs, row, t0_rb);
+        else if (drop) {
+            const uint4 r = philox4x32_10((uint64_t)(cur * kTile + row), a.drop.stream, step, seed);
+            keep_lo[row] = r.x;
+            keep_next = r.y;
+        }
+    }
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = tmem_base_s + 256u * grp;
-    const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), e_a = tc::smem_u32(E), dl_a = tc::smem_u32(DL);
+    if (active && gt == 0) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
+    if (active && drop && half == 0) keep_next = keep_lo[row];
+    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, cur + stride, a.T, gt) : XsRegs{0.f, 0.f};
+
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint64_t* bar = &bar_s[grp];
-    uint64_t* bar_acc = &bar_acc_s[grp];
-    const int bar_id = 1 + grp;
-    uint32_t phase = 0, phase_acc = 0;
+    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
     bool pending = false, first = true;
+    const float dz_scale = drop ? 0.25f : 0.125f;
 
-    const long long n_tiles = (long long)a.B * a.T / 2;
-    const float dz_scale = a.drop.enabled ? 0.25f : 0.125f;
-    const KRow y_row{DL, row};
-    const MnRow dl_row{DL, row}, d2_row{D2, row};
-
-    for (long long tile = (long long)blockIdx.x * 2 + grp; tile < n_tiles; tile += (long long)gridDim.x * 2) {
-        load_xs(a.x, tile, a.T, xs, gt, 256);
-        if (pending) { tc::mbar_wait(bar_acc, phase_acc); phase_acc ^= 1; pending = false; }   // E / DL / D2 free again
-        bar_sync_named(bar_id, 256);
-        if (half == 0) {
-            const int tr = row >> 6, f = row & 63;
-            float tap[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) tap[k] = tc::tf32_rn(xs[(tr + k / 3) * 66 + f + (k % 3)]);
-            const float4 c0 = make_float4(tap[0], tap[1], tap[2], tap[3]), c1 = make_float4(tap[4], tap[5], tap[6], tap[7]),
-                         c2 = make_float4(tap[8], 1.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 0)) = c0;
-            *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 1)) = c1;
-            *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(row, 2)) = c2;
-            *reinterpret_cast<float4*>(E + tc::sw128b32_chunk(row, 0)) = c0;
-            *reinterpret_cast<float4*>(E + tc::sw128b32_chunk(row, 1)) = c1;
-            *reinterpret_cast<float4*>(E + tc::sw128b32_chunk(row, 2)) = c2;
-        } else if (a.drop.enabled) {
-            const uint4 r = philox4x32_10((uint64_t)(tile * kTile + row), a.drop.stream, step, seed);
-            keep_s[row] = make_uint2(r.x, r.y);
-        }
-        tc::fence_proxy_async();
-        bar_sync_named(bar_id, 256);
-        if (gt == 0) {
-            tc::fence_after_sync();
-            issue_mma0(tmem, t0_a);
-            tc::umma_commit(bar);
-        }
-        tc::mbar_wait(bar, phase);
-        phase ^= 1;
+    for (; cur < n_tiles; cur += stride) {
+        const long long nxt = cur + stride;
+        const bool has_next = nxt < n_tiles;
+        const uint32_t keep = keep_next;
+        tc::mbar_wait(&bars[0], ph0);            // y of `cur` is in TMEM; T0 may be read / rewritten
+        ph0 ^= 1;
+        if (pending) { tc::mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }   // E / DL / D2 free again
         tc::fence_after_sync();
+        if (half == 0) {                          // E (MN-major copy of this tile's operand rows) for MMA3
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 v = lds128(chunk_addr(t0_rb, c));
+                sts128(chunk_addr(e_rb, c), v.x, v.y, v.z, v.w);
+            }
+        }
+        uint32_t keep_hi_next = 0xffffffffu;
+        if (has_next) {
+            xs_commit(xr, xs, gt);
+            bar_sync_named(bar_id, 256);
+            if (half == 0) write_taps(xs, row, t0_rb);
+            else if (drop) {
+                const uint4 r = philox4x32_10((uint64_t)(nxt * kTile + row), a.drop.stream, step, seed);
+                keep_lo[row] = r.x;
+                keep_hi_next = r.y;
+            }
+            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, nxt + stride, a.T, gt);
+        }
         float g[32];
         {
             float y[32];
@@ -379,39 +456,39 @@ cnn0_bwd_kernel(Cnn0Args a) {
             tc::fence_before_sync();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                *y_row.chunk(8 * half + q) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                sts128(chunk_addr(y_rb, 8 * half + q), y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
             sigmoid32(y, g);
         }
         tc::fence_proxy_async();
         bar_sync_named(bar_id, 256);
         if (gt == 0) {
             tc::fence_after_sync();
-            tc::umma_128x64x64_kmajor(tmem, dl_a, wb_a, false);
-            tc::umma_commit(bar);
+            tc::umma_128x64x64_kmajor(tmem + 64, dl_a, wb_a, false);
+            tc::umma_commit(&bars[1]);
+            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
         }
         // gradient of the pooled output for this pixel's window, dropout mask and 1/8 folded in (overlaps MMA1)
         float dz[32];
         {
             const int f = row & 63;
-            const float4* dsrc = reinterpret_cast<const float4*>(a.d_out + (tile * 16 + (f >> 2)) * 64) + 8 * half;
+            const float4* dsrc = reinterpret_cast<const float4*>(a.d_out + (cur * 16 + (f >> 2)) * 64) + 8 * half;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 d = __ldg(dsrc + q);
                 dz[4 * q] = d.x * dz_scale; dz[4 * q + 1] = d.y * dz_scale; dz[4 * q + 2] = d.z * dz_scale; dz[4 * q + 3] = d.w * dz_scale;
             }
-            if (a.drop.enabled) {
-                const uint2 kw = keep_s[row];
-                const uint32_t keep = half ? kw.y : kw.x;
+            if (drop) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) dz[i] = (keep & (1u << i)) ? dz[i] : 0.f;
+                keep_next = half ? keep_hi_next : keep_lo[row];
             }
         }
-        tc::mbar_wait(bar, phase);
-        phase ^= 1;
+        tc::mbar_wait(&bars[1], ph1);
+        ph1 ^= 1;
         tc::fence_after_sync();
         {
             float lin[32];
-            tmem_ld32(tmem + lane_base + 32 * half, lin);
+            tmem_ld32(tmem + 64 + lane_base + 32 * half, lin);
             tc::fence_before_sync();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -425,8 +502,9 @@ cnn0_bwd_kernel(Cnn0Args a) {
                     dl[e] = dz[i] * g[i];                        // grad wrt lin
                     d2[e] = dl[e] * fmaf(-t, g[i], t);           // grad wrt y through the gate: dz t g (1 - g)
                 }
-                *dl_row.chunk(8 * half + q) = make_float4(dl[0], dl[1], dl[2], dl[3]);   // overwrites y (MMA1 done)
-                *d2_row.chunk(8 * half + q) = make_float4(d2[0], d2[1], d2[2], d2[3]);
+                const uint32_t addr = chunk_addr(dl_rb, 8 * half + q);
+                sts128(addr, dl[0], dl[1], dl[2], dl[3]);                 // overwrites y (MMA1 has completed)
+                sts128(addr + 32768u, d2[0], d2[1], d2[2], d2[3]);
             }
         }
         tc::fence_proxy_async();
@@ -436,18 +514,18 @@ cnn0_bwd_kernel(Cnn0Args a) {
             constexpr uint32_t idesc = tc::idesc_tf32(128, 16, 1, 1);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                tc::umma_tf32(tmem + 64, tc::smem_desc(dl_a + j * 1024, 16384, 512, 1), tc::smem_desc(e_a + j * 1024, 16384, 512, 1),
+                tc::umma_tf32(tmem + 128, tc::smem_desc(dl_a + j * 1024, 16384, 512, 1), tc::smem_desc(e_a + j * 1024, 16384, 512, 1),
                               idesc, (!first || j > 0) ? 1u : 0u);
-            tc::umma_commit(bar_acc);
+            tc::umma_commit(&bars[2]);
         }
         pending = true;
         first = false;
     }
-    if (pending) { tc::mbar_wait(bar_acc, phase_acc); phase_acc ^= 1; }
+    if (pending) { tc::mbar_wait(&bars[2], ph2); ph2 ^= 1; }
     tc::fence_after_sync();
     if (!first && (warp & 7) < 4) {        // warps 0..3 of each group: accumulator rows 32 q .. 32 q + 31
         float v[16];
-        tc::tmem_ld16(tmem + 64 + lane_base, v);
+        tc::tmem_ld16(tmem + 128 + lane_base, v);
         tc::tmem_ld_wait();
         const int m = 32 * (warp & 3) + lane;
 #pragma unroll
@@ -455,7 +533,7 @@ cnn0_bwd_kernel(Cnn0Args a) {
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+    if (warp == 0) tc::tmem_dealloc(*tmem_base_s, 512);
 }
 
 // One block of 256 threads: {U, S2} -> GLU parameter gradients and S = Wg^T U + S2; then (threads 0..63) the
