@@ -50,5 +50,6 @@ struct ColsumBatch {
 
 int launch_sgemm_batch(const GemmBatch& g, cudaStream_t s);
 int launch_colsum_batch(const ColsumBatch& c, cudaStream_t s);
+int gru_kernels_init();
 int launch_gru_fwd(const GruFwdArgs& a, cudaStream_t s);
 int launch_gru_bwd(const GruBwdArgs& a, cudaStream_t s);
