@@ -12,10 +12,43 @@
 //   wgrad           : D[n][c]    += sum_pixel d_pre[pixel][n] * halo[pixel + tap][c]      M=64, N=64, K=pixels
 //                     (MN-major operands, SWIZZLE_128B_BASE32B), 3 taps (one dy) per CTA, accumulated in TMEM over
 //                     all tiles of the persistent CTA
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "cnn.cuh"
 #include "tc.cuh"
 
 namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+
+// 4-D view [B][T_l][F][64] of a channels-last activation; box = [1][rows][pitch][32 channels] lands in shared memory as
+// rows * pitch consecutive 128-byte rows in the tensor core's swizzled operand layout; out-of-range frames / mel bins
+// (the zero padding of the convolution, tile tails) are zero-filled by the TMA unit.
+int make_act_map(CUtensorMap* map, const float* base, int B, int T_l, int F, int box_rows, int pitch, CUtensorMapSwizzle swz) {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)F, (cuuint64_t)T_l, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {64 * sizeof(float), (cuuint64_t)F * 64 * sizeof(float), (cuuint64_t)T_l * F * 64 * sizeof(float)};
+    const cuuint32_t box[4] = {32, (cuuint32_t)pitch, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { dcase_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DCASE_ERR_CUDA; }
+    return DCASE_OK;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            tc::smem_u32(dst_smem)),
+        "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
 
 constexpr int kTile = 128;
 constexpr int kHaloRows = 192;                    // >= 18 * 10 + 2, multiple of 8
@@ -191,6 +224,130 @@ conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const flo
     if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad, warp-specialised:  warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+// grid = (CTAs, 2): blockIdx.y selects 32 of the 64 output channels, so the CTA's weight image is 72 KB and THREE
+// 45 KB halo stages fit beside it: loads, MMAs and epilogues of consecutive tiles overlap (ring of full / empty
+// mbarriers, two TMEM accumulators).  The 18 x PITCH halo of a tile is two TMA boxes (one per 32-channel block).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStages = 3;
+constexpr int kStageBytes = 2 * kHaloBlk;              // 48 KB: 2 blocks x 192 rows x 128 B (180 rows written)
+constexpr int kWHalfBytes = 9 * 2 * 4096;              // [9 taps][2 k-blocks][32 rows][128 B]
+constexpr int kConv2SmemBytes = kWHalfBytes + kStages * kStageBytes + 128 + 16 * 8 + 16;
+constexpr int kConv2Threads = 192;
+
+template <int PITCH>
+__global__ void __launch_bounds__(kConv2Threads, 1)
+conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map, int B, int T_l, int F, const float* __restrict__ w_img,
+                   const float* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* Wi = smem;                               // 72 KB
+    unsigned char* halo = smem + kWHalfBytes;               // kStages x 48 KB (1024-B aligned: 73728 = 72 * 1024)
+    float* bias_s = reinterpret_cast<float*>(halo + kStages * kStageBytes);      // [32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 32);
+    uint64_t* full = bars;                                  // [kStages]  TMA -> MMA
+    uint64_t* empty = bars + kStages;                       // [kStages]  MMA done -> TMA
+    uint64_t* acc_full = bars + 2 * kStages;                // [2]        MMA done -> epilogue
+    uint64_t* acc_empty = bars + 2 * kStages + 2;           // [2]        epilogue drained -> MMA
+    uint64_t* w_bar = bars + 2 * kStages + 4;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 16);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler: role branches stay uniform
+    const int nh = blockIdx.y;
+    constexpr int halves = PITCH == 10 ? 2 : 1;
+    const int tblocks = (T_l + 15) / 16;
+    const int n_tiles = B * tblocks * halves;
+    if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+        tc::mbar_init(w_bar, 1);
+        tc::fence_mbar_init();
+    }
+    if (tid < 32) bias_s[tid] = bias ? __ldg(bias + 32 * nh + tid) : 0.f;
+    if (warp == 1) tc::tmem_alloc(tmem_base_s, 64);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // weights of this half: rows 32 nh .. 32 nh + 31 of every [tap][k-block] image block (4 KB each)
+            mbar_expect_tx(w_bar, kWHalfBytes);
+            for (int i = 0; i < 18; ++i)
+                bulk_g2s(Wi + i * 4096, reinterpret_cast<const unsigned char*>(w_img) + i * 8192 + nh * 4096, 4096, w_bar);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int st = it % kStages;
+                if (it >= kStages) tc::mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+                const TileGeom g = decode_tile(tile, halves, tblocks);
+                mbar_expect_tx(&full[st], 2 * 18 * PITCH * 128);
+                unsigned char* dst = halo + st * kStageBytes;
+                tma_load_4d(dst, &in_map, 0, g.f0 - 1, g.t0 - 1, g.b, &full[st]);
+                tma_load_4d(dst + kHaloBlk, &in_map, 32, g.f0 - 1, g.t0 - 1, g.b, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        // all 32 lanes run the loop with warp-uniform values; one lane is elected per MMA / commit (tc.cuh)
+        tc::mbar_wait(w_bar, 0);
+        constexpr uint32_t idesc = tc::idesc_tf32(128, 32, 0, 0);
+        const uint32_t w_a = tc::smem_u32(Wi), h_a = tc::smem_u32(halo);
+        const uint32_t a_hi = tc::desc_hi(PITCH * 128, 2), b_hi = tc::desc_hi(1024, 2);
+        const uint32_t b_lo0 = tc::desc_lo(w_a, 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int st = it % kStages, ac = it & 1;
+            tc::mbar_wait(&full[st], (it / kStages) & 1);
+            if (it >= 2) tc::mbar_wait(&acc_empty[ac], ((it >> 1) - 1) & 1);
+            tc::fence_after_sync();
+            const uint32_t d = tmem + ac * 32;
+            const uint32_t a_lo0 = tc::desc_lo(h_a + st * kStageBytes, 16);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    tc::umma_tf32_elect(d, a_lo0 + ((((1 + dy) * PITCH + 1 + dx) * 128 + (k >> 2) * kHaloBlk + (k & 3) * 32) >> 4), a_hi,
+                                        b_lo0 + ((tap * 8192 + (k >> 2) * 4096 + (k & 3) * 32) >> 4), b_hi, idesc,
+                                        (tap > 0 || k > 0) ? 1u : 0u);
+            }
+            tc::umma_commit_elect(&empty[st]);       // halo stage free once these MMAs have read it
+            tc::umma_commit_elect(&acc_full[ac]);
+        }
+    } else {
+        const int wq = warp & 3;                   // TMEM lane quadrant of this warp
+        const int row = 32 * wq + lane, ti = row >> 3, j = row & 7;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int ac = it & 1;
+            const TileGeom g = decode_tile(tile, halves, tblocks);
+            tc::mbar_wait(&acc_full[ac], (it >> 1) & 1);
+            tc::fence_after_sync();
+            float acc[32];
+            const uint32_t ta = tmem + ac * 32 + ((uint32_t)(wq * 32) << 16);
+            tc::tmem_ld16(ta, acc);
+            tc::tmem_ld16(ta + 16, acc + 16);
+            tc::tmem_ld_wait();
+            tc::fence_before_sync();
+            mbar_arrive(&acc_empty[ac]);
+            const int t = g.t0 + ti, f = g.f0 + j;
+            if (t < T_l && f < F) {
+                float4* dst = reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64 + 32 * nh);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 4 * c4);
+                    dst[c4] = make_float4(acc[4 * c4] + b4.x, acc[4 * c4 + 1] + b4.y, acc[4 * c4 + 2] + b4.z, acc[4 * c4 + 3] + b4.w);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 64);
+}
+
 // per-channel sum and sum of squares of a [n_pix][64] tensor (BatchNorm batch statistics, fp64 accumulation)
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float* __restrict__ y, long long n_pix, double* __restrict__ stats) {
@@ -302,6 +459,8 @@ conv_wgrad_tc_kernel(const float* __restrict__ d_pre, const float* __restrict__ 
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+#define DCASE_TRY_RC(expr) do { int rc__ = (expr); if (rc__ != DCASE_OK) return rc__; } while (0)
+
 int grid_for(int n_tiles, int num_sms, int per_sm) {
     const int g = num_sms * per_sm;
     return n_tiles < g ? n_tiles : g;
@@ -310,6 +469,15 @@ int grid_for(int n_tiles, int num_sms, int per_sm) {
 }  // namespace
 
 int conv_tc_kernels_init() {
+    if (!g_encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DCASE_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { dcase_set_error("cuTensorMapEncodeTiled is not available"); return DCASE_ERR_STATE; }
+        g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBytes));
     return DCASE_OK;
@@ -327,8 +495,13 @@ int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, c
     DCASE_PROF(bias ? (F == 16 ? "conv3x3_fwd_l1" : "conv3x3_fwd_l2") : (F == 16 ? "conv3x3_dgrad_l1" : "conv3x3_dgrad_l2"), s);
     DCASE_REQUIRE(F == 16 || F == 4, "conv3x3 is built for the 16- and 4-bin layers of cfg.crnn_kwargs");
     const int n_tiles = B * ((T_l + 15) / 16) * (F == 16 ? 2 : 1);
-    const int grid = grid_for(n_tiles, num_sms, 1);
-    conv3x3_tc_kernel<<<grid, kTile, kConvSmemBytes, s>>>(in, B, T_l, F, w_img, bias, out);
+    int gx = num_sms / 2;
+    if (gx > n_tiles) gx = n_tiles;
+    CUtensorMap in_map;
+    const int pitch = F == 16 ? 10 : 8;
+    DCASE_TRY_RC(make_act_map(&in_map, in, B, T_l, F, 18, pitch, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (F == 16) conv3x3_tma_kernel<10><<<dim3(gx, 2), kConv2Threads, kConv2SmemBytes, s>>>(in_map, B, T_l, F, w_img, bias, out);
+    else conv3x3_tma_kernel<8><<<dim3(gx, 2), kConv2Threads, kConv2SmemBytes, s>>>(in_map, B, T_l, F, w_img, bias, out);
     DCASE_LAUNCH_CHECK();
     if (stats) {
         DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
