@@ -68,6 +68,7 @@ SIGNATURES = {
     "dcase_sizeof_mt_args": (c_sz, []),
     "dcase_sizeof_step_scalars": (c_sz, []),
     "dcase_selftest_umma_shift": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "dcase_bench_umma": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
 }
 
 _lib = None

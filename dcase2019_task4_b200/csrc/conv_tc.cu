@@ -46,6 +46,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* m
         "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
@@ -225,48 +233,51 @@ conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const flo
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward / dgrad, warp-specialised:  warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
-// grid = (CTAs, 2): blockIdx.y selects 32 of the 64 output channels, so the CTA's weight image is 72 KB and THREE
-// 45 KB halo stages fit beside it: loads, MMAs and epilogues of consecutive tiles overlap (ring of full / empty
-// mbarriers, two TMEM accumulators).  The 18 x PITCH halo of a tile is two TMA boxes (one per 32-channel block).
+// forward / dgrad, warp-specialised:  warp 0 = TMA producer, warps 1 and 6 = MMA issuers (even / odd tiles: one warp
+// sustains ~7 uniform-datapath instructions = ~105 cycles per MMA, two keep the tensor core at its 48-cycle
+// shared-memory operand floor for M = 128, N = 64 tf32), warps 2..5 = epilogue.
+// The 144 KB weight image (all 64 output channels: N = 64 halves the shared-memory operand traffic per MAC
+// compared with two N = 32 passes) leaves room for THREE 24 KB staging units, each one 32-channel block of the
+// 18 x PITCH input halo of a tile (one TMA box).  The MMA loop runs k-block outer, so a unit is released after 36
+// MMAs and refilled with the next tile's block while the other block is being multiplied: loads, MMAs and
+// epilogues of consecutive tiles overlap (full / empty mbarrier ring, two TMEM accumulators).
 // ---------------------------------------------------------------------------------------------
-constexpr int kStages = 3;
-constexpr int kStageBytes = 2 * kHaloBlk;              // 48 KB: 2 blocks x 192 rows x 128 B (180 rows written)
-constexpr int kWHalfBytes = 9 * 2 * 4096;              // [9 taps][2 k-blocks][32 rows][128 B]
-constexpr int kConv2SmemBytes = kWHalfBytes + kStages * kStageBytes + 128 + 16 * 8 + 16;
-constexpr int kConv2Threads = 192;
+constexpr int kUnits = 3;
+constexpr int kConv2SmemBytes = kWImgBytes + kUnits * kHaloBlk + 256 + 18 * 8 + 4 * 2048;
+constexpr int kConv2Threads = 224;
 
 template <int PITCH>
 __global__ void __launch_bounds__(kConv2Threads, 1)
-conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map, int B, int T_l, int F, const float* __restrict__ w_img,
+conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_constant__ CUtensorMap in_map2, int B, int T_l, int F,
+                   const float* __restrict__ w_img,
                    const float* __restrict__ bias, float* __restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* Wi = smem;                               // 72 KB
-    unsigned char* halo = smem + kWHalfBytes;               // kStages x 48 KB (1024-B aligned: 73728 = 72 * 1024)
-    float* bias_s = reinterpret_cast<float*>(halo + kStages * kStageBytes);      // [32]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 32);
-    uint64_t* full = bars;                                  // [kStages]  TMA -> MMA
-    uint64_t* empty = bars + kStages;                       // [kStages]  MMA done -> TMA
-    uint64_t* acc_full = bars + 2 * kStages;                // [2]        MMA done -> epilogue
-    uint64_t* acc_empty = bars + 2 * kStages + 2;           // [2]        epilogue drained -> MMA
-    uint64_t* w_bar = bars + 2 * kStages + 4;
+    unsigned char* Wi = smem;                               // 144 KB
+    unsigned char* units = smem + kWImgBytes;               // kUnits x 24 KB (1024-B aligned)
+    float* bias_s = reinterpret_cast<float*>(units + kUnits * kHaloBlk);      // [64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 64);
+    uint64_t* full = bars;                                  // [kUnits]   TMA -> MMA
+    uint64_t* empty = bars + kUnits;                        // [kUnits]   MMA done -> TMA
+    uint64_t* acc_full = bars + 2 * kUnits;                 // [2]        MMA done -> epilogue
+    uint64_t* acc_empty = bars + 2 * kUnits + 2;            // [2]        epilogue drained -> MMA
+    uint64_t* w_bar = bars + 2 * kUnits + 4;
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 16);
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(bars + 18);    // 4 warps x 2 KB epilogue staging (128-B aligned)
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler: role branches stay uniform
-    const int nh = blockIdx.y;
     constexpr int halves = PITCH == 10 ? 2 : 1;
     const int tblocks = (T_l + 15) / 16;
     const int n_tiles = B * tblocks * halves;
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
 
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kUnits; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
         tc::mbar_init(w_bar, 1);
         tc::fence_mbar_init();
     }
-    if (tid < 32) bias_s[tid] = bias ? __ldg(bias + 32 * nh + tid) : 0.f;
-    if (warp == 1) tc::tmem_alloc(tmem_base_s, 64);
+    if (tid < 64) bias_s[tid] = bias ? __ldg(bias + tid) : 0.f;
+    if (warp == 1) tc::tmem_alloc(tmem_base_s, 128);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -274,78 +285,141 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map, int B, int T_l, i
 
     if (warp == 0) {
         if (lane == 0) {
-            // weights of this half: rows 32 nh .. 32 nh + 31 of every [tap][k-block] image block (4 KB each)
-            mbar_expect_tx(w_bar, kWHalfBytes);
-            for (int i = 0; i < 18; ++i)
-                bulk_g2s(Wi + i * 4096, reinterpret_cast<const unsigned char*>(w_img) + i * 8192 + nh * 4096, 4096, w_bar);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int st = it % kStages;
-                if (it >= kStages) tc::mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+            mbar_expect_tx(w_bar, kWImgBytes);
+            for (int i = 0; i < 9; ++i)
+                bulk_g2s(Wi + i * 16384, reinterpret_cast<const unsigned char*>(w_img) + i * 16384, 16384, w_bar);
+            int u = 0, n = 0;                       // staging unit of the next box and how often it has been used
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const TileGeom g = decode_tile(tile, halves, tblocks);
-                mbar_expect_tx(&full[st], 2 * 18 * PITCH * 128);
-                unsigned char* dst = halo + st * kStageBytes;
-                tma_load_4d(dst, &in_map, 0, g.f0 - 1, g.t0 - 1, g.b, &full[st]);
-                tma_load_4d(dst + kHaloBlk, &in_map, 32, g.f0 - 1, g.t0 - 1, g.b, &full[st]);
-            }
-        }
-    } else if (warp == 1) {
-        // all 32 lanes run the loop with warp-uniform values; one lane is elected per MMA / commit (tc.cuh)
-        tc::mbar_wait(w_bar, 0);
-        constexpr uint32_t idesc = tc::idesc_tf32(128, 32, 0, 0);
-        const uint32_t w_a = tc::smem_u32(Wi), h_a = tc::smem_u32(halo);
-        const uint32_t a_hi = tc::desc_hi(PITCH * 128, 2), b_hi = tc::desc_hi(1024, 2);
-        const uint32_t b_lo0 = tc::desc_lo(w_a, 16);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int st = it % kStages, ac = it & 1;
-            tc::mbar_wait(&full[st], (it / kStages) & 1);
-            if (it >= 2) tc::mbar_wait(&acc_empty[ac], ((it >> 1) - 1) & 1);
-            tc::fence_after_sync();
-            const uint32_t d = tmem + ac * 32;
-            const uint32_t a_lo0 = tc::desc_lo(h_a + st * kStageBytes, 16);
+#pragma unroll 1
+                for (int kb = 0; kb < 2; ++kb) {
+                    if (n >= 1) tc::mbar_wait(&empty[u], (n - 1) & 1);
+                    // the 18 halo rows arrive as five boxes (4 + 4 + 4 + 4 + 2 frames, 1024-byte aligned pieces): the TMA
+                    // unit works on boxes concurrently but walks the 128-byte rows of one box slowly (~30 ns per row)
+                    mbar_expect_tx(&full[u], 18 * PITCH * 128);
+                    unsigned char* dst = units + u * kHaloBlk;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    tc::umma_tf32_elect(d, a_lo0 + ((((1 + dy) * PITCH + 1 + dx) * 128 + (k >> 2) * kHaloBlk + (k & 3) * 32) >> 4), a_hi,
-                                        b_lo0 + ((tap * 8192 + (k >> 2) * 4096 + (k & 3) * 32) >> 4), b_hi, idesc,
-                                        (tap > 0 || k > 0) ? 1u : 0u);
-            }
-            tc::umma_commit_elect(&empty[st]);       // halo stage free once these MMAs have read it
-            tc::umma_commit_elect(&acc_full[ac]);
-        }
-    } else {
-        const int wq = warp & 3;                   // TMEM lane quadrant of this warp
-        const int row = 32 * wq + lane, ti = row >> 3, j = row & 7;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int ac = it & 1;
-            const TileGeom g = decode_tile(tile, halves, tblocks);
-            tc::mbar_wait(&acc_full[ac], (it >> 1) & 1);
-            tc::fence_after_sync();
-            float acc[32];
-            const uint32_t ta = tmem + ac * 32 + ((uint32_t)(wq * 32) << 16);
-            tc::tmem_ld16(ta, acc);
-            tc::tmem_ld16(ta + 16, acc + 16);
-            tc::tmem_ld_wait();
-            tc::fence_before_sync();
-            mbar_arrive(&acc_empty[ac]);
-            const int t = g.t0 + ti, f = g.f0 + j;
-            if (t < T_l && f < F) {
-                float4* dst = reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64 + 32 * nh);
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 4 * c4);
-                    dst[c4] = make_float4(acc[4 * c4] + b4.x, acc[4 * c4 + 1] + b4.y, acc[4 * c4 + 2] + b4.z, acc[4 * c4 + 3] + b4.w);
+                    for (int q = 0; q < 4; ++q)
+                        tma_load_4d(dst + q * 4 * PITCH * 128, &in_map4, 32 * kb, g.f0 - 1, g.t0 - 1 + 4 * q, g.b, &full[u]);
+                    tma_load_4d(dst + 16 * PITCH * 128, &in_map2, 32 * kb, g.f0 - 1, g.t0 + 15, g.b, &full[u]);
+                    if (++u == kUnits) { u = 0; ++n; }
                 }
             }
         }
+    } else if (warp == 1 || warp == 6) {
+        // all 32 lanes run the loop with warp-uniform values; one lane is elected per MMA / commit (tc.cuh).
+        // Issuer w takes the tiles it = w, w + 2, ... (accumulator w); unit j = 2 it + kb of the producer's sequence.
+        const int w = warp == 1 ? 0 : 1;
+        tc::mbar_wait(w_bar, 0);
+        constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+        const uint32_t a_hi = tc::desc_hi(PITCH * 128, 2), b_hi = tc::desc_hi(1024, 2);
+        const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wi), 16);
+        const uint32_t u_lo0 = tc::desc_lo(tc::smem_u32(units), 16);
+        const uint32_t d = tmem + w * 64;
+        int use = 0;                                   // how often this issuer's accumulator has been used
+#ifdef DCASE_CONV_TIMING
+        long long t_acc = 0, t_full = 0, t_issue = 0, tt;
+        const long long t_begin = clock64();
+#define TICK() tt = clock64()
+#define TOCK(acc) acc += clock64() - tt
+#else
+#define TICK()
+#define TOCK(acc)
+#endif
+        for (int it = w; blockIdx.x + (long long)it * gridDim.x < n_tiles; it += 2, ++use) {
+            TICK();
+            if (use >= 1) tc::mbar_wait(&acc_empty[w], (use - 1) & 1);
+            TOCK(t_acc);
+#pragma unroll 1
+            for (int kb = 0; kb < 2; ++kb) {
+                const int j = 2 * it + kb, u = j % kUnits, n = j / kUnits;
+                TICK();
+                tc::mbar_wait(&full[u], n & 1);
+                TOCK(t_full);
+                TICK();
+                tc::fence_after_sync();
+                const uint32_t a_lo0 = u_lo0 + u * (kHaloBlk >> 4);
+                const uint32_t b_lo1 = b_lo0 + kb * (8192 >> 4);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc::umma_tf32_elect(d, a_lo0 + ((((1 + dy) * PITCH + 1 + dx) * 128 + k4 * 32) >> 4), a_hi,
+                                            b_lo1 + ((tap * 16384 + k4 * 32) >> 4), b_hi, idesc, (kb > 0 || tap > 0 || k4 > 0) ? 1u : 0u);
+                }
+                tc::umma_commit_elect(&empty[u]);        // unit free once these MMAs have read it
+                TOCK(t_issue);
+            }
+            tc::umma_commit_elect(&acc_full[w]);
+        }
+#ifdef DCASE_CONV_TIMING
+        if (blockIdx.x == 3 && lane == 0)
+            printf("mma warp %d: total %lld  wait acc_empty %lld  wait full %lld  issue %lld  tiles %d\n", w, clock64() - t_begin, t_acc,
+                   t_full, t_issue, use);
+#endif
+    } else {
+        const int wq = warp & 3;                   // TMEM lane quadrant of this warp
+        const uint32_t stage_a = tc::smem_u32(stage_base) + (uint32_t)wq * 2048u;
+        int it = 0;
+#ifdef DCASE_CONV_TIMING
+        long long t_wait = 0, t_ld = 0, t_st = 0, tt;
+        const long long t_begin = clock64();
+#endif
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int ac = it & 1;
+            const TileGeom g = decode_tile(tile, halves, tblocks);
+            TICK();
+            tc::mbar_wait(&acc_full[ac], (it >> 1) & 1);
+            TOCK(t_wait);
+            TICK();
+            tc::fence_after_sync();
+            float acc[64];
+            tc::tmem_ld_row64(tmem, wq, ac * 64, acc);
+            tc::fence_before_sync();
+            mbar_arrive(&acc_empty[ac]);
+            TOCK(t_ld);
+            TICK();
+            // A thread owns one pixel row (256 B), so direct stores would touch 32 different lines with 16 B each per
+            // instruction (measured: 4450 cycles per tile, the kernel's bottleneck).  Instead 16 rows x 128 B at a time
+            // go through a 2 KB per-warp staging tile (XOR-swizzled chunks) and leave as full 128-byte lines.
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    if ((lane >> 4) == rh) {
+                        const uint32_t rb = stage_a + (uint32_t)(lane & 15) * 128u;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 32 * ch + 4 * q);
+                            const int e = 32 * ch + 4 * q;
+                            st_shared_v4(rb + (uint32_t)((q ^ (lane & 7)) << 4), acc[e] + b4.x, acc[e + 1] + b4.y, acc[e + 2] + b4.z,
+                                         acc[e + 3] + b4.w);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int idx = lane + 32 * q, r = idx >> 3, c = idx & 7;
+                        const float4 v = ld_shared_v4(stage_a + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
+                        const int prow = 32 * wq + 16 * rh + r;                // pixel row of the tile
+                        const int t = g.t0 + (prow >> 3), f = g.f0 + (prow & 7);
+                        if (t < T_l && f < F)
+                            *reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64 + 32 * ch + 4 * c) = v;
+                    }
+                    __syncwarp();
+                }
+            }
+            TOCK(t_st);
+        }
+#ifdef DCASE_CONV_TIMING
+        if (blockIdx.x == 3 && tid == 64)
+            printf("epilogue: total %lld  wait acc_full %lld  ldtm %lld  stores %lld  tiles %d\n", clock64() - t_begin, t_wait, t_ld, t_st, it);
+#endif
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, 64);
+    if (warp == 1) tc::tmem_dealloc(tmem, 128);
 }
 
 // per-channel sum and sum of squares of a [n_pix][64] tensor (BatchNorm batch statistics, fp64 accumulation)
@@ -495,13 +569,13 @@ int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, c
     DCASE_PROF(bias ? (F == 16 ? "conv3x3_fwd_l1" : "conv3x3_fwd_l2") : (F == 16 ? "conv3x3_dgrad_l1" : "conv3x3_dgrad_l2"), s);
     DCASE_REQUIRE(F == 16 || F == 4, "conv3x3 is built for the 16- and 4-bin layers of cfg.crnn_kwargs");
     const int n_tiles = B * ((T_l + 15) / 16) * (F == 16 ? 2 : 1);
-    int gx = num_sms / 2;
-    if (gx > n_tiles) gx = n_tiles;
-    CUtensorMap in_map;
+    const int gx = n_tiles < num_sms ? n_tiles : num_sms;
+    CUtensorMap in_map4, in_map2;
     const int pitch = F == 16 ? 10 : 8;
-    DCASE_TRY_RC(make_act_map(&in_map, in, B, T_l, F, 18, pitch, CU_TENSOR_MAP_SWIZZLE_128B));
-    if (F == 16) conv3x3_tma_kernel<10><<<dim3(gx, 2), kConv2Threads, kConv2SmemBytes, s>>>(in_map, B, T_l, F, w_img, bias, out);
-    else conv3x3_tma_kernel<8><<<dim3(gx, 2), kConv2Threads, kConv2SmemBytes, s>>>(in_map, B, T_l, F, w_img, bias, out);
+    DCASE_TRY_RC(make_act_map(&in_map4, in, B, T_l, F, 4, pitch, CU_TENSOR_MAP_SWIZZLE_128B));
+    DCASE_TRY_RC(make_act_map(&in_map2, in, B, T_l, F, 2, pitch, CU_TENSOR_MAP_SWIZZLE_128B));
+    if (F == 16) conv3x3_tma_kernel<10><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out);
+    else conv3x3_tma_kernel<8><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out);
     DCASE_LAUNCH_CHECK();
     if (stats) {
         DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));

@@ -133,3 +133,86 @@ extern "C" int dcase_selftest_umma_shift(dcase_ctx* ctx, int shift, int pitch, i
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
+
+namespace {
+// Micro-benchmark: one warp per CTA issues `reps` back-to-back tcgen05.mma kind::tf32 (shape M x N x 8, both operands
+// in shared memory) and reports cycles per MMA (clock64 around issue .. completion).  Used to size the kernels:
+// small-N tf32 MMAs are bound by the tensor core's shared-memory operand fetch, not by its math rate.
+__global__ void __launch_bounds__(32)
+umma_bench_kernel(int M, int N, int a_mn, int b_mn, int reps, int a_sbo, int a_shift, int commit_every, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t tmem_base_s;
+    if (threadIdx.x == 0) tc::mbar_init(&bar2, 1);
+    for (int i = threadIdx.x; i < 128 * 1024 / 16; i += 32) reinterpret_cast<float4*>(smem)[i] = make_float4(1.f, 0.5f, 0.25f, 2.f);
+    if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::tmem_alloc(&tmem_base_s, 256);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncwarp();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t a_base = tc::smem_u32(smem), b_base = a_base + 65536;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+                           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const uint32_t a_hi = a_mn ? tc::desc_hi(512, 1) : tc::desc_hi(a_sbo, 2), b_hi = b_mn ? tc::desc_hi(512, 1) : tc::desc_hi(1024, 2);
+    const uint32_t a_lo = tc::desc_lo(a_base + a_shift, 16384), b_lo = tc::desc_lo(b_base, 16384);
+    const uint32_t a_step = a_mn ? 64 : 2, b_step = b_mn ? 64 : 2;      // next K step, in 16-byte units
+    if (commit_every < 0) {
+        // the conv3x3 issue pattern: 9 taps x 4 K steps with compile-time operand offsets, one commit per 36 MMAs
+        constexpr int PITCH = 10;
+        const long long c0 = clock64();
+        for (int r = 0; r < reps; r += 36) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    tc::umma_tf32_elect(tmem, a_lo + ((((1 + dy) * PITCH + 1 + dx) * 128 + k4 * 32) >> 4), a_hi,
+                                        b_lo + ((tap * 4096 + k4 * 32) >> 4), b_hi, idesc, (tap > 0 || k4 > 0) ? 1u : 0u);
+            }
+            tc::umma_commit_elect(&bar2);
+        }
+        tc::umma_commit_elect(&bar);
+        tc::mbar_wait(&bar, 0);
+        const long long c1 = clock64();
+        if (threadIdx.x == 0) out[blockIdx.x] = (float)(c1 - c0) / (float)reps;
+        tc::fence_before_sync();
+        __syncwarp();
+        tc::tmem_dealloc(tmem, 256);
+        return;
+    }
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            tc::umma_tf32_elect(tmem, a_lo + j * a_step, a_hi, b_lo + j * b_step, b_hi, idesc, 1u);
+        if (commit_every > 0 && (r + 4) % commit_every == 0) tc::umma_commit_elect(&bar2);    // nobody waits on bar2
+    }
+    tc::umma_commit_elect(&bar);
+    tc::mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = (float)(t1 - t0) / (float)reps;
+    tc::fence_before_sync();
+    __syncwarp();
+    tc::tmem_dealloc(tmem, 256);
+}
+}  // namespace
+
+extern "C" int dcase_bench_umma(dcase_ctx* ctx, int M, int N, int a_mn_major, int b_mn_major, int reps, int n_ctas,
+                                int a_sbo_bytes, int a_shift_bytes, int commit_every, float* cycles_per_mma, void* stream) {
+    DCASE_REQUIRE(ctx && cycles_per_mma, "null argument");
+    DCASE_REQUIRE((M == 64 || M == 128) && N >= 8 && N <= 256 && N % 8 == 0 && (M == 64 || N % 16 == 0), "illegal MMA shape");
+    DCASE_REQUIRE(reps >= 4 && reps % 4 == 0 && n_ctas >= 1, "reps must be a positive multiple of 4");
+    static bool attr_set = false;
+    if (!attr_set) {
+        DCASE_CUDA_CHECK(cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        attr_set = true;
+    }
+    DCASE_REQUIRE(a_sbo_bytes >= 1024 && a_sbo_bytes % 128 == 0 && a_shift_bytes % 128 == 0 && a_shift_bytes + 16 * a_sbo_bytes <= 49152,
+                  "A operand does not fit the 64 KB buffer");
+    umma_bench_kernel<<<n_ctas, 32, 131072, (cudaStream_t)stream>>>(M, N, a_mn_major, b_mn_major, reps, a_sbo_bytes, a_shift_bytes,
+                                                                   commit_every, cycles_per_mma);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}

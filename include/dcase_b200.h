@@ -65,6 +65,14 @@ int dcase_selftest_umma(dcase_ctx* ctx, int mode, const float* A, const float* B
  * encoding the kernels use (descriptor base_offset = 0: the swizzle follows absolute shared-memory addresses). */
 int dcase_selftest_umma_shift(dcase_ctx* ctx, int shift, int pitch, int base_mode, const float* A, const float* B,
                               float* D, void* stream);
+/* Micro-benchmark of the tensor core issue path: n_ctas CTAs (one warp each) issue `reps` back-to-back
+ * tcgen05.mma kind::tf32 of shape M x N x 8 with both operands in shared memory; cycles_per_mma[n_ctas] (device)
+ * receives the measured SM cycles per MMA (a_sbo / a_shift reproduce the strided, shifted halo operand of the convs).  tools/umma_bench.py prints the table DESIGN.md quotes. */
+int dcase_bench_umma(dcase_ctx* ctx, int M, int N, int a_mn_major, int b_mn_major, int reps, int n_ctas,
+                     int a_sbo_bytes /* K-major A: byte pitch of the 8-row groups (1024 = dense) */,
+                     int a_shift_bytes /* K-major A: start offset into the buffer (multiple of 128) */,
+                     int commit_every /* > 0: a tcgen05.commit after every commit_every MMAs (multiple of 4) */,
+                     float* cycles_per_mma, void* stream);
 
 /* Per-step scalars in device memory (so a captured CUDA graph replays with new values).
  * Layout must match DcaseStepScalars in csrc/common.cuh. */
