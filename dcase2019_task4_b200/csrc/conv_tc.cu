@@ -444,6 +444,117 @@ bn_stats_kernel(const float* __restrict__ y, long long n_pix, double* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// weight gradient, warp-specialised:  warp 0 = TMA producer, warps 1..3 = MMA issuers (one tap row dy each),
+// warps 4..7 = final read-out.  grid = (CTAs, 2): blockIdx.y selects 32 of the 64 INPUT channels c, so the nine
+// [64 n][32 c] accumulators (288 TMEM columns) of all taps stay resident over the CTA's whole tile stream and every
+// tile is fetched once per half: d_pre tile (32 KB, two TMA boxes) + one 32-channel halo block (one box), both
+// landing directly in the MN-major (SWIZZLE_128B_ATOM_32B) operand layout; 4-stage full / empty ring.
+//   D_tap[n][c] += sum over the 8 mel slots of frame row r:  d_pre[(r, j)][n] * in[(r + dy, j + dx)][c]
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgStages = 4;
+constexpr int kWgStageBytes = 32768 + kHaloBlk;          // d_pre 2 x 16 KB | halo block 24 KB (18 * PITCH rows written)
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 16 * 8 + 16;
+constexpr int kWgThreads = 256;
+
+template <int PITCH>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap dpre_map, const __grid_constant__ CUtensorMap in_map, int B, int T_l,
+                      int F, float* __restrict__ g_w) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+    uint64_t* full = bars;                     // [kWgStages]  TMA -> MMA
+    uint64_t* empty = bars + kWgStages;        // [kWgStages]  3 issuers done -> TMA
+    uint64_t* done = bars + 2 * kWgStages;     // all MMAs of the CTA complete -> read-out
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 16);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int ch = blockIdx.y;
+    constexpr int halves = PITCH == 10 ? 2 : 1;
+    const int tblocks = (T_l + 15) / 16;
+    const int n_tiles = B * tblocks * halves;
+    if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
+
+    // rows never written by the TMA boxes (halo rows >= 18 * PITCH) must be finite: they meet zero d_pre rows
+    for (int i = tid; i < kWgStages * kWgStageBytes / 16; i += kWgThreads) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        for (int i = 0; i < kWgStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 3); }
+        tc::mbar_init(done, 3);
+        tc::fence_mbar_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_base_s, 512);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_base_s;
+    const bool any = (int)blockIdx.x < n_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int st = it % kWgStages, n = it / kWgStages;
+                if (n >= 1) tc::mbar_wait(&empty[st], (n - 1) & 1);
+                const TileGeom g = decode_tile(tile, halves, tblocks);
+                unsigned char* dst = smem + st * kWgStageBytes;
+                mbar_expect_tx(&full[st], 32768 + 18 * PITCH * 128);
+                tma_load_4d(dst, &dpre_map, 0, g.f0, g.t0, g.b, &full[st]);
+                tma_load_4d(dst + 16384, &dpre_map, 32, g.f0, g.t0, g.b, &full[st]);
+                tma_load_4d(dst + 32768, &in_map, 32 * ch, g.f0 - 1, g.t0 - 1, g.b, &full[st]);
+            }
+        }
+    } else if (warp <= 3) {
+        // issuer of tap row dy = warp - 2: 3 taps x 16 K steps per tile; all lanes run the loop, one is elected per MMA
+        const int dyi = warp - 1;                              // 0, 1, 2
+        constexpr uint32_t idesc = tc::idesc_tf32(64, 32, 1, 1);
+        const uint32_t hi = tc::desc_hi(512, 1);
+        const uint32_t s_lo0 = tc::desc_lo(tc::smem_u32(smem), 16384);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int st = it % kWgStages;
+            tc::mbar_wait(&full[st], (it / kWgStages) & 1);
+            tc::fence_after_sync();
+            const uint32_t a_lo = s_lo0 + st * (kWgStageBytes >> 4);
+            const uint32_t b_lo = a_lo + ((32768 + dyi * PITCH * 128) >> 4);
+            const uint32_t acc1 = it > 0 ? 1u : 0u;
+#pragma unroll
+            for (int dxi = 0; dxi < 3; ++dxi) {
+                const uint32_t d = tmem + (dyi * 3 + dxi) * 32;
+#pragma unroll
+                for (int r = 0; r < 16; ++r)               // K step = the 8 mel slots of frame row r of the tile
+                    tc::umma_tf32_elect(d, a_lo + r * (1024 >> 4), hi, b_lo + ((r * PITCH + dxi) * 128 >> 4), hi, idesc,
+                                        r > 0 ? 1u : acc1);
+            }
+            tc::umma_commit_elect(&empty[st]);
+        }
+        tc::umma_commit_elect(done);
+    } else if (any) {
+        const int wq = warp & 3;
+        tc::mbar_wait(done, 0);
+        tc::fence_after_sync();
+        const int n = 16 * wq + lane;                       // M = 64 accumulators: row m in TMEM lane 32*(m/16) + m%16
+        const bool own = lane < 16;
+        const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16);
+        float v[16];
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                tc::tmem_ld16(tbase + tap * 32 + c0, v);
+                tc::tmem_ld_wait();
+                if (own) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) atomicAdd(g_w + n * 576 + (32 * ch + c0 + c) * 9 + tap, v[c]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
 // grid = (chunks, 3): blockIdx.y selects dy; TMEM holds the three [64 n][64 c] accumulators of dx = -1, 0, +1.
 __global__ void __launch_bounds__(kTile, 2)
 conv_wgrad_tc_kernel(const float* __restrict__ d_pre, const float* __restrict__ in, int B, int T_l, int F,
@@ -550,6 +661,8 @@ int conv_tc_kernels_init() {
         if (!fn || qres != cudaDriverEntryPointSuccess) { dcase_set_error("cuTensorMapEncodeTiled is not available"); return DCASE_ERR_STATE; }
         g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
     }
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
@@ -593,10 +706,15 @@ int launch_conv_wgrad(const float* d_pre, const float* in, int B, int T_l, int F
     DCASE_PROF(F == 16 ? "conv3x3_wgrad_l1" : "conv3x3_wgrad_l2", s);
     DCASE_REQUIRE(F == 16 || F == 4, "conv wgrad is built for the 16- and 4-bin layers of cfg.crnn_kwargs");
     const int n_tiles = B * ((T_l + 15) / 16) * (F == 16 ? 2 : 1);
-    int chunks = (2 * num_sms) / 3;
-    if (chunks > n_tiles) chunks = n_tiles;
-    if (chunks < 1) chunks = 1;
-    conv_wgrad_tc_kernel<<<dim3(chunks, 3), kTile, kWgradSmemBytes, s>>>(d_pre, in, B, T_l, F, g_w);
+    int gx = num_sms / 2;
+    if (gx > n_tiles) gx = n_tiles;
+    if (gx < 1) gx = 1;
+    const int pitch = F == 16 ? 10 : 8;
+    CUtensorMap dpre_map, in_map;
+    DCASE_TRY_RC(make_act_map(&dpre_map, d_pre, B, T_l, F, 16, 8, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    DCASE_TRY_RC(make_act_map(&in_map, in, B, T_l, F, 18, pitch, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    if (F == 16) conv_wgrad_tma_kernel<10><<<dim3(gx, 2), kWgThreads, kWgSmemBytes, s>>>(dpre_map, in_map, B, T_l, F, g_w);
+    else conv_wgrad_tma_kernel<8><<<dim3(gx, 2), kWgThreads, kWgSmemBytes, s>>>(dpre_map, in_map, B, T_l, F, g_w);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
