@@ -233,6 +233,7 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     if (rc == DCASE_OK) rc = cnn_kernels_init();
     if (rc == DCASE_OK) rc = cnn0_kernels_init();
     if (rc == DCASE_OK) rc = conv_tc_kernels_init();
+    if (rc == DCASE_OK) rc = glu_tma_kernels_init();
     if (rc == DCASE_OK) rc = head_kernels_init();
     if (rc == DCASE_OK) rc = gru_kernels_init();
     if (rc != DCASE_OK) { delete ctx; return rc; }

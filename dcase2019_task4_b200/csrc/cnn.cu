@@ -690,7 +690,6 @@ constexpr size_t kGluBwdSmem = kGluBwdSmemBytes;
 }  // namespace
 
 int cnn_kernels_init() {
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluFwdSmem));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(glu_pool_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGluBwdSmem));
     return DCASE_OK;
 }
@@ -718,17 +717,6 @@ int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w,
 static int grid_for(long long n_tiles, int num_sms, int per_sm) {
     long long g = (long long)num_sms * per_sm;
     return (int)(n_tiles < g ? n_tiles : g);
-}
-
-int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
-                        const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
-    DCASE_PROF(F == 16 ? "glu_pool_fwd_l1" : "glu_pool_fwd_l2", s);
-    GluArgs a{};
-    a.src = ypre; a.n_pix = n_pix; a.F = F; a.aff = bn; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
-    const long long n_tiles = (n_pix + kTile - 1) / kTile;
-    glu_pool_fwd_kernel<false><<<grid_for(n_tiles, num_sms, 4), kThreads, kGluFwdSmem, s>>>(a);
-    DCASE_LAUNCH_CHECK();
-    return DCASE_OK;
 }
 
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta, float* running,

@@ -60,4 +60,5 @@ int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const fl
 int launch_conv_wgrad(const float* d_pre, const float* in, int B, int T_l, int F, float* g_w, int num_sms,
                       cudaStream_t s);
 int cnn_kernels_init();
+int glu_tma_kernels_init();
 int conv_tc_kernels_init();

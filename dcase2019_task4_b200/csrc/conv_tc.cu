@@ -9,13 +9,13 @@
 //
 //   forward / dgrad : D[pixel][n] = sum_tap sum_c halo[pixel + tap][c] * W[tap][n][c]     M=128, N=64, K=9*64
 //                     the 144 KB weight image arrives by ONE bulk-async copy group (cp.async.bulk, mbarrier tx)
-//   wgrad           : D[n][c]    += sum_pixel d_pre[pixel][n] * halo[pixel + tap][c]      M=64, N=64, K=pixels
-//                     (MN-major operands, SWIZZLE_128B_BASE32B), 3 taps (one dy) per CTA, accumulated in TMEM over
-//                     all tiles of the persistent CTA
-#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
-
+//   wgrad           : D[n][c]    += sum_pixel d_pre[pixel][n] * halo[pixel + tap][c]      M=64, N=32, K=pixels
+//                     (MN-major operands, SWIZZLE_128B_BASE32B), all 9 taps of one input-channel half per CTA,
+//                     accumulated in TMEM over all tiles of the persistent CTA
+// Both are warp-specialised (TMA producer / MMA issuer warps / epilogue warps) around mbarrier rings.
 #include "cnn.cuh"
 #include "tc.cuh"
+#include "tma.cuh"            // CUtensorMap helpers (the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace {
 
@@ -24,56 +24,49 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
 
-// 4-D view [B][T_l][F][64] of a channels-last activation; box = [1][rows][pitch][32 channels] lands in shared memory as
-// rows * pitch consecutive 128-byte rows in the tensor core's swizzled operand layout; out-of-range frames / mel bins
-// (the zero padding of the convolution, tile tails) are zero-filled by the TMA unit.
-int make_act_map(CUtensorMap* map, const float* base, int B, int T_l, int F, int box_rows, int pitch, CUtensorMapSwizzle swz) {
-    const cuuint64_t dims[4] = {64, (cuuint64_t)F, (cuuint64_t)T_l, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {64 * sizeof(float), (cuuint64_t)F * 64 * sizeof(float), (cuuint64_t)T_l * F * 64 * sizeof(float)};
-    const cuuint32_t box[4] = {32, (cuuint32_t)pitch, (cuuint32_t)box_rows, 1};
+int encode_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+               CUtensorMapSwizzle swz) {
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dcase_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DCASE_ERR_CUDA; }
     return DCASE_OK;
 }
 
-__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-            tc::smem_u32(dst_smem)),
-        "l"(map), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
+}  // namespace
+
+int dcase_tma_init() {
+    if (!g_encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        DCASE_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { dcase_set_error("cuTensorMapEncodeTiled is not available"); return DCASE_ERR_STATE; }
+        g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    return DCASE_OK;
 }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, float x, float y, float z, float w) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+
+int make_act_map(CUtensorMap* map, const float* base, int B, int T_l, int F, int box_rows, int pitch, CUtensorMapSwizzle swz) {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)F, (cuuint64_t)T_l, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {64 * sizeof(float), (cuuint64_t)F * 64 * sizeof(float), (cuuint64_t)T_l * F * 64 * sizeof(float)};
+    const cuuint32_t box[4] = {32, (cuuint32_t)pitch, (cuuint32_t)box_rows, 1};
+    return encode_map(map, base, 4, dims, strides, box, swz);
 }
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
+
+int make_rows_map(CUtensorMap* map, const float* base, long long n_rows, int box_rows, CUtensorMapSwizzle swz) {
+    const cuuint64_t dims[2] = {64, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {64 * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    return encode_map(map, base, 2, dims, strides, box, swz);
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
+
+namespace {
 
 constexpr int kTile = 128;
 constexpr int kHaloRows = 192;                    // >= 18 * 10 + 2, multiple of 8
 constexpr int kHaloBlk = kHaloRows * 128;         // bytes per 32-channel block
 constexpr int kWImgBytes = 9 * 16384;             // [9 taps][2 k-blocks][64 rows][128 B]
-constexpr int kConvSmemBytes = 1024 + kWImgBytes + 2 * kHaloBlk + 256;
-constexpr int kWgradSmemBytes = 1024 + 2 * 16384 + 2 * kHaloBlk;
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     tc::smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(tc::smem_u32(bar))
-                 : "memory");
-}
 
 // W [n][c][tap] -> shared-memory images (K-major SW128 B operands, rows = output channel of the pass)
 //   forward: image[tap ][c / 32][row n][c % 32] = W[n][c][tap]
@@ -98,138 +91,6 @@ __device__ __forceinline__ TileGeom decode_tile(int tile, int halves, int tblock
     g.t0 = (r % tblocks) * 16;
     g.b = r / tblocks;
     return g;
-}
-
-// stage halo rows [row_lo, row_hi) (18 x PITCH pixels; row 0 = frame t0 - 1, slot 0 = mel f0 - 1), zero outside the clip
-template <bool B32>
-__device__ __forceinline__ void load_halo(const float* __restrict__ in, const TileGeom& g, int T_l, int F, int pitch,
-                                          int row_lo, int row_hi, unsigned char* halo) {
-    const int n_items = (row_hi - row_lo) * pitch * 16;
-    for (int idx = threadIdx.x; idx < n_items; idx += kTile) {
-        const int q = idx & 15;
-        const int hp = row_lo * pitch + (idx >> 4);
-        const int hr = hp / pitch, hs = hp - hr * pitch;
-        const int t = g.t0 - 1 + hr, f = g.f0 - 1 + hs;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t >= 0 && t < T_l && f >= 0 && f < F)
-            v = __ldg(reinterpret_cast<const float4*>(in) + (((long long)g.b * T_l + t) * F + f) * 16 + q);
-        const uint32_t off = (q >> 3) * kHaloBlk + (B32 ? tc::sw128b32_chunk(hp, q & 7) : tc::sw128_chunk(hp, q & 7));
-        *reinterpret_cast<float4*>(halo + off) = v;
-    }
-}
-
-__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, bool valid) {
-    const uint32_t n = valid ? 16u : 0u;     // src-size 0: nothing is read, 16 zero bytes are written
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(n) : "memory");
-}
-
-// asynchronous (register-free) staging of the 18 x PITCH halo of a tile, K-major SW128 layout, zero fill outside the clip
-__device__ __forceinline__ void prefetch_halo(const float* __restrict__ in, const TileGeom& g, int T_l, int F, int pitch,
-                                              unsigned char* halo) {
-    const int n_items = 18 * pitch * 16;
-    for (int idx = threadIdx.x; idx < n_items; idx += kTile) {
-        const int q = idx & 15;
-        const int hp = idx >> 4;
-        const int hr = hp / pitch, hs = hp - hr * pitch;
-        const int t = g.t0 - 1 + hr, f = g.f0 - 1 + hs;
-        const bool ok = t >= 0 && t < T_l && f >= 0 && f < F;
-        const float4* src = reinterpret_cast<const float4*>(in) + (ok ? (((long long)g.b * T_l + t) * F + f) * 16 + q : 0);
-        cp_async16_zfill(halo + (q >> 3) * kHaloBlk + tc::sw128_chunk(hp, q & 7), src, ok);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-// Software pipeline per CTA (persistent over its tiles, single halo buffer, two TMEM accumulators):
-//   wait halo(i) | issue MMA(i) -> TMEM[i & 1] | epilogue(i-1) from TMEM[(i-1) & 1] overlaps MMA(i) |
-//   wait MMA(i) | cp.async halo(i+1) (the buffer is free once MMA(i) has completed)
-__global__ void __launch_bounds__(kTile, 1)
-conv3x3_tc_kernel(const float* __restrict__ in, int B, int T_l, int F, const float* __restrict__ w_img,
-                  const float* __restrict__ bias, float* __restrict__ out) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* Wi = smem;                          // weight image, 144 KB
-    unsigned char* halo = smem + kWImgBytes;           // 2 blocks x 192 rows x 128 B
-    float* bias_s = reinterpret_cast<float*>(halo + 2 * kHaloBlk);
-    __shared__ uint64_t w_bar, mma_bar;
-    __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int pitch = F == 16 ? 10 : 8;
-    const int halves = F == 16 ? 2 : 1;
-    const int tblocks = (T_l + 15) / 16;
-    const int n_tiles = B * tblocks * halves;
-
-    if (tid == 0) {
-        tc::mbar_init(&w_bar, 1);
-        tc::mbar_init(&mma_bar, 1);
-        tc::fence_mbar_init();
-        mbar_expect_tx(&w_bar, kWImgBytes);
-        for (int i = 0; i < 9; ++i) bulk_g2s(Wi + i * 16384, reinterpret_cast<const unsigned char*>(w_img) + i * 16384, 16384, &w_bar);
-    }
-    if (tid < 64) bias_s[tid] = bias ? __ldg(bias + tid) : 0.f;
-    for (int i = tid; i < 2 * kHaloBlk / 16; i += kTile) reinterpret_cast<float4*>(halo)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = tmem_base_s;
-    const uint32_t w_a = tc::smem_u32(Wi), h_a = tc::smem_u32(halo);
-    uint32_t phase = 0;
-    const int ti = tid >> 3, j = tid & 7;
-
-    auto epilogue = [&](const TileGeom& g, int buf) {
-        float acc[64];
-        tc::tmem_ld_row64(tmem, warp, buf * 64, acc);
-        tc::fence_before_sync();
-        const int t = g.t0 + ti, f = g.f0 + j;
-        if (t < T_l && f < F) {
-            float4* dst = reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64);
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 4 * c4);
-                dst[c4] = make_float4(acc[4 * c4] + b4.x, acc[4 * c4 + 1] + b4.y, acc[4 * c4 + 2] + b4.z, acc[4 * c4 + 3] + b4.w);
-            }
-        }
-    };
-
-    int tile = blockIdx.x;
-    if (tile < n_tiles) prefetch_halo(in, decode_tile(tile, halves, tblocks), T_l, F, pitch, halo);
-    TileGeom prev{};
-    int it = 0;
-    for (; tile < n_tiles; tile += gridDim.x, ++it) {
-        const TileGeom g = decode_tile(tile, halves, tblocks);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        tc::fence_proxy_async();
-        __syncthreads();                               // halo(i) complete and visible; epilogue(i-2) has drained TMEM[i & 1]
-        if (tid == 0) {
-            tc::mbar_wait(&w_bar, 0);                  // weight image landed (no-op after the first tile)
-            tc::fence_after_sync();
-            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
-            const uint32_t d = tmem + (it & 1) * 64;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                const uint32_t a0 = h_a + ((1 + dy) * pitch + 1 + dx) * 128;
-                const uint32_t b0 = w_a + tap * 16384;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    tc::umma_tf32(d, tc::smem_desc_sw128(a0 + (k >> 2) * kHaloBlk + (k & 3) * 32, 16, pitch * 128),
-                                  tc::smem_desc_sw128(b0 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024), idesc,
-                                  (tap > 0 || k > 0) ? 1u : 0u);
-            }
-            tc::umma_commit(&mma_bar);
-        }
-        if (it > 0) epilogue(prev, (it - 1) & 1);      // overlaps MMA(i)
-        tc::mbar_wait(&mma_bar, phase);
-        phase ^= 1;
-        tc::fence_after_sync();
-        const int next = tile + gridDim.x;
-        if (next < n_tiles) prefetch_halo(in, decode_tile(next, halves, tblocks), T_l, F, pitch, halo);
-        prev = g;
-    }
-    if (it > 0) epilogue(prev, (it - 1) & 1);
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -555,95 +416,6 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap dpre_map, const __grid
     if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 
-// grid = (chunks, 3): blockIdx.y selects dy; TMEM holds the three [64 n][64 c] accumulators of dx = -1, 0, +1.
-__global__ void __launch_bounds__(kTile, 2)
-conv_wgrad_tc_kernel(const float* __restrict__ d_pre, const float* __restrict__ in, int B, int T_l, int F,
-                     float* __restrict__ g_w) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* DP = smem;                          // d_pre tile, MN-major B32: 2 blocks x 128 rows
-    unsigned char* halo = smem + 32768;                // input halo, MN-major B32: 2 blocks x 192 rows
-    __shared__ uint64_t mma_bar;
-    __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int dy = (int)blockIdx.y - 1;
-    const int pitch = F == 16 ? 10 : 8;
-    const int halves = F == 16 ? 2 : 1;
-    const int tblocks = (T_l + 15) / 16;
-    const int n_tiles = B * tblocks * halves;
-
-    if (tid == 0) { tc::mbar_init(&mma_bar, 1); tc::fence_mbar_init(); }
-    for (int i = tid; i < 2 * kHaloBlk / 16; i += kTile) reinterpret_cast<float4*>(halo)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = tmem_base_s;
-    const uint32_t dp_a = tc::smem_u32(DP), h_a = tc::smem_u32(halo);
-    uint32_t phase = 0;
-    bool pending = false, first = true;
-    const int ti = tid >> 3, j = tid & 7;
-
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileGeom g = decode_tile(tile, halves, tblocks);
-        if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; pending = false; }
-        {   // d_pre row of this thread's pixel (zero for pixels outside the clip / mel range)
-            const int t = g.t0 + ti, f = g.f0 + j;
-            const bool valid = t < T_l && f < F;
-            const float4* src = reinterpret_cast<const float4*>(d_pre) + (((long long)g.b * T_l + t) * F + f) * 16;
-#pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4)
-                *reinterpret_cast<float4*>(DP + (c4 >> 3) * 16384 + tc::sw128b32_chunk(tid, c4 & 7)) =
-                    valid ? __ldg(src + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        load_halo<true>(in, g, T_l, F, pitch, 1 + dy, 17 + dy, halo);
-        // the two slack pixels past row 17+dy read by the dx = +1 tap of the last frame stay zero / stale-but-finite:
-        // they only meet d_pre rows of slots j >= 6 of ... (see below) -> keep them exact: slots beyond the row are
-        // the next row's first slots, which the loop above has just rewritten or which are still zero.
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 1, 1);
-#pragma unroll 1
-            for (int dxi = 0; dxi < 3; ++dxi) {
-#pragma unroll 4
-                for (int r = 0; r < 16; ++r)           // K step = the 8 pixels of frame row r of the tile
-                    tc::umma_tf32(tmem + dxi * 64, tc::smem_desc(dp_a + r * 1024, 16384, 512, 1),
-                                  tc::smem_desc(h_a + ((1 + dy + r) * pitch + dxi) * 128, kHaloBlk, 512, 1), idesc,
-                                  (!first || r > 0) ? 1u : 0u);
-            }
-            tc::umma_commit(&mma_bar);
-        }
-        pending = true;
-        first = false;
-    }
-    if (pending) { tc::mbar_wait(&mma_bar, phase); phase ^= 1; }
-    tc::fence_after_sync();
-    if (!first) {
-        const int n = 16 * warp + lane;                // M = 64 accumulators: row m in TMEM lane 32*(m/16) + m%16
-        const bool own = lane < 16;
-        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16);
-        float v[16];
-#pragma unroll 1
-        for (int dxi = 0; dxi < 3; ++dxi) {
-            const int tap = (dy + 1) * 3 + dxi;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-                tc::tmem_ld16(tbase + dxi * 64 + c0, v);
-                tc::tmem_ld_wait();
-                if (own) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) atomicAdd(g_w + n * 576 + (c0 + c) * 9 + tap, v[c]);
-                }
-            }
-        }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
-}
-
 #define DCASE_TRY_RC(expr) do { int rc__ = (expr); if (rc__ != DCASE_OK) return rc__; } while (0)
 
 int grid_for(int n_tiles, int num_sms, int per_sm) {
@@ -654,19 +426,11 @@ int grid_for(int n_tiles, int num_sms, int per_sm) {
 }  // namespace
 
 int conv_tc_kernels_init() {
-    if (!g_encode_tiled) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        DCASE_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) { dcase_set_error("cuTensorMapEncodeTiled is not available"); return DCASE_ERR_STATE; }
-        g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
-    }
+    { const int rc = dcase_tma_init(); if (rc != DCASE_OK) return rc; }
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgradSmemBytes));
     return DCASE_OK;
 }
 
