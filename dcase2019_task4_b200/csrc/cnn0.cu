@@ -137,12 +137,21 @@ __device__ __forceinline__ void stage_w0(const float* __restrict__ fold0, unsign
     for (int r = t; r < 128; r += nt) *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(r, 3)) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// The MMA issue helpers are called by ALL lanes of one warp with warp-uniform arguments (tc.cuh: one lane is elected
+// per instruction; issuing under `if (tid == 0)` costs ~16 instructions per MMA on the critical warp).
 __device__ __forceinline__ void issue_mma0(uint32_t d_tmem, uint32_t t0_addr) {   // y = T W0^T, K = 16
     constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+    const uint32_t lo = tc::desc_lo(t0_addr, 16), hi = tc::desc_hi(1024, 2);
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-        tc::umma_tf32(d_tmem, tc::smem_desc_sw128(t0_addr + k * 32, 16, 1024), tc::smem_desc_sw128(t0_addr + 64 + k * 32, 16, 1024),
-                      idesc, k);
+    for (int k = 0; k < 2; ++k) tc::umma_tf32_elect(d_tmem, lo + 2 * k, hi, lo + 4 + 2 * k, hi, idesc, k);
+}
+__device__ __forceinline__ void issue_mma1(uint32_t d_tmem, uint32_t a_addr, uint32_t wb_addr) {   // lin = y Wg^T, K = 64
+    constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+    const uint32_t a_lo = tc::desc_lo(a_addr, 16), b_lo = tc::desc_lo(wb_addr, 16), hi = tc::desc_hi(1024, 2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        tc::umma_tf32_elect(d_tmem, a_lo + (((j >> 2) * 16384 + (j & 3) * 32) >> 4), hi, b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi,
+                            idesc, j > 0 ? 1u : 0u);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -189,7 +198,8 @@ cnn0_fwd_kernel(Cnn0Args a) {
     uint32_t* keep_lo = reinterpret_cast<uint32_t*>(xs + 4 * 66);
     uint64_t* bars = reinterpret_cast<uint64_t*>(keep_lo + 128);     // [0] MMA0, [1] MMA1, [2] MMA2 (pool)
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 3);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
     const int row = tid & 127, half = tid >> 7;
 
     stage_wg(a.glu_w, Wb, tid, kFwdThreads);
@@ -228,7 +238,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    if (tid == 0) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
+    if (warp == 0) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
     if (drop && half == 0) keep_next = keep_lo[row];
     XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, cur + stride, a.T, tid) : XsRegs{0.f, 0.f};
 
@@ -284,11 +294,11 @@ cnn0_fwd_kernel(Cnn0Args a) {
         }
         tc::fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             tc::fence_after_sync();
-            tc::umma_128x64x64_kmajor(tmem + 64, a_a, wb_a, false);
-            tc::umma_commit(&bars[1]);
-            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
+            issue_mma1(tmem + 64, a_a, wb_a);
+            tc::umma_commit_elect(&bars[1]);
+            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
         }
         if (drop) {
 #pragma unroll
@@ -312,14 +322,16 @@ cnn0_fwd_kernel(Cnn0Args a) {
         }
         tc::fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {                    // MMA2: pooled[n][w] = sum_p z[p][n] P[w][p];  A MN-major (z), B K-major (P)
+        if (warp == 0) {                   // MMA2: pooled[n][w] = sum_p z[p][n] P[w][p];  A MN-major (z), B K-major (P)
             tc::fence_after_sync();
             constexpr uint32_t idesc = tc::idesc_tf32(64, 16, 1, 0);
+            const uint32_t z_lo = tc::desc_lo(a_a, 16384), p_lo = tc::desc_lo(p_a, 16);
+            const uint32_t mn_hi = tc::desc_hi(512, 1), k_hi = tc::desc_hi(1024, 2);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                tc::umma_tf32(tmem + 64, tc::smem_desc(a_a + j * 1024, 16384, 512, 1),
-                              tc::smem_desc_sw128(p_a + (j >> 2) * 2048 + (j & 3) * 32, 16, 1024), idesc, j > 0 ? 1u : 0u);
-            tc::umma_commit(&bars[2]);
+                tc::umma_tf32_elect(tmem + 64, z_lo + (j * 1024 >> 4), mn_hi, p_lo + (((j >> 2) * 2048 + (j & 3) * 32) >> 4), k_hi, idesc,
+                                    j > 0 ? 1u : 0u);
+            tc::umma_commit_elect(&bars[2]);
         }
         prev = cur;
     }
@@ -362,7 +374,9 @@ cnn0_bwd_kernel(Cnn0Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     require_aligned_smem(smem);
     const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
+    const bool issuer = (warp & 7) == 0;                           // warp 0 of each group issues its MMAs
     const int row = gt & 127, half = gt >> 7;
     unsigned char* Wb = smem;
     unsigned char* gbase = smem + 16384 + grp * kBwdGroupBytes;
@@ -413,7 +427,7 @@ cnn0_bwd_kernel(Cnn0Args a) {
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    if (active && gt == 0) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
+    if (active && issuer) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
     if (active && drop && half == 0) keep_next = keep_lo[row];
     XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, cur + stride, a.T, gt) : XsRegs{0.f, 0.f};
 
@@ -461,11 +475,11 @@ cnn0_bwd_kernel(Cnn0Args a) {
         }
         tc::fence_proxy_async();
         bar_sync_named(bar_id, 256);
-        if (gt == 0) {
+        if (issuer) {
             tc::fence_after_sync();
-            tc::umma_128x64x64_kmajor(tmem + 64, dl_a, wb_a, false);
-            tc::umma_commit(&bars[1]);
-            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit(&bars[0]); }
+            issue_mma1(tmem + 64, dl_a, wb_a);
+            tc::umma_commit_elect(&bars[1]);
+            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
         }
         // gradient of the pooled output for this pixel's window, dropout mask and 1/8 folded in (overlaps MMA1)
         float dz[32];
@@ -509,14 +523,15 @@ cnn0_bwd_kernel(Cnn0Args a) {
         }
         tc::fence_proxy_async();
         bar_sync_named(bar_id, 256);
-        if (gt == 0) {                     // MMA3: {U | S2}[m][j] += sum_p [DL | D2][p][m] E[p][j]
+        if (issuer) {                      // MMA3: {U | S2}[m][j] += sum_p [DL | D2][p][m] E[p][j]
             tc::fence_after_sync();
             constexpr uint32_t idesc = tc::idesc_tf32(128, 16, 1, 1);
+            const uint32_t d_lo = tc::desc_lo(dl_a, 16384), e_lo = tc::desc_lo(e_a, 16384), mn_hi = tc::desc_hi(512, 1);
+            const uint32_t acc1 = first ? 0u : 1u;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                tc::umma_tf32(tmem + 128, tc::smem_desc(dl_a + j * 1024, 16384, 512, 1), tc::smem_desc(e_a + j * 1024, 16384, 512, 1),
-                              idesc, (!first || j > 0) ? 1u : 0u);
-            tc::umma_commit(&bars[2]);
+                tc::umma_tf32_elect(tmem + 128, d_lo + (j * 1024 >> 4), mn_hi, e_lo + (j * 1024 >> 4), mn_hi, idesc, j > 0 ? 1u : acc1);
+            tc::umma_commit_elect(&bars[2]);
         }
         pending = true;
         first = false;
