@@ -130,6 +130,7 @@ WsLayout ws_layout(int B, int T, int NC) {
     add("fold0", kFold0Size);
     add("bn1", kBnSize);
     add("bn2", kBnSize);
+    add("gluimg1", kGluImgBytes / 4); add("gluimg2", kGluImgBytes / 4);
     add("wprep1_f", 36864); add("wprep1_d", 36864); add("wprep2_f", 36864); add("wprep2_d", 36864);
     add("out0", n0); add("ypre1", n0); add("out1", n1); add("ypre2", n1); add("out2", BT * 64);
     add("gi", 2 * BT * 192);
@@ -298,8 +299,8 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), out0, sms, s));
 
     // ---- CNN blocks 1, 2 ----
-    const char* names[3][6] = {{}, {"wprep1_f", "wprep1_d", "ypre1", "stats1", "bn1", "out1"},
-                               {"wprep2_f", "wprep2_d", "ypre2", "stats2", "bn2", "out2"}};
+    const char* names[3][7] = {{}, {"wprep1_f", "wprep1_d", "ypre1", "stats1", "bn1", "out1", "gluimg1"},
+                               {"wprep2_f", "wprep2_d", "ypre2", "stats2", "bn2", "out2", "gluimg2"}};
     const float* in = out0;
     for (int l = 1; l <= 2; ++l) {
         const int T_l = l == 1 ? T / 2 : T / 4;
@@ -314,9 +315,10 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
         float* out = wsp<float>(ws, L, names[l][5]);
         DCASE_TRY(launch_conv_w_prep(params + o.conv_w[l], wf, wd, s));
         DCASE_TRY(launch_conv3x3(in, B, T_l, F_l, wf, params + o.conv_b[l], ypre, training ? stats : nullptr, sms, s));
+        float* glu_img = wsp<float>(ws, L, names[l][6]);
         DCASE_TRY(launch_bn_finalize(stats, n_pix, params + o.bn_w[l], params + o.bn_b[l], bn_running + l * 128,
-                                     training, bn, s));
-        DCASE_TRY(launch_glu_pool_fwd(ypre, n_pix, F_l, bn, params + o.glu_w[l], params + o.glu_b[l], drop(l), out, sms, s));
+                                     training, bn, params + o.glu_w[l], params + o.glu_b[l], F_l, glu_img, s));
+        DCASE_TRY(launch_glu_pool_fwd(ypre, n_pix, F_l, glu_img, drop(l), out, sms, s));
         in = out;
     }
 

@@ -104,31 +104,66 @@ __global__ void bn0_finalize_kernel(const double* __restrict__ mom, long long n_
     fold0[kFold0A + c] = a;
 }
 
-// BN statistics of layers 1,2 from the conv epilogue's per-channel sum / sum of squares.
-__global__ void bn_finalize_kernel(const double* __restrict__ stats, long long n_pix, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running, int training,
-                                   float* __restrict__ bn) {
-    const int c = threadIdx.x;
-    double mean, var;
-    if (training) {
-        mean = stats[c] / (double)n_pix;
-        var = stats[64 + c] / (double)n_pix - mean * mean;
-        if (var < 0.0) var = 0.0;
-        if (running) {
-            running[c] = (1.f - kBnMomentum) * running[c] + kBnMomentum * (float)mean;
-            const double unbiased = var * (double)n_pix / (double)(n_pix - 1);
-            running[64 + c] = (1.f - kBnMomentum) * running[64 + c] + kBnMomentum * (float)unbiased;
+// BN statistics of layers 1,2 from the per-channel sum / sum of squares (one block of 256 threads; threads 0..63 own a
+// channel).  Also emits the shared-memory image the GLU forward kernel bulk-copies (glu_tma.cu): BatchNorm folded into
+// the GLU weights, W'[n][k] = Wg[n][k] * scale[k] in the swizzled K-major operand layout, bias' = bg + Wg shift, the
+// gate's exponent coefficients, and the 0/1 pooling-window matrix of this block's geometry.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ stats, long long n_pix, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ running, int training, float* __restrict__ bn,
+                   const float* __restrict__ glu_w, const float* __restrict__ glu_b, int F, float* __restrict__ img) {
+    __shared__ float sc_s[64], sh_s[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) {
+        const int c = tid;
+        double mean, var;
+        if (training) {
+            mean = stats[c] / (double)n_pix;
+            var = stats[64 + c] / (double)n_pix - mean * mean;
+            if (var < 0.0) var = 0.0;
+            if (running) {
+                running[c] = (1.f - kBnMomentum) * running[c] + kBnMomentum * (float)mean;
+                const double unbiased = var * (double)n_pix / (double)(n_pix - 1);
+                running[64 + c] = (1.f - kBnMomentum) * running[64 + c] + kBnMomentum * (float)unbiased;
+            }
+        } else {
+            mean = running[c];
+            var = running[64 + c];
         }
-    } else {
-        mean = running[c];
-        var = running[64 + c];
+        const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+        const float a = gamma[c] * invstd;
+        const float sh = beta[c] - a * (float)mean;
+        bn[kBnScale + c] = a;
+        bn[kBnShift + c] = sh;
+        bn[kBnMean + c] = (float)mean;
+        bn[kBnInvstd + c] = invstd;
+        sc_s[c] = a;
+        sh_s[c] = sh;
     }
-    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
-    const float a = gamma[c] * invstd;
-    bn[kBnScale + c] = a;
-    bn[kBnShift + c] = beta[c] - a * (float)mean;
-    bn[kBnMean + c] = (float)mean;
-    bn[kBnInvstd + c] = invstd;
+    __syncthreads();
+    if (!img) return;
+    constexpr float kComp = 1.f + 3.5221e-4f;          // tf32 operand truncation compensation (cnn0.cu)
+    constexpr float kNegLog2e = -1.4426950408889634f;
+    unsigned char* Wb = reinterpret_cast<unsigned char*>(img);
+    for (int i = tid; i < 4096; i += 256) {
+        const int n = i >> 6, k = i & 63;
+        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kComp * __ldg(glu_w + i) * sc_s[k]);
+    }
+    unsigned char* Pm = Wb + kGluImgP;
+    const int wpr = F >> 2;
+    for (int i = tid; i < 16 * 128; i += 256) {         // P[w][r] = 1 if tile row r = (tr, f) lies in pool window w
+        const int w = i >> 7, r = i & 127;
+        const int tr = r / F, f = r - tr * F;
+        *reinterpret_cast<float*>(Pm + (r >> 5) * 2048 + tc::sw128_off(w, r & 31)) = ((tr >> 1) * wpr + (f >> 2)) == w ? 1.f : 0.f;
+    }
+    float* misc = reinterpret_cast<float*>(Wb + kGluImgMisc);      // bias'[64] | -log2(e) scale[64] | -log2(e) shift[64]
+    if (tid < 64) {
+        float b = __ldg(glu_b + tid);
+        for (int k = 0; k < 64; ++k) b = fmaf(__ldg(glu_w + tid * 64 + k), sh_s[k], b);
+        misc[tid] = b;
+        misc[64 + tid] = kNegLog2e * sc_s[tid];
+        misc[128 + tid] = kNegLog2e * sh_s[tid];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,9 +755,9 @@ static int grid_for(long long n_tiles, int num_sms, int per_sm) {
 }
 
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta, float* running,
-                       int training, float* bn, cudaStream_t s) {
+                       int training, float* bn, const float* glu_w, const float* glu_b, int F, float* glu_img, cudaStream_t s) {
     DCASE_PROF("bn_finalize", s);
-    bn_finalize_kernel<<<1, 64, 0, s>>>(stats, n_pix, gamma, beta, running, training, bn);
+    bn_finalize_kernel<<<1, 256, 0, s>>>(stats, n_pix, gamma, beta, running, training, bn, glu_w, glu_b, F, glu_img);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

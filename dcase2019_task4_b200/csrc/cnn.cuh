@@ -42,14 +42,19 @@ int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* co
                              const float* fold0, const float* glu_w, const float* us, float* g_conv_w, float* g_conv_b,
                              float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b, cudaStream_t s);
 int cnn0_kernels_init();
-int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
-                        const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
+int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* glu_img, DropoutCfg drop, float* out,
+                        int num_sms, cudaStream_t s);
 // conv_tc.cu: weight images are the swizzled shared-memory layout of the tcgen05 B operand (36864 floats each)
 int launch_conv_w_prep(const float* w /*[64][64][3][3]*/, float* img_fwd, float* img_dgrad, cudaStream_t s);
 int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, const float* bias,
                    float* out, double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
+// GLU forward operand image written by bn_finalize (bytes): W' 16 KB | P 8 KB | {bias', exp scale, exp shift} 768 B
+constexpr int kGluImgP = 16384;
+constexpr int kGluImgMisc = 16384 + 8192;
+constexpr int kGluImgBytes = 16384 + 8192 + 768;
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta,
-                       float* running, int training, float* bn, cudaStream_t s);
+                       float* running, int training, float* bn, const float* glu_w, const float* glu_b, int F,
+                       float* glu_img /*nullable, kGluImgBytes*/, cudaStream_t s);
 int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* bn, const float* gamma,
                         const float* beta, const float* glu_w, const float* glu_b, DropoutCfg drop,
                         const float* d_out, float* d_y, float* s12 /*[2][64]*/, float* g_glu_w, float* g_glu_b,

@@ -336,8 +336,10 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap dpre_map, const __grid
     const int n_tiles = B * tblocks * halves;
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
 
-    // rows never written by the TMA boxes (halo rows >= 18 * PITCH) must be finite: they meet zero d_pre rows
-    for (int i = tid; i < kWgStages * kWgStageBytes / 16; i += kWgThreads) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the 8 halo rows behind the TMA box (read by the dx = +1 tap of the last frame row when PITCH = 8) must be finite:
+    // they only ever meet zero d_pre rows
+    for (int i = tid; i < kWgStages * 64; i += kWgThreads)
+        reinterpret_cast<float4*>(smem + (i >> 6) * kWgStageBytes + 32768 + 18 * PITCH * 128)[i & 63] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         for (int i = 0; i < kWgStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 3); }
         tc::mbar_init(done, 3);
@@ -397,16 +399,22 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap dpre_map, const __grid
         const int n = 16 * wq + lane;                       // M = 64 accumulators: row m in TMEM lane 32*(m/16) + m%16
         const bool own = lane < 16;
         const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16);
-        float v[16];
+        // g_w[n][c][tap]: the 9 taps of 4 consecutive channels are 36 contiguous, 16-byte aligned floats -> 9 vector REDs
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll 1
-            for (int c0 = 0; c0 < 32; c0 += 16) {
-                tc::tmem_ld16(tbase + tap * 32 + c0, v);
-                tc::tmem_ld_wait();
-                if (own) {
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+            float v[9][4];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) atomicAdd(g_w + n * 576 + (32 * ch + c0 + c) * 9 + tap, v[c]);
+            for (int tap = 0; tap < 9; ++tap) tc::tmem_ld4(tbase + tap * 32 + c0, v[tap]);
+            tc::tmem_ld_wait();
+            if (own) {
+                float* dst = g_w + n * 576 + (32 * ch + c0) * 9;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    float e[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const int idx = 4 * q + k; e[k] = v[idx % 9][idx / 9]; }
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3])
+                                 : "memory");
                 }
             }
         }

@@ -6,7 +6,8 @@
 // Tile = 128 consecutive pixels = 16 pool windows.  Nothing is staged through registers:
 //   * the [128][64] fp32 tile arrives by TMA directly in the tensor core's K-major operand layout (two 16 KB boxes),
 //   * BatchNorm is folded into the GEMM:  lin = Wg (a v + s) + bg = (Wg diag(a)) v + (Wg s + bg), so MMA1 runs on the
-//     RAW tile the moment it lands (issued by the control warp, no thread pass in front of it),
+//     RAW tile the moment it lands (issued by the control warp, no thread pass in front of it); the folded, swizzled
+//     weight image and the pooling matrix are prepared once per launch by bn_finalize and bulk-copied (25 KB),
 //   * the 8 compute warps read v back from the same tile for the gate  z = lin * sigmoid(a v + s) * keep,  write z over
 //     it (MN-major) and the (2,4) average pool is a second MMA with a 0/1 window matrix (as in cnn0.cu).
 // Control warp (warp 8): TMA ring of two input buffers, MMA1 one tile ahead, MMA2, all through mbarriers; the compute
@@ -24,9 +25,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 struct GluFwdArgs {
     long long n_pix;
     int F;                 // 16 or 4
-    const float* bn;       // bn_finalize output (cnn.cuh): scale[64], shift[64], ...
-    const float* glu_w;    // [64][64]
-    const float* glu_b;    // [64]
+    const float* img;      // operand image written by bn_finalize (cnn.cuh: kGluImg*)
     DropoutCfg drop;
     float* out;            // [n_pix / 8][64]
 };
@@ -57,7 +56,7 @@ __device__ __forceinline__ uint32_t chunk_addr(uint32_t row_base, int c4) {
 //                                     keep_lo[2][128] | 8 mbarriers | tmem base
 // TMEM (256 columns): lin[2] at 0 / 64, pooled[2] at 128 / 144 (M = 64 channels, N = 16 windows)
 constexpr int kWb = 0, kIn = 16384, kP = 16384 + 65536, kMisc = kP + 8192;
-constexpr int kSmemBytes = kMisc + 3 * 64 * 4 + 2 * 128 * 4 + 8 * 8 + 16;
+constexpr int kSmemBytes = kMisc + 3 * 64 * 4 + 2 * 128 * 4 + 9 * 8 + 16;
 constexpr int kThreads = 288;              // warps 0..7 compute (row = tid & 127, half = tid >> 7), warp 8 control
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -74,43 +73,31 @@ glu_pool_fwd_tma_kernel(const __grid_constant__ CUtensorMap in_map, GluFwdArgs a
     uint64_t* lin_full = bars + 2;     // [2] MMA1 complete                   (1)
     uint64_t* z_ready = bars + 4;      // [2] compute warps wrote z           (256)
     uint64_t* pool_full = bars + 6;    // [2] MMA2 complete: pooled tile ready, input buffer free   (1)
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* img_bar = bars + 8;      // operand image landed (tx)
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 9);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if ((tc::smem_u32(smem) & 1023u) != 0) __trap();
 
-    // ---- prologue: folded weights W'[n][k] = Wg[n][k] * scale[k] (x truncation compensation), bias' = bg + Wg shift ----
-    for (int i = tid; i < 4096; i += kThreads) {
-        const int n = i >> 6, k = i & 63;
-        const float w = __ldg(a.glu_w + i) * __ldg(a.bn + kBnScale + k);
-        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kTruncComp * w);
-    }
-    if (tid < 64) {
-        float b = __ldg(a.glu_b + tid);
-        for (int k = 0; k < 64; ++k) b = fmaf(__ldg(a.glu_w + tid * 64 + k), __ldg(a.bn + kBnShift + k), b);
-        bias_s[tid] = b;
-        scale_s[tid] = -kLog2e * __ldg(a.bn + kBnScale + tid);     // exp(-y) = 2^(-log2(e) (a v + s))
-        shift_s[tid] = -kLog2e * __ldg(a.bn + kBnShift + tid);
-    }
-    const int wpr = a.F >> 2;                      // windows per frame-row pair
-    for (int i = tid; i < 16 * 128; i += kThreads) {    // P[w][r] = 1 if tile row r = (tr, f) lies in window w
-        const int w = i >> 7, r = i & 127;
-        const int tr = r / a.F, f = r - tr * a.F;
-        const int wr = (tr >> 1) * wpr + (f >> 2);
-        *reinterpret_cast<float*>(Pm + (r >> 5) * 2048 + tc::sw128_off(w, r & 31)) = wr == w ? 1.f : 0.f;
-    }
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&in_full[i], 1); tc::mbar_init(&lin_full[i], 1);
             tc::mbar_init(&z_ready[i], 256); tc::mbar_init(&pool_full[i], 1);
         }
+        tc::mbar_init(img_bar, 1);
         tc::fence_mbar_init();
+        // W' | P | misc are laid out in the image exactly as in shared memory: Wb at 0, P at kP, misc at kMisc
+        mbar_expect_tx(img_bar, kGluImgBytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.img);
+        bulk_g2s(Wb, src, 16384, img_bar);
+        bulk_g2s(Pm, src + kGluImgP, 8192, img_bar);
+        bulk_g2s(bias_s, src + kGluImgMisc, 768, img_bar);
     }
     if (warp == 8) tc::tmem_alloc(tmem_base_s, 256);
-    tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    tc::mbar_wait(img_bar, 0);
     const uint32_t tmem = *tmem_base_s;
     const long long n_tiles = (a.n_pix + kTile - 1) / kTile;
     const long long stride = gridDim.x;
@@ -262,13 +249,13 @@ int glu_tma_kernels_init() {
     return DCASE_OK;
 }
 
-int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_w,
-                        const float* glu_b, DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
+int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* glu_img, DropoutCfg drop, float* out,
+                        int num_sms, cudaStream_t s) {
     DCASE_PROF(F == 16 ? "glu_pool_fwd_l1" : "glu_pool_fwd_l2", s);
     DCASE_REQUIRE(F == 16 || F == 4, "glu_pool is built for the 16- and 4-bin blocks of cfg.crnn_kwargs");
     DCASE_REQUIRE(n_pix > 0 && n_pix % (2 * F) == 0 && n_pix < (1ll << 31), "pixel count must be whole frame pairs");
     GluFwdArgs a{};
-    a.n_pix = n_pix; a.F = F; a.bn = bn; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
+    a.n_pix = n_pix; a.F = F; a.img = glu_img; a.drop = drop; a.out = out;
     CUtensorMap in_map;
     { const int rc = make_rows_map(&in_map, ypre, n_pix, kTile, CU_TENSOR_MAP_SWIZZLE_128B); if (rc != DCASE_OK) return rc; }
     const long long n_tiles = (n_pix + kTile - 1) / kTile;
