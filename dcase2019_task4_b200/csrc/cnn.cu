@@ -121,7 +121,7 @@ bn_finalize_kernel(const double* __restrict__ stats, long long n_pix, const floa
             mean = stats[c] / (double)n_pix;
             var = stats[64 + c] / (double)n_pix - mean * mean;
             if (var < 0.0) var = 0.0;
-            if (running) {
+            if (running && blockIdx.x == 0) {
                 running[c] = (1.f - kBnMomentum) * running[c] + kBnMomentum * (float)mean;
                 const double unbiased = var * (double)n_pix / (double)(n_pix - 1);
                 running[64 + c] = (1.f - kBnMomentum) * running[64 + c] + kBnMomentum * (float)unbiased;
@@ -133,34 +133,41 @@ bn_finalize_kernel(const double* __restrict__ stats, long long n_pix, const floa
         const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
         const float a = gamma[c] * invstd;
         const float sh = beta[c] - a * (float)mean;
-        bn[kBnScale + c] = a;
-        bn[kBnShift + c] = sh;
-        bn[kBnMean + c] = (float)mean;
-        bn[kBnInvstd + c] = invstd;
+        if (blockIdx.x == 0) {
+            bn[kBnScale + c] = a;
+            bn[kBnShift + c] = sh;
+            bn[kBnMean + c] = (float)mean;
+            bn[kBnInvstd + c] = invstd;
+        }
         sc_s[c] = a;
         sh_s[c] = sh;
     }
     __syncthreads();
     if (!img) return;
+    // the image is split over the grid's blocks (each block recomputed scale / shift above)
     constexpr float kComp = 1.f + 3.5221e-4f;          // tf32 operand truncation compensation (cnn0.cu)
     constexpr float kNegLog2e = -1.4426950408889634f;
+    const int nb = gridDim.x, bid = blockIdx.x;
     unsigned char* Wb = reinterpret_cast<unsigned char*>(img);
-    for (int i = tid; i < 4096; i += 256) {
+    for (int i = bid * 256 + tid; i < 4096; i += nb * 256) {
         const int n = i >> 6, k = i & 63;
         *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kComp * __ldg(glu_w + i) * sc_s[k]);
     }
     unsigned char* Pm = Wb + kGluImgP;
     const int wpr = F >> 2;
-    for (int i = tid; i < 16 * 128; i += 256) {         // P[w][r] = 1 if tile row r = (tr, f) lies in pool window w
+    for (int i = bid * 256 + tid; i < 16 * 128; i += nb * 256) {   // P[w][r] = 1 if tile row r = (tr, f) lies in pool window w
         const int w = i >> 7, r = i & 127;
         const int tr = r / F, f = r - tr * F;
         *reinterpret_cast<float*>(Pm + (r >> 5) * 2048 + tc::sw128_off(w, r & 31)) = ((tr >> 1) * wpr + (f >> 2)) == w ? 1.f : 0.f;
     }
     float* misc = reinterpret_cast<float*>(Wb + kGluImgMisc);      // bias'[64] | -log2(e) scale[64] | -log2(e) shift[64]
-    if (tid < 64) {
-        float b = __ldg(glu_b + tid);
-        for (int k = 0; k < 64; ++k) b = fmaf(__ldg(glu_w + tid * 64 + k), sh_s[k], b);
-        misc[tid] = b;
+    for (int n = bid * 8 + (tid >> 5); n < 64; n += nb * 8) {      // bias'[n] = bg[n] + sum_k Wg[n][k] shift[k], one warp per n
+        const int l = tid & 31;
+        float b = __ldg(glu_w + n * 64 + l) * sh_s[l] + __ldg(glu_w + n * 64 + 32 + l) * sh_s[32 + l];
+        b = warp_sum(b);
+        if (l == 0) misc[n] = b + __ldg(glu_b + n);
+    }
+    if (bid == 0 && tid < 64) {
         misc[64 + tid] = kNegLog2e * sc_s[tid];
         misc[128 + tid] = kNegLog2e * sh_s[tid];
     }
@@ -757,7 +764,7 @@ static int grid_for(long long n_tiles, int num_sms, int per_sm) {
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta, float* running,
                        int training, float* bn, const float* glu_w, const float* glu_b, int F, float* glu_img, cudaStream_t s) {
     DCASE_PROF("bn_finalize", s);
-    bn_finalize_kernel<<<1, 256, 0, s>>>(stats, n_pix, gamma, beta, running, training, bn, glu_w, glu_b, F, glu_img);
+    bn_finalize_kernel<<<glu_img ? 8 : 1, 256, 0, s>>>(stats, n_pix, gamma, beta, running, training, bn, glu_w, glu_b, F, glu_img);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
