@@ -65,156 +65,260 @@ __device__ __forceinline__ void load_head_weights(const HeadArgs& a, float* Wd, 
     }
 }
 
-__global__ void __launch_bounds__(128)
+// ---------------------------------------------------------------------------------------------------------------
+// One CTA per clip, 256 threads.  The clip's [To][128] BiGRU output is staged once in shared memory (coalesced loads,
+// dropout applied on the way in, rows padded to 132 floats so that a warp's 32 rows hit distinct banks); thread
+// (row, head) then owns the 10 logits of one head (dense / softmax) of one frame: 1280 FMAs against weights that
+// are warp-broadcast from shared memory.  The previous thread-per-row version spent its time in un-coalesced row
+// reads and 2560 serial FMAs per thread.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kXPitch = 132;
+constexpr int kHeadThreads = 256;
+
+// x rows [t0, t0 + n_rows) of clip b -> xm[r][kXPitch] with inverted dropout (keep bits from Philox, one call per row)
+__device__ __forceinline__ void stage_rows(const HeadArgs& a, int b, int t0, int n_rows, uint64_t seed, uint32_t step, float* xm,
+                                           uint4* keep_s) {
+    const int tid = threadIdx.x;
+    if (a.drop && tid < n_rows) keep_s[tid] = philox4x32_10((uint64_t)((long long)b * a.To + t0 + tid), a.stream, step, seed);
+    if (a.drop) __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(a.x + ((long long)b * a.To + t0) * kD);
+    for (int i = tid; i < n_rows * (kD / 4); i += kHeadThreads) {
+        const int r = i >> 5, k4 = i & 31;
+        float4 v = __ldg(src + i);
+        if (a.drop) {
+            const uint4 kw4 = keep_s[r];
+            const uint32_t kw = k4 < 8 ? kw4.x : (k4 < 16 ? kw4.y : (k4 < 24 ? kw4.z : kw4.w));
+            const uint32_t bits = kw >> ((4 * k4) & 31);
+            v.x = (bits & 1u) ? 2.f * v.x : 0.f;
+            v.y = (bits & 2u) ? 2.f * v.y : 0.f;
+            v.z = (bits & 4u) ? 2.f * v.z : 0.f;
+            v.w = (bits & 8u) ? 2.f * v.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(xm + r * kXPitch + 4 * k4) = v;
+    }
+}
+
+// the kMaxC logits of one head for one staged row: acc[c] = bias[c] + sum_k xm_row[k] W[c][k]
+__device__ __forceinline__ void head_logits(const float* xm_row, const float* W, const float* bias, float (&acc)[kMaxC]) {
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) acc[c] = bias[c];
+#pragma unroll 2
+    for (int k4 = 0; k4 < kD / 4; ++k4) {
+        const float4 v = *reinterpret_cast<const float4*>(xm_row + 4 * k4);
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+            const float4 w = *reinterpret_cast<const float4*>(W + c * kD + 4 * k4);
+            acc[c] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[c]))));
+        }
+    }
+}
+
+// dynamic smem: Wd, Ws [16][128] | bd, bs [16] | keep [128] uint4 | xm [128][132] | ex [128][2 * 16]
+constexpr int kHeadRows = 128;
+constexpr size_t kHeadSmem = (2 * kMaxC * kD + 2 * kMaxC) * sizeof(float) + kHeadRows * sizeof(uint4) +
+                             (kHeadRows * kXPitch + kHeadRows * 2 * kMaxC) * sizeof(float);
+
+__global__ void __launch_bounds__(kHeadThreads)
 head_fwd_kernel(HeadArgs a) {
-    __shared__ __align__(16) float Wd[kMaxC * kD];
-    __shared__ __align__(16) float Ws[kMaxC * kD];
-    __shared__ float bd[kMaxC], bs[kMaxC];
-    __shared__ float red[4][2 * kMaxC];
+    extern __shared__ __align__(16) float smem[];
+    float* Wd = smem;
+    float* Ws = Wd + kMaxC * kD;
+    float* bd = Ws + kMaxC * kD;
+    float* bs = bd + kMaxC;
+    uint4* keep_s = reinterpret_cast<uint4*>(bs + kMaxC);
+    float* xm = reinterpret_cast<float*>(keep_s + kHeadRows);
+    float* ex = xm + kHeadRows * kXPitch;              // [row][0..15] = sigmoid(dense), [16..31] = clamped class softmax
+    __shared__ float red[8][2 * kMaxC];
     const int tid = threadIdx.x, b = blockIdx.x;
     load_head_weights(a, Wd, Ws, bd, bs);
     uint64_t seed = a.seed; uint32_t step = a.step;
     if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
-    __syncthreads();
-    float num[kMaxC], den[kMaxC];
+    const int r = tid & 127, head = tid >> 7;          // head 0: dense -> strong; head 1: dense_softmax -> attention
+    float num = 0.f, den = 0.f;                        // threads 0..NC-1 of the final pass own a class
+    float pn[kMaxC], pd[kMaxC];
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) { num[c] = 0.f; den[c] = 0.f; }
-    for (int t = tid; t < a.To; t += 128) {
-        const long long row = (long long)b * a.To + t;
-        uint4 keep = make_uint4(0, 0, 0, 0);
-        if (a.drop) keep = philox4x32_10((uint64_t)row, a.stream, step, seed);
-        float ld[kMaxC], ls[kMaxC], ar[kMaxC];
-        head_row_forward(a.x + row * kD, keep, a.drop, Wd, Ws, bd, bs, a.NC, ld, ls, nullptr);
-        softmax_classes(ls, a.NC, ar);
+    for (int c = 0; c < kMaxC; ++c) { pn[c] = 0.f; pd[c] = 0.f; }
+    for (int t0 = 0; t0 < a.To; t0 += kHeadRows) {
+        const int n_rows = min(kHeadRows, a.To - t0);
+        __syncthreads();                               // weights staged / previous chunk consumed
+        stage_rows(a, b, t0, n_rows, seed, step, xm, keep_s);
+        __syncthreads();
+        if (r < n_rows) {
+            float acc[kMaxC];
+            head_logits(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
+            if (head == 0) {
+                const long long row = (long long)b * a.To + t0 + r;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
-            if (c < a.NC) {
-                const float s = sigmoid_fast(ld[c]);
-                const float at = fminf(fmaxf(ar[c], 1e-7f), 1.f);
-                a.strong[row * a.NC + c] = s;
-                num[c] = fmaf(s, at, num[c]);
-                den[c] += at;
+                for (int c = 0; c < kMaxC; ++c) {
+                    const float sg = sigmoid_fast(acc[c]);
+                    ex[r * 2 * kMaxC + c] = sg;
+                    if (c < a.NC) a.strong[row * a.NC + c] = sg;
+                }
+            } else {
+                float ar[kMaxC];
+                softmax_classes(acc, a.NC, ar);
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) ex[r * 2 * kMaxC + kMaxC + c] = fminf(fmaxf(ar[c], 1e-7f), 1.f);
+            }
+        }
+        __syncthreads();
+        // attention pooling partial sums: thread (row, head 0) folds its row, then warps reduce per class
+        if (head == 0 && r < n_rows) {
+#pragma unroll
+            for (int c = 0; c < kMaxC; ++c) {
+                const float at = ex[r * 2 * kMaxC + kMaxC + c];
+                pn[c] = fmaf(ex[r * 2 * kMaxC + c], at, pn[c]);
+                pd[c] += at;
             }
         }
     }
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c) {
-        const float n = warp_sum(num[c]), d = warp_sum(den[c]);
+        const float n = warp_sum(pn[c]), d = warp_sum(pd[c]);
         if ((tid & 31) == 0) { red[tid >> 5][c] = n; red[tid >> 5][kMaxC + c] = d; }
     }
     __syncthreads();
     if (tid < a.NC) {
-        const float n = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-        const float d = red[0][kMaxC + tid] + red[1][kMaxC + tid] + red[2][kMaxC + tid] + red[3][kMaxC + tid];
-        a.weak[b * a.NC + tid] = n / d;
-        if (a.den) a.den[b * a.NC + tid] = d;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { num += red[w][tid]; den += red[w][kMaxC + tid]; }     // warps 0..3 hold head 0
+        a.weak[b * a.NC + tid] = num / den;
+        if (a.den) a.den[b * a.NC + tid] = den;
     }
 }
 
-// Backward of the head for one clip per CTA; forward recomputed from x.  dynamic smem:
-//   Wd,Ws [16][128] | bd,bs [16] | xm [128][132] | dl [128][33]
-__global__ void __launch_bounds__(128)
+// Backward of the head for one clip per CTA; forward recomputed from the staged rows.  Thread (row, head) owns the
+// logit gradients of its head; d_x needs both heads' gradients of the row (exchanged through shared memory), and the
+// weight gradients are per-thread column sums over the staged chunk.
+__global__ void __launch_bounds__(kHeadThreads)
 head_bwd_kernel(HeadArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* Wd = smem;
     float* Ws = Wd + kMaxC * kD;
     float* bd = Ws + kMaxC * kD;
     float* bs = bd + kMaxC;
-    float* xm = bs + kMaxC;            // [128][132]
-    float* dl = xm + 128 * 132;        // [128][33]  (0..15 dense logits grad, 16..31 softmax logits grad)
+    uint4* keep_s = reinterpret_cast<uint4*>(bs + kMaxC);
+    float* xm = reinterpret_cast<float*>(keep_s + kHeadRows);
+    float* dl = xm + kHeadRows * kXPitch;              // [row][0..15] dense logit grads, [16..31] softmax logit grads
+    __shared__ float sig_s[kHeadRows][kMaxC];          // sigmoid(dense) of the chunk (softmax branch needs s - weak)
     const int tid = threadIdx.x, b = blockIdx.x;
     load_head_weights(a, Wd, Ws, bd, bs);
     uint64_t seed = a.seed; uint32_t step = a.step;
     if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
-    __syncthreads();
-    float gw[2 * kMaxC];
+    const int r = tid & 127, head = tid >> 7;
+    // weight gradients: thread tid owns column k = tid & 127 of head (tid >> 7): 16 accumulators + bias slot
+    float gw[kMaxC];
 #pragma unroll
-    for (int c = 0; c < 2 * kMaxC; ++c) gw[c] = 0.f;
+    for (int c = 0; c < kMaxC; ++c) gw[c] = 0.f;
     float gb = 0.f;
-    for (int t0 = 0; t0 < a.To; t0 += 128) {
-        const int t = t0 + tid;
-        const bool valid = t < a.To;
-        float* xm_row = xm + tid * 132;
-        float* dl_row = dl + tid * 33;
-        if (valid) {
-            const long long row = (long long)b * a.To + t;
-            uint4 keep = make_uint4(0, 0, 0, 0);
-            if (a.drop) keep = philox4x32_10((uint64_t)row, a.stream, step, seed);
-            float ld[kMaxC], ls[kMaxC], ar[kMaxC];
-            head_row_forward(a.x + row * kD, keep, a.drop, Wd, Ws, bd, bs, a.NC, ld, ls, xm_row);
-            softmax_classes(ls, a.NC, ar);
-            float da[kMaxC];
-            float dot = 0.f;
+    for (int t0 = 0; t0 < a.To; t0 += kHeadRows) {
+        const int n_rows = min(kHeadRows, a.To - t0);
+        __syncthreads();
+        stage_rows(a, b, t0, n_rows, seed, step, xm, keep_s);
+        __syncthreads();
+        float acc[kMaxC], ar[kMaxC];
+        const bool live = r < n_rows;
+        const long long row = (long long)b * a.To + t0 + r;
+        if (live) {
+            head_logits(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
+            if (head == 0) {
 #pragma unroll
-            for (int c = 0; c < kMaxC; ++c) {
-                da[c] = 0.f;
-                float dld = 0.f;
-                if (c < a.NC) {
-                    const float s = sigmoid_fast(ld[c]);
-                    const float at = fminf(fmaxf(ar[c], 1e-7f), 1.f);
-                    const float dwk = __ldg(a.d_weak + b * a.NC + c);
-                    const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
-                    const float wk = __ldg(a.weak + b * a.NC + c);
-                    const float ds = __ldg(a.d_strong + row * a.NC + c) + dwk * at * inv_den;
-                    dld = ds * s * (1.f - s);
-                    const bool pass = ar[c] >= 1e-7f && ar[c] <= 1.f;   // clamp passes gradient inside [min, max]
-                    da[c] = pass ? dwk * (s - wk) * inv_den : 0.f;
-                    dot = fmaf(da[c], ar[c], dot);
-                }
-                dl_row[c] = dld;
+                for (int c = 0; c < kMaxC; ++c) sig_s[r][c] = sigmoid_fast(acc[c]);
+            } else {
+                softmax_classes(acc, a.NC, ar);
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) dl[r * 2 * kMaxC + kMaxC + c] = ar[c];       // parked: head 0 needs `at`
             }
-#pragma unroll
-            for (int c = 0; c < kMaxC; ++c) dl_row[kMaxC + c] = c < a.NC ? ar[c] * (da[c] - dot) : 0.f;
-            // d x = mask * 2 * (Wd^T dl_d + Ws^T dl_s)
-            const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
-            float4* dx = reinterpret_cast<float4*>(a.d_x + row * kD);
-#pragma unroll 4
-            for (int k4 = 0; k4 < kD / 4; ++k4) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        if (live) {
+            if (head == 0) {
 #pragma unroll
                 for (int c = 0; c < kMaxC; ++c) {
+                    float dld = 0.f;
                     if (c < a.NC) {
-                        const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
-                        const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
-                        const float gd = dl_row[c], gs = dl_row[kMaxC + c];
-                        acc.x = fmaf(gd, wd.x, fmaf(gs, ws.x, acc.x));
-                        acc.y = fmaf(gd, wd.y, fmaf(gs, ws.y, acc.y));
-                        acc.z = fmaf(gd, wd.z, fmaf(gs, ws.z, acc.z));
-                        acc.w = fmaf(gd, wd.w, fmaf(gs, ws.w, acc.w));
+                        const float sg = sig_s[r][c];
+                        const float at = fminf(fmaxf(dl[r * 2 * kMaxC + kMaxC + c], 1e-7f), 1.f);
+                        const float dwk = __ldg(a.d_weak + b * a.NC + c);
+                        const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
+                        const float ds = __ldg(a.d_strong + row * a.NC + c) + dwk * at * inv_den;
+                        dld = ds * sg * (1.f - sg);
+                    }
+                    acc[c] = dld;
+                }
+            } else {
+                float da[kMaxC];
+                float dot = 0.f;
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) {
+                    da[c] = 0.f;
+                    if (c < a.NC) {
+                        const float dwk = __ldg(a.d_weak + b * a.NC + c);
+                        const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
+                        const float wk = __ldg(a.weak + b * a.NC + c);
+                        const bool pass = ar[c] >= 1e-7f && ar[c] <= 1.f;   // clamp passes gradient inside [min, max]
+                        da[c] = pass ? dwk * (sig_s[r][c] - wk) * inv_den : 0.f;
+                        dot = fmaf(da[c], ar[c], dot);
                     }
                 }
-                if (a.drop) {
-                    const uint32_t bits = kw[k4 >> 3] >> ((4 * k4) & 31);
-                    acc.x = (bits & 1u) ? 2.f * acc.x : 0.f;
-                    acc.y = (bits & 2u) ? 2.f * acc.y : 0.f;
-                    acc.z = (bits & 4u) ? 2.f * acc.z : 0.f;
-                    acc.w = (bits & 8u) ? 2.f * acc.w : 0.f;
-                }
-                dx[k4] = acc;
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) acc[c] = c < a.NC ? ar[c] * (da[c] - dot) : 0.f;
             }
-        } else {
-            for (int k = 0; k < kD; ++k) xm_row[k] = 0.f;
-            for (int c = 0; c < 2 * kMaxC; ++c) dl_row[c] = 0.f;
         }
-        __syncthreads();
-        // thread k owns column k of both weight gradients; threads 0..31 also own one bias slot
-        for (int q = 0; q < 128; ++q) {
-            const float xv = xm[q * 132 + tid];
+        __syncthreads();                               // every head-0 thread has read its `at` values
 #pragma unroll
-            for (int c = 0; c < 2 * kMaxC; ++c) gw[c] = fmaf(dl[q * 33 + c], xv, gw[c]);
-            if (tid < 2 * kMaxC) gb += dl[q * 33 + tid];
-        }
+        for (int c = 0; c < kMaxC; ++c) dl[r * 2 * kMaxC + head * kMaxC + c] = live ? acc[c] : 0.f;
         __syncthreads();
-    }
+        // d x = mask * 2 * (Wd^T dl_d + Ws^T dl_s): thread (row, head) writes channels 64 head .. 64 head + 63
+        if (live) {
+            const uint4 kw4 = a.drop ? keep_s[r] : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            const float* dl_row = dl + r * 2 * kMaxC;
+            float4* dx = reinterpret_cast<float4*>(a.d_x + row * kD);
+#pragma unroll 2
+            for (int k4 = 16 * head; k4 < 16 * head + 16; ++k4) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
-        if (c < a.NC) {
-            atomicAdd(a.g_w_dense + c * kD + tid, gw[c]);
-            atomicAdd(a.g_w_soft + c * kD + tid, gw[kMaxC + c]);
+                for (int c = 0; c < kMaxC; ++c) {
+                    const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
+                    const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
+                    const float gd = dl_row[c], gs = dl_row[kMaxC + c];
+                    o.x = fmaf(gd, wd.x, fmaf(gs, ws.x, o.x));
+                    o.y = fmaf(gd, wd.y, fmaf(gs, ws.y, o.y));
+                    o.z = fmaf(gd, wd.z, fmaf(gs, ws.z, o.z));
+                    o.w = fmaf(gd, wd.w, fmaf(gs, ws.w, o.w));
+                }
+                if (a.drop) {
+                    const uint32_t kw = k4 < 8 ? kw4.x : (k4 < 16 ? kw4.y : (k4 < 24 ? kw4.z : kw4.w));
+                    const uint32_t bits = kw >> ((4 * k4) & 31);
+                    o.x = (bits & 1u) ? 2.f * o.x : 0.f;
+                    o.y = (bits & 2u) ? 2.f * o.y : 0.f;
+                    o.z = (bits & 4u) ? 2.f * o.z : 0.f;
+                    o.w = (bits & 8u) ? 2.f * o.w : 0.f;
+                }
+                dx[k4] = o;
+            }
+        }
+        // weight gradients of the chunk: column k of head (tid >> 7)
+        {
+            const int k = tid & 127;
+            for (int q = 0; q < n_rows; ++q) {
+                const float xv = xm[q * kXPitch + k];
+                const float* dq = dl + q * 2 * kMaxC + head * kMaxC;
+#pragma unroll
+                for (int c = 0; c < kMaxC; ++c) gw[c] = fmaf(dq[c], xv, gw[c]);
+            }
+            if (k < kMaxC)
+                for (int q = 0; q < n_rows; ++q) gb += dl[q * 2 * kMaxC + head * kMaxC + k];
         }
     }
-    if (tid < kMaxC) { if (tid < a.NC) atomicAdd(a.g_b_dense + tid, gb); }
-    else if (tid < 2 * kMaxC) { if (tid - kMaxC < a.NC) atomicAdd(a.g_b_soft + tid - kMaxC, gb); }
+    {
+        const int k = tid & 127;
+        float* g_w = head ? a.g_w_soft : a.g_w_dense;
+        float* g_b = head ? a.g_b_soft : a.g_b_dense;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c)
+            if (c < a.NC) atomicAdd(g_w + c * kD + k, gw[c]);
+        if (k < a.NC) atomicAdd(g_b + k, gb);
+    }
 }
 
 __device__ __forceinline__ float bce_term(float p, float y) {
@@ -344,25 +448,25 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     }
 }
 
-constexpr size_t kHeadBwdSmem = (2 * kMaxC * kD + 2 * kMaxC + 128 * 132 + 128 * 33) * sizeof(float);
 
 }  // namespace
 
 int head_kernels_init() {
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadBwdSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
     return DCASE_OK;
 }
 
 int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
     DCASE_PROF("head_fwd", s);
-    head_fwd_kernel<<<a.B, 128, 0, s>>>(a);
+    head_fwd_kernel<<<a.B, kHeadThreads, kHeadSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 
 int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
     DCASE_PROF("head_bwd", s);
-    head_bwd_kernel<<<a.B, 128, kHeadBwdSmem, s>>>(a);
+    head_bwd_kernel<<<a.B, kHeadThreads, kHeadSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
