@@ -76,21 +76,32 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
-// x rows t0-1 .. t0+2 (zero padded) of a tile = xs[4][66]; thread t of nt owns elements t, t + nt (nt >= 132)
+// x rows t0-1 .. t0+2 (zero padded) of a tile = xs[4][66]; thread t of 256 owns elements t and (t < 8) t + 256.
+// The tile's (clip, first frame) pair is carried incrementally (32-bit): a 64-bit division per tile and thread was
+// 30 % of the kernel's instructions.
 struct XsRegs { float v0, v1; };
-__device__ __forceinline__ float xs_value(const float* __restrict__ x, long long tile, int T, int i) {
-    const long long r0 = 2 * tile;
-    const long long b = r0 / T;
-    const int t0 = (int)(r0 - b * T);
+struct TilePos {          // tile -> clip b, first frame t0
+    int b, t0;
+    __device__ __forceinline__ void init(long long tile, int T) {
+        const unsigned r0 = (unsigned)(2 * tile);
+        b = (int)(r0 / (unsigned)T);
+        t0 = (int)(r0 - (unsigned)b * (unsigned)T);
+    }
+    __device__ __forceinline__ void advance(int rows, int T) {      // rows >= 0
+        t0 += rows;
+        while (t0 >= T) { t0 -= T; ++b; }
+    }
+};
+__device__ __forceinline__ float xs_value(const float* __restrict__ x, const TilePos& p, int T, int i) {
     const int hr = i / 66, hc = i - hr * 66;
-    const int tt = t0 - 1 + hr, ff = hc - 1;
+    const int tt = p.t0 - 1 + hr, ff = hc - 1;
     const bool ok = tt >= 0 && tt < T && ff >= 0 && ff < 64;
-    return ok ? __ldg(x + (b * T + tt) * 64 + ff) : 0.f;
+    return ok ? __ldg(x + ((long long)p.b * T + tt) * 64 + ff) : 0.f;
 }
-__device__ __forceinline__ XsRegs xs_prefetch(const float* __restrict__ x, long long tile, int T, int t) {
+__device__ __forceinline__ XsRegs xs_prefetch(const float* __restrict__ x, const TilePos& p, int T, int t) {
     XsRegs r;
-    r.v0 = xs_value(x, tile, T, t);
-    r.v1 = t + 256 < 4 * 66 ? xs_value(x, tile, T, t + 256) : 0.f;
+    r.v0 = xs_value(x, p, T, t);
+    r.v1 = t + 256 < 4 * 66 ? xs_value(x, p, T, t + 256) : 0.f;
     return r;
 }
 __device__ __forceinline__ void xs_commit(const XsRegs& r, float* xs, int t) {
@@ -222,8 +233,11 @@ cnn0_fwd_kernel(Cnn0Args a) {
 
     // prologue: operands of the first tile, its MMA0, and the x rows of the second tile in registers
     uint32_t keep_next = 0xffffffffu;       // keep bits (this thread's 32 channels) of the tile whose MMA0 is in flight
+    TilePos pos;                            // position of the tile whose x rows are fetched next
+    pos.init(cur, a.T);
+    const int pos_step = (int)(2 * stride);
     {
-        XsRegs xr = xs_prefetch(a.x, cur, a.T, tid);
+        XsRegs xr = xs_prefetch(a.x, pos, a.T, tid);
         xs_commit(xr, xs, tid);
     }
     __syncthreads();
@@ -240,7 +254,8 @@ cnn0_fwd_kernel(Cnn0Args a) {
     tc::fence_after_sync();
     if (warp == 0) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
     if (drop && half == 0) keep_next = keep_lo[row];
-    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, cur + stride, a.T, tid) : XsRegs{0.f, 0.f};
+    pos.advance(pos_step, a.T);
+    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, pos, a.T, tid) : XsRegs{0.f, 0.f};
 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
@@ -248,11 +263,24 @@ cnn0_fwd_kernel(Cnn0Args a) {
     const float pool_scale = (drop ? 0.25f : 0.125f) * kTruncComp;
     long long prev = -1;
 
+#ifdef DCASE_CNN0_TIMING
+    long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tt;
+    int n_done = 0;
+    const long long t_begin = clock64();
+#define TICK() tt = clock64()
+#define TOCK(i) tm[i] += clock64() - tt
+#else
+#define TICK()
+#define TOCK(i)
+#endif
     for (; cur < n_tiles; cur += stride) {
         const long long nxt = cur + stride;
         const bool has_next = nxt < n_tiles;
         const uint32_t keep = keep_next;
+        TICK();
         tc::mbar_wait(&bars[0], ph0);            // y of `cur` is in TMEM; T0 may be rewritten
+        TOCK(0);
+        TICK();
         ph0 ^= 1;
         tc::fence_after_sync();
         uint32_t keep_hi_next = 0xffffffffu;
@@ -265,8 +293,11 @@ cnn0_fwd_kernel(Cnn0Args a) {
                 keep_lo[row] = r.x;
                 keep_hi_next = r.y;
             }
-            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, nxt + stride, a.T, tid);
+            pos.advance(pos_step, a.T);
+            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, pos, a.T, tid);
         }
+        TOCK(1);
+        TICK();
         if (prev >= 0) {                          // pooled tile `prev`: TMEM -> out; also frees the z buffer
             tc::mbar_wait(&bars[2], ph2);
             ph2 ^= 1;
@@ -282,6 +313,8 @@ cnn0_fwd_kernel(Cnn0Args a) {
                 }
             }
         }
+        TOCK(2);
+        TICK();
         float g[32];
         {
             float y[32];
@@ -293,7 +326,11 @@ cnn0_fwd_kernel(Cnn0Args a) {
             sigmoid32(y, g);
         }
         tc::fence_proxy_async();
+        TOCK(3);
+        TICK();
         __syncthreads();
+        TOCK(4);
+        TICK();
         if (warp == 0) {
             tc::fence_after_sync();
             issue_mma1(tmem + 64, a_a, wb_a);
@@ -306,6 +343,8 @@ cnn0_fwd_kernel(Cnn0Args a) {
             keep_next = half ? keep_hi_next : keep_lo[row];
         }
         tc::mbar_wait(&bars[1], ph1);
+        TOCK(5);
+        TICK();
         ph1 ^= 1;
         tc::fence_after_sync();
         {
@@ -321,6 +360,8 @@ cnn0_fwd_kernel(Cnn0Args a) {
             }
         }
         tc::fence_proxy_async();
+        TOCK(6);
+        TICK();
         __syncthreads();
         if (warp == 0) {                   // MMA2: pooled[n][w] = sum_p z[p][n] P[w][p];  A MN-major (z), B K-major (P)
             tc::fence_after_sync();
@@ -333,8 +374,17 @@ cnn0_fwd_kernel(Cnn0Args a) {
                                     j > 0 ? 1u : 0u);
             tc::umma_commit_elect(&bars[2]);
         }
+        TOCK(7);
+#ifdef DCASE_CNN0_TIMING
+        ++n_done;
+#endif
         prev = cur;
     }
+#ifdef DCASE_CNN0_TIMING
+    if (blockIdx.x == 7 && (tid == 0 || tid == 160))
+        printf("cnn0_fwd tid %d: total %lld tiles %d | wait y %lld | taps %lld | pooled %lld | phase d %lld | sync %lld | mma1+mask+wait %lld | phase f %lld | sync+mma2 %lld\n",
+               tid, clock64() - t_begin, n_done, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7]);
+#endif
     if (prev >= 0) {
         tc::mbar_wait(&bars[2], ph2);
         tc::fence_after_sync();
@@ -409,8 +459,11 @@ cnn0_bwd_kernel(Cnn0Args a) {
     const int bar_id = 1 + grp;
 
     uint32_t keep_next = 0xffffffffu;
+    TilePos pos;
+    pos.init(active ? cur : 0, a.T);
+    const int pos_step = (int)(2 * stride);
     if (active) {
-        XsRegs xr0 = xs_prefetch(a.x, cur, a.T, gt);
+        XsRegs xr0 = xs_prefetch(a.x, pos, a.T, gt);
         xs_commit(xr0, xs, gt);
     }
     __syncthreads();
@@ -429,7 +482,8 @@ cnn0_bwd_kernel(Cnn0Args a) {
     tc::fence_after_sync();
     if (active && issuer) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
     if (active && drop && half == 0) keep_next = keep_lo[row];
-    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, cur + stride, a.T, gt) : XsRegs{0.f, 0.f};
+    pos.advance(pos_step, a.T);
+    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, pos, a.T, gt) : XsRegs{0.f, 0.f};
 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
@@ -461,7 +515,8 @@ cnn0_bwd_kernel(Cnn0Args a) {
                 keep_lo[row] = r.x;
                 keep_hi_next = r.y;
             }
-            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, nxt + stride, a.T, gt);
+            pos.advance(pos_step, a.T);
+            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, pos, a.T, gt);
         }
         float g[32];
         {
