@@ -43,11 +43,16 @@ def _bounds(mask, B):
     return lo, max(lo, hi)
 
 
+# mirror of dcase_step_scalars (include/dcase_b200.h)
+_SCALARS = np.dtype([("seed", "<u8"), ("step", "<u4"), ("cons_weight", "<f4"), ("ema_alpha", "<f4"), ("lr", "<f4"),
+                     ("bc1", "<f4"), ("bc2", "<f4"), ("grad_scale", "<f4"), ("pad", "<f4")])
+
+
 class MeanTeacherEngine(object):
     """Device-resident buffers + launch sequence of one mean-teacher iteration for a fixed batch shape."""
 
     def __init__(self, model, optimizer, ema_model=None, weak_mask=None, strong_mask=None, batch_size=None,
-                 frames=cfg.max_frames, process_group=None):
+                 frames=cfg.max_frames, process_group=None, use_graph=None):
         self.model, self.ema_model, self.optimizer = model, ema_model, optimizer
         self.B, self.T, self.NC = batch_size, frames, model.nclass
         self.To = frames // cfg.pooling_time_ratio
@@ -79,6 +84,17 @@ class MeanTeacherEngine(object):
         self._bind_adam_state(n)
         self._x = torch.empty(B, frames, 64, **f32)
         self._x_ema = torch.empty(B, frames, 64, **f32) if ema_model is not None else None
+        # CUDA-graph replay of step_from_waveforms (single GPU): the ~60 launches of one iteration are captured once
+        # per (waveform, target, scaler) buffer set; everything that changes from step to step (Philox seed / step,
+        # consistency weight, EMA alpha, lr, Adam bias corrections) lives in a 40-byte device struct the kernels read.
+        self.use_graph = (self.world == 1) if use_graph is None else bool(use_graph)
+        if self.use_graph and self.world > 1:
+            raise NotImplementedError("graph replay is wired for single-GPU steps (the NCCL all-reduce runs eagerly)")
+        self._graphs = {}
+        self.graph_launches = 0            # kernels launched through graph replays (bench.py's gpu_launches)
+        assert K.lib().dcase_sizeof_step_scalars() == _SCALARS.itemsize
+        self._sc_host = torch.zeros(_SCALARS.itemsize, dtype=torch.uint8).pin_memory()
+        self._sc_dev = torch.zeros(_SCALARS.itemsize, dtype=torch.uint8, device=dev)
 
     # torch.optim.Adam bookkeeping -----------------------------------------------------------------------
     def _bind_adam_state(self, n):
@@ -116,29 +132,12 @@ class MeanTeacherEngine(object):
         x = batch_input.contiguous()
         xt = ema_batch_input.contiguous() if ema is not None else None
         assert x.shape[0] == self.B and x.shape[-2] == self.T
-        wl, wh = _bounds(self.weak_mask, self.B)
-        sl, sh = _bounds(self.strong_mask, self.B)
         flags = model.forward_flags()
         seed, step = model.next_rng()
-        a = MtArgs()
-        a.x_student = x.data_ptr()
-        a.x_teacher = xt.data_ptr() if xt is not None else None
-        a.target = target.contiguous().data_ptr()
-        a.B, a.T, a.n_class = self.B, self.T, self.NC
-        a.weak_lo, a.weak_hi, a.strong_lo, a.strong_hi = wl, wh, sl, sh
-        a.params_s = model.flat_parameters().data_ptr()
-        a.bn_s = model.flat_bn_running().data_ptr()
+        a = self._mt_args(x, xt, target.contiguous(), flags, seed, step, cons_weight, None)
         if ema is not None:
-            a.params_t = ema.flat_parameters().data_ptr()
-            a.bn_t = ema.flat_bn_running().data_ptr()
-            a.strong_t, a.weak_t = self.strong_t.data_ptr(), self.weak_t.data_ptr()
-            a.ws_t = self.ws_t.data_ptr()
             ema._nbt_pending += 1
         model._nbt_pending += 1
-        a.flags, a.seed, a.step, a.cons_weight, a.scalars = flags, seed, step, float(cons_weight), None
-        a.strong_s, a.weak_s = self.strong_s.data_ptr(), self.weak_s.data_ptr()
-        a.meters, a.d_strong, a.d_weak = self.meters.data_ptr(), self.d_strong.data_ptr(), self.d_weak.data_ptr()
-        a.ws_s, a.grads = self.ws_s.data_ptr(), self.grads.data_ptr()
         if check and self._pending:
             self.check_loss()
         with torch.cuda.device(self.dev):
@@ -155,13 +154,87 @@ class MeanTeacherEngine(object):
             self.meters_event.record()
         self._pending = True
 
+    def _mt_args(self, x, xt, target, flags, seed, step, cons_weight, scalars):
+        model, ema = self.model, self.ema_model
+        wl, wh = _bounds(self.weak_mask, self.B)
+        sl, sh = _bounds(self.strong_mask, self.B)
+        a = MtArgs()
+        a.x_student = x.data_ptr()
+        a.x_teacher = xt.data_ptr() if xt is not None else None
+        a.target = target.data_ptr()
+        a.B, a.T, a.n_class = self.B, self.T, self.NC
+        a.weak_lo, a.weak_hi, a.strong_lo, a.strong_hi = wl, wh, sl, sh
+        a.params_s = model.flat_parameters().data_ptr()
+        a.bn_s = model.flat_bn_running().data_ptr()
+        if ema is not None:
+            a.params_t = ema.flat_parameters().data_ptr()
+            a.bn_t = ema.flat_bn_running().data_ptr()
+            a.strong_t, a.weak_t = self.strong_t.data_ptr(), self.weak_t.data_ptr()
+            a.ws_t = self.ws_t.data_ptr()
+        a.flags, a.seed, a.step, a.cons_weight, a.scalars = flags, seed, step, float(cons_weight), scalars
+        a.strong_s, a.weak_s = self.strong_s.data_ptr(), self.weak_s.data_ptr()
+        a.meters, a.d_strong, a.d_weak = self.meters.data_ptr(), self.d_strong.data_ptr(), self.d_weak.data_ptr()
+        a.ws_s, a.grads = self.ws_s.data_ptr(), self.grads.data_ptr()
+        return a
+
+    def _graph_step(self, wave, target, mean, std, cons_weight, global_step_after, check):
+        model, ema = self.model, self.ema_model
+        if check and self._pending:
+            self.check_loss()
+        target = target.contiguous()
+        g = self.optimizer.param_groups[0]
+        seed, step = model.next_rng()
+        t = self._adam_step_count() + 1
+        sc = np.zeros(1, dtype=_SCALARS)
+        sc["seed"], sc["step"], sc["cons_weight"] = seed, step, cons_weight
+        sc["ema_alpha"] = min(1 - 1 / (global_step_after + 1), 0.999)
+        sc["lr"] = g["lr"]
+        sc["bc1"], sc["bc2"] = 1.0 - g["betas"][0] ** t, 1.0 - g["betas"][1] ** t
+        sc["grad_scale"] = 1.0
+        with torch.cuda.device(self.dev):
+            self._sc_host.copy_(torch.from_numpy(sc.view(np.uint8)))
+            self._sc_dev.copy_(self._sc_host, non_blocking=True)
+            key = (wave.data_ptr(), tuple(wave.shape), wave.dtype, target.data_ptr(), mean.data_ptr(), std.data_ptr(),
+                   model.forward_flags(), g["betas"], g["eps"])
+            entry = self._graphs.get(key)
+            if entry is None:
+                graph = torch.cuda.CUDAGraph()
+                l0 = K.launch_count()
+                with torch.cuda.graph(graph):
+                    scp = self._sc_dev.data_ptr()
+                    amp = K.logmel_fwd(wave)
+                    if ema is not None:
+                        x, x_ema = K.logmel_finish(amp, mean, std, self.T, noisy=True, scalars=self._sc_dev,
+                                                   out_clean=self._x, out_noisy=self._x_ema)
+                    else:
+                        x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None
+                    K.mt_fwd_bwd(self._mt_args(x, x_ema, target, model.forward_flags(), 0, 0, 0.0, scp))
+                    K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
+                                    ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
+                                    beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
+                    self.meters_host.copy_(self.meters, non_blocking=True)
+                entry = (graph, K.launch_count() - l0)
+                self._graphs[key] = entry
+            entry[0].replay()
+            self.graph_launches += entry[1]
+            self.meters_event.record()
+        torch._foreach_add_(self._steps, 1.0)
+        model._nbt_pending += 1
+        if ema is not None:
+            ema._nbt_pending += 1
+        self._pending = True
+
     def step_from_waveforms(self, wave, target, mean, std, cons_weight, global_step_after, check=True):
         """The whole hot path for one batch of raw clips already on the device: wave [B, L] (float32 or int16
         PCM) -> calculate_mel_spec -> noise / dB / pad / z-score (clean + noisy) -> mean-teacher iteration."""
+        if self.use_graph:
+            return self._graph_step(wave, target, mean, std, cons_weight, global_step_after, check)
         amp = K.logmel_fwd(wave)
         seed, _ = self.model._rng_seed, 0
         if self.ema_model is not None:
-            x, x_ema = K.logmel_finish(amp, mean, std, self.T, noisy=True, seed=seed ^ 0x5DEECE66D,
+            # same (seed, step) as the dropout of this iteration (next_rng in step()); the noise has its own Philox
+            # stream id, and the graph path reads the very same pair from the device scalars
+            x, x_ema = K.logmel_finish(amp, mean, std, self.T, noisy=True, seed=seed,
                                        step=self.model._rng_step & 0xFFFFFFFF, out_clean=self._x, out_noisy=self._x_ema)
         else:
             x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None

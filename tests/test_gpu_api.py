@@ -169,3 +169,47 @@ def test_train_three_steps_match_oracle(pkg, cuda_device):
     for name in ("Loss", "Strong loss", "weak_class_loss", "Consistency strong", "Consistency weak"):
         assert abs(meters[name].val - last[name]) <= 1e-4 * max(1.0, abs(last[name])), name
     assert int(student.state_dict()["cnn"]["batchnorm2.num_batches_tracked"]) == 3
+
+
+def test_graph_replay_matches_eager_steps(pkg, cuda_device):
+    """MeanTeacherEngine.step_from_waveforms replayed from a CUDA graph (per-step scalars read from device memory)
+    vs the same three iterations launched eagerly: same Philox seed / step, so the two runs differ only by the order of
+    floating-point atomics."""
+    cfg, CRNN, bmain = pkg["cfg"], pkg["CRNN"], pkg["main"]
+    from dcase2019_task4_b200 import synth
+    B, T, L = 8, 64, 511 * 64
+    waves, events = synth.make_clips(3 * B, seed=7, n_samples=L)
+    waves = torch.from_numpy(waves.reshape(3, B, L)).to(cuda_device)
+    tgt = (torch.rand(3, B, T // 8, 10, generator=torch.Generator().manual_seed(3)) < 0.2).float()
+    tgt[:, 2:6] = -1
+    tgt = tgt.to(cuda_device)
+    mean = torch.full((64,), -30.0, device=cuda_device)
+    std = torch.full((64,), 12.0, device=cuda_device)
+    ps, pt = ocrnn.init_params(seed=41), ocrnn.init_params(seed=42)
+    results = []
+    for use_graph in (False, True):
+        student, teacher = CRNN(**cfg.crnn_kwargs), CRNN(**cfg.crnn_kwargs)
+        _load(student, ps)
+        _load(teacher, pt)
+        for q in teacher.parameters():
+            q.detach_()
+        student, teacher = student.train().cuda(), teacher.train().cuda()
+        student._rng_seed, student._rng_step = 1234567, 0
+        opt = torch.optim.Adam(student.parameters(), lr=0.001, betas=(0.9, 0.999))
+        eng = bmain.MeanTeacherEngine(student, opt, teacher, slice(2), slice(6, 8), B, T, use_graph=use_graph)
+        losses = []
+        for i in range(3):
+            eng.step_from_waveforms(waves[i], tgt[i], mean, std, 0.5, i + 1, check=False)
+            losses.append(eng.read_meters()["Loss"])
+        if use_graph:
+            assert len(eng._graphs) == 3 and eng.graph_launches > 0
+        results.append((losses, student.flat_parameters().detach().cpu().clone(),
+                        teacher.flat_parameters().detach().cpu().clone(), float(opt.state_dict()["state"][0]["step"])))
+    (l0, s0, t0, n0), (l1, s1, t1, n1) = results
+    assert n0 == n1 == 3.0
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(a)), (l0, l1)
+    for a, b in ((s0, s1), (t0, t1)):
+        d = (a.double() - b.double()).abs()
+        assert float(d.max()) <= 6e-3 + 1e-6
+        assert int((d > 1e-4).sum()) <= 0.005 * d.numel()
