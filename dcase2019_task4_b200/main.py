@@ -12,6 +12,7 @@ batch become one asynchronous 32-byte copy whose assertion is checked one batch 
 ``main_simple_CRNN.train`` (main_simple_CRNN.py:31-82) is the same body with ``ema_model=None``.
 """
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -87,7 +88,7 @@ class MeanTeacherEngine(object):
         # CUDA-graph replay of step_from_waveforms (single GPU): the ~60 launches of one iteration are captured once
         # per (waveform, target, scaler) buffer set; everything that changes from step to step (Philox seed / step,
         # consistency weight, EMA alpha, lr, Adam bias corrections) lives in a 40-byte device struct the kernels read.
-        self.use_graph = (self.world == 1) if use_graph is None else bool(use_graph)
+        self.use_graph = (self.world == 1 and os.environ.get("DCASE_NO_GRAPH", "0") != "1") if use_graph is None else bool(use_graph)
         if self.use_graph and self.world > 1:
             raise NotImplementedError("graph replay is wired for single-GPU steps (the NCCL all-reduce runs eagerly)")
         self._graphs = {}

@@ -36,7 +36,8 @@ def main():
         p.detach_()
     crnn, crnn_ema = crnn.train().cuda(), crnn_ema.train().cuda()
     opt = torch.optim.Adam(crnn.parameters(), lr=0.001, betas=(0.9, 0.999))
-    eng = MeanTeacherEngine(crnn, opt, crnn_ema, slice(6), slice(18, 24), 24, 864)
+    eng = MeanTeacherEngine(crnn, opt, crnn_ema, slice(6), slice(18, 24), 24, 864,
+                            use_graph=False)      # ncu needs the eager launches (it invalidates stream capture)
     for i in range(args.steps):
         eng.step_from_waveforms(wave_dev[i % 2], target_dev[i % 2], mean, std, 0.1, i + 1, check=False)
     if args.mel_clips:
