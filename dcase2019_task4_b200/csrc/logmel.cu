@@ -54,6 +54,13 @@ __device__ __forceinline__ float load_sample<int16_t>(const int16_t* p, int i) {
     return (float)__ldg(p + i) * (1.0f / 32768.0f);  // soundfile's int16 -> float scaling
 }
 
+// sqrt(x) = x * rsqrt(x) (2 ulp), exact 0 for x = 0: the IEEE sqrtf sequence was 9 % of the kernel's instructions
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return x > 0.f ? x * r : 0.f;
+}
+
 template <typename WaveT>
 __global__ void __launch_bounds__(256, 3)
 stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, float* __restrict__ mel_amp) {
@@ -75,6 +82,13 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, flo
         span[i] = (s >= 0 && s < L) ? load_sample<WaveT>(clip, s) : 0.f;
     }
     __syncthreads();
+
+    // this thread's run of Slaney weights (<= 22 of them) is the same for every frame: the first 16 are loaded once per
+    // CTA and kept in registers, the few longer runs read their tail through L1
+    const int4 mel_e = __ldg(tab.mel_work + (tid & 127));           // {bin start, weight offset, count, band}
+    float mel_wt[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mel_wt[i] = i < mel_e.z ? __ldg(tab.mel_w + mel_e.y + i) : 0.f;
 
     const int n_pairs = min(kFramesPerCta, T - t0 + 1) / 2;  // frames [t0, T) in pairs (odd tail rounds up)
     for (int p = 0; p < n_pairs; ++p) {
@@ -108,26 +122,26 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, flo
             const cf32 zn = bufB[fft_pad((kNfft - k) & (kNfft - 1))];
             const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
             const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
-            mag[k] = sqrtf(ar * ar + ai * ai);
-            mag[kMagPitch + k] = sqrtf(br * br + bi * bi);
+            mag[k] = fast_sqrt(ar * ar + ai * ai);
+            mag[kMagPitch + k] = fast_sqrt(br * br + bi * bi);
         }
         __syncthreads();
         // sparse Slaney mel projection (1,983 non-zeros per frame), load balanced: 128 threads per frame, each owns
-        // a contiguous run of <= 16 weights inside one band (host-built table); band owners combine the partials
+        // a contiguous run of weights inside one band (host-built table); band owners combine the partials
         {
-            const int fr = tid >> 7, slot = tid & 127;
-            const int4 e = __ldg(tab.mel_work + slot);          // {bin start, weight offset, count, -}
-            const float* w = tab.mel_w + e.y;
-            const float* mg = mag + fr * kMagPitch + e.x;
+            const int fr = tid >> 7;
+            const float* mg = mag + fr * kMagPitch + mel_e.x;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int i = 0;
-            for (; i + 3 < e.z; i += 4) {
-                a0 = fmaf(__ldg(w + i), mg[i], a0);
-                a1 = fmaf(__ldg(w + i + 1), mg[i + 1], a1);
-                a2 = fmaf(__ldg(w + i + 2), mg[i + 2], a2);
-                a3 = fmaf(__ldg(w + i + 3), mg[i + 3], a3);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                if (i < mel_e.z) {                      // zero weights pad the run: mg stays inside the padded buffer
+                    a0 = fmaf(mel_wt[i], mg[i], a0);
+                    a1 = fmaf(mel_wt[i + 1], mg[i + 1], a1);
+                    a2 = fmaf(mel_wt[i + 2], mg[i + 2], a2);
+                    a3 = fmaf(mel_wt[i + 3], mg[i + 3], a3);
+                }
             }
-            for (; i < e.z; ++i) a0 = fmaf(__ldg(w + i), mg[i], a0);
+            for (int i = 16; i < mel_e.z; ++i) a0 = fmaf(__ldg(tab.mel_w + mel_e.y + i), mg[i], a0);
             part[tid] = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
