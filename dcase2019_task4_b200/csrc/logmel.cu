@@ -77,9 +77,23 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, flo
     const WaveT* clip = wave + (size_t)b * L;
 
     const int s0 = t0 * kHop - kNfft / 2;
-    for (int i = tid; i < kSpan; i += 256) {
-        int s = reflect_index(s0 + i, L);
-        span[i] = (s >= 0 && s < L) ? load_sample<WaveT>(clip, s) : 0.f;
+    if (sizeof(WaveT) == 4) {
+        // float clips: asynchronous 4-byte copies straight into shared memory (all 22 per thread in flight at once)
+        const uint32_t span_a = (uint32_t)__cvta_generic_to_shared(span);
+        for (int i = tid; i < kSpan; i += 256) {
+            const int s = reflect_index(s0 + i, L);
+            if (s >= 0 && s < L)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(span_a + 4u * i), "l"(clip + s) : "memory");
+            else
+                span[i] = 0.f;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+        for (int i = tid; i < kSpan; i += 256) {
+            const int s = reflect_index(s0 + i, L);
+            span[i] = (s >= 0 && s < L) ? load_sample<WaveT>(clip, s) : 0.f;
+        }
     }
     __syncthreads();
 
