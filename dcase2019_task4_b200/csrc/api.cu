@@ -426,6 +426,7 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
             cb.A[2 * d + 1] = dgh_d; cb.out[2 * d + 1] = grads + o.b_hh[l][d];
         }
         gb.n = 6; gb.split = BT >= 512 ? 16 : 1; gb.mode = 1;
+        gb.psplit[2] = gb.psplit[5] = 1;      // d_in: K = 3H = 192 needs no K split (every slice costs an atomic per element)
         cb.n = 4; cb.M = BT; cb.N = 3 * kH;
         DCASE_TRY(launch_sgemm_batch(gb, s));
         DCASE_TRY(launch_colsum_batch(cb, s));

@@ -34,14 +34,18 @@ __global__ void __launch_bounds__(256)
 sgemm_batch_kernel(GemmBatch g) {
     __shared__ float As[16][68];
     __shared__ float Bs[16][68];
-    const GemmProblem& pr = g.p[blockIdx.z / g.split];
-    const int ks = blockIdx.z % g.split;
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) pi += (i < g.n && (int)blockIdx.z >= g.zoff[i]) ? 1 : 0;
+    const GemmProblem& pr = g.p[pi];
+    const int ks = blockIdx.z - g.zoff[pi];
+    const int nsplit = g.zoff[pi + 1] - g.zoff[pi];
     const int M = pr.M, N = pr.N, K = pr.K;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     if (m0 >= M || n0 >= N) return;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    const int kchunk = ((K + g.split - 1) / g.split + 15) / 16 * 16;
+    const int kchunk = ((K + nsplit - 1) / nsplit + 15) / 16 * 16;
     const int kbeg = ks * kchunk;
     const int kend = min(K, kbeg + kchunk);
     const float* __restrict__ A = pr.A;
@@ -343,12 +347,18 @@ gru_bwd_kernel(GruBwdArgs a) {
 
 }  // namespace
 
-int launch_sgemm_batch(const GemmBatch& g, cudaStream_t s) {
+int launch_sgemm_batch(const GemmBatch& g_in, cudaStream_t s) {
     DCASE_PROF("sgemm", s);
+    GemmBatch g = g_in;
     int maxM = 0, maxN = 0;
     for (int i = 0; i < g.n; ++i) { maxM = g.p[i].M > maxM ? g.p[i].M : maxM; maxN = g.p[i].N > maxN ? g.p[i].N : maxN; }
     if (g.n <= 0 || maxM <= 0 || maxN <= 0) return DCASE_OK;
-    dim3 grid((maxN + 63) / 64, (maxM + 63) / 64, g.n * g.split);
+    g.zoff[0] = 0;
+    for (int i = 0; i < 8; ++i) {
+        const int sp = i < g.n ? (g.psplit[i] > 0 ? g.psplit[i] : g.split) : 0;
+        g.zoff[i + 1] = g.zoff[i] + sp;
+    }
+    dim3 grid((maxN + 63) / 64, (maxM + 63) / 64, g.zoff[g.n]);
     sgemm_batch_kernel<<<grid, 256, 0, s>>>(g);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;

@@ -39,8 +39,10 @@ struct GemmProblem {
 struct GemmBatch {
     GemmProblem p[8];
     int n;          // problems in this launch
-    int split;      // K slices per problem
+    int split;      // default K slices per problem
     int mode;       // 0: C = result (split must be 1); 1: atomicAdd into C
+    int psplit[8];  // per-problem K slices (0 = use `split`); problems with a short K need none
+    int zoff[9];    // filled by launch_sgemm_batch: first blockIdx.z of every problem
 };
 struct ColsumBatch {
     const float* A[4];   // [M][N] each
