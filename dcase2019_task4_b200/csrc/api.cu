@@ -142,7 +142,7 @@ WsLayout ws_layout(int B, int T, int NC) {
     add("acc0", kCnn0AccFloats); add("s12_1", 128); add("s12_2", 128);
     L.acc_bytes = L.total - L.acc_off;
     add("d_rnn1", BT * 128); add("d_rnn0", BT * 128);
-    add("dgi", 2 * BT * 192); add("dgh", 2 * BT * 192);
+    add("dgi0", 2 * BT * 192); add("dgh0", 2 * BT * 192); add("dgi1", 2 * BT * 192); add("dgh1", 2 * BT * 192);
     add("d_out2", BT * 64);
     add("dy2", n1); add("d_out1", n1); add("dy1", n0); add("d_out0", n0);
     return L;
@@ -228,6 +228,10 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     DCASE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_bwd_fork[i], cudaEventDisableTiming));
+        DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_bwd_join[i], cudaEventDisableTiming));
+    }
     DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_loss_scratch, kLossScratchBytes));
     DCASE_CUDA_CHECK(cudaMemset(ctx->d_loss_scratch, 0, kLossScratchBytes));
     int rc = dcase_logmel_tables_create(ctx);
@@ -249,6 +253,7 @@ int dcase_ctx_destroy(dcase_ctx* ctx) {
     cudaStreamDestroy(ctx->aux_stream);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_bwd_fork[i]); cudaEventDestroy(ctx->ev_bwd_join[i]); }
     delete ctx;
     return DCASE_OK;
 }
@@ -394,11 +399,15 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
     DCASE_TRY(launch_head_bwd(h, s));
 
     // ---- BiGRU BPTT, layer 1 then layer 0 ----
-    float* dgi = wsp<float>(ws, L, "dgi");
-    float* dgh = wsp<float>(ws, L, "dgh");
+    // Only the input gradient d_in feeds the next kernel of the chain; the weight / bias gradients of both directions
+    // (4 split-K GEMMs + 4 column sums per layer) run on the context's second stream beside the next layer's recurrence
+    // (latency bound, 48 CTAs) and are joined at the end of the backward.
     const char* sv[2][5] = {{"s0_r", "s0_z", "s0_n", "s0_hn", "s0_hp"}, {"s1_r", "s1_z", "s1_n", "s1_hn", "s1_hp"}};
+    cudaStream_t aux = ctx->aux_stream;
     for (int l = 1; l >= 0; --l) {
         const int nin = l == 0 ? kC : 2 * kH;
+        float* dgi = wsp<float>(ws, L, l == 1 ? "dgi1" : "dgi0");
+        float* dgh = wsp<float>(ws, L, l == 1 ? "dgh1" : "dgh0");
         const float* d_out = wsp<float>(ws, L, l == 1 ? "d_rnn1" : "d_rnn0");
         const float* xin = wsp<float>(ws, L, l == 1 ? "rnn0" : "out2");
         float* d_in = wsp<float>(ws, L, l == 1 ? "d_rnn0" : "d_out2");
@@ -409,27 +418,30 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
         g.save_n = wsp<float>(ws, L, sv[l][2]); g.save_hn = wsp<float>(ws, L, sv[l][3]);
         g.save_hp = wsp<float>(ws, L, sv[l][4]);
         g.dgi = dgi; g.dgh = dgh; g.B = B; g.T = To;
-        DCASE_TRY(launch_gru_bwd(g, s));
-        // weight / bias / input gradients of both directions: 6 GEMMs in one launch + 4 column sums in one launch
         DCASE_CUDA_CHECK(cudaMemsetAsync(d_in, 0, (size_t)BT * nin * sizeof(float), s));
-        GemmBatch gb{};
+        DCASE_TRY(launch_gru_bwd(g, s));
+        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_bwd_fork[l], s));
+        DCASE_CUDA_CHECK(cudaStreamWaitEvent(aux, ctx->ev_bwd_fork[l], 0));
+        GemmBatch gin{}, gw{};
         ColsumBatch cb{};
         for (int d = 0; d < 2; ++d) {
             const float* dgi_d = dgi + (size_t)d * BT * 3 * kH;
             const float* dgh_d = dgh + (size_t)d * BT * 3 * kH;
             const float* hp_d = g.save_hp + (size_t)d * BT * kH;
-            // dW_ih [3H][nin] = dgi^T X ;  dW_hh [3H][H] = dgh^T Hprev ;  d_in [BT][nin] += dgi W_ih
-            gb.p[3 * d + 0] = GemmProblem{3 * kH, nin, BT, dgi_d, 1, 3 * kH, xin, nin, 1, grads + o.w_ih[l][d], nin, nullptr};
-            gb.p[3 * d + 1] = GemmProblem{3 * kH, kH, BT, dgh_d, 1, 3 * kH, hp_d, kH, 1, grads + o.w_hh[l][d], kH, nullptr};
-            gb.p[3 * d + 2] = GemmProblem{BT, nin, 3 * kH, dgi_d, 3 * kH, 1, params + o.w_ih[l][d], nin, 1, d_in, nin, nullptr};
+            // d_in [BT][nin] += dgi W_ih ;  dW_ih [3H][nin] = dgi^T X ;  dW_hh [3H][H] = dgh^T Hprev
+            gin.p[d] = GemmProblem{BT, nin, 3 * kH, dgi_d, 3 * kH, 1, params + o.w_ih[l][d], nin, 1, d_in, nin, nullptr};
+            gw.p[2 * d + 0] = GemmProblem{3 * kH, nin, BT, dgi_d, 1, 3 * kH, xin, nin, 1, grads + o.w_ih[l][d], nin, nullptr};
+            gw.p[2 * d + 1] = GemmProblem{3 * kH, kH, BT, dgh_d, 1, 3 * kH, hp_d, kH, 1, grads + o.w_hh[l][d], kH, nullptr};
             cb.A[2 * d] = dgi_d; cb.out[2 * d] = grads + o.b_ih[l][d];
             cb.A[2 * d + 1] = dgh_d; cb.out[2 * d + 1] = grads + o.b_hh[l][d];
         }
-        gb.n = 6; gb.split = BT >= 512 ? 16 : 1; gb.mode = 1;
-        gb.psplit[2] = gb.psplit[5] = 1;      // d_in: K = 3H = 192 needs no K split (every slice costs an atomic per element)
+        gin.n = 2; gin.split = 1; gin.mode = 1;
+        gw.n = 4; gw.split = BT >= 512 ? 16 : 1; gw.mode = 1;
         cb.n = 4; cb.M = BT; cb.N = 3 * kH;
-        DCASE_TRY(launch_sgemm_batch(gb, s));
-        DCASE_TRY(launch_colsum_batch(cb, s));
+        DCASE_TRY(launch_sgemm_batch(gin, s));
+        DCASE_TRY(launch_sgemm_batch(gw, aux));
+        DCASE_TRY(launch_colsum_batch(cb, aux));
+        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_bwd_join[l], aux));
     }
 
     // ---- CNN blocks 2, 1 ----
@@ -466,6 +478,7 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
                                        params + o.conv_b[0], fold0, params + o.glu_w[0], acc0, grads + o.conv_w[0],
                                        grads + o.conv_b[0], grads + o.bn_w[0], grads + o.bn_b[0], grads + o.glu_w[0],
                                        grads + o.glu_b[0], s));
+    for (int l = 0; l < 2; ++l) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_bwd_join[l], 0));
     return DCASE_OK;
 }
 
