@@ -228,7 +228,7 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     DCASE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
         DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_bwd_fork[i], cudaEventDisableTiming));
         DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_bwd_join[i], cudaEventDisableTiming));
     }
@@ -253,7 +253,7 @@ int dcase_ctx_destroy(dcase_ctx* ctx) {
     cudaStreamDestroy(ctx->aux_stream);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_bwd_fork[i]); cudaEventDestroy(ctx->ev_bwd_join[i]); }
+    for (int i = 0; i < 4; ++i) { cudaEventDestroy(ctx->ev_bwd_fork[i]); cudaEventDestroy(ctx->ev_bwd_join[i]); }
     delete ctx;
     return DCASE_OK;
 }
@@ -465,7 +465,11 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
                                       grads + o.glu_b[l], sms, s));
         DCASE_TRY(launch_bn_bwd_apply(dy, ypre, n_pix, bn, params + o.bn_w[l], s12, grads + o.bn_w[l],
                                       grads + o.bn_b[l], grads + o.conv_b[l], sms, s));
-        DCASE_TRY(launch_conv_wgrad(dy, lin, B, T_l, F_l, grads + o.conv_w[l], sms, s));
+        // the weight gradient only feeds the optimizer: second stream, beside the data gradient and the next block
+        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_bwd_fork[1 + l], s));
+        DCASE_CUDA_CHECK(cudaStreamWaitEvent(aux, ctx->ev_bwd_fork[1 + l], 0));
+        DCASE_TRY(launch_conv_wgrad(dy, lin, B, T_l, F_l, grads + o.conv_w[l], sms, aux));
+        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_bwd_join[1 + l], aux));
         DCASE_TRY(launch_conv3x3(dy, B, T_l, F_l, wd, nullptr, d_in, nullptr, sms, s));
     }
 
@@ -478,7 +482,7 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
                                        params + o.conv_b[0], fold0, params + o.glu_w[0], acc0, grads + o.conv_w[0],
                                        grads + o.conv_b[0], grads + o.bn_w[0], grads + o.bn_b[0], grads + o.glu_w[0],
                                        grads + o.glu_b[0], s));
-    for (int l = 0; l < 2; ++l) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_bwd_join[l], 0));
+    for (int l = 0; l < 4; ++l) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_bwd_join[l], 0));
     return DCASE_OK;
 }
 

@@ -16,8 +16,8 @@ struct dcase_ctx {
     // second stream + events: the teacher forward runs concurrently with the student forward (dcase_mt_fwd_bwd)
     cudaStream_t aux_stream;
     cudaEvent_t ev_fork, ev_join;
-    // backward: the GRU weight-gradient GEMMs leave the critical path (dcase_crnn_backward)
-    cudaEvent_t ev_bwd_fork[2], ev_bwd_join[2];
+    // backward: the GRU and conv weight-gradient kernels leave the critical path (dcase_crnn_backward)
+    cudaEvent_t ev_bwd_fork[4], ev_bwd_join[4];   // [0,1] GRU layers, [2,3] conv blocks 1, 2
     // scratch of the loss kernel: per-CTA partial sums + completion ticket (head_loss.cuh)
     float* d_loss_scratch;
     // host copy of the dense filterbank for dcase_mel_filterbank()
