@@ -460,9 +460,8 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
         const float* lin = wsp<float>(ws, L, names[l][5]);
         const float* wd = wsp<float>(ws, L, names[l][6]);
         float* d_in = wsp<float>(ws, L, names[l][7]);
-        DCASE_TRY(launch_glu_pool_bwd(ypre, n_pix, F_l, bn, params + o.bn_w[l], params + o.bn_b[l], params + o.glu_w[l],
-                                      params + o.glu_b[l], drop(l), d_out, dy, s12, grads + o.glu_w[l],
-                                      grads + o.glu_b[l], sms, s));
+        DCASE_TRY(launch_glu_pool_bwd(ypre, n_pix, F_l, bn, wsp<float>(ws, L, l == 1 ? "gluimg1" : "gluimg2"), drop(l), d_out, dy,
+                                      s12, grads + o.glu_w[l], grads + o.glu_b[l], sms, s));
         DCASE_TRY(launch_bn_bwd_apply(dy, ypre, n_pix, bn, params + o.bn_w[l], s12, grads + o.bn_w[l],
                                       grads + o.bn_b[l], grads + o.conv_b[l], sms, s));
         // the weight gradient only feeds the optimizer: second stream, beside the data gradient and the next block

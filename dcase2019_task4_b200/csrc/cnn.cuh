@@ -48,17 +48,18 @@ int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* 
 int launch_conv_w_prep(const float* w /*[64][64][3][3]*/, float* img_fwd, float* img_dgrad, cudaStream_t s);
 int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, const float* bias,
                    float* out, double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
-// GLU forward operand image written by bn_finalize (bytes): W' 16 KB | P 8 KB | {bias', exp scale, exp shift} 768 B
+// GLU operand image written by bn_finalize (bytes): W' 16 KB | P 8 KB | {bias', exp scale, exp shift} 768 B |
+// Wm 16 KB (the un-folded Wg as MN-major operand of the backward's dY = DL Wg)
 constexpr int kGluImgP = 16384;
 constexpr int kGluImgMisc = 16384 + 8192;
-constexpr int kGluImgBytes = 16384 + 8192 + 768;
+constexpr int kGluImgWm = 16384 + 8192 + 768;
+constexpr int kGluImgBytes = kGluImgWm + 16384;
 int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma, const float* beta,
                        float* running, int training, float* bn, const float* glu_w, const float* glu_b, int F,
                        float* glu_img /*nullable, kGluImgBytes*/, cudaStream_t s);
-int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* bn, const float* gamma,
-                        const float* beta, const float* glu_w, const float* glu_b, DropoutCfg drop,
-                        const float* d_out, float* d_y, float* s12 /*[2][64]*/, float* g_glu_w, float* g_glu_b,
-                        int num_sms, cudaStream_t s);
+int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_img, DropoutCfg drop,
+                        const float* d_out, float* d_y, float* s12 /*[2][64]*/, float* g_glu_w, float* g_glu_b, int num_sms,
+                        cudaStream_t s);
 int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const float* bn, const float* gamma,
                         const float* s12, float* g_gamma, float* g_beta, float* g_conv_b, int num_sms,
                         cudaStream_t s);
