@@ -90,6 +90,8 @@ class MeanTeacherEngine(object):
         # consistency weight, EMA alpha, lr, Adam bias corrections) lives in a 40-byte device struct the kernels read.
         self.use_graph = (self.world == 1 and os.environ.get("DCASE_NO_GRAPH", "0") != "1") if use_graph is None else bool(use_graph)
         if self.use_graph and self.world > 1:
+            # capturing the NCCL all-reduce with the rest of the iteration hung on the 2-GPU box (round 1 experiment),
+            # so data-parallel steps launch eagerly
             raise NotImplementedError("graph replay is wired for single-GPU steps (the NCCL all-reduce runs eagerly)")
         self._graphs = {}
         self.graph_launches = 0            # kernels launched through graph replays (bench.py's gpu_launches)
