@@ -34,6 +34,10 @@ STEP_FLOPS_PER_CLIP = 4.7232e9
 LAYER_FLOPS_PER_CLIP = {"conv0": 63.70e6, "glu0": 452.98e6, "conv1": 509.61e6, "glu1": 56.62e6,
                         "conv2": 63.70e6, "glu2": 7.08e6}
 MEL_BYTES_PER_CLIP = 441000 * 4 + 864 * 64 * 4
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 24 from the committed `ncu --set full` capture
+# (profiles/r1_ncu_summary_final.csv); bench.py cannot run under ncu, so `roofline.traffic` quotes the capture
+NCU_DRAM_BYTES = {"cnn0_fused_fwd": 5.66e6, "cnn0_fused_bwd": 47.85e6, "stft_mel": 42.47e6, "conv3x3_fwd_l1": 46.59e6,
+                  "conv3x3_dgrad_l1": 46.59e6, "conv3x3_wgrad_l1": 90.74e6, "glu_pool_fwd_l1": 42.53e6}
 
 
 def kernel_flops_per_launch(name, B):
@@ -320,7 +324,10 @@ def run_b200(args, rank, local_rank, world):
         roof = {"bound": "tensor", "achieved": dom_flops / dom_avg_s / 1e12, "peak": peaks["tf_sustained"],
                 "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"traffic": None, "kernel": dom_name, "kernel_ms": dom_ms / dom_cnt,
+    traffic = NCU_DRAM_BYTES.get(dom_name)
+    roof.update({"traffic": traffic * (B_PER_GPU / 24.0) if traffic else None,
+                 "traffic_source": "profiles/r1_ncu_summary_final.csv (ncu --set full, bytes per launch)" if traffic else None,
+                 "kernel": dom_name, "kernel_ms": dom_ms / dom_cnt,
                  "kernel_share_of_step": dom_ms / total_prof, "peak_source": peaks["source"] + " (sustained bf16 dense)",
                  "step_tensor_frac": (value / world) * STEP_FLOPS_PER_CLIP / 1e12 / peaks["tf_sustained"],
                  "per_kernel_ms": {k: round(ms / n_prof, 4) for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}})
