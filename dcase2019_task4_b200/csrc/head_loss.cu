@@ -11,36 +11,6 @@ namespace {
 constexpr int kD = 128;        // 2 * hidden
 constexpr int kMaxC = 16;      // class slots
 
-__device__ __forceinline__ void head_row_forward(const float* __restrict__ x, const uint4 keep, int drop,
-                                                 const float* __restrict__ Wd, const float* __restrict__ Ws,
-                                                 const float* __restrict__ bd, const float* __restrict__ bs, int NC,
-                                                 float (&ld)[kMaxC], float (&ls)[kMaxC], float* xm_row) {
-#pragma unroll
-    for (int c = 0; c < kMaxC; ++c) { ld[c] = bd[c]; ls[c] = bs[c]; }
-    const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
-#pragma unroll 4
-    for (int k4 = 0; k4 < kD / 4; ++k4) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(x) + k4);
-        if (drop) {
-            const uint32_t bits = kw[k4 >> 3] >> ((4 * k4) & 31);
-            v.x = (bits & 1u) ? 2.f * v.x : 0.f;
-            v.y = (bits & 2u) ? 2.f * v.y : 0.f;
-            v.z = (bits & 4u) ? 2.f * v.z : 0.f;
-            v.w = (bits & 8u) ? 2.f * v.w : 0.f;
-        }
-        if (xm_row) *reinterpret_cast<float4*>(xm_row + 4 * k4) = v;
-#pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
-            if (c < NC) {
-                const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
-                const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
-                ld[c] = fmaf(v.x, wd.x, fmaf(v.y, wd.y, fmaf(v.z, wd.z, fmaf(v.w, wd.w, ld[c]))));
-                ls[c] = fmaf(v.x, ws.x, fmaf(v.y, ws.y, fmaf(v.z, ws.z, fmaf(v.w, ws.w, ls[c]))));
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ void softmax_classes(const float (&ls)[kMaxC], int NC, float (&a_raw)[kMaxC]) {
     float mx = -INFINITY;
 #pragma unroll

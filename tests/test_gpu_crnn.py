@@ -218,3 +218,16 @@ def test_full_size_eval_and_train_step_properties(K, cuda_device):
     assert torch.equal(a1, a2)
     a3, _ = K.crnn_forward(x.to(dev), pf, bn.clone(), FLAGS_TRAIN, ws, seed=1, step=2)
     assert not torch.equal(a1, a3)
+
+
+def test_sequence_longer_than_the_resident_gru_fails_loudly(K, cuda_device):
+    """The GRU kernels keep a sequence's operands in shared memory (T/8 <= 136 output frames, DESIGN.md section 4);
+    a longer input must raise, not silently fall back."""
+    from dcase2019_task4_b200._lib import DcaseError
+    B, T = 1, 8 * 144
+    p = ocrnn.init_params(seed=1)
+    ws = K.new_workspace(B, T, 10, cuda_device)
+    x = torch.zeros(B, T, 64, device=cuda_device)
+    with pytest.raises(DcaseError):
+        K.crnn_forward(x, H.flat_params(p).to(cuda_device), H.bn_running_flat(_buffers(0)).to(cuda_device), 0, ws)
+        torch.cuda.synchronize()

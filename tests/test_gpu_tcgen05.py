@@ -62,3 +62,19 @@ def test_umma_shifted_operand(cuda_device, pitch, shift):
     rows = torch.tensor([shift + (m // 8) * pitch + (m % 8) for m in range(128)], device=cuda_device)
     ref = _tf32(A[rows]).double() @ _tf32(B).double().t()
     assert float((D.double() - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+
+
+def test_umma_issue_microbenchmark_matches_operand_floor(cuda_device):
+    """dcase_bench_umma (tools/umma_bench.py): a tf32 MMA can never beat max(M,128) N / 256 cycles, nor the 128 B/cycle
+    shared-memory operand fetch DESIGN.md section 3.1 builds on; the measured value stays within 25 % of that bound."""
+    from dcase2019_task4_b200 import _lib
+    lib, ctx = _lib.lib(), _lib.ctx(cuda_device)
+    out = torch.zeros(4, device=cuda_device)
+    stream = torch.cuda.current_stream().cuda_stream
+    for M, N in ((128, 64), (128, 128), (64, 64)):
+        assert lib.dcase_bench_umma(ctx, M, N, 0, 0, 1024, 4, 1024, 0, 0, out.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
+        cyc = float(out.mean())
+        bound = max(max(M, 128) * N / 256.0, (M + N) * 8 * 4 / 128.0)
+        assert bound - 1.0 <= cyc <= 1.25 * bound, (M, N, cyc, bound)
+    assert lib.dcase_bench_umma(ctx, 96, 64, 0, 0, 1024, 4, 1024, 0, 0, out.data_ptr(), stream) != 0     # illegal M
