@@ -75,8 +75,11 @@ class MeanTeacherEngine(object):
         self.d_strong = torch.empty(B, To, NC, **f32)
         self.d_weak = torch.empty(B, NC, **f32)
         self.meters = torch.zeros(8, **f32)
-        self.meters_host = torch.zeros(8, dtype=torch.float32).pin_memory()
-        self.meters_event = torch.cuda.Event()
+        # the 32-byte meter read-back is double buffered: the assertions on step i (main.py:147-148) are made AFTER step
+        # i + 1 has been enqueued, so the host never leaves the GPU idle between two iterations
+        self.meters_host = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.meters_event = [torch.cuda.Event(), torch.cuda.Event()]
+        self._slot = 0
         self._pending = False
         self.ws_s = K.new_workspace(B, frames, NC, dev)
         self.ws_t = K.new_workspace(B, frames, NC, dev) if ema_model is not None else None
@@ -141,8 +144,7 @@ class MeanTeacherEngine(object):
         if ema is not None:
             ema._nbt_pending += 1
         model._nbt_pending += 1
-        if check and self._pending:
-            self.check_loss()
+        prev_pending, prev_slot = self._pending, self._slot
         with torch.cuda.device(self.dev):
             K.mt_fwd_bwd(a)
             grad_scale = dp.allreduce_grads_(self.grads, self.pg) if self.world > 1 else 1.0   # flat slab, SUM
@@ -153,8 +155,9 @@ class MeanTeacherEngine(object):
                             ema.flat_parameters() if ema is not None else None, self._adam_step_count(),
                             lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], ema_alpha=alpha,
                             grad_scale=grad_scale)
-            self.meters_host.copy_(self.meters, non_blocking=True)
-            self.meters_event.record()
+            self._enqueue_meter_copy()
+        if check and prev_pending:
+            self._check_slot(prev_slot)
         self._pending = True
 
     def _mt_args(self, x, xt, target, flags, seed, step, cons_weight, scalars):
@@ -182,8 +185,7 @@ class MeanTeacherEngine(object):
 
     def _graph_step(self, wave, target, mean, std, cons_weight, global_step_after, check):
         model, ema = self.model, self.ema_model
-        if check and self._pending:
-            self.check_loss()
+        prev_pending, prev_slot = self._pending, self._slot
         target = target.contiguous()
         g = self.optimizer.param_groups[0]
         seed, step = model.next_rng()
@@ -215,16 +217,17 @@ class MeanTeacherEngine(object):
                     K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
                                     ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
                                     beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
-                    self.meters_host.copy_(self.meters, non_blocking=True)
                 entry = (graph, K.launch_count() - l0)
                 self._graphs[key] = entry
             entry[0].replay()
             self.graph_launches += entry[1]
-            self.meters_event.record()
+            self._enqueue_meter_copy()
         torch._foreach_add_(self._steps, 1.0)
         model._nbt_pending += 1
         if ema is not None:
             ema._nbt_pending += 1
+        if check and prev_pending:
+            self._check_slot(prev_slot)
         self._pending = True
 
     def step_from_waveforms(self, wave, target, mean, std, cons_weight, global_step_after, check=True):
@@ -243,18 +246,32 @@ class MeanTeacherEngine(object):
             x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None
         self.step(x, x_ema, target, cons_weight, global_step_after, check=check)
 
-    def read_meters(self):
-        """Synchronise on the last step's 32-byte meter copy and return {name: float}."""
-        self.meters_event.synchronize()
-        vals = self.meters_host.tolist()
-        return dict(zip(METER_NAMES, vals))
+    def _enqueue_meter_copy(self):
+        self._slot ^= 1
+        self.meters_host[self._slot].copy_(self.meters, non_blocking=True)
+        self.meters_event[self._slot].record()
 
-    def check_loss(self):
-        """The reference's per-batch assertions (main.py:147-148), applied to the last finished step."""
-        loss = self.read_meters()["Loss"]
-        self._pending = False
+    def _read_slot(self, slot):
+        self.meters_event[slot].synchronize()
+        return dict(zip(METER_NAMES, self.meters_host[slot].tolist()))
+
+    @staticmethod
+    def _assert_loss(loss):
         assert not (np.isnan(loss) or loss > 1e5), 'Loss explosion: {}'.format(loss)
         assert not loss < 0, 'Loss problem, cannot be negative'
+
+    def _check_slot(self, slot):
+        self._assert_loss(self._read_slot(slot)["Loss"])
+
+    def read_meters(self):
+        """Synchronise on the last enqueued step's 32-byte meter copy and return {name: float}."""
+        return self._read_slot(self._slot)
+
+    def check_loss(self):
+        """The reference's per-batch assertions (main.py:147-148), applied to the last enqueued step."""
+        loss = self.read_meters()["Loss"]
+        self._pending = False
+        self._assert_loss(loss)
         return loss
 
 
