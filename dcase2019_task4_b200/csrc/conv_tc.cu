@@ -465,7 +465,7 @@ int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, c
     if (stats) {
         DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
         const long long n_pix = (long long)B * T_l * F;
-        long long blocks = (n_pix + 16 * 32 - 1) / (16 * 32);
+        long long blocks = (n_pix + 63) / 64;             // >= 4 rows per row-lane even for the small block-2 tensor
         if (blocks > num_sms * 4) blocks = num_sms * 4;
         bn_stats_kernel<<<(int)blocks, 256, 0, s>>>(out, n_pix, stats);
         DCASE_LAUNCH_CHECK();
