@@ -213,3 +213,45 @@ def test_graph_replay_matches_eager_steps(pkg, cuda_device):
         d = (a.double() - b.double()).abs()
         assert float(d.max()) <= 6e-3 + 1e-6
         assert int((d > 1e-4).sum()) <= 0.005 * d.numel()
+
+
+def test_get_predictions_batched_matches_clip_by_clip(pkg, cuda_device):
+    """evaluation_measures.get_predictions (batched forward + vectorised threshold / median filter / region decoding)
+    vs the reference's clip-by-clip recipe (evaluation_measures.py:203-231) on the same model."""
+    import pandas as pd
+    import scipy.ndimage
+    from dcase2019_task4_b200 import evaluation_measures as em
+    from dcase2019_task4_b200.utils.utils import ManyHotEncoder
+    cfg, CRNN = pkg["cfg"], pkg["CRNN"]
+    T = 136
+    model = CRNN(**cfg.crnn_kwargs)
+    _load(model, ocrnn.init_params(seed=8))
+    with torch.no_grad():
+        model.dense.bias.fill_(0.3)                     # posteriors around 0.5 so that events actually appear
+        model.dense.weight.mul_(30.0)
+    model = model.eval().cuda()
+    g = torch.Generator().manual_seed(2)
+
+    class _Set(list):
+        pass
+
+    ds = _Set([(torch.randn(1, T, 64, generator=g), None) for _ in range(7)])
+    ds.filenames = pd.Series(["clip%d.wav" % i for i in range(7)])
+    enc = ManyHotEncoder(cfg.classes, n_frames=T // cfg.pooling_time_ratio)
+    got = em.get_predictions(model, ds, enc.decode_strong, pooling_time_ratio=cfg.pooling_time_ratio, batch_size=3)
+    rows = []
+    for i, (x, _) in enumerate(ds):
+        strong, _ = model(x.cuda().unsqueeze(0))
+        p = strong.squeeze(0).detach().cpu().numpy()
+        p = scipy.ndimage.median_filter((p > 0.5).astype(float), (cfg.median_window, 1))
+        for label, on, off in enc.decode_strong(p):
+            k = cfg.pooling_time_ratio / (cfg.sample_rate / cfg.hop_length)
+            rows.append((label, on * k, off * k, ds.filenames.iloc[i]))
+    ref = pd.DataFrame(rows, columns=["event_label", "onset", "offset", "filename"])
+    assert len(ref) > 0 and len(got) == len(ref)
+    key = ["filename", "event_label", "onset"]
+    a, b = got.sort_values(key).reset_index(drop=True), ref.sort_values(key).reset_index(drop=True)
+    assert (a.event_label == b.event_label).all() and (a.filename == b.filename).all()
+    assert np.allclose(a.onset.to_numpy(float), b.onset.to_numpy(float)) and np.allclose(a.offset.to_numpy(float), b.offset.to_numpy(float))
+    f1 = em.compute_strong_metrics(got, ref).results()["overall"]["f_measure"]["f_measure"]
+    assert f1 == 1.0

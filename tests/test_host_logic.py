@@ -145,3 +145,76 @@ def test_crnn_module_surface_on_cpu():
         p.detach_()                                                               # main.py:286-287
     with pytest.raises(NotImplementedError):
         CRNN(**dict(cfg.crnn_kwargs, activation="relu"))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# posteriors -> events -> event-based F1 (restated sed_eval definitions, hand-computed cases)
+# ------------------------------------------------------------------------------------------------------------
+def _events(rows):
+    import pandas as pd
+    return pd.DataFrame(rows, columns=["filename", "event_label", "onset", "offset"])
+
+
+def test_postprocess_threshold_median_and_decode_to_seconds():
+    import numpy as np
+    from dcase2019_task4_b200 import config as cfg
+    from dcase2019_task4_b200 import evaluation_measures as em
+    from dcase2019_task4_b200.utils.utils import ManyHotEncoder
+    T, C = 108, 10
+    p = np.full((2, T, C), 0.1, dtype=np.float32)
+    p[0, 10:30, 2] = 0.9          # a 20-frame event
+    p[0, 50, 2] = 0.99            # a single-frame blip: removed by the 5-frame median filter
+    p[0, 70:90, 5] = 0.9
+    p[0, 80, 5] = 0.2             # a single-frame hole: filled by the median filter
+    p[1, 0:3, 0] = 0.6            # touches the clip start (scipy 'reflect' boundary keeps it)
+    act = em.postprocess_posteriors(p)
+    assert act.shape == p.shape and act.dtype == bool
+    assert act[0, 10:30, 2].all() and not act[0, 40:60, 2].any() and act[0, 70:90, 5].all()
+    enc = ManyHotEncoder(["c%d" % i for i in range(C)], n_frames=T)
+    ev = enc.decode_strong(act[0])
+    assert sorted(ev) == [["c2", 10, 30], ["c5", 70, 90]]
+    sec = em.frames_to_seconds(np.array([10.0, 30.0]), pooling_time_ratio=cfg.pooling_time_ratio)
+    assert np.allclose(sec, np.array([10.0, 30.0]) * 8 * 511 / 44100)     # evaluation_measures.py:226-227
+    assert act[1, 0:3, 0].all() and not act[1, 4:, 0].any()
+
+
+def test_event_based_f1_collars_and_optimal_matching():
+    from dcase2019_task4_b200 import evaluation_measures as em
+    ref = _events([["a.wav", "Dog", 1.0, 6.0],        # 5-s event: offset tolerance max(0.2, 0.2 * 5) = 1.0 s
+                   ["a.wav", "Speech", 0.0, 1.0],
+                   ["a.wav", "Speech", 0.15, 1.15],
+                   ["b.wav", "Dog", 2.0, 2.5]])
+    est = _events([["a.wav", "Dog", 1.15, 6.9],       # onset +0.15 (<= 0.2), offset +0.9 (<= 1.0): hit
+                   ["a.wav", "Speech", 0.1, 1.1],     # X: could pair with either Speech event
+                   ["a.wav", "Speech", -0.1, 0.9],    # Y: pairs only with the first one -> optimal matching finds 2 hits
+                   ["b.wav", "Dog", 2.25, 2.5],       # onset +0.25: miss
+                   ["b.wav", "Cat", 0.0, 1.0]])       # a class absent from the reference
+    m = em.event_based_evaluation_df(ref, est)
+    r = m.results()
+    cw = r["class_wise"]
+    assert cw["Dog"]["count"] == {"Nref": 2, "Nsys": 2, "Ntp": 1}
+    assert cw["Speech"]["count"] == {"Nref": 2, "Nsys": 2, "Ntp": 2}
+    assert cw["Cat"]["count"] == {"Nref": 0, "Nsys": 1, "Ntp": 0}
+    assert abs(cw["Dog"]["f_measure"]["f_measure"] - 0.5) < 1e-12 and cw["Speech"]["f_measure"]["f_measure"] == 1.0
+    ov = r["overall"]["f_measure"]                    # micro: Ntp 3, Nsys 5, Nref 4
+    assert abs(ov["precision"] - 3 / 5) < 1e-12 and abs(ov["recall"] - 3 / 4) < 1e-12
+    assert abs(ov["f_measure"] - 2 * 0.6 * 0.75 / 1.35) < 1e-12
+    # macro average over the union of labels: Cat (system events, no reference event) scores 0
+    assert abs(r["class_wise_average"]["f_measure"]["f_measure"] - 0.5) < 1e-12
+    # offset just outside the 20 % tolerance
+    est2 = _events([["a.wav", "Dog", 1.0, 7.1]])
+    assert em.event_based_evaluation_df(ref[ref.event_label == "Dog"], est2).results()["overall"]["count"]["Ntp"] == 0
+    assert "class-wise average" in str(m)
+
+
+def test_segment_based_metric_and_empty_files():
+    import numpy as np
+    from dcase2019_task4_b200 import evaluation_measures as em
+    ref = _events([["a.wav", "Dog", 0.2, 2.4], ["b.wav", np.nan, np.nan, np.nan]])      # b.wav: no event (tsv convention)
+    est = _events([["a.wav", "Dog", 1.1, 3.5]])
+    seg = em.segment_based_evaluation_df(ref, est, time_resolution=1.0).results()
+    # reference active in segments 0,1,2; system in 1,2,3 -> Ntp 2
+    assert seg["class_wise"]["Dog"]["count"] == {"Nref": 3, "Nsys": 3, "Ntp": 2}
+    ev = em.compute_strong_metrics(est, ref).results()
+    assert ev["overall"]["count"] == {"Nref": 1, "Nsys": 1, "Ntp": 0}
+    assert em.get_event_list_current_file(ref, "b.wav") == []
