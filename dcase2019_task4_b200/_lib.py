@@ -54,6 +54,8 @@ SIGNATURES = {
     "dcase_logmel_fwd": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
     "dcase_logmel_fwd_pcm16": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
     "dcase_logmel_finish": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_u64, c_u32, c_p, c_p, c_p, c_p, c_p]),
+    "dcase_scaler_accumulate": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "dcase_scaler_finalize": (c_i, [c_p, c_p, ctypes.c_longlong, c_p, c_p, c_p, c_p, c_p]),
     "dcase_crnn_param_count": (c_sz, [c_i]),
     "dcase_crnn_param_offset": (ctypes.c_longlong, [c_i, ctypes.c_char_p]),
     "dcase_crnn_workspace_bytes": (c_sz, [c_i, c_i, c_i]),

@@ -269,6 +269,63 @@ finish_kernel(const float* __restrict__ mel_amp, int B, int T_in, int T_out, con
     }
 }
 
+// ---- K2c: Scaler.means (utils/Scaler.py:34-87) on the device -----------------------------------------
+// sums[0][m] += mean over the T_out frames of L[b][t][m], sums[1][m] += the same of fl32(L * L)  (the reference squares
+// in the sample's own dtype, float32, and only the np.mean accumulates in float64).  apply_log: L = dB of the amplitude
+// mel with the clip's top_db floor, truncated / zero-padded to T_out frames (ApplyLog -> PadOrTrunc; pad rows are
+// 0.0 dB and add nothing); otherwise the rows are taken as they are.  grid (slices, B); a CTA is 16 frame lanes x 16
+// quads, so one warp reads two whole 256-byte rows.
+__global__ void __launch_bounds__(256)
+scaler_accum_kernel(const float* __restrict__ feats, int T_in, int T_out, int apply_log,
+                    const float* __restrict__ clip_max, double* __restrict__ sums) {
+    __shared__ double red[2][16][kMel];
+    const int b = blockIdx.y, q = threadIdx.x & 15, lane = threadIdx.x >> 4;
+    const int T = T_in < T_out ? T_in : T_out;
+    const int per = (T + gridDim.x - 1) / gridDim.x;
+    const int t0 = blockIdx.x * per;
+    const int t1 = t0 + per < T ? t0 + per : T;
+    const float floor_c = apply_log ? amp_to_db(clip_max[b]) - 80.f : 0.f;
+    const float4* src = reinterpret_cast<const float4*>(feats + (size_t)b * T_in * kMel);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+    for (int t = t0 + lane; t < t1; t += 16) {
+        float4 x = __ldg(src + (size_t)t * 16 + q);
+        if (apply_log) {
+            x.x = fmaxf(amp_to_db(x.x), floor_c);
+            x.y = fmaxf(amp_to_db(x.y), floor_c);
+            x.z = fmaxf(amp_to_db(x.z), floor_c);
+            x.w = fmaxf(amp_to_db(x.w), floor_c);
+        }
+        s0 += (double)x.x; s1 += (double)x.y; s2 += (double)x.z; s3 += (double)x.w;
+        r0 += (double)__fmul_rn(x.x, x.x); r1 += (double)__fmul_rn(x.y, x.y);
+        r2 += (double)__fmul_rn(x.z, x.z); r3 += (double)__fmul_rn(x.w, x.w);
+    }
+    red[0][lane][4 * q] = s0; red[0][lane][4 * q + 1] = s1; red[0][lane][4 * q + 2] = s2; red[0][lane][4 * q + 3] = s3;
+    red[1][lane][4 * q] = r0; red[1][lane][4 * q + 1] = r1; red[1][lane][4 * q + 2] = r2; red[1][lane][4 * q + 3] = r3;
+    __syncthreads();
+    if (threadIdx.x < 2 * kMel) {
+        const int which = threadIdx.x >> 6, m = threadIdx.x & (kMel - 1);
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < 16; ++l) acc += red[which][l][m];
+        atomicAdd(sums + which * kMel + m, acc / (double)T_out);
+    }
+}
+
+// mean_ = sums[0] / n, mean_of_square_ = sums[1] / n (Scaler.py:72-73), std_ = sqrt(mean_of_square_ - mean_^2)
+// (Scaler.py:31-32, :89-97; no fused multiply-add, as numpy), plus the float32 copies dcase_logmel_finish reads.
+__global__ void scaler_finalize_kernel(const double* __restrict__ sums, double n, double* __restrict__ mean_,
+                                       double* __restrict__ mean_of_square_, float* __restrict__ mean_f32,
+                                       float* __restrict__ std_f32) {
+    const int m = threadIdx.x;
+    if (m >= kMel) return;
+    const double mu = sums[m] / n, sq = sums[kMel + m] / n;
+    const double sd = sqrt(__dsub_rn(sq, __dmul_rn(mu, mu)));
+    if (mean_) mean_[m] = mu;
+    if (mean_of_square_) mean_of_square_[m] = sq;
+    if (mean_f32) mean_f32[m] = (float)mu;
+    if (std_f32) std_f32[m] = (float)sd;
+}
+
 // ---- host-side constant tables -----------------------------------------------------------------
 double hz_to_mel(double f) {
     const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
@@ -424,6 +481,45 @@ int dcase_logmel_finish(dcase_ctx* ctx, const float* mel_amp, int B, int T_in, i
     if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
     finish_kernel<<<blocks, 256, 0, stream>>>(mel_amp, B, T_in, T_out, mean, stdv, noise, seed, step, sc, clip_max_ws,
                                              clean, noisy);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int dcase_scaler_accumulate(dcase_ctx* ctx, const float* feats, int B, int T_in, int T_out, int apply_log,
+                            float* clip_max_ws, double* sums, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCASE_REQUIRE(ctx && feats && sums, "null argument");
+    DCASE_REQUIRE(B >= 0 && T_in > 0 && T_out > 0, "bad shape");
+    DCASE_REQUIRE(!apply_log || clip_max_ws, "apply_log needs the [B] clip_max scratch");
+    DCASE_REQUIRE(apply_log || T_in == T_out, "finished features are reduced as they are (T_in == T_out)");
+    if (B == 0) return DCASE_OK;
+    DCASE_PROF("scaler_accumulate", stream);
+    const int want = (ctx->num_sms * 8 + B - 1) / B;
+    if (apply_log) {
+        DCASE_CUDA_CHECK(cudaMemsetAsync(clip_max_ws, 0, (size_t)B * sizeof(float), stream));
+        const int n_quads = T_in * (kMel / 4);
+        int slices = (n_quads + 1023) / 1024;
+        if (slices > want) slices = want;
+        if (slices < 1) slices = 1;
+        clip_max_kernel<<<dim3(slices, B), 256, 0, stream>>>(feats, T_in, nullptr, 0, 0, 0, nullptr, clip_max_ws, B);
+        DCASE_LAUNCH_CHECK();
+    }
+    const int T = T_in < T_out ? T_in : T_out;
+    int slices = (T + 63) / 64;                                  // >= 4 rows per thread
+    if (slices > want) slices = want;
+    if (slices < 1) slices = 1;
+    scaler_accum_kernel<<<dim3(slices, B), 256, 0, stream>>>(feats, T_in, T_out, apply_log, clip_max_ws, sums);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int dcase_scaler_finalize(dcase_ctx* ctx, const double* sums, long long n_samples, double* mean,
+                          double* mean_of_square, float* mean_f32, float* std_f32, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCASE_REQUIRE(ctx && sums, "null argument");
+    DCASE_REQUIRE(n_samples > 0, "Scaler.means over an empty dataset");
+    DCASE_PROF("scaler_finalize", stream);
+    scaler_finalize_kernel<<<1, kMel, 0, stream>>>(sums, (double)n_samples, mean, mean_of_square, mean_f32, std_f32);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

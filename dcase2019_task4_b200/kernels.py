@@ -70,6 +70,35 @@ def logmel_finish(mel_amp, mean, std, frames, noisy=False, noise=None, seed=0, s
     return (clean, nz) if want_noisy else clean
 
 
+def scaler_accumulate(feats, sums, frames=None, apply_log=True):
+    """Scaler.means over one batch: feats [B, T_in, 64] (amplitude mels with apply_log, finished features
+    otherwise) are reduced into ``sums`` (CUDA float64 [2, 64], accumulated in place)."""
+    feats = _f32(feats)
+    B, T_in, F = feats.shape
+    assert F == N_MELS and sums.is_cuda and sums.dtype == torch.float64 and sums.numel() == 2 * N_MELS
+    assert sums.is_contiguous()
+    frames = T_in if frames is None else int(frames)
+    dev = feats.device
+    scratch = torch.empty(max(B, 1), device=dev, dtype=torch.float32) if apply_log else None
+    with torch.cuda.device(dev):
+        check(lib().dcase_scaler_accumulate(ctx(dev), ptr(feats), B, T_in, frames, int(bool(apply_log)), ptr(scratch),
+                                            ptr(sums), stream_ptr()))
+    return sums
+
+
+def scaler_finalize(sums, n_samples):
+    """-> (mean_ f64 [64], mean_of_square_ f64 [64], mean f32 [64], std f32 [64]) device tensors."""
+    dev = sums.device
+    mean = torch.empty(N_MELS, device=dev, dtype=torch.float64)
+    msq = torch.empty(N_MELS, device=dev, dtype=torch.float64)
+    mean32 = torch.empty(N_MELS, device=dev, dtype=torch.float32)
+    std32 = torch.empty(N_MELS, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        check(lib().dcase_scaler_finalize(ctx(dev), ptr(sums), int(n_samples), ptr(mean), ptr(msq), ptr(mean32),
+                                          ptr(std32), stream_ptr()))
+    return mean, msq, mean32, std32
+
+
 def param_count(n_class=10):
     return lib().dcase_crnn_param_count(n_class)
 
@@ -199,4 +228,4 @@ def mt_fwd_bwd(args):
 
 __all__ = ["FLAG_BN_BATCH_STATS", "FLAG_DROPOUT", "logmel_fwd", "logmel_finish", "crnn_forward", "crnn_backward",
            "mt_loss", "adam_ema_step", "mt_fwd_bwd", "param_count", "param_offset", "new_workspace", "ws_tensor",
-           "mel_filterbank", "num_frames", "workspace_bytes"]
+           "mel_filterbank", "num_frames", "workspace_bytes", "scaler_accumulate", "scaler_finalize"]

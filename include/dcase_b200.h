@@ -113,6 +113,20 @@ int dcase_logmel_finish(dcase_ctx* ctx, const float* mel_amp, int B, int T_in, i
                         const float* stdv, const float* noise, uint64_t seed, uint32_t step, const void* scalars,
                         float* clip_max_ws, float* clean, float* noisy, void* stream);
 
+/* Scaler.means (utils/Scaler.py:34-87) over a batch of clips, as main.py:249-250 runs it over the training set
+ * through get_transforms(frames) without a scaler: sums [2][64] float64 (zeroed by the caller before the first
+ * batch) accumulates, per mel bin, the per-clip mean over the T_out frames of the feature and of its float32
+ * square.  apply_log = 1: feats is the amplitude mel [B][T_in][64] and the kernel applies ApplyLog (dB, top_db
+ * floor at the clip maximum) and PadOrTrunc(T_out) itself; clip_max_ws is [B] floats of scratch.
+ * apply_log = 0: feats [B][T_in == T_out][64] are reduced as they are (clip_max_ws may be NULL). */
+int dcase_scaler_accumulate(dcase_ctx* ctx, const float* feats, int B, int T_in, int T_out, int apply_log,
+                            float* clip_max_ws, double* sums, void* stream);
+/* Scaler.means' division by the sample count (Scaler.py:72-73) and Scaler.calculate_scaler's std
+ * (Scaler.py:89-97): mean / mean_of_square [64] float64 (the state_dict wire format, Scaler.py:107-113) and the
+ * float32 mean / std [64] that dcase_logmel_finish reads.  Any output may be NULL. */
+int dcase_scaler_finalize(dcase_ctx* ctx, const double* sums, long long n_samples, double* mean,
+                          double* mean_of_square, float* mean_f32, float* std_f32, void* stream);
+
 /* ---- CRNN ------------------------------------------------------------------------------------------ */
 
 /* Number of fp32 elements of the flat parameter slab (214,356 for n_class = 10). */

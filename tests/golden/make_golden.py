@@ -5,6 +5,10 @@
 * crnn_reference.npz  -- outputs of the UNMODIFIED reference ``baseline/models/CRNN.py`` (imported from
   /root/reference): eval-mode posteriors, train-mode (dropout=0 kwargs) posteriors, loss and a checksum of every
   parameter gradient, for parameters ``oracle.crnn.init_params(seed=7)`` (stored) and a seeded input (stored).
+* scaler_reference.npz -- ``mean_``, ``mean_of_square_``, ``std_`` computed by the UNMODIFIED reference
+  ``baseline/utils/Scaler.py`` (``calculate_scaler``) over seeded amplitude mels sent through the oracle's
+  ApplyLog / PadOrTrunc / ToTensor chain (DataLoad.py is not importable here: librosa), one set padded
+  (frames = 48 > T), one truncated (frames = 32 < T), plus ``normalize`` of one sample.
 * mel_oracle.npz      -- float64 oracle log-mel features of three short seeded synthetic clips (librosa itself is
   not installed: these pin the restatement against accidental edits, not against librosa; "parity unpinned").
 """
@@ -89,7 +93,40 @@ def main():
                         mean=mean, std=std, clean=np.stack(clean), noisy=np.stack(noisy),
                         fb_sum=np.float64(omel.mel_filterbank().astype(np.float64).sum()),
                         fb_nnz=np.int64(np.count_nonzero(omel.mel_filterbank())))
+    scaler_fixture()
     print("wrote fixtures to", HERE)
+
+
+def reference_scaler():
+    """The reference's Scaler class; utils/Logger.py opens Baseline.log in the CWD on import -> scratch dir."""
+    import tempfile
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())
+    try:
+        from utils.Scaler import Scaler
+    finally:
+        os.chdir(cwd)
+    return Scaler
+
+
+def scaler_fixture():
+    Scaler = reference_scaler()
+    waves, _ = synth.make_clips(8, seed=77, n_samples=22050)          # 44 frames each; clip 7 is half silent
+    amps = np.stack([omel.calculate_mel_spec(w.astype(np.float64)) for w in waves])
+    out = {"mel_amp": amps}
+    for frames in (48, 32):
+        data = [(torch.from_numpy(omel.transform_chain(a, None, None, frames=frames)[0]), None) for a in amps]
+        sc = Scaler()
+        mean, std = sc.calculate_scaler(data)
+        out["mean_%d" % frames] = np.asarray(mean)
+        out["mean_of_square_%d" % frames] = np.asarray(sc.mean_of_square_)
+        out["std_%d" % frames] = np.asarray(std)
+        if frames == 48:
+            out["normalized_48"] = sc.normalize(data[0][0]).numpy()
+            assert set(sc.state_dict()) == {"mean_", "mean_of_square_"}
+    np.savez_compressed(os.path.join(HERE, "scaler_reference.npz"), **out)
 
 
 if __name__ == "__main__":

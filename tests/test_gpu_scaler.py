@@ -1,0 +1,108 @@
+"""GPU parity of the device Scaler: ``Scaler.means`` / ``calculate_scaler``
+(utils/Scaler.py:34-97) as ``dcase_scaler_accumulate`` + ``dcase_scaler_finalize`` against the fixture written by
+the UNMODIFIED reference Scaler (tests/golden/scaler_reference.npz) and against the float64 oracle.
+
+Tolerances: the device takes the dB in float32 with ``log10f`` (the reference: numpy float32 ``log10``), so single
+features differ by ~1 ulp of |L| <= 100 (8e-6); per-bin means are compared at 2e-5 dB, mean squares at 2e-3 dB^2
+(|L| up to 100) and std at 1e-4 dB.  The float64 reduction itself is checked at 1e-9 on finished features."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import mel as omel
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def pkg(cuda_device):
+    from dcase2019_task4_b200 import DataLoad, kernels as K, synth
+    from dcase2019_task4_b200.utils.Scaler import Scaler
+    from dcase2019_task4_b200.utils.utils import get_transforms
+    return dict(DataLoad=DataLoad, K=K, Scaler=Scaler, get_transforms=get_transforms, synth=synth)
+
+
+def _dataset(pkg, amps, frames, names=None):
+    names = names or ["clip%d.wav" % i for i in range(len(amps))]
+    store = dict(zip(names, amps))
+    df = pd.DataFrame({"filename": names})
+    return pkg["DataLoad"].DataLoadDf(df, lambda f: store[f], None, transform=pkg["get_transforms"](frames))
+
+
+@pytest.mark.parametrize("frames", [48, 32])
+def test_calculate_scaler_on_dataset_matches_reference_fixture(pkg, frames):
+    """main.py:249-250: Scaler().calculate_scaler(ConcatDataset([...])) over datasets carrying get_transforms(frames)."""
+    z = np.load(os.path.join(GOLD, "scaler_reference.npz"))
+    amps = z["mel_amp"]
+    ds = pkg["DataLoad"].ConcatDataset([_dataset(pkg, amps[:3], frames), _dataset(pkg, amps[3:], frames)])
+    sc = pkg["Scaler"]()
+    mean, std = sc.calculate_scaler(ds)
+    assert mean.dtype == np.float64 and mean.shape == (64,) and type(sc.mean_) is np.ndarray
+    assert np.abs(mean - z["mean_%d" % frames]).max() <= 2e-5
+    assert np.abs(sc.mean_of_square_ - z["mean_of_square_%d" % frames]).max() <= 2e-3
+    assert np.abs(std - z["std_%d" % frames]).max() <= 1e-4
+    sd = sc.state_dict()                                             # wire format, Scaler.py:107-113
+    assert set(sd) == {"mean_", "mean_of_square_"} and len(sd["mean_"]) == 64
+    # and the statistics feed the fused finish kernel: normalised features against Scaler.normalize of the reference
+    if frames == 48:
+        x = pkg["get_transforms"](48, sc)((amps[0], np.zeros((6, 10))))[0]
+        assert np.abs(x.cpu().numpy() - z["normalized_48"]).max() <= 2e-5
+
+
+def test_generic_iterable_float64_reduction(pkg, cuda_device):
+    """Any iterable of (features, label) with [..., 64] samples is reduced as it is; same-shape rule as Scaler.py:57-61."""
+    rng = np.random.default_rng(11)
+    data = [(torch.from_numpy(rng.normal(-30, 12, (1, 37, 64)).astype(np.float32)), None) for _ in range(131)]
+    sc = pkg["Scaler"]()
+    mean, std = sc.calculate_scaler(data)                            # 131 samples: three launches (64 + 64 + 3)
+    m, m2 = omel.scaler_means([d[0].numpy() for d in data])
+    assert np.abs(mean - m).max() <= 1e-9 and np.abs(sc.mean_of_square_ - m2).max() <= 1e-9 * 1e3
+    assert np.abs(std - omel.scaler_std(m, m2)).max() <= 1e-9
+    cuda_data = [d[0].cuda() for d in data[:5]]                      # bare CUDA tensors work too
+    sc2 = pkg["Scaler"]().means(cuda_data)
+    assert np.abs(sc2.mean_ - omel.scaler_means([d[0].numpy() for d in data[:5]])[0]).max() <= 1e-9
+    with pytest.raises(NotImplementedError):
+        pkg["Scaler"]().means(data[:2] + [(torch.zeros(1, 36, 64), None)])
+    with pytest.raises(ValueError):
+        pkg["Scaler"]().means([])
+
+
+def test_ragged_clip_lengths_and_full_size(pkg, cuda_device):
+    """Clips of different length (cached features are [T, 64] with T = 1 + len // 511) are grouped per shape and padded /
+    truncated to 864 by the kernel; one is silent (amin floor) and one has a silent half (top_db floor)."""
+    rng = np.random.default_rng(3)
+    amps = []
+    for T in (864, 864, 431, 900, 864, 17):
+        a = np.abs(rng.normal(0, 1, (T, 64))).astype(np.float32) * rng.uniform(0.01, 50)
+        amps.append(a)
+    amps[1][400:] = 0.0
+    amps[4][:] = 0.0
+    sc = pkg["Scaler"]()
+    mean, std = sc.calculate_scaler(_dataset(pkg, amps, 864))
+    m, m2 = omel.scaler_means([omel.transform_chain(a, None, None, frames=864)[0] for a in amps])
+    assert np.abs(mean - m).max() <= 2e-5 and np.abs(sc.mean_of_square_ - m2).max() <= 2e-3
+    assert np.abs(std - omel.scaler_std(m, m2)).max() <= 1e-4
+
+
+def test_means_from_waveforms_and_linearity(pkg, cuda_device):
+    """Raw clips -> dcase_logmel_fwd -> reduction; and the size-independent property: statistics of the union of two
+    sets are the count-weighted mean of the sets' statistics."""
+    waves, _ = pkg["synth"].make_clips(6, seed=5, n_samples=44100)
+    frames = 96                                                       # 87 frames per clip, padded to 96
+    sc = pkg["Scaler"]()
+    mean, std = sc.calculate_scaler_from_waveforms([torch.from_numpy(waves[:4]), torch.from_numpy(waves[4:])], frames)
+    amps = [omel.calculate_mel_spec(w.astype(np.float64)) for w in waves]
+    m, m2 = omel.scaler_means([omel.transform_chain(a, None, None, frames=frames)[0] for a in amps])
+    assert np.abs(mean - m).max() <= 5e-3 and np.abs(std - omel.scaler_std(m, m2)).max() <= 5e-3   # fp32 STFT upstream
+    a = pkg["Scaler"]().means_from_waveforms([torch.from_numpy(waves[:4])], frames)
+    b = pkg["Scaler"]().means_from_waveforms([torch.from_numpy(waves[4:])], frames)
+    assert np.abs((4 * a.mean_ + 2 * b.mean_) / 6 - sc.mean_).max() <= 1e-10
+    assert np.abs((4 * a.mean_of_square_ + 2 * b.mean_of_square_) / 6 - sc.mean_of_square_).max() <= 1e-8
+    pcm = torch.from_numpy((np.clip(waves, -1, 1) * 32767).astype(np.int16))
+    c = pkg["Scaler"]().means_from_waveforms([pcm], frames)           # 16-bit PCM input (soundfile scaling 1 / 32768)
+    d = pkg["Scaler"]().means_from_waveforms([pcm.float() / 32768.0], frames)
+    assert np.abs(c.mean_ - d.mean_).max() <= 1e-6 and np.abs(c.mean_ - sc.mean_).max() <= 0.5

@@ -90,21 +90,30 @@ def test_many_hot_encoder_roundtrip_and_regions():
     assert ManyHotEncoder.load_state_dict(enc.state_dict()).labels == cfg.classes
 
 
-def test_scaler_matches_oracle_and_wire_format(tmp_path):
+def test_scaler_wire_format_and_no_cpu_fallback(tmp_path):
+    """state_dict / save / load / normalize keep the reference's wire format (Scaler.py:99-125); the reduction
+    itself (means / calculate_scaler) is a device kernel and raises without a GPU (tests/test_gpu_scaler.py)."""
     rng = np.random.default_rng(0)
     data = [(torch.from_numpy(rng.normal(-20, 8, (1, 50, 64)).astype(np.float32)), None) for _ in range(5)]
-    sc = Scaler()
-    mean, std = sc.calculate_scaler(data)
     m, m2 = omel.scaler_means([d[0].numpy() for d in data])
-    assert np.allclose(mean, m) and np.allclose(std, omel.scaler_std(m, m2))
+    sc = Scaler()
+    with pytest.raises(NotImplementedError):
+        sc.state_dict()                                   # nothing computed yet (Scaler.py:108-109)
+    sc.load_state_dict({"mean_": m.tolist(), "mean_of_square_": m2.tolist()})
+    assert np.allclose(sc.std_, omel.scaler_std(m, m2), rtol=0, atol=1e-12)
     sd = sc.state_dict()
     assert set(sd) == {"mean_", "mean_of_square_"} and isinstance(sd["mean_"], list)
     sc.save(tmp_path / "s.json")
     sc2 = Scaler()
     sc2.load(tmp_path / "s.json")
-    assert np.allclose(sc2.std_, sc.std_)
+    assert np.array_equal(sc2.std_, sc.std_) and np.array_equal(sc2.mean_, sc.mean_)
     x = data[0][0]
-    assert np.allclose(sc.normalize(x).numpy(), (x.numpy() - mean) / std, atol=1e-5)
+    assert np.allclose(sc.normalize(x).numpy(), (x.numpy() - m) / sc.std_, atol=1e-5)
+    assert np.allclose(sc.normalize(x.numpy()), (x.numpy() - m) / sc.std_)
+    if not torch.cuda.is_available():
+        from dcase2019_task4_b200._lib import DcaseError
+        with pytest.raises(DcaseError):
+            Scaler().calculate_scaler(data)
 
 
 def test_transform_chain_structure_and_small_utils():

@@ -62,6 +62,20 @@ def test_oracle_mel_matches_fixture():
         assert np.array_equal(c, z["clean"][i]) and np.array_equal(n, z["noisy"][i])
 
 
+def test_oracle_scaler_matches_reference_scaler_fixture():
+    """oracle.mel.scaler_means / scaler_std against mean_ / mean_of_square_ / std_ produced by the UNMODIFIED
+    reference utils/Scaler.py (tests/golden/make_golden.py), padded (48) and truncated (32) chains."""
+    z = np.load(os.path.join(GOLD, "scaler_reference.npz"))
+    for frames in (48, 32):
+        feats = [omel.transform_chain(a, None, None, frames=frames)[0] for a in z["mel_amp"]]
+        m, m2 = omel.scaler_means(feats)
+        assert np.abs(m - z["mean_%d" % frames]).max() < 1e-12
+        assert np.abs(m2 - z["mean_of_square_%d" % frames]).max() < 1e-10
+        assert np.abs(omel.scaler_std(m, m2) - z["std_%d" % frames]).max() < 1e-11
+    feats = omel.transform_chain(z["mel_amp"][0], z["mean_48"], z["std_48"], frames=48)[0]
+    assert np.abs(feats - z["normalized_48"]).max() < 1e-6          # Scaler.normalize (Scaler.py:99-105)
+
+
 def test_oracle_stft_matches_torch_stft():
     rng = np.random.default_rng(0)
     y = rng.standard_normal(20000)

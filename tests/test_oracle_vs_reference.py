@@ -129,3 +129,22 @@ def test_state_dict_format_roundtrip():
     assert set(sd.keys()) == {"cnn", "rnn", "dense"}
     assert torch.equal(sd["cnn"]["conv1.weight"], p["cnn.cnn.conv1.weight"])
     assert torch.equal(sd["rnn"]["rnn.weight_hh_l1_reverse"], p["rnn.rnn.weight_hh_l1_reverse"])
+
+
+def test_scaler_means_match_reference_scaler(tmp_path, monkeypatch):
+    """oracle.mel.scaler_means / scaler_std against the reference's utils/Scaler.py run live (float32 [1,T,64]
+    samples as the transform chain yields them), incl. the state_dict wire format."""
+    from oracle import mel as omel
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    monkeypatch.chdir(tmp_path)                      # utils/Logger.py opens Baseline.log in the CWD on import
+    from utils.Scaler import Scaler
+    rng = np.random.default_rng(5)
+    data = [(torch.from_numpy(rng.normal(-30, 12, (1, 37, 64)).astype(np.float32)), None) for _ in range(7)]
+    sc = Scaler()
+    mean, std = sc.calculate_scaler(data)
+    m, m2 = omel.scaler_means([d[0].numpy() for d in data])
+    assert np.abs(m - mean).max() < 1e-12 and np.abs(m2 - sc.mean_of_square_).max() < 1e-10
+    assert np.abs(omel.scaler_std(m, m2) - std).max() < 1e-11
+    sd = sc.state_dict()
+    assert set(sd) == {"mean_", "mean_of_square_"} and isinstance(sd["mean_"], list) and len(sd["mean_"]) == 64
