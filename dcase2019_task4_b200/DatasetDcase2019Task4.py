@@ -45,6 +45,28 @@ class DatasetDcase2019Task4:
             a = a.float()
         return K.logmel_fwd(a.cuda(non_blocking=True))
 
+    def extract_features_from_files(self, wav_dir, wav_names):
+        """The loop body of extract_features_from_meta (:233-270) for a list of wav files: read_audio (mono mix-down
+        on the GPU) -> calculate_mel_spec (dcase_logmel_fwd) -> ``<name>.npy`` in the reference's cache format.
+        Missing files are reported and skipped, empty ones flagged as corrupted, as the reference does.
+        Returns the names whose features exist afterwards."""
+        from .utils.utils import read_audio_device
+        done = []
+        for wav_name in wav_names:
+            out_path = os.path.join(self.feature_dir, os.path.splitext(wav_name)[0] + ".npy")
+            if self.recompute_features or not os.path.exists(out_path):
+                wav_path = os.path.join(wav_dir, wav_name)
+                if not os.path.isfile(wav_path):
+                    print("File %s is in the tsv file but the feature is not extracted!" % wav_path)
+                    continue
+                audio, _ = read_audio_device(wav_path, cfg.sample_rate)
+                if audio.shape[0] == 0:
+                    print("File %s is corrupted!" % wav_path)
+                    continue
+                np.save(out_path, K.logmel_fwd(audio[None])[0].cpu().numpy())
+            done.append(wav_name)
+        return done
+
     def extract_features_to_cache(self, names_and_audio):
         """Write ``<name>.npy`` caches (reference format) for an iterable of (wav_name, waveform)."""
         for name, audio in names_and_audio:

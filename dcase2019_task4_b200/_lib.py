@@ -53,6 +53,7 @@ SIGNATURES = {
     "dcase_mel_filterbank": (c_i, [c_p, c_p]),
     "dcase_logmel_fwd": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
     "dcase_logmel_fwd_pcm16": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
+    "dcase_audio_mixdown": (c_i, [c_p, c_p, c_i, ctypes.c_longlong, c_i, c_p, c_p]),
     "dcase_logmel_finish": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_u64, c_u32, c_p, c_p, c_p, c_p, c_p]),
     "dcase_scaler_accumulate": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "dcase_scaler_finalize": (c_i, [c_p, c_p, ctypes.c_longlong, c_p, c_p, c_p, c_p, c_p]),
@@ -61,6 +62,8 @@ SIGNATURES = {
     "dcase_crnn_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "dcase_crnn_ws_tensor": (c_i, [c_i, c_i, c_i, ctypes.c_char_p, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]),
     "dcase_crnn_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_u64, c_u32, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "dcase_bigru_workspace_bytes": (c_sz, [c_i, c_i]),
+    "dcase_bigru_forward": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "dcase_crnn_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_u64, c_u32, c_i, c_p, c_p, c_p, c_p, c_p,
                                   c_p, c_p]),
     "dcase_mt_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p,

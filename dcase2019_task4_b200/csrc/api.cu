@@ -367,6 +367,46 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     return DCASE_OK;
 }
 
+size_t dcase_bigru_workspace_bytes(int B, int To) {
+    if (B < 1 || To < 1) return 0;
+    const size_t BT = (size_t)B * To;
+    return (BT * 2 * 3 * kH + BT * 2 * kH) * sizeof(float);          // gi of both directions + layer-0 output
+}
+
+int dcase_bigru_forward(dcase_ctx* ctx, const float* x, int B, int To, const float* rnn_params, float* out, void* ws,
+                        void* stream_) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    DCASE_REQUIRE(ctx && x && rnn_params && out && ws, "null argument");
+    DCASE_REQUIRE(B >= 1 && To >= 1, "bad shape");
+    const POff o = param_offsets(10);
+    const long long base = o.w_ih[0][0];                             // rnn.rnn.weight_ih_l0 opens the GRU block
+    const int BT = B * To;
+    float* gi = (float*)ws;
+    float* mid = gi + (size_t)BT * 2 * 3 * kH;
+    const float* rin = x;
+    for (int l = 0; l < 2; ++l) {
+        const int nin = l == 0 ? kC : 2 * kH;
+        float* rout = l == 0 ? mid : out;
+        GemmBatch gb{};
+        for (int d = 0; d < 2; ++d)
+            gb.p[d] = GemmProblem{BT, 3 * kH, nin, rin, nin, 1, rnn_params + (o.w_ih[l][d] - base), 1, nin,
+                                  gi + (size_t)d * BT * 3 * kH, 3 * kH, rnn_params + (o.b_ih[l][d] - base)};
+        gb.n = 2; gb.split = 1; gb.mode = 0;
+        DCASE_TRY(launch_sgemm_batch(gb, s));
+        GruFwdArgs g{};
+        g.gi = gi;
+        for (int d = 0; d < 2; ++d) {
+            g.w_hh[d] = rnn_params + (o.w_hh[l][d] - base);
+            g.b_hh[d] = rnn_params + (o.b_hh[l][d] - base);
+        }
+        g.out = rout;
+        g.B = B; g.T = To;
+        DCASE_TRY(launch_gru_fwd(g, s));
+        rin = rout;
+    }
+    return DCASE_OK;
+}
+
 int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, const float* params, int flags,
                         uint64_t seed, uint32_t step, int model_id, const void* scalars, const float* d_strong,
                         const float* d_weak, const float* weak, void* ws, float* grads, void* stream_) {

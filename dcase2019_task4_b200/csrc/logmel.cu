@@ -326,6 +326,22 @@ __global__ void scaler_finalize_kernel(const double* __restrict__ sums, double n
     if (std_f32) std_f32[m] = (float)sd;
 }
 
+// ---- read_audio's mono mix-down (utils/utils.py:187-189): mean over the channels of interleaved frames ----------
+// 16-bit PCM is scaled by 1 / 32768 first (soundfile's float conversion); the mean is taken in fp32 (<= 8 channels of
+// 16-bit samples are exact in fp32 up to the final division).
+template <typename Tin>
+__global__ void __launch_bounds__(256)
+mixdown_kernel(const Tin* __restrict__ in, long long n_frames, int n_ch, float* __restrict__ mono) {
+    const float scale = sizeof(Tin) == 2 ? 1.f / 32768.f : 1.f;
+    const float inv = 1.f / (float)n_ch;
+    for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < n_frames;
+         f += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int c = 0; c < n_ch; ++c) acc += (float)in[f * n_ch + c] * scale;
+        mono[f] = acc * inv;
+    }
+}
+
 // ---- host-side constant tables -----------------------------------------------------------------
 double hz_to_mel(double f) {
     const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
@@ -520,6 +536,23 @@ int dcase_scaler_finalize(dcase_ctx* ctx, const double* sums, long long n_sample
     DCASE_REQUIRE(n_samples > 0, "Scaler.means over an empty dataset");
     DCASE_PROF("scaler_finalize", stream);
     scaler_finalize_kernel<<<1, kMel, 0, stream>>>(sums, (double)n_samples, mean, mean_of_square, mean_f32, std_f32);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+int dcase_audio_mixdown(dcase_ctx* ctx, const void* interleaved, int is_pcm16, long long n_frames, int n_channels,
+                        float* mono, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCASE_REQUIRE(ctx && interleaved && mono, "null argument");
+    DCASE_REQUIRE(n_frames >= 0 && n_channels >= 1 && n_channels <= 64, "bad shape");
+    if (n_frames == 0) return DCASE_OK;
+    DCASE_PROF("audio_mixdown", stream);
+    long long blocks = (n_frames + 255) / 256;
+    if (blocks > ctx->num_sms * 16) blocks = ctx->num_sms * 16;
+    if (is_pcm16)
+        mixdown_kernel<int16_t><<<(int)blocks, 256, 0, stream>>>((const int16_t*)interleaved, n_frames, n_channels, mono);
+    else
+        mixdown_kernel<float><<<(int)blocks, 256, 0, stream>>>((const float*)interleaved, n_frames, n_channels, mono);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

@@ -45,6 +45,18 @@ def logmel_fwd(wave):
     return out
 
 
+def audio_mixdown(frames):
+    """read_audio's mix-down: interleaved [n_frames, n_channels] (CUDA float32 or int16 PCM) -> mono float32 [n_frames]."""
+    assert frames.is_cuda and frames.dim() == 2 and frames.dtype in (torch.float32, torch.int16)
+    frames = frames.contiguous()
+    n, ch = frames.shape
+    out = torch.empty(n, device=frames.device, dtype=torch.float32)
+    with torch.cuda.device(frames.device):
+        check(lib().dcase_audio_mixdown(ctx(frames.device), ptr(frames), int(frames.dtype == torch.int16), n, ch,
+                                        ptr(out), stream_ptr()))
+    return out
+
+
 def logmel_finish(mel_amp, mean, std, frames, noisy=False, noise=None, seed=0, step=0, scalars=None,
                   out_clean=None, out_noisy=None):
     """get_transforms(frames, scaler, augment_type='noise' if noisy) on a batch of amplitude mels.
@@ -162,6 +174,25 @@ def crnn_backward(x, params, flags, ws, d_strong, d_weak, weak, n_class=10, seed
     return grads
 
 
+GRU_PARAM_COUNT = 124416      # the 16 rnn.rnn.* tensors of the 2-layer bidirectional GRU(64, 64)
+
+
+def bigru_forward(x, rnn_params, out=None, ws=None):
+    """BidirectionalGRU.forward: x [B, To, 64] -> [B, To, 128]; rnn_params is the GRU block of the flat slab
+    (``flat[param_offset('rnn.rnn.weight_ih_l0'):][:GRU_PARAM_COUNT]``)."""
+    x = _f32(x)
+    B, To, F = x.shape
+    assert F == N_MELS and rnn_params.numel() >= GRU_PARAM_COUNT
+    dev = x.device
+    if out is None:
+        out = torch.empty(B, To, 128, device=dev, dtype=torch.float32)
+    if ws is None:
+        ws = torch.empty(lib().dcase_bigru_workspace_bytes(B, To), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().dcase_bigru_forward(ctx(dev), ptr(x), B, To, ptr(_f32(rnn_params)), ptr(out), ptr(ws), stream_ptr()))
+    return out
+
+
 def _slice_bounds(mask, B):
     if mask is None:
         return 0, 0
@@ -228,4 +259,4 @@ def mt_fwd_bwd(args):
 
 __all__ = ["FLAG_BN_BATCH_STATS", "FLAG_DROPOUT", "logmel_fwd", "logmel_finish", "crnn_forward", "crnn_backward",
            "mt_loss", "adam_ema_step", "mt_fwd_bwd", "param_count", "param_offset", "new_workspace", "ws_tensor",
-           "mel_filterbank", "num_frames", "workspace_bytes", "scaler_accumulate", "scaler_finalize"]
+           "mel_filterbank", "num_frames", "workspace_bytes", "scaler_accumulate", "scaler_finalize", "bigru_forward", "audio_mixdown"]

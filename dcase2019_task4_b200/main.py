@@ -363,3 +363,67 @@ def train(train_loader, model, optimizer, epoch, ema_model=None, weak_mask=None,
     msg = 'Epoch: {}\tTime {:.2f}\t{meters}'.format(epoch, epoch_time, meters=meters)
     (log.info if log is not None else print)(msg)
     return meters
+
+
+# ---- checkpoint dict (main.py:293-309, :339-356; read back by TestModel.py:26-40) -----------------------------
+def build_state(crnn, optimizer, crnn_kwargs, optim_kwargs, pooling_time_ratio, scaler, many_hot_encoder,
+                crnn_ema=None):
+    """The dict the reference ``torch.save``s: nested model state dicts (CRNN.py:49-53), torch's own optimizer state,
+    the Scaler wire format and the encoder.  ``model_ema`` is absent for main_simple_CRNN (main_simple_CRNN.py:203-215)."""
+    state = {'model': {"name": crnn.__class__.__name__, 'args': '', "kwargs": crnn_kwargs,
+                       'state_dict': crnn.state_dict()}}
+    if crnn_ema is not None:
+        state['model_ema'] = {"name": crnn_ema.__class__.__name__, 'args': '', "kwargs": crnn_kwargs,
+                              'state_dict': crnn_ema.state_dict()}
+    state['optimizer'] = {"name": optimizer.__class__.__name__, 'args': '', "kwargs": optim_kwargs,
+                          'state_dict': optimizer.state_dict()}
+    state["pooling_time_ratio"] = pooling_time_ratio
+    state["scaler"] = scaler.state_dict()
+    state["many_hot_encoder"] = many_hot_encoder.state_dict()
+    return state
+
+
+def update_state(state, crnn, optimizer, epoch, valid_metric=None, crnn_ema=None):
+    """End-of-epoch refresh, main.py:335-339."""
+    state['model']['state_dict'] = crnn.state_dict()
+    if crnn_ema is not None:
+        state['model_ema']['state_dict'] = crnn_ema.state_dict()
+    state['optimizer']['state_dict'] = optimizer.state_dict()
+    state['epoch'] = epoch
+    state['valid_metric'] = valid_metric
+    return state
+
+
+def _to_cpu(obj):
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().cpu().clone()
+    if isinstance(obj, dict):
+        return {k: _to_cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cpu(v) for v in obj)
+    return obj
+
+
+def save_checkpoint(state, model_fname):
+    """``torch.save(state, model_fname)`` (main.py:342, :352) with every tensor detached from the flat device slabs,
+    so the file loads on a machine without a GPU (TestModel.py:75 uses map_location="cpu")."""
+    torch.save(_to_cpu(state), model_fname)
+
+
+def load_checkpoint(model_fname, map_location="cpu"):
+    """``torch.load`` of a reference-format checkpoint; the dict holds lists / floats / sed_eval results next to the
+    tensors, which torch >= 2.6 refuses unless ``weights_only=False``."""
+    return torch.load(model_fname, map_location=map_location, weights_only=False)
+
+
+def restore_from_state(state):
+    """TestModel.py:30-40: (crnn, scaler, many_hot_encoder, pooling_time_ratio) rebuilt from a checkpoint dict --
+    ours or one written by the reference (same keys)."""
+    from .models.CRNN import CRNN
+    from .utils.Scaler import Scaler
+    from .utils.utils import ManyHotEncoder
+    crnn = CRNN(**state["model"]["kwargs"])
+    crnn.load(parameters=state["model"]["state_dict"])
+    scaler = Scaler()
+    scaler.load_state_dict(state["scaler"])
+    return crnn, scaler, ManyHotEncoder.load_state_dict(state["many_hot_encoder"]), state["pooling_time_ratio"]

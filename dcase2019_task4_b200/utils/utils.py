@@ -1,7 +1,8 @@
 """Host-side mirror of ``baseline/utils/utils.py`` (boundary objects that ``main.py`` calls around the replaced
 hot path): ``ManyHotEncoder`` (:22-172, defines the [108,10] target layout), ``weights_init`` (:205-224),
 ``to_cuda_if_available`` (:227-239), ``SaveBest`` (:242-283), ``AverageMeterSet`` / ``AverageMeter`` (:337-394),
-``create_folder`` (:196-202), ``get_transforms`` (:397-412).  ``dcase_util`` is not installed, so the contiguous
+``create_folder`` (:196-202), ``get_transforms`` (:397-412), ``read_audio`` (:175-193, wav container parsed on the
+host, mix-down on the GPU).  ``dcase_util`` is not installed, so the contiguous
 region decode (:146-162) is restated with numpy."""
 import os
 
@@ -91,6 +92,50 @@ class ManyHotEncoder:
     @classmethod
     def load_state_dict(cls, state_dict):
         return cls(state_dict["labels"], state_dict["n_frames"])
+
+
+def read_wav_frames(path):
+    """(interleaved frames [n_frames, n_channels] as int16 PCM or float32, sampling rate) of a RIFF wav file.
+    soundfile is not installed; scipy.io.wavfile parses the container (PCM 8/16/24/32 bit, IEEE float).  16-bit PCM
+    -- what the DCASE wavs are -- stays int16 (the device applies soundfile's 1 / 32768); other encodings are
+    converted to soundfile's float range here."""
+    import scipy.io.wavfile
+    fs, data = scipy.io.wavfile.read(path)
+    if data.ndim == 1:
+        data = data[:, None]
+    if data.dtype == np.int16:
+        pass
+    elif data.dtype == np.int32:
+        data = (data.astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif data.dtype == np.uint8:
+        data = ((data.astype(np.float32) - 128.0) / 128.0).astype(np.float32)
+    else:
+        data = data.astype(np.float32)
+    return np.ascontiguousarray(data), int(fs)
+
+
+def read_audio_device(path, target_fs=None):
+    """read_audio (utils/utils.py:175-193) with the samples left on the GPU: (CUDA float32 mono [n], fs).
+    Multi-channel files are mixed down by the mean (dcase_audio_mixdown); 16-bit PCM is scaled by 1 / 32768."""
+    from .. import kernels as K
+    frames, fs = read_wav_frames(path)
+    if target_fs is not None and fs != target_fs:
+        raise NotImplementedError(
+            "{}: {} Hz, wanted {} Hz -- librosa.resample (utils/utils.py:191) is an unpinned third-party resampler "
+            "(kaiser_best before librosa 0.10, soxr_hq after) and is not rebuilt; resample the file offline".format(
+                path, fs, target_fs))
+    if not torch.cuda.is_available():
+        raise RuntimeError("read_audio feeds the GPU feature extraction (dcase_audio_mixdown); no CPU fallback")
+    dev_frames = torch.from_numpy(frames).cuda(non_blocking=True)
+    if frames.shape[0] == 0:
+        return torch.empty(0, device=dev_frames.device), fs
+    return K.audio_mixdown(dev_frames), fs
+
+
+def read_audio(path, target_fs=None):
+    """Reference signature: (numpy mono waveform, sampling rate)."""
+    audio, fs = read_audio_device(path, target_fs)
+    return audio.cpu().numpy(), fs
 
 
 def create_folder(fd):

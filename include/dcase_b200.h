@@ -103,6 +103,12 @@ int dcase_logmel_fwd(dcase_ctx* ctx, const float* wave, int B, int L, float* mel
 /* Same from 16-bit PCM as stored in the wav files (soundfile scaling 1/32768, utils/utils.py:187). */
 int dcase_logmel_fwd_pcm16(dcase_ctx* ctx, const int16_t* wave, int B, int L, float* mel_amp, void* stream);
 
+/* read_audio's mono mix-down (utils/utils.py:187-189: np.mean(audio, axis=1)): interleaved frames
+ * [n_frames][n_channels] of float32 or 16-bit PCM (scaled by 1 / 32768 like soundfile.read) -> mono float32
+ * [n_frames], ready for dcase_logmel_fwd. */
+int dcase_audio_mixdown(dcase_ctx* ctx, const void* interleaved, int is_pcm16, long long n_frames, int n_channels,
+                        float* mono, void* stream);
+
 /* get_transforms(frames, scaler, augment_type="noise") (utils/utils.py:397-412) on a batch:
  * AugmentGaussianNoise (DataLoad.py:274-287) -> ApplyLog / librosa.amplitude_to_db (DataLoad.py:192-207)
  * -> PadOrTrunc (DataLoad.py:210-259) -> ToTensor -> Normalize / Scaler.normalize (Scaler.py:99-105).
@@ -146,6 +152,15 @@ int dcase_crnn_ws_tensor(int B, int T, int n_class, const char* name, size_t* of
 int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int n_class, const float* params,
                        float* bn_running, int flags, uint64_t seed, uint32_t step, int model_id,
                        const void* scalars, float* strong, float* weak, void* workspace, void* stream);
+
+/* BidirectionalGRU.forward (models/RNN.py:7-16) on its own: nn.GRU(64, 64, num_layers=2, bidirectional=True,
+ * batch_first=True), gate order (r, z, n), zero initial state.  x [B][To][64] -> out [B][To][128] (forward | reverse).
+ * rnn_params points at rnn.rnn.weight_ih_l0 inside the flat slab (or at a copy of the 16 GRU tensors in
+ * named_parameters() order: weight_ih, weight_hh, bias_ih, bias_hh for l0, l0_reverse, l1, l1_reverse = 124,416
+ * floats).  To <= 136 (the sequence is resident in shared memory).  BASELINE.json configs[4] times this entry. */
+size_t dcase_bigru_workspace_bytes(int B, int To);
+int dcase_bigru_forward(dcase_ctx* ctx, const float* x, int B, int To, const float* rnn_params, float* out,
+                        void* workspace, void* stream);
 
 /* Backward of the forward pass that filled `workspace` (same x, params, flags, seed, step, model_id).
  * grads (param_count elements) is overwritten with d loss / d params  (loss.backward(), main.py:153). */

@@ -106,3 +106,35 @@ def test_means_from_waveforms_and_linearity(pkg, cuda_device):
     c = pkg["Scaler"]().means_from_waveforms([pcm], frames)           # 16-bit PCM input (soundfile scaling 1 / 32768)
     d = pkg["Scaler"]().means_from_waveforms([pcm.float() / 32768.0], frames)
     assert np.abs(c.mean_ - d.mean_).max() <= 1e-6 and np.abs(c.mean_ - sc.mean_).max() <= 0.5
+
+
+def test_read_audio_and_feature_cache_from_wav_files(pkg, cuda_device, tmp_path):
+    """wav ingestion (read_audio, utils/utils.py:175-193: stereo mix-down by the mean,
+    16-bit PCM scaled by 1 / 32768) and the reference's cache layout
+    features/sr44100_win2048_hop511_mels64_nolog/features/<name>.npy holding float32 [T, 64] amplitude mels."""
+    import scipy.io.wavfile
+    from dcase2019_task4_b200.DatasetDcase2019Task4 import DatasetDcase2019Task4
+    from dcase2019_task4_b200.utils.utils import read_audio
+    waves, _ = pkg["synth"].make_clips(2, seed=9, n_samples=30000)
+    left = (np.clip(waves[0], -1, 1) * 32767).astype(np.int16)
+    right = (np.clip(waves[1], -1, 1) * 32767).astype(np.int16)
+    scipy.io.wavfile.write(tmp_path / "stereo.wav", 44100, np.stack([left, right], axis=1))
+    scipy.io.wavfile.write(tmp_path / "mono.wav", 44100, left)
+    scipy.io.wavfile.write(tmp_path / "float.wav", 44100, np.stack([waves[0], waves[1]], axis=1))
+    scipy.io.wavfile.write(tmp_path / "slow.wav", 16000, left)
+    audio, fs = read_audio(tmp_path / "stereo.wav", 44100)
+    ref = np.mean(np.stack([left, right], axis=1) / 32768.0, axis=1)          # soundfile.read + np.mean(axis=1)
+    assert fs == 44100 and audio.shape == (30000,) and np.abs(audio - ref).max() <= 1e-7
+    assert np.array_equal(read_audio(tmp_path / "mono.wav")[0], (left / 32768.0).astype(np.float32))
+    assert np.abs(read_audio(tmp_path / "float.wav")[0] - waves.mean(axis=0)).max() <= 1e-7
+    with pytest.raises(NotImplementedError):
+        read_audio(tmp_path / "slow.wav", 44100)
+    ds = DatasetDcase2019Task4(str(tmp_path), base_feature_dir=str(tmp_path / "features"), save_log_feature=False)
+    assert ds.feature_dir.endswith(os.path.join("sr44100_win2048_hop511_mels64_nolog", "features"))
+    done = ds.extract_features_from_files(str(tmp_path), ["stereo.wav", "mono.wav", "missing.wav"])
+    assert done == ["stereo.wav", "mono.wav"]
+    feat = ds.get_feature_file("stereo.wav")
+    assert feat.dtype == np.float32 and feat.shape == (1 + 30000 // 511, 64)
+    want = omel.calculate_mel_spec(ref)
+    assert np.abs(feat - want).max() <= 2e-5 * want.max()                     # same bar as tests/test_gpu_logmel.py
+    assert np.array_equal(np.load(os.path.join(ds.feature_dir, "mono.npy")), ds.calculate_mel_spec(left / 32768.0))

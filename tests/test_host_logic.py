@@ -227,3 +227,54 @@ def test_segment_based_metric_and_empty_files():
     ev = em.compute_strong_metrics(est, ref).results()
     assert ev["overall"]["count"] == {"Nref": 1, "Nsys": 1, "Ntp": 0}
     assert em.get_event_list_current_file(ref, "b.wav") == []
+
+
+def test_checkpoint_dict_matches_reference_layout(tmp_path):
+    """main.py:293-309 / :335-356 / TestModel.py:26-40: same keys, nested model state dicts, loadable on CPU."""
+    from dcase2019_task4_b200 import main as bmain
+    from dcase2019_task4_b200 import main_simple_CRNN as simple
+    crnn, ema = CRNN(**cfg.crnn_kwargs), CRNN(**cfg.crnn_kwargs)
+    crnn.apply(weights_init)
+    optim_kwargs = {"lr": 0.001, "betas": (0.9, 0.999)}
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, crnn.parameters()), **optim_kwargs)
+    sc = Scaler()
+    sc.load_state_dict({"mean_": list(range(64)), "mean_of_square_": [float(i * i + 4) for i in range(64)]})
+    enc = ManyHotEncoder(cfg.classes, n_frames=cfg.max_frames // cfg.pooling_time_ratio)
+    state = bmain.build_state(crnn, opt, cfg.crnn_kwargs, optim_kwargs, cfg.pooling_time_ratio, sc, enc, crnn_ema=ema)
+    assert list(state) == ["model", "model_ema", "optimizer", "pooling_time_ratio", "scaler", "many_hot_encoder"]
+    assert list(state["model"]) == ["name", "args", "kwargs", "state_dict"] and state["model"]["name"] == "CRNN"
+    assert set(state["model"]["state_dict"]) == {"cnn", "rnn", "dense"} and state["optimizer"]["name"] == "Adam"
+    bmain.update_state(state, crnn, opt, 3, valid_metric={"overall": {"f_measure": {"f_measure": 0.25}}}, crnn_ema=ema)
+    bmain.save_checkpoint(state, tmp_path / "baseline_epoch_3")
+    back = bmain.load_checkpoint(tmp_path / "baseline_epoch_3")
+    assert back["epoch"] == 3 and back["valid_metric"]["overall"]["f_measure"]["f_measure"] == 0.25
+    m2, sc2, enc2, ptr = bmain.restore_from_state(back)
+    assert ptr == cfg.pooling_time_ratio and enc2.labels == cfg.classes and np.array_equal(sc2.std_, sc.std_)
+    for k in ("cnn.cnn.conv1.weight", "rnn.rnn.weight_hh_l1_reverse", "dense.bias"):
+        assert torch.equal(dict(m2.named_parameters())[k], dict(crnn.named_parameters())[k])
+    simple_state = bmain.build_state(crnn, opt, cfg.crnn_kwargs, optim_kwargs, cfg.pooling_time_ratio, sc, enc)
+    assert "model_ema" not in simple_state                       # main_simple_CRNN.py:203-215
+    assert simple.masks_for(24) == (slice(12), slice(12, 24)) and simple.masks_for(24, no_weak=True) == (None, slice(24))
+
+
+def test_wav_container_parsing_and_loud_failures(tmp_path):
+    """read_audio's host half (utils/utils.py:175-193): container parsing keeps 16-bit PCM as int16 frames, maps other
+    encodings to soundfile's float range; resampling and CPU execution fail loudly."""
+    import scipy.io.wavfile
+    from dcase2019_task4_b200.utils.utils import read_audio, read_wav_frames
+    rng = np.random.default_rng(0)
+    pcm = rng.integers(-32768, 32767, (1000, 2)).astype(np.int16)
+    scipy.io.wavfile.write(tmp_path / "a.wav", 44100, pcm)
+    scipy.io.wavfile.write(tmp_path / "b.wav", 22050, (pcm[:, 0].astype(np.int32) << 16))
+    scipy.io.wavfile.write(tmp_path / "c.wav", 44100, (pcm[:, 0] / 32768.0).astype(np.float32))
+    frames, fs = read_wav_frames(tmp_path / "a.wav")
+    assert fs == 44100 and frames.dtype == np.int16 and np.array_equal(frames, pcm)
+    frames, fs = read_wav_frames(tmp_path / "b.wav")
+    assert fs == 22050 and frames.shape == (1000, 1) and np.allclose(frames[:, 0], pcm[:, 0] / 32768.0)
+    frames, _ = read_wav_frames(tmp_path / "c.wav")
+    assert frames.dtype == np.float32 and np.allclose(frames[:, 0], pcm[:, 0] / 32768.0)
+    with pytest.raises(NotImplementedError):
+        read_audio(tmp_path / "b.wav", 44100)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            read_audio(tmp_path / "a.wav", 44100)

@@ -148,3 +148,43 @@ def test_scaler_means_match_reference_scaler(tmp_path, monkeypatch):
     assert np.abs(omel.scaler_std(m, m2) - std).max() < 1e-11
     sd = sc.state_dict()
     assert set(sd) == {"mean_", "mean_of_square_"} and isinstance(sd["mean_"], list) and len(sd["mean_"]) == 64
+
+
+def test_our_checkpoint_loads_into_reference_modules(tmp_path, monkeypatch):
+    """A checkpoint written by dcase2019_task4_b200.main.save_checkpoint is consumed by the reference's own
+    TestModel.py:30-38 recipe (CRNN(**kwargs).load(parameters=...), Scaler.load_state_dict) and gives the same
+    eval posteriors as the oracle with those parameters."""
+    from dcase2019_task4_b200 import config as cfg, main as bmain
+    from dcase2019_task4_b200.models.CRNN import CRNN as OurCRNN
+    from dcase2019_task4_b200.utils.Scaler import Scaler as OurScaler
+    from dcase2019_task4_b200.utils.utils import ManyHotEncoder
+    monkeypatch.chdir(tmp_path)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from utils.Scaler import Scaler as RefScaler
+    p = ocrnn.init_params(seed=9)
+    ours = OurCRNN(**cfg.crnn_kwargs)
+    with torch.no_grad():
+        for k, v in ours.named_parameters():
+            v.copy_(p[k])
+    opt = torch.optim.Adam(ours.parameters(), lr=0.001, betas=(0.9, 0.999))
+    sc = OurScaler()
+    sc.load_state_dict({"mean_": np.linspace(-5, 5, 64).tolist(), "mean_of_square_": np.linspace(30, 90, 64).tolist()})
+    enc = ManyHotEncoder(cfg.classes, n_frames=108)
+    state = bmain.build_state(ours, opt, cfg.crnn_kwargs, {"lr": 0.001, "betas": (0.9, 0.999)}, 8, sc, enc)
+    bmain.save_checkpoint(bmain.update_state(state, ours, opt, 0), tmp_path / "ck")
+    back = torch.load(tmp_path / "ck", map_location="cpu", weights_only=False)      # TestModel.py:75
+    ref = ref_crnn(**{k: v for k, v in back["model"]["kwargs"].items() if k not in CRNN_KWARGS})
+    ref.load(parameters=back["model"]["state_dict"])
+    rs = RefScaler()
+    rs.load_state_dict(back["scaler"])
+    assert np.array_equal(rs.std_, sc.std_)
+    x = torch.randn(2, 1, 64, 64)
+    ref.eval()
+    with torch.no_grad():
+        s_ref, _ = ref(x)
+        pp = dict(p)
+        pp["dense_softmax.weight"] = dict(ref.named_parameters())["dense_softmax.weight"].detach()   # not in the checkpoint
+        pp["dense_softmax.bias"] = dict(ref.named_parameters())["dense_softmax.bias"].detach()
+        s, _ = ocrnn.crnn_forward(x, pp, ocrnn.init_buffers(), training=False)
+    assert float((s - s_ref).abs().max()) < 2e-6
