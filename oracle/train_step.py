@@ -111,8 +111,10 @@ def train_batch(student_p, student_buf, adam_state, x, target, global_step, step
     loss, meters = mean_teacher_losses(strong, weak, strong_t, weak_t, target, weak_mask, strong_mask, cons_w)
     assert not (math.isnan(meters["Loss"]) or meters["Loss"] > 1e5), "Loss explosion"
     assert not meters["Loss"] < 0, "Loss problem, cannot be negative"
-    glist = torch.autograd.grad(loss, list(sp.values()))
-    grads = dict(zip(sp.keys(), glist))
+    # loss.backward() leaves .grad = None on parameters outside the graph (the attention head when weak_mask is None,
+    # main_simple_CRNN.py --no_weak) and Adam skips them: a zero gradient gives the same (unchanged) value
+    glist = torch.autograd.grad(loss, list(sp.values()), allow_unused=True)
+    grads = {k: (torch.zeros_like(v) if g is None else g) for (k, v), g in zip(sp.items(), glist)}
     adam_update(student_p, grads, adam_state, lr=lr)
     if teacher_p is not None:
         a = ema_alpha(global_step + 1)
