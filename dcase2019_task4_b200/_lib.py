@@ -77,7 +77,7 @@ SIGNATURES = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()     # re-entrant: ctx() loads the library (lib()) while holding it
 _ctx = {}
 
 
@@ -121,12 +121,13 @@ def ctx(device=None):
         device = torch.cuda.current_device()
     device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
+    handle = lib()                       # load (and lock) before taking the context lock
     if idx not in _ctx:
         with _lock:
             if idx not in _ctx:
                 h = c_p()
                 with torch.cuda.device(idx):
-                    check(lib().dcase_ctx_create(ctypes.byref(h), idx))
+                    check(handle.dcase_ctx_create(ctypes.byref(h), idx))
                 _ctx[idx] = h
     return _ctx[idx]
 

@@ -69,3 +69,40 @@ def test_no_cpu_fallback(lib):
     m = CRNN(**cfg.crnn_kwargs)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 864, 64))
+
+
+def test_ctx_as_first_call_does_not_deadlock(monkeypatch):
+    """Regression: ``_lib.ctx()`` used to take the module lock and then call ``lib()``, which takes it again -- a
+    deadlock whenever a context was requested before anything else had loaded the library (the GPU Scaler tests run
+    alone).  Here the library loads on the CPU, the context creation itself fails (no GPU) and must raise promptly."""
+    import contextlib
+    import threading
+    import torch
+    from dcase2019_task4_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_ctx", {})
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda idx: contextlib.nullcontext())
+    outcome = {}
+
+    def run():
+        try:
+            _lib.ctx()
+            outcome["result"] = "created"
+        except _lib.DcaseError as e:
+            outcome["result"] = "raised: %s" % e
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    t.join(timeout=20)
+    assert not t.is_alive(), "ctx() deadlocked on the library lock"
+    if not torch.backends.cuda.is_built() or not _real_cuda_available():
+        assert outcome["result"].startswith("raised")
+
+
+def _real_cuda_available():
+    import subprocess
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, timeout=10).returncode == 0
+    except (OSError, subprocess.TimeoutExpired):
+        return False
