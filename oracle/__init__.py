@@ -20,7 +20,9 @@ The reference ships NO tests, golden vectors or fixtures, 
   own ``baseline/models/CRNN.py`` imported unmodified from ``/root/reference``
   (``tests/test_oracle_vs_reference.py``, and the committed fixtures made by
   ``tests/golden/make_golden.py``).
-* ``oracle.mel`` restates librosa's published algorithm (un-vendored, unpinned
+* ``oracle.mel.scaler_means`` / ``scaler_std`` are pinned against the reference's own ``baseline/utils/Scaler.py``
+  (live and through ``tests/golden/scaler_reference.npz``).
+* the rest of ``oracle.mel`` restates librosa's published algorithm (un-vendored, unpinned
   third-party dependency, environment.yml:17) and is cross-checked against
   ``torch.stft`` and ``torchaudio.functional.melscale_fbanks``:
   **parity unpinned** against librosa itself.
