@@ -237,7 +237,8 @@ def run_b200(args, rank, local_rank, world):
     optimizer = torch.optim.Adam(filter(lambda p: p.requires_grad, crnn.parameters()), lr=0.001, betas=(0.9, 0.999))
     weak_mask = slice(BATCH_SIZES[0])
     strong_mask = slice(BATCH_SIZES[0] + BATCH_SIZES[1], B_PER_GPU)
-    use_graph = world == 1 and os.environ.get("DCASE_NO_GRAPH", "0") != "1"
+    # data-parallel steps launch eagerly unless DCASE_DP_GRAPH=1 opts into capturing the NCCL all-reduce (unverified)
+    use_graph = (world == 1 or os.environ.get("DCASE_DP_GRAPH", "0") == "1") and os.environ.get("DCASE_NO_GRAPH", "0") != "1"
     engine = MeanTeacherEngine(crnn, optimizer, crnn_ema, weak_mask, strong_mask, B_PER_GPU, FRAMES, use_graph=use_graph)
     rampup_length = STEPS_PER_EPOCH * cfg.n_epoch // 2
 

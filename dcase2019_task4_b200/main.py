@@ -92,9 +92,11 @@ class MeanTeacherEngine(object):
         # per (waveform, target, scaler) buffer set; everything that changes from step to step (Philox seed / step,
         # consistency weight, EMA alpha, lr, Adam bias corrections) lives in a 40-byte device struct the kernels read.
         self.use_graph = (self.world == 1 and os.environ.get("DCASE_NO_GRAPH", "0") != "1") if use_graph is None else bool(use_graph)
-        if self.use_graph and self.world > 1:
-            # capturing the NCCL all-reduce with the rest of the iteration hung on the 2-GPU box (round 1 experiment),
-            # so data-parallel steps launch eagerly
+        if self.use_graph and self.world > 1 and os.environ.get("DCASE_DP_GRAPH", "0") != "1":
+            # capturing the NCCL all-reduce with the rest of the iteration hung on the 2-GPU box (round 1 experiment,
+            # default "global" capture mode: the NCCL watchdog thread's event queries are illegal during a global
+            # capture), so data-parallel steps launch eagerly.  DCASE_DP_GRAPH=1 opts into the thread-local capture
+            # below -- UNVERIFIED on hardware, run it under a short timeout
             raise NotImplementedError("graph replay is wired for single-GPU steps (the NCCL all-reduce runs eagerly)")
         self._graphs = {}
         self.graph_launches = 0            # kernels launched through graph replays (bench.py's gpu_launches)
@@ -195,7 +197,7 @@ class MeanTeacherEngine(object):
         sc["ema_alpha"] = min(1 - 1 / (global_step_after + 1), 0.999)
         sc["lr"] = g["lr"]
         sc["bc1"], sc["bc2"] = 1.0 - g["betas"][0] ** t, 1.0 - g["betas"][1] ** t
-        sc["grad_scale"] = 1.0
+        sc["grad_scale"] = 1.0 / self.world
         with torch.cuda.device(self.dev):
             self._sc_host.copy_(torch.from_numpy(sc.view(np.uint8)))
             self._sc_dev.copy_(self._sc_host, non_blocking=True)
@@ -205,7 +207,7 @@ class MeanTeacherEngine(object):
             if entry is None:
                 graph = torch.cuda.CUDAGraph()
                 l0 = K.launch_count()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
                     scp = self._sc_dev.data_ptr()
                     amp = K.logmel_fwd(wave)
                     if ema is not None:
@@ -214,6 +216,8 @@ class MeanTeacherEngine(object):
                     else:
                         x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None
                     K.mt_fwd_bwd(self._mt_args(x, x_ema, target, model.forward_flags(), 0, 0, 0.0, scp))
+                    if self.world > 1:                     # opt-in (DCASE_DP_GRAPH=1): the all-reduce as a graph node
+                        dp.allreduce_grads_(self.grads, self.pg)
                     K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
                                     ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
                                     beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
