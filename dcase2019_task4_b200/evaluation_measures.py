@@ -17,6 +17,10 @@ Mirrors the part of the reference's ``baseline/evaluation_measures.py`` that sit
   PARITY UNPINNED against sed_eval itself (no copy to run, no golden vectors upstream); ``tests/test_host_logic.py``
   pins the definitions on hand-computed cases.
 
+* ``get_f_measure_by_class`` / ``intermediate_at_measures`` / ``macro_f_measure`` (evaluation_measures.py:19-122,
+  :183-199): the per-class weak F-measure main.py logs every epoch (dcase_util's global / class threshold binarisation
+  restated as ``>``).
+
 Host-side code: the only device work is the batched model forward.
 """
 import math
@@ -73,6 +77,58 @@ def get_predictions(model, valid_dataset, decoder, pooling_time_ratio=1, save_pr
     if save_predictions is not None:
         prediction_df.to_csv(save_predictions, index=False, sep="\t")
     return prediction_df
+
+
+# ------------------------------------------------------------------------------------------------------------
+# weak (audio tagging) F-measure per class, evaluation_measures.py:19-122, :183-199
+# ------------------------------------------------------------------------------------------------------------
+def intermediate_at_measures(encoded_ref, encoded_est):
+    """(tp, fp, fn, tn) per class of two 0/1 arrays [n, classes] (evaluation_measures.py:85-101)."""
+    tp = (encoded_est + encoded_ref == 2).sum(axis=0)
+    fp = (encoded_est - encoded_ref == 1).sum(axis=0)
+    fn = (encoded_ref - encoded_est == 1).sum(axis=0)
+    tn = (encoded_est + encoded_ref == 0).sum(axis=0)
+    return tp, fp, fn, tn
+
+
+def macro_f_measure(tp, fp, fn):
+    """2 tp / (2 tp + fp + fn) per class, 0 where the denominator is empty (evaluation_measures.py:183-199)."""
+    tp, fp, fn = np.asarray(tp, dtype=float), np.asarray(fp, dtype=float), np.asarray(fn, dtype=float)
+    out = np.zeros(tp.shape[-1])
+    mask = 2 * tp + fp + fn != 0
+    out[mask] = 2 * tp[mask] / (2 * tp + fp + fn)[mask]
+    return out
+
+
+def get_f_measure_by_class(torch_model, nb_tags, dataloader_, thresholds_=None):
+    """The "Valid weak metric" of main.py:326-331: F-measure per class of the clip-level (weak) predictions over a
+    loader of ``(batch_x, y)``.  Same conventions as the reference: frame-level labels / predictions are reduced by
+    the maximum over time, probabilities are binarised with ``> 0.5`` (dcase_util ``global_threshold``) or per-class
+    thresholds.  The forward runs on the model's device; the counting is host arithmetic on [batch, classes]."""
+    import torch
+
+    device = (torch_model.flat_parameters().device if hasattr(torch_model, "flat_parameters")
+              else next(torch_model.parameters()).device)
+    tp, tn, fp, fn = (np.zeros(nb_tags) for _ in range(4))
+    if thresholds_ is not None:
+        assert type(thresholds_) is list
+    thresh = 0.5 if thresholds_ is None else np.asarray(thresholds_, dtype=float)[None, :]
+    with torch.no_grad():
+        for batch_x, y in dataloader_:
+            _, pred_weak = torch_model(batch_x.to(device))
+            pred_weak = pred_weak.float().cpu().numpy()
+            labels = y.cpu().numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
+            if pred_weak.ndim == 3:                      # a model predicting only strong outputs
+                pred_weak = np.max(pred_weak, axis=1)
+            if labels.ndim == 3:
+                labels = (np.max(labels, axis=1) > 0.5).astype(int)
+            batch_predictions = (pred_weak > thresh).astype(int)
+            tp_, fp_, fn_, tn_ = intermediate_at_measures(labels, batch_predictions)
+            tp += tp_
+            fp += fp_
+            fn += fn_
+            tn += tn_
+    return macro_f_measure(tp, fp, fn)
 
 
 # ------------------------------------------------------------------------------------------------------------

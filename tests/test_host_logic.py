@@ -278,3 +278,39 @@ def test_wav_container_parsing_and_loud_failures(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             read_audio(tmp_path / "a.wav", 44100)
+
+
+def test_weak_f_measure_by_class_hand_computed():
+    """evaluation_measures.get_f_measure_by_class (evaluation_measures.py:19-82) on a stub model: counts by hand."""
+    from dcase2019_task4_b200 import evaluation_measures as em
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, x):                 # weak posterior = the first three features of frame 0
+            return x[:, 0, :, :3].repeat(1, 4, 1), x[:, 0, 0, :3]
+
+    def batch(weak, labels):
+        x = torch.zeros(len(weak), 1, 4, 64)
+        x[:, 0, 0, :3] = torch.tensor(weak)
+        return x, torch.tensor(labels, dtype=torch.float32)
+
+    loader = [batch([[0.9, 0.2, 0.5], [0.8, 0.7, 0.1]], [[1, 0, 0], [0, 1, 0]]),
+              batch([[0.1, 0.6, 0.4], [0.6, 0.4, 0.3]], [[1, 1, 0], [1, 0, 0]])]
+    # class 0: est 1,1,0,1 vs ref 1,0,1,1 -> tp 2 fp 1 fn 1 -> 4/6;  class 1: est 0,1,1,0 vs ref 0,1,1,0 -> 1.0
+    # class 2: est 0 (0.5 is not > 0.5),0,0,0 vs ref 0 -> empty denominator -> 0
+    f = em.get_f_measure_by_class(Stub(), 3, loader)
+    assert np.allclose(f, [4 / 6, 1.0, 0.0])
+    f = em.get_f_measure_by_class(Stub(), 3, loader, thresholds_=[0.85, 0.5, 0.45])
+    # class 0 @0.85: est 1,0,0,0 -> tp 1 fn 2 -> 2/4;  class 2 @0.45: est 1,0,0,0 vs ref 0 -> fp 1 -> 0
+    assert np.allclose(f, [0.5, 1.0, 0.0])
+    # frame-level labels are reduced by the maximum over time
+    x, y = loader[0]
+    y3 = torch.zeros(2, 5, 3)
+    y3[0, 2, 0] = 1
+    y3[1, 4, 1] = 1
+    assert np.allclose(em.get_f_measure_by_class(Stub(), 3, [(x, y3)]), em.get_f_measure_by_class(Stub(), 3, [(x, y)]))
+    tp, fp, fn, tn = em.intermediate_at_measures(np.array([[1, 0], [0, 0]]), np.array([[1, 1], [0, 0]]))
+    assert (tp.tolist(), fp.tolist(), fn.tolist(), tn.tolist()) == ([1, 0], [0, 1], [0, 0], [1, 1])
