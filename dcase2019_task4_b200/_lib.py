@@ -64,6 +64,9 @@ SIGNATURES = {
     "dcase_crnn_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_u64, c_u32, c_i, c_p, c_p, c_p, c_p, c_p]),
     "dcase_bigru_workspace_bytes": (c_sz, [c_i, c_i]),
     "dcase_bigru_forward": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "dcase_bigru_param_count_h": (c_sz, [c_i, c_i]),
+    "dcase_bigru_workspace_bytes_h": (c_sz, [c_i, c_i, c_i]),
+    "dcase_bigru_forward_h": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "dcase_crnn_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_u64, c_u32, c_i, c_p, c_p, c_p, c_p, c_p,
                                   c_p, c_p]),
     "dcase_mt_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p,

@@ -193,6 +193,23 @@ def bigru_forward(x, rnn_params, out=None, ws=None):
     return out
 
 
+def bigru_forward_h(x, rnn_params, hidden, out=None, ws=None):
+    """EXPERIMENTAL cluster BiGRU for hidden 128 / 256 (csrc/gru_cluster.cu; not yet run on hardware):
+    x [B, To, n_in] -> [B, To, 2 * hidden]; rnn_params = nn.GRU's 16 tensors flattened in named_parameters() order."""
+    x = _f32(x)
+    B, To, n_in = x.shape
+    assert rnn_params.numel() == lib().dcase_bigru_param_count_h(n_in, hidden)
+    dev = x.device
+    if out is None:
+        out = torch.empty(B, To, 2 * hidden, device=dev, dtype=torch.float32)
+    if ws is None:
+        ws = torch.empty(lib().dcase_bigru_workspace_bytes_h(B, To, hidden), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().dcase_bigru_forward_h(ctx(dev), ptr(x), B, To, n_in, hidden, ptr(_f32(rnn_params)), ptr(out), ptr(ws),
+                                          stream_ptr()))
+    return out
+
+
 def _slice_bounds(mask, B):
     if mask is None:
         return 0, 0
@@ -259,4 +276,4 @@ def mt_fwd_bwd(args):
 
 __all__ = ["FLAG_BN_BATCH_STATS", "FLAG_DROPOUT", "logmel_fwd", "logmel_finish", "crnn_forward", "crnn_backward",
            "mt_loss", "adam_ema_step", "mt_fwd_bwd", "param_count", "param_offset", "new_workspace", "ws_tensor",
-           "mel_filterbank", "num_frames", "workspace_bytes", "scaler_accumulate", "scaler_finalize", "bigru_forward", "audio_mixdown"]
+           "mel_filterbank", "num_frames", "workspace_bytes", "scaler_accumulate", "scaler_finalize", "bigru_forward", "bigru_forward_h", "audio_mixdown"]

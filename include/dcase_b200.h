@@ -162,6 +162,16 @@ size_t dcase_bigru_workspace_bytes(int B, int To);
 int dcase_bigru_forward(dcase_ctx* ctx, const float* x, int B, int To, const float* rnn_params, float* out,
                         void* workspace, void* stream);
 
+/* EXPERIMENTAL (compiles, not yet run on hardware): the same operator for hidden sizes 128 / 256 (the other
+ * points of BASELINE.json configs[4]), nn.GRU(n_in, H, num_layers=2, bidirectional=True, batch_first=True).
+ * x [B][To][n_in] -> out [B][To][2H]; rnn_params = the 16 tensors in named_parameters() order
+ * (dcase_bigru_param_count_h floats).  The recurrence of one (direction, 4 clips) runs on a thread-block cluster
+ * of H / 32 CTAs that exchange h through distributed shared memory (csrc/gru_cluster.cu); no length limit. */
+size_t dcase_bigru_param_count_h(int n_in, int H);
+size_t dcase_bigru_workspace_bytes_h(int B, int To, int H);
+int dcase_bigru_forward_h(dcase_ctx* ctx, const float* x, int B, int To, int n_in, int H, const float* rnn_params,
+                          float* out, void* workspace, void* stream);
+
 /* Backward of the forward pass that filled `workspace` (same x, params, flags, seed, step, model_id).
  * grads (param_count elements) is overwritten with d loss / d params  (loss.backward(), main.py:153). */
 int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int n_class, const float* params, int flags,

@@ -71,6 +71,17 @@ def test_no_cpu_fallback(lib):
         m(torch.zeros(1, 1, 864, 64))
 
 
+def test_bigru_parameter_layout_matches_nn_gru():
+    """Host arithmetic only: the experimental cluster BiGRU reads nn.GRU's tensors in named_parameters() order."""
+    import torch
+    from dcase2019_task4_b200 import _lib
+    for H in (64, 128, 256):
+        gru = torch.nn.GRU(64, H, num_layers=2, bidirectional=True, batch_first=True)
+        assert _lib.lib().dcase_bigru_param_count_h(64, H) == sum(p.numel() for p in gru.parameters())
+    assert _lib.lib().dcase_bigru_workspace_bytes_h(24, 108, 256) == 24 * 108 * (6 * 256 + 2 * 256) * 4
+    assert _lib.lib().dcase_bigru_workspace_bytes(24, 108) == 24 * 108 * (6 * 64 + 2 * 64) * 4
+
+
 def test_ctx_as_first_call_does_not_deadlock(monkeypatch):
     """Regression: ``_lib.ctx()`` used to take the module lock and then call ``lib()``, which takes it again -- a
     deadlock whenever a context was requested before anything else had loaded the library (the GPU Scaler tests run

@@ -3,7 +3,7 @@ T = 108 (cfg.max_frames // pooling_time_ratio), batch {24, 256}.
 
 Hidden size 64 (the only one cfg.crnn_kwargs selects) runs through dcase_bigru_forward; every (H, B) point is also
 timed through cuDNN (torch.nn.GRU on the same GPU, fp32, TF32 off) as the library baseline SURVEY.md section 8d asks
-for.  H = 128 / 256 are NOT built in this library (recorded as null).  FLOPs (forward) =
+for.  H = 128 / 256 run through the experimental cluster kernel only under DCASE_EXPERIMENTAL=1 (null otherwise).  FLOPs (forward) =
 2 B T [(In 3H + H 3H) + (2H 3H + H 3H)] 2.  Writes gpurun_out/gru_sweep.json and prints it.
 
     python tools/gru_sweep.py [--iters 200]
@@ -62,6 +62,13 @@ def main():
                 out = torch.empty(B, T, 128, device=dev)
                 ws = torch.empty(K.lib().dcase_bigru_workspace_bytes(B, T), dtype=torch.uint8, device=dev)
                 ours_ms = time_ms(lambda: K.bigru_forward(x, flat, out=out, ws=ws), args.iters)
+                with torch.no_grad():
+                    err = float((out - gru(x)[0]).abs().max())
+            elif os.environ.get("DCASE_EXPERIMENTAL", "0") == "1":       # cluster BiGRU (csrc/gru_cluster.cu)
+                flat = torch.cat([p.detach().reshape(-1) for _, p in gru.named_parameters()]).contiguous()
+                out = torch.empty(B, T, 2 * H, device=dev)
+                ws = torch.empty(K.lib().dcase_bigru_workspace_bytes_h(B, T, H), dtype=torch.uint8, device=dev)
+                ours_ms = time_ms(lambda: K.bigru_forward_h(x, flat, H, out=out, ws=ws), args.iters)
                 with torch.no_grad():
                     err = float((out - gru(x)[0]).abs().max())
             f = flops(B, H)
