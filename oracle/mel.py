@@ -18,8 +18,9 @@ Follows, stage by stage:
 librosa (un-vendored, unpinned: ``environment.yml:17``, README ">=0.6.3") is
 not installed here, so the four librosa calls are restated from its published
 algorithm.  PARITY UNPINNED against librosa itself; cross-checked in
-``tests/test_oracle_mel.py`` against ``torch.stft`` and
-``torchaudio.functional.melscale_fbanks``.
+``tests/test_oracle_golden.py`` against ``torch.stft``,
+``torchaudio.functional.melscale_fbanks`` and ``transformers.audio_utils``
+(spectrogram / mel_filter_bank / amplitude_to_db).
 """
 import numpy as np
 

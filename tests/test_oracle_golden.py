@@ -93,6 +93,26 @@ def test_oracle_filterbank_matches_torchaudio():
     assert np.abs(omel.mel_filterbank() - ref).max() < 1e-5       # torchaudio computes it in float32
 
 
+def test_oracle_mel_chain_matches_transformers_audio_utils():
+    """Third independent implementation: ``transformers.audio_utils`` (numpy, written upstream to reproduce librosa's
+    stft / filters.mel / amplitude_to_db).  librosa itself is still absent, so the oracle stays "parity unpinned", but
+    window / centering / reflect padding / frame count / Slaney filterbank / dB floor all agree."""
+    au = pytest.importorskip("transformers.audio_utils")
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(30000) * 0.1
+    y[20000:] = 0.0                                                  # exercises amin and the top_db floor
+    fb = au.mel_filter_bank(num_frequency_bins=1025, num_mel_filters=64, min_frequency=0.0, max_frequency=22050.0,
+                            sampling_rate=44100, norm=None, mel_scale="slaney")
+    assert np.abs(fb.T - omel.mel_filterbank()).max() < 1e-6
+    S = au.spectrogram(y, np.hamming(2048), frame_length=2048, hop_length=511, fft_length=2048, power=1.0, center=True,
+                       pad_mode="reflect", onesided=True, mel_filters=fb, mel_floor=0.0)
+    ref = omel.calculate_mel_spec(y)
+    assert S.T.shape == ref.shape == (1 + 30000 // 511, 64)
+    assert np.abs(S.T - ref).max() <= 2e-7 * ref.max() + 1e-6        # ours is rounded to float32 (DatasetDcase2019Task4.py:230)
+    db = au.amplitude_to_db(ref.astype(np.float64).T, reference=1.0, min_value=1e-5, db_range=80.0)
+    assert np.abs(db - omel.amplitude_to_db(ref.astype(np.float64).T)).max() < 1e-9
+
+
 def test_amplitude_to_db_top_db_and_amin():
     S = np.array([[1.0, 1e-7, 0.0], [10.0, 1e-3, 1e-5]])
     L = omel.amplitude_to_db(S)
