@@ -1,56 +1,51 @@
-"""Hyper-parameters of the reference (baseline/config.py), kept verbatim in value and name.
+"""Hyper-parameters of the reference (``baseline/config.py``): every module-level name the reference's code reads
+through ``import config as cfg`` exists here with the same value (``tests/test_oracle_vs_reference.py`` compares the two
+modules attribute by attribute).
 
-The reference derives ``classes`` by reading validation.tsv at import (config.py:50-51); the tsv is not part of
-this repo, so the resulting sorted list is stated directly."""
+Differences in form only: the reference derives ``classes`` by reading ``validation.tsv`` at import time
+(config.py:50-51); that table is not part of this repo, so the resulting sorted list is stated directly
+(SURVEY.md section 10).  Quantities the B200 kernels compile in (44.1 kHz, 2048 / 511 STFT, 64 mel bins, 64-channel
+CNN, 64-cell 2-layer BiGRU, pooling (2, 4) x 3) are fixed in ``csrc/``: changing them here does not re-shape the
+kernels; ``models.CRNN.CRNN`` / ``models.CNN.CNN`` raise for constructor arguments other than ``crnn_kwargs``'.
+"""
 import math
 
+# ---- where the reference looks for its metadata (relative to ``workspace``) ------------------------------------
 workspace = ".."
-weak = 'dataset/metadata/train/weak.tsv'
-unlabel = 'dataset/metadata/train/unlabel_in_domain.tsv'
-synthetic = 'dataset/metadata/train/synthetic.tsv'
-validation = 'dataset/metadata/validation/validation.tsv'
-test2018 = 'dataset/metadata/validation/test_dcase2018.tsv'
-eval2018 = 'dataset/metadata/validation/eval_dcase2018.tsv'
-eval_desed = "dataset/metadata/eval/public.tsv"
+_META = "dataset/metadata"
+weak, unlabel, synthetic = ("%s/train/%s.tsv" % (_META, name) for name in ("weak", "unlabel_in_domain", "synthetic"))
+validation, test2018, eval2018 = ("%s/validation/%s.tsv" % (_META, name)
+                                  for name in ("validation", "test_dcase2018", "eval_dcase2018"))
+eval_desed = "%s/eval/public.tsv" % _META
 
-sample_rate = 44100
-n_window = 2048
-hop_length = 511
-n_mels = 64
+# ---- feature extraction: what dcase_logmel_fwd implements ------------------------------------------------------
+sample_rate, n_window, hop_length, n_mels = 44100, 2048, 511, 64
+f_min, f_max = 0., sample_rate / 2                                    # 22050.
 max_len_seconds = 10.
-max_frames = math.ceil(max_len_seconds * sample_rate / hop_length)   # 864
+max_frames = math.ceil(max_len_seconds * sample_rate / hop_length)    # 864 frames of a 10-s clip
 
-f_min = 0.
-f_max = 22050.
+# ---- model: what dcase_crnn_forward / _backward implement -------------------------------------------------------
+classes = ["Alarm_bell_ringing", "Blender", "Cat", "Dishes", "Dog", "Electric_shaver_toothbrush", "Frying",
+           "Running_water", "Speech", "Vacuum_cleaner"]
+_N_BLOCKS = 3
+crnn_kwargs = dict(n_in_channel=1, nclass=len(classes), attention=True, n_RNN_cell=64, n_layers_RNN=2,
+                   activation="glu", dropout=0.5,
+                   kernel_size=_N_BLOCKS * [3], padding=_N_BLOCKS * [1], stride=_N_BLOCKS * [1],
+                   nb_filters=_N_BLOCKS * [64], pooling=_N_BLOCKS * [(2, 4)])
+pooling_time_ratio = 2 ** _N_BLOCKS                                   # time pooling of the three blocks: 8
 
-lr = 0.0001
-initial_lr = 0.
-beta1_before_rampdown = 0.9
-beta1_after_rampdown = 0.5
-beta2_during_rampdup = 0.99
-beta2_after_rampup = 0.999
-weight_decay_during_rampup = 0.99
-weight_decay_after_rampup = 0.999
-
-max_consistency_cost = 2
-max_learning_rate = 0.001
-
-median_window = 5
-
-num_workers = 12
+# ---- training loop (main.py) -------------------------------------------------------------------------------------
 batch_size = 24
 n_epoch = 100
-
+num_workers = 12
+max_consistency_cost = 2          # consistency weight after the sigmoid ramp-up (main.py:127)
+max_learning_rate = 0.001
+median_window = 5                 # frames of the posterior median filter (evaluation_measures.py:214)
 checkpoint_epochs = 1
 save_best = True
 
-classes = ["Alarm_bell_ringing", "Blender", "Cat", "Dishes", "Dog", "Electric_shaver_toothbrush", "Frying",
-           "Running_water", "Speech", "Vacuum_cleaner"]
-
-crnn_kwargs = {"n_in_channel": 1, "nclass": len(classes), "attention": True, "n_RNN_cell": 64,
-               "n_layers_RNN": 2,
-               "activation": "glu",
-               "dropout": 0.5,
-               "kernel_size": 3 * [3], "padding": 3 * [1], "stride": 3 * [1], "nb_filters": [64, 64, 64],
-               "pooling": list(3 * ((2, 4),))}
-pooling_time_ratio = 8  # 2 * 2 * 2
+# read by nothing on the path (main.py:81 has adjust_learning_rate commented out); kept because the names are public
+lr, initial_lr = 0.0001, 0.
+beta1_before_rampdown, beta1_after_rampdown = 0.9, 0.5
+beta2_during_rampdup, beta2_after_rampup = 0.99, 0.999
+weight_decay_during_rampup, weight_decay_after_rampup = 0.99, 0.999

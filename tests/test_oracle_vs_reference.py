@@ -188,3 +188,24 @@ def test_our_checkpoint_loads_into_reference_modules(tmp_path, monkeypatch):
         pp["dense_softmax.bias"] = dict(ref.named_parameters())["dense_softmax.bias"].detach()
         s, _ = ocrnn.crnn_forward(x, pp, ocrnn.init_buffers(), training=False)
     assert float((s - s_ref).abs().max()) < 2e-6
+
+
+def test_config_matches_reference_config():
+    """Every public name of baseline/config.py exists in dcase2019_task4_b200.config with the same value."""
+    import importlib.util
+    from dcase2019_task4_b200 import config as ours
+    spec = importlib.util.spec_from_file_location("_ref_config", os.path.join(REF, "config.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)                       # reads ../dataset/metadata/validation/validation.tsv
+    names = [n for n in vars(ref) if not n.startswith("_") and n not in ("math", "os", "pd", "file_path")]
+    assert len(names) >= 35
+    for n in names:
+        a, b = getattr(ref, n), getattr(ours, n)
+        if n == "classes":
+            assert list(a) == list(b)
+        elif n == "crnn_kwargs":
+            assert set(a) == set(b)
+            for k in a:
+                assert list(a[k]) == list(b[k]) if isinstance(a[k], (list, tuple)) else a[k] == b[k], k
+        else:
+            assert a == b and type(a) is type(b), n
