@@ -49,6 +49,44 @@ _SCALARS = np.dtype([("seed", "<u8"), ("step", "<u4"), ("cons_weight", "<f4"), (
                      ("bc1", "<f4"), ("bc2", "<f4"), ("grad_scale", "<f4"), ("pad", "<f4")])
 
 
+def bind_flat_adam_state(opt, plist, slices, n, device):
+    """Make ``torch.optim.Adam``'s per-parameter ``exp_avg`` / ``exp_avg_sq`` views into two flat slabs (what
+    dcase_adam_ema_step updates), so ``optimizer.state_dict()`` (saved at main.py:339) stays valid.  The slabs belong to
+    the OPTIMIZER, not to one engine: engines for other batch shapes (a smaller last batch, main_simple_CRNN.py:190)
+    keep updating the same moments.  Existing state (a resumed checkpoint) is copied in.  -> (m, v, [step tensors])."""
+    if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
+        raise NotImplementedError("the fused step implements torch.optim.Adam with one param group (main.py:290)")
+    g = opt.param_groups[0]
+    if g.get("amsgrad") or g.get("weight_decay", 0) != 0 or g.get("maximize"):
+        raise NotImplementedError("amsgrad / weight_decay / maximize are not on the reference's path")
+    if [id(p) for p in g["params"]] != [id(p) for p in plist]:
+        raise NotImplementedError("the optimizer must hold exactly model.parameters() in order (main.py:290)")
+    shared = opt.__dict__.get("_dcase_flat_state")
+    bound = shared is not None and shared[0].numel() == n and shared[0].device == device and all(
+        "exp_avg" in opt.state[p] and opt.state[p]["exp_avg"].data_ptr() == shared[0][off:off + 1].data_ptr()
+        and opt.state[p]["exp_avg_sq"].data_ptr() == shared[1][off:off + 1].data_ptr()
+        for p, (off, cnt) in zip(plist, slices))
+    if bound:
+        m, v = shared
+    else:
+        m = torch.zeros(n, device=device)
+        v = torch.zeros(n, device=device)
+        opt.__dict__["_dcase_flat_state"] = (m, v)
+    steps = []
+    for p, (off, cnt) in zip(plist, slices):
+        st = opt.state[p]
+        if not bound:
+            if "exp_avg" in st:
+                m[off:off + cnt].copy_(st["exp_avg"].reshape(-1))
+                v[off:off + cnt].copy_(st["exp_avg_sq"].reshape(-1))
+            st["exp_avg"] = m[off:off + cnt].view(p.shape)
+            st["exp_avg_sq"] = v[off:off + cnt].view(p.shape)
+        if "step" not in st:
+            st["step"] = torch.tensor(0.0)
+        steps.append(st["step"])
+    return m, v, steps
+
+
 class MeanTeacherEngine(object):
     """Device-resident buffers + launch sequence of one mean-teacher iteration for a fixed batch shape."""
 
@@ -106,28 +144,8 @@ class MeanTeacherEngine(object):
 
     # torch.optim.Adam bookkeeping -----------------------------------------------------------------------
     def _bind_adam_state(self, n):
-        opt = self.optimizer
-        if type(opt) is not torch.optim.Adam or len(opt.param_groups) != 1:
-            raise NotImplementedError("the fused step implements torch.optim.Adam with one param group (main.py:290)")
-        g = opt.param_groups[0]
-        if g.get("amsgrad") or g.get("weight_decay", 0) != 0 or g.get("maximize"):
-            raise NotImplementedError("amsgrad / weight_decay / maximize are not on the reference's path")
-        plist = self.model._param_list
-        if [id(p) for p in g["params"]] != [id(p) for p in plist]:
-            raise NotImplementedError("the optimizer must hold exactly model.parameters() in order (main.py:290)")
-        self.m = torch.zeros(n, device=self.dev)
-        self.v = torch.zeros(n, device=self.dev)
-        self._steps = []
-        for p, (off, cnt) in zip(plist, self.model._param_slices):
-            st = opt.state[p]
-            if "exp_avg" in st:
-                self.m[off:off + cnt].copy_(st["exp_avg"].reshape(-1))
-                self.v[off:off + cnt].copy_(st["exp_avg_sq"].reshape(-1))
-            if "step" not in st:
-                st["step"] = torch.tensor(0.0)
-            st["exp_avg"] = self.m[off:off + cnt].view(p.shape)
-            st["exp_avg_sq"] = self.v[off:off + cnt].view(p.shape)
-            self._steps.append(st["step"])
+        self.m, self.v, self._steps = bind_flat_adam_state(self.optimizer, self.model._param_list,
+                                                            self.model._param_slices, n, self.dev)
 
     def _adam_step_count(self):
         return int(self._steps[0].item()) if self._steps else 0

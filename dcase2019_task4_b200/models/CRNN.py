@@ -41,7 +41,7 @@ class _CrnnFunction(torch.autograd.Function):
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the reference's path")
         grads = K.crnn_backward(x, module._flat, flags, ctx.ws, d_strong.contiguous(), d_weak.contiguous(), weak,
                                 n_class=module.nclass, seed=seed, step=step, model_id=module.model_id)
-        module._give_workspace(ctx.ws)
+        module._give_workspace(ctx.ws, x.shape[0], x.shape[-2])
         ctx.ws = None
         out = []
         for p, (off, n) in zip(module._param_list, module._param_slices):
@@ -135,11 +135,11 @@ class CRNN(nn.Module):
             return pool[0]
         return pool.pop() if pool else K.new_workspace(B, T, self.nclass, device)
 
-    def _give_workspace(self, ws):
-        for key, pool in self._ws_pool.items():
-            if len(pool) < 2:
-                pool.append(ws)
-                return
+    def _give_workspace(self, ws, B, T):
+        """Return a workspace taken with keep=True to the pool of ITS OWN shape (at most two are kept per shape)."""
+        pool = self._ws_pool.setdefault((B, T, str(ws.device)), [])
+        if len(pool) < 2 and ws.numel() == K.workspace_bytes(B, T, self.nclass):
+            pool.append(ws)
 
     def _flush_counters(self):
         if self._nbt_pending:

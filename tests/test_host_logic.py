@@ -314,3 +314,46 @@ def test_weak_f_measure_by_class_hand_computed():
     assert np.allclose(em.get_f_measure_by_class(Stub(), 3, [(x, y3)]), em.get_f_measure_by_class(Stub(), 3, [(x, y)]))
     tp, fp, fn, tn = em.intermediate_at_measures(np.array([[1, 0], [0, 0]]), np.array([[1, 1], [0, 0]]))
     assert (tp.tolist(), fp.tolist(), fn.tolist(), tn.tolist()) == ([1, 0], [0, 1], [0, 0], [1, 1])
+
+
+def test_workspace_pool_returns_buffers_to_their_own_shape():
+    """Regression: a workspace given back after backward used to land in the first pool with a free slot, whatever
+    its shape -- a small buffer could then be handed to a larger batch.  Host bookkeeping only (CPU tensors)."""
+    from dcase2019_task4_b200 import kernels as K
+    m = CRNN(**cfg.crnn_kwargs)
+    big = torch.empty(K.workspace_bytes(2, 64, 10), dtype=torch.uint8)
+    small = torch.empty(K.workspace_bytes(1, 64, 10), dtype=torch.uint8)
+    assert small.numel() < big.numel()
+    m._ws_pool = {(2, 64, "cpu"): [big]}                       # one free slot left in the pool of the larger shape
+    m._give_workspace(small, 1, 64)
+    assert m._ws_pool[(2, 64, "cpu")] == [big] or all(w is big for w in m._ws_pool[(2, 64, "cpu")])
+    assert m._ws_pool[(1, 64, "cpu")][0] is small
+    m._give_workspace(small, 2, 64)                            # a buffer of the wrong size is never pooled
+    assert all(w is big for w in m._ws_pool[(2, 64, "cpu")])
+    assert m._take_workspace(2, 64, torch.device("cpu"), keep=True) is big
+
+
+def test_flat_adam_state_is_shared_between_engines_and_survives_resume():
+    """bind_flat_adam_state (main.py): the flat moment slabs belong to the optimizer -- a second binding (another
+    batch shape's engine) gets the SAME slabs, torch's own state_dict sees the fused kernel's updates, and a resumed
+    optimizer.load_state_dict() is re-bound with its values copied in."""
+    from dcase2019_task4_b200.main import bind_flat_adam_state
+    m = CRNN(**cfg.crnn_kwargs)
+    opt = torch.optim.Adam(m.parameters(), lr=0.001, betas=(0.9, 0.999))
+    n = m.flat_parameters().numel()
+    dev = torch.device("cpu")
+    m1, v1, steps1 = bind_flat_adam_state(opt, m._param_list, m._param_slices, n, dev)
+    m1.fill_(0.25)                                             # "the fused kernel updated the moments"
+    v1.fill_(0.5)
+    m2, v2, steps2 = bind_flat_adam_state(opt, m._param_list, m._param_slices, n, dev)
+    assert m2 is m1 and v2 is v1 and all(a is b for a, b in zip(steps1, steps2)) and len(steps1) == 38
+    sd = opt.state_dict()
+    assert float(sd["state"][0]["exp_avg"].mean()) == 0.25 and float(sd["state"][37]["exp_avg_sq"].mean()) == 0.5
+    # resume: load_state_dict replaces the state tensors -> re-bound, values preserved
+    opt2 = torch.optim.Adam(m.parameters(), lr=0.001, betas=(0.9, 0.999))
+    opt2.load_state_dict(sd)
+    m3, v3, _ = bind_flat_adam_state(opt2, m._param_list, m._param_slices, n, dev)
+    assert m3 is not m1 and float(m3.min()) == 0.25 and float(v3.max()) == 0.5
+    assert opt2.state[m._param_list[5]]["exp_avg"].data_ptr() == m3[m._param_slices[5][0]:].data_ptr()
+    with pytest.raises(NotImplementedError):
+        bind_flat_adam_state(torch.optim.Adam(list(m.parameters())[:3]), m._param_list, m._param_slices, n, dev)
