@@ -8,7 +8,7 @@ float64, the square taken in the sample's float32, then the mean over samples), 
 (``dcase_scaler_accumulate`` / ``dcase_scaler_finalize``, csrc/logmel.cu):
 
 * a ``DataLoadDf`` / ``ConcatDataset`` whose transform is the chain of ``get_transforms(frames)`` is read through
-  ``get_sample`` (the cached amplitude mels), batched, and ApplyLog + PadOrTrunc + the reduction are ONE pass over
+  ``get_feature_file_func`` (the cached amplitude mels), batched, and ApplyLog + PadOrTrunc + the reduction are ONE pass over
   each batch -- the log features are never written;
 * ``means_from_waveforms`` starts from raw clips (``dcase_logmel_fwd`` first), for runs without a feature cache;
 * any other iterable of ``[..., 64]`` samples is stacked and reduced as it is.
@@ -83,7 +83,8 @@ class Scaler(object):
         group, shape = [], None
         for d in members:
             for i in range(len(d)):
-                f = np.ascontiguousarray(d.get_sample(i)[0], dtype=np.float32)
+                # features only: the labels (pandas work per sample in get_sample) play no part in the statistics
+                f = np.ascontiguousarray(d.get_feature_file_func(d.filenames.iloc[i]), dtype=np.float32)
                 if f.ndim != 2 or f.shape[1] != 64:
                     raise NotImplementedError("features are [T, 64] amplitude mels, got {}".format(f.shape))
                 if group and (f.shape != shape or len(group) == self.BATCH_CLIPS):
