@@ -44,7 +44,10 @@ def _fused_sources(dataset):
 
 class Scaler(object):
 
-    BATCH_CLIPS = 64     # clips per device launch (64 x 864 x 64 fp32 = 14 MB staged per batch)
+    # clips per device launch: 256 x 864 x 64 fp32 = 57 MB staged per batch, still L2-resident (126 MB) for the
+    # reduction's second pass; the ~15 us host cost of a launch is amortised 4x better than at 64 clips
+    # (profiles/r1_scaler_bench*.json)
+    BATCH_CLIPS = 256
 
     def __init__(self):
         self.mean_ = None
