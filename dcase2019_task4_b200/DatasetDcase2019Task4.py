@@ -28,6 +28,59 @@ class DatasetDcase2019Task4:
         if create_dirs and not os.path.exists(self.feature_dir):
             os.makedirs(self.feature_dir)
 
+    # ---- tsv bookkeeping around the feature extraction (DatasetDcase2019Task4.py:92-181) --------------------------
+    def initialize_and_get_df(self, tsv_path, subpart_data=None, download=True):
+        """The DataFrame of one metadata table, with the features of its files extracted into the cache.  The youtube
+        download of the reference is not rebuilt: ``download`` is accepted and the audio must already be on disk."""
+        meta_name = os.path.join(self.local_path, tsv_path)
+        return self.extract_features_from_meta(meta_name, subpart_data)
+
+    @staticmethod
+    def get_classes(list_dfs):
+        found = set()
+        for df in list_dfs:
+            if "event_label" in df.columns:
+                found.update(df["event_label"].dropna().unique())
+            elif "event_labels" in df.columns:
+                found.update(df.event_labels.str.split(',', expand=True).unstack().dropna().unique())
+        return list(found)
+
+    @staticmethod
+    def get_subpart_data(df, subpart_data):
+        if subpart_data <= len(df["filename"].unique()):
+            keep = df["filename"].drop_duplicates().sample(subpart_data, random_state=10)
+            df = df[df["filename"].isin(keep)].reset_index(drop=True)
+        return df
+
+    @staticmethod
+    def get_df_from_meta(meta_name, subpart_data=None):
+        import pandas as pd
+        df = pd.read_csv(meta_name, header=0, sep="\t")
+        return df if subpart_data is None else DatasetDcase2019Task4.get_subpart_data(df, subpart_data)
+
+    @staticmethod
+    def get_audio_dir_path_from_meta(filepath):
+        """dataset/metadata/train/weak.tsv -> dataset/audio/train/weak; validation tables share dataset/audio/validation."""
+        parts = os.path.splitext(filepath)[0].replace("metadata", "audio").split('/')
+        if len(parts) >= 2 and parts[-2] == 'validation':
+            parts = parts[:-1]
+        return os.path.abspath('/'.join(parts))
+
+    def extract_features_from_meta(self, tsv_audio, subpart_data=None):
+        """DatasetDcase2019Task4.py:233-270: features of every file of the table that exists on disk; rows of missing
+        files are dropped from the returned DataFrame."""
+        df_meta = self.get_df_from_meta(tsv_audio, subpart_data)
+        wav_dir = self.get_audio_dir_path_from_meta(tsv_audio)
+        names = list(df_meta.filename.unique())
+        cached = [n for n in names
+                  if os.path.exists(os.path.join(self.feature_dir, os.path.splitext(n)[0] + ".npy"))]
+        todo = [n for n in names if n not in set(cached)]
+        done = set(cached) | set(self.extract_features_from_files(wav_dir, todo) if todo else [])
+        missing = [n for n in names if n not in done and not os.path.isfile(os.path.join(wav_dir, n))]
+        if missing:
+            df_meta = df_meta[~df_meta.filename.isin(missing)]
+        return df_meta.reset_index(drop=True)
+
     def get_feature_file(self, filename):
         return np.load(os.path.join(self.feature_dir, os.path.splitext(filename)[0] + ".npy"))
 

@@ -131,6 +131,40 @@ def get_f_measure_by_class(torch_model, nb_tags, dataloader_, thresholds_=None):
     return macro_f_measure(tp, fp, fn)
 
 
+def format_df(df, mhe):
+    """One row per file with the many-hot weak encoding of its event labels (evaluation_measures.py:249-257)."""
+    if "onset" in df.columns or "offset" in df.columns:
+        rows = [{"filename": fname, "event_label": mhe.encode_weak(g["event_label"].drop_duplicates().dropna().tolist())}
+                for fname, g in df.groupby("filename", sort=True)]
+        df = pd.DataFrame(rows, columns=["filename", "event_label"])
+    return df
+
+
+def audio_tagging_results(reference, estimated):
+    """Per-class F-measure of the clip-level tags implied by two event DataFrames (evaluation_measures.py:259-296):
+    files are matched by an outer join, a file missing on one side counts as "no tags" there."""
+    from .utils.utils import ManyHotEncoder
+    if "event_label" in reference.columns:
+        classes = sorted(set(reference.event_label.dropna().unique()) | set(estimated.event_label.dropna().unique()))
+        mhe = ManyHotEncoder(classes)
+        reference, estimated = format_df(reference, mhe), format_df(estimated, mhe)
+    else:
+        def split(df):
+            return set(df.event_labels.str.split(',', expand=True).unstack().dropna().unique())
+        classes = sorted(split(reference) | split(estimated))
+        mhe = ManyHotEncoder(classes)
+    if estimated.empty:
+        return pd.Series(np.zeros(len(classes)), index=mhe.labels)
+    matching = reference.merge(estimated, how='outer', on="filename", suffixes=["_ref", "_pred"])
+
+    def tags(val):
+        return val if isinstance(val, np.ndarray) else np.zeros(len(classes))
+    ref = np.array([tags(v) for v in matching.event_label_ref])
+    est = np.array([tags(v) for v in matching.event_label_pred])
+    tp, fp, fn, _ = intermediate_at_measures(ref, est)
+    return pd.Series(macro_f_measure(tp, fp, fn), index=mhe.labels)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # restated sed_eval metrics
 # ------------------------------------------------------------------------------------------------------------

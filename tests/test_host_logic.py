@@ -1,10 +1,13 @@
 """CPU: host-side mirror of the reference interface (no kernels involved)."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
 import torch
 
 from dcase2019_task4_b200 import DataLoad, config as cfg, dp
+from dcase2019_task4_b200.DatasetDcase2019Task4 import DatasetDcase2019Task4 as DatasetBook
 from dcase2019_task4_b200.models.CRNN import CRNN
 from dcase2019_task4_b200.utils import ramps
 from dcase2019_task4_b200.utils.Scaler import Scaler
@@ -357,3 +360,50 @@ def test_flat_adam_state_is_shared_between_engines_and_survives_resume():
     assert opt2.state[m._param_list[5]]["exp_avg"].data_ptr() == m3[m._param_slices[5][0]:].data_ptr()
     with pytest.raises(NotImplementedError):
         bind_flat_adam_state(torch.optim.Adam(list(m.parameters())[:3]), m._param_list, m._param_slices, n, dev)
+
+
+def test_audio_tagging_results_hand_computed():
+    """evaluation_measures.audio_tagging_results (evaluation_measures.py:259-296): clip-level tags from event tables."""
+    from dcase2019_task4_b200 import evaluation_measures as em
+    ref = pd.DataFrame([("a.wav", 0.0, 1.0, "Dog"), ("a.wav", 2.0, 3.0, "Cat"), ("b.wav", 0.0, 1.0, "Dog"),
+                        ("c.wav", 1.0, 2.0, "Speech")], columns=["filename", "onset", "offset", "event_label"])
+    est = pd.DataFrame([("a.wav", 0.1, 0.9, "Dog"), ("b.wav", 0.0, 1.0, "Cat"), ("b.wav", 3.0, 4.0, "Dog"),
+                        ("d.wav", 0.0, 1.0, "Speech")], columns=["filename", "onset", "offset", "event_label"])
+    res = em.audio_tagging_results(ref, est)
+    # Dog: ref a,b  est a,b -> tp 2 -> 1.0;  Cat: ref a  est b -> fp 1 fn 1 -> 0;  Speech: ref c  est d -> fp 1 fn 1 -> 0
+    assert res.to_dict() == {"Cat": 0.0, "Dog": 1.0, "Speech": 0.0}
+    assert em.audio_tagging_results(ref, est.iloc[0:0]).tolist() == [0.0, 0.0, 0.0]
+    weak_ref = pd.DataFrame({"filename": ["a.wav", "b.wav"], "event_labels": ["Dog,Cat", "Dog"]})
+    mhe = ManyHotEncoder(["Cat", "Dog"])
+    weak_ref2 = pd.DataFrame({"filename": ["a.wav", "b.wav"], "event_labels": ["Dog,Cat", "Dog"],
+                              "event_label": [mhe.encode_weak(["Dog", "Cat"]), mhe.encode_weak(["Dog"])]})
+    assert sorted(DatasetBook.get_classes([weak_ref])) == ["Cat", "Dog"] and weak_ref2.shape == (2, 3)
+
+
+def test_dataset_bookkeeping_and_logger(tmp_path, monkeypatch):
+    """tsv side of DatasetDcase2019Task4 (DatasetDcase2019Task4.py:92-181) and utils.Logger without side effects."""
+    D = DatasetBook
+    assert D.get_audio_dir_path_from_meta("/x/dataset/metadata/train/weak.tsv") == "/x/dataset/audio/train/weak"
+    assert D.get_audio_dir_path_from_meta("/x/dataset/metadata/validation/eval_dcase2018.tsv") == "/x/dataset/audio/validation"
+    tsv = tmp_path / "dataset" / "metadata" / "train" / "synthetic.tsv"
+    tsv.parent.mkdir(parents=True)
+    pd.DataFrame([("f%d.wav" % (i // 2), 0.5 * i, 0.5 * i + 1, "Dog") for i in range(12)],
+                 columns=["filename", "onset", "offset", "event_label"]).to_csv(tsv, sep="\t", index=False)
+    df = D.get_df_from_meta(str(tsv))
+    assert len(df) == 12 and D.get_classes([df]) == ["Dog"]
+    sub = D.get_df_from_meta(str(tsv), 3)
+    assert sub.filename.nunique() == 3 and len(sub) == 6
+    assert len(D.get_df_from_meta(str(tsv), 100)) == 12            # asking for more files than there are keeps all
+    # features already cached -> no device work; rows of files with neither cache nor audio are dropped
+    ds = D(str(tmp_path), base_feature_dir=str(tmp_path / "dataset" / "features"), save_log_feature=False)
+    for i in range(5):
+        np.save(os.path.join(ds.feature_dir, "f%d.npy" % i), np.zeros((3, 64), np.float32))
+    out = ds.initialize_and_get_df("dataset/metadata/train/synthetic.tsv", download=False)
+    assert sorted(out.filename.unique()) == ["f%d.wav" % i for i in range(5)] and len(out) == 10
+    assert ds.get_feature_file("f2.wav").shape == (3, 64)
+    monkeypatch.chdir(tmp_path)
+    import importlib
+    from dcase2019_task4_b200.utils import Logger
+    importlib.reload(Logger)
+    Logger.LOG.info("hello")
+    assert not os.path.exists(tmp_path / "Baseline.log")

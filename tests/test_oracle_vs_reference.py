@@ -209,3 +209,30 @@ def test_config_matches_reference_config():
                 assert list(a[k]) == list(b[k]) if isinstance(a[k], (list, tuple)) else a[k] == b[k], k
         else:
             assert a == b and type(a) is type(b), n
+
+
+def test_reference_scripts_import_against_this_package(tmp_path):
+    """dropin.install() aliases this package under the names baseline/main.py:19-29 imports; the reference's OWN
+    main.py, main_simple_CRNN.py and TestModel.py then import unchanged (every ``from X import a, b, c`` resolves), and
+    the objects they bind are ours.  Runs in a subprocess: the aliases are process-global."""
+    import subprocess
+    code = (
+        "import sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from dcase2019_task4_b200 import dropin\n"
+        "dropin.install()\n"
+        "sys.path.append(%r)\n"
+        "import main, main_simple_CRNN, TestModel\n"
+        "assert main.CRNN.__module__ == 'dcase2019_task4_b200.models.CRNN'\n"
+        "assert main.Scaler.__module__ == 'dcase2019_task4_b200.utils.Scaler'\n"
+        "assert main.get_transforms.__module__ == 'dcase2019_task4_b200.utils.utils'\n"
+        "assert main.MultiStreamBatchSampler.__module__ == 'dcase2019_task4_b200.DataLoad'\n"
+        "assert TestModel.get_predictions.__module__ == 'dcase2019_task4_b200.evaluation_measures'\n"
+        "assert main.__file__.startswith(%r) and callable(main.train) and callable(main_simple_CRNN.train)\n"
+        "m = main.CRNN(**main.cfg.crnn_kwargs); m.apply(main.weights_init)\n"
+        "opt = __import__('torch').optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=0.001)\n"
+        "print('DROPIN-OK', len(list(m.parameters())))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), REF, REF)
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "DROPIN-OK 38" in r.stdout, r.stdout + r.stderr
+    assert not os.path.exists(tmp_path / "Baseline.log")
