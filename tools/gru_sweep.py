@@ -78,7 +78,7 @@ def main():
                          "speedup_vs_cudnn": None if ours_ms is None else cudnn_ms / ours_ms,
                          "max_abs_diff_vs_cudnn": err})
     out = {"config": "BiGRU sweep (BASELINE.json configs[4])", "dtype": "f32", "device": torch.cuda.get_device_name(0),
-           "note": "hidden 128 / 256 are not built (cfg.crnn_kwargs selects 64); cuDNN rows are the library baseline",
+           "note": "hidden 128 / 256 run through the experimental cluster kernel only under DCASE_EXPERIMENTAL=1 (null otherwise; cfg.crnn_kwargs selects 64); cuDNN rows are the library baseline",
            "rows": rows}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "gru_sweep.json"), "w") as fh:
