@@ -249,9 +249,21 @@ def run_b200(args, rank, local_rank, world):
         r = ramps.sigmoid_rampup(gs, rampup_length) if gs < rampup_length else 1.0
         return cfg.max_consistency_cost * r
 
+    # DCASE_PIPELINE=1 (opt-in, unverified on hardware): the features of batch i + 1 are prepared on a side stream during
+    # iteration i (MeanTeacherEngine.step_pipelined); every batch still goes through every kernel inside the timed region
+    pipeline = os.environ.get("DCASE_PIPELINE", "0") == "1"
+    if pipeline:
+        engine.prime_features(wave_dev[0], mean, std)
+
     def resident_step(i):
-        engine.step_from_waveforms(wave_dev[i % n_pool], target_dev[i % n_pool], mean, std, cons_weight(),
-                                   state["gs"] + 1, check=False)
+        if pipeline:
+            k = state.setdefault("pipe", 0)                        # batch whose features sit in the current slot
+            engine.step_pipelined(wave_dev[(k + 1) % n_pool], target_dev[k % n_pool], mean, std, cons_weight(),
+                                  state["gs"] + 1, check=False)
+            state["pipe"] = k + 1
+        else:
+            engine.step_from_waveforms(wave_dev[i % n_pool], target_dev[i % n_pool], mean, std, cons_weight(),
+                                       state["gs"] + 1, check=False)
         state["gs"] += 1
 
     prefetch = HostBatchPrefetcher(dev, (B_PER_GPU, N_SAMPLES), (B_PER_GPU, FRAMES // 8, 10))

@@ -193,7 +193,7 @@ clip_max_kernel(const float* __restrict__ mel_amp, int T_in, const float* __rest
                 uint64_t seed, uint32_t step, const DcaseStepScalars* __restrict__ sc,
                 float* __restrict__ clip_max, int B) {
     __shared__ float red[2][8];
-    if (sc) { seed = sc->seed; step = sc->step; }
+    if (sc) { seed = sc->seed; step += sc->step; }    // `step` is an offset on top of the device scalars
     const int b = blockIdx.y;
     const int n_quads = T_in * (kMel / 4);
     const float4* src = reinterpret_cast<const float4*>(mel_amp + (size_t)b * T_in * kMel);
@@ -231,7 +231,7 @@ finish_kernel(const float* __restrict__ mel_amp, int B, int T_in, int T_out, con
               const float* __restrict__ stdv, const float* __restrict__ noise, uint64_t seed, uint32_t step,
               const DcaseStepScalars* __restrict__ sc, const float* __restrict__ clip_max,
               float* __restrict__ clean, float* __restrict__ noisy) {
-    if (sc) { seed = sc->seed; step = sc->step; }
+    if (sc) { seed = sc->seed; step += sc->step; }    // `step` is an offset on top of the device scalars
     const size_t total = (size_t)B * T_out * (kMel / 4);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int q = (int)(i & 15);

@@ -268,6 +268,108 @@ class MeanTeacherEngine(object):
             x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None
         self.step(x, x_ema, target, cons_weight, global_step_after, check=check)
 
+    # ---- features one step ahead (opt-in; see ROUND2_PLAN.md) ---------------------------------------------------
+    # The log-mel phase of a batch does not depend on the model, and the backward spends ~260 us in kernels that occupy
+    # 24-48 CTAs (GRU BPTT, head, loss) while the STFT launches thousands: ``step_pipelined`` runs the iteration on the
+    # features already sitting in the current slot and, on a side stream, prepares the features of the NEXT batch into
+    # the other slot.  Same kernels, same Philox (seed, step) per batch as ``step_from_waveforms``; only the order of
+    # launches differs.  UNVERIFIED on hardware (written after round 1's GPU budget was spent).
+    def _feature_slots(self):
+        if getattr(self, "_xp", None) is None:
+            f32 = dict(device=self.dev, dtype=torch.float32)
+            self._xp = [torch.empty(self.B, self.T, 64, **f32) for _ in range(2)]
+            self._xp_ema = ([torch.empty(self.B, self.T, 64, **f32) for _ in range(2)]
+                            if self.ema_model is not None else [None, None])
+            self._feat_slot = 0
+            self._side = torch.cuda.Stream(self.dev)
+            self._pgraphs = {}
+        return self._xp, self._xp_ema
+
+    def _finish_into(self, amp, mean, std, slot, seed=0, step=0, scalars=None):
+        xp, xpe = self._feature_slots()
+        if self.ema_model is not None:
+            K.logmel_finish(amp, mean, std, self.T, noisy=True, seed=seed, step=step, scalars=scalars,
+                            out_clean=xp[slot], out_noisy=xpe[slot])
+        else:
+            K.logmel_finish(amp, mean, std, self.T, out_clean=xp[slot])
+
+    def prime_features(self, wave, mean, std):
+        """Features of the FIRST batch of a pipelined run (current slot), with the upcoming iteration's noise."""
+        self._feature_slots()
+        self._finish_into(K.logmel_fwd(wave), mean, std, self._feat_slot, seed=self.model._rng_seed,
+                          step=self.model._rng_step & 0xFFFFFFFF)
+
+    def step_pipelined(self, wave_next, target, mean, std, cons_weight, global_step_after, check=True,
+                       wave_ready_event=None):
+        """One iteration on the current slot's features (``target`` belongs to THAT batch) while the features of
+        ``wave_next`` -- the batch of the next call -- are prepared on a side stream.  ``wave_ready_event``: an event
+        the side stream waits for before reading ``wave_next`` (a host-to-device copy still in flight)."""
+        xp, xpe = self._feature_slots()
+        slot, nxt = self._feat_slot, self._feat_slot ^ 1
+        main = torch.cuda.current_stream(self.dev)
+        if not self.use_graph:
+            self._side.wait_stream(main)                   # the other slot's last reader (the previous step) is done
+            if wave_ready_event is not None:
+                self._side.wait_event(wave_ready_event)
+            with torch.cuda.stream(self._side):
+                amp = K.logmel_fwd(wave_next)
+                amp.record_stream(self._side)
+                self._finish_into(amp, mean, std, nxt, seed=self.model._rng_seed,
+                                  step=(self.model._rng_step + 1) & 0xFFFFFFFF)
+            self.step(xp[slot], xpe[slot], target, cons_weight, global_step_after, check=check)
+            main.wait_stream(self._side)
+            self._feat_slot = nxt
+            return
+        # graph replay: one graph per (next waveform buffer, target buffer, slot)
+        model, ema = self.model, self.ema_model
+        prev_pending, prev_slot = self._pending, self._slot
+        target = target.contiguous()
+        g = self.optimizer.param_groups[0]
+        seed, step = model.next_rng()
+        t = self._adam_step_count() + 1
+        sc = np.zeros(1, dtype=_SCALARS)
+        sc["seed"], sc["step"], sc["cons_weight"] = seed, step, cons_weight
+        sc["ema_alpha"] = min(1 - 1 / (global_step_after + 1), 0.999)
+        sc["lr"] = g["lr"]
+        sc["bc1"], sc["bc2"] = 1.0 - g["betas"][0] ** t, 1.0 - g["betas"][1] ** t
+        sc["grad_scale"] = 1.0 / self.world
+        with torch.cuda.device(self.dev):
+            self._sc_host.copy_(torch.from_numpy(sc.view(np.uint8)))
+            self._sc_dev.copy_(self._sc_host, non_blocking=True)
+            if wave_ready_event is not None:
+                main.wait_event(wave_ready_event)
+            key = (wave_next.data_ptr(), tuple(wave_next.shape), wave_next.dtype, target.data_ptr(), mean.data_ptr(),
+                   std.data_ptr(), slot, model.forward_flags(), g["betas"], g["eps"])
+            entry = self._pgraphs.get(key)
+            if entry is None:
+                graph = torch.cuda.CUDAGraph()
+                l0 = K.launch_count()
+                with torch.cuda.graph(graph):
+                    cap = torch.cuda.current_stream(self.dev)
+                    self._side.wait_stream(cap)
+                    with torch.cuda.stream(self._side):
+                        amp = K.logmel_fwd(wave_next)
+                        self._finish_into(amp, mean, std, nxt, step=1, scalars=self._sc_dev)   # next iteration's noise
+                    K.mt_fwd_bwd(self._mt_args(xp[slot], xpe[slot], target, model.forward_flags(), 0, 0, 0.0,
+                                               self._sc_dev.data_ptr()))
+                    K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
+                                    ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
+                                    beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
+                    cap.wait_stream(self._side)
+                entry = (graph, K.launch_count() - l0)
+                self._pgraphs[key] = entry
+            entry[0].replay()
+            self.graph_launches += entry[1]
+            self._enqueue_meter_copy()
+        torch._foreach_add_(self._steps, 1.0)
+        model._nbt_pending += 1
+        if ema is not None:
+            ema._nbt_pending += 1
+        if check and prev_pending:
+            self._check_slot(prev_slot)
+        self._pending = True
+        self._feat_slot = nxt
+
     def _enqueue_meter_copy(self):
         self._slot ^= 1
         self.meters_host[self._slot].copy_(self.meters, non_blocking=True)

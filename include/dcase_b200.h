@@ -113,8 +113,9 @@ int dcase_audio_mixdown(dcase_ctx* ctx, const void* interleaved, int is_pcm16, l
  * AugmentGaussianNoise (DataLoad.py:274-287) -> ApplyLog / librosa.amplitude_to_db (DataLoad.py:192-207)
  * -> PadOrTrunc (DataLoad.py:210-259) -> ToTensor -> Normalize / Scaler.normalize (Scaler.py:99-105).
  * mel_amp [B][T_in][64] -> clean [B][T_out][64] and, if noisy != NULL, noisy [B][T_out][64].
- * noise: explicit |N(0,0.25)| sample [B][T_in][64] or NULL (Philox, see RNG contract; scalars overrides
- * seed/step when non-NULL).  clip_max_ws: [2*B] floats of scratch. */
+ * noise: explicit |N(0,0.25)| sample [B][T_in][64] or NULL (Philox, see RNG contract).  With scalars non-NULL the
+ * seed comes from the device struct and `step` is an OFFSET added to its step (0 = this iteration's noise, 1 = the
+ * noise of the next iteration, for features prepared one step ahead).  clip_max_ws: [2*B] floats of scratch. */
 int dcase_logmel_finish(dcase_ctx* ctx, const float* mel_amp, int B, int T_in, int T_out, const float* mean,
                         const float* stdv, const float* noise, uint64_t seed, uint32_t step, const void* scalars,
                         float* clip_max_ws, float* clean, float* noisy, void* stream);
