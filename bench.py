@@ -283,6 +283,27 @@ def run_b200(args, rank, local_rank, world):
         if last:
             engine.check_loss()                                     # syncs on the 32-byte meter copy
 
+    if pipeline:
+        # pipelined variant of the same public-API loop: three staging slots (the batch being trained, the batch whose
+        # features are being prepared, the batch being copied); batch j's waveform is read one call before its targets
+        prefetch3 = HostBatchPrefetcher(dev, (B_PER_GPU, N_SAMPLES), (B_PER_GPU, FRAMES // 8, 10), slots=3)
+
+        def e2e_step(i, last=True):                                 # noqa: F811  (replaces the plain loop above)
+            if i == 0:
+                prefetch3.submit(wave_host[0], target_host[0])
+                prefetch3.submit(wave_host[1 % n_pool], target_host[1 % n_pool])
+                w0, _ = prefetch3.next()
+                engine.prime_features(w0, mean, std)
+            prefetch3.submit(wave_host[(i + 2) % n_pool], target_host[(i + 2) % n_pool])
+            _, t = prefetch3.next()
+            w_next, _, ready = prefetch3.peek(1)
+            engine.step_pipelined(w_next, t, mean, std, cons_weight(), state["gs"] + 1, check=True,
+                                  wave_ready_event=ready)
+            prefetch3.release()
+            state["gs"] += 1
+            if last:
+                engine.check_loss()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -314,9 +335,10 @@ def run_b200(args, rank, local_rank, world):
     value = world * B_PER_GPU * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the public API with host buffers ----
-    for i in range(3):                            # primes the copy pipeline (and captures the two staging buffers' graphs)
+    n_prime = 7 if pipeline else 3               # primes the copy pipeline and captures every staging-buffer graph
+    for i in range(n_prime):                      # (plain: 2 buffers; pipelined: 3 staging x 2 feature slots = 6)
         e2e_step(i)
-    ms_e2e = timed(lambda i: e2e_step(i + 3, last=(i == args.steps - 1)), args.steps)
+    ms_e2e = timed(lambda i: e2e_step(i + n_prime, last=(i == args.steps - 1)), args.steps)
     e2e_value = world * B_PER_GPU * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel durations (CUDA events on the launching stream, separate pass) ----

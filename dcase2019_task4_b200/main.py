@@ -430,6 +430,14 @@ class HostBatchPrefetcher(object):
         torch.cuda.current_stream(self.dev).wait_event(self.copied[k])
         return self.wave[k], self.target[k]
 
+    def peek(self, offset=1):
+        """(wave, target, copied-event) of the batch ``offset`` places behind the one ``next`` returns, WITHOUT making
+        any stream wait: the caller hands the event to the stream that reads the buffers (step_pipelined's side
+        stream reads the NEXT batch's waveform while the current batch trains)."""
+        k = (self.tail + offset) % self.slots
+        assert self.tail + offset < self.head, "that batch has not been submitted yet"
+        return self.wave[k], self.target[k], self.copied[k]
+
     def release(self):
         """Call after the kernels consuming the batch returned by ``next`` have been enqueued."""
         k = self.tail % self.slots
