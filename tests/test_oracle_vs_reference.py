@@ -236,3 +236,27 @@ def test_reference_scripts_import_against_this_package(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "DROPIN-OK 38" in r.stdout, r.stdout + r.stderr
     assert not os.path.exists(tmp_path / "Baseline.log")
+
+
+def test_config0_full_geometry_logmel_plus_reference_crnn_forward():
+    """BASELINE.json configs[0] at the real geometry (10-s clips -> 864 frames -> 108 output frames), scaled to 8 clips
+    to stay within seconds: restated float64 log-mel -> dB -> z-score, then the UNMODIFIED reference models.CRNN in eval
+    mode against the torch oracle on the same features (the pin the GPU parity tests inherit at full size)."""
+    from oracle import mel as omel
+    from dcase2019_task4_b200 import synth
+    waves, _ = synth.make_clips(8, seed=123)
+    amps = [omel.calculate_mel_spec(w.astype(np.float64)) for w in waves]
+    assert amps[0].shape == (864, 64)
+    feats = [omel.transform_chain(a, None, None, frames=864)[0] for a in amps]
+    m_, m2_ = omel.scaler_means(feats)
+    x = np.stack([omel.transform_chain(a, m_, omel.scaler_std(m_, m2_), frames=864)[0] for a in amps])
+    x = torch.from_numpy(x)                                          # [8, 1, 864, 64]
+    p = ocrnn.init_params(seed=5)
+    buf = ocrnn.init_buffers()
+    m = ref_crnn().eval()
+    load_oracle_params(m, p, buf)
+    with torch.no_grad():
+        s_ref, w_ref = m(x)
+        s, w = ocrnn.crnn_forward(x, p, buf, training=False)
+    assert tuple(s_ref.shape) == (8, 108, 10) and tuple(w_ref.shape) == (8, 10)
+    assert float((s - s_ref).abs().max()) < 5e-6 and float((w - w_ref).abs().max()) < 5e-6
