@@ -19,7 +19,9 @@ The reference ships NO tests, golden vectors or fixtures, 
 * ``oracle.crnn`` / ``oracle.train_step`` are pinned against the reference's
   own ``baseline/models/CRNN.py`` imported unmodified from ``/root/reference``
   (``tests/test_oracle_vs_reference.py``, and the committed fixtures made by
-  ``tests/golden/make_golden.py``).
+  ``tests/golden/make_golden.py``); ``oracle.train_step.train_batch`` additionally
+  against the reference's own ``main.train`` / ``main_simple_CRNN.train`` run
+  unmodified on the CPU (``tests/scripts/ref_train_vs_oracle.py``).
 * ``oracle.mel.scaler_means`` / ``scaler_std`` are pinned against the reference's own ``baseline/utils/Scaler.py``
   (live and through ``tests/golden/scaler_reference.npz``).
 * the rest of ``oracle.mel`` restates librosa's published algorithm (un-vendored, unpinned

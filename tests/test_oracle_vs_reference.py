@@ -260,3 +260,19 @@ def test_config0_full_geometry_logmel_plus_reference_crnn_forward():
         s, w = ocrnn.crnn_forward(x, p, buf, training=False)
     assert tuple(s_ref.shape) == (8, 108, 10) and tuple(w_ref.shape) == (8, 10)
     assert float((s - s_ref).abs().max()) < 5e-6 and float((w - w_ref).abs().max()) < 5e-6
+
+
+def test_step_oracle_matches_the_reference_train_functions(tmp_path):
+    """The reference's OWN ``main.train`` (mean teacher) and ``main_simple_CRNN.train``, imported unmodified and run on
+    the CPU with the reference's ``models.CRNN``, against ``oracle.train_step.train_batch`` for three batches
+    (tests/scripts/ref_train_vs_oracle.py): loss composition, ramp-up, masks, Adam, EMA alpha schedule, BN statistics.
+    Adam's first steps move every element by ~lr, so 1e-4 on parameters after three steps is a tight bound."""
+    import subprocess
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "ref_train_vs_oracle.py")
+    r = subprocess.run([sys.executable, script], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("REF-TRAIN-OK")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
+    d_student, d_teacher, d_simple, d_var, d_mean = (float(v) for v in lines[0].split()[1:])
+    assert d_student <= 1e-4 and d_teacher <= 1e-4 and d_simple <= 1e-4
+    assert d_var <= 1e-5
+    assert d_mean <= 2.5e-3          # conv biases random-walk by +-lr on rounding noise (see the script)
