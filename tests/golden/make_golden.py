@@ -9,6 +9,8 @@
   ``baseline/utils/Scaler.py`` (``calculate_scaler``) over seeded amplitude mels sent through the oracle's
   ApplyLog / PadOrTrunc / ToTensor chain (DataLoad.py is not importable here: librosa), one set padded
   (frames = 48 > T), one truncated (frames = 32 < T), plus ``normalize`` of one sample.
+* train_reference.npz -- inputs of three mean-teacher batches and (a strided subsample of) the student / teacher
+  parameters after the reference's OWN ``baseline/main.py::train`` processed them on the CPU (dropout=0 kwargs).
 * mel_oracle.npz      -- float64 oracle log-mel features of three short seeded synthetic clips (librosa itself is
   not installed: these pin the restatement against accidental edits, not against librosa; "parity unpinned").
 """
@@ -94,7 +96,18 @@ def main():
                         fb_sum=np.float64(omel.mel_filterbank().astype(np.float64).sum()),
                         fb_nnz=np.int64(np.count_nonzero(omel.mel_filterbank())))
     scaler_fixture()
+    train_fixture()
     print("wrote fixtures to", HERE)
+
+
+def train_fixture():
+    """train_reference.npz: three batches through the reference's OWN main.train (tests/scripts/ref_train_vs_oracle.py
+    runs it unmodified on the CPU): inputs + a strided subsample of the student / teacher slabs afterwards."""
+    import subprocess
+    import tempfile
+    script = os.path.join(ROOT, "tests", "scripts", "ref_train_vs_oracle.py")
+    subprocess.run([sys.executable, script, os.path.join(HERE, "train_reference.npz")], cwd=tempfile.mkdtemp(),
+                   check=True)
 
 
 def reference_scaler():

@@ -104,4 +104,18 @@ for i, (x, tgt) in enumerate(simple_batches):
     otrain.train_batch(p2, buf2, adam2, x, tgt, i, len(simple_batches), weak_mask=slice(4), strong_mask=slice(4, 8))
 d_simple = max_diff(model, p2)
 
+if len(sys.argv) > 1:          # tests/golden/make_golden.py: save what the REFERENCE produced (strided subsample of the slabs)
+    import numpy as np
+    names = [k for k, _ in student.named_parameters()]
+    flat_s = torch.cat([v.detach().reshape(-1) for _, v in student.named_parameters()]).numpy()
+    flat_t = torch.cat([v.detach().reshape(-1) for _, v in teacher.named_parameters()]).numpy()
+    out = {"stride": np.int64(8), "student_after": flat_s[::8].copy(), "teacher_after": flat_t[::8].copy(),
+           "seeds": np.array([31, 32, 5], dtype=np.int64), "B": np.int64(B), "T": np.int64(T),
+           "n_params": np.int64(flat_s.size), "first_name": np.array(names[0])}
+    for i in range(3):
+        out["running_var%d" % i] = bn["cnn.cnn.batchnorm%d.running_var" % i].numpy()
+    for j, (x, xe, tgt) in enumerate(batches):
+        out["x%d" % j], out["xe%d" % j], out["tgt%d" % j] = x.numpy(), xe.numpy(), tgt.numpy()
+    np.savez_compressed(sys.argv[1], **out)
+
 print("REF-TRAIN-OK %.3e %.3e %.3e %.3e %.3e" % (d_student, d_teacher, d_simple, d_bn, d_rm))

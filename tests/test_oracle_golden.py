@@ -137,3 +137,27 @@ def test_ramp_and_ema_schedule():
     assert otrain.ema_alpha(1) == 0.5 and otrain.ema_alpha(999) == pytest.approx(0.999) and otrain.ema_alpha(5000) == 0.999
     assert otrain.consistency_weight(0, 210) == pytest.approx(2 * np.exp(-5.0))
     assert otrain.consistency_weight(10499, 210) < 2.0 and otrain.consistency_weight(10500, 210) == 2.0
+
+
+def test_step_oracle_matches_reference_train_fixture():
+    """oracle.train_step.train_batch on the inputs of tests/golden/train_reference.npz reproduces what the reference's
+    OWN main.train left in the student / teacher parameters (strided subsample) and in the BN running variances."""
+    z = np.load(os.path.join(GOLD, "train_reference.npz"))
+    s_seed, t_seed, _ = (int(v) for v in z["seeds"])
+    ps, pt = ocrnn.init_params(seed=s_seed), ocrnn.init_params(seed=t_seed)
+    sbuf, tbuf = ocrnn.init_buffers(), ocrnn.init_buffers()
+    adam = otrain.new_adam_state(ps)
+    for i in range(3):
+        otrain.train_batch(ps, sbuf, adam, torch.from_numpy(z["x%d" % i]), torch.from_numpy(z["tgt%d" % i]), i, 3,
+                           teacher_p=pt, teacher_buf=tbuf, x_ema=torch.from_numpy(z["xe%d" % i]),
+                           weak_mask=slice(2), strong_mask=slice(6, 8))
+    stride = int(z["stride"])
+    names = list(ocrnn.param_shapes(10).keys())
+    keep = torch.cat([torch.full((int(np.prod(ocrnn.param_shapes(10)[k])),), not (".conv" in k and k.endswith("bias")))
+                      for k in names])[::stride].numpy().astype(bool)   # conv biases: rounding-noise random walk
+    for p, key in ((ps, "student_after"), (pt, "teacher_after")):
+        flat = torch.cat([p[k].reshape(-1) for k in names]).numpy()
+        assert flat.size == int(z["n_params"])
+        assert np.abs(flat[::stride] - z[key])[keep].max() <= 1e-4
+    for i in range(3):
+        assert np.abs(sbuf["cnn.cnn.batchnorm%d.running_var" % i].numpy() - z["running_var%d" % i]).max() <= 1e-5
