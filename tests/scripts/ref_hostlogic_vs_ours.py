@@ -1,0 +1,130 @@
+"""Run by tests/test_oracle_vs_reference.py in a SUBPROCESS (needs /root/reference).
+
+Pins this package's HOST logic against the reference's own ``baseline/utils/utils.py`` and ``baseline/DataLoad.py``,
+imported unmodified.  Those modules import soundfile / librosa / dcase_util at the top (absent here), so empty stub
+modules stand in for the three packages; everything compared below is the reference's own code EXCEPT
+``librosa.amplitude_to_db``, which the stub forwards to the oracle's restatement (so the dB step itself is not pinned
+here; order of the chain, noise, padding, tensor conversion and normalisation are).  ``Sampler.__init__`` is patched to
+accept the ``data_source`` argument the reference still passes (removed in torch >= 2.2).
+Prints ``REF-HOST-OK <n checks>``.
+"""
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference/baseline"
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import pandas as pd  # noqa: E402
+import torch  # noqa: E402
+
+from oracle import mel as omel  # noqa: E402
+
+for name in ("soundfile", "dcase_util", "dcase_util.data", "sed_eval"):
+    sys.modules[name] = types.ModuleType(name)
+sys.modules["dcase_util.data"].DecisionEncoder = type("DecisionEncoder", (), {})
+sys.modules["dcase_util.data"].ProbabilityEncoder = type("ProbabilityEncoder", (), {})
+librosa = types.ModuleType("librosa")
+librosa.amplitude_to_db = omel.amplitude_to_db
+sys.modules["librosa"] = librosa
+torch.utils.data.sampler.Sampler.__init__ = lambda self, *a, **k: None
+
+sys.path.insert(1, REF)
+import DataLoad as ref_dl  # noqa: E402          (the reference's)
+from utils import utils as ref_utils  # noqa: E402
+from utils.Scaler import Scaler as RefScaler  # noqa: E402
+assert ref_dl.__file__.startswith(REF) and ref_utils.__file__.startswith(REF)
+
+from dcase2019_task4_b200 import DataLoad as our_dl  # noqa: E402
+from dcase2019_task4_b200.utils import utils as our_utils  # noqa: E402
+
+checks = 0
+CLASSES = ["Alarm_bell_ringing", "Blender", "Cat", "Dishes", "Dog", "Electric_shaver_toothbrush", "Frying",
+           "Running_water", "Speech", "Vacuum_cleaner"]
+
+# ---- ManyHotEncoder (utils/utils.py:22-172): the [108, 10] target layout ----
+ref_enc, our_enc = ref_utils.ManyHotEncoder(CLASSES, n_frames=108), our_utils.ManyHotEncoder(CLASSES, n_frames=108)
+strong_df = pd.DataFrame({"onset": [3.0, 50.0, 0.0], "offset": [9.0, 108.0, 20.5], "event_label": ["Dog", "Cat", "Speech"]})
+cases = [strong_df, strong_df.iloc[0], ["Dog", "Speech"], [["Dog", 2, 6], ["Cat", 0, 20]], "empty", [],
+         pd.Series(["Blender"]), pd.DataFrame({"onset": [np.nan], "offset": [np.nan], "event_label": [np.nan]})]
+for c in cases:
+    assert np.array_equal(ref_enc.encode_strong_df(c), our_enc.encode_strong_df(c)), c
+    checks += 1
+for c in (["Dog", "Cat"], "empty", [], pd.Series(["Speech", np.nan]), strong_df):
+    assert np.array_equal(ref_enc.encode_weak(c), our_enc.encode_weak(c)), c
+    checks += 1
+assert ref_enc.decode_weak(ref_enc.encode_weak(["Dog", "Cat"])) == our_enc.decode_weak(our_enc.encode_weak(["Dog", "Cat"]))
+assert ref_enc.state_dict() == our_enc.state_dict()
+checks += 2
+
+# ---- DataLoadDf (DataLoad.py:25-154) + ConcatDataset (:383-439) ----
+rng = np.random.default_rng(0)
+feat = {("f%d.wav" % i): rng.random((7, 64)).astype(np.float32) for i in range(12)}
+weak_df = pd.DataFrame({"filename": ["f0.wav", "f1.wav", "f2.wav"], "event_labels": ["Dog,Cat", "Speech", "Dishes"]})
+unl_df = pd.DataFrame({"filename": ["f3.wav", "f4.wav", "f5.wav", "f6.wav"]})
+syn_df = pd.DataFrame({"filename": ["f7.wav", "f7.wav", "f8.wav", "f9.wav", "f9.wav"], "onset": [1.0, 30.0, 5.0, 0.0, 60.0],
+                       "offset": [9.0, 50.0, 80.0, 10.0, 100.0], "event_label": ["Dog", "Cat", "Speech", "Frying", "Dog"]})
+sets = {}
+for tag, mod, enc in (("ref", ref_dl, ref_enc), ("our", our_dl, our_enc)):
+    sets[tag] = [mod.DataLoadDf(df, lambda f: feat[f], enc.encode_strong_df) for df in (weak_df, unl_df, syn_df)]
+for a, b in zip(sets["ref"], sets["our"]):
+    assert len(a) == len(b) and list(a.filenames) == list(b.filenames)
+    for i in range(len(a)):
+        (fa, ya), (fb, yb) = a[i], b[i]
+        assert np.array_equal(fa, fb) and np.array_equal(ya, yb), (i, ya.sum(), yb.sum())
+        checks += 1
+cat_ref, cat_our = ref_dl.ConcatDataset(sets["ref"]), our_dl.ConcatDataset(sets["our"])
+assert len(cat_ref) == len(cat_our) == 10
+assert [list(r) for r in cat_ref.cluster_indices] == [list(r) for r in cat_our.cluster_indices]
+for i in range(10):
+    assert np.array_equal(cat_ref[i][1], cat_our[i][1])
+checks += 3
+
+# ---- MultiStreamBatchSampler (:539-577): same numpy global RNG stream -> same batches ----
+for shuffle in (False, True):
+    np.random.seed(11)
+    ref_batches = [tuple(int(v) for v in b) for b in ref_dl.MultiStreamBatchSampler(cat_ref, [1, 2, 1], shuffle=shuffle)]
+    np.random.seed(11)
+    our_sampler = our_dl.MultiStreamBatchSampler(cat_our, [1, 2, 1], shuffle=shuffle)
+    our_batches = [tuple(int(v) for v in b) for b in our_sampler]
+    assert ref_batches == our_batches and len(our_batches) == len(our_sampler) == 2, (ref_batches, our_batches)
+    checks += 1
+
+# ---- transform chain (DataLoad.py:189-350 through get_transforms, utils/utils.py:397-412) vs the oracle chain ----
+ref_scaler = RefScaler()
+ref_scaler.load_state_dict({"mean_": np.linspace(-40, -10, 64).tolist(),
+                            "mean_of_square_": (np.linspace(-40, -10, 64) ** 2 + np.linspace(50, 200, 64)).tolist()})
+amp = (np.abs(rng.normal(0, 1, (87, 64))) * 30).astype(np.float32)
+label = np.zeros((108, 10))
+for frames in (96, 64):
+    chain = ref_utils.get_transforms(frames, ref_scaler, augment_type="noise")
+    np.random.seed(3)
+    x, x_noisy, y = chain((amp, label))
+    np.random.seed(3)
+    noise = np.abs(np.random.normal(0, 0.5 ** 2, amp.shape))
+    c, n = omel.transform_chain(amp, ref_scaler.mean_, ref_scaler.std_, noise=noise, frames=frames)
+    assert tuple(x.shape) == (1, frames, 64) and x.dtype == torch.float32 and y.dtype == torch.float32
+    assert np.abs(x.numpy() - c).max() <= 1e-6 and np.abs(x_noisy.numpy() - n).max() <= 1e-6
+    plain = ref_utils.get_transforms(frames)((amp, label))
+    assert len(plain) == 2 and np.abs(plain[0].numpy() - omel.transform_chain(amp, None, None, frames=frames)[0]).max() <= 1e-6
+    ours = our_utils.get_transforms(frames, ref_scaler, augment_type="noise")
+    assert [type(t).__name__ for t in ours.transforms] == [type(t).__name__ for t in chain.transforms]
+    checks += 3
+
+# ---- small utilities: SaveBest, AverageMeterSet (utils/utils.py:242-394) ----
+for comp in ("inf", "sup"):
+    a, b = ref_utils.SaveBest(comp), our_utils.SaveBest(comp)
+    for v in (0.3, 0.5, 0.1, 0.1, 0.7):
+        assert a.apply(v) == b.apply(v)
+    assert (a.best_val, a.best_epoch) == (b.best_val, b.best_epoch)
+    checks += 1
+ma, mb = ref_utils.AverageMeterSet(), our_utils.AverageMeterSet()
+for k, v in (("Loss", 2.0), ("Loss", 4.0), ("lr", 0.001)):
+    ma.update(k, v)
+    mb.update(k, v)
+assert str(ma) == str(mb) and ma.averages() == mb.averages() and ma.sums() == mb.sums()
+checks += 1
+
+print("REF-HOST-OK %d" % checks)
