@@ -127,4 +127,29 @@ for k, v in (("Loss", 2.0), ("Loss", 4.0), ("lr", 0.001)):
 assert str(ma) == str(mb) and ma.averages() == mb.averages() and ma.sums() == mb.sums()
 checks += 1
 
+# ---- pure helpers of evaluation_measures.py (:85-122, :183-199); the sed_eval / dcase_util users are restated ----
+import evaluation_measures as ref_em  # noqa: E402          (the reference's, with the stubs above)
+from dcase2019_task4_b200 import evaluation_measures as our_em  # noqa: E402
+assert ref_em.__file__.startswith(REF)
+ra = rng.integers(0, 2, (40, 10))
+rb = rng.integers(0, 2, (40, 10))
+for x, y in zip(ref_em.intermediate_at_measures(ra, rb), our_em.intermediate_at_measures(ra, rb)):
+    assert np.array_equal(x, y)
+tp, fp, fn, _ = ref_em.intermediate_at_measures(ra, rb)
+assert np.array_equal(ref_em.macro_f_measure(tp, fp, fn), our_em.macro_f_measure(tp, fp, fn))
+events = pd.DataFrame([("a.wav", 0.0, 1.0, "Dog"), ("a.wav", 2.0, 3.0, "Cat"), ("b.wav", np.nan, np.nan, np.nan)],
+                      columns=["filename", "onset", "offset", "event_label"])
+assert ref_em.get_event_list_current_file(events, "a.wav") == our_em.get_event_list_current_file(events, "a.wav")
+# a file whose single row has no label: the reference returns [{"filename": ...}] (a label-less entry sed_eval ignores),
+# ours returns [] -- the same "no events" for the restated metrics
+assert ref_em.get_event_list_current_file(events, "b.wav") == [{"filename": "b.wav"}]
+assert our_em.get_event_list_current_file(events, "b.wav") == []
+checks += 4
+try:                                  # pandas >= 2.2 drops the grouping column inside groupby.apply: the reference breaks
+    ref_em.audio_tagging_results(events.dropna(), events.dropna())
+    ref_tagging = "works"
+except KeyError:
+    ref_tagging = "KeyError"
+print("reference audio_tagging_results under this pandas:", ref_tagging)
+
 print("REF-HOST-OK %d" % checks)
