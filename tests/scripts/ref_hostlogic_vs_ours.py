@@ -6,7 +6,8 @@ modules stand in for the three packages; everything compared below is the refere
 ``librosa.amplitude_to_db``, which the stub forwards to the oracle's restatement (so the dB step itself is not pinned
 here; order of the chain, noise, padding, tensor conversion and normalisation are).  ``Sampler.__init__`` is patched to
 accept the ``data_source`` argument the reference still passes (removed in torch >= 2.2).
-Prints ``REF-HOST-OK <n checks>``.
+The tsv bookkeeping of ``DatasetDcase2019Task4.py`` (static methods, cache naming) is compared on the metadata tables the
+reference ships.  Prints ``REF-HOST-OK <n checks>``.
 """
 import os
 import sys
@@ -151,5 +152,35 @@ try:                                  # pandas >= 2.2 drops the grouping column 
 except KeyError:
     ref_tagging = "KeyError"
 print("reference audio_tagging_results under this pandas:", ref_tagging)
+
+# ---- tsv bookkeeping of DatasetDcase2019Task4.py (:92-181), static methods only (no audio here) ----
+sys.modules["download_data"] = types.ModuleType("download_data")
+sys.modules["download_data"].download = lambda *a, **k: None
+cwd = os.getcwd()
+import DatasetDcase2019Task4 as ref_ds_mod  # noqa: E402   (reference; utils.Logger opens Baseline.log in the CWD = tmp)
+from dcase2019_task4_b200.DatasetDcase2019Task4 import DatasetDcase2019Task4 as OurDS  # noqa: E402
+RefDS = ref_ds_mod.DatasetDcase2019Task4
+assert ref_ds_mod.__file__.startswith(REF)
+meta = os.path.join(os.path.dirname(REF), "dataset", "metadata")
+for rel in ("train/weak.tsv", "train/synthetic.tsv", "train/unlabel_in_domain.tsv", "validation/validation.tsv",
+            "validation/eval_dcase2018.tsv"):
+    path = os.path.join(meta, rel)
+    assert RefDS.get_audio_dir_path_from_meta(path) == OurDS.get_audio_dir_path_from_meta(path), rel
+    a, b = RefDS.get_df_from_meta(path), OurDS.get_df_from_meta(path)
+    assert a.equals(b)
+    a, b = RefDS.get_df_from_meta(path, 25), OurDS.get_df_from_meta(path, 25)
+    assert a.equals(b) and a.filename.nunique() == 25
+    checks += 3
+dfs = [RefDS.get_df_from_meta(os.path.join(meta, "train/weak.tsv")), RefDS.get_df_from_meta(os.path.join(meta, "train/synthetic.tsv"))]
+assert sorted(RefDS.get_classes(dfs)) == sorted(OurDS.get_classes(dfs)) == CLASSES
+checks += 1
+ref_ds = RefDS(cwd, base_feature_dir=os.path.join(cwd, "features_ref"), save_log_feature=False)
+our_ds = OurDS(cwd, base_feature_dir=os.path.join(cwd, "features_our"), save_log_feature=False)
+assert os.path.relpath(ref_ds.feature_dir, os.path.join(cwd, "features_ref")) == \
+    os.path.relpath(our_ds.feature_dir, os.path.join(cwd, "features_our"))          # cache directory naming
+np.save(os.path.join(ref_ds.feature_dir, "clip.npy"), amp)
+np.save(os.path.join(our_ds.feature_dir, "clip.npy"), amp)
+assert np.array_equal(ref_ds.get_feature_file("clip.wav"), our_ds.get_feature_file("clip.wav"))
+checks += 2
 
 print("REF-HOST-OK %d" % checks)
