@@ -153,6 +153,26 @@ except KeyError:
     ref_tagging = "KeyError"
 print("reference audio_tagging_results under this pandas:", ref_tagging)
 
+# ---- weights_init (utils/utils.py:205-224) applied to THIS package's CRNN through module.apply (main.py:282) ----
+from dcase2019_task4_b200 import config as our_cfg  # noqa: E402
+from dcase2019_task4_b200.models.CRNN import CRNN as OurCRNN  # noqa: E402
+torch.manual_seed(123)
+m_ref_init = OurCRNN(**our_cfg.crnn_kwargs)
+torch.manual_seed(7)
+m_ref_init.apply(ref_utils.weights_init)                 # the reference's function visits our sub-modules by class name
+torch.manual_seed(123)
+m_our_init = OurCRNN(**our_cfg.crnn_kwargs)
+torch.manual_seed(7)
+m_our_init.apply(our_utils.weights_init)
+for (k, a), (_, b) in zip(m_ref_init.named_parameters(), m_our_init.named_parameters()):
+    assert torch.equal(a, b), k                          # same generator consumption, same values
+pr = dict(m_ref_init.named_parameters())
+assert float(pr["cnn.cnn.conv1.bias"].abs().max()) == 0.0 and abs(float(pr["cnn.cnn.batchnorm1.weight"].mean()) - 1) < 0.02
+w = pr["rnn.rnn.weight_hh_l0"].detach()
+assert float((w.t() @ w - torch.eye(64)).abs().max()) < 1e-5          # orthogonal init of the GRU matrices
+assert 0.008 < float(pr["dense.weight"].std()) < 0.012 and float(pr["dense_softmax.bias"].abs().max()) == 0.0
+checks += 2
+
 # ---- tsv bookkeeping of DatasetDcase2019Task4.py (:92-181), static methods only (no audio here) ----
 sys.modules["download_data"] = types.ModuleType("download_data")
 sys.modules["download_data"].download = lambda *a, **k: None
