@@ -2,9 +2,9 @@
 
 Pins this package's HOST logic against the reference's own ``baseline/utils/utils.py`` and ``baseline/DataLoad.py``,
 imported unmodified.  Those modules import soundfile / librosa / dcase_util at the top (absent here), so empty stub
-modules stand in for the three packages; everything compared below is the reference's own code EXCEPT
-``librosa.amplitude_to_db``, which the stub forwards to the oracle's restatement (so the dB step itself is not pinned
-here; order of the chain, noise, padding, tensor conversion and normalisation are).  ``Sampler.__init__`` is patched to
+modules stand in for soundfile / dcase_util, and ``librosa``'s three entry points (stft, feature.melspectrogram,
+amplitude_to_db) are served by ``torch.stft`` and ``transformers.audio_utils`` -- independent implementations, not the
+oracle -- so the reference's own call sites are what is compared with the oracle's restatement.  ``Sampler.__init__`` is patched to
 accept the ``data_source`` argument the reference still passes (removed in torch >= 2.2).
 The tsv bookkeeping of ``DatasetDcase2019Task4.py`` (static methods, cache naming) is compared on the metadata tables the
 reference ships.  Prints ``REF-HOST-OK <n checks>``.
@@ -23,13 +23,39 @@ import torch  # noqa: E402
 
 from oracle import mel as omel  # noqa: E402
 
+from transformers import audio_utils as _au  # noqa: E402   (before the stubs: transformers probes for soundfile)
+import importlib.machinery  # noqa: E402
+
 for name in ("soundfile", "dcase_util", "dcase_util.data", "sed_eval"):
     sys.modules[name] = types.ModuleType(name)
+    sys.modules[name].__spec__ = importlib.machinery.ModuleSpec(name, None)
 sys.modules["dcase_util.data"].DecisionEncoder = type("DecisionEncoder", (), {})
 sys.modules["dcase_util.data"].ProbabilityEncoder = type("ProbabilityEncoder", (), {})
+# librosa stand-in built on transformers.audio_utils (an independent numpy implementation written upstream to reproduce
+# librosa) and torch.stft -- NOT on the oracle -- so that the reference's own call sites (which arguments, which
+# transposes and casts: DatasetDcase2019Task4.py:209-231, DataLoad.py:203-207) are what gets compared with the oracle
+
+
+def _stft(y, n_fft, hop_length, window, center=True, pad_mode="reflect"):
+    out = torch.stft(torch.as_tensor(np.asarray(y, dtype=np.float64)), n_fft=n_fft, hop_length=hop_length,
+                     window=torch.as_tensor(np.asarray(window, dtype=np.float64)), center=center, pad_mode=pad_mode,
+                     return_complex=True)
+    return out.numpy()
+
+
+def _melspectrogram(S, sr, n_mels, fmin, fmax, htk=False, norm=None):
+    fb = _au.mel_filter_bank(num_frequency_bins=S.shape[0], num_mel_filters=n_mels, min_frequency=fmin, max_frequency=fmax,
+                             sampling_rate=sr, norm=norm, mel_scale="htk" if htk else "slaney")
+    return np.dot(fb.T.astype(np.float32), S)            # librosa stores the basis as float32
+
+
 librosa = types.ModuleType("librosa")
-librosa.amplitude_to_db = omel.amplitude_to_db
+librosa.feature = types.ModuleType("librosa.feature")
+librosa.stft = _stft
+librosa.feature.melspectrogram = _melspectrogram
+librosa.amplitude_to_db = lambda S: _au.amplitude_to_db(np.asarray(S), reference=1.0, min_value=1e-5, db_range=80.0)
 sys.modules["librosa"] = librosa
+sys.modules["librosa.feature"] = librosa.feature
 torch.utils.data.sampler.Sampler.__init__ = lambda self, *a, **k: None
 
 sys.path.insert(1, REF)
@@ -109,7 +135,8 @@ for frames in (96, 64):
     assert tuple(x.shape) == (1, frames, 64) and x.dtype == torch.float32 and y.dtype == torch.float32
     assert np.abs(x.numpy() - c).max() <= 1e-6 and np.abs(x_noisy.numpy() - n).max() <= 1e-6
     plain = ref_utils.get_transforms(frames)((amp, label))
-    assert len(plain) == 2 and np.abs(plain[0].numpy() - omel.transform_chain(amp, None, None, frames=frames)[0]).max() <= 1e-6
+    # raw dB in float32: 20 log10(max(amin, x)) (stand-in) vs 10 log10(max(amin^2, x^2)) (librosa's form, oracle): 1-2 ulp at ~40 dB
+    assert len(plain) == 2 and np.abs(plain[0].numpy() - omel.transform_chain(amp, None, None, frames=frames)[0]).max() <= 2e-5
     ours = our_utils.get_transforms(frames, ref_scaler, augment_type="noise")
     assert [type(t).__name__ for t in ours.transforms] == [type(t).__name__ for t in chain.transforms]
     checks += 3
@@ -198,6 +225,16 @@ ref_ds = RefDS(cwd, base_feature_dir=os.path.join(cwd, "features_ref"), save_log
 our_ds = OurDS(cwd, base_feature_dir=os.path.join(cwd, "features_our"), save_log_feature=False)
 assert os.path.relpath(ref_ds.feature_dir, os.path.join(cwd, "features_ref")) == \
     os.path.relpath(our_ds.feature_dir, os.path.join(cwd, "features_our"))          # cache directory naming
+# the reference's own calculate_mel_spec (its window, centring, padding, transposition, float32 cast) over the
+# transformers / torch.stft stand-in, against the oracle's restatement
+from dcase2019_task4_b200 import synth  # noqa: E402
+clips, _ = synth.make_clips(2, seed=9, n_samples=30000)
+for wv in clips:
+    ref_mel = ref_ds.calculate_mel_spec(wv.astype(np.float64))
+    ora_mel = omel.calculate_mel_spec(wv.astype(np.float64))
+    assert ref_mel.dtype == np.float32 and ref_mel.shape == ora_mel.shape == (1 + 30000 // 511, 64)
+    assert np.abs(ref_mel - ora_mel).max() <= 2e-7 * ora_mel.max() + 1e-6
+    checks += 1
 np.save(os.path.join(ref_ds.feature_dir, "clip.npy"), amp)
 np.save(os.path.join(our_ds.feature_dir, "clip.npy"), amp)
 assert np.array_equal(ref_ds.get_feature_file("clip.wav"), our_ds.get_feature_file("clip.wav"))
