@@ -72,6 +72,13 @@ SIGNATURES = {
     "dcase_mt_loss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p,
                             c_p, c_p]),
     "dcase_adam_ema_step": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_p, c_p]),
+    "dcase_p2p_handle_bytes": (c_i, []),
+    "dcase_p2p_create": (c_i, [c_p, c_i, c_i, c_sz, ctypes.POINTER(c_p), c_p]),
+    "dcase_p2p_connect": (c_i, [c_p, c_p]),
+    "dcase_p2p_grads": (c_p, [c_p]),
+    "dcase_p2p_begin_step": (c_i, [c_p, c_p]),
+    "dcase_p2p_adam_ema_step": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_p]),
+    "dcase_p2p_destroy": (c_i, [c_p]),
     "dcase_mt_fwd_bwd": (c_i, [c_p, ctypes.POINTER(MtArgs), c_p]),
     "dcase_sizeof_mt_args": (c_sz, []),
     "dcase_sizeof_step_scalars": (c_sz, []),

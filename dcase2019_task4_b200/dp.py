@@ -52,3 +52,47 @@ def broadcast_model_(model, src=0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(model.flat_parameters(), src, group=group)
         dist.broadcast(model.flat_bn_running(), src, group=group)
+
+
+class _RawCudaArray(object):
+    """Minimal __cuda_array_interface__ carrier: lets torch alias memory the C library owns (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class P2PGradExchange(object):
+    """EXPERIMENTAL (DCASE_DP_P2P=1; compiles, not yet run on hardware): the gradient exchange fused with Adam + EMA
+    over NVLink peer memory (csrc/p2p.cu).  ``grads`` is a torch view of the library-owned, IPC-exported slab the
+    backward writes into; ``begin_step`` goes before the backward, ``adam_ema_step`` replaces all-reduce + optimizer."""
+
+    def __init__(self, n_floats, group=None):
+        import ctypes
+        from . import _lib
+        self._lib = _lib
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = _lib.lib()
+        blob = ctypes.create_string_buffer(L.dcase_p2p_handle_bytes())
+        self.handle = ctypes.c_void_p()
+        _lib.check(L.dcase_p2p_create(_lib.ctx(), self.world, self.rank, int(n_floats), ctypes.byref(self.handle), blob))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(blob.raw), group=group)
+        self._all = ctypes.create_string_buffer(b"".join(gathered))
+        _lib.check(L.dcase_p2p_connect(self.handle, self._all))
+        dist.barrier(group)                                   # every rank has mapped every slab before anyone signals
+        self._raw = _RawCudaArray(L.dcase_p2p_grads(self.handle), n_floats)
+        self.grads = torch.as_tensor(self._raw, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def begin_step(self):
+        self._lib.check(self._lib.lib().dcase_p2p_begin_step(self.handle, self._lib.stream_ptr()))
+
+    def adam_ema_step(self, p, m, v, p_ema, step_t, lr, beta1, beta2, eps, ema_alpha, scalars=None):
+        L, ptr = self._lib.lib(), self._lib.ptr
+        self._lib.check(L.dcase_p2p_adam_ema_step(self._lib.ctx(), self.handle, ptr(p), ptr(m), ptr(v), ptr(p_ema),
+                                                  lr, beta1, beta2, eps, int(step_t), float(ema_alpha), ptr(scalars),
+                                                  self._lib.stream_ptr()))
+
+    def close(self):
+        if self.handle:
+            self._lib.lib().dcase_p2p_destroy(self.handle)
+            self.handle = None

@@ -123,6 +123,12 @@ class MeanTeacherEngine(object):
         self.ws_t = K.new_workspace(B, frames, NC, dev) if ema_model is not None else None
         n = model.flat_parameters().numel()
         self.grads = torch.zeros(n, **f32)
+        # opt-in (DCASE_DP_P2P=1, unverified on hardware): gradient exchange fused with Adam + EMA over NVLink peer
+        # memory instead of NCCL all-reduce + optimizer kernel; the backward then writes into the library-owned slab
+        self.p2p = None
+        if self.world > 1 and os.environ.get("DCASE_DP_P2P", "0") == "1":
+            self.p2p = dp.P2PGradExchange(n, process_group)
+            self.grads = self.p2p.grads
         self._bind_adam_state(n)
         self._x = torch.empty(B, frames, 64, **f32)
         self._x_ema = torch.empty(B, frames, 64, **f32) if ema_model is not None else None
@@ -166,15 +172,23 @@ class MeanTeacherEngine(object):
         model._nbt_pending += 1
         prev_pending, prev_slot = self._pending, self._slot
         with torch.cuda.device(self.dev):
-            K.mt_fwd_bwd(a)
-            grad_scale = dp.allreduce_grads_(self.grads, self.pg) if self.world > 1 else 1.0   # flat slab, SUM
             g = self.optimizer.param_groups[0]
-            torch._foreach_add_(self._steps, 1.0)
             alpha = min(1 - 1 / (global_step_after + 1), 0.999)
-            K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
-                            ema.flat_parameters() if ema is not None else None, self._adam_step_count(),
-                            lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], ema_alpha=alpha,
-                            grad_scale=grad_scale)
+            if self.p2p is not None:
+                self.p2p.begin_step()                      # nobody still reads this rank's slab of the previous step
+                K.mt_fwd_bwd(a)
+                torch._foreach_add_(self._steps, 1.0)
+                self.p2p.adam_ema_step(model.flat_parameters(), self.m, self.v,
+                                       ema.flat_parameters() if ema is not None else None, self._adam_step_count(),
+                                       g["lr"], g["betas"][0], g["betas"][1], g["eps"], alpha)
+            else:
+                K.mt_fwd_bwd(a)
+                grad_scale = dp.allreduce_grads_(self.grads, self.pg) if self.world > 1 else 1.0   # flat slab, SUM
+                torch._foreach_add_(self._steps, 1.0)
+                K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
+                                ema.flat_parameters() if ema is not None else None, self._adam_step_count(),
+                                lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], ema_alpha=alpha,
+                                grad_scale=grad_scale)
             self._enqueue_meter_copy()
         if check and prev_pending:
             self._check_slot(prev_slot)

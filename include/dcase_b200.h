@@ -195,6 +195,25 @@ int dcase_adam_ema_step(dcase_ctx* ctx, float* p, const float* g, float* m, floa
                         float lr, float beta1, float beta2, float eps, int step_t, float ema_alpha,
                         float grad_scale, const void* scalars, void* stream);
 
+/* ---- EXPERIMENTAL (compiles, not yet run on hardware): data-parallel gradient exchange fused with the optimizer ---- */
+/* Under data parallelism (one process per GPU of one node) the pair "all-reduce of the gradient slab" +
+ * dcase_adam_ema_step becomes ONE kernel that reads every rank's slab out of the peers' HBM over NVLink (CUDA IPC
+ * mappings), sums in rank order, and applies Adam + EMA (main.py:152-157, :45-49 on N replicas).  csrc/p2p.cu describes
+ * the flag protocol.  Set-up: every rank calls dcase_p2p_create (allocates its slab + flag block, returns
+ * dcase_p2p_handle_bytes() bytes of IPC handles into HOST memory), the ranks exchange the handle blobs (any host
+ * channel, e.g. torch.distributed.all_gather_object), then dcase_p2p_connect(world x blob, rank-major).  Per step:
+ * dcase_p2p_begin_step before the backward writes dcase_p2p_grads(), dcase_p2p_adam_ema_step after it. */
+typedef struct dcase_p2p dcase_p2p;
+int dcase_p2p_handle_bytes(void);
+int dcase_p2p_create(dcase_ctx* ctx, int world, int rank, size_t n_floats, dcase_p2p** out, void* handles_out_host);
+int dcase_p2p_connect(dcase_p2p* h, const void* all_handles_host);
+float* dcase_p2p_grads(dcase_p2p* h);
+int dcase_p2p_begin_step(dcase_p2p* h, void* stream);
+int dcase_p2p_adam_ema_step(dcase_ctx* ctx, dcase_p2p* h, float* p, float* m, float* v, float* p_ema, float lr,
+                            float beta1, float beta2, float eps, int step_t, float ema_alpha, const void* scalars,
+                            void* stream);
+int dcase_p2p_destroy(dcase_p2p* h);
+
 /* ---- one mean-teacher iteration, main.py:84-153 (forward x2, losses, backward) ----------------------- */
 typedef struct dcase_mt_args {
     const float* x_student;   /* [B][T][64] clean */

@@ -231,3 +231,41 @@ def test_sequence_longer_than_the_resident_gru_fails_loudly(K, cuda_device):
     with pytest.raises(DcaseError):
         K.crnn_forward(x, H.flat_params(p).to(cuda_device), H.bn_running_flat(_buffers(0)).to(cuda_device), 0, ws)
         torch.cuda.synchronize()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("DCASE_EXPERIMENTAL", "0") != "1",
+                    reason="csrc/p2p.cu has not run on hardware yet (written after round 1's GPU budget was spent); "
+                           "set DCASE_EXPERIMENTAL=1 to run it")
+def test_p2p_fused_exchange_world1_matches_adam_ema(K, cuda_device):
+    """The fused exchange + optimizer kernel with a world of ONE rank (its own slab is the only peer): the flag protocol
+    runs through three epochs and the update equals dcase_adam_ema_step on the same gradients.  The multi-GPU wiring
+    (CUDA IPC mappings, remote flag stores) needs two GPUs: `DCASE_DP_P2P=1 torchrun ... bench.py --gpus 2`."""
+    import ctypes
+    from dcase2019_task4_b200 import _lib
+    L = _lib.lib()
+    n = K.param_count(10)
+    blob = ctypes.create_string_buffer(L.dcase_p2p_handle_bytes())
+    h = ctypes.c_void_p()
+    _lib.check(L.dcase_p2p_create(_lib.ctx(), 1, 0, n, ctypes.byref(h), blob))
+    _lib.check(L.dcase_p2p_connect(h, blob))
+    from dcase2019_task4_b200.dp import _RawCudaArray
+    raw = _RawCudaArray(L.dcase_p2p_grads(h), n)
+    slab = torch.as_tensor(raw, device=cuda_device)
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=g).to(cuda_device)
+    pa, pb = p0.clone(), p0.clone()
+    ma, va, mb, vb = (torch.zeros(n, device=cuda_device) for _ in range(4))
+    ea, eb = p0.clone(), p0.clone()
+    try:
+        for t in range(1, 4):
+            grad = (0.01 * torch.randn(n, generator=g)).to(cuda_device)
+            _lib.check(L.dcase_p2p_begin_step(h, _lib.stream_ptr()))
+            slab.copy_(grad)                                         # "the backward wrote the slab"
+            _lib.check(L.dcase_p2p_adam_ema_step(_lib.ctx(), h, _lib.ptr(pa), _lib.ptr(ma), _lib.ptr(va), _lib.ptr(ea),
+                                                 1e-3, 0.9, 0.999, 1e-8, t, 0.5, None, _lib.stream_ptr()))
+            K.adam_ema_step(pb, grad, mb, vb, eb, t, ema_alpha=0.5)
+        torch.cuda.synchronize()
+        for a, b in ((pa, pb), (ma, mb), (va, vb), (ea, eb)):
+            assert float((a - b).abs().max()) <= 1e-7
+    finally:
+        L.dcase_p2p_destroy(h)
