@@ -24,6 +24,7 @@
 // STATUS (round 1): compiles for sm_100a; written after the round's GPU budget was spent -- not yet run on hardware.
 // Enabled only by DCASE_DP_P2P=1 (dcase2019_task4_b200/dp.py); the default data-parallel step uses NCCL.
 #include <cuda_runtime.h>
+#include <math.h>
 
 #include "../../include/dcase_b200.h"
 #include "common.cuh"
@@ -205,8 +206,11 @@ int dcase_p2p_adam_ema_step(dcase_ctx* ctx, dcase_p2p* h, float* p, float* m, fl
     DCASE_PROF("adam_ema_p2p", s);
     p2p_signal_ready_kernel<<<1, 32, 0, s>>>(h->sync, h->d_peer_sync, h->world, h->rank);
     DCASE_LAUNCH_CHECK();
-    const float bc1 = scalars ? 1.f : 1.f - powf(beta1, (float)step_t);
-    const float bc2 = scalars ? 1.f : 1.f - powf(beta2, (float)step_t);
+    float bc1 = 1.f, bc2 = 1.f;                             // same arithmetic as dcase_adam_ema_step (api.cu)
+    if (step_t >= 1) {
+        bc1 = (float)(1.0 - pow((double)beta1, (double)step_t));
+        bc2 = (float)(1.0 - pow((double)beta2, (double)step_t));
+    }
     long long blocks = ((long long)h->n / 4 + 255) / 256;
     if (blocks > ctx->num_sms * 2) blocks = ctx->num_sms * 2;     // every CTA must be co-resident: they all spin on the flags
     adam_ema_p2p_kernel<<<(int)blocks, 256, 0, s>>>(p, h->d_peer_grads, h->sync, h->d_peer_sync, h->world, h->rank, m, v,
