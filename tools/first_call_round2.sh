@@ -12,12 +12,12 @@ run() {  # name, timeout seconds, command...
 }
 : > gpurun_out/first_call.log
 run default_suite 90 python -u -m pytest -q -m gpu --timeout 60 --timeout-method=thread tests
-DCASE_EXPERIMENTAL=1 run exp_bigru 60 python -u -m pytest -q -m gpu --timeout 40 --timeout-method=thread tests/test_gpu_bigru.py
-DCASE_EXPERIMENTAL=1 run exp_p2p_world1 40 python -u -m pytest -q -m gpu --timeout 30 --timeout-method=thread tests/test_gpu_crnn.py -k p2p
-DCASE_EXPERIMENTAL=1 run exp_pipelined 60 python -u -m pytest -q -m gpu --timeout 40 --timeout-method=thread tests/test_gpu_api.py -k "pipelined or reference_train_fixture"
-DCASE_EXPERIMENTAL=1 run gru_sweep 60 python tools/gru_sweep.py --iters 50
+run exp_bigru 60 env DCASE_EXPERIMENTAL=1 python -u -m pytest -q -m gpu --timeout 40 --timeout-method=thread tests/test_gpu_bigru.py
+run exp_p2p_world1 40 env DCASE_EXPERIMENTAL=1 python -u -m pytest -q -m gpu --timeout 30 --timeout-method=thread tests/test_gpu_crnn.py -k p2p
+run exp_pipelined 60 env DCASE_EXPERIMENTAL=1 python -u -m pytest -q -m gpu --timeout 40 --timeout-method=thread tests/test_gpu_api.py -k "pipelined or reference_train_fixture"
+run gru_sweep 60 env DCASE_EXPERIMENTAL=1 python tools/gru_sweep.py --iters 50
 run scaler_bench 40 python tools/scaler_bench.py
 run main_synthetic 150 python examples/main_synthetic.py --clips 96 --epochs 2
 run bench_default 240 python bench.py --steps 30 --warmup 6
-DCASE_PIPELINE=1 run bench_pipelined 240 python bench.py --steps 30 --warmup 6 --no-cpu-baseline
+run bench_pipelined 240 env DCASE_PIPELINE=1 python bench.py --steps 30 --warmup 6 --no-cpu-baseline
 cat gpurun_out/first_call.log
