@@ -29,8 +29,33 @@ import importlib.machinery  # noqa: E402
 for name in ("soundfile", "dcase_util", "dcase_util.data", "sed_eval"):
     sys.modules[name] = types.ModuleType(name)
     sys.modules[name].__spec__ = importlib.machinery.ModuleSpec(name, None)
-sys.modules["dcase_util.data"].DecisionEncoder = type("DecisionEncoder", (), {})
-sys.modules["dcase_util.data"].ProbabilityEncoder = type("ProbabilityEncoder", (), {})
+
+
+class _DecisionEncoder(object):
+    """dcase_util.data.DecisionEncoder.find_contiguous_regions as published (written out here, not imported from this
+    package, so the reference's decode_strong / get_predictions run over an independent statement of it)."""
+
+    def find_contiguous_regions(self, activity_array):
+        activity_array = np.asarray(activity_array).astype(bool)
+        change_indices = np.logical_xor(activity_array[1:], activity_array[:-1]).nonzero()[0]
+        change_indices += 1
+        if activity_array[0]:
+            change_indices = np.r_[0, change_indices]
+        if activity_array[-1]:
+            change_indices = np.r_[change_indices, activity_array.size]
+        return change_indices.reshape((-1, 2))
+
+
+class _ProbabilityEncoder(object):
+    """dcase_util.data.ProbabilityEncoder.binarization, 'global_threshold' branch: strictly greater than the threshold."""
+
+    def binarization(self, probabilities, binarization_type="global_threshold", threshold=0.5, time_axis=1):
+        assert binarization_type == "global_threshold"
+        return np.array(np.asarray(probabilities) > threshold, dtype=int)
+
+
+sys.modules["dcase_util.data"].DecisionEncoder = _DecisionEncoder
+sys.modules["dcase_util.data"].ProbabilityEncoder = _ProbabilityEncoder
 # librosa stand-in built on transformers.audio_utils (an independent numpy implementation written upstream to reproduce
 # librosa) and torch.stft -- NOT on the oracle -- so that the reference's own call sites (which arguments, which
 # transposes and casts: DatasetDcase2019Task4.py:209-231, DataLoad.py:203-207) are what gets compared with the oracle
@@ -199,6 +224,48 @@ w = pr["rnn.rnn.weight_hh_l0"].detach()
 assert float((w.t() @ w - torch.eye(64)).abs().max()) < 1e-5          # orthogonal init of the GRU matrices
 assert 0.008 < float(pr["dense.weight"].std()) < 0.012 and float(pr["dense_softmax.bias"].abs().max()) == 0.0
 checks += 2
+
+# ---- get_predictions (evaluation_measures.py:203-231): the reference's clip-by-clip loop vs the batched restatement ----
+if not hasattr(pd.DataFrame, "append"):                  # removed in pandas 2: shim for the reference
+    pd.DataFrame.append = lambda self, other: pd.concat([self, other])
+
+
+class _StubModel(torch.nn.Module):                       # posteriors are a fixed function of the input, CPU only
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):                                # [B, 1, T, 64] -> strong [B, T/8, 10], weak [B, 10]
+        s = torch.sigmoid(3.0 * x[:, 0].reshape(x.shape[0], x.shape[2] // 8, 8, 64)[:, :, :, :10].mean(2))
+        return s, s.mean(1)
+
+
+class _ValidSet(list):
+    pass
+
+
+T_valid = 136
+valid = _ValidSet((torch.randn(1, T_valid, 64, generator=torch.Generator().manual_seed(40 + i)), None) for i in range(7))
+valid.filenames = pd.Series(["clip%d.wav" % i for i in range(7)])
+stub = _StubModel().eval()
+ref_dec = ref_utils.ManyHotEncoder(CLASSES, n_frames=T_valid // 8)
+our_dec = our_utils.ManyHotEncoder(CLASSES, n_frames=T_valid // 8)
+with torch.no_grad():
+    ref_pred = ref_em.get_predictions(stub, valid, ref_dec.decode_strong, pooling_time_ratio=8)
+    our_pred = our_em.get_predictions(stub, valid, our_dec.decode_strong, pooling_time_ratio=8, batch_size=3)
+key = ["filename", "event_label", "onset"]
+a = ref_pred.sort_values(key).reset_index(drop=True)
+b = our_pred.sort_values(key).reset_index(drop=True)
+assert len(a) == len(b) and len(a) > 10, (len(a), len(b))
+assert list(a.event_label) == list(b.event_label) and list(a.filename) == list(b.filename)
+assert np.allclose(a.onset.to_numpy(float), b.onset.to_numpy(float), rtol=0, atol=1e-12)
+assert np.allclose(a.offset.to_numpy(float), b.offset.to_numpy(float), rtol=0, atol=1e-12)
+for lab in ([1, 0, 0, 1, 1, 0, 1], [0, 0, 0], [1, 1, 1]):
+    col = np.zeros((len(lab), 10))
+    col[:, 4] = lab
+    assert [list(map(int, r[1:])) for r in ref_dec.decode_strong(col)] == \
+        [list(map(int, r[1:])) for r in our_dec.decode_strong(col)]
+checks += 5
 
 # ---- tsv bookkeeping of DatasetDcase2019Task4.py (:92-181), static methods only (no audio here) ----
 sys.modules["download_data"] = types.ModuleType("download_data")
