@@ -267,6 +267,17 @@ for lab in ([1, 0, 0, 1, 1, 0, 1], [0, 0, 0], [1, 1, 1]):
         [list(map(int, r[1:])) for r in our_dec.decode_strong(col)]
 checks += 5
 
+# ---- get_f_measure_by_class (evaluation_measures.py:19-82), global threshold, weak and frame-level labels ----
+gq = torch.Generator().manual_seed(77)
+loader_weak = [(torch.randn(6, 1, 64, 64, generator=gq), (torch.rand(6, 10, generator=gq) < 0.4).float()) for _ in range(3)]
+loader_strong = [(x, (torch.rand(6, 8, 10, generator=gq) < 0.1).float()) for x, _ in loader_weak]
+for loader in (loader_weak, loader_strong):
+    with torch.no_grad():
+        f_ref = ref_em.get_f_measure_by_class(stub, 10, loader)
+        f_our = our_em.get_f_measure_by_class(stub, 10, loader)
+    assert np.allclose(f_ref, f_our, rtol=0, atol=1e-12) and f_ref.max() > 0
+    checks += 1
+
 # ---- tsv bookkeeping of DatasetDcase2019Task4.py (:92-181), static methods only (no audio here) ----
 sys.modules["download_data"] = types.ModuleType("download_data")
 sys.modules["download_data"].download = lambda *a, **k: None
