@@ -36,7 +36,8 @@ class MtArgs(ctypes.Structure):
                 ("params_s", c_p), ("params_t", c_p), ("bn_s", c_p), ("bn_t", c_p),
                 ("flags", c_i), ("seed", c_u64), ("step", c_u32), ("cons_weight", c_f), ("scalars", c_p),
                 ("strong_s", c_p), ("weak_s", c_p), ("strong_t", c_p), ("weak_t", c_p), ("meters", c_p),
-                ("d_strong", c_p), ("d_weak", c_p), ("ws_s", c_p), ("ws_t", c_p), ("grads", c_p)]
+                ("d_strong", c_p), ("d_weak", c_p), ("ws_s", c_p), ("ws_t", c_p), ("grads", c_p),
+                ("after_forward_event", c_p)]
 
 
 # name -> (restype, argtypes); every symbol include/dcase_b200.h declares

@@ -573,6 +573,7 @@ int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* a, void* stream) {
     }
     DCASE_TRY(dcase_crnn_forward(ctx, a->x_student, a->B, a->T, a->n_class, a->params_s, a->bn_s, a->flags, a->seed,
                                  a->step, 0, a->scalars, a->strong_s, a->weak_s, a->ws_s, stream));
+    if (a->after_forward_event) DCASE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a->after_forward_event, s));
     if (a->x_teacher) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     DCASE_TRY(dcase_mt_loss(ctx, a->strong_s, a->weak_s, a->x_teacher ? a->strong_t : nullptr,
                             a->x_teacher ? a->weak_t : nullptr, a->target, a->B, To, a->n_class, a->weak_lo, a->weak_hi,

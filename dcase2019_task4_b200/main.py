@@ -215,6 +215,7 @@ class MeanTeacherEngine(object):
         a.strong_s, a.weak_s = self.strong_s.data_ptr(), self.weak_s.data_ptr()
         a.meters, a.d_strong, a.d_weak = self.meters.data_ptr(), self.d_strong.data_ptr(), self.d_weak.data_ptr()
         a.ws_s, a.grads = self.ws_s.data_ptr(), self.grads.data_ptr()
+        a.after_forward_event = getattr(self, "_fork_handle", None)      # step_pipelined only; NULL otherwise
         return a
 
     def _graph_step(self, wave, target, mean, std, cons_weight, global_step_after, check):
@@ -296,6 +297,8 @@ class MeanTeacherEngine(object):
                             if self.ema_model is not None else [None, None])
             self._feat_slot = 0
             self._side = torch.cuda.Stream(self.dev)
+            self._fwd_done = torch.cuda.Event()
+            self._fwd_done.record()                    # creates the CUDA event; dcase_mt_fwd_bwd re-records it by handle
             self._pgraphs = {}
         return self._xp, self._xp_ema
 
@@ -322,15 +325,21 @@ class MeanTeacherEngine(object):
         slot, nxt = self._feat_slot, self._feat_slot ^ 1
         main = torch.cuda.current_stream(self.dev)
         if not self.use_graph:
-            self._side.wait_stream(main)                   # the other slot's last reader (the previous step) is done
+            next_noise_step = (self.model._rng_step + 1) & 0xFFFFFFFF
+            self._fork_handle = self._fwd_done.cuda_event      # recorded by dcase_mt_fwd_bwd after the student forward
+            try:
+                self.step(xp[slot], xpe[slot], target, cons_weight, global_step_after, check=check)
+            finally:
+                self._fork_handle = None
+            # the side stream starts once this step's forward is done (which also means the previous step -- the last
+            # reader of the other slot -- is done) and runs beside the backward
+            self._side.wait_event(self._fwd_done)
             if wave_ready_event is not None:
                 self._side.wait_event(wave_ready_event)
             with torch.cuda.stream(self._side):
                 amp = K.logmel_fwd(wave_next)
                 amp.record_stream(self._side)
-                self._finish_into(amp, mean, std, nxt, seed=self.model._rng_seed,
-                                  step=(self.model._rng_step + 1) & 0xFFFFFFFF)
-            self.step(xp[slot], xpe[slot], target, cons_weight, global_step_after, check=check)
+                self._finish_into(amp, mean, std, nxt, seed=self.model._rng_seed, step=next_noise_step)
             main.wait_stream(self._side)
             self._feat_slot = nxt
             return
@@ -360,12 +369,16 @@ class MeanTeacherEngine(object):
                 l0 = K.launch_count()
                 with torch.cuda.graph(graph):
                     cap = torch.cuda.current_stream(self.dev)
-                    self._side.wait_stream(cap)
+                    self._fork_handle = self._fwd_done.cuda_event
+                    try:
+                        K.mt_fwd_bwd(self._mt_args(xp[slot], xpe[slot], target, model.forward_flags(), 0, 0, 0.0,
+                                                   self._sc_dev.data_ptr()))
+                    finally:
+                        self._fork_handle = None
+                    self._side.wait_event(self._fwd_done)          # graph edge from the end of the student forward
                     with torch.cuda.stream(self._side):
                         amp = K.logmel_fwd(wave_next)
                         self._finish_into(amp, mean, std, nxt, step=1, scalars=self._sc_dev)   # next iteration's noise
-                    K.mt_fwd_bwd(self._mt_args(xp[slot], xpe[slot], target, model.forward_flags(), 0, 0, 0.0,
-                                               self._sc_dev.data_ptr()))
                     K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
                                     ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
                                     beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)

@@ -242,6 +242,9 @@ typedef struct dcase_mt_args {
     void* ws_s;
     void* ws_t;
     float* grads;             /* [param_count] out */
+    void* after_forward_event; /* optional cudaEvent_t recorded on `stream` once the student forward is enqueued (NULL: none):
+                                 lets the caller start independent work -- the next batch's features -- on another stream
+                                 alongside the backward instead of alongside the forward */
 } dcase_mt_args;
 
 int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* args, void* stream);
