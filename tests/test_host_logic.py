@@ -407,3 +407,60 @@ def test_dataset_bookkeeping_and_logger(tmp_path, monkeypatch):
     importlib.reload(Logger)
     Logger.LOG.info("hello")
     assert not os.path.exists(tmp_path / "Baseline.log")
+
+
+def test_properties_of_encoder_regions_and_sampler():
+    """Size-independent properties (hypothesis): region decoding inverts frame encoding; every multi-stream batch holds
+    exactly batch_sizes[i] distinct indices of stream i in stream order; rank-strided shards of one epoch are disjoint
+    and together cover what a single process would draw from the same permutation."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.booleans(), min_size=1, max_size=120))
+    def regions_roundtrip(bits):
+        a = np.array(bits)
+        regions = find_contiguous_regions(a)
+        back = np.zeros_like(a)
+        for on, off in regions:
+            assert off > on
+            back[on:off] = True
+        assert np.array_equal(back, a)
+        assert all(regions[i][1] < regions[i + 1][0] for i in range(len(regions) - 1))     # maximal, separated runs
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.integers(1, 40), min_size=1, max_size=4), st.data())
+    def sampler_batches(sizes, data):
+        bs = [data.draw(st.integers(1, max(1, n))) for n in sizes]
+
+        class Src:
+            cluster_indices = [range(sum(sizes[:i]), sum(sizes[:i + 1])) for i in range(len(sizes))]
+        sampler = DataLoad.MultiStreamBatchSampler(Src(), bs, shuffle=True, seed=data.draw(st.integers(0, 1000)))
+        batches = list(sampler)
+        assert len(batches) == len(sampler) == min(n // b for n, b in zip(sizes, bs))
+        seen = set()
+        for batch in batches:
+            assert len(batch) == sum(bs)
+            pos = 0
+            for i, b in enumerate(bs):
+                part = batch[pos:pos + b]
+                assert all(int(v) in Src.cluster_indices[i] for v in part)
+                pos += b
+            assert not (seen & set(int(v) for v in batch))
+            seen |= set(int(v) for v in batch)
+
+    @settings(max_examples=30, deadline=None)
+    @given(st.integers(2, 4), st.integers(0, 100))
+    def shards_partition(world, seed):
+        class Src:
+            cluster_indices = [range(0, 24), range(24, 72)]
+        drawn = []
+        for rank in range(world):
+            s = DataLoad.MultiStreamBatchSampler(Src(), [2, 3], shuffle=True, rank=rank, world_size=world, seed=seed)
+            drawn.append([int(v) for batch in s for v in batch])
+            assert len(s) == min(24 // world // 2, 48 // world // 3)
+        flat = [v for d in drawn for v in d]
+        assert len(flat) == len(set(flat))                      # disjoint across ranks
+
+    regions_roundtrip()
+    sampler_batches()
+    shards_partition()
