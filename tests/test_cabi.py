@@ -117,3 +117,21 @@ def _real_cuda_available():
         return subprocess.run(["nvidia-smi", "-L"], capture_output=True, timeout=10).returncode == 0
     except (OSError, subprocess.TimeoutExpired):
         return False
+
+
+def test_fft_passes_of_the_logmel_kernel_on_the_host(tmp_path):
+    """csrc/fft2048.cuh is __host__ __device__: the Stockham passes the STFT kernel runs (radix 8, 8, 8, 4) are compiled
+    for the CPU and checked against a naive float64 DFT (tests/csrc/fft_host_check.cu).  fp32 bound: 1e-4 of the
+    largest bin."""
+    import shutil
+    import subprocess
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = str(tmp_path / "fft_check")
+    src = os.path.join(ROOT, "tests", "csrc", "fft_host_check.cu")
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True,
+                   capture_output=True, timeout=300)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    err, mag = float(r.stdout.split()[1]), float(r.stdout.split()[3])
+    assert err <= 1e-4 * mag + 1e-5
