@@ -135,3 +135,28 @@ def test_fft_passes_of_the_logmel_kernel_on_the_host(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     err, mag = float(r.stdout.split()[1]), float(r.stdout.split()[3])
     assert err <= 1e-4 * mag + 1e-5
+
+
+def test_device_philox_code_on_the_host_matches_kat_and_numpy_restatement(tmp_path):
+    """csrc/common.cuh::philox4x32_10 (the function the dropout / noise kernels call) compiled for the CPU: Random123
+    known-answer vectors, and the same words as oracle/philox.py for the (row, stream, step, seed) counter layout of the
+    RNG contract (include/dcase_b200.h)."""
+    import shutil
+    import subprocess
+    import numpy as np
+    from oracle import philox
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = str(tmp_path / "philox_check")
+    src = os.path.join(ROOT, "tests", "csrc", "philox_host_check.cu")
+    subprocess.run(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe, src], check=True,
+                   capture_output=True, timeout=300)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    lines = r.stdout.strip().splitlines()
+    assert r.returncode == 0 and lines[0] == "kat_failures 0", r.stdout + r.stderr
+    seed = 0x0123456789abcdef
+    for i, line in enumerate(lines[1:]):
+        row, *words = (int(v) for v in line.split())
+        want = philox.philox4x32(np.uint32(row & 0xFFFFFFFF), np.uint32(row >> 32), np.uint32(8 * 1 + 2), np.uint32(41 + i),
+                                 np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32))
+        assert [int(np.asarray(w).reshape(-1)[0]) for w in want] == words, (row, words)
