@@ -240,13 +240,23 @@ class MultiStreamBatchSampler(Sampler):
                                               "the source {} != {}".format(len(batch_sizes), n_streams)
         self.shuffle = shuffle
         self.rank, self.world_size = rank, world_size
+        if world_size > 1 and seed is None:
+            # every rank must draw the SAME permutation, or the rank-strided shards overlap / miss clips
+            raise ValueError("MultiStreamBatchSampler: world_size > 1 needs a seed shared by all ranks")
+        if not 0 <= rank < world_size:
+            raise ValueError("rank must be in [0, world_size)")
         self._rng = np.random if seed is None else np.random.RandomState(seed)
 
     def _stream_indices(self):
         out = []
-        for ind in self.data_source.cluster_indices:
+        n_batches = len(self)
+        for ind, bs in zip(self.data_source.cluster_indices, self.batch_sizes):
             ind = self._rng.permutation(ind) if self.shuffle else np.asarray(ind)
-            out.append(ind[self.rank::self.world_size] if self.world_size > 1 else ind)
+            if self.world_size > 1:
+                # truncate BEFORE striding so every rank yields exactly len(self) batches (an extra batch on one rank
+                # would issue a gradient exchange its peers never join)
+                ind = ind[:n_batches * bs * self.world_size][self.rank::self.world_size]
+            out.append(ind)
         return out
 
     def __iter__(self):

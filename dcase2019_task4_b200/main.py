@@ -45,6 +45,8 @@ def _bounds(mask, B):
 
 
 # mirror of dcase_step_scalars (include/dcase_b200.h)
+_SC_RING = 8          # pinned slots for the per-step scalars (see MeanTeacherEngine._upload_scalars)
+_GRAPH_CACHE = 16     # captured graphs kept per engine
 _SCALARS = np.dtype([("seed", "<u8"), ("step", "<u4"), ("cons_weight", "<f4"), ("ema_alpha", "<f4"), ("lr", "<f4"),
                      ("bc1", "<f4"), ("bc2", "<f4"), ("grad_scale", "<f4"), ("pad", "<f4")])
 
@@ -145,8 +147,57 @@ class MeanTeacherEngine(object):
         self._graphs = {}
         self.graph_launches = 0            # kernels launched through graph replays (bench.py's gpu_launches)
         assert K.lib().dcase_sizeof_step_scalars() == _SCALARS.itemsize
-        self._sc_host = torch.zeros(_SCALARS.itemsize, dtype=torch.uint8).pin_memory()
+        # the per-step scalars go host -> device by an ASYNC copy from pinned memory; graph replay costs the host tens of
+        # microseconds per ~ms step, so the host runs ahead: each pinned slot carries an event recorded after its copy
+        # and is only rewritten once that copy has been consumed (ring of _SC_RING slots)
+        self._sc_ring = [torch.zeros(_SCALARS.itemsize, dtype=torch.uint8).pin_memory() for _ in range(_SC_RING)]
+        self._sc_event = [None] * _SC_RING
+        self._sc_next = 0
         self._sc_dev = torch.zeros(_SCALARS.itemsize, dtype=torch.uint8, device=dev)
+
+    def _upload_scalars(self, seed, step, cons_weight, global_step_after):
+        """Fill the next pinned ring slot with this iteration's dcase_step_scalars and enqueue its copy to the device."""
+        g = self.optimizer.param_groups[0]
+        t = self._adam_step_count() + 1
+        sc = np.zeros(1, dtype=_SCALARS)
+        sc["seed"], sc["step"], sc["cons_weight"] = seed, step, cons_weight
+        sc["ema_alpha"] = min(1 - 1 / (global_step_after + 1), 0.999)
+        sc["lr"] = g["lr"]
+        sc["bc1"], sc["bc2"] = 1.0 - g["betas"][0] ** t, 1.0 - g["betas"][1] ** t
+        sc["grad_scale"] = 1.0 / self.world
+        k = self._sc_next
+        self._sc_next = (k + 1) % _SC_RING
+        if self._sc_event[k] is not None:
+            self._sc_event[k].synchronize()        # the DMA that read this slot _SC_RING steps ago has finished
+        else:
+            self._sc_event[k] = torch.cuda.Event()
+        self._sc_ring[k].copy_(torch.from_numpy(sc.view(np.uint8)))
+        self._sc_dev.copy_(self._sc_ring[k], non_blocking=True)
+        self._sc_event[k].record()
+
+    def _graph_key_common(self):
+        """Every address a captured graph bakes in besides its inputs: the parameter / BN / Adam slabs of both models
+        (CRNN._flatten may re-allocate them on a device or dtype change)."""
+        model, ema = self.model, self.ema_model
+        g = self.optimizer.param_groups[0]
+        return (model.flat_parameters().data_ptr(), model.flat_bn_running().data_ptr(),
+                ema.flat_parameters().data_ptr() if ema is not None else 0,
+                ema.flat_bn_running().data_ptr() if ema is not None else 0,
+                self.m.data_ptr(), self.v.data_ptr(), model.forward_flags(), g["betas"], g["eps"])
+
+    @staticmethod
+    def _cache_put(cache, key, entry):
+        """Bounded graph cache (least recently used out): callers that pass fresh buffers every step must not grow it."""
+        cache[key] = entry
+        while len(cache) > _GRAPH_CACHE:
+            cache.pop(next(iter(cache)))
+
+    @staticmethod
+    def _cache_get(cache, key):
+        entry = cache.pop(key, None)
+        if entry is not None:
+            cache[key] = entry                     # re-insert: dicts keep insertion order, so the front is the LRU entry
+        return entry
 
     # torch.optim.Adam bookkeeping -----------------------------------------------------------------------
     def _bind_adam_state(self, n):
@@ -158,7 +209,7 @@ class MeanTeacherEngine(object):
 
     # one iteration ------------------------------------------------------------------------------------------
     def step(self, batch_input, ema_batch_input, target, cons_weight, global_step_after, check=True):
-        """main.py:84-157 for one batch already on the device.  Returns nothing; meters are read asynchronously
+        """main.py:84-157 for one batch already on the device.  Returns the meters of the PREVIOUS step (or None); meters are read asynchronously
         (``read_meters``).  ``global_step_after`` is the reference's ``global_step`` after its increment."""
         model, ema = self.model, self.ema_model
         x = batch_input.contiguous()
@@ -190,9 +241,10 @@ class MeanTeacherEngine(object):
                                 lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], ema_alpha=alpha,
                                 grad_scale=grad_scale)
             self._enqueue_meter_copy()
-        if check and prev_pending:
-            self._check_slot(prev_slot)
         self._pending = True
+        if check and prev_pending:
+            return self._check_slot(prev_slot)
+        return None
 
     def _mt_args(self, x, xt, target, flags, seed, step, cons_weight, scalars):
         model, ema = self.model, self.ema_model
@@ -224,19 +276,11 @@ class MeanTeacherEngine(object):
         target = target.contiguous()
         g = self.optimizer.param_groups[0]
         seed, step = model.next_rng()
-        t = self._adam_step_count() + 1
-        sc = np.zeros(1, dtype=_SCALARS)
-        sc["seed"], sc["step"], sc["cons_weight"] = seed, step, cons_weight
-        sc["ema_alpha"] = min(1 - 1 / (global_step_after + 1), 0.999)
-        sc["lr"] = g["lr"]
-        sc["bc1"], sc["bc2"] = 1.0 - g["betas"][0] ** t, 1.0 - g["betas"][1] ** t
-        sc["grad_scale"] = 1.0 / self.world
         with torch.cuda.device(self.dev):
-            self._sc_host.copy_(torch.from_numpy(sc.view(np.uint8)))
-            self._sc_dev.copy_(self._sc_host, non_blocking=True)
-            key = (wave.data_ptr(), tuple(wave.shape), wave.dtype, target.data_ptr(), mean.data_ptr(), std.data_ptr(),
-                   model.forward_flags(), g["betas"], g["eps"])
-            entry = self._graphs.get(key)
+            self._upload_scalars(seed, step, cons_weight, global_step_after)
+            key = (wave.data_ptr(), tuple(wave.shape), wave.dtype, target.data_ptr(), mean.data_ptr(), std.data_ptr()
+                   ) + self._graph_key_common()
+            entry = self._cache_get(self._graphs, key)
             if entry is None:
                 graph = torch.cuda.CUDAGraph()
                 l0 = K.launch_count()
@@ -255,7 +299,7 @@ class MeanTeacherEngine(object):
                                     ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
                                     beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
                 entry = (graph, K.launch_count() - l0)
-                self._graphs[key] = entry
+                self._cache_put(self._graphs, key, entry)
             entry[0].replay()
             self.graph_launches += entry[1]
             self._enqueue_meter_copy()
@@ -349,21 +393,13 @@ class MeanTeacherEngine(object):
         target = target.contiguous()
         g = self.optimizer.param_groups[0]
         seed, step = model.next_rng()
-        t = self._adam_step_count() + 1
-        sc = np.zeros(1, dtype=_SCALARS)
-        sc["seed"], sc["step"], sc["cons_weight"] = seed, step, cons_weight
-        sc["ema_alpha"] = min(1 - 1 / (global_step_after + 1), 0.999)
-        sc["lr"] = g["lr"]
-        sc["bc1"], sc["bc2"] = 1.0 - g["betas"][0] ** t, 1.0 - g["betas"][1] ** t
-        sc["grad_scale"] = 1.0 / self.world
         with torch.cuda.device(self.dev):
-            self._sc_host.copy_(torch.from_numpy(sc.view(np.uint8)))
-            self._sc_dev.copy_(self._sc_host, non_blocking=True)
+            self._upload_scalars(seed, step, cons_weight, global_step_after)
             if wave_ready_event is not None:
                 main.wait_event(wave_ready_event)
             key = (wave_next.data_ptr(), tuple(wave_next.shape), wave_next.dtype, target.data_ptr(), mean.data_ptr(),
-                   std.data_ptr(), slot, model.forward_flags(), g["betas"], g["eps"])
-            entry = self._pgraphs.get(key)
+                   std.data_ptr(), slot, xp[0].data_ptr()) + self._graph_key_common()
+            entry = self._cache_get(self._pgraphs, key)
             if entry is None:
                 graph = torch.cuda.CUDAGraph()
                 l0 = K.launch_count()
@@ -384,7 +420,7 @@ class MeanTeacherEngine(object):
                                     beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
                     cap.wait_stream(self._side)
                 entry = (graph, K.launch_count() - l0)
-                self._pgraphs[key] = entry
+                self._cache_put(self._pgraphs, key, entry)
             entry[0].replay()
             self.graph_launches += entry[1]
             self._enqueue_meter_copy()
@@ -412,7 +448,16 @@ class MeanTeacherEngine(object):
         assert not loss < 0, 'Loss problem, cannot be negative'
 
     def _check_slot(self, slot):
-        self._assert_loss(self._read_slot(slot)["Loss"])
+        vals = self._read_slot(slot)
+        self._assert_loss(vals["Loss"])
+        return vals
+
+    def drain(self):
+        """Meters of the last enqueued step (asserted like every other batch), or None if nothing is pending."""
+        if not self._pending:
+            return None
+        self._pending = False
+        return self._check_slot(self._slot)
 
     def read_meters(self):
         """Synchronise on the last enqueued step's 32-byte meter copy and return {name: float}."""
@@ -480,6 +525,20 @@ def _engine_for(model, optimizer, ema_model, weak_mask, strong_mask, B, T):
     return cache[key]
 
 
+def _update_meters(meters, vals, ema_model, weak_mask, strong_mask):
+    """meters.update(...) of main.py:101-145 for one batch (``vals`` from the engine's 32-byte read-back, or None)."""
+    if vals is None:
+        return
+    for name in METER_NAMES:
+        if ema_model is None and ("EMA" in name or "Consistency" in name):
+            continue
+        if weak_mask is None and name in ("weak_class_loss", "Weak EMA loss"):
+            continue
+        if strong_mask is None and name in ("Strong loss", "Strong EMA loss"):
+            continue
+        meters.update(name, vals[name])
+
+
 def train(train_loader, model, optimizer, epoch, ema_model=None, weak_mask=None, strong_mask=None, log=None):
     """One epoch of a Mean Teacher model (or of the plain CRNN when ``ema_model`` is None).
 
@@ -503,21 +562,17 @@ def train(train_loader, model, optimizer, epoch, ema_model=None, weak_mask=None,
         if ema_batch_input is not None:
             ema_batch_input = ema_batch_input.to(dev, non_blocking=True)
         if engine is None or engine.B != batch_input.shape[0] or engine.T != batch_input.shape[-2]:
+            if engine is not None:                     # a smaller last batch: settle the previous engine first
+                _update_meters(meters, engine.drain(), ema_model, weak_mask, strong_mask)
             engine = _engine_for(model, optimizer, ema_model, weak_mask, strong_mask, batch_input.shape[0],
                                  batch_input.shape[-2])
         consistency_cost = cfg.max_consistency_cost * rampup_value
-        engine.step(batch_input, ema_batch_input, target, consistency_cost, global_step + 1)
-        vals = engine.read_meters() if i == len(train_loader) - 1 else None
-        if vals is not None:
-            engine.check_loss()
-            for name in METER_NAMES:
-                if ema_model is None and ("EMA" in name or "Consistency" in name):
-                    continue
-                if weak_mask is None and name in ("weak_class_loss", "Weak EMA loss"):
-                    continue
-                if strong_mask is None and name in ("Strong loss", "Strong EMA loss"):
-                    continue
-                meters.update(name, vals[name])
+        # the reference updates every meter and asserts on the loss every batch (main.py:147-163); here the values of
+        # batch i - 1 are read (and asserted) right after batch i has been enqueued, so the GPU never waits on the host
+        prev = engine.step(batch_input, ema_batch_input, target, consistency_cost, global_step + 1)
+        _update_meters(meters, prev, ema_model, weak_mask, strong_mask)
+    if engine is not None:
+        _update_meters(meters, engine.drain(), ema_model, weak_mask, strong_mask)
     epoch_time = time.time() - start
     msg = 'Epoch: {}\tTime {:.2f}\t{meters}'.format(epoch, epoch_time, meters=meters)
     (log.info if log is not None else print)(msg)

@@ -22,14 +22,16 @@ class _CrnnFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, flags, seed, step, *params):
         B, T = x.shape[0], x.shape[-2]
-        need_grad = any(ctx.needs_input_grad[5:])
+        # needs_input_grad stays True under torch.no_grad(); only a grad-enabled TRAINING forward keeps its workspace
+        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[5:]) and bool(flags & K.FLAG_BN_BATCH_STATS)
         ws = module._take_workspace(B, T, x.device, keep=need_grad)
         strong, weak = K.crnn_forward(x, module._flat, module._bn_flat, flags, ws, n_class=module.nclass,
                                       seed=seed, step=step, model_id=module.model_id)
         ctx.module = module
-        ctx.ws = ws
+        ctx.ws = ws if need_grad else None
         ctx.cfg = (flags, seed, step)
-        ctx.save_for_backward(x, weak)
+        if need_grad:
+            ctx.save_for_backward(x, weak)
         return strong, weak
 
     @staticmethod
@@ -37,7 +39,7 @@ class _CrnnFunction(torch.autograd.Function):
         module = ctx.module
         x, weak = ctx.saved_tensors
         flags, seed, step = ctx.cfg
-        if not (flags & K.FLAG_BN_BATCH_STATS):
+        if not (flags & K.FLAG_BN_BATCH_STATS) or ctx.ws is None:
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the reference's path")
         grads = K.crnn_backward(x, module._flat, flags, ctx.ws, d_strong.contiguous(), d_weak.contiguous(), weak,
                                 n_class=module.nclass, seed=seed, step=step, model_id=module.model_id)
@@ -90,6 +92,8 @@ class CRNN(nn.Module):
         params = list(self.parameters())
         dev = params[0].device
         n_total = sum(p.numel() for p in params)
+        if self._slabs_current(params, dev, n_total):
+            return                                  # .cuda() / .to() / .float() that changed nothing: addresses stay stable
         flat = torch.empty(n_total, device=dev, dtype=torch.float32)
         slices = []
         off = 0
@@ -113,6 +117,27 @@ class CRNN(nn.Module):
                     getattr(m, name).data = view
         self._bn_flat = bn
         self._ws_pool = {}
+
+    def _slabs_current(self, params, dev, n_total):
+        """True when every parameter and BN statistic is still the fp32 view into the current slabs that _flatten
+        made (captured CUDA graphs and the engines hold these addresses; main.py:316 re-applies .cuda() every epoch)."""
+        flat, bn = self._flat, self._bn_flat
+        if flat is None or bn is None or flat.device != dev or flat.numel() != n_total or bn.device != dev:
+            return False
+        if len(params) != len(getattr(self, "_param_list", ())):
+            return False
+        base, off = flat.data_ptr(), 0
+        for p, q in zip(params, self._param_list):
+            if p is not q or p.dtype != torch.float32 or p.data_ptr() != base + 4 * off or not p.is_contiguous():
+                return False
+            off += p.numel()
+        for i in range(3):
+            m = getattr(self.cnn.cnn, "batchnorm%d" % i)
+            for j, name in enumerate(("running_mean", "running_var")):
+                t = getattr(m, name)
+                if t.dtype != torch.float32 or t.data_ptr() != bn.data_ptr() + 4 * (2 * i + j) * 64:
+                    return False
+        return True
 
     def _apply(self, fn, recurse=True):
         out = super(CRNN, self)._apply(fn, recurse)

@@ -306,9 +306,6 @@ def test_pipelined_features_match_plain_steps(pkg, cuda_device, use_graph):
         assert int((d > 1e-4).sum()) <= 0.005 * d.numel()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("DCASE_EXPERIMENTAL", "0") != "1",
-                    reason="added after round 1's GPU budget was spent; the same comparison against the oracle "
-                           "(test_train_three_steps_match_oracle) is green -- set DCASE_EXPERIMENTAL=1 to run this one")
 def test_train_three_steps_match_reference_train_fixture(pkg, cuda_device):
     """main.train on the inputs of tests/golden/train_reference.npz against what the reference's OWN main.train left
     in the student / teacher parameters (the fixture is written by tests/golden/make_golden.py from the unmodified

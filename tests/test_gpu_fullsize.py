@@ -1,0 +1,258 @@
+"""TRAINING parity at the BASELINE configuration (B = 24 clips x 864 frames, dropout 0.5) -- VERDICT r1 "what's weak" 1.
+
+At this size the kernels take different code paths than in the small tests: multi-wave tile schedules, multi-CTA
+BatchNorm reductions over 1.3 M pixels, split-K weight gradients, the teacher / student two-stream overlap and the CUDA
+graph replay of ``step_from_waveforms``.  Dropout masks and teacher noise are the device's own Philox streams, injected
+into the plain-torch oracle (``tests/helpers.oracle_masks``, ``oracle.philox.teacher_noise``).  Follows
+``baseline/main.py:84-157`` (+ ``DataLoad.py:274-287`` / ``utils/utils.py:397-412`` for the features).
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import crnn as ocrnn
+from oracle import mel as omel
+from oracle import philox
+from oracle import train_step as otrain
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+B, T = 24, 864
+POSTERIOR_TOL = 1e-3            # north star: frame posteriors within 1e-3 abs of the reference path
+FLAGS_TRAIN = 3
+
+
+@pytest.fixture(scope="module")
+def K(cuda_device):
+    from dcase2019_task4_b200 import kernels
+    return kernels
+
+
+def _load(model, p):
+    with torch.no_grad():
+        for k, v in model.named_parameters():
+            v.copy_(p[k].to(v.device))
+
+
+def test_train_forward_and_all_gradients_at_baseline_size(K, cuda_device):
+    """Train-mode forward (dropout ON, batch statistics) and all 38 gradients at B = 24 x T = 864 vs the oracle."""
+    dev = cuda_device
+    To = T // 8
+    seed, step = 0x5EED0000BEEF, 11
+    p = ocrnn.init_params(seed=6)
+    buf = ocrnn.init_buffers()
+    buf_ref = copy.deepcopy(buf)
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(B, 1, T, 64, generator=g) * 1.2 + 0.1
+    strong_t = torch.rand(B, To, 10, generator=g)
+    weak_t = torch.rand(B, 10, generator=g)
+    target = (torch.rand(B, To, 10, generator=g) < 0.2).float()
+    target[6:18] = -1                                           # the unlabeled stream (utils.py:82-85)
+    wm, sm = slice(0, 6), slice(18, 24)                          # main.py:240-247 at batch 24
+    masks = H.oracle_masks(B, T, seed, step, model_id=0)
+    sp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    s_ref, w_ref = ocrnn.crnn_forward(x, sp, buf_ref, training=True, masks=masks)
+    loss, _ = otrain.mean_teacher_losses(s_ref, w_ref, strong_t, weak_t, target, wm, sm, 1.3)
+    gref = dict(zip(sp.keys(), torch.autograd.grad(loss, list(sp.values()))))
+
+    ws = K.new_workspace(B, T, 10, dev)
+    pf = H.flat_params(p).to(dev)
+    bn = H.bn_running_flat(buf).to(dev)
+    xd = x.to(dev)
+    s, w = K.crnn_forward(xd, pf, bn, FLAGS_TRAIN, ws, seed=seed, step=step)
+    es, ew = H.maxerr(s.cpu(), s_ref.detach()), H.maxerr(w.cpu(), w_ref.detach())
+    print(f"B=24 T=864 train (dropout on): strong Linf {es:.3e} weak Linf {ew:.3e}")
+    assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
+    ebn = H.maxerr(bn.cpu(), H.bn_running_flat(buf_ref))
+    print(f"running statistics err {ebn:.3e}")
+    assert ebn <= 1e-3
+    _, ds, dw = K.mt_loss(s, w, strong_t.to(dev), weak_t.to(dev), target.to(dev), wm, sm, 1.3)
+    got = H.unflat_params(K.crnn_backward(xd, pf, FLAGS_TRAIN, ws, ds, dw, w, seed=seed, step=step).cpu())
+    worst = 0.0
+    for k, gr in gref.items():
+        scale = float(gr.abs().max())
+        err = H.maxerr(got[k], gr)
+        if ".conv" in k and k.endswith("bias"):
+            assert err <= 1e-6, k                                # exact zeros behind BatchNorm
+            continue
+        rel = err / max(scale, 1e-12)
+        print(f"{k:40s} max|g| {scale:.3e} err {err:.3e} rel {rel:.2e}")
+        worst = max(worst, rel)
+        assert rel <= 1e-2, k                                    # reduced-precision tensor-core operands
+    print(f"worst relative gradient error {worst:.2e}")
+
+
+def test_three_graph_steps_from_waveforms_match_oracle(cuda_device):
+    """Three full ``step_from_waveforms`` iterations (CUDA-graph replay; waveform -> log-mel -> noise / dB / z-score ->
+    teacher + student forward -> losses -> backward -> Adam -> EMA) at B = 24 x 441,000 samples against
+    ``oracle.train_step.train_batch`` fed by ``oracle.mel``: per-step posteriors, meters, BatchNorm running statistics,
+    Adam moments, student and teacher parameters."""
+    import dcase2019_task4_b200.config as cfg
+    from dcase2019_task4_b200 import main as bmain
+    from dcase2019_task4_b200 import synth
+    from dcase2019_task4_b200.models.CRNN import CRNN
+    dev = cuda_device
+    L, N = 441000, 3
+    assert omel.n_frames_for(L) == T
+    waves, _ = synth.make_clips(N * B, seed=77, n_samples=L)
+    waves = waves.reshape(N, B, L)
+    g = torch.Generator().manual_seed(31)
+    tgt = (torch.rand(N, B, T // 8, 10, generator=g) < 0.2).float()
+    tgt[:, 6:18] = -1
+    wm, sm = slice(0, 6), slice(18, 24)
+    mean = np.full(64, -32.0) + np.linspace(-6, 6, 64)
+    std = np.full(64, 11.0) + np.linspace(0, 4, 64)
+    ps, pt = ocrnn.init_params(seed=51), ocrnn.init_params(seed=52)
+    ps0 = {k: v.clone() for k, v in ps.items()}
+    student, teacher = CRNN(**cfg.crnn_kwargs), CRNN(**cfg.crnn_kwargs)
+    assert cfg.crnn_kwargs["dropout"] == 0.5
+    _load(student, ps)
+    _load(teacher, pt)
+    for q in teacher.parameters():
+        q.detach_()
+    student, teacher = student.train().cuda(), teacher.train().cuda()
+    seed = 0x0DDBA11C0FFEE
+    student._rng_seed, student._rng_step = seed, 40
+    opt = torch.optim.Adam(student.parameters(), lr=0.001, betas=(0.9, 0.999))
+    eng = bmain.MeanTeacherEngine(student, opt, teacher, wm, sm, B, T, use_graph=True)
+    wd = torch.from_numpy(waves).to(dev)
+    td = tgt.to(dev)
+    md = torch.from_numpy(mean.astype(np.float32)).to(dev)
+    sd = torch.from_numpy(std.astype(np.float32)).to(dev)
+    steps_per_epoch = 0          # ramp-up length 0: the consistency weight is at its maximum (2.0) from the first step
+    for i in range(N):
+        cw = otrain.consistency_weight(i, steps_per_epoch)
+        eng.step_from_waveforms(wd[i], td[i], md, sd, cw, i + 1, check=False)      # no host sync between the steps
+    torch.cuda.synchronize()
+    assert len(eng._graphs) == N and eng.graph_launches > 0
+    last_strong, last_weak = eng.strong_s.cpu(), eng.weak_s.cpu()
+    last_meters = eng.read_meters()
+
+    sbuf, tbuf = ocrnn.init_buffers(), ocrnn.init_buffers()
+    adam = otrain.new_adam_state(ps)
+    fb = omel.mel_filterbank()
+    for i in range(N):
+        step = 40 + i
+        mels = np.stack([omel.calculate_mel_spec(w.astype(np.float64), fb) for w in waves[i]])
+        noise = philox.teacher_noise(B * T, seed, step).reshape(B, T, 64).astype(np.float64)
+        feats = [omel.transform_chain(mels[b], mean, std, noise=noise[b], frames=T) for b in range(B)]
+        x = torch.from_numpy(np.stack([f[0] for f in feats]))          # [B, 1, T, 64]
+        xe = torch.from_numpy(np.stack([f[1] for f in feats]))
+        meters, _ = otrain.train_batch(ps, sbuf, adam, x, tgt[i], i, steps_per_epoch, teacher_p=pt, teacher_buf=tbuf,
+                                       x_ema=xe, weak_mask=wm, strong_mask=sm,
+                                       masks_student=H.oracle_masks(B, T, seed, step, 0),
+                                       masks_teacher=H.oracle_masks(B, T, seed, step, 1))
+    es, ew = H.maxerr(last_strong, meters["strong"]), H.maxerr(last_weak, meters["weak"])
+    print(f"step 3 posteriors (student, train mode): strong Linf {es:.3e} weak Linf {ew:.3e}")
+    # after two optimizer steps the two runs no longer hold identical weights (Adam's +-lr steps on near-zero
+    # gradients, see below), so the third step's posteriors carry that drift on top of the kernel error
+    assert es <= 3e-3 and ew <= 3e-3
+    for name in ("Loss", "Strong loss", "weak_class_loss", "Consistency strong", "Consistency weak", "Strong EMA loss",
+                 "Weak EMA loss"):
+        assert abs(last_meters[name] - meters[name]) <= 2e-3 * max(1.0, abs(meters[name])), (name, last_meters, meters)
+    got_s = {k: v.detach().cpu() for k, v in student.named_parameters()}
+    got_t = {k: v.detach().cpu() for k, v in teacher.named_parameters()}
+    n_tot = n_bad = 0
+    for k in ps:
+        if ".conv" in k and k.endswith("bias"):
+            assert torch.equal(got_s[k], ps0[k])                  # exact zero gradient: conv biases stay put
+            continue
+        for got, ref in ((got_s[k], ps[k]), (got_t[k], pt[k])):
+            d = (got.double() - ref.double()).abs()
+            assert float(d.max()) <= 2 * N * 1e-3 + 1e-6, k       # nobody travels further than N Adam steps apart
+            n_tot += d.numel()
+            n_bad += int((d > 1e-4).sum())
+    print(f"parameters off by more than 1e-4 after {N} steps: {n_bad} of {n_tot}")
+    assert n_bad <= 0.005 * n_tot
+    for i in range(3):
+        bn = getattr(student.cnn.cnn, f"batchnorm{i}")
+        assert H.maxerr(bn.running_var.cpu(), sbuf[f"cnn.cnn.batchnorm{i}.running_var"]) <= 1e-3
+        rm = bn.running_mean.cpu() - got_s[f"cnn.cnn.conv{i}.bias"]
+        rm_ref = sbuf[f"cnn.cnn.batchnorm{i}.running_mean"] - ps[f"cnn.cnn.conv{i}.bias"]
+        err = (rm.double() - rm_ref.double()).abs()
+        assert float((err <= 1.3e-3).double().mean()) >= 0.95 and float(err.max()) <= 4e-3, (i, float(err.max()))
+    st = opt.state_dict()["state"]
+    assert float(st[0]["step"]) == float(N)
+    k0 = "cnn.cnn.conv1.weight"
+    idx = list(ps.keys()).index(k0)
+    m_err = H.maxerr(st[idx]["exp_avg"].cpu(), adam["exp_avg"][k0])
+    print(f"Adam exp_avg[{k0}] err {m_err:.3e} (max {float(adam['exp_avg'][k0].abs().max()):.3e})")
+    assert m_err <= 2e-2 * float(adam["exp_avg"][k0].abs().max())
+
+
+def test_graph_steps_without_host_sync_match_eager(cuda_device):
+    """the per-step scalars (Philox seed / step, consistency weight, EMA alpha, lr, Adam bias corrections) reach
+    the device through a ring of pinned buffers; the host may run many replays ahead of the GPU.  Twelve replayed
+    steps with NO host synchronisation in between must equal twelve eager steps (which pass the scalars by value)."""
+    import dcase2019_task4_b200.config as cfg
+    from dcase2019_task4_b200 import main as bmain
+    from dcase2019_task4_b200 import synth
+    from dcase2019_task4_b200.models.CRNN import CRNN
+    dev = cuda_device
+    Bs, Ts, L, N = 8, 64, 511 * 64, 12
+    waves, _ = synth.make_clips(2 * Bs, seed=9, n_samples=L)
+    waves = torch.from_numpy(waves.reshape(2, Bs, L)).to(dev)
+    tgt = (torch.rand(2, Bs, Ts // 8, 10, generator=torch.Generator().manual_seed(3)) < 0.2).float()
+    tgt[:, 2:6] = -1
+    tgt = tgt.to(dev)
+    mean = torch.full((64,), -30.0, device=dev)
+    std = torch.full((64,), 12.0, device=dev)
+    ps, pt = ocrnn.init_params(seed=61), ocrnn.init_params(seed=62)
+    out = []
+    for use_graph in (False, True):
+        student, teacher = CRNN(**cfg.crnn_kwargs), CRNN(**cfg.crnn_kwargs)
+        _load(student, ps)
+        _load(teacher, pt)
+        for q in teacher.parameters():
+            q.detach_()
+        student, teacher = student.train().cuda(), teacher.train().cuda()
+        student._rng_seed, student._rng_step = 424242, 0
+        opt = torch.optim.Adam(student.parameters(), lr=0.001, betas=(0.9, 0.999))
+        eng = bmain.MeanTeacherEngine(student, opt, teacher, slice(2), slice(6, 8), Bs, Ts, use_graph=use_graph)
+        # steps 0 / 1 capture the two buffer sets; from step 2 on the host only replays and runs ahead of the GPU
+        for i in range(N):
+            eng.step_from_waveforms(waves[i % 2], tgt[i % 2], mean, std, 0.1 * i, i + 1, check=False)
+        torch.cuda.synchronize()
+        out.append((student.flat_parameters().detach().cpu().clone(), teacher.flat_parameters().detach().cpu().clone(),
+                    eng.read_meters()))
+    (s0, t0, m0), (s1, t1, m1) = out
+    # a stale Philox step or a stale EMA alpha / bias correction would move EVERY parameter; atomics-order noise does not
+    for a, b in ((s0, s1), (t0, t1)):
+        d = (a.double() - b.double()).abs()
+        assert int((d > 1e-4).sum()) <= 0.01 * d.numel(), float(d.max())
+    assert abs(m0["Consistency weight"] - m1["Consistency weight"]) <= 1e-6
+    assert abs(m0["Loss"] - m1["Loss"]) <= 2e-3 * max(1.0, abs(m0["Loss"]))
+
+
+def test_slabs_survive_repeated_cuda_calls_with_live_graphs(cuda_device):
+    """baseline/main.py:316 calls ``to_cuda_if_available([crnn, crnn_ema])`` every epoch.  The slabs must keep
+    their addresses (captured graphs hold them) and a replay after ``.cuda()`` must still train the live parameters."""
+    import dcase2019_task4_b200.config as cfg
+    from dcase2019_task4_b200 import main as bmain
+    from dcase2019_task4_b200 import synth
+    from dcase2019_task4_b200.models.CRNN import CRNN
+    dev = cuda_device
+    Bs, Ts, L = 8, 64, 511 * 64
+    waves, _ = synth.make_clips(Bs, seed=19, n_samples=L)
+    waves = torch.from_numpy(waves).to(dev)
+    tgt = (torch.rand(Bs, Ts // 8, 10, generator=torch.Generator().manual_seed(5)) < 0.2).float().to(dev)
+    mean = torch.full((64,), -30.0, device=dev)
+    std = torch.full((64,), 12.0, device=dev)
+    student, teacher = CRNN(**cfg.crnn_kwargs).train().cuda(), CRNN(**cfg.crnn_kwargs).train().cuda()
+    for q in teacher.parameters():
+        q.detach_()
+    opt = torch.optim.Adam(student.parameters(), lr=0.001, betas=(0.9, 0.999))
+    eng = bmain.MeanTeacherEngine(student, opt, teacher, slice(2), slice(6, 8), Bs, Ts, use_graph=True)
+    eng.step_from_waveforms(waves, tgt, mean, std, 0.5, 1)
+    ptr0 = student.flat_parameters().data_ptr()
+    student, teacher = student.cuda(), teacher.cuda()
+    assert student.flat_parameters().data_ptr() == ptr0
+    before = student.flat_parameters().clone()
+    eng.step_from_waveforms(waves, tgt, mean, std, 0.5, 2)
+    torch.cuda.synchronize()
+    assert len(eng._graphs) == 1
+    assert not torch.equal(before, student.flat_parameters())
+    assert student.cnn.cnn.conv1.weight.data_ptr() >= ptr0

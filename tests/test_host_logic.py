@@ -448,19 +448,53 @@ def test_properties_of_encoder_regions_and_sampler():
             assert not (seen & set(int(v) for v in batch))
             seen |= set(int(v) for v in batch)
 
-    @settings(max_examples=30, deadline=None)
-    @given(st.integers(2, 4), st.integers(0, 100))
-    def shards_partition(world, seed):
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(2, 4), st.integers(0, 100), st.integers(1, 60), st.integers(1, 130), st.integers(1, 7),
+           st.integers(1, 17))
+    def shards_partition(world, seed, n0, n1, b0, b1):
+        # stream lengths NOT divisible by the world size (101 clips, batch 17, world 2 gave rank 0 an extra
+        # batch and a hung all-reduce): every rank must yield exactly len(sampler) batches, shards disjoint
         class Src:
-            cluster_indices = [range(0, 24), range(24, 72)]
-        drawn = []
+            cluster_indices = [range(0, n0), range(n0, n0 + n1)]
+        drawn, counts = [], []
         for rank in range(world):
-            s = DataLoad.MultiStreamBatchSampler(Src(), [2, 3], shuffle=True, rank=rank, world_size=world, seed=seed)
-            drawn.append([int(v) for batch in s for v in batch])
-            assert len(s) == min(24 // world // 2, 48 // world // 3)
+            s = DataLoad.MultiStreamBatchSampler(Src(), [b0, b1], shuffle=True, rank=rank, world_size=world, seed=seed)
+            batches = list(s)
+            counts.append(len(batches))
+            assert len(batches) == len(s) == min(n0 // world // b0, n1 // world // b1)
+            drawn.append([int(v) for batch in batches for v in batch])
+        assert len(set(counts)) == 1
         flat = [v for d in drawn for v in d]
         assert len(flat) == len(set(flat))                      # disjoint across ranks
 
+    def seedless_shards_raise():
+        class Src:
+            cluster_indices = [range(0, 101)]
+        with pytest.raises(ValueError):
+            DataLoad.MultiStreamBatchSampler(Src(), [17], rank=0, world_size=2)
+        got = [len(list(DataLoad.MultiStreamBatchSampler(Src(), [17], rank=r, world_size=2, seed=3))) for r in (0, 1)]
+        assert got == [2, 2]
+
+    seedless_shards_raise()
     regions_roundtrip()
     sampler_batches()
     shards_partition()
+
+
+def test_flat_slabs_keep_their_address_when_apply_changes_nothing():
+    """the reference re-applies ``.cuda()`` to both models every epoch (main.py:316); captured CUDA graphs and
+    the engines hold the slab addresses, so a no-op ``_apply`` must not re-allocate them."""
+    m = CRNN(**cfg.crnn_kwargs)
+    p0, b0 = m.flat_parameters().data_ptr(), m.flat_bn_running().data_ptr()
+    m.float()
+    m.to("cpu")
+    m.train()
+    assert m.flat_parameters().data_ptr() == p0 and m.flat_bn_running().data_ptr() == b0
+    assert m.cnn.cnn.conv0.weight.data_ptr() == p0
+    m.double()                                     # a real change re-flattens (fp32 slab, parameters re-viewed)
+    m.float()
+    assert m.flat_parameters().dtype == torch.float32
+    off = 0
+    for p in m.parameters():
+        assert p.data_ptr() == m.flat_parameters().data_ptr() + 4 * off
+        off += p.numel()
