@@ -76,7 +76,6 @@ SIGNATURES = {
     "dcase_p2p_handle_bytes": (c_i, []),
     "dcase_p2p_create": (c_i, [c_p, c_i, c_i, c_sz, ctypes.POINTER(c_p), c_p]),
     "dcase_p2p_connect": (c_i, [c_p, c_p]),
-    "dcase_p2p_connect_local": (c_i, [ctypes.POINTER(c_p), c_i]),
     "dcase_p2p_grads": (c_p, [c_p]),
     "dcase_p2p_begin_step": (c_i, [c_p, c_p]),
     "dcase_p2p_adam_ema_step": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_p]),

@@ -187,24 +187,6 @@ int dcase_p2p_connect(dcase_p2p* h, const void* all_handles) {
     return DCASE_OK;
 }
 
-// Test hook: wire `world` handles that live in ONE process (one GPU, one rank per stream) to each other with plain
-// device pointers -- CUDA IPC cannot map a process's own allocation -- so the flag protocol and the rank-ordered sum can be
-// exercised on a single GPU (tests/test_gpu_crnn.py).
-int dcase_p2p_connect_local(dcase_p2p* const* all, int world) {
-    DCASE_REQUIRE(all && world >= 1 && world <= kMaxWorld, "bad argument");
-    float* pg[kMaxWorld];
-    uint32_t* ps[kMaxWorld];
-    for (int r = 0; r < world; ++r) {
-        DCASE_REQUIRE(all[r] && all[r]->world == world && all[r]->rank == r, "handles must be rank-ordered and of one world");
-        pg[r] = all[r]->grads; ps[r] = all[r]->sync;
-    }
-    for (int r = 0; r < world; ++r) {
-        DCASE_CUDA_CHECK(cudaMemcpy(all[r]->d_peer_grads, pg, world * sizeof(float*), cudaMemcpyHostToDevice));
-        DCASE_CUDA_CHECK(cudaMemcpy(all[r]->d_peer_sync, ps, world * sizeof(uint32_t*), cudaMemcpyHostToDevice));
-    }
-    return DCASE_OK;
-}
-
 float* dcase_p2p_grads(dcase_p2p* h) { return h ? h->grads : nullptr; }
 
 int dcase_p2p_begin_step(dcase_p2p* h, void* stream) {

@@ -20,10 +20,11 @@ class _CrnnFunction(torch.autograd.Function):
     """dcase_crnn_forward / dcase_crnn_backward as one autograd node over all parameters."""
 
     @staticmethod
-    def forward(ctx, module, x, flags, seed, step, *params):
+    def forward(ctx, module, x, flags, seed, step, keep, *params):
         B, T = x.shape[0], x.shape[-2]
-        # needs_input_grad stays True under torch.no_grad(); only a grad-enabled TRAINING forward keeps its workspace
-        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad[5:]) and bool(flags & K.FLAG_BN_BATCH_STATS)
+        # ``keep``: grad mode of the CALLER (inside Function.forward grad mode is always off, and needs_input_grad stays
+        # True under torch.no_grad()); only a grad-enabled TRAINING forward keeps its workspace for the backward
+        need_grad = bool(keep) and any(ctx.needs_input_grad[6:]) and bool(flags & K.FLAG_BN_BATCH_STATS)
         ws = module._take_workspace(B, T, x.device, keep=need_grad)
         strong, weak = K.crnn_forward(x, module._flat, module._bn_flat, flags, ws, n_class=module.nclass,
                                       seed=seed, step=step, model_id=module.model_id)
@@ -48,7 +49,7 @@ class _CrnnFunction(torch.autograd.Function):
         out = []
         for p, (off, n) in zip(module._param_list, module._param_slices):
             out.append(grads[off:off + n].view(p.shape) if p.requires_grad else None)
-        return (None, None, None, None, None) + tuple(out)
+        return (None, None, None, None, None, None) + tuple(out)
 
 
 class CRNN(nn.Module):
@@ -94,29 +95,39 @@ class CRNN(nn.Module):
         n_total = sum(p.numel() for p in params)
         if self._slabs_current(params, dev, n_total):
             return                                  # .cuda() / .to() / .float() that changed nothing: addresses stay stable
-        flat = torch.empty(n_total, device=dev, dtype=torch.float32)
+        # nn.GRU._apply re-packs its weights into a buffer of its own on every .cuda() (flatten_parameters), so a no-op
+        # .cuda() still lands here: copy back INTO the existing slabs so their addresses (held by captured CUDA graphs,
+        # engines and the optimizer state views) stay stable
+        reuse = self._flat is not None and self._flat.device == dev and self._flat.numel() == n_total
+        flat = self._flat if reuse else torch.empty(n_total, device=dev, dtype=torch.float32)
         slices = []
         off = 0
         with torch.no_grad():
             for p in params:
                 n = p.numel()
-                flat[off:off + n].copy_(p.detach().reshape(-1))
-                p.data = flat[off:off + n].view(p.shape)
+                view = flat[off:off + n].view(p.shape)
+                if not (p.dtype == torch.float32 and p.data_ptr() == view.data_ptr() and p.is_contiguous()):
+                    view.copy_(p.detach())
+                    p.data = view
                 slices.append((off, n))
                 off += n
         self._flat = flat
         self._param_list = params
         self._param_slices = slices
-        bn = torch.empty(3 * 2 * 64, device=dev, dtype=torch.float32)
+        reuse_bn = self._bn_flat is not None and self._bn_flat.device == dev
+        bn = self._bn_flat if reuse_bn else torch.empty(3 * 2 * 64, device=dev, dtype=torch.float32)
         with torch.no_grad():
             for i in range(3):
                 m = getattr(self.cnn.cnn, "batchnorm%d" % i)
                 for j, name in enumerate(("running_mean", "running_var")):
                     view = bn[(2 * i + j) * 64:(2 * i + j + 1) * 64]
-                    view.copy_(getattr(m, name))
-                    getattr(m, name).data = view
+                    t = getattr(m, name)
+                    if not (t.dtype == torch.float32 and t.data_ptr() == view.data_ptr()):
+                        view.copy_(t)
+                        t.data = view
         self._bn_flat = bn
-        self._ws_pool = {}
+        if not (reuse and reuse_bn):
+            self._ws_pool = {}
 
     def _slabs_current(self, params, dev, n_total):
         """True when every parameter and BN statistic is still the fp32 view into the current slabs that _flatten
@@ -231,5 +242,5 @@ class CRNN(nn.Module):
         if self.training:
             self._nbt_pending += 1
         x = x.contiguous().float()
-        strong, weak = _CrnnFunction.apply(self, x, flags, seed, step, *self._param_list)
+        strong, weak = _CrnnFunction.apply(self, x, flags, seed, step, torch.is_grad_enabled(), *self._param_list)
         return strong, weak

@@ -207,8 +207,6 @@ typedef struct dcase_p2p dcase_p2p;
 int dcase_p2p_handle_bytes(void);
 int dcase_p2p_create(dcase_ctx* ctx, int world, int rank, size_t n_floats, dcase_p2p** out, void* handles_out_host);
 int dcase_p2p_connect(dcase_p2p* h, const void* all_handles_host);
-/* test hook: `world` handles created in ONE process (one GPU, one rank per stream) wired with plain device pointers */
-int dcase_p2p_connect_local(dcase_p2p* const* all, int world);
 float* dcase_p2p_grads(dcase_p2p* h);
 int dcase_p2p_begin_step(dcase_p2p* h, void* stream);
 int dcase_p2p_adam_ema_step(dcase_ctx* ctx, dcase_p2p* h, float* p, float* m, float* v, float* p_ema, float lr,

@@ -76,7 +76,9 @@ def test_train_forward_and_all_gradients_at_baseline_size(K, cuda_device):
         scale = float(gr.abs().max())
         err = H.maxerr(got[k], gr)
         if ".conv" in k and k.endswith("bias"):
-            assert err <= 1e-6, k                                # exact zeros behind BatchNorm
+            # behind BatchNorm the true gradient is 0: torch returns rounding noise (here up to ~3e-6 over 1.3 M pixels),
+            # the kernels return exact zeros
+            assert float(got[k].abs().max()) == 0.0 and scale <= 1e-4, k
             continue
         rel = err / max(scale, 1e-12)
         print(f"{k:40s} max|g| {scale:.3e} err {err:.3e} rel {rel:.2e}")
@@ -169,7 +171,10 @@ def test_three_graph_steps_from_waveforms_match_oracle(cuda_device):
     assert n_bad <= 0.005 * n_tot
     for i in range(3):
         bn = getattr(student.cnn.cnn, f"batchnorm{i}")
-        assert H.maxerr(bn.running_var.cpu(), sbuf[f"cnn.cnn.batchnorm{i}.running_var"]) <= 1e-3
+        rv_ref = sbuf[f"cnn.cnn.batchnorm{i}.running_var"]
+        rv_err = ((bn.running_var.cpu().double() - rv_ref.double()).abs() / rv_ref.double().clamp(min=1.0)).max()
+        print(f"batchnorm{i} running_var relative err {float(rv_err):.3e}")
+        assert float(rv_err) <= 3e-3        # two Adam steps of parameter drift on top of the tf32 conv (observed 5e-4)
         rm = bn.running_mean.cpu() - got_s[f"cnn.cnn.conv{i}.bias"]
         rm_ref = sbuf[f"cnn.cnn.batchnorm{i}.running_mean"] - ps[f"cnn.cnn.conv{i}.bias"]
         err = (rm.double() - rm_ref.double()).abs()
