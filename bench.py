@@ -243,9 +243,17 @@ def run_b200(args, rank, local_rank, world):
     optimizer = torch.optim.Adam(filter(lambda p: p.requires_grad, crnn.parameters()), lr=0.001, betas=(0.9, 0.999))
     weak_mask = slice(BATCH_SIZES[0])
     strong_mask = slice(BATCH_SIZES[0] + BATCH_SIZES[1], B_PER_GPU)
-    # data-parallel steps launch eagerly unless DCASE_DP_GRAPH=1 opts into capturing the NCCL all-reduce (unverified)
-    use_graph = (world == 1 or os.environ.get("DCASE_DP_GRAPH", "0") == "1") and os.environ.get("DCASE_NO_GRAPH", "0") != "1"
-    engine = MeanTeacherEngine(crnn, optimizer, crnn_ema, weak_mask, strong_mask, B_PER_GPU, FRAMES, use_graph=use_graph)
+    # N > 1: gradient exchange fused with Adam + EMA over NVLink peer memory inside the step's CUDA graph (csrc/p2p.cu);
+    # DCASE_DP_NCCL=1 selects the NCCL all-reduce + separate optimizer kernel, launched eagerly
+    engine = MeanTeacherEngine(crnn, optimizer, crnn_ema, weak_mask, strong_mask, B_PER_GPU, FRAMES)
+    use_graph = engine.use_graph
+    if world == 1:
+        dp_mode = "dp1"
+    elif engine.p2p is not None:
+        dp_mode = "dp%d: per-stream shards, gradient exchange + Adam + EMA as one kernel over NVLink peer memory%s" % (
+            world, " inside the step's CUDA graph" if use_graph else "")
+    else:
+        dp_mode = "dp%d: per-stream shards, NCCL all-reduce of the flat gradient slab, eager launches" % world
     rampup_length = STEPS_PER_EPOCH * cfg.n_epoch // 2
 
     state = {"gs": 0}
@@ -403,7 +411,7 @@ def run_b200(args, rank, local_rank, world):
                 "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
                 "config": {"workload": workload_name(), "global_batch": world * B_PER_GPU, "frames": FRAMES,
-                           "parallelism": "dp%d" % world,
+                           "parallelism": dp_mode,
                            "l2": "inputs larger than L2: rotating pool of 6 waveform batches (254 MB) per GPU, "
                                  "plus ~400 MB of activations rewritten every step"},
                 "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,

@@ -125,10 +125,12 @@ class MeanTeacherEngine(object):
         self.ws_t = K.new_workspace(B, frames, NC, dev) if ema_model is not None else None
         n = model.flat_parameters().numel()
         self.grads = torch.zeros(n, **f32)
-        # opt-in (DCASE_DP_P2P=1, unverified on hardware): gradient exchange fused with Adam + EMA over NVLink peer
-        # memory instead of NCCL all-reduce + optimizer kernel; the backward then writes into the library-owned slab
+        # data parallel: the gradient exchange is FUSED with Adam + EMA into one kernel over NVLink peer memory
+        # (csrc/p2p.cu; the backward writes into the library-owned, IPC-exported slab).  DCASE_DP_NCCL=1 selects the
+        # plain NCCL all-reduce + optimizer kernel instead (eager launches only: capturing NCCL into the step's graph
+        # hung on hardware in rounds 1 and 2 and is not offered)
         self.p2p = None
-        if self.world > 1 and os.environ.get("DCASE_DP_P2P", "0") == "1":
+        if self.world > 1 and os.environ.get("DCASE_DP_NCCL", "0") != "1":
             self.p2p = dp.P2PGradExchange(n, process_group)
             self.grads = self.p2p.grads
         self._bind_adam_state(n)
@@ -137,13 +139,12 @@ class MeanTeacherEngine(object):
         # CUDA-graph replay of step_from_waveforms (single GPU): the ~60 launches of one iteration are captured once
         # per (waveform, target, scaler) buffer set; everything that changes from step to step (Philox seed / step,
         # consistency weight, EMA alpha, lr, Adam bias corrections) lives in a 40-byte device struct the kernels read.
-        self.use_graph = (self.world == 1 and os.environ.get("DCASE_NO_GRAPH", "0") != "1") if use_graph is None else bool(use_graph)
-        if self.use_graph and self.world > 1 and os.environ.get("DCASE_DP_GRAPH", "0") != "1":
-            # capturing the NCCL all-reduce with the rest of the iteration hung on the 2-GPU box (round 1 experiment,
-            # default "global" capture mode: the NCCL watchdog thread's event queries are illegal during a global
-            # capture), so data-parallel steps launch eagerly.  DCASE_DP_GRAPH=1 opts into the thread-local capture
-            # below -- UNVERIFIED on hardware, run it under a short timeout
-            raise NotImplementedError("graph replay is wired for single-GPU steps (the NCCL all-reduce runs eagerly)")
+        graph_ok = self.world == 1 or self.p2p is not None
+        self.use_graph = (graph_ok and os.environ.get("DCASE_NO_GRAPH", "0") != "1") if use_graph is None else bool(use_graph)
+        if self.use_graph and not graph_ok:
+            raise NotImplementedError("graph replay under data parallelism needs the fused p2p exchange (the NCCL "
+                                      "all-reduce is launched eagerly)")
+        K.ctx(dev)                                 # the library context must exist before any stream capture starts
         self._graphs = {}
         self.graph_launches = 0            # kernels launched through graph replays (bench.py's gpu_launches)
         assert K.lib().dcase_sizeof_step_scalars() == _SCALARS.itemsize
@@ -284,6 +285,7 @@ class MeanTeacherEngine(object):
             if entry is None:
                 graph = torch.cuda.CUDAGraph()
                 l0 = K.launch_count()
+                # thread-local capture under DP: NCCL's watchdog thread queries events of its own while we capture
                 with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
                     scp = self._sc_dev.data_ptr()
                     amp = K.logmel_fwd(wave)
@@ -292,12 +294,17 @@ class MeanTeacherEngine(object):
                                                    out_clean=self._x, out_noisy=self._x_ema)
                     else:
                         x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None
+                    if self.p2p is not None:               # nobody still reads this rank's slab of the previous step
+                        self.p2p.begin_step()
                     K.mt_fwd_bwd(self._mt_args(x, x_ema, target, model.forward_flags(), 0, 0, 0.0, scp))
-                    if self.world > 1:                     # opt-in (DCASE_DP_GRAPH=1): the all-reduce as a graph node
-                        dp.allreduce_grads_(self.grads, self.pg)
-                    K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
-                                    ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
-                                    beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
+                    if self.p2p is not None:               # exchange + Adam + EMA as one kernel over NVLink peer memory
+                        self.p2p.adam_ema_step(model.flat_parameters(), self.m, self.v,
+                                               ema.flat_parameters() if ema is not None else None, 0, g["lr"],
+                                               g["betas"][0], g["betas"][1], g["eps"], 0.0, scalars=self._sc_dev)
+                    else:
+                        K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
+                                        ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
+                                        beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
                 entry = (graph, K.launch_count() - l0)
                 self._cache_put(self._graphs, key, entry)
             entry[0].replay()

@@ -13,7 +13,8 @@ run() {
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
 run test_eager 200 python -u -m pytest -q -m gpu -s --timeout 180 --timeout-method=thread tests/test_gpu_dp.py -k "bit_identical"
 run test_graph 200 python -u -m pytest -q -m gpu -s --timeout 180 --timeout-method=thread tests/test_gpu_dp.py -k "cuda_graph"
-run test_p2p 200 python -u -m pytest -q -m gpu -s --timeout 180 --timeout-method=thread tests/test_gpu_dp.py -k "p2p"
+run test_p2p 200 python -u -m pytest -q -m gpu -s --timeout 180 --timeout-method=thread tests/test_gpu_dp.py -k "p2p_exchange_and"
+run test_p2p_graph 200 python -u -m pytest -q -m gpu -s --timeout 180 --timeout-method=thread tests/test_gpu_dp.py -k "p2p_exchange_inside"
 run bench_eager 200 $TR bench.py --gpus 2 --steps 30 --warmup 6
 run bench_graph 200 env DCASE_DP_GRAPH=1 $TR bench.py --gpus 2 --steps 30 --warmup 6
 run bench_p2p 200 env DCASE_DP_P2P=1 $TR bench.py --gpus 2 --steps 30 --warmup 6
