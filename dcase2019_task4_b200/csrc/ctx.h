@@ -1,14 +1,12 @@
 // Internal definition of the opaque dcase_ctx handle.
 #pragma once
 #include <cuda_runtime.h>
-#include "fft2048.cuh"
 
 struct dcase_ctx {
     int device;
     int num_sms;
     // log-mel constant tables (device)
-    float* d_window;     // [2048] symmetric Hamming
-    cf32* d_twiddle;     // [2048] exp(-2 pi i m / 2048)
+    float2* d_window2;   // [1024] {w[2n], w[2n+1]} of the symmetric Hamming window
     float* d_mel_w;      // packed non-zero Slaney weights
     int* d_mel_work;     // [128][4] balanced work items of the mel projection
     int* d_mel_owner;    // [64][2]  slots of each band

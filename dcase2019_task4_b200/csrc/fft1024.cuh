@@ -33,13 +33,13 @@ __device__ __forceinline__ cpx cmake(float x, float y) {
     return r;
 }
 __device__ __forceinline__ float cre(cpx a) {
-    float x, y;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+    float x;
+    asm("{ .reg .b32 hi; mov.b64 {%0, hi}, %1; }" : "=f"(x) : "l"(a.v));
     return x;
 }
 __device__ __forceinline__ float cim(cpx a) {
-    float x, y;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+    float y;
+    asm("{ .reg .b32 lo; mov.b64 {lo, %0}, %1; }" : "=f"(y) : "l"(a.v));
     return y;
 }
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) {
@@ -200,7 +200,8 @@ __host__ __device__ __forceinline__ void stft_pass2(cpx* v, int lane, const cpx*
                        0.95694033573220886494f, 0.98078528040323044913f, 0.99518472667219688624f}
 
 // squared magnitudes (x 4) of X[k] and X[1024 - k] for k = lane + 32 p from Zk = Z[k] and Zm = Z[1024 - k]:
-// returns |A + T|^2 in `lo` and |A - T|^2 in `hi`; the caller takes sqrt and halves.  wl = W_2048^lane.
+// returns |A + T|^2 = |2 X[k]|^2 in `lo` and |A - T|^2 = |2 X[1024 - k]|^2 in `hi` (the kernel keeps the factor 2 and
+// halves the mel weights instead, which is exact).  wl = W_2048^lane.
 __host__ __device__ __forceinline__ void stft_post_pair(cpx zk, cpx zm, cpx wl, float c64, float s64, float& lo,
                                                         float& hi) {
     const cpx a = cfma_elem(zm, cmake(1.f, -1.f), zk);           // Zk + conj(Zm)

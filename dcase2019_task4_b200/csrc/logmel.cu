@@ -5,11 +5,18 @@
 //   baseline/DataLoad.py:274-287,192-207,210-259,302-321 + utils/Scaler.py:99-105
 //   (order: utils/utils.py:397-412 get_transforms)                            -> dcase_logmel_finish
 //
-// K1 layout: one CTA = 8 consecutive frames of one clip. The contiguous waveform span
-// (7*511 + 2048 samples, reflect-padded at the clip ends) is staged once in shared memory, so the
-// 4x frame overlap (2048/511) is served on-chip (HBM / L2 see each sample ~1.4x); 59 KB of shared memory per
-// CTA keep 3 CTAs (24 warps) resident per SM. Two real frames are
-// packed into one complex 2048-point Stockham FFT (radix 8,8,8,4) held in shared memory.
+// K1 layout (round 2): persistent CTAs of 8 warps; a tile = 8 consecutive frames of one clip, ONE WARP PER FRAME.
+//   * the tile's contiguous waveform span (7 * 511 + 2048 samples, reflect-padded at the clip ends) is staged once per
+//     tile with 16-byte global loads and stored DE-INTERLEAVED by sample parity (E[m] = x[2m], O[m] = x[2m+1]), so that
+//     the packing z[n] = x[2n] + i x[2n+1] of a real frame into a 1024-point complex FFT reads two stride-1 arrays
+//     (conflict-free) whatever the parity of the frame's offset (hop 511 is odd);
+//   * the warp runs the whole real FFT on its own (csrc/fft1024.cuh): two 32-point DFTs in registers with one
+//     32 x 32 transpose through the warp's private 8.4 KB of shared memory, the Hermitian split with the partner values
+//     fetched by warp shuffles, packed f32x2 additions -- no block barrier inside a frame;
+//   * magnitudes go to the warp's scratch, the sparse Slaney projection (1,983 non-zeros, weights in shared memory,
+//     staged once per CTA together with the interleaved window by two cp.async.bulk copies) runs as 4 balanced work
+//     items per lane, band owners add the partials and write the frame's 64 mel amplitudes as two 128-byte rows.
+// 108 KB of shared memory per CTA: two CTAs (16 warps) per SM; while one stages its next span the other computes.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -18,7 +25,7 @@
 #include "../../include/dcase_b200.h"
 #include "common.cuh"
 #include "ctx.h"
-#include "fft2048.cuh"
+#include "fft1024.cuh"
 
 namespace {
 
@@ -26,17 +33,28 @@ constexpr int kNfft = 2048;
 constexpr int kHop = 511;
 constexpr int kBins = 1025;
 constexpr int kMel = 64;
-constexpr int kFramesPerCta = 8;
-constexpr int kSpan = (kFramesPerCta - 1) * kHop + kNfft;  // 5625
-constexpr int kSpanPad = (kSpan + 15) / 16 * 16;
-constexpr int kMagPitch = 1032;
+constexpr int kFramesPerTile = 8;
+constexpr int kStftWarps = 8;
+constexpr int kSpan = (kFramesPerTile - 1) * kHop + kNfft;  // 5625 samples
+constexpr int kHalfSpan = 2816;                              // ceil(5625 / 2) = 2813, padded
+constexpr int kMelWPad = 1984;                               // 1,983 packed weights, padded to 16 bytes
+constexpr int kMelItems = 128;                               // work items of the mel projection (4 per lane)
 
 struct MelTables {
-    const float* window;
-    const cf32* twiddle;
-    const float* mel_w;
-    const int4* mel_work;    // [128] per-thread work items {bin start, weight offset, count, band}
+    const float2* window2;   // [1024] {w[2n], w[2n+1]} symmetric Hamming
+    const float* mel_w;      // [kMelWPad] packed non-zero Slaney weights
+    const int4* mel_work;    // [128] work items {bin start, weight offset, count, band}
     const int2* mel_owner;   // [64]  {first slot, slot count} per band
+};
+
+struct StftSmem {
+    float even[kHalfSpan];                 // x[s0 + 2m]
+    float odd[kHalfSpan];                  // x[s0 + 2m + 1]
+    float2 window2[kNfft / 2];
+    float mel_w[kMelWPad];
+    cpx xchg[kStftWarps][kXchgSize];       // per-warp transpose buffer, re-used for the frame's 1025 magnitudes
+    float part[kStftWarps][kMelItems];
+    unsigned long long bar;
 };
 
 __device__ __forceinline__ int reflect_index(int s, int L) {
@@ -46,128 +64,194 @@ __device__ __forceinline__ int reflect_index(int s, int L) {
 }
 
 template <typename WaveT>
-__device__ __forceinline__ float load_sample(const WaveT* p, int i);
+__device__ __forceinline__ float load_sample(const WaveT* p, long long i);
 template <>
-__device__ __forceinline__ float load_sample<float>(const float* p, int i) { return __ldg(p + i); }
+__device__ __forceinline__ float load_sample<float>(const float* p, long long i) { return __ldg(p + i); }
 template <>
-__device__ __forceinline__ float load_sample<int16_t>(const int16_t* p, int i) {
+__device__ __forceinline__ float load_sample<int16_t>(const int16_t* p, long long i) {
     return (float)__ldg(p + i) * (1.0f / 32768.0f);  // soundfile's int16 -> float scaling
 }
 
-// sqrt(x) = x * rsqrt(x) (2 ulp), exact 0 for x = 0: the IEEE sqrtf sequence was 9 % of the kernel's instructions
+// one MUFU: sqrt.approx (relative error ~1e-7), exact 0 for x = 0 and exact under scaling by 4
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return x > 0.f ? x * r : 0.f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stage the span [s0, s0 + kSpan) of one clip, de-interleaved.  Interior tiles whose global address is 16-byte
+// aligned-down-able read whole 16-byte vectors (4 floats / 8 PCM samples); edge tiles (reflect padding) go sample by
+// sample.
+template <typename WaveT>
+__device__ __forceinline__ void stage_span(const WaveT* __restrict__ wave, long long clip_off, long long total, int L,
+                                           int s0, bool base_aligned, StftSmem& sm, int tid) {
+    constexpr int V = 16 / (int)sizeof(WaveT);
+    const bool interior = s0 >= 0 && s0 + kSpan <= L;
+    if (interior && base_aligned) {
+        const long long g0 = clip_off + s0;
+        const int a = (int)(g0 & (V - 1));
+        const long long gv = g0 - a;                               // 16-byte aligned element index
+        const int n_vec = (kSpan + a + V - 1) / V;
+        for (int c = tid; c < n_vec; c += 32 * kStftWarps) {
+            const long long g = gv + (long long)V * c;
+            float x[V];
+            if (g + V <= total) {
+                if (sizeof(WaveT) == 4) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(wave + g));
+                    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+                } else {
+                    const int4 q = __ldg(reinterpret_cast<const int4*>(wave + g));
+                    const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {              // little endian: the low half is the earlier sample
+                        x[(2 * e) % V] = (float)(short)(w[e] & 0xFFFF) * (1.0f / 32768.0f);
+                        x[(2 * e + 1) % V] = (float)(short)(w[e] >> 16) * (1.0f / 32768.0f);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) x[e] = g + e < total ? load_sample<WaveT>(wave, g + e) : 0.f;
+            }
+            const int i0 = V * c - a;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const int i = i0 + e;
+                if (i >= 0 && i < kSpan) (i & 1 ? sm.odd : sm.even)[i >> 1] = x[e];
+            }
+        }
+    } else {
+        for (int i = tid; i < kSpan; i += 32 * kStftWarps) {
+            const int s = reflect_index(s0 + i, L);
+            const float x = (s >= 0 && s < L) ? load_sample<WaveT>(wave, clip_off + s) : 0.f;
+            (i & 1 ? sm.odd : sm.even)[i >> 1] = x;
+        }
+    }
 }
 
 template <typename WaveT>
-__global__ void __launch_bounds__(256, 3)
-stft_mel_kernel(const WaveT* __restrict__ wave, int L, int T, MelTables tab, float* __restrict__ mel_amp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* span = reinterpret_cast<float*>(smem_raw);                 // [kSpan] (+pad)
-    cf32* bufA = reinterpret_cast<cf32*>(span + kSpanPad);            // [2304] (padded, fft_pad)
-    cf32* bufB = bufA + kFftPaddedSize;                               // [2304]
-    __shared__ float part[256];
-    const cf32* __restrict__ tw = tab.twiddle;                        // [2048], read through L1 (16 KB, hot)
+__global__ void __launch_bounds__(32 * kStftWarps, 2)
+stft_mel_kernel(const WaveT* __restrict__ wave, int B, int L, int T, MelTables tab, float* __restrict__ mel_amp) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];   // every member of StftSmem is a multiple of 16 bytes
+    StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_dyn);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    const int t0 = blockIdx.x * kFramesPerCta;
-    const WaveT* clip = wave + (size_t)b * L;
-
-    const int s0 = t0 * kHop - kNfft / 2;
-    if (sizeof(WaveT) == 4) {
-        // float clips: asynchronous 4-byte copies straight into shared memory (all 22 per thread in flight at once)
-        const uint32_t span_a = (uint32_t)__cvta_generic_to_shared(span);
-        for (int i = tid; i < kSpan; i += 256) {
-            const int s = reflect_index(s0 + i, L);
-            if (s >= 0 && s < L)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(span_a + 4u * i), "l"(clip + s) : "memory");
-            else
-                span[i] = 0.f;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else {
-        for (int i = tid; i < kSpan; i += 256) {
-            const int s = reflect_index(s0 + i, L);
-            span[i] = (s >= 0 && s < L) ? load_sample<WaveT>(clip, s) : 0.f;
-        }
+    // constant tables: two bulk copies per CTA (window 8 KB, mel weights 7.8 KB), complete on an mbarrier
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sm.bar)),
+                     "r"((uint32_t)(sizeof(sm.window2) + sizeof(sm.mel_w))) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(sm.window2)), "l"(tab.window2), "r"((uint32_t)sizeof(sm.window2)), "r"(smem_addr(&sm.bar))
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(sm.mel_w)), "l"(tab.mel_w), "r"((uint32_t)sizeof(sm.mel_w)), "r"(smem_addr(&sm.bar))
+                     : "memory");
     }
-    __syncthreads();
 
-    // this thread's run of Slaney weights (<= 22 of them) is the same for every frame: the first 16 are loaded once per
-    // CTA and kept in registers, the few longer runs read their tail through L1
-    const int4 mel_e = __ldg(tab.mel_work + (tid & 127));           // {bin start, weight offset, count, band}
-    float mel_wt[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) mel_wt[i] = i < mel_e.z ? __ldg(tab.mel_w + mel_e.y + i) : 0.f;
+    // per-lane constants: W_1024^(lane 2^j) for the pass-1 twiddles, W_2048^lane for the Hermitian split
+    Pass1Twiddles tw1;
+    cpx wl;
+    {
+        float s, c;
+        sincospif(-(float)lane / 512.f, &s, &c);   tw1.w1 = cmake(c, s);
+        sincospif(-(float)lane / 256.f, &s, &c);   tw1.w2 = cmake(c, s);
+        sincospif(-(float)lane / 128.f, &s, &c);   tw1.w4 = cmake(c, s);
+        sincospif(-(float)lane / 64.f, &s, &c);    tw1.w8 = cmake(c, s);
+        sincospif(-(float)lane / 32.f, &s, &c);    tw1.w16 = cmake(c, s);
+        sincospif(-(float)lane / 1024.f, &s, &c);  wl = cmake(c, s);
+    }
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
+    const long long total = (long long)B * L;
+    const int tiles_per_clip = (T + kFramesPerTile - 1) / kFramesPerTile;
+    const int n_tiles = tiles_per_clip * B;
+    cpx* const xb = sm.xchg[warp];
+    float* const mag = reinterpret_cast<float*>(xb);
+    bool tables_ready = false;
 
-    const int n_pairs = min(kFramesPerCta, T - t0 + 1) / 2;  // frames [t0, T) in pairs (odd tail rounds up)
-    for (int p = 0; p < n_pairs; ++p) {
-        // pass 1 (Ns = 1): windowed load straight from the span, two real frames -> one complex signal
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_clip;
+        const int t0 = (tile - b * tiles_per_clip) * kFramesPerTile;
+        __syncthreads();                                          // every warp is done with the previous span
+        stage_span<WaveT>(wave, (long long)b * L, total, L, t0 * kHop - kNfft / 2, base_aligned, sm, tid);
+        __syncthreads();
+        if (!tables_ready) {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(smem_addr(&sm.bar)) : "memory");
+            tables_ready = true;
+        }
+        const int t = t0 + warp;
+        if (t >= T) continue;                                     // warp-uniform: the tile's tail frames do not exist
+
+        // ---- load + window: z[n1] = (x[o + 2n], x[o + 2n + 1]) * (w[2n], w[2n + 1]), n = 32 n1 + lane ----
+        const int o = warp * kHop;
+        const float* pre = (o & 1) ? sm.odd + (o >> 1) : sm.even + (o >> 1);
+        const float* pim = (o & 1) ? sm.even + ((o + 1) >> 1) : sm.odd + (o >> 1);
+        cpx v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const float2 w = sm.window2[32 * n1 + lane];
+            v[n1] = cmul_elem(cmake(pre[32 * n1 + lane], pim[32 * n1 + lane]), cmake(w.x, w.y));
+        }
+        stft_pass1(v, tw1, lane, xb);
+        __syncwarp();
+        stft_pass2(v, lane, xb);                                  // v[k2] = Z[lane + 32 k2]
+        __syncwarp();                                             // the transpose buffer becomes the magnitude buffer
+
+        // ---- Hermitian split: partner Z[1024 - k] of k = lane + 32 p sits in lane (32 - lane) % 32, register 31 - p
+        //      (lane 0 pairs with itself: Z[1024 - 32 p] is its own register 32 - p, Z[1024] = Z[0]) ----
         {
-            const float* fa = span + (2 * p) * kHop;
-            const float* fb = fa + kHop;
-            cf32 v[8];
+            constexpr float c64[16] = DCASE_W64_COS;
+            constexpr float s64[16] = DCASE_W64_SIN;
+            const int src = (32 - lane) & 31;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int n = tid + r * 256;
-                const float w = __ldg(tab.window + n);
-                v[r] = cf32{fa[n] * w, fb[n] * w};
+            for (int p = 0; p < 16; ++p) {
+                const float mx = __shfl_sync(0xffffffffu, cre(v[31 - p]), src);
+                const float my = __shfl_sync(0xffffffffu, cim(v[31 - p]), src);
+                const cpx own = v[(32 - p) & 31];
+                const cpx zm = lane == 0 ? own : cmake(mx, my);
+                float lo, hi;
+                stft_post_pair(v[p], zm, wl, c64[p], s64[p], lo, hi);
+                mag[lane + 32 * p] = fast_sqrt(lo);               // 2 |X[k]|: the staged mel weights carry the 1/2
+                mag[1024 - lane - 32 * p] = fast_sqrt(hi);
             }
-            fft8(v);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) bufA[fft_pad(tid * 8 + r)] = v[r];
-        }
-        __syncthreads();
-        stockham_pass<8>(tid, 8, bufA, bufB, tw);
-        __syncthreads();
-        stockham_pass<8>(tid, 64, bufB, bufA, tw);
-        __syncthreads();
-        stockham_pass<4>(tid, 512, bufA, bufB, tw);
-        stockham_pass<4>(tid + 256, 512, bufA, bufB, tw);
-        __syncthreads();
-        // separate the two real spectra and take magnitudes (bins 0..1024)
-        float* mag = reinterpret_cast<float*>(bufA);  // [2][kMagPitch]
-        for (int k = tid; k < kBins; k += 256) {
-            const cf32 zk = bufB[fft_pad(k)];
-            const cf32 zn = bufB[fft_pad((kNfft - k) & (kNfft - 1))];
-            const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-            const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
-            mag[k] = fast_sqrt(ar * ar + ai * ai);
-            mag[kMagPitch + k] = fast_sqrt(br * br + bi * bi);
-        }
-        __syncthreads();
-        // sparse Slaney mel projection (1,983 non-zeros per frame), load balanced: 128 threads per frame, each owns
-        // a contiguous run of weights inside one band (host-built table); band owners combine the partials
-        {
-            const int fr = tid >> 7;
-            const float* mg = mag + fr * kMagPitch + mel_e.x;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                if (i < mel_e.z) {                      // zero weights pad the run: mg stays inside the padded buffer
-                    a0 = fmaf(mel_wt[i], mg[i], a0);
-                    a1 = fmaf(mel_wt[i + 1], mg[i + 1], a1);
-                    a2 = fmaf(mel_wt[i + 2], mg[i + 2], a2);
-                    a3 = fmaf(mel_wt[i + 3], mg[i + 3], a3);
-                }
+            if (lane == 0) {                                      // |X[512]| = |Z[512]|
+                const float x = cre(v[16]), y = cim(v[16]);
+                mag[512] = 2.f * fast_sqrt(x * x + y * y);
             }
-            for (int i = 16; i < mel_e.z; ++i) a0 = fmaf(__ldg(tab.mel_w + mel_e.y + i), mg[i], a0);
-            part[tid] = (a0 + a1) + (a2 + a3);
         }
-        __syncthreads();
-        if ((tid & 127) < kMel) {
-            const int fr = tid >> 7, m = tid & 127;
-            const int2 o = __ldg(tab.mel_owner + m);            // {first slot, slot count} of band m
+        __syncwarp();
+
+        // ---- sparse Slaney projection: 4 work items per lane (each a contiguous run of weights inside one band) ----
+        float* part = sm.part[warp];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int4 it = __ldg(tab.mel_work + lane + 32 * j);  // {bin start, weight offset, count, band}
+            const float* mg = mag + it.x;
+            const float* wt = sm.mel_w + it.y;
+            float a0 = 0.f, a1 = 0.f;
+            int i = 0;
+            for (; i + 1 < it.z; i += 2) {
+                a0 = fmaf(wt[i], mg[i], a0);
+                a1 = fmaf(wt[i + 1], mg[i + 1], a1);
+            }
+            if (i < it.z) a0 = fmaf(wt[i], mg[i], a0);
+            part[lane + 32 * j] = a0 + a1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int m = lane + 32 * j;
+            const int2 ow = __ldg(tab.mel_owner + m);             // {first slot, slot count} of band m
             float acc = 0.f;
-            for (int q = 0; q < o.y; ++q) acc += part[fr * 128 + o.x + q];
-            const int t = t0 + 2 * p + fr;
-            if (t < T) mel_amp[((size_t)b * T + t) * kMel + m] = acc;
+            for (int q = 0; q < ow.y; ++q) acc += part[ow.x + q];
+            mel_amp[((size_t)b * T + t) * kMel + m] = acc;
         }
-        __syncthreads();
+        __syncwarp();                                             // part / mag are re-used by the next tile
     }
 }
 
@@ -352,19 +436,14 @@ double mel_to_hz(double m) {
     return m >= min_log_mel ? min_log_hz * exp(logstep * (m - min_log_mel)) : f_sp * m;
 }
 
-constexpr size_t kStftSmemBytes = kSpanPad * sizeof(float) + 2 * kFftPaddedSize * sizeof(cf32);
+constexpr size_t kStftSmemBytes = sizeof(StftSmem);
 
 }  // namespace
 
 int dcase_logmel_tables_create(dcase_ctx* ctx) {
     const double sr = 44100.0, f_lo = 0.0, f_hi = 22050.0;
-    std::vector<float> win(kNfft);
+    std::vector<float> win(kNfft);            // np.hamming(2048); stored as float2 {w[2n], w[2n + 1]}
     for (int n = 0; n < kNfft; ++n) win[n] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * n / (kNfft - 1)));
-    std::vector<cf32> tw(kNfft);
-    for (int m = 0; m < kNfft; ++m) {
-        const double a = -2.0 * M_PI * m / kNfft;
-        tw[m] = cf32{(float)cos(a), (float)sin(a)};
-    }
     // Slaney filterbank, librosa.filters.mel(sr, n_fft, n_mels=64, fmin, fmax, htk=False, norm=None)
     std::vector<double> mel_f(kMel + 2);
     const double m_lo = hz_to_mel(f_lo), m_hi = hz_to_mel(f_hi);
@@ -388,12 +467,13 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
         for (int k = 0; k < len[i]; ++k) packed.push_back(ctx->h_mel_dense[(size_t)i * kBins + start[i] + k]);
     }
     ctx->mel_nnz = (int)packed.size();
-    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_window, kNfft * sizeof(float)));
-    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_twiddle, kNfft * sizeof(cf32)));
+    if ((int)packed.size() > kMelWPad) { dcase_set_error("mel weight table larger than its shared-memory slot"); return DCASE_ERR_STATE; }
+    packed.resize(kMelWPad, 0.f);
+    for (float& w : packed) w *= 0.5f;        // the kernel's magnitudes are 2 |X[k]| (exact power-of-two rescale)
+    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_window2, kNfft * sizeof(float)));
     DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_w, packed.size() * sizeof(float)));
     DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
-    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_window, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
-    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_twiddle, tw.data(), kNfft * sizeof(cf32), cudaMemcpyHostToDevice));
+    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_window2, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
     // balanced work split: band m gets n_m of the 128 slots (proportional to its length, at least one)
     {
         std::vector<int> n_slots(kMel, 1);
@@ -430,11 +510,14 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
                                           (int)kStftSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kStftSmemBytes));
+    // two 108 KB CTAs per SM need the whole carve-out
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<int16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return DCASE_OK;
 }
 
 void dcase_logmel_tables_destroy(dcase_ctx* ctx) {
-    cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_w);
+    cudaFree(ctx->d_window2); cudaFree(ctx->d_mel_w);
     cudaFree(ctx->d_mel_work); cudaFree(ctx->d_mel_owner);
     free(ctx->h_mel_dense);
 }
@@ -456,12 +539,15 @@ static int logmel_fwd_impl(dcase_ctx* ctx, const void* wave, int is_pcm16, int B
     if (B == 0) return DCASE_OK;
     const int T = 1 + L / kHop;
     DCASE_PROF("stft_mel", stream);
-    MelTables tab{ctx->d_window, ctx->d_twiddle, ctx->d_mel_w, (const int4*)ctx->d_mel_work, (const int2*)ctx->d_mel_owner};
-    dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);
+    MelTables tab{ctx->d_window2, ctx->d_mel_w, (const int4*)ctx->d_mel_work, (const int2*)ctx->d_mel_owner};
+    const long long n_tiles = (long long)((T + kFramesPerTile - 1) / kFramesPerTile) * B;
+    DCASE_REQUIRE(n_tiles < (1ll << 31), "too many frames for one launch");
+    // persistent CTAs: two per SM (108 KB of shared memory each), each looping over 8-frame tiles
+    const int grid = (int)(n_tiles < 2ll * ctx->num_sms ? n_tiles : 2ll * ctx->num_sms);
     if (is_pcm16)
-        stft_mel_kernel<int16_t><<<grid, 256, kStftSmemBytes, stream>>>((const int16_t*)wave, L, T, tab, mel_amp);
+        stft_mel_kernel<int16_t><<<grid, 32 * kStftWarps, kStftSmemBytes, stream>>>((const int16_t*)wave, B, L, T, tab, mel_amp);
     else
-        stft_mel_kernel<float><<<grid, 256, kStftSmemBytes, stream>>>((const float*)wave, L, T, tab, mel_amp);
+        stft_mel_kernel<float><<<grid, 32 * kStftWarps, kStftSmemBytes, stream>>>((const float*)wave, B, L, T, tab, mel_amp);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

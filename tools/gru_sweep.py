@@ -3,7 +3,7 @@ T = 108 (cfg.max_frames // pooling_time_ratio), batch {24, 256}.
 
 Hidden size 64 (the only one cfg.crnn_kwargs selects) runs through dcase_bigru_forward; every (H, B) point is also
 timed through cuDNN (torch.nn.GRU on the same GPU, fp32, TF32 off) as the library baseline SURVEY.md section 8d asks
-for.  H = 128 / 256 run through the experimental cluster kernel only under DCASE_EXPERIMENTAL=1 (null otherwise).  FLOPs (forward) =
+for.  H = 128 / 256 run through the thread-block-cluster kernel (csrc/gru_cluster.cu).  FLOPs (forward) =
 2 B T [(In 3H + H 3H) + (2H 3H + H 3H)] 2.  Writes gpurun_out/gru_sweep.json and prints it.
 
     python tools/gru_sweep.py [--iters 200]
@@ -18,6 +18,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+import bench  # noqa: E402
 from dcase2019_task4_b200 import kernels as K  # noqa: E402
 
 T = 108
@@ -45,6 +46,7 @@ def main():
     ap.add_argument("--iters", type=int, default=200)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
+    _sampler = bench.ClockSampler(0)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     rows = []
@@ -64,7 +66,7 @@ def main():
                 ours_ms = time_ms(lambda: K.bigru_forward(x, flat, out=out, ws=ws), args.iters)
                 with torch.no_grad():
                     err = float((out - gru(x)[0]).abs().max())
-            elif os.environ.get("DCASE_EXPERIMENTAL", "0") == "1":       # cluster BiGRU (csrc/gru_cluster.cu)
+            else:                                                          # cluster BiGRU (csrc/gru_cluster.cu)
                 flat = torch.cat([p.detach().reshape(-1) for _, p in gru.named_parameters()]).contiguous()
                 out = torch.empty(B, T, 2 * H, device=dev)
                 ws = torch.empty(K.lib().dcase_bigru_workspace_bytes_h(B, T, H), dtype=torch.uint8, device=dev)
@@ -78,8 +80,9 @@ def main():
                          "speedup_vs_cudnn": None if ours_ms is None else cudnn_ms / ours_ms,
                          "max_abs_diff_vs_cudnn": err})
     out = {"config": "BiGRU sweep (BASELINE.json configs[4])", "dtype": "f32", "device": torch.cuda.get_device_name(0),
-           "note": "hidden 128 / 256 run through the experimental cluster kernel only under DCASE_EXPERIMENTAL=1 (null otherwise; cfg.crnn_kwargs selects 64); cuDNN rows are the library baseline",
+           "note": "hidden 128 / 256 run through the thread-block-cluster kernel csrc/gru_cluster.cu (cfg.crnn_kwargs selects 64); cuDNN rows are the library baseline",
            "rows": rows}
+    out["clocks"] = _sampler.stop()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "gru_sweep.json"), "w") as fh:
         json.dump(out, fh, indent=1)

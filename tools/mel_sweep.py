@@ -30,6 +30,7 @@ def main():
     mean = torch.full((64,), -30.0, device=dev)
     std = torch.full((64,), 12.0, device=dev)
     out = {}
+    sampler = bench.ClockSampler(0)
     for name, fn in (("stft_mel", lambda w: K.logmel_fwd(w)),
                      ("stft_mel+finish", lambda w: K.logmel_finish(K.logmel_fwd(w), mean, std, 864))):
         best = None
@@ -45,8 +46,9 @@ def main():
             best = ms if best is None else min(best, ms)
         gbs = n * bench.MEL_BYTES_PER_CLIP / (best * 1e-3) / 1e9
         out[name] = {"ms": best, "clips_per_s": n / (best * 1e-3), "achieved_GBs": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"]}
-    print(json.dumps({"config": "mel-feature-only sweep", "clips": n, "peak_hbm_GBs": peaks["hbm_gbs"],
-                      "peak_source": peaks["source"], "results": out}))
+    print(json.dumps({"config": "mel-feature-only sweep (BASELINE.json configs[3])", "clips": n, "dtype": "f32",
+                      "peak_hbm_GBs": peaks["hbm_gbs"], "peak_source": peaks["source"], "clocks": sampler.stop(),
+                      "algorithmic_bytes_per_clip": bench.MEL_BYTES_PER_CLIP, "results": out}))
 
 
 if __name__ == "__main__":
