@@ -7,9 +7,9 @@ struct dcase_ctx {
     int num_sms;
     // log-mel constant tables (device)
     float2* d_window2;   // [1024] {w[2n], w[2n+1]} of the symmetric Hamming window
-    float* d_mel_w;      // packed non-zero Slaney weights
-    int* d_mel_work;     // [128][4] balanced work items of the mel projection
-    int* d_mel_owner;    // [64][2]  slots of each band
+    float* d_mel_wt;     // [4][22][32] Slaney weights of the 128 work items, transposed, zero padded, halved
+    int* d_mel_start;    // [128] first FFT bin of each work item
+    int* d_mel_owner;    // [64][2] {first item, item count} of each band
     int mel_nnz;
     // second stream + events: the teacher forward runs concurrently with the student forward (dcase_mt_fwd_bwd)
     cudaStream_t aux_stream;

@@ -6,17 +6,18 @@
 //   (order: utils/utils.py:397-412 get_transforms)                            -> dcase_logmel_finish
 //
 // K1 layout (round 2): persistent CTAs of 8 warps; a tile = 8 consecutive frames of one clip, ONE WARP PER FRAME.
-//   * the tile's contiguous waveform span (7 * 511 + 2048 samples, reflect-padded at the clip ends) is staged once per
-//     tile with 16-byte global loads and stored DE-INTERLEAVED by sample parity (E[m] = x[2m], O[m] = x[2m+1]), so that
-//     the packing z[n] = x[2n] + i x[2n+1] of a real frame into a 1024-point complex FFT reads two stride-1 arrays
-//     (conflict-free) whatever the parity of the frame's offset (hop 511 is odd);
+//   * the tile's contiguous waveform span (7 * 511 + 2048 samples) arrives by ONE cp.async.bulk (1-D TMA) of its 16-byte
+//     aligned superset, issued for tile i + 1 as soon as every warp has pulled its frame of tile i into registers, so
+//     the copy flies under the FFT / mel phase of tile i (mbarrier completion).  Tiles that touch the clip ends
+//     (reflect padding), 16-bit PCM input and unaligned buffers are staged by ordinary loads instead;
 //   * the warp runs the whole real FFT on its own (csrc/fft1024.cuh): two 32-point DFTs in registers with one
 //     32 x 32 transpose through the warp's private 8.4 KB of shared memory, the Hermitian split with the partner values
-//     fetched by warp shuffles, packed f32x2 additions -- no block barrier inside a frame;
-//   * magnitudes go to the warp's scratch, the sparse Slaney projection (1,983 non-zeros, weights in shared memory,
-//     staged once per CTA together with the interleaved window by two cp.async.bulk copies) runs as 4 balanced work
-//     items per lane, band owners add the partials and write the frame's 64 mel amplitudes as two 128-byte rows.
-// 108 KB of shared memory per CTA: two CTAs (16 warps) per SM; while one stages its next span the other computes.
+//     fetched by warp shuffles, packed f32x2 additions -- no block barrier inside the FFT;
+//   * magnitudes go to the warp's scratch; the sparse Slaney projection (1,983 non-zeros) runs as 4 work items per lane
+//     (each a run of <= 22 weights inside one band) with the weights stored TRANSPOSED and zero padded in shared
+//     memory ([round][i][lane]: conflict-free, fixed trip count, no predicates); band owners add the partials and
+//     write the frame's 64 mel amplitudes as two 128-byte rows.  Window + mel tables: cp.async.bulk once per CTA.
+// 112 KB of shared memory per CTA: two CTAs (16 warps) per SM.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,26 +36,28 @@ constexpr int kBins = 1025;
 constexpr int kMel = 64;
 constexpr int kFramesPerTile = 8;
 constexpr int kStftWarps = 8;
+constexpr int kStftThreads = 32 * kStftWarps;
 constexpr int kSpan = (kFramesPerTile - 1) * kHop + kNfft;  // 5625 samples
-constexpr int kHalfSpan = 2816;                              // ceil(5625 / 2) = 2813, padded
-constexpr int kMelWPad = 1984;                               // 1,983 packed weights, padded to 16 bytes
-constexpr int kMelItems = 128;                               // work items of the mel projection (4 per lane)
+constexpr int kSpanBuf = 5632;                               // + up to 3 samples of alignment slack, 16-byte multiple
+constexpr int kMelItems = 128;                               // work items of the mel projection (4 rounds x 32 lanes)
+constexpr int kMelRun = 22;                                  // longest run of one item
 
 struct MelTables {
     const float2* window2;   // [1024] {w[2n], w[2n+1]} symmetric Hamming
-    const float* mel_w;      // [kMelWPad] packed non-zero Slaney weights
-    const int4* mel_work;    // [128] work items {bin start, weight offset, count, band}
-    const int2* mel_owner;   // [64]  {first slot, slot count} per band
+    const float* mel_wt;     // [4][kMelRun][32] weights of item (lane + 32 j), transposed, zero padded, pre-halved
+    const int* mel_start;    // [128] first FFT bin of each item
+    const int2* mel_owner;   // [64]  {first item, item count} per band
 };
 
 struct StftSmem {
-    float even[kHalfSpan];                 // x[s0 + 2m]
-    float odd[kHalfSpan];                  // x[s0 + 2m + 1]
+    float span[kSpanBuf];
     float2 window2[kNfft / 2];
-    float mel_w[kMelWPad];
+    float mel_wt[4 * kMelRun * 32];
+    int mel_start[kMelItems];
+    int2 mel_owner[kMel];
     cpx xchg[kStftWarps][kXchgSize];       // per-warp transpose buffer, re-used for the frame's 1025 magnitudes
     float part[kStftWarps][kMelItems];
-    unsigned long long bar;
+    unsigned long long bar_tables, bar_span;
 };
 
 __device__ __forceinline__ int reflect_index(int s, int L) {
@@ -80,76 +83,82 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init1(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
 
-// Stage the span [s0, s0 + kSpan) of one clip, de-interleaved.  Interior tiles whose global address is 16-byte
-// aligned-down-able read whole 16-byte vectors (4 floats / 8 PCM samples); edge tiles (reflect padding) go sample by
-// sample.
+// Where a tile's span sits: sm.span[i] = x[s0 - a + i] (reflect padded), a = alignment slack of the bulk copy.
+struct TileStage {
+    int b, t0, a;
+    bool async;
+};
+
+// Stage the span of `tile` into sm.span.  Returns how it was staged; the async form is issued by thread 0 alone and
+// completes on sm.bar_span, the synchronous form is written by all threads (the caller barriers before reading).
 template <typename WaveT>
-__device__ __forceinline__ void stage_span(const WaveT* __restrict__ wave, long long clip_off, long long total, int L,
-                                           int s0, bool base_aligned, StftSmem& sm, int tid) {
-    constexpr int V = 16 / (int)sizeof(WaveT);
-    const bool interior = s0 >= 0 && s0 + kSpan <= L;
-    if (interior && base_aligned) {
+__device__ __forceinline__ TileStage stage_span(const WaveT* __restrict__ wave, int tile, int tiles_per_clip, int B, int L,
+                                                bool base_aligned, StftSmem& sm, int tid) {
+    TileStage st;
+    st.b = tile / tiles_per_clip;
+    st.t0 = (tile - st.b * tiles_per_clip) * kFramesPerTile;
+    const int s0 = st.t0 * kHop - kNfft / 2;
+    const long long clip_off = (long long)st.b * L;
+    st.a = 0;
+    st.async = false;
+    if (sizeof(WaveT) == 4 && base_aligned && s0 >= 0 && s0 + kSpan <= L) {
         const long long g0 = clip_off + s0;
-        const int a = (int)(g0 & (V - 1));
-        const long long gv = g0 - a;                               // 16-byte aligned element index
-        const int n_vec = (kSpan + a + V - 1) / V;
-        for (int c = tid; c < n_vec; c += 32 * kStftWarps) {
-            const long long g = gv + (long long)V * c;
-            float x[V];
-            if (g + V <= total) {
-                if (sizeof(WaveT) == 4) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(wave + g));
-                    x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-                } else {
-                    const int4 q = __ldg(reinterpret_cast<const int4*>(wave + g));
-                    const int w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {              // little endian: the low half is the earlier sample
-                        x[(2 * e) % V] = (float)(short)(w[e] & 0xFFFF) * (1.0f / 32768.0f);
-                        x[(2 * e + 1) % V] = (float)(short)(w[e] >> 16) * (1.0f / 32768.0f);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < V; ++e) x[e] = g + e < total ? load_sample<WaveT>(wave, g + e) : 0.f;
+        const int a = (int)(g0 & 3);
+        const uint32_t n = (uint32_t)((kSpan + a + 3) & ~3);
+        if (g0 - a + n <= (long long)B * L) {
+            st.a = a;
+            st.async = true;
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads / writes of the buffer
+                mbar_expect(&sm.bar_span, 4u * n);
+                bulk_load(sm.span, wave + (g0 - a), 4u * n, &sm.bar_span);
             }
-            const int i0 = V * c - a;
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const int i = i0 + e;
-                if (i >= 0 && i < kSpan) (i & 1 ? sm.odd : sm.even)[i >> 1] = x[e];
-            }
-        }
-    } else {
-        for (int i = tid; i < kSpan; i += 32 * kStftWarps) {
-            const int s = reflect_index(s0 + i, L);
-            const float x = (s >= 0 && s < L) ? load_sample<WaveT>(wave, clip_off + s) : 0.f;
-            (i & 1 ? sm.odd : sm.even)[i >> 1] = x;
+            return st;
         }
     }
+    for (int i = tid; i < kSpan; i += kStftThreads) {
+        const int s = reflect_index(s0 + i, L);
+        sm.span[i] = (s >= 0 && s < L) ? load_sample<WaveT>(wave, clip_off + s) : 0.f;
+    }
+    return st;
 }
 
 template <typename WaveT>
-__global__ void __launch_bounds__(32 * kStftWarps, 2)
+__global__ void __launch_bounds__(kStftThreads, 2)
 stft_mel_kernel(const WaveT* __restrict__ wave, int B, int L, int T, MelTables tab, float* __restrict__ mel_amp) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];   // every member of StftSmem is a multiple of 16 bytes
     StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_dyn);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // constant tables: two bulk copies per CTA (window 8 KB, mel weights 7.8 KB), complete on an mbarrier
+    // constant tables: four bulk copies per CTA (window 8 KB, mel weights 11 KB, item starts, band owners)
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.bar)) : "memory");
+        mbar_init1(&sm.bar_tables);
+        mbar_init1(&sm.bar_span);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sm.bar)),
-                     "r"((uint32_t)(sizeof(sm.window2) + sizeof(sm.mel_w))) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_addr(sm.window2)), "l"(tab.window2), "r"((uint32_t)sizeof(sm.window2)), "r"(smem_addr(&sm.bar))
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_addr(sm.mel_w)), "l"(tab.mel_w), "r"((uint32_t)sizeof(sm.mel_w)), "r"(smem_addr(&sm.bar))
-                     : "memory");
+        mbar_expect(&sm.bar_tables, (uint32_t)(sizeof(sm.window2) + sizeof(sm.mel_wt) + sizeof(sm.mel_start) + sizeof(sm.mel_owner)));
+        bulk_load(sm.window2, tab.window2, (uint32_t)sizeof(sm.window2), &sm.bar_tables);
+        bulk_load(sm.mel_wt, tab.mel_wt, (uint32_t)sizeof(sm.mel_wt), &sm.bar_tables);
+        bulk_load(sm.mel_start, tab.mel_start, (uint32_t)sizeof(sm.mel_start), &sm.bar_tables);
+        bulk_load(sm.mel_owner, tab.mel_owner, (uint32_t)sizeof(sm.mel_owner), &sm.bar_tables);
     }
+    __syncthreads();                                              // the mbarriers exist before anybody polls them
 
     // per-lane constants: W_1024^(lane 2^j) for the pass-1 twiddles, W_2048^lane for the Hermitian split
     Pass1Twiddles tw1;
@@ -164,39 +173,40 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int B, int L, int T, MelTables t
         sincospif(-(float)lane / 1024.f, &s, &c);  wl = cmake(c, s);
     }
     const bool base_aligned = (reinterpret_cast<uintptr_t>(wave) & 15) == 0;
-    const long long total = (long long)B * L;
     const int tiles_per_clip = (T + kFramesPerTile - 1) / kFramesPerTile;
     const int n_tiles = tiles_per_clip * B;
     cpx* const xb = sm.xchg[warp];
     float* const mag = reinterpret_cast<float*>(xb);
-    bool tables_ready = false;
+    float* const part = sm.part[warp];
+    uint32_t span_parity = 0;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_clip;
-        const int t0 = (tile - b * tiles_per_clip) * kFramesPerTile;
-        __syncthreads();                                          // every warp is done with the previous span
-        stage_span<WaveT>(wave, (long long)b * L, total, L, t0 * kHop - kNfft / 2, base_aligned, sm, tid);
-        __syncthreads();
-        if (!tables_ready) {
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(done) : "r"(smem_addr(&sm.bar)) : "memory");
-            tables_ready = true;
-        }
-        const int t = t0 + warp;
-        if (t >= T) continue;                                     // warp-uniform: the tile's tail frames do not exist
+    int tile = blockIdx.x;
+    TileStage cur{0, 0, 0, false};
+    if (tile < n_tiles) cur = stage_span<WaveT>(wave, tile, tiles_per_clip, B, L, base_aligned, sm, tid);
+    mbar_wait_parity(&sm.bar_tables, 0);
+
+    for (; tile < n_tiles; tile += gridDim.x) {
+        if (cur.async) { mbar_wait_parity(&sm.bar_span, span_parity); span_parity ^= 1; }
+        else __syncthreads();                                     // the span was written with ordinary stores
+        const int t = cur.t0 + warp;
+        const bool active = t < T;                                // warp-uniform: the tile's tail frames do not exist
+        const int b = cur.b;
 
         // ---- load + window: z[n1] = (x[o + 2n], x[o + 2n + 1]) * (w[2n], w[2n + 1]), n = 32 n1 + lane ----
-        const int o = warp * kHop;
-        const float* pre = (o & 1) ? sm.odd + (o >> 1) : sm.even + (o >> 1);
-        const float* pim = (o & 1) ? sm.even + ((o + 1) >> 1) : sm.odd + (o >> 1);
         cpx v[32];
+        if (active) {
+            const float* fr = sm.span + cur.a + warp * kHop + 2 * lane;
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-            const float2 w = sm.window2[32 * n1 + lane];
-            v[n1] = cmul_elem(cmake(pre[32 * n1 + lane], pim[32 * n1 + lane]), cmake(w.x, w.y));
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const float2 w = sm.window2[32 * n1 + lane];
+                v[n1] = cmul_elem(cmake(fr[64 * n1], fr[64 * n1 + 1]), cmake(w.x, w.y));
+            }
         }
+        __syncthreads();                                          // every warp holds its frame: the span buffer is free
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) cur = stage_span<WaveT>(wave, next, tiles_per_clip, B, L, base_aligned, sm, tid);
+        if (!active) continue;
+
         stft_pass1(v, tw1, lane, xb);
         __syncwarp();
         stft_pass2(v, lane, xb);                                  // v[k2] = Z[lane + 32 k2]
@@ -226,27 +236,25 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int B, int L, int T, MelTables t
         }
         __syncwarp();
 
-        // ---- sparse Slaney projection: 4 work items per lane (each a contiguous run of weights inside one band) ----
-        float* part = sm.part[warp];
+        // ---- sparse Slaney projection: item (lane + 32 j) is a run of <= 22 weights inside one band; the zero padding
+        //      of the transposed weight table makes the trip count fixed (magnitudes past the run are finite) ----
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int4 it = __ldg(tab.mel_work + lane + 32 * j);  // {bin start, weight offset, count, band}
-            const float* mg = mag + it.x;
-            const float* wt = sm.mel_w + it.y;
+            const float* mg = mag + sm.mel_start[lane + 32 * j];
+            const float* wt = sm.mel_wt + j * (kMelRun * 32) + lane;
             float a0 = 0.f, a1 = 0.f;
-            int i = 0;
-            for (; i + 1 < it.z; i += 2) {
-                a0 = fmaf(wt[i], mg[i], a0);
-                a1 = fmaf(wt[i + 1], mg[i + 1], a1);
+#pragma unroll
+            for (int i = 0; i < kMelRun; i += 2) {
+                a0 = fmaf(wt[32 * i], mg[i], a0);
+                a1 = fmaf(wt[32 * i + 32], mg[i + 1], a1);
             }
-            if (i < it.z) a0 = fmaf(wt[i], mg[i], a0);
             part[lane + 32 * j] = a0 + a1;
         }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int m = lane + 32 * j;
-            const int2 ow = __ldg(tab.mel_owner + m);             // {first slot, slot count} of band m
+            const int2 ow = sm.mel_owner[m];                      // {first item, item count} of band m
             float acc = 0.f;
             for (int q = 0; q < ow.y; ++q) acc += part[ow.x + q];
             mel_amp[((size_t)b * T + t) * kMel + m] = acc;
@@ -467,18 +475,15 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
         for (int k = 0; k < len[i]; ++k) packed.push_back(ctx->h_mel_dense[(size_t)i * kBins + start[i] + k]);
     }
     ctx->mel_nnz = (int)packed.size();
-    if ((int)packed.size() > kMelWPad) { dcase_set_error("mel weight table larger than its shared-memory slot"); return DCASE_ERR_STATE; }
-    packed.resize(kMelWPad, 0.f);
-    for (float& w : packed) w *= 0.5f;        // the kernel's magnitudes are 2 |X[k]| (exact power-of-two rescale)
     DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_window2, kNfft * sizeof(float)));
-    DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_w, packed.size() * sizeof(float)));
-    DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_w, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
     DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_window2, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
-    // balanced work split: band m gets n_m of the 128 slots (proportional to its length, at least one)
+    // balanced work split: band m gets n_m of the 128 items (proportional to its length, at least one); item q is a
+    // contiguous run of weights inside its band.  The kernel reads the weights of item (lane + 32 j) transposed
+    // ([j][i][lane]), zero padded to kMelRun and halved (its magnitudes are 2 |X[k]|: exact power-of-two rescale).
     {
         std::vector<int> n_slots(kMel, 1);
         int used = kMel;
-        while (used < 128) {            // give the next slot to the band with the largest per-slot load
+        while (used < kMelItems) {      // give the next item to the band with the largest per-item load
             int best = 0;
             double best_load = -1.0;
             for (int m = 0; m < kMel; ++m) {
@@ -488,37 +493,40 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
             ++n_slots[best];
             ++used;
         }
-        std::vector<int> work(128 * 4), owner(kMel * 2);
+        std::vector<int> item_start(kMelItems, 0), owner(kMel * 2);
+        std::vector<float> wt((size_t)4 * kMelRun * 32, 0.f);
         int slot = 0;
         for (int m = 0; m < kMel; ++m) {
             owner[2 * m] = slot;
             owner[2 * m + 1] = n_slots[m];
             for (int q = 0; q < n_slots[m]; ++q, ++slot) {
                 const int beg = (int)((long long)len[m] * q / n_slots[m]), end = (int)((long long)len[m] * (q + 1) / n_slots[m]);
-                work[4 * slot] = start[m] + beg;
-                work[4 * slot + 1] = off[m] + beg;
-                work[4 * slot + 2] = end - beg;
-                work[4 * slot + 3] = m;
+                if (end - beg > kMelRun) { dcase_set_error("mel work item longer than kMelRun"); return DCASE_ERR_STATE; }
+                item_start[slot] = start[m] + beg;
+                for (int i = 0; i < end - beg; ++i)
+                    wt[((size_t)(slot >> 5) * kMelRun + i) * 32 + (slot & 31)] = 0.5f * packed[off[m] + beg + i];
             }
         }
-        DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_work, work.size() * sizeof(int)));
+        DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_wt, wt.size() * sizeof(float)));
+        DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_start, item_start.size() * sizeof(int)));
         DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_mel_owner, owner.size() * sizeof(int)));
-        DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_work, work.data(), work.size() * sizeof(int), cudaMemcpyHostToDevice));
+        DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+        DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_start, item_start.data(), item_start.size() * sizeof(int), cudaMemcpyHostToDevice));
         DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_mel_owner, owner.data(), owner.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kStftSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)kStftSmemBytes));
-    // two 108 KB CTAs per SM need the whole carve-out
+    // two 112 KB CTAs per SM need the whole carve-out
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(stft_mel_kernel<int16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     return DCASE_OK;
 }
 
 void dcase_logmel_tables_destroy(dcase_ctx* ctx) {
-    cudaFree(ctx->d_window2); cudaFree(ctx->d_mel_w);
-    cudaFree(ctx->d_mel_work); cudaFree(ctx->d_mel_owner);
+    cudaFree(ctx->d_window2); cudaFree(ctx->d_mel_wt);
+    cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_owner);
     free(ctx->h_mel_dense);
 }
 
@@ -539,10 +547,10 @@ static int logmel_fwd_impl(dcase_ctx* ctx, const void* wave, int is_pcm16, int B
     if (B == 0) return DCASE_OK;
     const int T = 1 + L / kHop;
     DCASE_PROF("stft_mel", stream);
-    MelTables tab{ctx->d_window2, ctx->d_mel_w, (const int4*)ctx->d_mel_work, (const int2*)ctx->d_mel_owner};
+    MelTables tab{ctx->d_window2, ctx->d_mel_wt, ctx->d_mel_start, (const int2*)ctx->d_mel_owner};
     const long long n_tiles = (long long)((T + kFramesPerTile - 1) / kFramesPerTile) * B;
     DCASE_REQUIRE(n_tiles < (1ll << 31), "too many frames for one launch");
-    // persistent CTAs: two per SM (108 KB of shared memory each), each looping over 8-frame tiles
+    // persistent CTAs: two per SM (112 KB of shared memory each), each looping over 8-frame tiles
     const int grid = (int)(n_tiles < 2ll * ctx->num_sms ? n_tiles : 2ll * ctx->num_sms);
     if (is_pcm16)
         stft_mel_kernel<int16_t><<<grid, 32 * kStftWarps, kStftSmemBytes, stream>>>((const int16_t*)wave, B, L, T, tab, mel_amp);

@@ -108,7 +108,6 @@ def test_three_graph_steps_from_waveforms_match_oracle(cuda_device):
     mean = np.full(64, -32.0) + np.linspace(-6, 6, 64)
     std = np.full(64, 11.0) + np.linspace(0, 4, 64)
     ps, pt = ocrnn.init_params(seed=51), ocrnn.init_params(seed=52)
-    ps0 = {k: v.clone() for k, v in ps.items()}
     student, teacher = CRNN(**cfg.crnn_kwargs), CRNN(**cfg.crnn_kwargs)
     assert cfg.crnn_kwargs["dropout"] == 0.5
     _load(student, ps)
@@ -125,67 +124,82 @@ def test_three_graph_steps_from_waveforms_match_oracle(cuda_device):
     md = torch.from_numpy(mean.astype(np.float32)).to(dev)
     sd = torch.from_numpy(std.astype(np.float32)).to(dev)
     steps_per_epoch = 0          # ramp-up length 0: the consistency weight is at its maximum (2.0) from the first step
-    for i in range(N):
-        cw = otrain.consistency_weight(i, steps_per_epoch)
-        eng.step_from_waveforms(wd[i], td[i], md, sd, cw, i + 1, check=False)      # no host sync between the steps
-    torch.cuda.synchronize()
-    assert len(eng._graphs) == N and eng.graph_launches > 0
-    last_strong, last_weak = eng.strong_s.cpu(), eng.weak_s.cpu()
-    last_meters = eng.read_meters()
-
-    sbuf, tbuf = ocrnn.init_buffers(), ocrnn.init_buffers()
-    adam = otrain.new_adam_state(ps)
     fb = omel.mel_filterbank()
+    names = list(ps.keys())
+
+    def bn_dict(flat):
+        buf = ocrnn.init_buffers()
+        for i in range(3):
+            buf[f"cnn.cnn.batchnorm{i}.running_mean"] = flat[(2 * i) * 64:(2 * i + 1) * 64].clone()
+            buf[f"cnn.cnn.batchnorm{i}.running_var"] = flat[(2 * i + 1) * 64:(2 * i + 2) * 64].clone()
+        return buf
+
+    # Adam turns a gradient at the tf32 noise level into a +-lr step of either sign, so two runs drift apart chaotically
+    # (a few hundred of 214 k parameters per step).  Every step is therefore compared FROM THE DEVICE'S OWN STATE: the
+    # oracle is loaded with the parameters / BN statistics / Adam moments the GPU held before the step.
     for i in range(N):
         step = 40 + i
+        torch.cuda.synchronize()
+        snap = {"ps": H.unflat_params(student.flat_parameters().detach().cpu().clone()),
+                "pt": H.unflat_params(teacher.flat_parameters().detach().cpu().clone()),
+                "sbuf": bn_dict(student.flat_bn_running().detach().cpu()),
+                "tbuf": bn_dict(teacher.flat_bn_running().detach().cpu()),
+                "m": H.unflat_params(eng.m.detach().cpu().clone()), "v": H.unflat_params(eng.v.detach().cpu().clone())}
+        cw = otrain.consistency_weight(i, steps_per_epoch)
+        eng.step_from_waveforms(wd[i], td[i], md, sd, cw, i + 1, check=False)      # CUDA-graph replay
+        torch.cuda.synchronize()
+        got_strong, got_weak, got_meters = eng.strong_s.cpu(), eng.weak_s.cpu(), eng.read_meters()
+        got_s = H.unflat_params(student.flat_parameters().detach().cpu().clone())
+        got_t = H.unflat_params(teacher.flat_parameters().detach().cpu().clone())
+        got_sbn, got_tbn = student.flat_bn_running().detach().cpu().clone(), teacher.flat_bn_running().detach().cpu().clone()
+        got_m = H.unflat_params(eng.m.detach().cpu().clone())
+
+        o_ps = {k: v.clone().contiguous() for k, v in snap["ps"].items()}
+        o_pt = {k: v.clone().contiguous() for k, v in snap["pt"].items()}
+        adam = {"step": i, "exp_avg": {k: v.clone() for k, v in snap["m"].items()},
+                "exp_avg_sq": {k: v.clone() for k, v in snap["v"].items()}}
         mels = np.stack([omel.calculate_mel_spec(w.astype(np.float64), fb) for w in waves[i]])
         noise = philox.teacher_noise(B * T, seed, step).reshape(B, T, 64).astype(np.float64)
         feats = [omel.transform_chain(mels[b], mean, std, noise=noise[b], frames=T) for b in range(B)]
         x = torch.from_numpy(np.stack([f[0] for f in feats]))          # [B, 1, T, 64]
         xe = torch.from_numpy(np.stack([f[1] for f in feats]))
-        meters, _ = otrain.train_batch(ps, sbuf, adam, x, tgt[i], i, steps_per_epoch, teacher_p=pt, teacher_buf=tbuf,
-                                       x_ema=xe, weak_mask=wm, strong_mask=sm,
+        meters, _ = otrain.train_batch(o_ps, snap["sbuf"], adam, x, tgt[i], i, steps_per_epoch, teacher_p=o_pt,
+                                       teacher_buf=snap["tbuf"], x_ema=xe, weak_mask=wm, strong_mask=sm,
                                        masks_student=H.oracle_masks(B, T, seed, step, 0),
                                        masks_teacher=H.oracle_masks(B, T, seed, step, 1))
-    es, ew = H.maxerr(last_strong, meters["strong"]), H.maxerr(last_weak, meters["weak"])
-    print(f"step 3 posteriors (student, train mode): strong Linf {es:.3e} weak Linf {ew:.3e}")
-    # after two optimizer steps the two runs no longer hold identical weights (Adam's +-lr steps on near-zero
-    # gradients, see below), so the third step's posteriors carry that drift on top of the kernel error
-    assert es <= 3e-3 and ew <= 3e-3
-    for name in ("Loss", "Strong loss", "weak_class_loss", "Consistency strong", "Consistency weak", "Strong EMA loss",
-                 "Weak EMA loss"):
-        assert abs(last_meters[name] - meters[name]) <= 2e-3 * max(1.0, abs(meters[name])), (name, last_meters, meters)
-    got_s = {k: v.detach().cpu() for k, v in student.named_parameters()}
-    got_t = {k: v.detach().cpu() for k, v in teacher.named_parameters()}
-    n_tot = n_bad = 0
-    for k in ps:
-        if ".conv" in k and k.endswith("bias"):
-            assert torch.equal(got_s[k], ps0[k])                  # exact zero gradient: conv biases stay put
-            continue
-        for got, ref in ((got_s[k], ps[k]), (got_t[k], pt[k])):
-            d = (got.double() - ref.double()).abs()
-            assert float(d.max()) <= 2 * N * 1e-3 + 1e-6, k       # nobody travels further than N Adam steps apart
-            n_tot += d.numel()
-            n_bad += int((d > 1e-4).sum())
-    print(f"parameters off by more than 1e-4 after {N} steps: {n_bad} of {n_tot}")
-    assert n_bad <= 0.005 * n_tot
-    for i in range(3):
-        bn = getattr(student.cnn.cnn, f"batchnorm{i}")
-        rv_ref = sbuf[f"cnn.cnn.batchnorm{i}.running_var"]
-        rv_err = ((bn.running_var.cpu().double() - rv_ref.double()).abs() / rv_ref.double().clamp(min=1.0)).max()
-        print(f"batchnorm{i} running_var relative err {float(rv_err):.3e}")
-        assert float(rv_err) <= 3e-3        # two Adam steps of parameter drift on top of the tf32 conv (observed 5e-4)
-        rm = bn.running_mean.cpu() - got_s[f"cnn.cnn.conv{i}.bias"]
-        rm_ref = sbuf[f"cnn.cnn.batchnorm{i}.running_mean"] - ps[f"cnn.cnn.conv{i}.bias"]
-        err = (rm.double() - rm_ref.double()).abs()
-        assert float((err <= 1.3e-3).double().mean()) >= 0.95 and float(err.max()) <= 4e-3, (i, float(err.max()))
+        es, ew = H.maxerr(got_strong, meters["strong"]), H.maxerr(got_weak, meters["weak"])
+        print(f"step {i + 1}: student posteriors (train mode, from waveforms) strong Linf {es:.3e} weak Linf {ew:.3e}")
+        assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
+        for name in ("Loss", "Strong loss", "weak_class_loss", "Consistency strong", "Consistency weak",
+                     "Strong EMA loss", "Weak EMA loss"):
+            assert abs(got_meters[name] - meters[name]) <= 1e-3 * max(1.0, abs(meters[name])), (i, name, got_meters, meters)
+        assert abs(got_meters["Consistency weight"] - cw) <= 1e-6
+        n_tot = n_bad = 0
+        for k in names:
+            if ".conv" in k and k.endswith("bias"):
+                assert torch.equal(got_s[k], snap["ps"][k])           # exact zero gradient: conv biases stay put
+                continue
+            for got, ref in ((got_s[k], o_ps[k]), (got_t[k], o_pt[k])):
+                d = (got.double() - ref.double()).abs()
+                assert float(d.max()) <= 2e-3 + 1e-6, (i, k)          # one Adam step apart at most (+-lr either way)
+                n_tot += d.numel()
+                n_bad += int((d > 1e-4).sum())
+        print(f"step {i + 1}: parameters off by more than 1e-4: {n_bad} of {n_tot}")
+        assert n_bad <= 0.005 * n_tot
+        for got_bn, ref_buf, who in ((got_sbn, snap["sbuf"], "student"), (got_tbn, snap["tbuf"], "teacher")):
+            for j in range(3):
+                rv = got_bn[(2 * j + 1) * 64:(2 * j + 2) * 64].double()
+                rv_ref = ref_buf[f"cnn.cnn.batchnorm{j}.running_var"].double()
+                assert float(((rv - rv_ref).abs() / rv_ref.clamp(min=1.0)).max()) <= 1e-3, (i, who, j)
+                rm = got_bn[(2 * j) * 64:(2 * j + 1) * 64].double()
+                rm_ref = ref_buf[f"cnn.cnn.batchnorm{j}.running_mean"].double()
+                assert float((rm - rm_ref).abs().max()) <= 1e-3, (i, who, j)
+        k0 = "cnn.cnn.conv1.weight"
+        m_err = H.maxerr(got_m[k0], adam["exp_avg"][k0])
+        assert m_err <= 1e-2 * float(adam["exp_avg"][k0].abs().max()), (i, m_err)
+    assert len(eng._graphs) == N and eng.graph_launches > 0
     st = opt.state_dict()["state"]
     assert float(st[0]["step"]) == float(N)
-    k0 = "cnn.cnn.conv1.weight"
-    idx = list(ps.keys()).index(k0)
-    m_err = H.maxerr(st[idx]["exp_avg"].cpu(), adam["exp_avg"][k0])
-    print(f"Adam exp_avg[{k0}] err {m_err:.3e} (max {float(adam['exp_avg'][k0].abs().max()):.3e})")
-    assert m_err <= 2e-2 * float(adam["exp_avg"][k0].abs().max())
 
 
 def test_graph_steps_without_host_sync_match_eager(cuda_device):
