@@ -37,10 +37,18 @@ STEP_FLOPS_PER_CLIP = 4.7232e9
 LAYER_FLOPS_PER_CLIP = {"conv0": 63.70e6, "glu0": 452.98e6, "conv1": 509.61e6, "glu1": 56.62e6,
                         "conv2": 63.70e6, "glu2": 7.08e6}
 MEL_BYTES_PER_CLIP = 441000 * 4 + 864 * 64 * 4
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 24 from the committed `ncu --set full` capture
-# (profiles/r1_ncu_summary_final.csv); bench.py cannot run under ncu, so `roofline.traffic` quotes the capture
-NCU_DRAM_BYTES = {"cnn0_fused_fwd": 5.66e6, "cnn0_fused_bwd": 47.85e6, "stft_mel": 42.47e6, "conv3x3_fwd_l1": 46.59e6,
-                  "conv3x3_dgrad_l1": 46.59e6, "conv3x3_wgrad_l1": 90.74e6, "glu_pool_fwd_l1": 42.53e6}
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 24 of kernel `name`, read at run time from the
+    committed ncu capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` run of
+    tools/profile_step.py; bench.py itself never runs under a profiler) -> (bytes or None, source)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(path))
+        return d["kernels"][name]["bytes_per_launch"], "profiles/ncu_traffic.json <- " + d["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
 
 
 def kernel_flops_per_launch(name, B):
@@ -129,6 +137,7 @@ def cpu_reference_steps(n_steps, n_warmup, clips_per_step, seed=0):
     from oracle import crnn as ocrnn, mel as omel, train_step as otrain
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    ocrnn.FUSED_GRU = True                      # torch's library GRU (as the reference's nn.GRU), not the Python time loop
     nb = clips_per_step
     sizes = [nb // 4, nb // 2, nb - nb // 4 - nb // 2]
     waves, events = synth.make_clips(nb, seed=seed, n_samples=N_SAMPLES)
@@ -155,6 +164,7 @@ def cpu_reference_steps(n_steps, n_warmup, clips_per_step, seed=0):
                  for _ in range(2)]
         for m in masks:
             m["head"] = torch.rand(nb, FRAMES // 8, 128, generator=g) < 0.5
+        # (oracle.crnn.FUSED_GRU: the recurrence through torch's own library GRU, what the reference's nn.GRU runs)
         otrain.train_batch(sp, sbuf, adam, x, target, it, STEPS_PER_EPOCH, teacher_p=tp, teacher_buf=tbuf, x_ema=x_ema,
                            weak_mask=slice(0, sizes[0]), strong_mask=slice(sizes[0] + sizes[1], nb),
                            masks_student=masks[0], masks_teacher=masks[1])
@@ -165,18 +175,23 @@ def cpu_reference_steps(n_steps, n_warmup, clips_per_step, seed=0):
     return nb / mean_t, {"cores": cores, "s_per_step": mean_t, "clips_per_step": nb}
 
 
+CPU_SAMPLE_NOTE = ("restated float64 numpy log-mel recomputed every step from the waveforms (librosa absent; the reference "
+                   "caches its features offline, DatasetDcase2019Task4.py:251-265) + plain-torch CRNN oracle (library "
+                   "GRU) + Adam + EMA, all host threads")
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     import torch  # noqa: F401
-    # bound the run: probe one small step, then size the per-step sample so K+W steps end within ~150 s
+    # the reference batch (24 clips) when K + W steps of it end within ~4 minutes, else the largest multiple of 4 that does
     _, probe = cpu_reference_steps(1, 0, 4)
     per_clip = probe["s_per_step"] / 4
     total_steps = args.steps + args.warmup
-    nb = int(max(4, min(B_PER_GPU, (150.0 / max(total_steps, 1)) / per_clip // 4 * 4)))
+    nb = int(max(4, min(B_PER_GPU, (240.0 / max(total_steps, 1)) / per_clip // 4 * 4)))
     value, info = cpu_reference_steps(args.steps, args.warmup, nb)
-    sample = (f"{args.steps} timed steps of {nb} clips each (reference batch is 24; bounded so the run ends in minutes); "
-              "restated float64 numpy log-mel (librosa absent) + plain-torch CRNN oracle + Adam + EMA")
+    sample = (f"{args.steps} timed steps of {nb} clips each (reference batch is 24"
+              + ("" if nb == B_PER_GPU else "; bounded so the run ends in minutes") + "); " + CPU_SAMPLE_NOTE)
     line = {"impl": "reference", "metric": "mean_teacher_train_clips_per_sec", "value": value, "unit": "clips/s",
             "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * info["s_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -263,9 +278,10 @@ def run_b200(args, rank, local_rank, world):
         r = ramps.sigmoid_rampup(gs, rampup_length) if gs < rampup_length else 1.0
         return cfg.max_consistency_cost * r
 
-    # DCASE_PIPELINE=1 (opt-in, unverified on hardware): the features of batch i + 1 are prepared on a side stream during
-    # iteration i (MeanTeacherEngine.step_pipelined); every batch still goes through every kernel inside the timed region
-    pipeline = os.environ.get("DCASE_PIPELINE", "0") == "1"
+    # the features of batch i + 1 are prepared on a side stream during iteration i (MeanTeacherEngine.step_pipelined:
+    # the STFT runs beside the backward's low-occupancy GRU / head kernels); every batch still goes through every kernel
+    # inside the timed region.  DCASE_PIPELINE=0 selects the plain order (features first, then the iteration).
+    pipeline = os.environ.get("DCASE_PIPELINE", "1") != "0"
     if pipeline:
         engine.prime_features(wave_dev[0], mean, std)
 
@@ -280,49 +296,39 @@ def run_b200(args, rank, local_rank, world):
                                        state["gs"] + 1, check=False)
         state["gs"] += 1
 
-    e2e_mode = {"pcm": os.environ.get("DCASE_E2E_F32", "0") != "1"}
-    prefetchers = {True: HostBatchPrefetcher(dev, (B_PER_GPU, N_SAMPLES), (B_PER_GPU, FRAMES // 8, 10),
-                                             wave_dtype=torch.int16, slots=3),
-                   False: HostBatchPrefetcher(dev, (B_PER_GPU, N_SAMPLES), (B_PER_GPU, FRAMES // 8, 10), slots=3)}
+    def make_e2e(pcm):
+        """Public-API loop with HOST buffers: every step copies its clips (16-bit PCM or float32) and targets from pinned
+        host memory on a copy stream (three staging slots: the batch being trained, the batch whose features are being
+        prepared, the batch being copied), runs the step and reads the meters back (the loss assertion of
+        main.py:147-148).  As in `train`, the assertion on step i is made right after step i + 1 has been enqueued
+        (check=True); the last step of a timed region is drained inside it."""
+        src = wave_host_pcm if pcm else wave_host
+        pf = HostBatchPrefetcher(dev, (B_PER_GPU, N_SAMPLES), (B_PER_GPU, FRAMES // 8, 10),
+                                 wave_dtype=torch.int16 if pcm else torch.float32, slots=3)
 
-    def e2e_step(i, last=True):
-        """Public-API call with HOST buffers: every step copies its clips and targets from pinned host memory
-        (double-buffered on a copy stream, overlapping the previous step's kernels), runs the step and reads the
-        meters back (the loss assertion of main.py:147-148).  As in `train`, the assertion on step i is made right
-        after step i + 1 has been enqueued (check=True); the last step of a timed region is drained inside it."""
-        prefetch = prefetchers[e2e_mode["pcm"]]
-        src = wave_host_pcm if e2e_mode["pcm"] else wave_host
-        if i == 0:
-            prefetch.submit(src[0], target_host[0])
-            prefetch.submit(src[1 % n_pool], target_host[1 % n_pool])
-        prefetch.submit(src[(i + 2) % n_pool], target_host[(i + 2) % n_pool])
-        w, t = prefetch.next()
-        engine.step_from_waveforms(w, t, mean, std, cons_weight(), state["gs"] + 1, check=True)
-        prefetch.release()
-        state["gs"] += 1
-        if last:
-            engine.check_loss()                                     # syncs on the 32-byte meter copy
-
-    if pipeline:
-        # pipelined variant of the same public-API loop: three staging slots (the batch being trained, the batch whose
-        # features are being prepared, the batch being copied); batch j's waveform is read one call before its targets
-        prefetch3 = HostBatchPrefetcher(dev, (B_PER_GPU, N_SAMPLES), (B_PER_GPU, FRAMES // 8, 10), slots=3)
-
-        def e2e_step(i, last=True):                                 # noqa: F811  (replaces the plain loop above)
+        def step(i, last=True):
             if i == 0:
-                prefetch3.submit(wave_host[0], target_host[0])
-                prefetch3.submit(wave_host[1 % n_pool], target_host[1 % n_pool])
-                w0, _ = prefetch3.next()
-                engine.prime_features(w0, mean, std)
-            prefetch3.submit(wave_host[(i + 2) % n_pool], target_host[(i + 2) % n_pool])
-            _, t = prefetch3.next()
-            w_next, _, ready = prefetch3.peek(1)
-            engine.step_pipelined(w_next, t, mean, std, cons_weight(), state["gs"] + 1, check=True,
-                                  wave_ready_event=ready)
-            prefetch3.release()
+                pf.submit(src[0], target_host[0])
+                pf.submit(src[1 % n_pool], target_host[1 % n_pool])
+                if pipeline:
+                    w0, _ = pf.next()
+                    engine.prime_features(w0, mean, std)
+            pf.submit(src[(i + 2) % n_pool], target_host[(i + 2) % n_pool])
+            w, t = pf.next()
+            if pipeline:                                  # batch j's waveform is read one call before its targets
+                w_next, _, ready = pf.peek(1)
+                engine.step_pipelined(w_next, t, mean, std, cons_weight(), state["gs"] + 1, check=True,
+                                      wave_ready_event=ready)
+            else:
+                engine.step_from_waveforms(w, t, mean, std, cons_weight(), state["gs"] + 1, check=True)
+            pf.release()
             state["gs"] += 1
             if last:
-                engine.check_loss()
+                engine.check_loss()                       # syncs on the 32-byte meter copy
+        return step
+
+    e2e_pcm = os.environ.get("DCASE_E2E_F32", "0") != "1"
+    e2e_step = make_e2e(e2e_pcm)
 
     def barrier():
         if world > 1:
@@ -356,20 +362,19 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- end-to-end through the public API with host buffers ----
     n_prime = 7 if pipeline else 4               # primes the copy pipeline and captures every staging-buffer graph
-    for i in range(n_prime):                      # (plain: 3 buffers; pipelined: 3 staging x 2 feature slots = 6)
+    for i in range(n_prime):                      # (plain: 3 staging buffers; pipelined: 3 staging x 2 feature slots = 6)
         e2e_step(i)
     ms_e2e = timed(lambda i: e2e_step(i + n_prime, last=(i == args.steps - 1)), args.steps)
     e2e_value = world * B_PER_GPU * args.steps / (ms_e2e * 1e-3)
-    e2e_wave_bytes = 2 if e2e_mode["pcm"] else 4
+    e2e_wave_bytes = 2 if e2e_pcm else 4
     e2e_f32 = None
-    if not pipeline and e2e_mode["pcm"]:          # the same loop shipping float32 waveforms, for comparison
-        e2e_mode["pcm"] = False
+    if e2e_pcm:                                   # the same loop shipping float32 waveforms, for comparison
+        f32_step = make_e2e(False)
         for i in range(n_prime):
-            e2e_step(i)
-        ms_f32 = timed(lambda i: e2e_step(i + n_prime, last=(i == args.steps - 1)), args.steps)
+            f32_step(i)
+        ms_f32 = timed(lambda i: f32_step(i + n_prime, last=(i == args.steps - 1)), args.steps)
         e2e_f32 = {"value": world * B_PER_GPU * args.steps / (ms_f32 * 1e-3), "ms_per_step": ms_f32 / args.steps,
                    "h2d_bytes_per_step": B_PER_GPU * N_SAMPLES * 4 + B_PER_GPU * (FRAMES // 8) * 10 * 4}
-        e2e_mode["pcm"] = True
 
     # ---- per-kernel durations (CUDA events on the launching stream, separate pass) ----
     use_graph, engine.use_graph = engine.use_graph, False        # per-kernel events need eager launches
@@ -391,9 +396,8 @@ def run_b200(args, rank, local_rank, world):
         roof = {"bound": "tensor", "achieved": dom_flops / dom_avg_s / 1e12, "peak": peaks["tf_sustained"],
                 "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    traffic = NCU_DRAM_BYTES.get(dom_name)
-    roof.update({"traffic": traffic * (B_PER_GPU / 24.0) if traffic else None,
-                 "traffic_source": "profiles/r1_ncu_summary_final.csv (ncu --set full, bytes per launch)" if traffic else None,
+    traffic, traffic_src = ncu_traffic(dom_name)
+    roof.update({"traffic": traffic * (B_PER_GPU / 24.0) if traffic else None, "traffic_source": traffic_src,
                  "kernel": dom_name, "kernel_ms": dom_ms / dom_cnt,
                  "kernel_share_of_step": dom_ms / total_prof, "peak_source": peaks["source"] + " (sustained bf16 dense)",
                  "step_tensor_frac": (value / world) * STEP_FLOPS_PER_CLIP / 1e12 / peaks["tf_sustained"],
@@ -403,15 +407,14 @@ def run_b200(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, info = cpu_reference_steps(1, 0, B_PER_GPU)
         cpu = {"value": v, "unit": "clips/s", "cores": info["cores"], "kind": "port",
-               "sample": "1 mean-teacher step on 24 clips (%.1f s): restated float64 numpy log-mel (librosa absent) + "
-                         "plain-torch CRNN oracle + Adam + EMA, all host threads" % info["s_per_step"]}
+               "sample": "1 mean-teacher step on 24 clips (%.1f s): %s" % (info["s_per_step"], CPU_SAMPLE_NOTE)}
 
     if rank == 0:
         line = {"metric": "mean_teacher_train_clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world,
                 "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
                 "config": {"workload": workload_name(), "global_batch": world * B_PER_GPU, "frames": FRAMES,
-                           "parallelism": dp_mode,
+                           "parallelism": dp_mode, "pipelined_features": pipeline,
                            "l2": "inputs larger than L2: rotating pool of 6 waveform batches (254 MB) per GPU, "
                                  "plus ~400 MB of activations rewritten every step"},
                 "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,

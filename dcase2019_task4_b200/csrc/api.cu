@@ -443,7 +443,9 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
     // (4 split-K GEMMs + 4 column sums per layer) run on the context's second stream beside the next layer's recurrence
     // (latency bound, 48 CTAs) and are joined at the end of the backward.
     const char* sv[2][5] = {{"s0_r", "s0_z", "s0_n", "s0_hn", "s0_hp"}, {"s1_r", "s1_z", "s1_n", "s1_hn", "s1_hp"}};
-    cudaStream_t aux = ctx->aux_stream;
+    // while per-kernel profiling is on, everything runs on ONE stream so that the event-bracketed durations are the
+    // kernels' own (two overlapping kernels would each be charged the other's time)
+    cudaStream_t aux = g_prof_on ? s : ctx->aux_stream;
     for (int l = 1; l >= 0; --l) {
         const int nin = l == 0 ? kC : 2 * kH;
         float* dgi = wsp<float>(ws, L, l == 1 ? "dgi1" : "dgi0");
@@ -565,11 +567,12 @@ int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* a, void* stream) {
         // the teacher forward (no grad, main.py:87-89) is independent of the student forward until the losses:
         // fork it onto the context's second stream so the two overlap (latency-bound GRU / single-CTA kernels)
         DCASE_REQUIRE(a->params_t && a->bn_t && a->strong_t && a->weak_t && a->ws_t, "teacher buffers missing");
+        cudaStream_t ts = g_prof_on ? s : ctx->aux_stream;      // profiling: one stream, isolated kernel durations
         DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
-        DCASE_CUDA_CHECK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+        DCASE_CUDA_CHECK(cudaStreamWaitEvent(ts, ctx->ev_fork, 0));
         DCASE_TRY(dcase_crnn_forward(ctx, a->x_teacher, a->B, a->T, a->n_class, a->params_t, a->bn_t, a->flags, a->seed,
-                                     a->step, 1, a->scalars, a->strong_t, a->weak_t, a->ws_t, ctx->aux_stream));
-        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+                                     a->step, 1, a->scalars, a->strong_t, a->weak_t, a->ws_t, ts));
+        DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_join, ts));
     }
     DCASE_TRY(dcase_crnn_forward(ctx, a->x_student, a->B, a->T, a->n_class, a->params_s, a->bn_s, a->flags, a->seed,
                                  a->step, 0, a->scalars, a->strong_s, a->weak_s, a->ws_s, stream));

@@ -334,12 +334,12 @@ class MeanTeacherEngine(object):
             x, x_ema = K.logmel_finish(amp, mean, std, self.T, out_clean=self._x), None
         self.step(x, x_ema, target, cons_weight, global_step_after, check=check)
 
-    # ---- features one step ahead (opt-in; see ROUND2_PLAN.md) ---------------------------------------------------
+    # ---- features one step ahead -------------------------------------------------------------------------------
     # The log-mel phase of a batch does not depend on the model, and the backward spends ~260 us in kernels that occupy
     # 24-48 CTAs (GRU BPTT, head, loss) while the STFT launches thousands: ``step_pipelined`` runs the iteration on the
     # features already sitting in the current slot and, on a side stream, prepares the features of the NEXT batch into
     # the other slot.  Same kernels, same Philox (seed, step) per batch as ``step_from_waveforms``; only the order of
-    # launches differs.  UNVERIFIED on hardware (written after round 1's GPU budget was spent).
+    # launches differs (tests/test_gpu_api.py::test_pipelined_features_match_plain_steps).
     def _feature_slots(self):
         if getattr(self, "_xp", None) is None:
             f32 = dict(device=self.dev, dtype=torch.float32)
@@ -410,8 +410,10 @@ class MeanTeacherEngine(object):
             if entry is None:
                 graph = torch.cuda.CUDAGraph()
                 l0 = K.launch_count()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
                     cap = torch.cuda.current_stream(self.dev)
+                    if self.p2p is not None:
+                        self.p2p.begin_step()
                     self._fork_handle = self._fwd_done.cuda_event
                     try:
                         K.mt_fwd_bwd(self._mt_args(xp[slot], xpe[slot], target, model.forward_flags(), 0, 0, 0.0,
@@ -422,9 +424,14 @@ class MeanTeacherEngine(object):
                     with torch.cuda.stream(self._side):
                         amp = K.logmel_fwd(wave_next)
                         self._finish_into(amp, mean, std, nxt, step=1, scalars=self._sc_dev)   # next iteration's noise
-                    K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
-                                    ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
-                                    beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
+                    if self.p2p is not None:
+                        self.p2p.adam_ema_step(model.flat_parameters(), self.m, self.v,
+                                               ema.flat_parameters() if ema is not None else None, 0, g["lr"],
+                                               g["betas"][0], g["betas"][1], g["eps"], 0.0, scalars=self._sc_dev)
+                    else:
+                        K.adam_ema_step(model.flat_parameters(), self.grads, self.m, self.v,
+                                        ema.flat_parameters() if ema is not None else None, 0, lr=g["lr"],
+                                        beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"], scalars=self._sc_dev)
                     cap.wait_stream(self._side)
                 entry = (graph, K.launch_count() - l0)
                 self._cache_put(self._pgraphs, key, entry)

@@ -109,7 +109,23 @@ def gru_direction(x, w_ih, w_hh, b_ih, b_hh, reverse):
     return torch.stack(outs, dim=1)
 
 
+FUSED_GRU = False     # bench.py's CPU arm sets this: same recurrence through torch's library GRU (as nn.GRU runs it)
+
+
+def bigru_fused(x, p, n_layers=2):
+    """The whole bidirectional stack through ``torch._VF.gru`` -- the routine ``nn.GRU.forward`` calls (RNN.py:12-15):
+    same weights, same gate order, h0 = 0; used where speed matters (the CPU baseline), checked against the explicit
+    loop below in tests/test_oracle_golden.py."""
+    flat = [p[f"rnn.rnn.{n}_l{layer}{suf}"] for layer in range(n_layers) for suf in ("", "_reverse")
+            for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    h0 = x.new_zeros(2 * n_layers, x.shape[0], flat[1].shape[1])
+    out, _ = torch._VF.gru(x, h0, flat, True, n_layers, 0.0, False, True, True)
+    return out
+
+
 def bigru(x, p, n_layers=2):
+    if FUSED_GRU:
+        return bigru_fused(x, p, n_layers)
     for layer in range(n_layers):
         outs = []
         for suf, rev in (("", False), ("_reverse", True)):

@@ -161,3 +161,21 @@ def test_step_oracle_matches_reference_train_fixture():
         assert np.abs(flat[::stride] - z[key])[keep].max() <= 1e-4
     for i in range(3):
         assert np.abs(sbuf["cnn.cnn.batchnorm%d.running_var" % i].numpy() - z["running_var%d" % i]).max() <= 1e-5
+
+
+def test_fused_library_gru_matches_the_explicit_recurrence():
+    """bench.py's CPU arm runs the BiGRU through torch's library routine (``oracle.crnn.bigru_fused``, what the
+    reference's nn.GRU calls, RNN.py:12-15); it must be the same function as the explicit (r, z, n) loop the parity tests
+    use -- outputs and gradients."""
+    import torch
+    from oracle import crnn as ocrnn
+    p = ocrnn.init_params(seed=3)
+    x = torch.randn(5, 27, 64, generator=torch.Generator().manual_seed(1))
+    a, b = ocrnn.bigru(x, p), ocrnn.bigru_fused(x, p)
+    assert float((a - b).abs().max()) <= 2e-6
+    sp = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    names = [k for k in sp if k.startswith("rnn.")]
+    g1 = torch.autograd.grad(ocrnn.bigru(x, sp).pow(2).sum(), [sp[k] for k in names])
+    g2 = torch.autograd.grad(ocrnn.bigru_fused(x, sp).pow(2).sum(), [sp[k] for k in names])
+    for k, u, v in zip(names, g1, g2):
+        assert float((u - v).abs().max()) <= 1e-5 * max(1.0, float(u.abs().max())), k
