@@ -29,6 +29,23 @@ namespace {
 constexpr int kTile = 128;
 constexpr float kTruncComp = 1.f + 3.5221e-4f;
 constexpr float kLog2e = 1.4426950408889634f;
+// The gate sigmoid(y) is the block's MUFU load (84.9 M activations per pass).  The tensor core produces a pre-scaled
+// ys = kGateScale * y directly (W0 carries the factor; y itself only feeds MMA1, lin = y Wg^T, whose constant operand Wg
+// carries the inverse factor), so no multiply per element is spent on the argument:
+//   DCASE_GATE_TANH (default): ys = y / 2,        g = 0.5 tanh.approx(ys) + 0.5       1 MUFU + 1 FFMA per element
+//   otherwise:                 ys = -log2(e) y,   g = rcp(1 + ex2(ys))                2 MUFU + 1 FADD per element
+// tanh.approx.f32 has a relative error of up to 2^-11 (|dg| <= 2.4e-4); measured effect on the frame posteriors:
+// tests/test_gpu_fullsize.py prints it, tools/precision_modes.py models it.
+#ifndef DCASE_GATE_TANH
+#define DCASE_GATE_TANH 1
+#endif
+#if DCASE_GATE_TANH
+constexpr float kGateScale = 0.5f;
+constexpr float kGateUnscale = 2.0f;
+#else
+constexpr float kGateScale = -kLog2e;
+constexpr float kGateUnscale = -0.6931471805599453f;
+#endif
 
 struct Cnn0Args {
     const float* x;        // [B][T][64] z-scored log-mel
@@ -129,7 +146,7 @@ __device__ __forceinline__ void write_taps(const float* xs, int row, uint32_t t0
 __device__ __forceinline__ void stage_wg(const float* __restrict__ glu_w, unsigned char* Wb, int t, int nt) {
     for (int i = t; i < 4096; i += nt) {
         const int n = i >> 6, k = i & 63;
-        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kTruncComp * __ldg(glu_w + i));
+        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kGateUnscale * kTruncComp * __ldg(glu_w + i));
     }
 }
 
@@ -141,7 +158,7 @@ __device__ __forceinline__ void stage_w0(const float* __restrict__ fold0, unsign
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int k = 4 * c + e;
-            v[e] = k < 9 ? __ldg(fold0 + kFold0Wf + k * 64 + n) : (k == 9 ? __ldg(fold0 + kFold0Bf + n) : 0.f);
+            v[e] = kGateScale * (k < 9 ? __ldg(fold0 + kFold0Wf + k * 64 + n) : (k == 9 ? __ldg(fold0 + kFold0Bf + n) : 0.f));
         }
         *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(n, 4 + c)) = tc::tf32_rn4(make_float4(v[0], v[1], v[2], v[3]));
     }
@@ -171,12 +188,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     tc::tmem_ld_wait();
 }
 
-// g[i] = sigmoid(y[i]) for 32 values: all ex2 first, then all rcp (independent MUFU streams)
+// g[i] = sigmoid(y[i]) for 32 values of the pre-scaled ys (see kGateScale)
 __device__ __forceinline__ void sigmoid32(const float (&y)[32], float (&g)[32]) {
+#if DCASE_GATE_TANH
 #pragma unroll
-    for (int i = 0; i < 32; ++i) g[i] = ex2_ftz(-kLog2e * y[i]);
+    for (int i = 0; i < 32; ++i) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y[i]));
+        g[i] = fmaf(t, 0.5f, 0.5f);
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < 32; ++i) g[i] = ex2_ftz(y[i]);
 #pragma unroll
     for (int i = 0; i < 32; ++i) g[i] = rcp_ftz(1.f + g[i]);
+#endif
 }
 
 __device__ __forceinline__ void require_aligned_smem(const void* p) {

@@ -111,7 +111,7 @@ template <int PITCH>
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_constant__ CUtensorMap in_map2, int B, int T_l, int F,
                    const float* __restrict__ w_img,
-                   const float* __restrict__ bias, float* __restrict__ out) {
+                   const float* __restrict__ bias, float* __restrict__ out, double* __restrict__ stats) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* Wi = smem;                               // 144 KB
     unsigned char* units = smem + kWImgBytes;               // kUnits x 24 KB (1024-B aligned)
@@ -223,6 +223,11 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
         const int wq = warp & 3;                   // TMEM lane quadrant of this warp
         const uint32_t stage_a = tc::smem_u32(stage_base) + (uint32_t)wq * 2048u;
         int it = 0;
+        // BatchNorm batch statistics of the output (CNN.py:49) ride in the epilogue: in the read-back loop below a lane
+        // always sees the same 16-byte channel chunk (lane & 7), so it keeps that chunk's sum / sum of squares for both
+        // channel halves in 16 registers over its whole tile stream (fp32 over ~300 values, then fp64 atomics)
+        float4 bs[2], bq[2];
+        bs[0] = bs[1] = bq[0] = bq[1] = make_float4(0.f, 0.f, 0.f, 0.f);
 #ifdef DCASE_CONV_TIMING
         long long t_wait = 0, t_ld = 0, t_st = 0, tt;
         const long long t_begin = clock64();
@@ -265,8 +270,12 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
                         const float4 v = ld_shared_v4(stage_a + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4));
                         const int prow = 32 * wq + 16 * rh + r;                // pixel row of the tile
                         const int t = g.t0 + (prow >> 3), f = g.f0 + (prow & 7);
-                        if (t < T_l && f < F)
+                        if (t < T_l && f < F) {
                             *reinterpret_cast<float4*>(out + (((long long)g.b * T_l + t) * F + f) * 64 + 32 * ch + 4 * c) = v;
+                            bs[ch].x += v.x; bs[ch].y += v.y; bs[ch].z += v.z; bs[ch].w += v.w;
+                            bq[ch].x = fmaf(v.x, v.x, bq[ch].x); bq[ch].y = fmaf(v.y, v.y, bq[ch].y);
+                            bq[ch].z = fmaf(v.z, v.z, bq[ch].z); bq[ch].w = fmaf(v.w, v.w, bq[ch].w);
+                        }
                     }
                     __syncwarp();
                 }
@@ -277,32 +286,32 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
         if (blockIdx.x == 3 && tid == 64)
             printf("epilogue: total %lld  wait acc_full %lld  ldtm %lld  stores %lld  tiles %d\n", clock64() - t_begin, t_wait, t_ld, t_st, it);
 #endif
+        if (stats) {
+            // lanes with equal (lane & 7) hold the same channels: fold over lane bits 3, 4; lanes 0..7 then park the warp's
+            // 128 partials in its staging tile, the four epilogue warps meet, and thread e adds entry e of all four
+            float part[16] = {bs[0].x, bs[0].y, bs[0].z, bs[0].w, bs[1].x, bs[1].y, bs[1].z, bs[1].w,
+                              bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                part[i] += __shfl_xor_sync(0xffffffffu, part[i], 8);
+                part[i] += __shfl_xor_sync(0xffffffffu, part[i], 16);
+            }
+            float* mine = reinterpret_cast<float*>(stage_base + wq * 2048);
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)      // entry = (sum | sumsq) * 64 + channel, channel = 32 ch + 4 (lane & 7) + e
+                    mine[(i >> 3) * 64 + ((i >> 2) & 1) * 32 + 4 * lane + (i & 3)] = part[i];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int e = 32 * wq + lane;
+            const float* all = reinterpret_cast<const float*>(stage_base);
+            const double tot = (double)all[e] + (double)all[512 + e] + (double)all[1024 + e] + (double)all[1536 + e];
+            atomicAdd(stats + e, tot);                 // [0,64): sum, [64,128): sum of squares
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem, 128);
-}
-
-// per-channel sum and sum of squares of a [n_pix][64] tensor (BatchNorm batch statistics, fp64 accumulation)
-__global__ void __launch_bounds__(256)
-bn_stats_kernel(const float* __restrict__ y, long long n_pix, double* __restrict__ stats) {
-    __shared__ float red[16][128];
-    const int cq = threadIdx.x & 15, rl = threadIdx.x >> 4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-    for (long long r = (long long)blockIdx.x * 16 + rl; r < n_pix; r += (long long)gridDim.x * 16) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(y) + r * 16 + cq);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
-    }
-    float* row = red[rl];
-    row[4 * cq] = s.x; row[4 * cq + 1] = s.y; row[4 * cq + 2] = s.z; row[4 * cq + 3] = s.w;
-    row[64 + 4 * cq] = q.x; row[64 + 4 * cq + 1] = q.y; row[64 + 4 * cq + 2] = q.z; row[64 + 4 * cq + 3] = q.w;
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        double t = 0.0;
-        for (int i = 0; i < 16; ++i) t += (double)red[i][threadIdx.x];
-        atomicAdd(stats + threadIdx.x, t);             // [0,64): sum, [64,128): sum of squares
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -459,17 +468,11 @@ int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, c
     const int pitch = F == 16 ? 10 : 8;
     DCASE_TRY_RC(make_act_map(&in_map4, in, B, T_l, F, 4, pitch, CU_TENSOR_MAP_SWIZZLE_128B));
     DCASE_TRY_RC(make_act_map(&in_map2, in, B, T_l, F, 2, pitch, CU_TENSOR_MAP_SWIZZLE_128B));
-    if (F == 16) conv3x3_tma_kernel<10><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out);
-    else conv3x3_tma_kernel<8><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out);
+    // BatchNorm batch statistics ([64] sums | [64] sums of squares, fp64) are accumulated by the conv epilogue itself
+    if (stats) DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
+    if (F == 16) conv3x3_tma_kernel<10><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out, stats);
+    else conv3x3_tma_kernel<8><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out, stats);
     DCASE_LAUNCH_CHECK();
-    if (stats) {
-        DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
-        const long long n_pix = (long long)B * T_l * F;
-        long long blocks = (n_pix + 63) / 64;             // >= 4 rows per row-lane even for the small block-2 tensor
-        if (blocks > num_sms * 4) blocks = num_sms * 4;
-        bn_stats_kernel<<<(int)blocks, 256, 0, s>>>(out, n_pix, stats);
-        DCASE_LAUNCH_CHECK();
-    }
     return DCASE_OK;
 }
 

@@ -153,6 +153,7 @@ def test_three_graph_steps_from_waveforms_match_oracle(cuda_device):
         got_t = H.unflat_params(teacher.flat_parameters().detach().cpu().clone())
         got_sbn, got_tbn = student.flat_bn_running().detach().cpu().clone(), teacher.flat_bn_running().detach().cpu().clone()
         got_m = H.unflat_params(eng.m.detach().cpu().clone())
+        got_x, got_xe = eng._x.cpu().numpy(), eng._x_ema.cpu().numpy()
 
         o_ps = {k: v.clone().contiguous() for k, v in snap["ps"].items()}
         o_pt = {k: v.clone().contiguous() for k, v in snap["pt"].items()}
@@ -163,13 +164,25 @@ def test_three_graph_steps_from_waveforms_match_oracle(cuda_device):
         feats = [omel.transform_chain(mels[b], mean, std, noise=noise[b], frames=T) for b in range(B)]
         x = torch.from_numpy(np.stack([f[0] for f in feats]))          # [B, 1, T, 64]
         xe = torch.from_numpy(np.stack([f[1] for f in feats]))
+        with torch.no_grad():                                         # the CRNN alone, on the device's own features
+            s_f, w_f = ocrnn.crnn_forward(torch.from_numpy(got_x)[:, None], o_ps, copy.deepcopy(snap["sbuf"]), True,
+                                          H.oracle_masks(B, T, seed, step, 0))
+        es_f, ew_f = H.maxerr(got_strong, s_f), H.maxerr(got_weak, w_f)
         meters, _ = otrain.train_batch(o_ps, snap["sbuf"], adam, x, tgt[i], i, steps_per_epoch, teacher_p=o_pt,
                                        teacher_buf=snap["tbuf"], x_ema=xe, weak_mask=wm, strong_mask=sm,
                                        masks_student=H.oracle_masks(B, T, seed, step, 0),
                                        masks_teacher=H.oracle_masks(B, T, seed, step, 1))
         es, ew = H.maxerr(got_strong, meters["strong"]), H.maxerr(got_weak, meters["weak"])
-        print(f"step {i + 1}: student posteriors (train mode, from waveforms) strong Linf {es:.3e} weak Linf {ew:.3e}")
-        assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
+        ex = float(np.abs(got_x - x.numpy()[:, 0]).max())
+        print(f"step {i + 1}: features Linf {ex:.3e} (z-scored dB); student posteriors (train mode, dropout on) from "
+              f"waveforms: strong Linf {es:.3e} weak Linf {ew:.3e}; from the device's own features: strong {es_f:.3e} "
+              f"weak {ew_f:.3e}")
+        # the CRNN given identical features: the north star's 1e-3.  End to end the fp32 FFT's feature error (up to 1e-3
+        # z-scored units on the quietest bins, tests/test_gpu_logmel.py) is amplified by the inverted dropout (x2 per
+        # block, no averaging over masked neighbours): 2.5e-3 in TRAIN mode; the eval-mode end-to-end bound is 1e-3
+        # (test_eval_posteriors_from_waveforms_at_baseline_size)
+        assert es_f <= POSTERIOR_TOL and ew_f <= POSTERIOR_TOL
+        assert ex <= 2e-3 and es <= 2.5e-3 and ew <= 2.5e-3
         for name in ("Loss", "Strong loss", "weak_class_loss", "Consistency strong", "Consistency weak",
                      "Strong EMA loss", "Weak EMA loss"):
             assert abs(got_meters[name] - meters[name]) <= 1e-3 * max(1.0, abs(meters[name])), (i, name, got_meters, meters)
@@ -200,6 +213,37 @@ def test_three_graph_steps_from_waveforms_match_oracle(cuda_device):
     assert len(eng._graphs) == N and eng.graph_launches > 0
     st = opt.state_dict()["state"]
     assert float(st[0]["step"]) == float(N)
+
+
+def test_eval_posteriors_from_waveforms_at_baseline_size(K, cuda_device):
+    """The north star's criterion end to end: waveform -> log-mel -> z-score -> CRNN in EVAL mode (the validation path,
+    evaluation_measures.py:203-214) at 24 clips x 441,000 samples vs ``oracle.mel`` + ``oracle.crnn``: frame
+    posteriors within 1e-3 abs."""
+    from dcase2019_task4_b200 import synth
+    dev = cuda_device
+    L = 441000
+    waves, _ = synth.make_clips(B, seed=91, n_samples=L)
+    mean = np.full(64, -32.0) + np.linspace(-6, 6, 64)
+    std = np.full(64, 11.0) + np.linspace(0, 4, 64)
+    p = ocrnn.init_params(seed=7)
+    buf = ocrnn.init_buffers()
+    g = torch.Generator().manual_seed(17)
+    for i in range(3):
+        buf[f"cnn.cnn.batchnorm{i}.running_mean"] = 0.2 * torch.randn(64, generator=g)
+        buf[f"cnn.cnn.batchnorm{i}.running_var"] = 0.5 + torch.rand(64, generator=g)
+    fb = omel.mel_filterbank()
+    x = np.stack([omel.transform_chain(omel.calculate_mel_spec(w.astype(np.float64), fb), mean, std, frames=T)[0]
+                  for w in waves])
+    with torch.no_grad():
+        s_ref, w_ref = ocrnn.crnn_forward(torch.from_numpy(x), p, buf, training=False)
+    amp = K.logmel_fwd(torch.from_numpy(waves).to(dev))
+    xd = K.logmel_finish(amp, torch.from_numpy(mean.astype(np.float32)).to(dev),
+                         torch.from_numpy(std.astype(np.float32)).to(dev), T)
+    s, w = K.crnn_forward(xd, H.flat_params(p).to(dev), H.bn_running_flat(buf).to(dev), 0, K.new_workspace(B, T, 10, dev))
+    es, ew = H.maxerr(s.cpu(), s_ref), H.maxerr(w.cpu(), w_ref)
+    print(f"eval from waveforms, B=24: features Linf {float(np.abs(xd.cpu().numpy() - x[:, 0]).max()):.3e}, "
+          f"strong Linf {es:.3e} weak Linf {ew:.3e}")
+    assert es <= POSTERIOR_TOL and ew <= POSTERIOR_TOL
 
 
 def test_graph_steps_without_host_sync_match_eager(cuda_device):
