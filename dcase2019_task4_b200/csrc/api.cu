@@ -124,7 +124,7 @@ WsLayout ws_layout(int B, int T, int NC) {
     const size_t BT = (size_t)B * (T / 8);
     const size_t n0 = (size_t)B * (T / 2) * 16 * 64;   // out0 / ypre1 elements
     const size_t n1 = (size_t)B * (T / 4) * 4 * 64;    // out1 / ypre2
-    add("mom0", 56, sizeof(double));        // 54 tap moments + completion ticket of the moments kernel
+    add("mom0", 54, sizeof(double));
     add("stats1", 128, sizeof(double));
     add("stats2", 128, sizeof(double));
     add("fold0", kFold0Size);
@@ -297,12 +297,9 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     double* mom0 = wsp<double>(ws, L, "mom0");
     float* fold0 = wsp<float>(ws, L, "fold0");
     const long long n_pix0 = (long long)B * T * 64;
-    if (training)
-        DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
-                                      params + o.bn_b[0], bn_running, fold0, sms, s));
-    else
-        DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
-                                      params + o.bn_b[0], bn_running, training, fold0, s));
+    if (training) DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, sms, s));
+    DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
+                                  params + o.bn_b[0], bn_running, training, fold0, s));
     float* out0 = wsp<float>(ws, L, "out0");
     DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), out0, sms, s));
 

@@ -28,9 +28,7 @@ struct DropoutCfg {
     const DcaseStepScalars* sc;  // if non-null overrides seed/step (CUDA-graph replay)
 };
 
-// training: tap moments of the input AND (last block) the BN fold of block 0; eval: launch_bn0_finalize alone
-int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* conv_w, const float* conv_b,
-                        const float* gamma, const float* beta, float* running, float* fold0, int num_sms, cudaStream_t s);
+int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, cudaStream_t s);
 int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running /*[2][64]*/, int training,
                         float* fold0, cudaStream_t s);

@@ -182,6 +182,17 @@ __device__ __forceinline__ void issue_mma1(uint32_t d_tmem, uint32_t a_addr, uin
                             idesc, j > 0 ? 1u : 0u);
 }
 
+// lin = y Wg^T with y read IN PLACE from the MMA0 accumulator in tensor memory (an M = 128 accumulator has exactly the
+// [lane = row][column = k] layout of a TMEM A operand): no shared-memory round trip for y, and the GEMM can be issued the
+// moment MMA0 has completed, before any thread has touched y
+__device__ __forceinline__ void issue_mma1_tmem(uint32_t d_tmem, uint32_t y_tmem, uint32_t wb_addr) {
+    constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+    const uint32_t b_lo = tc::desc_lo(wb_addr, 16), hi = tc::desc_hi(1024, 2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        tc::umma_tf32_tmem_a_elect(d_tmem, y_tmem + 8 * j, b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, j > 0 ? 1u : 0u);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     tc::tmem_ld16(taddr, v);
     tc::tmem_ld16(taddr + 16, v + 16);
@@ -309,22 +320,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
         TICK();
         ph0 ^= 1;
         tc::fence_after_sync();
-        uint32_t keep_hi_next = 0xffffffffu;
-        if (has_next) {
-            xs_commit(xr, xs, tid);
-            __syncthreads();
-            if (half == 0) write_taps(xs, row, t0_rb);
-            else if (drop) {
-                const uint4 r = philox4x32_10((uint64_t)(nxt * kTile + row), a.drop.stream, step, seed);
-                keep_lo[row] = r.x;
-                keep_hi_next = r.y;
-            }
-            pos.advance(pos_step, a.T);
-            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, pos, a.T, tid);
-        }
-        TOCK(1);
-        TICK();
-        if (prev >= 0) {                          // pooled tile `prev`: TMEM -> out; also frees the z buffer
+        if (prev >= 0) {                          // pooled tile `prev`: TMEM -> out; frees the lin columns and the z buffer
             tc::mbar_wait(&bars[2], ph2);
             ph2 ^= 1;
             tc::fence_after_sync();
@@ -341,27 +337,44 @@ cnn0_fwd_kernel(Cnn0Args a) {
         }
         TOCK(2);
         TICK();
+        if (has_next) xs_commit(xr, xs, tid);
+        tc::fence_before_sync();
+        __syncthreads();                          // the pooled tile has been read by everybody; xs of `nxt` is complete
+        TOCK(1);
+        TICK();
+        if (warp == 0) {                          // MMA1 runs under the gate phase below: y is read from tensor memory
+            tc::fence_after_sync();
+            issue_mma1_tmem(tmem + 64, tmem, wb_a);
+            tc::umma_commit_elect(&bars[1]);
+        }
+        uint32_t keep_hi_next = 0xffffffffu;
+        if (has_next) {
+            if (half == 0) write_taps(xs, row, t0_rb);
+            else if (drop) {
+                const uint4 r = philox4x32_10((uint64_t)(nxt * kTile + row), a.drop.stream, step, seed);
+                keep_lo[row] = r.x;
+                keep_hi_next = r.y;
+            }
+            pos.advance(pos_step, a.T);
+            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, pos, a.T, tid);
+        }
         float g[32];
         {
             float y[32];
             tmem_ld32(tmem + lane_base + 32 * half, y);
             tc::fence_before_sync();
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                sts128(chunk_addr(y_rb, 8 * half + q), y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
             sigmoid32(y, g);
         }
-        tc::fence_proxy_async();
+        tc::fence_proxy_async();                  // the taps of `nxt`
         TOCK(3);
         TICK();
-        __syncthreads();
+        __syncthreads();                          // everybody holds its y: MMA0 of `nxt` may overwrite the columns
         TOCK(4);
         TICK();
-        if (warp == 0) {
+        if (warp == 0 && has_next) {
             tc::fence_after_sync();
-            issue_mma1(tmem + 64, a_a, wb_a);
-            tc::umma_commit_elect(&bars[1]);
-            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
+            issue_mma0(tmem, t0_a);
+            tc::umma_commit_elect(&bars[0]);
         }
         if (drop) {
 #pragma unroll
@@ -522,6 +535,11 @@ cnn0_bwd_kernel(Cnn0Args a) {
         const uint32_t keep = keep_next;
         tc::mbar_wait(&bars[0], ph0);            // y of `cur` is in TMEM; T0 may be read / rewritten
         ph0 ^= 1;
+        tc::fence_after_sync();
+        if (issuer) {                             // MMA1 straight away: y is read from tensor memory, and the lin columns
+            issue_mma1_tmem(tmem + 64, tmem, wb_a);   // were drained by every thread before the previous tile's last barrier
+            tc::umma_commit_elect(&bars[1]);
+        }
         if (pending) { tc::mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }   // E / DL / D2 free again
         tc::fence_after_sync();
         if (half == 0) {                          // E (MN-major copy of this tile's operand rows) for MMA3
@@ -549,18 +567,14 @@ cnn0_bwd_kernel(Cnn0Args a) {
             float y[32];
             tmem_ld32(tmem + lane_base + 32 * half, y);
             tc::fence_before_sync();
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                sts128(chunk_addr(y_rb, 8 * half + q), y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
             sigmoid32(y, g);
         }
         tc::fence_proxy_async();
-        bar_sync_named(bar_id, 256);
-        if (issuer) {
+        bar_sync_named(bar_id, 256);              // everybody holds its y: MMA0 of `nxt` may overwrite the columns
+        if (issuer && has_next) {
             tc::fence_after_sync();
-            issue_mma1(tmem + 64, dl_a, wb_a);
-            tc::umma_commit_elect(&bars[1]);
-            if (has_next) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
+            issue_mma0(tmem, t0_a);
+            tc::umma_commit_elect(&bars[0]);
         }
         // gradient of the pooled output for this pixel's window, dropout mask and 1/8 folded in (overlaps MMA1)
         float dz[32];

@@ -9,6 +9,8 @@ namespace {
 
 // mode 0: D[128][64] = A[128][64] * B[64][64]^T          (A, B K-major)
 // mode 1: raw TMEM dump [128 lanes][64 cols] of  D[m][n] = sum_p A[p][m] * B[p][n],  p < 128  (A, B MN-major, M = 64)
+// mode 2: D[128][64] = (A B^T) B^T with the second GEMM's A operand read straight from the first one's accumulator in
+//         tensor memory (tc::umma_tf32_tmem_a_elect), both GEMMs issued back to back by one warp
 __global__ void __launch_bounds__(128)
 umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
     extern __shared__ unsigned char smem_raw[];
@@ -18,28 +20,49 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int b_rows = mode == 0 ? 64 : 128;
+    const int b_rows = mode == 1 ? 128 : 64;
     // fill operands (thread = row)
     for (int c = 0; c < 16; ++c) {
         const float4 v = *reinterpret_cast<const float4*>(A + tid * 64 + 4 * c);
         *reinterpret_cast<float4*>(a_s + (c >> 3) * (128 * 128) +
-                                   (mode == 0 ? tc::sw128_chunk(tid, c & 7) : tc::sw128b32_chunk(tid, c & 7))) = v;
+                                   (mode != 1 ? tc::sw128_chunk(tid, c & 7) : tc::sw128b32_chunk(tid, c & 7))) = v;
     }
     if (tid < b_rows) {
         for (int c = 0; c < 16; ++c) {
             const float4 v = *reinterpret_cast<const float4*>(B + tid * 64 + 4 * c);
             *reinterpret_cast<float4*>(b_s + (c >> 3) * (b_rows * 128) +
-                                       (mode == 0 ? tc::sw128_chunk(tid, c & 7) : tc::sw128b32_chunk(tid, c & 7))) = v;
+                                       (mode != 1 ? tc::sw128_chunk(tid, c & 7) : tc::sw128b32_chunk(tid, c & 7))) = v;
         }
     }
     if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-    if (tid == 0) {
+    if (mode == 2) {
+        if (warp == 0) {                       // warp-uniform issue path
+            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+            const uint32_t a_lo = tc::desc_lo(tc::smem_u32(a_s), 16), b_lo = tc::desc_lo(tc::smem_u32(b_s), 16);
+            const uint32_t hi = tc::desc_hi(1024, 2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                tc::umma_tf32_elect(tmem, a_lo + (((j >> 2) * 16384 + (j & 3) * 32) >> 4), hi,
+                                    b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, j > 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)        // A = columns [8 j, 8 j + 8) of the first accumulator
+                tc::umma_tf32_tmem_a_elect(tmem + 64, tmem + 8 * j, b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc,
+                                           j > 0 ? 1u : 0u);
+            // write-after-read check: the first accumulator is overwritten (doubled) right behind the GEMM that reads it
+            // as its A operand, as cnn0 does with the next tile's conv -- the chained result must not see the new values
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                tc::umma_tf32_elect(tmem, a_lo + (((j >> 2) * 16384 + (j & 3) * 32) >> 4), hi,
+                                    b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, 1u);
+            tc::umma_commit_elect(&bar);
+        }
+    } else if (tid == 0) {
         if (mode == 0) tc::umma_128x64x64_kmajor(tmem, tc::smem_u32(a_s), tc::smem_u32(b_s), false);
         else tc::umma_64x64_mnmajor(tmem, tc::smem_u32(a_s), tc::smem_u32(b_s), 128, false);
         tc::umma_commit(&bar);
@@ -47,18 +70,18 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
     tc::mbar_wait(&bar, 0);
     tc::fence_after_sync();
     float v[64];
-    tc::tmem_ld_row64(tmem, warp, 0, v);
+    tc::tmem_ld_row64(tmem, warp, mode == 2 ? 64 : 0, v);
     for (int c = 0; c < 64; ++c) D[tid * 64 + c] = v[c];
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
 }
 
 }  // namespace
 
 extern "C" int dcase_selftest_umma(dcase_ctx* ctx, int mode, const float* A, const float* B, float* D, void* stream) {
     DCASE_REQUIRE(ctx && A && B && D, "null argument");
-    DCASE_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    DCASE_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
     static bool attr_set = false;
     if (!attr_set) {
         DCASE_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560));

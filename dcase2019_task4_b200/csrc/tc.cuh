@@ -161,6 +161,22 @@ __device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint32_t a_lo, 
         "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with the A operand read from TENSOR MEMORY: [a_tmem] = 128 lanes (rows m) x K fp32 columns, i.e. exactly the
+// layout an M = 128 accumulator has -- a GEMM can consume the previous GEMM's result without a shared-memory round
+// trip (values are truncated to tf32 as they are read).  K = 8 per instruction: advance a_tmem by 8 columns.
+__device__ __forceinline__ void umma_tf32_tmem_a_elect(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                                       uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n\t"
