@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "ctx.h"
 #include "gru.cuh"
+#include "gemm_tc.cuh"
 #include "head_loss.cuh"
 
 int dcase_logmel_tables_create(dcase_ctx* ctx);
@@ -241,6 +242,7 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     if (rc == DCASE_OK) rc = glu_tma_kernels_init();
     if (rc == DCASE_OK) rc = head_kernels_init();
     if (rc == DCASE_OK) rc = gru_kernels_init();
+    if (rc == DCASE_OK) rc = gemm_tc_init();
     if (rc != DCASE_OK) { delete ctx; return rc; }
     *out = ctx;
     return DCASE_OK;
@@ -334,13 +336,15 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     for (int l = 0; l < 2; ++l) {
         const int nin = l == 0 ? kC : 2 * kH;
         float* rout = wsp<float>(ws, L, l == 0 ? "rnn0" : "rnn1");
-        {   // input projections of both directions in one launch: gi[d] = X W_ih[d]^T + b_ih[d]
-            GemmBatch gb{};
-            for (int d = 0; d < 2; ++d)
-                gb.p[d] = GemmProblem{BT, 3 * kH, nin, rin, nin, 1, params + o.w_ih[l][d], 1, nin,
-                                      gi + (size_t)d * BT * 3 * kH, 3 * kH, params + o.b_ih[l][d]};
-            gb.n = 2; gb.split = 1; gb.mode = 0;
-            DCASE_TRY(launch_sgemm_batch(gb, s));
+        {   // input projections of both directions in one launch on the tensor cores: gi[d] = X W_ih[d]^T + b_ih[d]
+            GemmTcBatch gb{};
+            gb.problems = 2; gb.parts = 1; gb.M = BT; gb.N = 3 * kH; gb.K = nin;
+            gb.lda = nin; gb.ldb = nin; gb.b_mn_major = 0; gb.ldc = 3 * kH;
+            for (int d = 0; d < 2; ++d) {
+                gb.A[d] = rin; gb.B[d] = params + o.w_ih[l][d];
+                gb.C[d] = gi + (size_t)d * BT * 3 * kH; gb.bias[d] = params + o.b_ih[l][d];
+            }
+            DCASE_TRY(launch_gemm_tc(gb, s));
         }
         GruFwdArgs g{};
         g.gi = gi;
@@ -387,12 +391,14 @@ int dcase_bigru_forward(dcase_ctx* ctx, const float* x, int B, int To, const flo
     for (int l = 0; l < 2; ++l) {
         const int nin = l == 0 ? kC : 2 * kH;
         float* rout = l == 0 ? mid : out;
-        GemmBatch gb{};
-        for (int d = 0; d < 2; ++d)
-            gb.p[d] = GemmProblem{BT, 3 * kH, nin, rin, nin, 1, rnn_params + (o.w_ih[l][d] - base), 1, nin,
-                                  gi + (size_t)d * BT * 3 * kH, 3 * kH, rnn_params + (o.b_ih[l][d] - base)};
-        gb.n = 2; gb.split = 1; gb.mode = 0;
-        DCASE_TRY(launch_sgemm_batch(gb, s));
+        GemmTcBatch gb{};        // the same tensor-core projection the CRNN forward uses
+        gb.problems = 2; gb.parts = 1; gb.M = BT; gb.N = 3 * kH; gb.K = nin;
+        gb.lda = nin; gb.ldb = nin; gb.b_mn_major = 0; gb.ldc = 3 * kH;
+        for (int d = 0; d < 2; ++d) {
+            gb.A[d] = rin; gb.B[d] = rnn_params + (o.w_ih[l][d] - base);
+            gb.C[d] = gi + (size_t)d * BT * 3 * kH; gb.bias[d] = rnn_params + (o.b_ih[l][d] - base);
+        }
+        DCASE_TRY(launch_gemm_tc(gb, s));
         GruFwdArgs g{};
         g.gi = gi;
         for (int d = 0; d < 2; ++d) {
@@ -460,27 +466,29 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
         g.save_n = wsp<float>(ws, L, sv[l][2]); g.save_hn = wsp<float>(ws, L, sv[l][3]);
         g.save_hp = wsp<float>(ws, L, sv[l][4]);
         g.dgi = dgi; g.dgh = dgh; g.B = B; g.T = To;
-        DCASE_CUDA_CHECK(cudaMemsetAsync(d_in, 0, (size_t)BT * nin * sizeof(float), s));
         DCASE_TRY(launch_gru_bwd(g, s));
         DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_bwd_fork[l], s));
         DCASE_CUDA_CHECK(cudaStreamWaitEvent(aux, ctx->ev_bwd_fork[l], 0));
-        GemmBatch gin{}, gw{};
+        GemmTcBatch gin{};       // d_in [BT][nin] = dgi_fwd W_ih_fwd + dgi_bwd W_ih_bwd: two parts accumulate in tensor memory
+        gin.problems = 1; gin.parts = 2; gin.M = BT; gin.N = nin; gin.K = 3 * kH;
+        gin.lda = 3 * kH; gin.ldb = nin; gin.b_mn_major = 1; gin.ldc = nin;
+        gin.C[0] = d_in; gin.bias[0] = nullptr;
+        GemmBatch gw{};
         ColsumBatch cb{};
         for (int d = 0; d < 2; ++d) {
             const float* dgi_d = dgi + (size_t)d * BT * 3 * kH;
             const float* dgh_d = dgh + (size_t)d * BT * 3 * kH;
             const float* hp_d = g.save_hp + (size_t)d * BT * kH;
-            // d_in [BT][nin] += dgi W_ih ;  dW_ih [3H][nin] = dgi^T X ;  dW_hh [3H][H] = dgh^T Hprev
-            gin.p[d] = GemmProblem{BT, nin, 3 * kH, dgi_d, 3 * kH, 1, params + o.w_ih[l][d], nin, 1, d_in, nin, nullptr};
+            // dW_ih [3H][nin] = dgi^T X ;  dW_hh [3H][H] = dgh^T Hprev
+            gin.A[d] = dgi_d; gin.B[d] = params + o.w_ih[l][d];
             gw.p[2 * d + 0] = GemmProblem{3 * kH, nin, BT, dgi_d, 1, 3 * kH, xin, nin, 1, grads + o.w_ih[l][d], nin, nullptr};
             gw.p[2 * d + 1] = GemmProblem{3 * kH, kH, BT, dgh_d, 1, 3 * kH, hp_d, kH, 1, grads + o.w_hh[l][d], kH, nullptr};
             cb.A[2 * d] = dgi_d; cb.out[2 * d] = grads + o.b_ih[l][d];
             cb.A[2 * d + 1] = dgh_d; cb.out[2 * d + 1] = grads + o.b_hh[l][d];
         }
-        gin.n = 2; gin.split = 1; gin.mode = 1;
         gw.n = 4; gw.split = BT >= 512 ? 16 : 1; gw.mode = 1;
         cb.n = 4; cb.M = BT; cb.N = 3 * kH;
-        DCASE_TRY(launch_sgemm_batch(gin, s));
+        DCASE_TRY(launch_gemm_tc(gin, s));
         DCASE_TRY(launch_sgemm_batch(gw, aux));
         DCASE_TRY(launch_colsum_batch(cb, aux));
         DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_bwd_join[l], aux));

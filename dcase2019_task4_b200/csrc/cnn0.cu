@@ -372,7 +372,8 @@ cnn0_fwd_kernel(Cnn0Args a) {
         TOCK(4);
         TICK();
         if (warp == 0 && has_next) {
-            tc::fence_after_sync();
+            tc::mbar_wait(&bars[1], ph1);         // MMA1 has read y (long done: it ran under the gate phase); an MMA that
+            tc::fence_after_sync();               // overwrites a TMEM A operand must not be queued behind its reader
             issue_mma0(tmem, t0_a);
             tc::umma_commit_elect(&bars[0]);
         }
@@ -572,6 +573,7 @@ cnn0_bwd_kernel(Cnn0Args a) {
         tc::fence_proxy_async();
         bar_sync_named(bar_id, 256);              // everybody holds its y: MMA0 of `nxt` may overwrite the columns
         if (issuer && has_next) {
+            tc::mbar_wait(&bars[1], ph1);         // MMA1 has read y: see the forward kernel
             tc::fence_after_sync();
             issue_mma0(tmem, t0_a);
             tc::umma_commit_elect(&bars[0]);

@@ -61,6 +61,14 @@ int make_rows_map(CUtensorMap* map, const float* base, long long n_rows, int box
     return encode_map(map, base, 2, dims, strides, box, swz);
 }
 
+int make_matrix_map(CUtensorMap* map, const float* base, long long cols, long long rows, long long ld, int box_cols,
+                    int box_rows, CUtensorMapSwizzle swz) {
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    return encode_map(map, base, 2, dims, strides, box, swz);
+}
+
 namespace {
 
 constexpr int kTile = 128;

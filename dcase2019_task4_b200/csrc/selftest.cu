@@ -11,6 +11,9 @@ namespace {
 // mode 1: raw TMEM dump [128 lanes][64 cols] of  D[m][n] = sum_p A[p][m] * B[p][n],  p < 128  (A, B MN-major, M = 64)
 // mode 2: D[128][64] = (A B^T) B^T with the second GEMM's A operand read straight from the first one's accumulator in
 //         tensor memory (tc::umma_tf32_tmem_a_elect), both GEMMs issued back to back by one warp
+// mode 3: the same, followed by a third GEMM that overwrites (doubles) the first accumulator once the chained GEMM has
+//         COMPLETED (commit + mbarrier wait in between), the order cnn0 uses for the next tile's conv.  Issuing the
+//         overwriting GEMM directly behind the reading one is NOT safe: round 2 measured a corrupted chained result
 __global__ void __launch_bounds__(128)
 umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
     extern __shared__ unsigned char smem_raw[];
@@ -41,7 +44,7 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-    if (mode == 2) {
+    if (mode >= 2) {
         if (warp == 0) {                       // warp-uniform issue path
             constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
             const uint32_t a_lo = tc::desc_lo(tc::smem_u32(a_s), 16), b_lo = tc::desc_lo(tc::smem_u32(b_s), 16);
@@ -54,12 +57,15 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
             for (int j = 0; j < 8; ++j)        // A = columns [8 j, 8 j + 8) of the first accumulator
                 tc::umma_tf32_tmem_a_elect(tmem + 64, tmem + 8 * j, b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc,
                                            j > 0 ? 1u : 0u);
-            // write-after-read check: the first accumulator is overwritten (doubled) right behind the GEMM that reads it
-            // as its A operand, as cnn0 does with the next tile's conv -- the chained result must not see the new values
+            if (mode == 3) {
+                tc::umma_commit_elect(&bar);
+                tc::mbar_wait(&bar, 0);                      // the chained GEMM has read its A operand
+                tc::fence_after_sync();
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                tc::umma_tf32_elect(tmem, a_lo + (((j >> 2) * 16384 + (j & 3) * 32) >> 4), hi,
-                                    b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, 1u);
+                for (int j = 0; j < 8; ++j)
+                    tc::umma_tf32_elect(tmem, a_lo + (((j >> 2) * 16384 + (j & 3) * 32) >> 4), hi,
+                                        b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, 1u);
+            }
             tc::umma_commit_elect(&bar);
         }
     } else if (tid == 0) {
@@ -67,10 +73,10 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
         else tc::umma_64x64_mnmajor(tmem, tc::smem_u32(a_s), tc::smem_u32(b_s), 128, false);
         tc::umma_commit(&bar);
     }
-    tc::mbar_wait(&bar, 0);
+    tc::mbar_wait(&bar, mode == 3 ? 1 : 0);
     tc::fence_after_sync();
     float v[64];
-    tc::tmem_ld_row64(tmem, warp, mode == 2 ? 64 : 0, v);
+    tc::tmem_ld_row64(tmem, warp, mode >= 2 ? 64 : 0, v);
     for (int c = 0; c < 64; ++c) D[tid * 64 + c] = v[c];
     tc::fence_before_sync();
     __syncthreads();
@@ -81,7 +87,7 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
 
 extern "C" int dcase_selftest_umma(dcase_ctx* ctx, int mode, const float* A, const float* B, float* D, void* stream) {
     DCASE_REQUIRE(ctx && A && B && D, "null argument");
-    DCASE_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    DCASE_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 .. 3");
     static bool attr_set = false;
     if (!attr_set) {
         DCASE_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560));

@@ -17,6 +17,10 @@ int make_act_map(CUtensorMap* map, const float* base, int B, int T_l, int F, int
 // 2-D view [n_rows][64] of the same memory; box = [box_rows][32 channels]
 int make_rows_map(CUtensorMap* map, const float* base, long long n_rows, int box_rows, CUtensorMapSwizzle swz);
 
+// 2-D view of a row-major fp32 matrix [rows][cols] with row stride `ld` floats; box = [box_rows][box_cols]
+int make_matrix_map(CUtensorMap* map, const float* base, long long cols, long long rows, long long ld, int box_cols,
+                    int box_rows, CUtensorMapSwizzle swz);
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -80,14 +80,15 @@ def test_umma_issue_microbenchmark_matches_operand_floor(cuda_device):
     assert lib.dcase_bench_umma(ctx, 96, 64, 0, 0, 1024, 4, 1024, 0, 0, out.data_ptr(), stream) != 0     # illegal M
 
 
-def test_umma_a_operand_from_tensor_memory(cuda_device):
+@pytest.mark.parametrize("mode", [2, 3])
+def test_umma_a_operand_from_tensor_memory(cuda_device, mode):
     """A chained GEMM (A B^T) B^T whose second A operand is the first GEMM's accumulator, read in place from tensor memory
     (tc::umma_tf32_tmem_a_elect): an M = 128 accumulator already has the [lane = row][column = k] layout a TMEM A operand
     needs, so block 0's GLU linear can consume the conv output without a shared-memory round trip."""
     g = torch.Generator().manual_seed(5)
     A = torch.randn(128, 64, generator=g).to(cuda_device)
     B = (torch.randn(64, 64, generator=g) / 8).to(cuda_device)
-    D = _run(2, A, B)
+    D = _run(mode, A, B)      # mode 3: the first accumulator is overwritten after the chained GEMM has completed
     y = (_tf32(A).double() @ _tf32(B).double().t()).float()
     ref = _tf32(y).double() @ _tf32(B).double().t()
     err = float((D.double() - ref).abs().max())
