@@ -12,8 +12,7 @@ namespace {
 // mode 2: D[128][64] = (A B^T) B^T with the second GEMM's A operand read straight from the first one's accumulator in
 //         tensor memory (tc::umma_tf32_tmem_a_elect), both GEMMs issued back to back by one warp
 // mode 3: the same, followed by a third GEMM that overwrites (doubles) the first accumulator once the chained GEMM has
-//         COMPLETED (commit + mbarrier wait in between), the order cnn0 uses for the next tile's conv.  Issuing the
-//         overwriting GEMM directly behind the reading one is NOT safe: round 2 measured a corrupted chained result
+//         COMPLETED, the order cnn0 uses for the next tile's conv
 __global__ void __launch_bounds__(128)
 umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
     extern __shared__ unsigned char smem_raw[];
@@ -45,36 +44,51 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
     tc::fence_after_sync();
     const uint32_t tmem = tmem_base_s;
     if (mode >= 2) {
-        if (warp == 0) {                       // warp-uniform issue path
-            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
-            const uint32_t a_lo = tc::desc_lo(tc::smem_u32(a_s), 16), b_lo = tc::desc_lo(tc::smem_u32(b_s), 16);
-            const uint32_t hi = tc::desc_hi(1024, 2);
+        // Hazards through a TMEM A operand are NOT interlocked by the tensor core (round 2 measured garbage when the reading
+        // GEMM was queued directly behind the producing one): each hand-over needs tcgen05.commit + an mbarrier wait,
+        // exactly like a thread reading the result.  Every thread follows all barrier phases in order.
+        constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+        const uint32_t a_lo = tc::desc_lo(tc::smem_u32(a_s), 16), b_lo = tc::desc_lo(tc::smem_u32(b_s), 16);
+        const uint32_t hi = tc::desc_hi(1024, 2);
+        const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+        if (warp_u == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 tc::umma_tf32_elect(tmem, a_lo + (((j >> 2) * 16384 + (j & 3) * 32) >> 4), hi,
                                     b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, j > 0 ? 1u : 0u);
+            tc::umma_commit_elect(&bar);
+        }
+        tc::mbar_wait(&bar, 0);                              // the first accumulator is complete
+        tc::fence_after_sync();
+        if (warp_u == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)        // A = columns [8 j, 8 j + 8) of the first accumulator
                 tc::umma_tf32_tmem_a_elect(tmem + 64, tmem + 8 * j, b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc,
                                            j > 0 ? 1u : 0u);
-            if (mode == 3) {
-                tc::umma_commit_elect(&bar);
-                tc::mbar_wait(&bar, 0);                      // the chained GEMM has read its A operand
-                tc::fence_after_sync();
+            tc::umma_commit_elect(&bar);
+        }
+        tc::mbar_wait(&bar, 1);                              // the chained GEMM is complete (and has read its A operand)
+        tc::fence_after_sync();
+        if (mode == 3) {
+            if (warp_u == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     tc::umma_tf32_elect(tmem, a_lo + (((j >> 2) * 16384 + (j & 3) * 32) >> 4), hi,
                                         b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, 1u);
+                tc::umma_commit_elect(&bar);
             }
-            tc::umma_commit_elect(&bar);
+            tc::mbar_wait(&bar, 0);
+            tc::fence_after_sync();
         }
-    } else if (tid == 0) {
-        if (mode == 0) tc::umma_128x64x64_kmajor(tmem, tc::smem_u32(a_s), tc::smem_u32(b_s), false);
-        else tc::umma_64x64_mnmajor(tmem, tc::smem_u32(a_s), tc::smem_u32(b_s), 128, false);
-        tc::umma_commit(&bar);
+    } else {
+        if (tid == 0) {
+            if (mode == 0) tc::umma_128x64x64_kmajor(tmem, tc::smem_u32(a_s), tc::smem_u32(b_s), false);
+            else tc::umma_64x64_mnmajor(tmem, tc::smem_u32(a_s), tc::smem_u32(b_s), 128, false);
+            tc::umma_commit(&bar);
+        }
+        tc::mbar_wait(&bar, 0);
+        tc::fence_after_sync();
     }
-    tc::mbar_wait(&bar, mode == 3 ? 1 : 0);
-    tc::fence_after_sync();
     float v[64];
     tc::tmem_ld_row64(tmem, warp, mode >= 2 ? 64 : 0, v);
     for (int c = 0; c < 64; ++c) D[tid * 64 + c] = v[c];
