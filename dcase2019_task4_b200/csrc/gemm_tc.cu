@@ -15,7 +15,7 @@
 // Pipeline per CTA (256 threads): TMA (cp.async.bulk.tensor, SWIZZLE_128B / 128B_ATOM_32B, zero fill past M) brings a
 // K = 64 stage of A and B straight into the operand layout, double buffered; all threads derive the lo tiles (the
 // split is element-wise, so it ignores the swizzle), one elected lane issues the 24 MMAs of the stage, the next
-// stage's TMA is already in flight and its split overlaps the current stage's MMAs (hi and lo double buffered).  Epilogue: TMEM -> registers -> per-warp swizzled staging -> full 128-byte lines.
+// stage's TMA is already in flight.  Epilogue: TMEM -> registers -> per-warp swizzled staging -> full 128-byte lines.
 #include "gemm_tc.cuh"
 
 #include "tc.cuh"
@@ -28,7 +28,7 @@ constexpr int kABlock = 128 * 128;                   // bytes of one [128 rows][
 constexpr int kBBlock = 64 * 128;                    // bytes of one B block: K-major [64 n][32 k] or MN-major 2 x [32 k][32 n]
 constexpr int kStageBytes = 2 * kABlock + 2 * kBBlock;              // 48 KB
 constexpr int kGemmThreads = 256;
-constexpr int kGemmSmem = 4 * kStageBytes + 1024 /* alignment slack */ + 64;      // hi x 2 | lo x 2
+constexpr int kGemmSmem = 3 * kStageBytes + 1024 /* alignment slack */ + 64;
 
 // blockIdx.z = problem; operand pair (problem, part) uses maps[problem * parts + part] (problems * parts <= 2)
 struct GemmTcArgs {
@@ -47,9 +47,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* hi[2] = {smem, smem + kStageBytes};
-    unsigned char* lo[2] = {smem + 2 * kStageBytes, smem + 3 * kStageBytes};
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 4 * kStageBytes);     // [0,1] stage landed, [2,3] MMAs of stage parity done
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 4);
+    unsigned char* lo = smem + 2 * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * kStageBytes);     // [0,1] stage landed, [2] MMAs of a stage done
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 3);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
@@ -60,7 +60,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs g) {
     const int n_stages = stages_per_part * g.parts;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+        tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 64);
@@ -87,22 +87,20 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs g) {
             }
         }
     };
-    if (tid == 0) load_stage(0);       // (stage 1 is requested right after the MMAs of stage 0 have been issued)
+    if (tid == 0) load_stage(0);
 
-    // Stage s uses hi[s & 1] / lo[s & 1]; its MMAs signal bars[2 + (s & 1)].  The split of stage s only needs the buffers
-    // of stage s - 2 to be free, so it runs while the tensor core is still busy with stage s - 1.
-    uint32_t ph_full[2] = {0, 0}, ph_done[2] = {0, 0};
+    uint32_t ph_full[2] = {0, 0}, ph_done = 0;
     for (int s = 0; s < n_stages; ++s) {
-        const int b = s & 1;
-        if (s >= 2) {                           // the MMAs of stage s - 2 have read hi[b] and lo[b]
-            tc::mbar_wait(&bars[2 + b], ph_done[b]);
-            ph_done[b] ^= 1;
+        if (s > 0) {                            // the MMAs of stage s - 1 have read hi[(s + 1) & 1] and lo
+            tc::mbar_wait(&bars[2], ph_done);
+            ph_done ^= 1;
         }
-        tc::mbar_wait(&bars[b], ph_full[b]);
-        ph_full[b] ^= 1;
+        if (tid == 0 && s + 1 < n_stages) load_stage(s + 1);
+        tc::mbar_wait(&bars[s & 1], ph_full[s & 1]);
+        ph_full[s & 1] ^= 1;
         // lo = x - hi(x), element-wise over the whole stage (layout agnostic)
-        const float4* src = reinterpret_cast<const float4*>(hi[b]);
-        float4* dst = reinterpret_cast<float4*>(lo[b]);
+        const float4* src = reinterpret_cast<const float4*>(hi[s & 1]);
+        float4* dst = reinterpret_cast<float4*>(lo);
 #pragma unroll 4
         for (int i = tid; i < kStageBytes / 16; i += kGemmThreads) {
             const float4 v = src[i];
@@ -113,9 +111,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs g) {
         if (warp == 0) {
             tc::fence_after_sync();
             constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, B_MN ? 1 : 0);
-            const uint32_t a_hi_lo = tc::desc_lo(tc::smem_u32(hi[b]), 16), a_lo_lo = tc::desc_lo(tc::smem_u32(lo[b]), 16);
+            const uint32_t a_hi_lo = tc::desc_lo(tc::smem_u32(hi[s & 1]), 16), a_lo_lo = tc::desc_lo(tc::smem_u32(lo), 16);
             const uint32_t k_hi = tc::desc_hi(1024, 2);
-            const uint32_t bh = tc::smem_u32(hi[b]) + 2 * kABlock, bl = tc::smem_u32(lo[b]) + 2 * kABlock;
+            const uint32_t bh = tc::smem_u32(hi[s & 1]) + 2 * kABlock, bl = tc::smem_u32(lo) + 2 * kABlock;
             const uint32_t b_hi_lo = B_MN ? tc::desc_lo(bh, 4096) : tc::desc_lo(bh, 16);
             const uint32_t b_lo_lo = B_MN ? tc::desc_lo(bl, 4096) : tc::desc_lo(bl, 16);
             const uint32_t b_hi = B_MN ? tc::desc_hi(512, 1) : k_hi;
@@ -128,20 +126,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcArgs g) {
                 tc::umma_tf32_elect(tmem, a_lo_lo + a_off, k_hi, b_hi_lo + b_off, b_hi, idesc, 1u);
                 tc::umma_tf32_elect(tmem, a_hi_lo + a_off, k_hi, b_lo_lo + b_off, b_hi, idesc, 1u);
             }
-            tc::umma_commit_elect(&bars[2 + b]);
-        }
-        // the TMA of stage s + 1 overwrites hi[b ^ 1]: the MMAs of stage s - 1 must have read it (bars[2 + (b ^ 1)], whose
-        // phase is consumed again by the split of stage s + 1 above -- a completed phase may be polled twice)
-        if (tid == 0 && s + 1 < n_stages) {
-            if (s >= 1) tc::mbar_wait(&bars[2 + (b ^ 1)], ph_done[b ^ 1]);
-            load_stage(s + 1);
+            tc::umma_commit_elect(&bars[2]);
         }
     }
-    // all MMAs done: the last commit covers every earlier one (in-order execution)
-    {
-        const int b = (n_stages - 1) & 1;
-        tc::mbar_wait(&bars[2 + b], ph_done[b]);
-    }
+    tc::mbar_wait(&bars[2], ph_done);
     tc::fence_after_sync();
 
     // ---- epilogue: warps 0..3 own the four TMEM lane quadrants (rows 32 w .. 32 w + 31); rows leave as full lines ----
