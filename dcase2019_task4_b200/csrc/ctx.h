@@ -11,6 +11,7 @@ struct dcase_ctx {
     int* d_mel_start;    // [128] first FFT bin of each work item
     int* d_mel_owner;    // [64][2] {first item, item count} of each band
     int mel_nnz;
+    float* d_resample_win;    // [2][32769] kaiser_best half window | its forward differences (read_audio's resampler)
     // second stream + events: the teacher forward runs concurrently with the student forward (dcase_mt_fwd_bwd)
     cudaStream_t aux_stream;
     cudaEvent_t ev_fork, ev_join;

@@ -434,6 +434,61 @@ mixdown_kernel(const Tin* __restrict__ in, long long n_frames, int n_ch, float* 
     }
 }
 
+// ---- read_audio's resampler (utils/utils.py:190-192 -> librosa.resample -> resampy kaiser_best) -----------------------
+// One thread per output sample: band-limited sinc interpolation with the half window `win` (and its forward differences
+// `delta`) sampled 512 times per zero crossing; the table index advances by int(scale * 512) per input sample.  Times in
+// fp64 (resampy's own arithmetic), weights and the sum in fp32.  Samples past resampy's int(n_in * ratio) are librosa's
+// fix_length zero padding.
+constexpr int kRsZeros = 64, kRsTable = 512, kRsWin = kRsZeros * kRsTable + 1;
+__global__ void __launch_bounds__(256)
+resample_kernel(const float* __restrict__ x, long long n_in, float* __restrict__ y, long long n_out, long long n_valid,
+                double time_increment, double scale, int index_step, float gain, const float* __restrict__ win,
+                const float* __restrict__ delta) {
+    const long long t = blockIdx.x * 256ll + threadIdx.x;
+    if (t >= n_out) return;
+    if (t >= n_valid) { y[t] = 0.f; return; }
+    const double time_register = (double)t * time_increment;
+    const long long n = (long long)time_register;
+    double frac = scale * (time_register - (double)n);
+    float acc = 0.f;
+    {
+        const double index_frac = frac * kRsTable;
+        const int offset = (int)index_frac;
+        const float eta = (float)(index_frac - offset);
+        long long i_max = (kRsWin - offset) / index_step;
+        if (i_max > n + 1) i_max = n + 1;
+        for (long long i = 0; i < i_max; ++i) {
+            const int k = offset + (int)i * index_step;
+            acc = fmaf(fmaf(eta, __ldg(delta + k), __ldg(win + k)), __ldg(x + n - i), acc);
+        }
+    }
+    {
+        frac = scale - frac;
+        const double index_frac = frac * kRsTable;
+        const int offset = (int)index_frac;
+        const float eta = (float)(index_frac - offset);
+        long long k_max = (kRsWin - offset) / index_step;
+        if (k_max > n_in - n - 1) k_max = n_in - n - 1;
+        for (long long q = 0; q < k_max; ++q) {
+            const int k = offset + (int)q * index_step;
+            acc = fmaf(fmaf(eta, __ldg(delta + k), __ldg(win + k)), __ldg(x + n + q + 1), acc);
+        }
+    }
+    y[t] = gain * acc;
+}
+
+// modified Bessel function I0 by its power series (numpy.kaiser's i0), double precision
+double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0;
+    const double q = x * x / 4.0;
+    for (int k = 1; k < 500; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-17 * sum) break;
+    }
+    return sum;
+}
+
 // ---- host-side constant tables -----------------------------------------------------------------
 double hz_to_mel(double f) {
     const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = log(6.4) / 27.0;
@@ -477,6 +532,24 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
     ctx->mel_nnz = (int)packed.size();
     DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_window2, kNfft * sizeof(float)));
     DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_window2, win.data(), kNfft * sizeof(float), cudaMemcpyHostToDevice));
+    {   // resampy.filters.sinc_window(num_zeros=64, precision=9, window=kaiser(14.769656459379492), rolloff=0.9475937167399596)
+        const double beta = 14.769656459379492, rolloff = 0.9475937167399596;
+        const int n = kRsZeros * kRsTable;
+        std::vector<double> w(n + 1);
+        const double i0b = bessel_i0(beta);
+        for (int i = 0; i <= n; ++i) {
+            const double xz = rolloff * ((double)kRsZeros * i / n);           // rolloff * linspace(0, num_zeros, n + 1)
+            const double sinc = xz == 0.0 ? 1.0 : sin(M_PI * xz) / (M_PI * xz);
+            const double r = (double)i / n;                                    // np.kaiser(2 n + 1, beta)[n + i]
+            const double taper = bessel_i0(beta * sqrt(1.0 - r * r < 0.0 ? 0.0 : 1.0 - r * r)) / i0b;
+            w[i] = taper * rolloff * sinc;
+        }
+        std::vector<float> tab(2 * (size_t)kRsWin, 0.f);
+        for (int i = 0; i <= n; ++i) tab[i] = (float)w[i];
+        for (int i = 0; i < n; ++i) tab[kRsWin + i] = (float)(w[i + 1] - w[i]);
+        DCASE_CUDA_CHECK(cudaMalloc(&ctx->d_resample_win, tab.size() * sizeof(float)));
+        DCASE_CUDA_CHECK(cudaMemcpy(ctx->d_resample_win, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     // balanced work split: band m gets n_m of the 128 items (proportional to its length, at least one); item q is a
     // contiguous run of weights inside its band.  The kernel reads the weights of item (lane + 32 j) transposed
     // ([j][i][lane]), zero padded to kMelRun and halved (its magnitudes are 2 |X[k]|: exact power-of-two rescale).
@@ -525,7 +598,7 @@ int dcase_logmel_tables_create(dcase_ctx* ctx) {
 }
 
 void dcase_logmel_tables_destroy(dcase_ctx* ctx) {
-    cudaFree(ctx->d_window2); cudaFree(ctx->d_mel_wt);
+    cudaFree(ctx->d_window2); cudaFree(ctx->d_mel_wt); cudaFree(ctx->d_resample_win);
     cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_owner);
     free(ctx->h_mel_dense);
 }
@@ -630,6 +703,30 @@ int dcase_scaler_finalize(dcase_ctx* ctx, const double* sums, long long n_sample
     DCASE_REQUIRE(n_samples > 0, "Scaler.means over an empty dataset");
     DCASE_PROF("scaler_finalize", stream);
     scaler_finalize_kernel<<<1, kMel, 0, stream>>>(sums, (double)n_samples, mean, mean_of_square, mean_f32, std_f32);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+long long dcase_audio_resample_len(long long n_in, int sr_in, int sr_out) {
+    if (n_in <= 0 || sr_in <= 0 || sr_out <= 0) return 0;
+    return (long long)ceil((double)n_in * ((double)sr_out / (double)sr_in));
+}
+
+int dcase_audio_resample(dcase_ctx* ctx, const float* mono, long long n_in, int sr_in, int sr_out, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DCASE_REQUIRE(ctx && mono && out, "null argument");
+    DCASE_REQUIRE(n_in > 0 && sr_in > 0 && sr_out > 0, "bad shape / rate");
+    const double ratio = (double)sr_out / (double)sr_in;
+    const long long n_out = dcase_audio_resample_len(n_in, sr_in, sr_out);
+    const long long n_valid = (long long)((double)n_in * ratio);              // resampy: int(n_in * ratio)
+    DCASE_REQUIRE(n_valid >= 1, "input signal too short for the target rate");
+    const double scale = ratio < 1.0 ? ratio : 1.0;
+    const int index_step = (int)(scale * kRsTable);
+    DCASE_REQUIRE(index_step >= 1, "sample ratio too small for the 512-entry filter table");
+    DCASE_PROF("audio_resample", stream);
+    resample_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream>>>(mono, n_in, out, n_out, n_valid < n_out ? n_valid : n_out,
+                                                                        1.0 / ratio, scale, index_step, ratio < 1.0 ? (float)ratio : 1.f,
+                                                                        ctx->d_resample_win, ctx->d_resample_win + kRsWin);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

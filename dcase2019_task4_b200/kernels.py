@@ -57,6 +57,18 @@ def audio_mixdown(frames):
     return out
 
 
+def audio_resample(mono, sr_in, sr_out):
+    """read_audio's librosa.resample(audio, orig_sr, target_sr) (kaiser_best): CUDA float32 mono [n] -> [ceil(n * ratio)]."""
+    assert mono.is_cuda and mono.dim() == 1
+    mono = _f32(mono)
+    n_out = lib().dcase_audio_resample_len(mono.numel(), int(sr_in), int(sr_out))
+    out = torch.empty(n_out, device=mono.device, dtype=torch.float32)
+    with torch.cuda.device(mono.device):
+        check(lib().dcase_audio_resample(ctx(mono.device), ptr(mono), mono.numel(), int(sr_in), int(sr_out), ptr(out),
+                                         stream_ptr()))
+    return out
+
+
 def logmel_finish(mel_amp, mean, std, frames, noisy=False, noise=None, seed=0, step=0, scalars=None,
                   out_clean=None, out_noisy=None):
     """get_transforms(frames, scaler, augment_type='noise' if noisy) on a batch of amplitude mels.
@@ -276,4 +288,4 @@ def mt_fwd_bwd(args):
 
 __all__ = ["FLAG_BN_BATCH_STATS", "FLAG_DROPOUT", "logmel_fwd", "logmel_finish", "crnn_forward", "crnn_backward",
            "mt_loss", "adam_ema_step", "mt_fwd_bwd", "param_count", "param_offset", "new_workspace", "ws_tensor",
-           "mel_filterbank", "num_frames", "workspace_bytes", "scaler_accumulate", "scaler_finalize", "bigru_forward", "bigru_forward_h", "audio_mixdown"]
+           "mel_filterbank", "num_frames", "workspace_bytes", "scaler_accumulate", "scaler_finalize", "bigru_forward", "bigru_forward_h", "audio_mixdown", "audio_resample"]

@@ -116,20 +116,22 @@ def read_wav_frames(path):
 
 def read_audio_device(path, target_fs=None):
     """read_audio (utils/utils.py:175-193) with the samples left on the GPU: (CUDA float32 mono [n], fs).
-    Multi-channel files are mixed down by the mean (dcase_audio_mixdown); 16-bit PCM is scaled by 1 / 32768."""
+    Multi-channel files are mixed down by the mean (dcase_audio_mixdown); 16-bit PCM is scaled by 1 / 32768; a file at
+    another rate is resampled like librosa.resample's kaiser_best (dcase_audio_resample)."""
     from .. import kernels as K
     frames, fs = read_wav_frames(path)
-    if target_fs is not None and fs != target_fs:
-        raise NotImplementedError(
-            "{}: {} Hz, wanted {} Hz -- librosa.resample (utils/utils.py:191) is an unpinned third-party resampler "
-            "(kaiser_best before librosa 0.10, soxr_hq after) and is not rebuilt; resample the file offline".format(
-                path, fs, target_fs))
     if not torch.cuda.is_available():
         raise RuntimeError("read_audio feeds the GPU feature extraction (dcase_audio_mixdown); no CPU fallback")
     dev_frames = torch.from_numpy(frames).cuda(non_blocking=True)
     if frames.shape[0] == 0:
-        return torch.empty(0, device=dev_frames.device), fs
-    return K.audio_mixdown(dev_frames), fs
+        return torch.empty(0, device=dev_frames.device), fs if target_fs is None else target_fs
+    audio = K.audio_mixdown(dev_frames)
+    if target_fs is not None and fs != target_fs:
+        # librosa.resample(audio, orig_sr=fs, target_sr=target_fs) (utils/utils.py:190-192) with the 'kaiser_best' filter of
+        # the librosa versions the baseline was written for, on the device (dcase_audio_resample)
+        audio = K.audio_resample(audio, fs, target_fs)
+        fs = target_fs
+    return audio, fs
 
 
 def read_audio(path, target_fs=None):

@@ -109,6 +109,16 @@ int dcase_logmel_fwd_pcm16(dcase_ctx* ctx, const int16_t* wave, int B, int L, fl
 int dcase_audio_mixdown(dcase_ctx* ctx, const void* interleaved, int is_pcm16, long long n_frames, int n_channels,
                         float* mono, void* stream);
 
+/* read_audio's resampling step (utils/utils.py:190-192: librosa.resample(audio, orig_sr=fs, target_sr=target_fs), default
+ * res_type 'kaiser_best' of librosa < 0.10 = resampy's band-limited sinc interpolation: 64 zero crossings, 512 table
+ * samples per crossing, Kaiser beta 14.769656459379492, roll-off 0.9475937167399596; restated in oracle/resample.py,
+ * parity unpinned against resampy / librosa, which are not installed).  mono float32 [n_in] at sr_in -> [n_out] at
+ * sr_out with n_out = dcase_audio_resample_len(n_in, sr_in, sr_out) = ceil(n_in * sr_out / sr_in) (librosa's fix_length:
+ * the samples past resampy's int(n_in * ratio) are zero). */
+long long dcase_audio_resample_len(long long n_in, int sr_in, int sr_out);
+int dcase_audio_resample(dcase_ctx* ctx, const float* mono, long long n_in, int sr_in, int sr_out, float* out,
+                         void* stream);
+
 /* get_transforms(frames, scaler, augment_type="noise") (utils/utils.py:397-412) on a batch:
  * AugmentGaussianNoise (DataLoad.py:274-287) -> ApplyLog / librosa.amplitude_to_db (DataLoad.py:192-207)
  * -> PadOrTrunc (DataLoad.py:210-259) -> ToTensor -> Normalize / Scaler.normalize (Scaler.py:99-105).

@@ -128,8 +128,11 @@ def test_read_audio_and_feature_cache_from_wav_files(pkg, cuda_device, tmp_path)
     assert fs == 44100 and audio.shape == (30000,) and np.abs(audio - ref).max() <= 1e-7
     assert np.array_equal(read_audio(tmp_path / "mono.wav")[0], (left / 32768.0).astype(np.float32))
     assert np.abs(read_audio(tmp_path / "float.wav")[0] - waves.mean(axis=0)).max() <= 1e-7
-    with pytest.raises(NotImplementedError):
-        read_audio(tmp_path / "slow.wav", 44100)
+    slow, fs = read_audio(tmp_path / "slow.wav", 44100)                        # librosa.resample leg (utils.py:190-192)
+    from oracle import resample as oresample
+    want_slow = oresample.resample(left / 32768.0, 16000, 44100)
+    assert fs == 44100 and slow.shape == want_slow.shape == (int(np.ceil(30000 * 44100 / 16000)),)
+    assert np.abs(slow - want_slow).max() <= 2e-6 * max(1.0, np.abs(want_slow).max())
     ds = DatasetDcase2019Task4(str(tmp_path), base_feature_dir=str(tmp_path / "features"), save_log_feature=False)
     assert ds.feature_dir.endswith(os.path.join("sr44100_win2048_hop511_mels64_nolog", "features"))
     done = ds.extract_features_from_files(str(tmp_path), ["stereo.wav", "mono.wav", "missing.wav"])
@@ -139,3 +142,22 @@ def test_read_audio_and_feature_cache_from_wav_files(pkg, cuda_device, tmp_path)
     want = omel.calculate_mel_spec(ref)
     assert np.abs(feat - want).max() <= 2e-5 * want.max()                     # same bar as tests/test_gpu_logmel.py
     assert np.array_equal(np.load(os.path.join(ds.feature_dir, "mono.npy")), ds.calculate_mel_spec(left / 32768.0))
+
+
+@pytest.mark.parametrize("sr_in,sr_out,n", [(16000, 44100, 16000), (48000, 44100, 48001), (22050, 44100, 5000),
+                                            (44100, 16000, 44100), (32000, 44100, 777)])
+def test_audio_resample_matches_oracle(pkg, cuda_device, sr_in, sr_out, n):
+    """dcase_audio_resample (read_audio's librosa.resample step, kaiser_best band-limited sinc interpolation) against the
+    float64 restatement in oracle/resample.py: up- and down-sampling, lengths that do not divide, the zero-padded tail
+    of librosa's fix_length."""
+    from oracle import resample as oresample
+    from dcase2019_task4_b200 import kernels as K
+    rng = np.random.default_rng(sr_in + n)
+    t = np.arange(n) / sr_in
+    x = (0.6 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 0.3 * sr_in * t) + 0.05 * rng.standard_normal(n))
+    got = K.audio_resample(torch.from_numpy(x.astype(np.float32)).to(cuda_device), sr_in, sr_out).cpu().numpy()
+    want = oresample.resample(x.astype(np.float32), sr_in, sr_out)
+    assert got.shape == want.shape == (int(np.ceil(n * sr_out / sr_in)),)
+    err = np.abs(got - want).max()
+    print(f"{sr_in} -> {sr_out}, n = {n}: max err {err:.3e}")
+    assert err <= 2e-6 * max(1.0, np.abs(want).max())

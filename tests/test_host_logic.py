@@ -262,7 +262,7 @@ def test_checkpoint_dict_matches_reference_layout(tmp_path):
 
 def test_wav_container_parsing_and_loud_failures(tmp_path):
     """read_audio's host half (utils/utils.py:175-193): container parsing keeps 16-bit PCM as int16 frames, maps other
-    encodings to soundfile's float range; resampling and CPU execution fail loudly."""
+    encodings to soundfile's float range; CPU execution fails loudly (mix-down and resampling run on the device)."""
     import scipy.io.wavfile
     from dcase2019_task4_b200.utils.utils import read_audio, read_wav_frames
     rng = np.random.default_rng(0)
@@ -276,11 +276,40 @@ def test_wav_container_parsing_and_loud_failures(tmp_path):
     assert fs == 22050 and frames.shape == (1000, 1) and np.allclose(frames[:, 0], pcm[:, 0] / 32768.0)
     frames, _ = read_wav_frames(tmp_path / "c.wav")
     assert frames.dtype == np.float32 and np.allclose(frames[:, 0], pcm[:, 0] / 32768.0)
-    with pytest.raises(NotImplementedError):
-        read_audio(tmp_path / "b.wav", 44100)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             read_audio(tmp_path / "a.wav", 44100)
+        with pytest.raises(RuntimeError):
+            read_audio(tmp_path / "b.wav", 44100)
+
+
+def test_resample_oracle_is_a_band_limited_interpolator():
+    """oracle/resample.py restates librosa.resample's kaiser_best (resampy) from its published algorithm -- resampy and
+    librosa are absent, so the restatement is checked against what any correct band-limited resampler must do: tones
+    below both Nyquist limits come out as the same tones at the new rate (amplitude, frequency AND phase), the output
+    length is librosa's ceil(n * ratio), down-sampling removes what is above the new Nyquist, and an independent
+    polyphase resampler (scipy.signal.resample_poly) agrees away from the edges."""
+    import scipy.signal
+    from oracle import resample as oresample
+    for sr_in, sr_out in ((16000, 44100), (48000, 44100), (22050, 44100), (44100, 16000)):
+        n = sr_in // 2
+        t_in, n_out = np.arange(n) / sr_in, int(np.ceil(n * sr_out / sr_in))
+        t_out = np.arange(n_out) / sr_out
+        f1, f2 = 440.0, 0.35 * min(sr_in, sr_out)
+        tone = lambda t: 0.7 * np.sin(2 * np.pi * f1 * t + 0.3) + 0.2 * np.cos(2 * np.pi * f2 * t)
+        y = oresample.resample(tone(t_in), sr_in, sr_out)
+        assert y.shape == (n_out,)
+        core = slice(2000, n_out - 2000)                      # 64 zero crossings of filter support at the edges
+        # up-sampling interpolates exactly; down-sampling steps through the filter table in int(ratio * 512) entries (a
+        # truncation in resampy's own algorithm: 185 instead of 185.76 at 44.1 -> 16 kHz), a gain error of a few 1e-3
+        assert np.abs(y - tone(t_out))[core].max() <= (2e-5 if sr_out > sr_in else 5e-3)
+        g = np.gcd(sr_in, sr_out)
+        poly = scipy.signal.resample_poly(tone(t_in), sr_out // g, sr_in // g)
+        assert np.abs(y[core] - poly[:n_out][core]).max() <= 4e-3    # scipy's default Kaiser(5) filter is much shorter
+    # above the new Nyquist: gone (stop band of the kaiser_best filter)
+    n = 44100
+    high = np.sin(2 * np.pi * 15000.0 * np.arange(n) / 44100)
+    assert np.abs(oresample.resample(high, 44100, 16000))[2000:-2000].max() <= 1e-3
 
 
 def test_weak_f_measure_by_class_hand_computed():
