@@ -84,7 +84,7 @@ class ClockSampler(object):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -352,11 +352,12 @@ def run_b200(args, rank, local_rank, world):
     n_warm = max(args.warmup, 3, n_pool if use_graph else 0)      # every pool buffer's graph is captured before timing
     for i in range(n_warm):
         resident_step(i)
+    # nvidia-smi is polled every 20 ms from here until the end of the end-to-end region (the timed regions themselves
+    # last tens of milliseconds): every sample is taken with the GPU under this benchmark's load
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = K.launch_count() + engine.graph_launches
     ms_total = timed(resident_step, args.steps)
     launches = K.launch_count() + engine.graph_launches - l0     # eager launches + kernels inside replayed CUDA graphs
-    clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = world * B_PER_GPU * args.steps / (ms_total * 1e-3)
 
@@ -367,6 +368,7 @@ def run_b200(args, rank, local_rank, world):
     ms_e2e = timed(lambda i: e2e_step(i + n_prime, last=(i == args.steps - 1)), args.steps)
     e2e_value = world * B_PER_GPU * args.steps / (ms_e2e * 1e-3)
     e2e_wave_bytes = 2 if e2e_pcm else 4
+    clocks = sampler.stop() if sampler else None
     e2e_f32 = None
     if e2e_pcm:                                   # the same loop shipping float32 waveforms, for comparison
         f32_step = make_e2e(False)

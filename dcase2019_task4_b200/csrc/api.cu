@@ -125,7 +125,7 @@ WsLayout ws_layout(int B, int T, int NC) {
     const size_t BT = (size_t)B * (T / 8);
     const size_t n0 = (size_t)B * (T / 2) * 16 * 64;   // out0 / ypre1 elements
     const size_t n1 = (size_t)B * (T / 4) * 4 * 64;    // out1 / ypre2
-    add("mom0", 54, sizeof(double));
+    add("mom0", 56, sizeof(double));        // 54 tap moments + completion ticket of the moments kernel
     add("stats1", 128, sizeof(double));
     add("stats2", 128, sizeof(double));
     add("fold0", kFold0Size);
@@ -227,6 +227,11 @@ int dcase_ctx_create(dcase_ctx** out, int device) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     DCASE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        DCASE_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->prep_stream[i], cudaStreamNonBlocking));
+        DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_prep_fork[i], cudaEventDisableTiming));
+        DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_prep_join[i], cudaEventDisableTiming));
+    }
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     DCASE_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 4; ++i) {
@@ -252,6 +257,11 @@ int dcase_ctx_destroy(dcase_ctx* ctx) {
     if (!ctx) return DCASE_OK;
     dcase_logmel_tables_destroy(ctx);
     cudaFree(ctx->d_loss_scratch);
+    for (int i = 0; i < 2; ++i) {
+        cudaStreamDestroy(ctx->prep_stream[i]);
+        cudaEventDestroy(ctx->ev_prep_fork[i]);
+        cudaEventDestroy(ctx->ev_prep_join[i]);
+    }
     cudaStreamDestroy(ctx->aux_stream);
     cudaEventDestroy(ctx->ev_fork);
     cudaEventDestroy(ctx->ev_join);
@@ -295,13 +305,25 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     const int To = T / 8;
     const int BT = B * To;
 
+    // ---- conv weight images of blocks 1, 2: parameters only, so they are built beside block 0 on a side stream ----
+    const int mid = model_id ? 1 : 0;
+    cudaStream_t prep = g_prof_on ? s : ctx->prep_stream[mid];
+    DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_prep_fork[mid], s));
+    DCASE_CUDA_CHECK(cudaStreamWaitEvent(prep, ctx->ev_prep_fork[mid], 0));
+    DCASE_TRY(launch_conv_w_prep(params + o.conv_w[1], wsp<float>(ws, L, "wprep1_f"), wsp<float>(ws, L, "wprep1_d"),
+                                 params + o.conv_w[2], wsp<float>(ws, L, "wprep2_f"), wsp<float>(ws, L, "wprep2_d"), prep));
+    DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_prep_join[mid], prep));
+
     // ---- CNN block 0 (fused, nothing materialised at [B,64,T,64]) ----
     double* mom0 = wsp<double>(ws, L, "mom0");
     float* fold0 = wsp<float>(ws, L, "fold0");
     const long long n_pix0 = (long long)B * T * 64;
-    if (training) DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, sms, s));
-    DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
-                                  params + o.bn_b[0], bn_running, training, fold0, s));
+    if (training)
+        DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
+                                      params + o.bn_b[0], bn_running, fold0, sms, s));
+    else
+        DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
+                                      params + o.bn_b[0], bn_running, training, fold0, s));
     float* out0 = wsp<float>(ws, L, "out0");
     DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), out0, sms, s));
 
@@ -320,7 +342,8 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
         double* stats = wsp<double>(ws, L, names[l][3]);
         float* bn = wsp<float>(ws, L, names[l][4]);
         float* out = wsp<float>(ws, L, names[l][5]);
-        DCASE_TRY(launch_conv_w_prep(params + o.conv_w[l], wf, wd, s));
+        (void)wd;
+        if (l == 1) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_prep_join[mid], 0));
         DCASE_TRY(launch_conv3x3(in, B, T_l, F_l, wf, params + o.conv_b[l], ypre, training ? stats : nullptr, sms, s));
         float* glu_img = wsp<float>(ws, L, names[l][6]);
         DCASE_TRY(launch_bn_finalize(stats, n_pix, params + o.bn_w[l], params + o.bn_b[l], bn_running + l * 128,

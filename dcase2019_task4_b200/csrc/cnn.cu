@@ -27,10 +27,66 @@ __device__ __forceinline__ void resolve_rng(const DropoutCfg& d, uint64_t& seed,
 // ---------------------------------------------------------------------------------------------
 // Thread = one mel bin f of a 16-frame segment of one clip: it walks down the frames with a rolling 3 x 3 window in
 // registers (3 new loads per pixel instead of 9) and accumulates the 54 sums in fp32; fp64 from the block level on.
+__device__ __forceinline__ int tri_index(int k, int l) {  // k <= l, order of cnn0_moments_kernel
+    return 9 + k * 9 - (k * (k - 1)) / 2 + (l - k);
+}
+
+// ---- BN fold of block 0 from the tap moments (CNN.py:49) --------------------------------------------------------------
+// Task (c, k): row k of the 9 x 9 quadratic form  var_c = sum_kl w_ck w_cl (M_kl - m_k m_l)  and term k of the mean (fp64:
+// B200's fp64 rate is low, so the 81 terms of a channel are spread over nine tasks).
+__device__ __forceinline__ void bn0_task(int c, int k, const double* mom, long long n_pix, const float* __restrict__ w,
+                                         double (*pm)[64], double (*pv)[64]) {
+    const double inv_n = 1.0 / (double)n_pix;
+    const double mk = mom[k] * inv_n, wk = (double)w[c * 9 + k];
+    double v = 0.0;
+    for (int l = 0; l < 9; ++l) {
+        const double M = mom[k <= l ? tri_index(k, l) : tri_index(l, k)] * inv_n;
+        v += (double)w[c * 9 + l] * (M - mk * (mom[l] * inv_n));
+    }
+    pm[k][c] = wk * mk;
+    pv[k][c] = wk * v;
+}
+// Channel c: statistics (batch: from the task partials; eval: running), running-stat update (momentum 0.99, unbiased
+// variance), BatchNorm folded into the conv weights.
+__device__ __forceinline__ void bn0_channel(int c, double (*pm)[64], double (*pv)[64], long long n_pix,
+                                            const float* __restrict__ w, const float* __restrict__ b,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            float* __restrict__ running, int training, float* __restrict__ fold0) {
+    double mean, var;
+    if (training) {
+        mean = b[c];
+        var = 0.0;
+        for (int j = 0; j < 9; ++j) { mean += pm[j][c]; var += pv[j][c]; }
+        if (var < 0.0) var = 0.0;
+        if (running) {
+            running[c] = (1.f - kBnMomentum) * running[c] + kBnMomentum * (float)mean;
+            const double unbiased = var * (double)n_pix / (double)(n_pix - 1);
+            running[64 + c] = (1.f - kBnMomentum) * running[64 + c] + kBnMomentum * (float)unbiased;
+        }
+    } else {
+        mean = running[c];
+        var = running[64 + c];
+    }
+    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+    const float a = gamma[c] * invstd;
+    for (int j = 0; j < 9; ++j) fold0[kFold0Wf + j * 64 + c] = a * w[c * 9 + j];
+    fold0[kFold0Bf + c] = a * (b[c] - (float)mean) + beta[c];
+    fold0[kFold0Mean + c] = (float)mean;
+    fold0[kFold0Invstd + c] = invstd;
+    fold0[kFold0A + c] = a;
+}
+struct Bn0FinalizeArgs {      // training: the LAST block of the moments kernel folds BatchNorm (mom[54] is its ticket)
+    long long n_pix;
+    const float *w, *b, *gamma, *beta;
+    float *running, *fold0;
+};
+
 constexpr int kMomSeg = 16;
 __global__ void __launch_bounds__(256)
-cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restrict__ mom) {
+cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restrict__ mom, Bn0FinalizeArgs fin) {
     __shared__ float red[8][54];
+    __shared__ int is_last;
+    __shared__ double mom_s[54], pm[9][64], pv[9][64];
     float acc[54];
 #pragma unroll
     for (int i = 0; i < 54; ++i) acc[i] = 0.f;
@@ -76,57 +132,33 @@ cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restric
         for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
         atomicAdd(mom + threadIdx.x, s);
     }
+    // the last block to arrive folds BatchNorm into the conv weights: saves the one-block launch that sat between this
+    // kernel and cnn0_fwd on the forward chain
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        is_last = atomicAdd(reinterpret_cast<unsigned long long*>(mom + 54), 1ull) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 54) mom_s[threadIdx.x] = __ldcg(mom + threadIdx.x);     // from L2: the other blocks' atomics
+    __syncthreads();
+    for (int task = threadIdx.x; task < 576; task += 256) bn0_task(task & 63, task >> 6, mom_s, fin.n_pix, fin.w, pm, pv);
+    __syncthreads();
+    if (threadIdx.x < 64)
+        bn0_channel(threadIdx.x, pm, pv, fin.n_pix, fin.w, fin.b, fin.gamma, fin.beta, fin.running, 1, fin.fold0);
 }
 
-__device__ __forceinline__ int tri_index(int k, int l) {  // k <= l, order of cnn0_moments_kernel
-    return 9 + k * 9 - (k * (k - 1)) / 2 + (l - k);
-}
-
-// One block of 64 x 9 threads: batch (or running) statistics of conv0's output from the tap moments, BN folded into the
-// conv weights, running-stat update (momentum 0.99, unbiased variance), CNN.py:49.  Thread (c, k) owns row k of the
-// 9 x 9 quadratic form  var_c = sum_kl w_ck w_cl (M_kl - m_k m_l)  (fp64: B200's fp64 rate is low, so the 81 terms of a
-// channel are spread over nine threads -- the kernel sits between the moments pass and cnn0_fwd on the critical path).
+// Eval mode (running statistics, no moments pass), or a caller that wants the fold alone: one block of 64 x 9 threads.
 __global__ void __launch_bounds__(576)
 bn0_finalize_kernel(const double* __restrict__ mom, long long n_pix, const float* __restrict__ w,
                     const float* __restrict__ b, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ running, int training, float* __restrict__ fold0) {
     __shared__ double pm[9][64], pv[9][64];
     const int c = threadIdx.x & 63, k = threadIdx.x >> 6;
-    if (training) {
-        const double inv_n = 1.0 / (double)n_pix;
-        const double mk = mom[k] * inv_n, wk = (double)w[c * 9 + k];
-        double v = 0.0;
-        for (int l = 0; l < 9; ++l) {
-            const double M = mom[k <= l ? tri_index(k, l) : tri_index(l, k)] * inv_n;
-            v += (double)w[c * 9 + l] * (M - mk * (mom[l] * inv_n));
-        }
-        pm[k][c] = wk * mk;
-        pv[k][c] = wk * v;
-    }
+    if (training) bn0_task(c, k, mom, n_pix, w, pm, pv);
     __syncthreads();
-    if (k != 0) return;
-    double mean, var;
-    if (training) {
-        mean = b[c];
-        var = 0.0;
-        for (int j = 0; j < 9; ++j) { mean += pm[j][c]; var += pv[j][c]; }
-        if (var < 0.0) var = 0.0;
-        if (running) {
-            running[c] = (1.f - kBnMomentum) * running[c] + kBnMomentum * (float)mean;
-            const double unbiased = var * (double)n_pix / (double)(n_pix - 1);
-            running[64 + c] = (1.f - kBnMomentum) * running[64 + c] + kBnMomentum * (float)unbiased;
-        }
-    } else {
-        mean = running[c];
-        var = running[64 + c];
-    }
-    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
-    const float a = gamma[c] * invstd;
-    for (int j = 0; j < 9; ++j) fold0[kFold0Wf + j * 64 + c] = a * w[c * 9 + j];
-    fold0[kFold0Bf + c] = a * (b[c] - (float)mean) + beta[c];
-    fold0[kFold0Mean + c] = (float)mean;
-    fold0[kFold0Invstd + c] = invstd;
-    fold0[kFold0A + c] = a;
+    if (k == 0) bn0_channel(c, pm, pv, n_pix, w, b, gamma, beta, running, training, fold0);
 }
 
 // BN statistics of layers 1,2 from the per-channel sum / sum of squares (one block of 256 threads; threads 0..63 own a
@@ -237,14 +269,16 @@ int cnn_kernels_init() {
     return DCASE_OK;
 }
 
-int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, cudaStream_t s) {
+int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* conv_w, const float* conv_b,
+                        const float* gamma, const float* beta, float* running, float* fold0, int num_sms, cudaStream_t s) {
     DCASE_PROF("cnn0_moments", s);
-    DCASE_CUDA_CHECK(cudaMemsetAsync(mom, 0, 54 * sizeof(double), s));
+    DCASE_CUDA_CHECK(cudaMemsetAsync(mom, 0, 55 * sizeof(double), s));       // 54 sums + the completion ticket
     const long long n_seg = (long long)B * ((T + kMomSeg - 1) / kMomSeg);
     DCASE_REQUIRE(n_seg < (1ll << 30), "batch too large");
     long long blocks = (n_seg + 3) / 4;
     if (blocks > num_sms * 4) blocks = num_sms * 4;
-    cnn0_moments_kernel<<<(int)blocks, 256, 0, s>>>(x, B, T, mom);
+    Bn0FinalizeArgs fin{(long long)B * T * 64, conv_w, conv_b, gamma, beta, running, fold0};
+    cnn0_moments_kernel<<<(int)blocks, 256, 0, s>>>(x, B, T, mom, fin);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

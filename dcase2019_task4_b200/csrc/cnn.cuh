@@ -28,7 +28,9 @@ struct DropoutCfg {
     const DcaseStepScalars* sc;  // if non-null overrides seed/step (CUDA-graph replay)
 };
 
-int launch_cnn0_moments(const float* x, int B, int T, double* mom, int num_sms, cudaStream_t s);
+// training: tap moments of the input AND (last block) the BN fold of block 0; eval: launch_bn0_finalize alone
+int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* conv_w, const float* conv_b,
+                        const float* gamma, const float* beta, float* running, float* fold0, int num_sms, cudaStream_t s);
 int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running /*[2][64]*/, int training,
                         float* fold0, cudaStream_t s);
@@ -45,7 +47,9 @@ int cnn0_kernels_init();
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* glu_img, DropoutCfg drop, float* out,
                         int num_sms, cudaStream_t s);
 // conv_tc.cu: weight images are the swizzled shared-memory layout of the tcgen05 B operand (36864 floats each)
-int launch_conv_w_prep(const float* w /*[64][64][3][3]*/, float* img_fwd, float* img_dgrad, cudaStream_t s);
+// operand images (forward + mirrored / transposed for the data gradient) of BOTH 64 -> 64 conv layers, one launch
+int launch_conv_w_prep(const float* w1, float* w_fwd1, float* w_dgrad1, const float* w2, float* w_fwd2, float* w_dgrad2,
+                       cudaStream_t s);
 int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, const float* bias,
                    float* out, double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
 // GLU operand image written by bn_finalize (bytes): W' 16 KB | P 8 KB | {bias', exp scale, exp shift} 768 B |

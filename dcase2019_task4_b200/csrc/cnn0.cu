@@ -648,23 +648,27 @@ cnn0_bwd_kernel(Cnn0Args a) {
     if (warp == 0) tc::tmem_dealloc(*tmem_base_s, 512);
 }
 
-// One block of 256 threads: {U, S2} -> GLU parameter gradients and S = Wg^T U + S2; then (threads 0..63) the
-// BatchNorm / conv0 parameter gradients from S and the tap moments.
-__global__ void __launch_bounds__(256)
+// One block of 640 threads: {U, S2} -> GLU parameter gradients and S = Wg^T U + S2; then the BatchNorm / conv0 parameter
+// gradients from S and the tap moments, thread (c, k) owning tap k of channel c (the fp64 terms are spread over nine
+// threads per channel: B200's fp64 rate is low and this kernel is the last link of the backward chain before Adam).
+constexpr int kBwdFinThreads = 640;
+__global__ void __launch_bounds__(kBwdFinThreads)
 cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix, const float* __restrict__ w,
                          const float* __restrict__ b, const float* __restrict__ fold0, const float* __restrict__ glu_w,
                          const float* __restrict__ us, float* __restrict__ g_w, float* __restrict__ g_b,
                          float* __restrict__ g_gamma, float* __restrict__ g_beta, float* __restrict__ g_glu_w,
                          float* __restrict__ g_glu_b) {
     __shared__ float U[64][10], S[64][10], W0e[64][10];
+    __shared__ float Wg[64 * 65];                       // [n][c], padded: the S pass walks a column
     const int tid = threadIdx.x;
-    for (int i = tid; i < 640; i += 256) {
+    for (int i = tid; i < 640; i += kBwdFinThreads) {
         const int r = i / 10, j = i - r * 10;
         U[r][j] = us[r * 16 + j];
         W0e[r][j] = j < 9 ? fold0[kFold0Wf + j * 64 + r] : fold0[kFold0Bf + r];
     }
+    for (int i = tid; i < 4096; i += kBwdFinThreads) Wg[(i >> 6) * 65 + (i & 63)] = __ldg(glu_w + i);
     __syncthreads();
-    for (int i = tid; i < 4096; i += 256) {            // dWg[n][k] = sum_j U[n][j] W0e[k][j]
+    for (int i = tid; i < 4096; i += kBwdFinThreads) {  // dWg[n][k] = sum_j U[n][j] W0e[k][j]
         const int n = i >> 6, k = i & 63;
         float s = 0.f;
 #pragma unroll
@@ -672,34 +676,35 @@ cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix, const 
         g_glu_w[i] = s;
     }
     if (tid < 64) g_glu_b[tid] = U[tid][9];
-    for (int i = tid; i < 640; i += 256) {             // S[c][j] = sum_n Wg[n][c] U[n][j] + S2[c][j]
-        const int c = i / 10, j = i - c * 10;
+    {                                                   // S[c][j] = sum_n Wg[n][c] U[n][j] + S2[c][j]
+        const int c = tid / 10, j = tid - c * 10;
         float s = us[(64 + c) * 16 + j];
-        for (int n = 0; n < 64; ++n) s = fmaf(__ldg(glu_w + n * 64 + c), U[n][j], s);
+#pragma unroll 8
+        for (int n = 0; n < 64; ++n) s = fmaf(Wg[n * 65 + c], U[n][j], s);
         S[c][j] = s;
     }
     __syncthreads();
-    if (tid >= 64) return;
-    const int c = tid;
+    const int c = tid / 10, k = tid - c * 10;           // k = 9: the channel's gamma / beta / bias thread
     const double n = (double)n_pix;
     const double mean = fold0[kFold0Mean + c], invstd = fold0[kFold0Invstd + c], av = fold0[kFold0A + c];
     const double S1 = S[c][9];                          // sum dY
-    double G[9], wG = 0.0;
-    for (int k = 0; k < 9; ++k) { G[k] = S[c][k]; wG += (double)w[c * 9 + k] * G[k]; }   // sum dY * tap_k
+    double wG = 0.0;
+    for (int l = 0; l < 9; ++l) wG += (double)w[c * 9 + l] * (double)S[c][l];   // sum dY * (conv output - bias)
     const double bm = (double)b[c] - mean;
     const double S2 = invstd * (wG + bm * S1);          // sum dY * xhat
-    g_gamma[c] = (float)S2;
-    g_beta[c] = (float)S1;
-    g_b[c] = 0.f;                                       // BN cancels the conv bias
-    for (int k = 0; k < 9; ++k) {
-        double sxx = 0.0;                               // sum_p xhat_c * x_k
-        for (int l = 0; l < 9; ++l) {
-            const int lo = l <= k ? l : k, hi = l <= k ? k : l;
-            sxx += (double)w[c * 9 + l] * mom[9 + lo * 9 - (lo * (lo - 1)) / 2 + (hi - lo)];
-        }
-        sxx = invstd * (sxx + bm * mom[k]);
-        g_w[c * 9 + k] = (float)(av * (G[k] - (S1 / n) * mom[k] - (S2 / n) * sxx));
+    if (k == 9) {
+        g_gamma[c] = (float)S2;
+        g_beta[c] = (float)S1;
+        g_b[c] = 0.f;                                   // BN cancels the conv bias
+        return;
     }
+    double sxx = 0.0;                                   // sum_p xhat_c * x_k
+    for (int l = 0; l < 9; ++l) {
+        const int lo = l <= k ? l : k, hi = l <= k ? k : l;
+        sxx += (double)w[c * 9 + l] * mom[9 + lo * 9 - (lo * (lo - 1)) / 2 + (hi - lo)];
+    }
+    sxx = invstd * (sxx + bm * mom[k]);
+    g_w[c * 9 + k] = (float)(av * ((double)S[c][k] - (S1 / n) * mom[k] - (S2 / n) * sxx));
 }
 
 }  // namespace
@@ -738,7 +743,7 @@ int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* co
                              const float* fold0, const float* glu_w, const float* us, float* g_conv_w, float* g_conv_b,
                              float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b, cudaStream_t s) {
     DCASE_PROF("cnn0_bwd_finalize", s);
-    cnn0_bwd_finalize_kernel<<<1, 256, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, glu_w, us, g_conv_w, g_conv_b, g_gamma,
+    cnn0_bwd_finalize_kernel<<<1, kBwdFinThreads, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, glu_w, us, g_conv_w, g_conv_b, g_gamma,
                                              g_beta, g_glu_w, g_glu_b);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;

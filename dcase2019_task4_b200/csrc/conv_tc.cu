@@ -79,7 +79,15 @@ constexpr int kWImgBytes = 9 * 16384;             // [9 taps][2 k-blocks][64 row
 // W [n][c][tap] -> shared-memory images (K-major SW128 B operands, rows = output channel of the pass)
 //   forward: image[tap ][c / 32][row n][c % 32] = W[n][c][tap]
 //   dgrad  : image[8-tap][n / 32][row c][n % 32] = W[n][c][tap]      (mirrored taps, transposed channels)
-__global__ void conv_w_image_kernel(const float* __restrict__ w, float* __restrict__ img_fwd, float* __restrict__ img_dgrad) {
+struct ConvWPrepArgs {     // blockIdx.y = layer (both 64 -> 64 conv layers of the CNN in one launch)
+    const float* w[2];
+    float* img_fwd[2];
+    float* img_dgrad[2];
+};
+__global__ void conv_w_image_kernel(ConvWPrepArgs a) {
+    const float* __restrict__ w = a.w[blockIdx.y];
+    float* __restrict__ img_fwd = a.img_fwd[blockIdx.y];
+    float* __restrict__ img_dgrad = a.img_dgrad[blockIdx.y];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * 64 * 9; i += gridDim.x * blockDim.x) {
         const int tap = i % 9, c = (i / 9) & 63, n = i / 576;
         const float v = tc::tf32_rn(__ldg(w + i));
@@ -459,9 +467,11 @@ int conv_tc_kernels_init() {
     return DCASE_OK;
 }
 
-int launch_conv_w_prep(const float* w, float* w_fwd, float* w_dgrad, cudaStream_t s) {
+int launch_conv_w_prep(const float* w1, float* w_fwd1, float* w_dgrad1, const float* w2, float* w_fwd2, float* w_dgrad2,
+                       cudaStream_t s) {
     DCASE_PROF("conv_w_prep", s);
-    conv_w_image_kernel<<<144, 256, 0, s>>>(w, w_fwd, w_dgrad);
+    ConvWPrepArgs a{{w1, w2}, {w_fwd1, w_fwd2}, {w_dgrad1, w_dgrad2}};
+    conv_w_image_kernel<<<dim3(72, 2), 256, 0, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

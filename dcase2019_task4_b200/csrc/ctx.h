@@ -15,6 +15,10 @@ struct dcase_ctx {
     // second stream + events: the teacher forward runs concurrently with the student forward (dcase_mt_fwd_bwd)
     cudaStream_t aux_stream;
     cudaEvent_t ev_fork, ev_join;
+    // per model (0 student, 1 teacher): the conv weight images only depend on the parameters, so they are built on a side
+    // stream beside block 0 instead of sitting between cnn0 and conv1 on the forward chain
+    cudaStream_t prep_stream[2];
+    cudaEvent_t ev_prep_fork[2], ev_prep_join[2];
     // backward: the GRU and conv weight-gradient kernels leave the critical path (dcase_crnn_backward)
     cudaEvent_t ev_bwd_fork[4], ev_bwd_join[4];   // [0,1] GRU layers, [2,3] conv blocks 1, 2
     // scratch of the loss kernel: per-CTA partial sums + completion ticket (head_loss.cuh)
