@@ -57,6 +57,7 @@ SIGNATURES = {
     "dcase_audio_mixdown": (c_i, [c_p, c_p, c_i, ctypes.c_longlong, c_i, c_p, c_p]),
     "dcase_audio_resample_len": (ctypes.c_longlong, [ctypes.c_longlong, c_i, c_i]),
     "dcase_audio_resample": (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_i, c_p, c_p]),
+    "dcase_audio_resample_clock": (c_i, [ctypes.c_longlong, c_i, c_i, c_p]),
     "dcase_logmel_finish": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_u64, c_u32, c_p, c_p, c_p, c_p, c_p]),
     "dcase_scaler_accumulate": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "dcase_scaler_finalize": (c_i, [c_p, c_p, ctypes.c_longlong, c_p, c_p, c_p, c_p, c_p]),

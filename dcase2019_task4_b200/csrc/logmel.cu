@@ -440,14 +440,53 @@ mixdown_kernel(const Tin* __restrict__ in, long long n_frames, int n_ch, float* 
 // fp64 (resampy's own arithmetic), weights and the sum in fp32.  Samples past resampy's int(n_in * ratio) are librosa's
 // fix_length zero padding.
 constexpr int kRsZeros = 64, kRsTable = 512, kRsWin = kRsZeros * kRsTable + 1;
+// resampy's clock is the running sum  time_register += 1 / ratio  in float64.  Its rounding matters: whenever the exact time
+// is an integer (every 147th output sample at 48 -> 44.1 kHz) the algorithm's own index truncation makes the result jump by
+// ~1e-3 depending on which side of the integer the rounded sum falls.  The sum is reproduced EXACTLY without a serial
+// loop: while the register stays inside one binade every addition rounds the same way, so it advances by a constant
+// representable increment -- a table of <= kRsSegs linear segments {first sample, register there, increment}.
+constexpr int kRsSegs = 160;
+struct ResampleClock {
+    long long t0[kRsSegs];
+    double s0[kRsSegs];
+    double inc[kRsSegs];
+    int n;
+};
+int build_resample_clock(long long n_steps, double time_increment, ResampleClock* c) {
+    c->n = 0;
+    double s = 0.0;
+    long long t = 0;
+    while (t < n_steps) {
+        if (c->n >= kRsSegs) return -1;
+        const double nxt = s + time_increment;               // the one rounding resampy performs per sample
+        int es = 0, en = 0;
+        frexp(s, &es);
+        frexp(nxt, &en);
+        long long m = 1;
+        const double inc = nxt - s;                          // exact: both are multiples of the smaller ulp
+        if (s != 0.0 && es == en) {                          // same binade before and after: constant increment inside it
+            const double top = ldexp(1.0, es);               // frexp: s in [2^(es-1), 2^es)
+            m = (long long)((top - s) / inc);
+            while (m > 1 && s + (double)m * inc >= top) --m;
+            if (m < 1) m = 1;
+        }
+        c->t0[c->n] = t; c->s0[c->n] = s; c->inc[c->n] = inc; ++c->n;
+        t += m;
+        s += (double)m * inc;                                // exact (a multiple of the binade's ulp below its top)
+    }
+    return 0;
+}
+
 __global__ void __launch_bounds__(256)
 resample_kernel(const float* __restrict__ x, long long n_in, float* __restrict__ y, long long n_out, long long n_valid,
-                double time_increment, double scale, int index_step, float gain, const float* __restrict__ win,
-                const float* __restrict__ delta) {
+                const __grid_constant__ ResampleClock clk, double scale, int index_step, float gain,
+                const float* __restrict__ win, const float* __restrict__ delta) {
     const long long t = blockIdx.x * 256ll + threadIdx.x;
     if (t >= n_out) return;
     if (t >= n_valid) { y[t] = 0.f; return; }
-    const double time_register = (double)t * time_increment;
+    int sg = 0;
+    for (int i = 1; i < clk.n; ++i) sg = clk.t0[i] <= t ? i : sg;
+    const double time_register = clk.s0[sg] + (double)(t - clk.t0[sg]) * clk.inc[sg];
     const long long n = (long long)time_register;
     double frac = scale * (time_register - (double)n);
     float acc = 0.f;
@@ -712,6 +751,19 @@ long long dcase_audio_resample_len(long long n_in, int sr_in, int sr_out) {
     return (long long)ceil((double)n_in * ((double)sr_out / (double)sr_in));
 }
 
+// test hook (no GPU): the time registers  sum_{j < t} 1 / ratio  as the device reconstructs them, into host memory
+int dcase_audio_resample_clock(long long n, int sr_in, int sr_out, double* out_host) {
+    DCASE_REQUIRE(n >= 0 && sr_in > 0 && sr_out > 0 && out_host, "bad argument");
+    ResampleClock clk;
+    DCASE_REQUIRE(build_resample_clock(n, 1.0 / ((double)sr_out / (double)sr_in), &clk) == 0, "clock table overflow");
+    for (long long t = 0; t < n; ++t) {
+        int sg = 0;
+        for (int i = 1; i < clk.n; ++i) sg = clk.t0[i] <= t ? i : sg;
+        out_host[t] = clk.s0[sg] + (double)(t - clk.t0[sg]) * clk.inc[sg];
+    }
+    return DCASE_OK;
+}
+
 int dcase_audio_resample(dcase_ctx* ctx, const float* mono, long long n_in, int sr_in, int sr_out, float* out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DCASE_REQUIRE(ctx && mono && out, "null argument");
@@ -723,9 +775,11 @@ int dcase_audio_resample(dcase_ctx* ctx, const float* mono, long long n_in, int 
     const double scale = ratio < 1.0 ? ratio : 1.0;
     const int index_step = (int)(scale * kRsTable);
     DCASE_REQUIRE(index_step >= 1, "sample ratio too small for the 512-entry filter table");
+    ResampleClock clk;
+    DCASE_REQUIRE(build_resample_clock(n_valid, 1.0 / ratio, &clk) == 0, "signal too long for the resampler's clock table");
     DCASE_PROF("audio_resample", stream);
     resample_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream>>>(mono, n_in, out, n_out, n_valid < n_out ? n_valid : n_out,
-                                                                        1.0 / ratio, scale, index_step, ratio < 1.0 ? (float)ratio : 1.f,
+                                                                        clk, scale, index_step, ratio < 1.0 ? (float)ratio : 1.f,
                                                                         ctx->d_resample_win, ctx->d_resample_win + kRsWin);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;

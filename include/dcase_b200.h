@@ -118,6 +118,9 @@ int dcase_audio_mixdown(dcase_ctx* ctx, const void* interleaved, int is_pcm16, l
 long long dcase_audio_resample_len(long long n_in, int sr_in, int sr_out);
 int dcase_audio_resample(dcase_ctx* ctx, const float* mono, long long n_in, int sr_in, int sr_out, float* out,
                          void* stream);
+/* test hook, host only: resampy's float64 clock (the running sum of 1 / ratio) as the kernel reconstructs it from its
+ * per-binade segment table -- must equal the serial sum bit for bit */
+int dcase_audio_resample_clock(long long n, int sr_in, int sr_out, double* out_host);
 
 /* get_transforms(frames, scaler, augment_type="noise") (utils/utils.py:397-412) on a batch:
  * AugmentGaussianNoise (DataLoad.py:274-287) -> ApplyLog / librosa.amplitude_to_db (DataLoad.py:192-207)

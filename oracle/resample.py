@@ -43,8 +43,9 @@ def resample(x, orig_sr, target_sr):
     scale = min(1.0, ratio)
     index_step = int(scale * NUM_TABLE)
     nwin, n_orig = len(interp_win), len(x)
-    # resampy accumulates time_register += 1 / ratio; t / ratio differs from that sum by rounding only
-    time_register = np.cumsum(np.full(n_out, 1.0 / ratio)) - 1.0 / ratio
+    # resampy's clock: time_register = 0.0, then += 1 / ratio after every output sample (a serial float64 sum; its rounding
+    # decides on which side of an integer the register falls, where the truncated table step makes the result jump)
+    time_register = np.concatenate([[0.0], np.cumsum(np.full(max(n_out - 1, 0), 1.0 / ratio))])[:n_out]
     n = time_register.astype(np.int64)
     y = np.zeros(n_out)
     # left wing (samples n, n - 1, ...)

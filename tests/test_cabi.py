@@ -161,3 +161,21 @@ def test_device_philox_code_on_the_host_matches_kat_and_numpy_restatement(tmp_pa
         want = philox.philox4x32(np.uint32(row & 0xFFFFFFFF), np.uint32(row >> 32), np.uint32(8 * 1 + 2), np.uint32(41 + i),
                                  np.uint32(seed & 0xFFFFFFFF), np.uint32(seed >> 32))
         assert [int(np.asarray(w).reshape(-1)[0]) for w in want] == words, (row, words)
+
+
+def test_resampler_clock_equals_the_serial_float64_sum():
+    """dcase_audio_resample's clock: resampy adds 1 / ratio to a float64 register once per output sample; the kernel
+    rebuilds that serial sum from a per-binade table of linear segments (csrc/logmel.cu::build_resample_clock).  It must be
+    the SAME doubles, bit for bit, or the samples whose exact time is an integer (every 147th at 48 -> 44.1 kHz) land on
+    the other side of the algorithm's truncation jump."""
+    import ctypes
+    import numpy as np
+    from dcase2019_task4_b200 import _lib
+    L = _lib.lib()
+    for sr_in, sr_out, n in ((48000, 44100, 441000), (44100, 16000, 160000), (16000, 44100, 441000), (22050, 44100, 99999),
+                             (32000, 44100, 300001), (8000, 44100, 441000), (96000, 44100, 441000), (44100, 48000, 7)):
+        out = np.empty(n)
+        assert L.dcase_audio_resample_clock(n, sr_in, sr_out, ctypes.c_void_p(out.ctypes.data)) == 0
+        inc = 1.0 / (float(sr_out) / float(sr_in))
+        serial = np.concatenate([[0.0], np.cumsum(np.full(n - 1, inc))])      # numpy's cumsum is the serial sum
+        assert np.array_equal(out, serial), (sr_in, sr_out)
