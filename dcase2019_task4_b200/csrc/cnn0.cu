@@ -320,15 +320,6 @@ cnn0_fwd_kernel(Cnn0Args a) {
         TICK();
         ph0 ^= 1;
         tc::fence_after_sync();
-        // gate phase first: it only needs y, and the pooling MMA of `prev` (issued a moment ago) finishes under it
-        float g[32];
-        {
-            float y[32];
-            tmem_ld32(tmem + lane_base + 32 * half, y);
-            sigmoid32(y, g);
-        }
-        TOCK(3);
-        TICK();
         if (prev >= 0) {                          // pooled tile `prev`: TMEM -> out; frees the lin columns and the z buffer
             tc::mbar_wait(&bars[2], ph2);
             ph2 ^= 1;
@@ -348,10 +339,10 @@ cnn0_fwd_kernel(Cnn0Args a) {
         TICK();
         if (has_next) xs_commit(xr, xs, tid);
         tc::fence_before_sync();
-        __syncthreads();                          // everybody holds its y and has read the pooled tile; xs of `nxt` complete
+        __syncthreads();                          // the pooled tile has been read by everybody; xs of `nxt` is complete
         TOCK(1);
         TICK();
-        if (warp == 0) {                          // MMA1 (y read from tensor memory) runs under the set-up of `nxt` below
+        if (warp == 0) {                          // MMA1 runs under the gate phase below: y is read from tensor memory
             tc::fence_after_sync();
             issue_mma1_tmem(tmem + 64, tmem, wb_a);
             tc::umma_commit_elect(&bars[1]);
@@ -367,25 +358,35 @@ cnn0_fwd_kernel(Cnn0Args a) {
             pos.advance(pos_step, a.T);
             if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, pos, a.T, tid);
         }
+        float g[32];
+        {
+            float y[32];
+            tmem_ld32(tmem + lane_base + 32 * half, y);
+            tc::fence_before_sync();
+            sigmoid32(y, g);
+        }
+        tc::fence_proxy_async();                  // the taps of `nxt`
+        TOCK(3);
+        TICK();
+        __syncthreads();                          // everybody holds its y: MMA0 of `nxt` may overwrite the columns
+        TOCK(4);
+        TICK();
+        if (warp == 0 && has_next) {
+            tc::mbar_wait(&bars[1], ph1);         // MMA1 has read y (long done: it ran under the gate phase); an MMA that
+            tc::fence_after_sync();               // overwrites a TMEM A operand must not be queued behind its reader
+            issue_mma0(tmem, t0_a);
+            tc::umma_commit_elect(&bars[0]);
+        }
         if (drop) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) g[i] = (keep & (1u << i)) ? g[i] : 0.f;
+            keep_next = half ? keep_hi_next : keep_lo[row];
         }
-        tc::fence_proxy_async();                  // the taps of `nxt`
-        TOCK(4);
-        TICK();
-        tc::mbar_wait(&bars[1], ph1);             // lin of `cur`; MMA1 has also finished reading y
+        tc::mbar_wait(&bars[1], ph1);
         TOCK(5);
         TICK();
         ph1 ^= 1;
         tc::fence_after_sync();
-        __syncthreads();                          // taps / keep bits of `nxt` are written
-        if (warp == 0 && has_next) {              // (an MMA that overwrites a TMEM A operand must not be queued behind its
-            tc::fence_after_sync();               // reader: bars[1] has been waited for above)
-            issue_mma0(tmem, t0_a);
-            tc::umma_commit_elect(&bars[0]);
-        }
-        if (drop) keep_next = half ? keep_hi_next : keep_lo[row];
         {
             float lin[32];
             tmem_ld32(tmem + 64 + lane_base + 32 * half, lin);
