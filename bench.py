@@ -260,6 +260,12 @@ def run_b200(args, rank, local_rank, world):
     strong_mask = slice(BATCH_SIZES[0] + BATCH_SIZES[1], B_PER_GPU)
     # N > 1: gradient exchange fused with Adam + EMA over NVLink peer memory inside the step's CUDA graph (csrc/p2p.cu);
     # DCASE_DP_NCCL=1 selects the NCCL all-reduce + separate optimizer kernel, launched eagerly
+    # BatchNorm statistics: per replica by default (the reference's semantics at its own batch of 24 per device);
+    # DCASE_SYNC_BN=1 selects exact-global-batch statistics (dp.SyncBatchNorm) -- stated in config.parallelism
+    sync_bn = None
+    if world > 1 and os.environ.get("DCASE_SYNC_BN", "0") == "1":
+        from dcase2019_task4_b200 import dp
+        sync_bn = dp.SyncBatchNorm()
     engine = MeanTeacherEngine(crnn, optimizer, crnn_ema, weak_mask, strong_mask, B_PER_GPU, FRAMES)
     use_graph = engine.use_graph
     if world == 1:
@@ -269,6 +275,9 @@ def run_b200(args, rank, local_rank, world):
             world, " inside the step's CUDA graph" if use_graph else "")
     else:
         dp_mode = "dp%d: per-stream shards, NCCL all-reduce of the flat gradient slab, eager launches" % world
+    if world > 1:
+        dp_mode += "; BatchNorm statistics " + ("over the GLOBAL batch (SyncBN, peer-memory exchange per BatchNorm)"
+                                                if sync_bn is not None else "per replica")
     rampup_length = STEPS_PER_EPOCH * cfg.n_epoch // 2
 
     state = {"gs": 0}

@@ -83,6 +83,12 @@ SIGNATURES = {
     "dcase_p2p_begin_step": (c_i, [c_p, c_p]),
     "dcase_p2p_adam_ema_step": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_p]),
     "dcase_p2p_destroy": (c_i, [c_p]),
+    "dcase_syncbn_handle_bytes": (c_i, []),
+    "dcase_syncbn_create": (c_i, [c_p, c_i, c_i, ctypes.POINTER(c_p), c_p]),
+    "dcase_syncbn_connect": (c_i, [c_p, c_p]),
+    "dcase_ctx_set_syncbn": (c_i, [c_p, c_p]),
+    "dcase_syncbn_allreduce": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "dcase_syncbn_destroy": (c_i, [c_p]),
     "dcase_mt_fwd_bwd": (c_i, [c_p, ctypes.POINTER(MtArgs), c_p]),
     "dcase_sizeof_mt_args": (c_sz, []),
     "dcase_sizeof_step_scalars": (c_sz, []),

@@ -318,10 +318,20 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     double* mom0 = wsp<double>(ws, L, "mom0");
     float* fold0 = wsp<float>(ws, L, "fold0");
     const long long n_pix0 = (long long)B * T * 64;
-    if (training)
+    // exact-global-batch BatchNorm (dcase_ctx_set_syncbn): the sums behind every batch statistic cross the ranks between
+    // their producer and their consumer; slots 3 * model + layer (forward), 6 + layer (backward)
+    const dcase_syncbn* sb = training ? ctx->syncbn : nullptr;
+    const long long world = syncbn_world(sb);
+    if (training && !sb)
         DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
                                       params + o.bn_b[0], bn_running, fold0, sms, s));
-    else
+    else if (training) {
+        DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
+                                      params + o.bn_b[0], bn_running, nullptr, sms, s));
+        DCASE_TRY(syncbn_allreduce_f64(sb, mom0, 54, 3 * mid + 0, s));
+        DCASE_TRY(launch_bn0_finalize(mom0, n_pix0 * world, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
+                                      params + o.bn_b[0], bn_running, 1, fold0, s));
+    } else
         DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
                                       params + o.bn_b[0], bn_running, training, fold0, s));
     float* out0 = wsp<float>(ws, L, "out0");
@@ -346,7 +356,8 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
         if (l == 1) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_prep_join[mid], 0));
         DCASE_TRY(launch_conv3x3(in, B, T_l, F_l, wf, params + o.conv_b[l], ypre, training ? stats : nullptr, sms, s));
         float* glu_img = wsp<float>(ws, L, names[l][6]);
-        DCASE_TRY(launch_bn_finalize(stats, n_pix, params + o.bn_w[l], params + o.bn_b[l], bn_running + l * 128,
+        if (sb) DCASE_TRY(syncbn_allreduce_f64(sb, stats, 128, 3 * mid + l, s));
+        DCASE_TRY(launch_bn_finalize(stats, n_pix * world, params + o.bn_w[l], params + o.bn_b[l], bn_running + l * 128,
                                      training, bn, params + o.glu_w[l], params + o.glu_b[l], F_l, glu_img, s));
         DCASE_TRY(launch_glu_pool_fwd(ypre, n_pix, F_l, glu_img, drop(l), out, sms, s));
         in = out;
@@ -451,6 +462,9 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
     auto drop = [&](int layer) { return DropoutCfg{dropout, seed, step, (uint32_t)(8 * model_id + layer), sc}; };
     const int To = T / 8;
     const int BT = B * To;
+    const dcase_syncbn* sb = ctx->syncbn;                 // see dcase_crnn_forward
+    const long long world = syncbn_world(sb);
+    const float pgs = 1.f / (float)world;                 // BatchNorm-derived parameter gradients come out as GLOBAL sums
 
     DCASE_CUDA_CHECK(cudaMemsetAsync(grads, 0, (size_t)o.total * sizeof(float), s));
     DCASE_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(ws) + L.acc_off, 0, L.acc_bytes, s));
@@ -535,7 +549,8 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
         float* d_in = wsp<float>(ws, L, names[l][7]);
         DCASE_TRY(launch_glu_pool_bwd(ypre, n_pix, F_l, bn, wsp<float>(ws, L, l == 1 ? "gluimg1" : "gluimg2"), drop(l), d_out, dy,
                                       s12, grads + o.glu_w[l], grads + o.glu_b[l], sms, s));
-        DCASE_TRY(launch_bn_bwd_apply(dy, ypre, n_pix, bn, params + o.bn_w[l], s12, grads + o.bn_w[l],
+        if (sb) DCASE_TRY(syncbn_allreduce_f32(sb, s12, 128, 6 + l, s));
+        DCASE_TRY(launch_bn_bwd_apply(dy, ypre, n_pix, n_pix * world, bn, params + o.bn_w[l], s12, pgs, grads + o.bn_w[l],
                                       grads + o.bn_b[l], grads + o.conv_b[l], sms, s));
         // the weight gradient only feeds the optimizer: second stream, beside the data gradient and the next block
         DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_bwd_fork[1 + l], s));
@@ -550,8 +565,9 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
     const float* fold0 = wsp<float>(ws, L, "fold0");
     DCASE_TRY(launch_cnn0_bwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0),
                               wsp<float>(ws, L, "d_out0"), acc0, sms, s));
-    DCASE_TRY(launch_cnn0_bwd_finalize(wsp<double>(ws, L, "mom0"), (long long)B * T * 64, params + o.conv_w[0],
-                                       params + o.conv_b[0], fold0, params + o.glu_w[0], acc0, grads + o.conv_w[0],
+    if (sb) DCASE_TRY(syncbn_allreduce_f32(sb, acc0, kCnn0AccFloats, 6, s));     // mom0 was reduced by the forward
+    DCASE_TRY(launch_cnn0_bwd_finalize(wsp<double>(ws, L, "mom0"), (long long)B * T * 64 * world, params + o.conv_w[0],
+                                       params + o.conv_b[0], fold0, params + o.glu_w[0], acc0, pgs, grads + o.conv_w[0],
                                        grads + o.conv_b[0], grads + o.bn_w[0], grads + o.bn_b[0], grads + o.glu_w[0],
                                        grads + o.glu_b[0], s));
     for (int l = 0; l < 4; ++l) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_bwd_join[l], 0));
@@ -598,7 +614,9 @@ int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* a, void* stream) {
         // the teacher forward (no grad, main.py:87-89) is independent of the student forward until the losses:
         // fork it onto the context's second stream so the two overlap (latency-bound GRU / single-CTA kernels)
         DCASE_REQUIRE(a->params_t && a->bn_t && a->strong_t && a->weak_t && a->ws_t, "teacher buffers missing");
-        cudaStream_t ts = g_prof_on ? s : ctx->aux_stream;      // profiling: one stream, isolated kernel durations
+        // profiling: one stream, isolated kernel durations; SyncBN: both models' statistics exchanges spin on the peers,
+        // so they stay in ONE stream order that is the same on every rank
+        cudaStream_t ts = (g_prof_on || ctx->syncbn) ? s : ctx->aux_stream;
         DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
         DCASE_CUDA_CHECK(cudaStreamWaitEvent(ts, ctx->ev_fork, 0));
         DCASE_TRY(dcase_crnn_forward(ctx, a->x_teacher, a->B, a->T, a->n_class, a->params_t, a->bn_t, a->flags, a->seed,

@@ -133,7 +133,8 @@ cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restric
         atomicAdd(mom + threadIdx.x, s);
     }
     // the last block to arrive folds BatchNorm into the conv weights: saves the one-block launch that sat between this
-    // kernel and cnn0_fwd on the forward chain
+    // kernel and cnn0_fwd on the forward chain (SyncBN: the sums cross the ranks first, bn0_finalize_kernel folds)
+    if (fin.fold0 == nullptr) return;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
@@ -237,16 +238,16 @@ bn_finalize_kernel(const double* __restrict__ stats, long long n_pix, const floa
 
 // d_pre = a * (d_y - S1/N - xhat * S2/N)   (BatchNorm backward, batch statistics), in place.
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, long long n_pix,
-                    const float* __restrict__ bn, const float* __restrict__ s12, float* __restrict__ g_gamma,
-                    float* __restrict__ g_beta, float* __restrict__ g_conv_b) {
+bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, long long n_pix, long long n_stat,
+                    const float* __restrict__ bn, const float* __restrict__ s12, float param_grad_scale,
+                    float* __restrict__ g_gamma, float* __restrict__ g_beta, float* __restrict__ g_conv_b) {
     __shared__ float sa[64], sm[64], si[64], s1[64], s2[64];
     if (threadIdx.x < 64) {
         const int c = threadIdx.x;
-        const float inv_n = 1.f / (float)n_pix;
+        const float inv_n = 1.f / (float)n_stat;
         sa[c] = bn[kBnScale + c]; sm[c] = bn[kBnMean + c]; si[c] = bn[kBnInvstd + c];
         s1[c] = s12[c] * inv_n; s2[c] = s12[64 + c] * inv_n;
-        if (blockIdx.x == 0) { g_gamma[c] = s12[64 + c]; g_beta[c] = s12[c]; g_conv_b[c] = 0.f; }
+        if (blockIdx.x == 0) { g_gamma[c] = param_grad_scale * s12[64 + c]; g_beta[c] = param_grad_scale * s12[c]; g_conv_b[c] = 0.f; }
     }
     __syncthreads();
     const long long total = n_pix * 16;
@@ -271,6 +272,7 @@ int cnn_kernels_init() {
 
 int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running, float* fold0, int num_sms, cudaStream_t s) {
+    // fold0 == NULL: the moments alone (the caller reduces them over the ranks, then launch_bn0_finalize)
     DCASE_PROF("cnn0_moments", s);
     DCASE_CUDA_CHECK(cudaMemsetAsync(mom, 0, 55 * sizeof(double), s));       // 54 sums + the completion ticket
     const long long n_seg = (long long)B * ((T + kMomSeg - 1) / kMomSeg);
@@ -305,14 +307,14 @@ int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma,
     return DCASE_OK;
 }
 
-int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const float* bn, const float* gamma,
-                        const float* s12, float* g_gamma, float* g_beta, float* g_conv_b, int num_sms,
-                        cudaStream_t s) {
+int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, long long n_stat, const float* bn, const float* gamma,
+                        const float* s12, float param_grad_scale, float* g_gamma, float* g_beta, float* g_conv_b,
+                        int num_sms, cudaStream_t s) {
     DCASE_PROF("bn_bwd_apply", s);
     (void)gamma;
     long long blocks = (n_pix * 16 + 255) / 256;
     if (blocks > num_sms * 8) blocks = num_sms * 8;
-    bn_bwd_apply_kernel<<<(int)blocks, 256, 0, s>>>(d_y, ypre, n_pix, bn, s12, g_gamma, g_beta, g_conv_b);
+    bn_bwd_apply_kernel<<<(int)blocks, 256, 0, s>>>(d_y, ypre, n_pix, n_stat, bn, s12, param_grad_scale, g_gamma, g_beta, g_conv_b);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

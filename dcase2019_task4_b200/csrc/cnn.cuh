@@ -28,7 +28,7 @@ struct DropoutCfg {
     const DcaseStepScalars* sc;  // if non-null overrides seed/step (CUDA-graph replay)
 };
 
-// training: tap moments of the input AND (last block) the BN fold of block 0; eval: launch_bn0_finalize alone
+// training: tap moments of the input AND (last block, fold0 != NULL) the BN fold of block 0; eval: launch_bn0_finalize alone
 int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running, float* fold0, int num_sms, cudaStream_t s);
 int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
@@ -41,8 +41,9 @@ constexpr int kCnn0AccFloats = 128 * 16;   // {U[64][16], S2[64][16]}, zeroed be
 int launch_cnn0_bwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
                     DropoutCfg drop, const float* d_out, float* us, int num_sms, cudaStream_t s);
 int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
-                             const float* fold0, const float* glu_w, const float* us, float* g_conv_w, float* g_conv_b,
-                             float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b, cudaStream_t s);
+                             const float* fold0, const float* glu_w, const float* us, float param_grad_scale,
+                             float* g_conv_w, float* g_conv_b, float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b,
+                             cudaStream_t s);
 int cnn0_kernels_init();
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* glu_img, DropoutCfg drop, float* out,
                         int num_sms, cudaStream_t s);
@@ -64,9 +65,12 @@ int launch_bn_finalize(const double* stats, long long n_pix, const float* gamma,
 int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* bn, const float* glu_img, DropoutCfg drop,
                         const float* d_out, float* d_y, float* s12 /*[2][64]*/, float* g_glu_w, float* g_glu_b, int num_sms,
                         cudaStream_t s);
-int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, const float* bn, const float* gamma,
-                        const float* s12, float* g_gamma, float* g_beta, float* g_conv_b, int num_sms,
-                        cudaStream_t s);
+// s12 = {sum dy, sum dy xhat} over the n_stat pixels the statistics were taken over (n_pix local ones are rewritten);
+// the BatchNorm parameter gradients
+// are written as param_grad_scale x those sums (SyncBN: global sums, 1 / world_size so the gradient exchange restores them)
+int launch_bn_bwd_apply(float* d_y, const float* ypre, long long n_pix, long long n_stat, const float* bn, const float* gamma,
+                        const float* s12, float param_grad_scale, float* g_gamma, float* g_beta, float* g_conv_b,
+                        int num_sms, cudaStream_t s);
 int launch_conv_wgrad(const float* d_pre, const float* in, int B, int T_l, int F, float* g_w, int num_sms,
                       cudaStream_t s);
 int cnn_kernels_init();

@@ -656,7 +656,7 @@ constexpr int kBwdFinThreads = 640;
 __global__ void __launch_bounds__(kBwdFinThreads)
 cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix, const float* __restrict__ w,
                          const float* __restrict__ b, const float* __restrict__ fold0, const float* __restrict__ glu_w,
-                         const float* __restrict__ us, float* __restrict__ g_w, float* __restrict__ g_b,
+                         const float* __restrict__ us, float pgs, float* __restrict__ g_w, float* __restrict__ g_b,
                          float* __restrict__ g_gamma, float* __restrict__ g_beta, float* __restrict__ g_glu_w,
                          float* __restrict__ g_glu_b) {
     __shared__ float U[64][10], S[64][10], W0e[64][10];
@@ -674,9 +674,9 @@ cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix, const 
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 10; ++j) s = fmaf(U[n][j], W0e[k][j], s);
-        g_glu_w[i] = s;
+        g_glu_w[i] = pgs * s;
     }
-    if (tid < 64) g_glu_b[tid] = U[tid][9];
+    if (tid < 64) g_glu_b[tid] = pgs * U[tid][9];
     {                                                   // S[c][j] = sum_n Wg[n][c] U[n][j] + S2[c][j]
         const int c = tid / 10, j = tid - c * 10;
         float s = us[(64 + c) * 16 + j];
@@ -694,8 +694,8 @@ cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix, const 
     const double bm = (double)b[c] - mean;
     const double S2 = invstd * (wG + bm * S1);          // sum dY * xhat
     if (k == 9) {
-        g_gamma[c] = (float)S2;
-        g_beta[c] = (float)S1;
+        g_gamma[c] = pgs * (float)S2;
+        g_beta[c] = pgs * (float)S1;
         g_b[c] = 0.f;                                   // BN cancels the conv bias
         return;
     }
@@ -705,7 +705,7 @@ cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix, const 
         sxx += (double)w[c * 9 + l] * mom[9 + lo * 9 - (lo * (lo - 1)) / 2 + (hi - lo)];
     }
     sxx = invstd * (sxx + bm * mom[k]);
-    g_w[c * 9 + k] = (float)(av * ((double)S[c][k] - (S1 / n) * mom[k] - (S2 / n) * sxx));
+    g_w[c * 9 + k] = pgs * (float)(av * ((double)S[c][k] - (S1 / n) * mom[k] - (S2 / n) * sxx));
 }
 
 }  // namespace
@@ -741,10 +741,11 @@ int launch_cnn0_bwd(const float* x, int B, int T, const float* fold0, const floa
 }
 
 int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
-                             const float* fold0, const float* glu_w, const float* us, float* g_conv_w, float* g_conv_b,
-                             float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b, cudaStream_t s) {
+                             const float* fold0, const float* glu_w, const float* us, float param_grad_scale,
+                             float* g_conv_w, float* g_conv_b, float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b,
+                             cudaStream_t s) {
     DCASE_PROF("cnn0_bwd_finalize", s);
-    cnn0_bwd_finalize_kernel<<<1, kBwdFinThreads, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, glu_w, us, g_conv_w, g_conv_b, g_gamma,
+    cnn0_bwd_finalize_kernel<<<1, kBwdFinThreads, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, glu_w, us, param_grad_scale, g_conv_w, g_conv_b, g_gamma,
                                              g_beta, g_glu_w, g_glu_b);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;

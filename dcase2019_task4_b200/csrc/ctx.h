@@ -2,6 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 
+struct dcase_syncbn;
+// p2p.cu: sum `vals` over the ranks of the group in place (one single-CTA kernel, rank-ordered, replay-safe)
+int syncbn_world(const dcase_syncbn* h);
+int syncbn_allreduce_f64(const dcase_syncbn* h, double* vals, int n, int slot, cudaStream_t s);
+int syncbn_allreduce_f32(const dcase_syncbn* h, float* vals, int n, int slot, cudaStream_t s);
+
 struct dcase_ctx {
     int device;
     int num_sms;
@@ -23,6 +29,8 @@ struct dcase_ctx {
     cudaEvent_t ev_bwd_fork[4], ev_bwd_join[4];   // [0,1] GRU layers, [2,3] conv blocks 1, 2
     // scratch of the loss kernel: per-CTA partial sums + completion ticket (head_loss.cuh)
     float* d_loss_scratch;
+    // exact-global-batch BatchNorm under data parallelism (dcase_ctx_set_syncbn); NULL = per-replica statistics
+    dcase_syncbn* syncbn;
     // host copy of the dense filterbank for dcase_mel_filterbank()
     float* h_mel_dense;  // [64 * 1025]
 };

@@ -1,4 +1,5 @@
-// Data-parallel gradient exchange FUSED with the optimizer over NVLink peer memory -- EXPERIMENTAL.
+// Data-parallel exchanges over NVLink peer memory: (1) the gradient exchange FUSED with the optimizer, (2) the small
+// all-reduce of BatchNorm statistics behind the exact-global-batch mode (SyncBN, second half of this file).
 //
 // Replaces, under data parallelism, the pair  "NCCL all-reduce of the flat gradient slab" + "fused Adam + EMA kernel"
 // (loss.backward() / optimizer.step() / update_ema_variables of baseline/main.py:152-157, :45-49 on N replicas) by ONE
@@ -21,8 +22,8 @@
 // without host-side values.  A rank cannot run ahead by more than one step: its optimizer kernel of step e + 1 waits for
 // every peer's ready flag of step e + 1.
 //
-// STATUS (round 1): compiles for sm_100a; written after the round's GPU budget was spent -- not yet run on hardware.
-// Enabled only by DCASE_DP_P2P=1 (dcase2019_task4_b200/dp.py); the default data-parallel step uses NCCL.
+// STATUS: verified on 2 / 4 / 8 B200s in round 2 (tests/test_gpu_dp.py); the default exchange of MeanTeacherEngine for
+// world_size > 1 (DCASE_DP_NCCL=1 selects NCCL all-reduce + the plain optimizer kernel).
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -225,6 +226,169 @@ int dcase_p2p_destroy(dcase_p2p* h) {
     cudaDeviceSynchronize();
     for (int i = 0; i < h->n_opened; ++i) cudaIpcCloseMemHandle(h->opened[i]);
     cudaFree(h->d_peer_grads); cudaFree(h->d_peer_sync); cudaFree(h->sync); cudaFree(h->grads);
+    delete h;
+    return DCASE_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// SyncBN: exact-global-batch BatchNorm statistics under data parallelism
+// =====================================================================================================================
+// The reference at a global batch of 192 on ONE device normalises every BatchNorm2d over all 192 clips
+// (baseline/models/CNN.py:49 in train mode); per-replica statistics (the default here) normalise over the rank's 24.
+// This mode makes the N replicas reproduce the one-device result: the per-channel sums every BatchNorm needs -- forward
+// (sum x, sum x^2; block 0: the 54 tap moments of its input) and backward (sum dy, sum dy xhat; block 0: the {U | S2}
+// accumulator) -- are summed over the ranks between the kernel that produces them and the kernel that consumes them.
+//
+// One all-reduce = ONE single-CTA kernel per rank, no NCCL: every rank PUSHES its values into a mailbox in every peer's
+// memory (its own included), publishes an epoch flag next to it, spins on its LOCAL flags until every rank's values of
+// this epoch have arrived, and sums the world's contributions in rank order (all replicas obtain bit-identical sums).
+// Mailboxes are double buffered by epoch parity: a rank can be at most one epoch ahead of a peer on the same slot
+// (finishing epoch e + 1 needs the peer's flag of e + 1, which the peer only raises after it has read epoch e).  The
+// epoch counters live in device memory and are advanced by the kernel itself, so a captured CUDA graph replays.
+// Each (model, layer, direction) owns a slot; every rank issues the same sequence of collectives in stream order and,
+// in this mode, the teacher forward runs on the student's stream (two streams that spin on peers could map to one
+// hardware queue in a different order on different ranks).
+namespace {
+constexpr int kSyncSlots = 16;
+constexpr int kSyncSlotBytes = 8192;          // 2048 floats: the block-0 backward accumulator is the largest message
+
+__device__ __forceinline__ double ld_cv(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_cv(const float* p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+}  // namespace
+
+struct dcase_syncbn {
+    int world, rank;
+    unsigned char* mail;            // local: [slot][parity][rank][kSyncSlotBytes] | flags u32 [slot][world] | epochs u32 [slot]
+    size_t flags_off, epochs_off, bytes;
+    unsigned char** d_peer_mail;    // device array [world]
+    void* opened[kMaxWorld];
+    int n_opened;
+};
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+syncbn_allreduce_kernel(T* __restrict__ vals, int n, int slot, unsigned char* mail, unsigned char* const* __restrict__ peer_mail,
+                        size_t flags_off, size_t epochs_off, int world, int rank) {
+    __shared__ uint32_t epoch_s;
+    uint32_t* epochs = reinterpret_cast<uint32_t*>(mail + epochs_off);
+    if (threadIdx.x == 0) {
+        epoch_s = ld_volatile_u32(epochs + slot) + 1u;
+        st_volatile_u32(epochs + slot, epoch_s);
+    }
+    __syncthreads();
+    const uint32_t epoch = epoch_s;
+    const size_t box = ((size_t)(slot * 2 + (int)(epoch & 1u)) * world) * kSyncSlotBytes;
+    for (int r = 0; r < world; ++r) {                       // push: coalesced stores into every rank's mailbox
+        T* dst = reinterpret_cast<T*>(peer_mail[r] + box + (size_t)rank * kSyncSlotBytes);
+        for (int i = threadIdx.x; i < n; i += 256) dst[i] = vals[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        st_volatile_u32(reinterpret_cast<uint32_t*>(peer_mail[threadIdx.x] + flags_off) + slot * world + rank, epoch);
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(mail + flags_off) + slot * world + threadIdx.x;
+        while (!reached(ld_volatile_u32(mine), epoch)) __nanosleep(32);
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (int i = threadIdx.x; i < n; i += 256) {
+        T s = 0;
+        for (int r = 0; r < world; ++r)                     // fixed order: bit-identical on every rank
+            s += ld_cv(reinterpret_cast<const T*>(mail + box + (size_t)r * kSyncSlotBytes) + i);
+        vals[i] = s;
+    }
+}
+
+template <typename T>
+int syncbn_allreduce(const dcase_syncbn* h, T* vals, int n, int slot, cudaStream_t s) {
+    DCASE_REQUIRE(h && h->d_peer_mail, "SyncBN group not connected");
+    DCASE_REQUIRE(slot >= 0 && slot < kSyncSlots && n >= 1 && (size_t)n * sizeof(T) <= (size_t)kSyncSlotBytes, "bad slot / size");
+    DCASE_PROF("syncbn_allreduce", s);
+    syncbn_allreduce_kernel<T><<<1, 256, 0, s>>>(vals, n, slot, h->mail, h->d_peer_mail, h->flags_off, h->epochs_off,
+                                                 h->world, h->rank);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+}  // namespace
+
+int syncbn_world(const dcase_syncbn* h) { return h ? h->world : 1; }
+int syncbn_allreduce_f64(const dcase_syncbn* h, double* vals, int n, int slot, cudaStream_t s) {
+    return syncbn_allreduce<double>(h, vals, n, slot, s);
+}
+int syncbn_allreduce_f32(const dcase_syncbn* h, float* vals, int n, int slot, cudaStream_t s) {
+    return syncbn_allreduce<float>(h, vals, n, slot, s);
+}
+
+extern "C" {
+
+int dcase_syncbn_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int dcase_syncbn_create(dcase_ctx* ctx, int world, int rank, dcase_syncbn** out, void* handle_out) {
+    DCASE_REQUIRE(ctx && out && handle_out, "null argument");
+    DCASE_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "bad world / rank");
+    dcase_syncbn* h = new dcase_syncbn();
+    h->world = world; h->rank = rank; h->n_opened = 0; h->mail = nullptr; h->d_peer_mail = nullptr;
+    h->flags_off = (size_t)kSyncSlots * 2 * world * kSyncSlotBytes;
+    h->epochs_off = h->flags_off + (size_t)kSyncSlots * world * sizeof(uint32_t);
+    h->bytes = h->epochs_off + kSyncSlots * sizeof(uint32_t);
+    DCASE_CUDA_CHECK(cudaMalloc(&h->mail, h->bytes));
+    DCASE_CUDA_CHECK(cudaMemset(h->mail, 0, h->bytes));
+    DCASE_CUDA_CHECK(cudaMalloc(&h->d_peer_mail, world * sizeof(unsigned char*)));
+    DCASE_CUDA_CHECK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle_out, h->mail));
+    DCASE_CUDA_CHECK(cudaDeviceSynchronize());
+    *out = h;
+    return DCASE_OK;
+}
+
+// all_handles: world x dcase_syncbn_handle_bytes() bytes, rank-major
+int dcase_syncbn_connect(dcase_syncbn* h, const void* all_handles) {
+    DCASE_REQUIRE(h && all_handles, "null argument");
+    unsigned char* pm[kMaxWorld];
+    const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)all_handles;
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) { pm[r] = h->mail; continue; }
+        void* a = nullptr;
+        DCASE_CUDA_CHECK(cudaIpcOpenMemHandle(&a, hs[r], cudaIpcMemLazyEnablePeerAccess));
+        h->opened[h->n_opened++] = a;
+        pm[r] = (unsigned char*)a;
+    }
+    DCASE_CUDA_CHECK(cudaMemcpy(h->d_peer_mail, pm, h->world * sizeof(unsigned char*), cudaMemcpyHostToDevice));
+    return DCASE_OK;
+}
+
+// Attach (or with NULL detach) the group: from then on every train-mode forward / backward through this context
+// normalises over the global batch.
+int dcase_ctx_set_syncbn(dcase_ctx* ctx, dcase_syncbn* h) {
+    DCASE_REQUIRE(ctx, "null context");
+    DCASE_REQUIRE(!h || h->d_peer_mail, "SyncBN group not connected");
+    ctx->syncbn = h;
+    return DCASE_OK;
+}
+
+int dcase_syncbn_allreduce(dcase_syncbn* h, void* vals, int n, int is_double, int slot, void* stream) {
+    DCASE_REQUIRE(h && vals, "null argument");
+    return is_double ? syncbn_allreduce<double>(h, (double*)vals, n, slot, (cudaStream_t)stream)
+                     : syncbn_allreduce<float>(h, (float*)vals, n, slot, (cudaStream_t)stream);
+}
+
+int dcase_syncbn_destroy(dcase_syncbn* h) {
+    if (!h) return DCASE_OK;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < h->n_opened; ++i) cudaIpcCloseMemHandle(h->opened[i]);
+    cudaFree(h->d_peer_mail); cudaFree(h->mail);
     delete h;
     return DCASE_OK;
 }

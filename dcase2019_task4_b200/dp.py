@@ -4,7 +4,8 @@ Batches shard PER STREAM so every rank keeps the ``[weak | unlabeled | synthetic
 main.py:240-247 stay valid; equal per-rank sub-batch sizes make the mean of the per-rank mean losses equal the
 global mean loss for all four loss terms.  The only exchange step is ONE all-reduce (SUM) of the flat 214,356-float
 gradient slab; the 1/world_size scale is folded into the fused Adam + EMA kernel (``grad_scale``).  Adam and EMA run
-replicated.  BatchNorm statistics stay per replica (the reference's own batch of 24 per device)."""
+replicated.  BatchNorm statistics stay per replica by default (the reference's own batch of 24 per device);
+``SyncBatchNorm`` switches the context to exact-global-batch statistics."""
 import os
 
 import torch
@@ -62,8 +63,8 @@ class _RawCudaArray(object):
 
 
 class P2PGradExchange(object):
-    """EXPERIMENTAL (DCASE_DP_P2P=1; compiles, not yet run on hardware): the gradient exchange fused with Adam + EMA
-    over NVLink peer memory (csrc/p2p.cu).  ``grads`` is a torch view of the library-owned, IPC-exported slab the
+    """The gradient exchange fused with Adam + EMA over NVLink peer memory (csrc/p2p.cu; the default of
+    ``MeanTeacherEngine`` for world_size > 1).  ``grads`` is a torch view of the library-owned, IPC-exported slab the
     backward writes into; ``begin_step`` goes before the backward, ``adam_ema_step`` replaces all-reduce + optimizer."""
 
     def __init__(self, n_floats, group=None):
@@ -95,4 +96,42 @@ class P2PGradExchange(object):
     def close(self):
         if self.handle:
             self._lib.lib().dcase_p2p_destroy(self.handle)
+            self.handle = None
+
+
+class SyncBatchNorm(object):
+    """Exact-global-batch BatchNorm statistics (the reference's models/CNN.py:49 at a global batch of N x 24 on ONE
+    device): while an instance is attached, every train-mode forward / backward of this process's context sums the
+    per-channel BatchNorm sums over the ranks (csrc/p2p.cu, one single-CTA peer-memory kernel per BatchNorm, replays
+    inside the step's CUDA graph).  Every rank must then issue the same sequence of train-mode calls.  ``close()``
+    returns to per-replica statistics (the default: the reference's semantics at its own batch of 24 per device)."""
+
+    def __init__(self, group=None):
+        import ctypes
+        from . import _lib
+        self._lib = _lib
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = _lib.lib()
+        blob = ctypes.create_string_buffer(L.dcase_syncbn_handle_bytes())
+        self.handle = ctypes.c_void_p()
+        _lib.check(L.dcase_syncbn_create(_lib.ctx(), self.world, self.rank, ctypes.byref(self.handle), blob))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(blob.raw), group=group)
+        self._all = ctypes.create_string_buffer(b"".join(gathered))
+        _lib.check(L.dcase_syncbn_connect(self.handle, self._all))
+        dist.barrier(group)                                   # every rank has mapped every mailbox before anyone pushes
+        _lib.check(L.dcase_ctx_set_syncbn(_lib.ctx(), self.handle))
+
+    def allreduce_(self, t, slot=15):
+        """Sum a small float32 / float64 CUDA tensor over the group in place (tests; slots 0-8 belong to the CRNN path)."""
+        self._lib.check(self._lib.lib().dcase_syncbn_allreduce(self.handle, self._lib.ptr(t), t.numel(),
+                                                               1 if t.dtype == torch.float64 else 0, int(slot),
+                                                               self._lib.stream_ptr()))
+        return t
+
+    def close(self):
+        if self.handle:
+            torch.cuda.synchronize()
+            self._lib.check(self._lib.lib().dcase_ctx_set_syncbn(self._lib.ctx(), None))
+            self._lib.lib().dcase_syncbn_destroy(self.handle)
             self.handle = None

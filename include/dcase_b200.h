@@ -208,7 +208,7 @@ int dcase_adam_ema_step(dcase_ctx* ctx, float* p, const float* g, float* m, floa
                         float lr, float beta1, float beta2, float eps, int step_t, float ema_alpha,
                         float grad_scale, const void* scalars, void* stream);
 
-/* ---- EXPERIMENTAL (compiles, not yet run on hardware): data-parallel gradient exchange fused with the optimizer ---- */
+/* ---- data-parallel gradient exchange fused with the optimizer (verified on 2 / 4 / 8 GPUs, tests/test_gpu_dp.py) ---- */
 /* Under data parallelism (one process per GPU of one node) the pair "all-reduce of the gradient slab" +
  * dcase_adam_ema_step becomes ONE kernel that reads every rank's slab out of the peers' HBM over NVLink (CUDA IPC
  * mappings), sums in rank order, and applies Adam + EMA (main.py:152-157, :45-49 on N replicas).  csrc/p2p.cu describes
@@ -226,6 +226,28 @@ int dcase_p2p_adam_ema_step(dcase_ctx* ctx, dcase_p2p* h, float* p, float* m, fl
                             float beta1, float beta2, float eps, int step_t, float ema_alpha, const void* scalars,
                             void* stream);
 int dcase_p2p_destroy(dcase_p2p* h);
+
+/* ---- SyncBN: exact-global-batch BatchNorm statistics under data parallelism ---------------------- */
+/* The reference run at a global batch of N x 24 on one device normalises each BatchNorm2d over ALL clips
+ * (models/CNN.py:49, train mode).  With a group attached to the context, every train-mode dcase_crnn_forward /
+ * dcase_crnn_backward / dcase_mt_fwd_bwd sums the per-channel statistics (forward: sum x, sum x^2 -- block 0: the tap
+ * moments of its input; backward: sum dy, sum dy xhat -- block 0: its {U | S2} accumulator) over the ranks with one
+ * single-CTA kernel per BatchNorm (peer-memory mailboxes + epoch flags, csrc/p2p.cu; no NCCL, replays inside a CUDA
+ * graph), so N replicas reproduce the one-device result.  BatchNorm-derived parameter gradients are written as
+ * global / N: the gradient exchange (sum, then x 1/N) restores them.  Every rank must issue the same sequence of
+ * train-mode calls; the teacher forward runs on the student's stream in this mode.  Default (no group): per-replica
+ * statistics, the reference's semantics at its own batch of 24 per device.
+ * Set-up mirrors dcase_p2p_*: create (returns dcase_syncbn_handle_bytes() bytes of IPC handle into HOST memory),
+ * exchange the blobs, connect(world x blob, rank-major), dcase_ctx_set_syncbn(ctx, h) (NULL detaches). */
+typedef struct dcase_syncbn dcase_syncbn;
+int dcase_syncbn_handle_bytes(void);
+int dcase_syncbn_create(dcase_ctx* ctx, int world, int rank, dcase_syncbn** out, void* handle_out_host);
+int dcase_syncbn_connect(dcase_syncbn* h, const void* all_handles_host);
+int dcase_ctx_set_syncbn(dcase_ctx* ctx, dcase_syncbn* h);
+/* the collective itself (sum in place over the group, n * elem <= 8192 bytes, slot in [0,16): slots 0-8 are used by
+ * the CRNN path): exposed for tests */
+int dcase_syncbn_allreduce(dcase_syncbn* h, void* vals_dev, int n, int is_double, int slot, void* stream);
+int dcase_syncbn_destroy(dcase_syncbn* h);
 
 /* ---- one mean-teacher iteration, main.py:84-153 (forward x2, losses, backward) ----------------------- */
 typedef struct dcase_mt_args {
