@@ -29,11 +29,18 @@ namespace {
 constexpr int kTile = 128;
 constexpr float kTruncComp = 1.f + 3.5221e-4f;
 constexpr float kLog2e = 1.4426950408889634f;
-// The gate sigmoid(y) is the block's MUFU load (84.9 M activations per pass).  The tensor core produces a pre-scaled
-// ys = kGateScale * y directly (W0 carries the factor; y itself only feeds MMA1, lin = y Wg^T, whose constant operand Wg
-// carries the inverse factor), so no multiply per element is spent on the argument:
-//   DCASE_GATE_TANH (default): ys = y / 2,        g = 0.5 tanh.approx(ys) + 0.5       1 MUFU + 1 FFMA per element
-//   otherwise:                 ys = -log2(e) y,   g = rcp(1 + ex2(ys))                2 MUFU + 1 FADD per element
+// The gate sigmoid(y) is the block's MUFU load (84.9 M activations per pass) and the per-element CUDA-core work around it
+// bounds both kernels, so everything that can ride on the tensor core does:
+//   * MMA0 produces a pre-scaled ys = kGateScale * y (W0 carries the factor), MMA1's constant operand carries the inverse;
+//   * the GLU bias rides in MMA1 as one more K = 8 slice: the tap rows hold two constant-1 columns and rows 64..127 of the
+//     T0 block (free: W0 only has 64 rows) hold [0.5 b_hi | 0.5 b_lo] against them, so MMA1 delivers u = (lin + b) / 2;
+//   * with a = tanh(y / 2) (one MUFU): sigmoid(y) = (1 + a) / 2, hence
+//       forward   z  = (lin + b) g           = fma(u, a, u)                 dropout: a := -1 gives exactly 0
+//       backward  DL = dz g                  = 1/2 * fma(dz, a, dz)
+//                 D2 = dz (lin + b) g (1-g)  = -1/2 * (dz u) (a a - 1)
+//     all as packed f32x2 instructions; the +-1/2 and the pool / dropout scale of dz are applied once to the [128][16]
+//     accumulator at the end of the backward (DL and D2 only feed that linear reduction).
+//   DCASE_GATE_TANH (default): ys = y / 2, a = tanh.approx(ys);  otherwise ys = -log2(e) y, a = 2 rcp(1 + ex2(ys)) - 1.
 // tanh.approx.f32 has a relative error of up to 2^-11 (|dg| <= 2.4e-4); measured effect on the frame posteriors:
 // tests/test_gpu_fullsize.py prints it, tools/precision_modes.py models it.
 #ifndef DCASE_GATE_TANH
@@ -46,6 +53,7 @@ constexpr float kGateUnscale = 2.0f;
 constexpr float kGateScale = -kLog2e;
 constexpr float kGateUnscale = -0.6931471805599453f;
 #endif
+constexpr float kLinScale = 0.5f * kGateUnscale;      // MMA1 delivers u = (lin + b) / 2 from the pre-scaled ys
 
 struct Cnn0Args {
     const float* x;        // [B][T][64] z-scored log-mel
@@ -93,9 +101,34 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
+// packed fp32 pairs (FFMA2 / FMUL2 on sm_100): half the issue slots of the per-element gate arithmetic
+__device__ __forceinline__ uint64_t pk(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void sts128_2(uint32_t addr, uint64_t lo, uint64_t hi) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(lo), "l"(hi) : "memory");
+}
+
 // x rows t0-1 .. t0+2 (zero padded) of a tile = xs[4][66]; thread t of 256 owns elements t and (t < 8) t + 256.
 // The tile's (clip, first frame) pair is carried incrementally (32-bit): a 64-bit division per tile and thread was
 // 30 % of the kernel's instructions.
+// rounds to the nearest tf32 (ties away), finite inputs only: 2 instructions instead of cvt.rna's 3
+__device__ __forceinline__ float tf32_round_fast(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 struct XsRegs { float v0, v1; };
 struct TilePos {          // tile -> clip b, first frame t0
     int b, t0;
@@ -121,32 +154,28 @@ __device__ __forceinline__ XsRegs xs_prefetch(const float* __restrict__ x, const
     r.v1 = t + 256 < 4 * 66 ? xs_value(x, p, T, t + 256) : 0.f;
     return r;
 }
-__device__ __forceinline__ void xs_commit(const XsRegs& r, float* xs, int t) {
-    xs[t] = r.v0;
-    if (t + 256 < 4 * 66) xs[t + 256] = r.v1;
+__device__ __forceinline__ void xs_commit(const XsRegs& r, float* xs, int t) {     // MMA0 operand: rounded to tf32 once, here
+    xs[t] = tf32_round_fast(r.v0);
+    if (t + 256 < 4 * 66) xs[t + 256] = tf32_round_fast(r.v1);
 }
 
-// rounds to the nearest tf32 (ties away), finite inputs only: 2 instructions instead of cvt.rna's 3
-__device__ __forceinline__ float tf32_round_fast(float x) {
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-}
-
-// operand rows of MMA0 for pixel `row` of a tile: [tap0..8, 1, 0, 0] -> chunks 0..2 of its row
+// operand rows of MMA0 for pixel `row` of a tile: [tap0..8, 1, 1, 0] -> chunks 0..2 of its row (column 9 meets the folded
+// conv bias in MMA0 and 0.5 b_hi in MMA1's bias slice, column 10 meets 0.5 b_lo; W0 is zero there)
 __device__ __forceinline__ void write_taps(const float* xs, int row, uint32_t t0_rowbase) {
     const int tr = row >> 6, f = row & 63;
     float tap[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) tap[k] = tf32_round_fast(xs[(tr + k / 3) * 66 + f + (k % 3)]);
+    for (int k = 0; k < 9; ++k) tap[k] = xs[(tr + k / 3) * 66 + f + (k % 3)];
     sts128(chunk_addr(t0_rowbase, 0), tap[0], tap[1], tap[2], tap[3]);
     sts128(chunk_addr(t0_rowbase, 1), tap[4], tap[5], tap[6], tap[7]);
-    sts128(chunk_addr(t0_rowbase, 2), tap[8], 1.f, 0.f, 0.f);
+    sts128(chunk_addr(t0_rowbase, 2), tap[8], 1.f, 1.f, 0.f);
 }
 
 // Wg[n][k] -> K-major SW128 B operand (two blocks of 64 rows), rounded to tf32 after the truncation compensation
 __device__ __forceinline__ void stage_wg(const float* __restrict__ glu_w, unsigned char* Wb, int t, int nt) {
     for (int i = t; i < 4096; i += nt) {
         const int n = i >> 6, k = i & 63;
-        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kGateUnscale * kTruncComp * __ldg(glu_w + i));
+        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kLinScale * kTruncComp * __ldg(glu_w + i));
     }
 }
 
@@ -163,6 +192,18 @@ __device__ __forceinline__ void stage_w0(const float* __restrict__ fold0, unsign
         *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(n, 4 + c)) = tc::tf32_rn4(make_float4(v[0], v[1], v[2], v[3]));
     }
     for (int r = t; r < 128; r += nt) *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(r, 3)) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// GLU bias as the B operand of MMA1's extra K = 8 slice: rows 64 + n of the T0 block, logical columns 24..31 (they face
+// the tap rows' columns 8..15 = [tap8, 1, 1, 0 | 0 0 0 0]): [0, hi, lo, 0 | 0 0 0 0] with hi + lo = b[n] / 2 to 2^-22
+__device__ __forceinline__ void stage_bias(const float* __restrict__ glu_b, unsigned char* T0, int t, int nt) {
+    for (int n = t; n < 64; n += nt) {
+        const float b = 0.5f * __ldg(glu_b + n);
+        const float hi = tc::tf32_rn(b), lo = tc::tf32_rn(b - hi);
+        *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(64 + n, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(64 + n, 5)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(64 + n, 6)) = make_float4(0.f, hi, lo, 0.f);
+        *reinterpret_cast<float4*>(T0 + tc::sw128_chunk(64 + n, 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // The MMA issue helpers are called by ALL lanes of one warp with warp-uniform arguments (tc.cuh: one lane is elected
@@ -185,12 +226,16 @@ __device__ __forceinline__ void issue_mma1(uint32_t d_tmem, uint32_t a_addr, uin
 // lin = y Wg^T with y read IN PLACE from the MMA0 accumulator in tensor memory (an M = 128 accumulator has exactly the
 // [lane = row][column = k] layout of a TMEM A operand): no shared-memory round trip for y, and the GEMM can be issued the
 // moment MMA0 has completed, before any thread has touched y
-__device__ __forceinline__ void issue_mma1_tmem(uint32_t d_tmem, uint32_t y_tmem, uint32_t wb_addr) {
+// The first instruction is the bias slice (stage_bias): A = columns 8..15 of the tap rows, still in shared memory.  The
+// next tile's taps may be written under it: the constant columns are rewritten with the same values and tap8 meets a
+// zero row of B.
+__device__ __forceinline__ void issue_mma1_tmem(uint32_t d_tmem, uint32_t y_tmem, uint32_t wb_addr, uint32_t t0_addr) {
     constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
     const uint32_t b_lo = tc::desc_lo(wb_addr, 16), hi = tc::desc_hi(1024, 2);
+    tc::umma_tf32_elect(d_tmem, tc::desc_lo(t0_addr, 16) + 2, hi, tc::desc_lo(t0_addr + 8192, 16) + 4 + 2, hi, idesc, 0u);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        tc::umma_tf32_tmem_a_elect(d_tmem, y_tmem + 8 * j, b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, j > 0 ? 1u : 0u);
+        tc::umma_tf32_tmem_a_elect(d_tmem, y_tmem + 8 * j, b_lo + (((j >> 2) * 8192 + (j & 3) * 32) >> 4), hi, idesc, 1u);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -199,20 +244,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     tc::tmem_ld_wait();
 }
 
-// g[i] = sigmoid(y[i]) for 32 values of the pre-scaled ys (see kGateScale)
-__device__ __forceinline__ void sigmoid32(const float (&y)[32], float (&g)[32]) {
+// a[i] = tanh(y[i] / 2) = 2 sigmoid(y[i]) - 1 for 32 values of the pre-scaled ys (see kGateScale)
+__device__ __forceinline__ void tanh32(const float (&y)[32], float (&a)[32]) {
 #if DCASE_GATE_TANH
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        float t;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(y[i]));
-        g[i] = fmaf(t, 0.5f, 0.5f);
-    }
+    for (int i = 0; i < 32; ++i) asm("tanh.approx.f32 %0, %1;" : "=f"(a[i]) : "f"(y[i]));
 #else
 #pragma unroll
-    for (int i = 0; i < 32; ++i) g[i] = ex2_ftz(y[i]);
+    for (int i = 0; i < 32; ++i) a[i] = ex2_ftz(y[i]);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) g[i] = rcp_ftz(1.f + g[i]);
+    for (int i = 0; i < 32; ++i) a[i] = fmaf(2.f, rcp_ftz(1.f + a[i]), -1.f);
 #endif
 }
 
@@ -223,16 +264,41 @@ __device__ __forceinline__ void require_aligned_smem(const void* p) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-// Software pipeline per CTA (3 CTAs / SM): MMA0 of the NEXT tile is issued together with MMA1 of the current one
-// and the next tile's x rows are prefetched into registers, so the only tensor-core round trip a tile waits for
-// is MMA1; the pooled result of tile i is drained while tile i + 1 computes.
-// smem (1024-B aligned, all dynamic): Wb 16 KB | T0 16 KB | A 32 KB (y K-major, then z MN-major) | P 8 KB |
-//                                     bg[64] | xs[4][66] | keep_lo[128] | 3 mbarriers | tmem base
-// TMEM (128 columns): [0,64) y (next tile's y while the current tile is in its GLU phase),
-//                     [64,128) lin, then [64,80) the pooled output (M = 64 channels, N = 16 windows)
-constexpr int kFwdWb = 0, kFwdT0 = 16384, kFwdA = 32768, kFwdP = 65536, kFwdMisc = 73728;
-constexpr int kFwdSmemBytes = kFwdMisc + 64 * 4 + 4 * 66 * 4 + 128 * 4 + 3 * 8 + 8;
+// Software pipeline per CTA (3 CTAs / SM), two block barriers per tile:
+//   top      MMA0 of this tile has completed (it was issued during the previous tile): MMA1 is issued at once
+//   phase P  the PREVIOUS tile's z is average-pooled from shared memory on the CUDA cores (thread = one window x four
+//            channels: 8 conflict-free 16-byte loads, one coalesced 16-byte store) -- under MMA1.  Round 2 replaced the
+//            pooling MMA (16 x M64 N16 K8 + commit, ~900 tensor-pipe cycles per tile and a third round trip, whose result
+//            also blocked the lin columns of tensor memory) by these ~40 instructions per thread
+//   phase D  operand rows of the NEXT tile (taps / dropout bits), x rows of the tile after it prefetched into registers,
+//            a = tanh(y / 2) from tensor memory
+//   barrier A, then MMA0 of the next tile;  phase F  z = u (1 + a) -> shared memory;  barrier C
+// smem (1024-B aligned, all dynamic): Wb 16 KB | T0 16 KB | Z 32 KB (swizzled rows of 64 channels) |
+//                                     xs[4][66] | keep_lo[128] | 2 mbarriers | tmem base
+// TMEM (128 columns): [0,64) y (the next tile's y from barrier A on), [64,128) u = (lin + b) / 2
+constexpr int kFwdWb = 0, kFwdT0 = 16384, kFwdA = 32768, kFwdMisc = 65536;
+constexpr int kFwdSmemBytes = kFwdMisc + 4 * 66 * 4 + 128 * 4 + 2 * 8 + 8;
 constexpr int kFwdThreads = 256;
+
+// average pool of one tile from its z rows in shared memory: thread = (window w, channels 4 c4 .. 4 c4 + 3)
+__device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scale, float* __restrict__ out_tile) {
+    const int w = tid >> 4, c4 = tid & 15;
+    const uint32_t base = z_region + (uint32_t)((w >> 1) * 1024 + (c4 >> 3) * 16384);
+    const int r0 = 4 * (w & 1);                       // rows 4 w + j of frame tr: 8-row group w / 2 (+ 8 tr), row r0 + j inside it
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t addr = base + (uint32_t)((r0 + j) * 128 + ((((r0 + j) ^ c4) & 7) << 4));
+#pragma unroll
+        for (int tr = 0; tr < 2; ++tr) {
+            const float4 v = lds128(addr + tr * 8192);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    *reinterpret_cast<float4*>(out_tile + w * 64 + 4 * c4) =            // conv1's MMA operand: rounded to tf32
+        make_float4(tf32_round_fast(scale * acc.x), tf32_round_fast(scale * acc.y), tf32_round_fast(scale * acc.z),
+                    tf32_round_fast(scale * acc.w));
+}
 
 __global__ void __launch_bounds__(kFwdThreads, 3)
 cnn0_fwd_kernel(Cnn0Args a) {
@@ -240,43 +306,40 @@ cnn0_fwd_kernel(Cnn0Args a) {
     require_aligned_smem(smem);
     unsigned char* Wb = smem + kFwdWb;
     unsigned char* T0 = smem + kFwdT0;
-    unsigned char* Pm = smem + kFwdP;
-    float* bg = reinterpret_cast<float*>(smem + kFwdMisc);
-    float* xs = bg + 64;
+    float* xs = reinterpret_cast<float*>(smem + kFwdMisc);
     uint32_t* keep_lo = reinterpret_cast<uint32_t*>(xs + 4 * 66);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(keep_lo + 128);     // [0] MMA0, [1] MMA1, [2] MMA2 (pool)
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 3);
-    const int tid = threadIdx.x, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(keep_lo + 128);     // [0] MMA0, [1] MMA1
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
     const int row = tid & 127, half = tid >> 7;
 
     stage_wg(a.glu_w, Wb, tid, kFwdThreads);
     stage_w0(a.fold0, T0, tid, kFwdThreads);
-    for (int i = tid; i < 16 * 128; i += kFwdThreads) {    // P[w][p] = 1 if pixel p = (tr, f) lies in window w = f / 4
-        const int w = i >> 7, p = i & 127;
-        *reinterpret_cast<float*>(Pm + (p >> 5) * 2048 + tc::sw128_off(w, p & 31)) = (((p & 63) >> 2) == w) ? 1.f : 0.f;
-    }
-    if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
-    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1); tc::fence_mbar_init(); }
+    stage_bias(a.glu_b, T0, tid, kFwdThreads);
+    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 128);
     uint64_t seed = a.drop.seed; uint32_t step = a.drop.step;
     if (a.drop.sc) { seed = a.drop.sc->seed; step = a.drop.sc->step; }
     const long long n_tiles = (long long)a.B * a.T / 2;
     const long long stride = gridDim.x;
     long long cur = blockIdx.x;
-    const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), a_a = tc::smem_u32(smem + kFwdA), p_a = tc::smem_u32(Pm);
-    const uint32_t t0_rb = krow_base(t0_a, row), y_rb = krow_base(a_a, row), z_rb = mnrow_base(a_a, row);
+    const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), a_a = tc::smem_u32(smem + kFwdA);
+    const uint32_t t0_rb = krow_base(t0_a, row), z_rb = krow_base(a_a, row);
     const bool drop = a.drop.enabled != 0;
 
-    // prologue: operands of the first tile, its MMA0, and the x rows of the second tile in registers
+    // prologue: operand rows of the first tile and its MMA0; x rows of the second tile in shared memory, of the third in
+    // registers
     uint32_t keep_next = 0xffffffffu;       // keep bits (this thread's 32 channels) of the tile whose MMA0 is in flight
     TilePos pos;                            // position of the tile whose x rows are fetched next
     pos.init(cur, a.T);
     const int pos_step = (int)(2 * stride);
     {
-        XsRegs xr = xs_prefetch(a.x, pos, a.T, tid);
-        xs_commit(xr, xs, tid);
+        XsRegs x0 = xs_prefetch(a.x, pos, a.T, tid);
+        xs_commit(x0, xs, tid);
     }
+    pos.advance(pos_step, a.T);
+    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, pos, a.T, tid) : XsRegs{0.f, 0.f};
     __syncthreads();
     const uint32_t tmem = *tmem_base_s;
     if (half == 0) write_taps(xs, row, t0_rb);
@@ -291,13 +354,13 @@ cnn0_fwd_kernel(Cnn0Args a) {
     tc::fence_after_sync();
     if (warp == 0) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
     if (drop && half == 0) keep_next = keep_lo[row];
+    xs_commit(xr, xs, tid);                 // the second tile's rows (the first tile's have been consumed)
     pos.advance(pos_step, a.T);
-    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, pos, a.T, tid) : XsRegs{0.f, 0.f};
+    __syncthreads();
 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ph0 = 0, ph1 = 0, ph2 = 0;
-    // 1/8 window, x2 inverted dropout, truncation of z undone here (P is exactly 1)
-    const float pool_scale = (drop ? 0.25f : 0.125f) * kTruncComp;
+    uint32_t ph0 = 0, ph1 = 0;
+    const float pool_scale = drop ? 0.25f : 0.125f;      // 1/8 window, x2 inverted dropout
     long long prev = -1;
 
 #ifdef DCASE_CNN0_TIMING
@@ -316,37 +379,17 @@ cnn0_fwd_kernel(Cnn0Args a) {
         const uint32_t keep = keep_next;
         TICK();
         tc::mbar_wait(&bars[0], ph0);            // y of `cur` is in TMEM; T0 may be rewritten
-        TOCK(0);
-        TICK();
         ph0 ^= 1;
         tc::fence_after_sync();
-        if (prev >= 0) {                          // pooled tile `prev`: TMEM -> out; frees the lin columns and the z buffer
-            tc::mbar_wait(&bars[2], ph2);
-            ph2 ^= 1;
-            tc::fence_after_sync();
-            if (warp < 4) {
-                float v[16];
-                tc::tmem_ld16(tmem + 64 + lane_base, v);
-                tc::tmem_ld_wait();
-                if (lane < 16) {                  // accumulator row m of an M=64 MMA lives in lane 32*(m/16) + m%16
-                    float* dst = a.out + prev * 16 * 64 + 16 * warp + lane;
-#pragma unroll
-                    for (int w = 0; w < 16; ++w) dst[w * 64] = tc::tf32_rn(pool_scale * v[w]);   // conv1 MMA operand
-                }
-            }
-        }
-        TOCK(2);
-        TICK();
-        if (has_next) xs_commit(xr, xs, tid);
-        tc::fence_before_sync();
-        __syncthreads();                          // the pooled tile has been read by everybody; xs of `nxt` is complete
-        TOCK(1);
-        TICK();
-        if (warp == 0) {                          // MMA1 runs under the gate phase below: y is read from tensor memory
-            tc::fence_after_sync();
-            issue_mma1_tmem(tmem + 64, tmem, wb_a);
+        if (warp == 0) {                          // MMA1 at once: y is read from tensor memory; the u columns were drained by
+            issue_mma1_tmem(tmem + 64, tmem, wb_a, t0_a);      // every thread before barrier C of the previous tile
             tc::umma_commit_elect(&bars[1]);
         }
+        TOCK(0);
+        TICK();
+        if (prev >= 0) pool_tile(a_a, tid, pool_scale, a.out + prev * 16 * 64);     // z of `prev`: complete since barrier C
+        TOCK(1);
+        TICK();
         uint32_t keep_hi_next = 0xffffffffu;
         if (has_next) {
             if (half == 0) write_taps(xs, row, t0_rb);
@@ -355,31 +398,33 @@ cnn0_fwd_kernel(Cnn0Args a) {
                 keep_lo[row] = r.x;
                 keep_hi_next = r.y;
             }
-            pos.advance(pos_step, a.T);
             if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, pos, a.T, tid);
+            pos.advance(pos_step, a.T);
         }
-        float g[32];
+        TOCK(2);
+        TICK();
+        float g[32];                              // a = tanh(y / 2); z = u (1 + a)
         {
             float y[32];
             tmem_ld32(tmem + lane_base + 32 * half, y);
             tc::fence_before_sync();
-            sigmoid32(y, g);
+            tanh32(y, g);
         }
         tc::fence_proxy_async();                  // the taps of `nxt`
         TOCK(3);
         TICK();
-        __syncthreads();                          // everybody holds its y: MMA0 of `nxt` may overwrite the columns
+        __syncthreads();                          // A: everybody holds its y, has pooled `prev` and written the rows of `nxt`
         TOCK(4);
         TICK();
         if (warp == 0 && has_next) {
-            tc::mbar_wait(&bars[1], ph1);         // MMA1 has read y (long done: it ran under the gate phase); an MMA that
+            tc::mbar_wait(&bars[1], ph1);         // MMA1 has read y (long done: it ran under phases P and D); an MMA that
             tc::fence_after_sync();               // overwrites a TMEM A operand must not be queued behind its reader
             issue_mma0(tmem, t0_a);
             tc::umma_commit_elect(&bars[0]);
         }
         if (drop) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) g[i] = (keep & (1u << i)) ? g[i] : 0.f;
+            for (int i = 0; i < 32; ++i) g[i] = (keep & (1u << i)) ? g[i] : -1.f;     // u * (-1) + u = 0 exactly
             keep_next = half ? keep_hi_next : keep_lo[row];
         }
         tc::mbar_wait(&bars[1], ph1);
@@ -388,32 +433,20 @@ cnn0_fwd_kernel(Cnn0Args a) {
         ph1 ^= 1;
         tc::fence_after_sync();
         {
-            float lin[32];
-            tmem_ld32(tmem + 64 + lane_base + 32 * half, lin);
+            float u[32];
+            tmem_ld32(tmem + 64 + lane_base + 32 * half, u);
             tc::fence_before_sync();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bg + 32 * half + 4 * q);
-                sts128(chunk_addr(z_rb, 8 * half + q),           // overwrites y (MMA1 has completed)
-                       (lin[4 * q + 0] + b4.x) * g[4 * q + 0], (lin[4 * q + 1] + b4.y) * g[4 * q + 1],
-                       (lin[4 * q + 2] + b4.z) * g[4 * q + 2], (lin[4 * q + 3] + b4.w) * g[4 * q + 3]);
+                const uint64_t u01 = pk(u[4 * q], u[4 * q + 1]), u23 = pk(u[4 * q + 2], u[4 * q + 3]);
+                sts128_2(chunk_addr(z_rb, 8 * half + q),
+                         fma2(u01, pk(g[4 * q], g[4 * q + 1]), u01), fma2(u23, pk(g[4 * q + 2], g[4 * q + 3]), u23));
             }
         }
-        tc::fence_proxy_async();
+        if (has_next && nxt + stride < n_tiles) xs_commit(xr, xs, tid);      // rows of the tile after `nxt` (those of `nxt` were consumed before A)
         TOCK(6);
         TICK();
-        __syncthreads();
-        if (warp == 0) {                   // MMA2: pooled[n][w] = sum_p z[p][n] P[w][p];  A MN-major (z), B K-major (P)
-            tc::fence_after_sync();
-            constexpr uint32_t idesc = tc::idesc_tf32(64, 16, 1, 0);
-            const uint32_t z_lo = tc::desc_lo(a_a, 16384), p_lo = tc::desc_lo(p_a, 16);
-            const uint32_t mn_hi = tc::desc_hi(512, 1), k_hi = tc::desc_hi(1024, 2);
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                tc::umma_tf32_elect(tmem + 64, z_lo + (j * 1024 >> 4), mn_hi, p_lo + (((j >> 2) * 2048 + (j & 3) * 32) >> 4), k_hi, idesc,
-                                    j > 0 ? 1u : 0u);
-            tc::umma_commit_elect(&bars[2]);
-        }
+        __syncthreads();                          // C: z of `cur` is complete, its u columns are drained
         TOCK(7);
 #ifdef DCASE_CNN0_TIMING
         ++n_done;
@@ -422,23 +455,10 @@ cnn0_fwd_kernel(Cnn0Args a) {
     }
 #ifdef DCASE_CNN0_TIMING
     if (blockIdx.x == 7 && (tid == 0 || tid == 160))
-        printf("cnn0_fwd tid %d: total %lld tiles %d | wait y %lld | taps %lld | pooled %lld | phase d %lld | sync %lld | mma1+mask+wait %lld | phase f %lld | sync+mma2 %lld\n",
+        printf("cnn0_fwd tid %d: total %lld tiles %d | wait y + mma1 %lld | pool %lld | taps %lld | phase d %lld | sync A %lld | mma0+mask+wait %lld | phase f %lld | sync C %lld\n",
                tid, clock64() - t_begin, n_done, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7]);
 #endif
-    if (prev >= 0) {
-        tc::mbar_wait(&bars[2], ph2);
-        tc::fence_after_sync();
-        if (warp < 4) {
-            float v[16];
-            tc::tmem_ld16(tmem + 64 + lane_base, v);
-            tc::tmem_ld_wait();
-            if (lane < 16) {
-                float* dst = a.out + prev * 16 * 64 + 16 * warp + lane;
-#pragma unroll
-                for (int w = 0; w < 16; ++w) dst[w * 64] = tc::tf32_rn(pool_scale * v[w]);
-            }
-        }
-    }
+    if (prev >= 0) pool_tile(a_a, tid, pool_scale, a.out + prev * 16 * 64);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 128);
@@ -481,9 +501,9 @@ cnn0_bwd_kernel(Cnn0Args a) {
 
     stage_wg(a.glu_w, Wb, tid, kBwdThreads);
     stage_w0(a.fold0, T0, gt, 256);
+    stage_bias(a.glu_b, T0, gt, 256);
     for (int r = gt; r < 128; r += 256)                    // E chunk 3 (columns 12..15) stays zero
         *reinterpret_cast<float4*>(E + tc::sw128b32_chunk(r, 3)) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < 64) bg[tid] = __ldg(a.glu_b + tid);
     if (gt == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1); tc::fence_mbar_init(); }
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 512);
     uint64_t seed = a.drop.seed; uint32_t step = a.drop.step;
@@ -538,7 +558,7 @@ cnn0_bwd_kernel(Cnn0Args a) {
         ph0 ^= 1;
         tc::fence_after_sync();
         if (issuer) {                             // MMA1 straight away: y is read from tensor memory, and the lin columns
-            issue_mma1_tmem(tmem + 64, tmem, wb_a);   // were drained by every thread before the previous tile's last barrier
+            issue_mma1_tmem(tmem + 64, tmem, wb_a, t0_a);   // were drained by every thread before the previous tile's last barrier
             tc::umma_commit_elect(&bars[1]);
         }
         // gate phase first: it only needs y, and the accumulating MMA of the previous tile finishes under it
@@ -547,7 +567,7 @@ cnn0_bwd_kernel(Cnn0Args a) {
             float y[32];
             tmem_ld32(tmem + lane_base + 32 * half, y);
             tc::fence_before_sync();
-            sigmoid32(y, g);
+            tanh32(y, g);                         // a = tanh(y / 2)
         }
         if (pending) { tc::mbar_wait(&bars[2], ph2); ph2 ^= 1; pending = false; }   // E / DL / D2 free again
         tc::fence_after_sync();
@@ -579,7 +599,8 @@ cnn0_bwd_kernel(Cnn0Args a) {
             issue_mma0(tmem, t0_a);
             tc::umma_commit_elect(&bars[0]);
         }
-        // gradient of the pooled output for this pixel's window, dropout mask and 1/8 folded in (overlaps MMA1)
+        // gradient of the pooled output for this pixel's window (raw: the pool / dropout scale is applied to the accumulator
+        // at the end), dropout mask applied; overlaps MMA1
         float dz[32];
         {
             const int f = row & 63;
@@ -587,7 +608,7 @@ cnn0_bwd_kernel(Cnn0Args a) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 d = __ldg(dsrc + q);
-                dz[4 * q] = d.x * dz_scale; dz[4 * q + 1] = d.y * dz_scale; dz[4 * q + 2] = d.z * dz_scale; dz[4 * q + 3] = d.w * dz_scale;
+                dz[4 * q] = d.x; dz[4 * q + 1] = d.y; dz[4 * q + 2] = d.z; dz[4 * q + 3] = d.w;
             }
             if (drop) {
 #pragma unroll
@@ -599,24 +620,23 @@ cnn0_bwd_kernel(Cnn0Args a) {
         ph1 ^= 1;
         tc::fence_after_sync();
         {
-            float lin[32];
-            tmem_ld32(tmem + 64 + lane_base + 32 * half, lin);
+            float u[32];                                  // (lin + b) / 2
+            tmem_ld32(tmem + 64 + lane_base + 32 * half, u);
             tc::fence_before_sync();
+            const uint64_t m1 = pk(-1.f, -1.f);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bg + 32 * half + 4 * q);
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                float dl[4], d2[4];
+                uint64_t dl[2], d2[2];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int i = 4 * q + e;
-                    const float t = lin[i] + bb[e];
-                    dl[e] = dz[i] * g[i];                        // grad wrt lin
-                    d2[e] = dl[e] * fmaf(-t, g[i], t);           // grad wrt y through the gate: dz t g (1 - g)
+                for (int e = 0; e < 2; ++e) {
+                    const int i = 4 * q + 2 * e;
+                    const uint64_t A = pk(g[i], g[i + 1]), D = pk(dz[i], dz[i + 1]), U = pk(u[i], u[i + 1]);
+                    dl[e] = fma2(D, A, D);                        // 2 x grad wrt lin:  dz (1 + a)
+                    d2[e] = mul2(mul2(D, U), fma2(A, A, m1));     // -2 x grad wrt y through the gate:  dz u (a a - 1)
                 }
                 const uint32_t addr = chunk_addr(dl_rb, 8 * half + q);
-                sts128(addr, dl[0], dl[1], dl[2], dl[3]);                 // overwrites y (MMA1 has completed)
-                sts128(addr + 32768u, d2[0], d2[1], d2[2], d2[3]);
+                sts128_2(addr, dl[0], dl[1]);                     // overwrites y (MMA1 has completed)
+                sts128_2(addr + 32768u, d2[0], d2[1]);
             }
         }
         tc::fence_proxy_async();
@@ -641,8 +661,9 @@ cnn0_bwd_kernel(Cnn0Args a) {
         tc::tmem_ld16(tmem + 128 + lane_base, v);
         tc::tmem_ld_wait();
         const int m = 32 * (warp & 3) + lane;
+        const float sc = ((warp & 2) ? -0.5f : 0.5f) * dz_scale * kTruncComp;     // rows < 64: U (from 2 DL), rows >= 64: S2 (from -2 D2)
 #pragma unroll
-        for (int j = 0; j < 10; ++j) atomicAdd(a.us + m * 16 + j, kTruncComp * v[j]);
+        for (int j = 0; j < 10; ++j) atomicAdd(a.us + m * 16 + j, sc * v[j]);
     }
     tc::fence_before_sync();
     __syncthreads();
