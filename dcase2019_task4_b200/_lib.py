@@ -49,6 +49,8 @@ SIGNATURES = {
     "dcase_launch_count": (ctypes.c_ulonglong, []),
     "dcase_profile_begin": (c_i, []),
     "dcase_profile_end": (c_i, [ctypes.c_char_p, c_sz]),
+    "dcase_profile_timeline_begin": (c_i, []),
+    "dcase_profile_timeline_end": (c_i, [ctypes.c_char_p, c_sz]),
     "dcase_selftest_umma": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p]),
     "dcase_logmel_num_frames": (c_i, [c_i]),
     "dcase_mel_filterbank": (c_i, [c_p, c_p]),

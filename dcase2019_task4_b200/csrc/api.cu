@@ -19,14 +19,20 @@ static thread_local char g_err[512] = "";
 unsigned long long g_dcase_launches = 0;
 
 namespace {
-struct ProfRec { const char* name; cudaEvent_t a, b; };
-bool g_prof_on = false;
+struct ProfRec { const char* name; cudaEvent_t a, b; int stream_id; };
+std::vector<cudaStream_t> g_prof_streams;
+bool g_prof_on = false;       // per-kernel events; the orchestration then keeps everything on ONE stream (isolated durations)
+bool g_prof_timeline = false; // events with the streams left as they are: a timeline of the overlapped step (dcase_profile_timeline)
 std::vector<ProfRec> g_prof;
 }  // namespace
 
 DcaseProfScope::DcaseProfScope(const char* name, cudaStream_t s) : slot(-1), stream(s) {
-    if (!g_prof_on) return;
-    ProfRec r{name, nullptr, nullptr};
+    if (!g_prof_on && !g_prof_timeline) return;
+    ProfRec r{name, nullptr, nullptr, 0};
+    for (size_t i = 0; i <= g_prof_streams.size(); ++i) {
+        if (i == g_prof_streams.size()) { g_prof_streams.push_back(s); }
+        if (g_prof_streams[i] == s) { r.stream_id = (int)i; break; }
+    }
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
     cudaEventRecord(r.a, s);
     g_prof.push_back(r);
@@ -205,6 +211,34 @@ int dcase_profile_end(char* buf, size_t cap) {
         out += line;
     }
     if (out.size() + 1 > cap) { dcase_set_error("profile buffer too small"); return DCASE_ERR_ARG; }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return DCASE_OK;
+}
+// Timeline mode: dcase_profile_timeline_begin(), run a step EAGERLY, dcase_profile_timeline_end(buf): one line per launch,
+// "name,stream,start_us,end_us" relative to the first launch; start = when the stream reached the launch, end = when the
+// kernel finished (CUDA events on the launching stream; the streams overlap as in production).
+int dcase_profile_timeline_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_timeline = true;
+    return DCASE_OK;
+}
+int dcase_profile_timeline_end(char* buf, size_t cap) {
+    g_prof_timeline = false;
+    DCASE_REQUIRE(buf && cap > 0, "null buffer");
+    DCASE_CUDA_CHECK(cudaDeviceSynchronize());
+    std::string out;
+    for (size_t i = 0; i < g_prof.size(); ++i) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, g_prof[0].a, g_prof[i].a);
+        cudaEventElapsedTime(&b, g_prof[0].a, g_prof[i].b);
+        char line[200];
+        snprintf(line, sizeof(line), "%s,%d,%.2f,%.2f\n", g_prof[i].name, g_prof[i].stream_id, a * 1e3, b * 1e3);
+        out += line;
+    }
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    if (out.size() + 1 > cap) { dcase_set_error("timeline buffer too small"); return DCASE_ERR_ARG; }
     memcpy(buf, out.c_str(), out.size() + 1);
     return DCASE_OK;
 }

@@ -264,7 +264,7 @@ __device__ __forceinline__ void require_aligned_smem(const void* p) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-// Software pipeline per CTA (3 CTAs / SM), two block barriers per tile:
+// Software pipeline per CTA (4 CTAs / SM), two block barriers per tile:
 //   top      MMA0 of this tile has completed (it was issued during the previous tile): MMA1 is issued at once
 //   phase P  the PREVIOUS tile's z is average-pooled from shared memory on the CUDA cores (thread = one window x four
 //            channels: 8 conflict-free 16-byte loads, one coalesced 16-byte store) -- under MMA1.  Round 2 replaced the
@@ -273,26 +273,43 @@ __device__ __forceinline__ void require_aligned_smem(const void* p) {
 //   phase D  operand rows of the NEXT tile (taps / dropout bits), x rows of the tile after it prefetched into registers,
 //            a = tanh(y / 2) from tensor memory
 //   barrier A, then MMA0 of the next tile;  phase F  z = u (1 + a) -> shared memory;  barrier C
-// smem (1024-B aligned, all dynamic): Wb 16 KB | T0 16 KB | Z 32 KB (swizzled rows of 64 channels) |
+// z is held as fp16 (round to nearest: 11 significant bits, one more than the tf32 operand the pooling MMA used to read)
+// and summed in fp32: 16 KB instead of 32 KB, which together with 63 registers per thread lets FOUR CTAs share an SM.
+// smem (1024-B aligned, all dynamic): Wb 16 KB | T0 16 KB | Z 16 KB (128 rows x 64 fp16, 16-byte chunks swizzled by row) |
 //                                     xs[4][66] | keep_lo[128] | 2 mbarriers | tmem base
-// TMEM (128 columns): [0,64) y (the next tile's y from barrier A on), [64,128) u = (lin + b) / 2
-constexpr int kFwdWb = 0, kFwdT0 = 16384, kFwdA = 32768, kFwdMisc = 65536;
+// TMEM (128 columns, 4 CTAs = all 512): [0,64) y (the next tile's y from barrier A on), [64,128) u = (lin + b) / 2
+constexpr int kFwdWb = 0, kFwdT0 = 16384, kFwdA = 32768, kFwdMisc = 49152;
 constexpr int kFwdSmemBytes = kFwdMisc + 4 * 66 * 4 + 128 * 4 + 2 * 8 + 8;
 constexpr int kFwdThreads = 256;
+constexpr int kFwdCtasPerSm = 4;
+
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+    float2 r;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(v));
+    return r;
+}
+// z row of pixel p: 128 bytes, 16-byte chunk c (8 channels) stored at chunk c ^ (p & 7)
+__device__ __forceinline__ uint32_t zrow_base(uint32_t region, int p) { return region + (uint32_t)(p * 128); }
 
 // average pool of one tile from its z rows in shared memory: thread = (window w, channels 4 c4 .. 4 c4 + 3)
 __device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scale, float* __restrict__ out_tile) {
     const int w = tid >> 4, c4 = tid & 15;
-    const uint32_t base = z_region + (uint32_t)((w >> 1) * 1024 + (c4 >> 3) * 16384);
-    const int r0 = 4 * (w & 1);                       // rows 4 w + j of frame tr: 8-row group w / 2 (+ 8 tr), row r0 + j inside it
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t addr = base + (uint32_t)((r0 + j) * 128 + ((((r0 + j) ^ c4) & 7) << 4));
+        const int p = 4 * w + j;                      // frame 0; frame 1 is 64 rows = 8192 bytes further (same p & 7)
+        const uint32_t addr = z_region + (uint32_t)(p * 128 + ((((c4 >> 1) ^ p) & 7) << 4) + (c4 & 1) * 8);
 #pragma unroll
         for (int tr = 0; tr < 2; ++tr) {
-            const float4 v = lds128(addr + tr * 8192);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            uint32_t v0, v1;
+            asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(addr + tr * 8192) : "memory");
+            const float2 a = unpack_half2(v0), b = unpack_half2(v1);
+            acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
         }
     }
     *reinterpret_cast<float4*>(out_tile + w * 64 + 4 * c4) =            // conv1's MMA operand: rounded to tf32
@@ -300,7 +317,7 @@ __device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scal
                     tf32_round_fast(scale * acc.w));
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 3)
+__global__ void __launch_bounds__(kFwdThreads, 4)
 cnn0_fwd_kernel(Cnn0Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     require_aligned_smem(smem);
@@ -325,7 +342,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
     const long long stride = gridDim.x;
     long long cur = blockIdx.x;
     const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), a_a = tc::smem_u32(smem + kFwdA);
-    const uint32_t t0_rb = krow_base(t0_a, row), z_rb = krow_base(a_a, row);
+    const uint32_t t0_rb = krow_base(t0_a, row), z_rb = zrow_base(a_a, row);
     const bool drop = a.drop.enabled != 0;
 
     // prologue: operand rows of the first tile and its MMA0; x rows of the second tile in shared memory, of the third in
@@ -437,10 +454,18 @@ cnn0_fwd_kernel(Cnn0Args a) {
             tmem_ld32(tmem + 64 + lane_base + 32 * half, u);
             tc::fence_before_sync();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint64_t u01 = pk(u[4 * q], u[4 * q + 1]), u23 = pk(u[4 * q + 2], u[4 * q + 3]);
-                sts128_2(chunk_addr(z_rb, 8 * half + q),
-                         fma2(u01, pk(g[4 * q], g[4 * q + 1]), u01), fma2(u23, pk(g[4 * q + 2], g[4 * q + 3]), u23));
+            for (int q = 0; q < 4; ++q) {         // 8 channels = one 16-byte chunk of fp16
+                uint32_t h[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 8 * q + 2 * e;
+                    const uint64_t uu = pk(u[i], u[i + 1]);
+                    float z0, z1;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(z0), "=f"(z1) : "l"(fma2(uu, pk(g[i], g[i + 1]), uu)));
+                    h[e] = pack_half2(z0, z1);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(z_rb + (uint32_t)((((4 * half + q) ^ row) & 7) << 4)),
+                             "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
             }
         }
         if (has_next && nxt + stride < n_tiles) xs_commit(xr, xs, tid);      // rows of the tile after `nxt` (those of `nxt` were consumed before A)
@@ -743,7 +768,7 @@ int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const floa
     Cnn0Args a{};
     a.x = x; a.B = B; a.T = T; a.fold0 = fold0; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
     const long long n_tiles = (long long)B * T / 2;
-    const long long grid = n_tiles < 3ll * num_sms ? n_tiles : 3ll * num_sms;
+    const long long grid = n_tiles < (long long)kFwdCtasPerSm * num_sms ? n_tiles : (long long)kFwdCtasPerSm * num_sms;
     cnn0_fwd_kernel<<<(int)grid, kFwdThreads, kFwdSmemBytes, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;

@@ -55,6 +55,9 @@ unsigned long long dcase_launch_count(void);
  * lines into buf (synchronises the device). */
 int dcase_profile_begin(void);
 int dcase_profile_end(char* buf, size_t cap);
+/* timeline of one EAGER step with the streams overlapping as in production: "name,stream,start_us,end_us" per launch */
+int dcase_profile_timeline_begin(void);
+int dcase_profile_timeline_end(char* buf, size_t cap);
 
 /* Self-test of the tcgen05 / TMEM primitives (csrc/tc.cuh).  mode 0: D[128][64] = A[128][64] * B[64][64]^T with
  * K-major operands; mode 1: raw TMEM dump [128 lanes][64 columns] of D[m][n] = sum_p A[p][m] * B[p][n], p < 128,
