@@ -39,6 +39,11 @@ constexpr int kStftWarps = 8;
 constexpr int kStftThreads = 32 * kStftWarps;
 constexpr int kSpan = (kFramesPerTile - 1) * kHop + kNfft;  // 5625 samples
 constexpr int kSpanBuf = 5632;                               // + up to 3 samples of alignment slack, 16-byte multiple
+// 16-bit PCM input: the raw span (+ up to 7 samples of slack, <= 5640 samples) lands in the UPPER half of the span buffer by
+// the same single bulk copy and is expanded to float32 in place (every thread first holds its samples in registers)
+constexpr int kPcmOff = kSpanBuf * 4 - 5640 * 2;             // byte offset, a multiple of 16
+constexpr int kPcmPerThread = (kSpan + kStftThreads - 1) / kStftThreads;
+static_assert(kPcmOff % 16 == 0, "bulk copies need 16-byte aligned destinations");
 constexpr int kMelItems = 128;                               // work items of the mel projection (4 rounds x 32 lanes)
 constexpr int kMelRun = 22;                                  // longest run of one item
 
@@ -104,6 +109,7 @@ __device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, uint32
 struct TileStage {
     int b, t0, a;
     bool async;
+    int a16;      // 16-bit PCM: slack of the raw span in the upper half of the buffer (a = 0 after the expansion)
 };
 
 // Stage the span of `tile` into sm.span.  Returns how it was staged; the async form is issued by thread 0 alone and
@@ -117,7 +123,23 @@ __device__ __forceinline__ TileStage stage_span(const WaveT* __restrict__ wave, 
     const int s0 = st.t0 * kHop - kNfft / 2;
     const long long clip_off = (long long)st.b * L;
     st.a = 0;
+    st.a16 = 0;
     st.async = false;
+    if (sizeof(WaveT) == 2 && base_aligned && s0 >= 0 && s0 + kSpan <= L) {
+        const long long g0 = clip_off + s0;
+        const int a = (int)(g0 & 7);
+        const uint32_t n = (uint32_t)((kSpan + a + 7) & ~7);
+        if (g0 - a + n <= (long long)B * L) {
+            st.a16 = a;
+            st.async = true;
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect(&sm.bar_span, 2u * n);
+                bulk_load(reinterpret_cast<unsigned char*>(sm.span) + kPcmOff, wave + (g0 - a), 2u * n, &sm.bar_span);
+            }
+            return st;
+        }
+    }
     if (sizeof(WaveT) == 4 && base_aligned && s0 >= 0 && s0 + kSpan <= L) {
         const long long g0 = clip_off + s0;
         const int a = (int)(g0 & 3);
@@ -181,13 +203,28 @@ stft_mel_kernel(const WaveT* __restrict__ wave, int B, int L, int T, MelTables t
     uint32_t span_parity = 0;
 
     int tile = blockIdx.x;
-    TileStage cur{0, 0, 0, false};
+    TileStage cur{0, 0, 0, false, 0};
     if (tile < n_tiles) cur = stage_span<WaveT>(wave, tile, tiles_per_clip, B, L, base_aligned, sm, tid);
     mbar_wait_parity(&sm.bar_tables, 0);
 
     for (; tile < n_tiles; tile += gridDim.x) {
         if (cur.async) { mbar_wait_parity(&sm.bar_span, span_parity); span_parity ^= 1; }
-        else __syncthreads();                                     // the span was written with ordinary stores
+        if (sizeof(WaveT) == 2 && cur.async) {                    // raw 16-bit span -> float32 in place (soundfile's 1/32768)
+            const int16_t* raw = reinterpret_cast<const int16_t*>(reinterpret_cast<const unsigned char*>(sm.span) + kPcmOff) + cur.a16;
+            int16_t smp[kPcmPerThread];
+#pragma unroll
+            for (int k = 0; k < kPcmPerThread; ++k) {
+                const int i = tid + k * kStftThreads;
+                smp[k] = i < kSpan ? raw[i] : (int16_t)0;
+            }
+            __syncthreads();                                      // everybody holds its samples: the buffer may be rewritten
+#pragma unroll
+            for (int k = 0; k < kPcmPerThread; ++k) {
+                const int i = tid + k * kStftThreads;
+                if (i < kSpan) sm.span[i] = (float)smp[k] * (1.0f / 32768.0f);
+            }
+            __syncthreads();
+        } else if (!cur.async) __syncthreads();                   // the span was written with ordinary stores
         const int t = cur.t0 + warp;
         const bool active = t < T;                                // warp-uniform: the tile's tail frames do not exist
         const int b = cur.b;
