@@ -37,7 +37,7 @@ class MtArgs(ctypes.Structure):
                 ("flags", c_i), ("seed", c_u64), ("step", c_u32), ("cons_weight", c_f), ("scalars", c_p),
                 ("strong_s", c_p), ("weak_s", c_p), ("strong_t", c_p), ("weak_t", c_p), ("meters", c_p),
                 ("d_strong", c_p), ("d_weak", c_p), ("ws_s", c_p), ("ws_t", c_p), ("grads", c_p),
-                ("after_forward_event", c_p)]
+                ("after_forward_event", c_p), ("mom_s", c_p), ("mom_t", c_p)]
 
 
 # name -> (restype, argtypes); every symbol include/dcase_b200.h declares
@@ -67,6 +67,7 @@ SIGNATURES = {
     "dcase_crnn_param_offset": (ctypes.c_longlong, [c_i, ctypes.c_char_p]),
     "dcase_crnn_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "dcase_crnn_ws_tensor": (c_i, [c_i, c_i, c_i, ctypes.c_char_p, ctypes.POINTER(c_sz), ctypes.POINTER(c_sz)]),
+    "dcase_cnn0_input_moments": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p]),
     "dcase_crnn_forward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_u64, c_u32, c_i, c_p, c_p, c_p, c_p, c_p]),
     "dcase_bigru_workspace_bytes": (c_sz, [c_i, c_i]),
     "dcase_bigru_forward": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),

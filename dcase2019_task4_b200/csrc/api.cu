@@ -323,9 +323,10 @@ int dcase_crnn_ws_tensor(int B, int T, int n_class, const char* name, size_t* of
     return DCASE_ERR_ARG;
 }
 
-int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, const float* params, float* bn_running,
-                       int flags, uint64_t seed, uint32_t step, int model_id, const void* scalars, float* strong,
-                       float* weak, void* ws, void* stream_) {
+// mom_in: the 54 tap moments of x computed ahead of the step (dcase_cnn0_input_moments) or NULL
+static int crnn_forward_impl(dcase_ctx* ctx, const float* x, int B, int T, int NC, const float* params, float* bn_running,
+                             int flags, uint64_t seed, uint32_t step, int model_id, const void* scalars, float* strong,
+                             float* weak, void* ws, const double* mom_in, void* stream_) {
     cudaStream_t s = (cudaStream_t)stream_;
     DCASE_REQUIRE(ctx && x && params && bn_running && strong && weak && ws, "null argument");
     DCASE_TRY(check_shape(B, T, NC));
@@ -356,18 +357,22 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     // their producer and their consumer; slots 3 * model + layer (forward), 6 + layer (backward)
     const dcase_syncbn* sb = training ? ctx->syncbn : nullptr;
     const long long world = syncbn_world(sb);
-    if (training && !sb)
+    if (training && !sb && !mom_in)
         DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
                                       params + o.bn_b[0], bn_running, fold0, sms, s));
+    else if (training && !sb)       // the moments only depend on the input: a pipelined caller computed them beside the previous step
+        DCASE_TRY(launch_bn0_finalize(mom_in, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
+                                      params + o.bn_b[0], bn_running, 1, fold0, mom0, s));
     else if (training) {
-        DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
-                                      params + o.bn_b[0], bn_running, nullptr, sms, s));
+        if (mom_in) DCASE_CUDA_CHECK(cudaMemcpyAsync(mom0, mom_in, 54 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        else DCASE_TRY(launch_cnn0_moments(x, B, T, mom0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
+                                           params + o.bn_b[0], bn_running, nullptr, sms, s));
         DCASE_TRY(syncbn_allreduce_f64(sb, mom0, 54, 3 * mid + 0, s));
         DCASE_TRY(launch_bn0_finalize(mom0, n_pix0 * world, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
-                                      params + o.bn_b[0], bn_running, 1, fold0, s));
+                                      params + o.bn_b[0], bn_running, 1, fold0, nullptr, s));
     } else
         DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
-                                      params + o.bn_b[0], bn_running, training, fold0, s));
+                                      params + o.bn_b[0], bn_running, training, fold0, nullptr, s));
     float* out0 = wsp<float>(ws, L, "out0");
     DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), out0, sms, s));
 
@@ -437,6 +442,19 @@ int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, con
     h.strong = strong; h.weak = weak; h.den = wsp<float>(ws, L, "den");
     DCASE_TRY(launch_head_fwd(h, s));
     return DCASE_OK;
+}
+
+int dcase_crnn_forward(dcase_ctx* ctx, const float* x, int B, int T, int NC, const float* params, float* bn_running,
+                       int flags, uint64_t seed, uint32_t step, int model_id, const void* scalars, float* strong,
+                       float* weak, void* ws, void* stream_) {
+    return crnn_forward_impl(ctx, x, B, T, NC, params, bn_running, flags, seed, step, model_id, scalars, strong, weak, ws,
+                             nullptr, stream_);
+}
+
+int dcase_cnn0_input_moments(dcase_ctx* ctx, const float* x, int B, int T, double* mom, void* stream) {
+    DCASE_REQUIRE(ctx && x && mom, "null argument");
+    DCASE_TRY(check_shape(B, T, 10));
+    return launch_cnn0_moments(x, B, T, mom, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->num_sms, (cudaStream_t)stream);
 }
 
 size_t dcase_bigru_workspace_bytes(int B, int To) {
@@ -653,12 +671,12 @@ int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* a, void* stream) {
         cudaStream_t ts = (g_prof_on || ctx->syncbn) ? s : ctx->aux_stream;
         DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, s));
         DCASE_CUDA_CHECK(cudaStreamWaitEvent(ts, ctx->ev_fork, 0));
-        DCASE_TRY(dcase_crnn_forward(ctx, a->x_teacher, a->B, a->T, a->n_class, a->params_t, a->bn_t, a->flags, a->seed,
-                                     a->step, 1, a->scalars, a->strong_t, a->weak_t, a->ws_t, ts));
+        DCASE_TRY(crnn_forward_impl(ctx, a->x_teacher, a->B, a->T, a->n_class, a->params_t, a->bn_t, a->flags, a->seed,
+                                    a->step, 1, a->scalars, a->strong_t, a->weak_t, a->ws_t, a->mom_t, ts));
         DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_join, ts));
     }
-    DCASE_TRY(dcase_crnn_forward(ctx, a->x_student, a->B, a->T, a->n_class, a->params_s, a->bn_s, a->flags, a->seed,
-                                 a->step, 0, a->scalars, a->strong_s, a->weak_s, a->ws_s, stream));
+    DCASE_TRY(crnn_forward_impl(ctx, a->x_student, a->B, a->T, a->n_class, a->params_s, a->bn_s, a->flags, a->seed,
+                                a->step, 0, a->scalars, a->strong_s, a->weak_s, a->ws_s, a->mom_s, stream));
     if (a->after_forward_event) DCASE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a->after_forward_event, s));
     if (a->x_teacher) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
     DCASE_TRY(dcase_mt_loss(ctx, a->strong_s, a->weak_s, a->x_teacher ? a->strong_t : nullptr,

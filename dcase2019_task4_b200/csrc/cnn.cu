@@ -82,9 +82,11 @@ struct Bn0FinalizeArgs {      // training: the LAST block of the moments kernel 
 };
 
 constexpr int kMomSeg = 16;
+constexpr int kMomPitch = 4 * 65 + 1;      // floats per row of the reduction buffer (4 strips of 64 threads, padded)
+constexpr int kMomSmemBytes = 54 * kMomPitch * 4;
 __global__ void __launch_bounds__(256)
 cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restrict__ mom, Bn0FinalizeArgs fin) {
-    __shared__ float red[8][54];
+    extern __shared__ float tr[];            // [54][kMomPitch]: the block's partial sums, transposed (see the reduction below)
     __shared__ int is_last;
     __shared__ double mom_s[54], pm[9][64], pv[9][64];
     float acc[54];
@@ -121,16 +123,25 @@ cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restric
             for (int j = 0; j < 3; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
         }
     }
+    // Block reduction through shared memory: every thread parks its 54 partials (conflict-free, transposed), then thread
+    // (i, q) adds a quarter of the block's 256 values of sum i and the quad folds -- ~190 instructions per thread instead
+    // of the 540 of 54 five-step warp butterflies, which cost as much as the accumulation itself.
+    {
+        const int col = (threadIdx.x >> 6) * 65 + (threadIdx.x & 63);
 #pragma unroll
-    for (int i = 0; i < 54; ++i) {
-        const float v = warp_sum(acc[i]);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+        for (int i = 0; i < 54; ++i) tr[i * kMomPitch + col] = acc[i];
     }
     __syncthreads();
-    if (threadIdx.x < 54) {
-        double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
-        atomicAdd(mom + threadIdx.x, s);
+    if (threadIdx.x < 224) {                 // whole warps (the quad fold shuffles): sums 54, 55 do not exist
+        const int i = threadIdx.x >> 2, q = threadIdx.x & 3;
+        const float* src = tr + (i < 54 ? i : 53) * kMomPitch + q * 65;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < 64; k += 4) { s0 += src[k]; s1 += src[k + 1]; s2 += src[k + 2]; s3 += src[k + 3]; }
+        double s = (double)(s0 + s1) + (double)(s2 + s3);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0 && i < 54) atomicAdd(mom + i, s);
     }
     // the last block to arrive folds BatchNorm into the conv weights: saves the one-block launch that sat between this
     // kernel and cnn0_fwd on the forward chain (SyncBN: the sums cross the ranks first, bn0_finalize_kernel folds)
@@ -154,10 +165,11 @@ cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restric
 __global__ void __launch_bounds__(576)
 bn0_finalize_kernel(const double* __restrict__ mom, long long n_pix, const float* __restrict__ w,
                     const float* __restrict__ b, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float* __restrict__ running, int training, float* __restrict__ fold0) {
+                    float* __restrict__ running, int training, float* __restrict__ fold0, double* __restrict__ mom_copy) {
     __shared__ double pm[9][64], pv[9][64];
     const int c = threadIdx.x & 63, k = threadIdx.x >> 6;
-    if (training) bn0_task(c, k, mom, n_pix, w, pm, pv);
+    if (mom_copy && threadIdx.x < 54) mom_copy[threadIdx.x] = mom[threadIdx.x];   // moments computed ahead of the step: the
+    if (training) bn0_task(c, k, mom, n_pix, w, pm, pv);                           // backward reads them from the workspace
     __syncthreads();
     if (k == 0) bn0_channel(c, pm, pv, n_pix, w, b, gamma, beta, running, training, fold0);
 }
@@ -267,6 +279,7 @@ bn_bwd_apply_kernel(float* __restrict__ d_y, const float* __restrict__ ypre, lon
 }  // namespace
 
 int cnn_kernels_init() {
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(cnn0_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMomSmemBytes));
     return DCASE_OK;
 }
 
@@ -280,16 +293,16 @@ int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* 
     long long blocks = (n_seg + 3) / 4;
     if (blocks > num_sms * 4) blocks = num_sms * 4;
     Bn0FinalizeArgs fin{(long long)B * T * 64, conv_w, conv_b, gamma, beta, running, fold0};
-    cnn0_moments_kernel<<<(int)blocks, 256, 0, s>>>(x, B, T, mom, fin);
+    cnn0_moments_kernel<<<(int)blocks, 256, kMomSmemBytes, s>>>(x, B, T, mom, fin);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 
 int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running, int training, float* fold0,
-                        cudaStream_t s) {
+                        double* mom_copy, cudaStream_t s) {
     DCASE_PROF("bn0_finalize", s);
-    bn0_finalize_kernel<<<1, 576, 0, s>>>(mom, n_pix, conv_w, conv_b, gamma, beta, running, training, fold0);
+    bn0_finalize_kernel<<<1, 576, 0, s>>>(mom, n_pix, conv_w, conv_b, gamma, beta, running, training, fold0, mom_copy);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

@@ -33,7 +33,7 @@ int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* 
                         const float* gamma, const float* beta, float* running, float* fold0, int num_sms, cudaStream_t s);
 int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
                         const float* gamma, const float* beta, float* running /*[2][64]*/, int training,
-                        float* fold0, cudaStream_t s);
+                        float* fold0, double* mom_copy /*nullable: also copy the 54 moments there*/, cudaStream_t s);
 // cnn0.cu: fused block 0 (conv0 + BN + GLU + dropout + pool), forward / backward / parameter gradients
 int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
                     DropoutCfg drop, float* out, int num_sms, cudaStream_t s);

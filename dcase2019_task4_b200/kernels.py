@@ -170,6 +170,16 @@ def crnn_forward(x, params, bn_running, flags, ws, n_class=10, seed=0, step=0, m
     return strong, weak
 
 
+def cnn0_input_moments(x, out=None):
+    """The 54 input moments behind block 0's BatchNorm batch statistics (float64 [56], see include/dcase_b200.h)."""
+    x = _f32(x)
+    B, T = x.shape[0], x.shape[-2]
+    if out is None:
+        out = torch.empty(56, dtype=torch.float64, device=x.device)
+    check(lib().dcase_cnn0_input_moments(ctx(), ptr(x), B, T, ptr(out), stream_ptr()))
+    return out
+
+
 def crnn_backward(x, params, flags, ws, d_strong, d_weak, weak, n_class=10, seed=0, step=0, model_id=0, scalars=None,
                   grads=None):
     x = _f32(x)

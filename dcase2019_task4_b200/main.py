@@ -269,6 +269,10 @@ class MeanTeacherEngine(object):
         a.meters, a.d_strong, a.d_weak = self.meters.data_ptr(), self.d_strong.data_ptr(), self.d_weak.data_ptr()
         a.ws_s, a.grads = self.ws_s.data_ptr(), self.grads.data_ptr()
         a.after_forward_event = getattr(self, "_fork_handle", None)      # step_pipelined only; NULL otherwise
+        moms = getattr(self, "_step_moms", None)                          # step_pipelined only: block-0 input moments of the
+        if moms is not None:                                              # current slot, computed beside the previous step
+            a.mom_s = moms[0].data_ptr()
+            a.mom_t = moms[1].data_ptr() if ema is not None else None
         return a
 
     def _graph_step(self, wave, target, mean, std, cons_weight, global_step_after, check):
@@ -346,6 +350,9 @@ class MeanTeacherEngine(object):
             self._xp = [torch.empty(self.B, self.T, 64, **f32) for _ in range(2)]
             self._xp_ema = ([torch.empty(self.B, self.T, 64, **f32) for _ in range(2)]
                             if self.ema_model is not None else [None, None])
+            # block 0's BatchNorm batch statistics follow from 54 moments of its INPUT (include/dcase_b200.h): they are
+            # taken right behind the features, beside the previous iteration, instead of at the head of the forward chain
+            self._moms = [torch.zeros(2, 56, dtype=torch.float64, device=self.dev) for _ in range(2)]
             self._feat_slot = 0
             self._side = torch.cuda.Stream(self.dev)
             self._fwd_done = torch.cuda.Event()
@@ -358,8 +365,10 @@ class MeanTeacherEngine(object):
         if self.ema_model is not None:
             K.logmel_finish(amp, mean, std, self.T, noisy=True, seed=seed, step=step, scalars=scalars,
                             out_clean=xp[slot], out_noisy=xpe[slot])
+            K.cnn0_input_moments(xpe[slot], out=self._moms[slot][1])
         else:
             K.logmel_finish(amp, mean, std, self.T, out_clean=xp[slot])
+        K.cnn0_input_moments(xp[slot], out=self._moms[slot][0])
 
     def prime_features(self, wave, mean, std):
         """Features of the FIRST batch of a pipelined run (current slot), with the upcoming iteration's noise."""
@@ -378,10 +387,12 @@ class MeanTeacherEngine(object):
         if not self.use_graph:
             next_noise_step = (self.model._rng_step + 1) & 0xFFFFFFFF
             self._fork_handle = self._fwd_done.cuda_event      # recorded by dcase_mt_fwd_bwd after the student forward
+            self._step_moms = self._moms[slot]
             try:
                 self.step(xp[slot], xpe[slot], target, cons_weight, global_step_after, check=check)
             finally:
                 self._fork_handle = None
+                self._step_moms = None
             # the side stream starts once this step's forward is done (which also means the previous step -- the last
             # reader of the other slot -- is done) and runs beside the backward
             self._side.wait_event(self._fwd_done)
@@ -415,11 +426,13 @@ class MeanTeacherEngine(object):
                     if self.p2p is not None:
                         self.p2p.begin_step()
                     self._fork_handle = self._fwd_done.cuda_event
+                    self._step_moms = self._moms[slot]
                     try:
                         K.mt_fwd_bwd(self._mt_args(xp[slot], xpe[slot], target, model.forward_flags(), 0, 0, 0.0,
                                                    self._sc_dev.data_ptr()))
                     finally:
                         self._fork_handle = None
+                        self._step_moms = None
                     self._side.wait_event(self._fwd_done)          # graph edge from the end of the student forward
                     with torch.cuda.stream(self._side):
                         amp = K.logmel_fwd(wave_next)

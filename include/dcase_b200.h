@@ -252,6 +252,12 @@ int dcase_ctx_set_syncbn(dcase_ctx* ctx, dcase_syncbn* h);
 int dcase_syncbn_allreduce(dcase_syncbn* h, void* vals_dev, int n, int is_double, int slot, void* stream);
 int dcase_syncbn_destroy(dcase_syncbn* h);
 
+/* BatchNorm batch statistics of CNN block 0 (models/CNN.py:49) follow from 54 moments of the block's INPUT (conv0 is
+ * linear in its 9 taps): 9 tap sums + 45 second moments, float64, mom[56] (the last two entries are scratch).  They
+ * depend on x alone, so a pipelined caller computes them beside the previous iteration and hands them to
+ * dcase_mt_fwd_bwd (mom_s / mom_t); otherwise the forward computes them itself. */
+int dcase_cnn0_input_moments(dcase_ctx* ctx, const float* x, int B, int T, double* mom, void* stream);
+
 /* ---- one mean-teacher iteration, main.py:84-153 (forward x2, losses, backward) ----------------------- */
 typedef struct dcase_mt_args {
     const float* x_student;   /* [B][T][64] clean */
@@ -281,6 +287,8 @@ typedef struct dcase_mt_args {
     void* after_forward_event; /* optional cudaEvent_t recorded on `stream` once the student forward is enqueued (NULL: none):
                                  lets the caller start independent work -- the next batch's features -- on another stream
                                  alongside the backward instead of alongside the forward */
+    const double* mom_s;      /* optional (NULL: computed inside): the tap moments of x_student / x_teacher from */
+    const double* mom_t;      /* dcase_cnn0_input_moments, e.g. computed beside the previous iteration             */
 } dcase_mt_args;
 
 int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* args, void* stream);
