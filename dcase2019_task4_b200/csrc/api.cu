@@ -138,8 +138,10 @@ WsLayout ws_layout(int B, int T, int NC) {
     add("bn1", kBnSize);
     add("bn2", kBnSize);
     add("gluimg1", kGluImgBytes / 4); add("gluimg2", kGluImgBytes / 4);
-    add("wprep1_f", 36864); add("wprep1_d", 36864); add("wprep2_f", 36864); add("wprep2_d", 36864);
+    add("wprep1_d", 36864); add("wprep2_d", 36864);                 // tf32 images of the data-gradient pass
+    add("wprep1_h", 36864 / 2); add("wprep2_h", 36864 / 2);         // fp16 images of the forward pass
     add("out0", n0); add("ypre1", n0); add("out1", n1); add("ypre2", n1); add("out2", BT * 64);
+    add("out0_h", n0 / 2); add("out1_h", n1 / 2);                   // fp16 copies: operands of the forward convs
     add("gi", 2 * BT * 192);
     const char* sv[2][5] = {{"s0_r", "s0_z", "s0_n", "s0_hn", "s0_hp"}, {"s1_r", "s1_z", "s1_n", "s1_hn", "s1_hp"}};
     for (int l = 0; l < 2; ++l) for (int k = 0; k < 5; ++k) add(sv[l][k], 2 * BT * 64);
@@ -345,8 +347,8 @@ static int crnn_forward_impl(dcase_ctx* ctx, const float* x, int B, int T, int N
     cudaStream_t prep = g_prof_on ? s : ctx->prep_stream[mid];
     DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_prep_fork[mid], s));
     DCASE_CUDA_CHECK(cudaStreamWaitEvent(prep, ctx->ev_prep_fork[mid], 0));
-    DCASE_TRY(launch_conv_w_prep(params + o.conv_w[1], wsp<float>(ws, L, "wprep1_f"), wsp<float>(ws, L, "wprep1_d"),
-                                 params + o.conv_w[2], wsp<float>(ws, L, "wprep2_f"), wsp<float>(ws, L, "wprep2_d"), prep));
+    DCASE_TRY(launch_conv_w_prep(params + o.conv_w[1], nullptr, wsp<float>(ws, L, "wprep1_d"), wsp<void>(ws, L, "wprep1_h"),
+                                 params + o.conv_w[2], nullptr, wsp<float>(ws, L, "wprep2_d"), wsp<void>(ws, L, "wprep2_h"), prep));
     DCASE_CUDA_CHECK(cudaEventRecord(ctx->ev_prep_join[mid], prep));
 
     // ---- CNN block 0 (fused, nothing materialised at [B,64,T,64]) ----
@@ -373,13 +375,18 @@ static int crnn_forward_impl(dcase_ctx* ctx, const float* x, int B, int T, int N
     } else
         DCASE_TRY(launch_bn0_finalize(mom0, n_pix0, params + o.conv_w[0], params + o.conv_b[0], params + o.bn_w[0],
                                       params + o.bn_b[0], bn_running, training, fold0, nullptr, s));
+    // The forward convs multiply fp16 copies of the block outputs (same 10 explicit mantissa bits as the tf32-rounded
+    // fp32 values, half the operand bytes); the fp32 copies only feed the backward's weight-gradient MMAs, and the teacher
+    // (model_id 1: no backward, main.py:87-89) does not write them.
+    const bool keep_f32 = model_id == 0;
     float* out0 = wsp<float>(ws, L, "out0");
-    DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), out0, sms, s));
+    DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), keep_f32 ? out0 : nullptr,
+                              wsp<void>(ws, L, "out0_h"), sms, s));
 
     // ---- CNN blocks 1, 2 ----
-    const char* names[3][7] = {{}, {"wprep1_f", "wprep1_d", "ypre1", "stats1", "bn1", "out1", "gluimg1"},
-                               {"wprep2_f", "wprep2_d", "ypre2", "stats2", "bn2", "out2", "gluimg2"}};
-    const float* in = out0;
+    const char* names[3][7] = {{}, {"wprep1_h", "wprep1_d", "ypre1", "stats1", "bn1", "out1", "gluimg1"},
+                               {"wprep2_h", "wprep2_d", "ypre2", "stats2", "bn2", "out2", "gluimg2"}};
+    const void* in_h = wsp<void>(ws, L, "out0_h");
     for (int l = 1; l <= 2; ++l) {
         const int T_l = l == 1 ? T / 2 : T / 4;
         const int F_l = l == 1 ? 16 : 4;
@@ -393,13 +400,13 @@ static int crnn_forward_impl(dcase_ctx* ctx, const float* x, int B, int T, int N
         float* out = wsp<float>(ws, L, names[l][5]);
         (void)wd;
         if (l == 1) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_prep_join[mid], 0));
-        DCASE_TRY(launch_conv3x3(in, B, T_l, F_l, wf, params + o.conv_b[l], ypre, training ? stats : nullptr, sms, s));
+        DCASE_TRY(launch_conv3x3_h(in_h, B, T_l, F_l, wf, params + o.conv_b[l], ypre, training ? stats : nullptr, sms, s));
         float* glu_img = wsp<float>(ws, L, names[l][6]);
         if (sb) DCASE_TRY(syncbn_allreduce_f64(sb, stats, 128, 3 * mid + l, s));
         DCASE_TRY(launch_bn_finalize(stats, n_pix * world, params + o.bn_w[l], params + o.bn_b[l], bn_running + l * 128,
                                      training, bn, params + o.glu_w[l], params + o.glu_b[l], F_l, glu_img, s));
-        DCASE_TRY(launch_glu_pool_fwd(ypre, n_pix, F_l, glu_img, drop(l), out, sms, s));
-        in = out;
+        DCASE_TRY(launch_glu_pool_fwd(ypre, n_pix, F_l, glu_img, drop(l), out, l == 1 ? wsp<void>(ws, L, "out1_h") : nullptr, sms, s));
+        in_h = wsp<void>(ws, L, "out1_h");
     }
 
     // ---- BiGRU, 2 layers (RNN.py:12-16) ----

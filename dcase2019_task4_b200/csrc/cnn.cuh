@@ -35,8 +35,10 @@ int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w,
                         const float* gamma, const float* beta, float* running /*[2][64]*/, int training,
                         float* fold0, double* mom_copy /*nullable: also copy the 54 moments there*/, cudaStream_t s);
 // cnn0.cu: fused block 0 (conv0 + BN + GLU + dropout + pool), forward / backward / parameter gradients
+// out (fp32, tf32-rounded: operand of the backward's weight-gradient MMAs) and out_h (fp16: operand of the next block's
+// forward conv) are both optional
 int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                    DropoutCfg drop, float* out, int num_sms, cudaStream_t s);
+                    DropoutCfg drop, float* out, void* out_h, int num_sms, cudaStream_t s);
 constexpr int kCnn0AccFloats = 128 * 16;   // {U[64][16], S2[64][16]}, zeroed before launch_cnn0_bwd
 int launch_cnn0_bwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
                     DropoutCfg drop, const float* d_out, float* us, int num_sms, cudaStream_t s);
@@ -46,11 +48,14 @@ int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* co
                              cudaStream_t s);
 int cnn0_kernels_init();
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* glu_img, DropoutCfg drop, float* out,
-                        int num_sms, cudaStream_t s);
+                        void* out_h /*nullable fp16 copy*/, int num_sms, cudaStream_t s);
 // conv_tc.cu: weight images are the swizzled shared-memory layout of the tcgen05 B operand (36864 floats each)
 // operand images (forward + mirrored / transposed for the data gradient) of BOTH 64 -> 64 conv layers, one launch
-int launch_conv_w_prep(const float* w1, float* w_fwd1, float* w_dgrad1, const float* w2, float* w_fwd2, float* w_dgrad2,
-                       cudaStream_t s);
+// (w_fwd: tf32 forward image, nullable; w_fwd_h: fp16 forward image [9][64][64] = 73,728 bytes, nullable)
+int launch_conv_w_prep(const float* w1, float* w_fwd1, float* w_dgrad1, void* w_fwd1_h, const float* w2, float* w_fwd2,
+                       float* w_dgrad2, void* w_fwd2_h, cudaStream_t s);
+int launch_conv3x3_h(const void* in_h, int B, int T_l, int F, const void* w_img_h, const float* bias, float* out,
+                     double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
 int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, const float* bias,
                    float* out, double* stats /*nullable [2][64]*/, int num_sms, cudaStream_t s);
 // GLU operand image written by bn_finalize (bytes): W' 16 KB | P 8 KB | {bias', exp scale, exp shift} 768 B |

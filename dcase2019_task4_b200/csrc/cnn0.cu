@@ -62,7 +62,8 @@ struct Cnn0Args {
     const float* glu_w;    // [64][64]
     const float* glu_b;    // [64]
     DropoutCfg drop;
-    float* out;            // fwd: [B][T/2][16][64]
+    float* out;            // fwd: [B][T/2][16][64], nullable
+    void* out_h;           // fwd: the same as fp16 (operand of conv1's forward), nullable
     const float* d_out;    // bwd: grad of out
     float* us;             // bwd: [128][16] accumulators {U[64][16], S2[64][16]} (zeroed by the caller)
 };
@@ -297,7 +298,8 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
 __device__ __forceinline__ uint32_t zrow_base(uint32_t region, int p) { return region + (uint32_t)(p * 128); }
 
 // average pool of one tile from its z rows in shared memory: thread = (window w, channels 4 c4 .. 4 c4 + 3)
-__device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scale, float* __restrict__ out_tile) {
+__device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scale, float* __restrict__ out_tile,
+                                          uint2* __restrict__ out_tile_h) {
     const int w = tid >> 4, c4 = tid & 15;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -312,9 +314,12 @@ __device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scal
             acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
         }
     }
-    *reinterpret_cast<float4*>(out_tile + w * 64 + 4 * c4) =            // conv1's MMA operand: rounded to tf32
-        make_float4(tf32_round_fast(scale * acc.x), tf32_round_fast(scale * acc.y), tf32_round_fast(scale * acc.z),
-                    tf32_round_fast(scale * acc.w));
+    const float4 o = make_float4(scale * acc.x, scale * acc.y, scale * acc.z, scale * acc.w);
+    if (out_tile)                                          // operand of the weight-gradient MMAs: rounded to tf32
+        *reinterpret_cast<float4*>(out_tile + w * 64 + 4 * c4) =
+            make_float4(tf32_round_fast(o.x), tf32_round_fast(o.y), tf32_round_fast(o.z), tf32_round_fast(o.w));
+    if (out_tile_h)                                        // operand of conv1's forward MMAs: fp16
+        out_tile_h[w * 16 + c4] = make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
 }
 
 __global__ void __launch_bounds__(kFwdThreads, 4)
@@ -344,6 +349,8 @@ cnn0_fwd_kernel(Cnn0Args a) {
     const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), a_a = tc::smem_u32(smem + kFwdA);
     const uint32_t t0_rb = krow_base(t0_a, row), z_rb = zrow_base(a_a, row);
     const bool drop = a.drop.enabled != 0;
+    float* const out_f = a.out;
+    uint2* const out_h = reinterpret_cast<uint2*>(a.out_h);
 
     // prologue: operand rows of the first tile and its MMA0; x rows of the second tile in shared memory, of the third in
     // registers
@@ -404,7 +411,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
         }
         TOCK(0);
         TICK();
-        if (prev >= 0) pool_tile(a_a, tid, pool_scale, a.out + prev * 16 * 64);     // z of `prev`: complete since barrier C
+        if (prev >= 0) pool_tile(a_a, tid, pool_scale, out_f ? out_f + prev * 16 * 64 : nullptr, out_h ? out_h + prev * 16 * 16 : nullptr);     // z of `prev`: complete since barrier C
         TOCK(1);
         TICK();
         uint32_t keep_hi_next = 0xffffffffu;
@@ -483,7 +490,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
         printf("cnn0_fwd tid %d: total %lld tiles %d | wait y + mma1 %lld | pool %lld | taps %lld | phase d %lld | sync A %lld | mma0+mask+wait %lld | phase f %lld | sync C %lld\n",
                tid, clock64() - t_begin, n_done, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7]);
 #endif
-    if (prev >= 0) pool_tile(a_a, tid, pool_scale, a.out + prev * 16 * 64);
+    if (prev >= 0) pool_tile(a_a, tid, pool_scale, out_f ? out_f + prev * 16 * 64 : nullptr, out_h ? out_h + prev * 16 * 16 : nullptr);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 128);
@@ -763,10 +770,10 @@ int cnn0_kernels_init() {
 }
 
 int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                    DropoutCfg drop, float* out, int num_sms, cudaStream_t s) {
+                    DropoutCfg drop, float* out, void* out_h, int num_sms, cudaStream_t s) {
     DCASE_PROF("cnn0_fused_fwd", s);
     Cnn0Args a{};
-    a.x = x; a.B = B; a.T = T; a.fold0 = fold0; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out;
+    a.x = x; a.B = B; a.T = T; a.fold0 = fold0; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out; a.out_h = out_h;
     const long long n_tiles = (long long)B * T / 2;
     const long long grid = n_tiles < (long long)kFwdCtasPerSm * num_sms ? n_tiles : (long long)kFwdCtasPerSm * num_sms;
     cnn0_fwd_kernel<<<(int)grid, kFwdThreads, kFwdSmemBytes, s>>>(a);

@@ -13,6 +13,8 @@
 //                     (MN-major operands, SWIZZLE_128B_BASE32B), all 9 taps of one input-channel half per CTA,
 //                     accumulated in TMEM over all tiles of the persistent CTA
 // Both are warp-specialised (TMA producer / MMA issuer warps / epilogue warps) around mbarrier rings.
+#include <cuda_fp16.h>
+
 #include "cnn.cuh"
 #include "tc.cuh"
 #include "tma.cuh"            // CUtensorMap helpers (the encoder is fetched through cudaGetDriverEntryPoint)
@@ -24,10 +26,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
 
-int encode_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
-               CUtensorMapSwizzle swz) {
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+               CUtensorMapSwizzle swz, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box,
+    const CUresult r = g_encode_tiled(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { dcase_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DCASE_ERR_CUDA; }
@@ -52,6 +54,14 @@ int make_act_map(CUtensorMap* map, const float* base, int B, int T_l, int F, int
     const cuuint64_t strides[3] = {64 * sizeof(float), (cuuint64_t)F * 64 * sizeof(float), (cuuint64_t)T_l * F * 64 * sizeof(float)};
     const cuuint32_t box[4] = {32, (cuuint32_t)pitch, (cuuint32_t)box_rows, 1};
     return encode_map(map, base, 4, dims, strides, box, swz);
+}
+
+// the same view of an fp16 copy of the activation: one 128-byte row holds all 64 channels of a pixel
+int make_act_map_h(CUtensorMap* map, const void* base, int B, int T_l, int F, int box_rows, int pitch) {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)F, (cuuint64_t)T_l, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {64 * 2, (cuuint64_t)F * 64 * 2, (cuuint64_t)T_l * F * 64 * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)pitch, (cuuint32_t)box_rows, 1};
+    return encode_map(map, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
 }
 
 int make_rows_map(CUtensorMap* map, const float* base, long long n_rows, int box_rows, CUtensorMapSwizzle swz) {
@@ -79,20 +89,26 @@ constexpr int kWImgBytes = 9 * 16384;             // [9 taps][2 k-blocks][64 row
 // W [n][c][tap] -> shared-memory images (K-major SW128 B operands, rows = output channel of the pass)
 //   forward: image[tap ][c / 32][row n][c % 32] = W[n][c][tap]
 //   dgrad  : image[8-tap][n / 32][row c][n % 32] = W[n][c][tap]      (mirrored taps, transposed channels)
+//   forward, fp16 (the forward pass multiplies fp16 copies: same 10 explicit mantissa bits as tf32, half the operand bytes):
+//            image[tap][row n][c] = W[n][c][tap], rows of 64 fp16 = 128 B, 16-byte chunks swizzled by row
 struct ConvWPrepArgs {     // blockIdx.y = layer (both 64 -> 64 conv layers of the CNN in one launch)
     const float* w[2];
-    float* img_fwd[2];
+    float* img_fwd[2];     // nullable
     float* img_dgrad[2];
+    __half* img_fwd_h[2];  // nullable
 };
 __global__ void conv_w_image_kernel(ConvWPrepArgs a) {
     const float* __restrict__ w = a.w[blockIdx.y];
     float* __restrict__ img_fwd = a.img_fwd[blockIdx.y];
     float* __restrict__ img_dgrad = a.img_dgrad[blockIdx.y];
+    __half* __restrict__ img_h = a.img_fwd_h[blockIdx.y];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * 64 * 9; i += gridDim.x * blockDim.x) {
         const int tap = i % 9, c = (i / 9) & 63, n = i / 576;
-        const float v = tc::tf32_rn(__ldg(w + i));
-        img_fwd[(tap * 16384 + (c >> 5) * 8192 + tc::sw128_off(n, c & 31)) >> 2] = v;
+        const float wv = __ldg(w + i);
+        const float v = tc::tf32_rn(wv);
+        if (img_fwd) img_fwd[(tap * 16384 + (c >> 5) * 8192 + tc::sw128_off(n, c & 31)) >> 2] = v;
         img_dgrad[((8 - tap) * 16384 + (n >> 5) * 8192 + tc::sw128_off(c, n & 31)) >> 2] = v;
+        if (img_h) img_h[(tap * 8192 + (n >> 3) * 1024 + (n & 7) * 128 + ((((c >> 3) ^ n) & 7) << 4) + (c & 7) * 2) >> 1] = __float2half_rn(wv);
     }
 }
 
@@ -119,11 +135,15 @@ __device__ __forceinline__ TileGeom decode_tile(int tile, int halves, int tblock
 // MMAs and refilled with the next tile's block while the other block is being multiplied: loads, MMAs and
 // epilogues of consecutive tiles overlap (full / empty mbarrier ring, two TMEM accumulators).
 // ---------------------------------------------------------------------------------------------
+// HALF = true (the forward pass): input and weights are fp16 copies, kind::f16 MMAs with K = 16.  A pixel's 64 channels
+// are ONE 128-byte row, so a tile's whole halo is one staging unit (one TMA box set) and a tile takes 36 MMAs instead of
+// 72; the weight image shrinks to 72 KB.
 constexpr int kUnits = 3;
 constexpr int kConv2SmemBytes = kWImgBytes + kUnits * kHaloBlk + 256 + 18 * 8 + 4 * 2048;
-constexpr int kConv2Threads = 224;
+constexpr int kConv2Threads = 352;          // warps 0 TMA, 1 and 6 MMA, 2..5 epilogue; HALF: 7..10 a second epilogue quartet
+constexpr int kHalfImgBytes = 9 * 8192;
 
-template <int PITCH>
+template <int PITCH, bool HALF>
 __global__ void __launch_bounds__(kConv2Threads, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_constant__ CUtensorMap in_map2, int B, int T_l, int F,
                    const float* __restrict__ w_img,
@@ -139,7 +159,10 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
     uint64_t* acc_empty = bars + 2 * kUnits + 2;            // [2]        epilogue drained -> MMA
     uint64_t* w_bar = bars + 2 * kUnits + 4;
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 16);
-    unsigned char* stage_base = reinterpret_cast<unsigned char*>(bars + 18);    // 4 warps x 2 KB epilogue staging (128-B aligned)
+    // epilogue staging, 2 KB per epilogue warp (128-B aligned): behind the barriers, or -- HALF: eight warps -- in the half
+    // of the weight region the fp16 image leaves free
+    unsigned char* stage_base = HALF ? Wi + kHalfImgBytes : reinterpret_cast<unsigned char*>(bars + 18);
+    constexpr int kEpiWarps = HALF ? 8 : 4;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler: role branches stay uniform
     constexpr int halves = PITCH == 10 ? 2 : 1;
@@ -149,7 +172,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
 
     if (tid == 0) {
         for (int i = 0; i < kUnits; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 32 * kEpiWarps); }
         tc::mbar_init(w_bar, 1);
         tc::fence_mbar_init();
     }
@@ -162,14 +185,15 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(w_bar, kWImgBytes);
+            constexpr int kTapBytes = HALF ? 8192 : 16384;
+            mbar_expect_tx(w_bar, 9 * kTapBytes);
             for (int i = 0; i < 9; ++i)
-                bulk_g2s(Wi + i * 16384, reinterpret_cast<const unsigned char*>(w_img) + i * 16384, 16384, w_bar);
+                bulk_g2s(Wi + i * kTapBytes, reinterpret_cast<const unsigned char*>(w_img) + i * kTapBytes, kTapBytes, w_bar);
             int u = 0, n = 0;                       // staging unit of the next box and how often it has been used
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const TileGeom g = decode_tile(tile, halves, tblocks);
 #pragma unroll 1
-                for (int kb = 0; kb < 2; ++kb) {
+                for (int kb = 0; kb < (HALF ? 1 : 2); ++kb) {
                     if (n >= 1) tc::mbar_wait(&empty[u], (n - 1) & 1);
                     // the 18 halo rows arrive as five boxes (4 + 4 + 4 + 4 + 2 frames, 1024-byte aligned pieces): the TMA
                     // unit works on boxes concurrently but walks the 128-byte rows of one box slowly (~30 ns per row)
@@ -188,7 +212,9 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
         // Issuer w takes the tiles it = w, w + 2, ... (accumulator w); unit j = 2 it + kb of the producer's sequence.
         const int w = warp == 1 ? 0 : 1;
         tc::mbar_wait(w_bar, 0);
-        constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+        constexpr uint32_t idesc = HALF ? tc::idesc_f16(128, 64, 0, 0) : tc::idesc_tf32(128, 64, 0, 0);
+        constexpr int kKb = HALF ? 1 : 2;              // staging units (32-channel blocks) per tile
+        constexpr int kTapBytes = HALF ? 8192 : 16384;
         const uint32_t a_hi = tc::desc_hi(PITCH * 128, 2), b_hi = tc::desc_hi(1024, 2);
         const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(Wi), 16);
         const uint32_t u_lo0 = tc::desc_lo(tc::smem_u32(units), 16);
@@ -208,8 +234,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
             if (use >= 1) tc::mbar_wait(&acc_empty[w], (use - 1) & 1);
             TOCK(t_acc);
 #pragma unroll 1
-            for (int kb = 0; kb < 2; ++kb) {
-                const int j = 2 * it + kb, u = j % kUnits, n = j / kUnits;
+            for (int kb = 0; kb < kKb; ++kb) {
+                const int j = kKb * it + kb, u = j % kUnits, n = j / kUnits;
                 TICK();
                 tc::mbar_wait(&full[u], n & 1);
                 TOCK(t_full);
@@ -221,9 +247,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
                 for (int tap = 0; tap < 9; ++tap) {
                     const int dy = tap / 3 - 1, dx = tap % 3 - 1;
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                        tc::umma_tf32_elect(d, a_lo0 + ((((1 + dy) * PITCH + 1 + dx) * 128 + k4 * 32) >> 4), a_hi,
-                                            b_lo1 + ((tap * 16384 + k4 * 32) >> 4), b_hi, idesc, (kb > 0 || tap > 0 || k4 > 0) ? 1u : 0u);
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint32_t al = a_lo0 + ((((1 + dy) * PITCH + 1 + dx) * 128 + k4 * 32) >> 4);
+                        const uint32_t bl = b_lo1 + ((tap * kTapBytes + k4 * 32) >> 4);
+                        const uint32_t acc = (kb > 0 || tap > 0 || k4 > 0) ? 1u : 0u;
+                        if (HALF) tc::umma_f16_elect(d, al, a_hi, bl, b_hi, idesc, acc);
+                        else tc::umma_tf32_elect(d, al, a_hi, bl, b_hi, idesc, acc);
+                    }
                 }
                 tc::umma_commit_elect(&empty[u]);        // unit free once these MMAs have read it
                 TOCK(t_issue);
@@ -235,9 +265,14 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
             printf("mma warp %d: total %lld  wait acc_empty %lld  wait full %lld  issue %lld  tiles %d\n", w, clock64() - t_begin, t_acc,
                    t_full, t_issue, use);
 #endif
-    } else {
+    } else if (warp <= 5 || HALF) {
+        // HALF: the MMAs of a tile take half as long, so the epilogue (accumulator -> staging -> 128-byte lines + statistics,
+        // ~3300 cycles per tile and quartet) would bound the kernel: two quartets split the 64 output channels
         const int wq = warp & 3;                   // TMEM lane quadrant of this warp
-        const uint32_t stage_a = tc::smem_u32(stage_base) + (uint32_t)wq * 2048u;
+        const int eh = warp >= 7 ? 1 : 0;          // second quartet: channels 32..63
+        const int slot = wq + 4 * eh;
+        const int ch_lo = HALF ? eh : 0, ch_hi = HALF ? eh + 1 : 2;
+        const uint32_t stage_a = tc::smem_u32(stage_base) + (uint32_t)slot * 2048u;
         int it = 0;
         // BatchNorm batch statistics of the output (CNN.py:49) ride in the epilogue: in the read-back loop below a lane
         // always sees the same 16-byte channel chunk (lane & 7), so it keeps that chunk's sum / sum of squares for both
@@ -257,7 +292,14 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
             TICK();
             tc::fence_after_sync();
             float acc[64];
-            tc::tmem_ld_row64(tmem, wq, ac * 64, acc);
+            if (HALF) {
+                const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ac * 64 + 32 * eh);
+                tc::tmem_ld16(ta, acc);              // this quartet's 32 columns sit in acc[0..31]
+                tc::tmem_ld16(ta + 16, acc + 16);
+                tc::tmem_ld_wait();
+            } else {
+                tc::tmem_ld_row64(tmem, wq, ac * 64, acc);
+            }
             tc::fence_before_sync();
             mbar_arrive(&acc_empty[ac]);
             TOCK(t_ld);
@@ -267,6 +309,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
             // go through a 2 KB per-warp staging tile (XOR-swizzled chunks) and leave as full 128-byte lines.
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
+                if (ch < ch_lo || ch >= ch_hi) continue;
 #pragma unroll
                 for (int rh = 0; rh < 2; ++rh) {
                     if ((lane >> 4) == rh) {
@@ -274,7 +317,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + 32 * ch + 4 * q);
-                            const int e = 32 * ch + 4 * q;
+                            const int e = (HALF ? 0 : 32 * ch) + 4 * q;
                             st_shared_v4(rb + (uint32_t)((q ^ (lane & 7)) << 4), acc[e] + b4.x, acc[e + 1] + b4.y, acc[e + 2] + b4.z,
                                          acc[e + 3] + b4.w);
                         }
@@ -312,17 +355,19 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap in_map4, const __grid_con
                 part[i] += __shfl_xor_sync(0xffffffffu, part[i], 8);
                 part[i] += __shfl_xor_sync(0xffffffffu, part[i], 16);
             }
-            float* mine = reinterpret_cast<float*>(stage_base + wq * 2048);
+            float* mine = reinterpret_cast<float*>(stage_base + slot * 2048);
             if (lane < 8) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i)      // entry = (sum | sumsq) * 64 + channel, channel = 32 ch + 4 (lane & 7) + e
                     mine[(i >> 3) * 64 + ((i >> 2) & 1) * 32 + 4 * lane + (i & 3)] = part[i];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int e = 32 * wq + lane;
-            const float* all = reinterpret_cast<const float*>(stage_base);
-            const double tot = (double)all[e] + (double)all[512 + e] + (double)all[1024 + e] + (double)all[1536 + e];
-            atomicAdd(stats + e, tot);                 // [0,64): sum, [64,128): sum of squares
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+            if (eh == 0) {                             // the first quartet's 128 threads own one entry each
+                const int e = 32 * wq + lane;
+                const float* all = reinterpret_cast<const float*>(stage_base) + (HALF ? ((e >> 5) & 1) * 2048 : 0);   // the quartet that owns
+                const double tot = (double)all[e] + (double)all[512 + e] + (double)all[1024 + e] + (double)all[1536 + e];   // the channel's half
+                atomicAdd(stats + e, tot);             // [0,64): sum, [64,128): sum of squares
+            }
         }
     }
     tc::fence_before_sync();
@@ -462,15 +507,17 @@ int conv_tc_kernels_init() {
     { const int rc = dcase_tma_init(); if (rc != DCASE_OK) return rc; }
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
     DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_tma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConv2SmemBytes));
     return DCASE_OK;
 }
 
-int launch_conv_w_prep(const float* w1, float* w_fwd1, float* w_dgrad1, const float* w2, float* w_fwd2, float* w_dgrad2,
-                       cudaStream_t s) {
+int launch_conv_w_prep(const float* w1, float* w_fwd1, float* w_dgrad1, void* w_fwd1_h, const float* w2, float* w_fwd2,
+                       float* w_dgrad2, void* w_fwd2_h, cudaStream_t s) {
     DCASE_PROF("conv_w_prep", s);
-    ConvWPrepArgs a{{w1, w2}, {w_fwd1, w_fwd2}, {w_dgrad1, w_dgrad2}};
+    ConvWPrepArgs a{{w1, w2}, {w_fwd1, w_fwd2}, {w_dgrad1, w_dgrad2}, {(__half*)w_fwd1_h, (__half*)w_fwd2_h}};
     conv_w_image_kernel<<<dim3(72, 2), 256, 0, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
@@ -488,8 +535,27 @@ int launch_conv3x3(const float* in, int B, int T_l, int F, const float* w_img, c
     DCASE_TRY_RC(make_act_map(&in_map2, in, B, T_l, F, 2, pitch, CU_TENSOR_MAP_SWIZZLE_128B));
     // BatchNorm batch statistics ([64] sums | [64] sums of squares, fp64) are accumulated by the conv epilogue itself
     if (stats) DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
-    if (F == 16) conv3x3_tma_kernel<10><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out, stats);
-    else conv3x3_tma_kernel<8><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out, stats);
+    if (F == 16) conv3x3_tma_kernel<10, false><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out, stats);
+    else conv3x3_tma_kernel<8, false><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w_img, bias, out, stats);
+    DCASE_LAUNCH_CHECK();
+    return DCASE_OK;
+}
+
+// forward pass on fp16 copies of the input activation and of the weights (image from launch_conv_w_prep); fp32 output
+int launch_conv3x3_h(const void* in_h, int B, int T_l, int F, const void* w_img_h, const float* bias, float* out,
+                     double* stats, int num_sms, cudaStream_t s) {
+    DCASE_PROF(F == 16 ? "conv3x3_fwd_l1" : "conv3x3_fwd_l2", s);
+    DCASE_REQUIRE(F == 16 || F == 4, "conv3x3 is built for the 16- and 4-bin layers of cfg.crnn_kwargs");
+    const int n_tiles = B * ((T_l + 15) / 16) * (F == 16 ? 2 : 1);
+    const int gx = n_tiles < num_sms ? n_tiles : num_sms;
+    CUtensorMap in_map4, in_map2;
+    const int pitch = F == 16 ? 10 : 8;
+    DCASE_TRY_RC(make_act_map_h(&in_map4, in_h, B, T_l, F, 4, pitch));
+    DCASE_TRY_RC(make_act_map_h(&in_map2, in_h, B, T_l, F, 2, pitch));
+    if (stats) DCASE_CUDA_CHECK(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
+    const float* w = reinterpret_cast<const float*>(w_img_h);
+    if (F == 16) conv3x3_tma_kernel<10, true><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w, bias, out, stats);
+    else conv3x3_tma_kernel<8, true><<<gx, kConv2Threads, kConv2SmemBytes, s>>>(in_map4, in_map2, B, T_l, F, w, bias, out, stats);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

@@ -12,6 +12,8 @@
 //     it (MN-major) and the (2,4) average pool is a second MMA with a 0/1 window matrix (as in cnn0.cu).
 // Control warp (warp 8): TMA ring of two input buffers, MMA1 one tile ahead, MMA2, all through mbarriers; the compute
 // warps never meet a block-wide barrier.  Two CTAs per SM.
+#include <cuda_fp16.h>
+
 #include "cnn.cuh"
 #include "tc.cuh"
 #include "tma.cuh"
@@ -28,6 +30,7 @@ struct GluFwdArgs {
     const float* img;      // operand image written by bn_finalize (cnn.cuh: kGluImg*)
     DropoutCfg drop;
     float* out;            // [n_pix / 8][64]
+    unsigned short* out_h; // the same as fp16 bits (operand of the next block's forward conv), nullable
 };
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -171,10 +174,14 @@ glu_pool_fwd_tma_kernel(const __grid_constant__ CUtensorMap in_map, GluFwdArgs a
                 if (lane < 16) {                  // accumulator row m of an M=64 MMA lives in lane 32*(m/16) + m%16
                     const long long o0 = ptile * 16;
                     float* dst = a.out + o0 * 64 + 16 * warp + lane;
+                    unsigned short* dst_h = a.out_h ? a.out_h + o0 * 64 + 16 * warp + lane : nullptr;
 #pragma unroll
                     for (int w = 0; w < 16; ++w) {
                         const float o = pool_scale * v[w];
-                        if (o0 + w < n_out) dst[w * 64] = round_out ? tc::tf32_rn(o) : o;
+                        if (o0 + w < n_out) {
+                            dst[w * 64] = round_out ? tc::tf32_rn(o) : o;
+                            if (dst_h) dst_h[w * 64] = __half_as_ushort(__float2half_rn(o));
+                        }
                     }
                 }
             }
@@ -600,12 +607,12 @@ int launch_glu_pool_bwd(const float* ypre, long long n_pix, int F, const float* 
 }
 
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* glu_img, DropoutCfg drop, float* out,
-                        int num_sms, cudaStream_t s) {
+                        void* out_h, int num_sms, cudaStream_t s) {
     DCASE_PROF(F == 16 ? "glu_pool_fwd_l1" : "glu_pool_fwd_l2", s);
     DCASE_REQUIRE(F == 16 || F == 4, "glu_pool is built for the 16- and 4-bin blocks of cfg.crnn_kwargs");
     DCASE_REQUIRE(n_pix > 0 && n_pix % (2 * F) == 0 && n_pix < (1ll << 31), "pixel count must be whole frame pairs");
     GluFwdArgs a{};
-    a.n_pix = n_pix; a.F = F; a.img = glu_img; a.drop = drop; a.out = out;
+    a.n_pix = n_pix; a.F = F; a.img = glu_img; a.drop = drop; a.out = out; a.out_h = (unsigned short*)out_h;
     CUtensorMap in_map;
     { const int rc = make_rows_map(&in_map, ypre, n_pix, kTile, CU_TENSOR_MAP_SWIZZLE_128B); if (rc != DCASE_OK) return rc; }
     const long long n_tiles = (n_pix + kTile - 1) / kTile;
