@@ -33,7 +33,8 @@ def main(path):
         rows = list(csv.reader(open(path)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
-    print(",".join(["kernel", "grid", "block"] + [c for c, _ in COLS] + ["stalls(cycles per issued inst)"]))
+    w = csv.writer(sys.stdout, lineterminator="\n")      # kernel names contain commas (template arguments): quoted
+    w.writerow(["kernel", "grid", "block"] + [c for c, _ in COLS] + ["stalls(cycles per issued inst)"])
     for r in data:
         out = [short(r[ix["Kernel Name"]]), r[ix["Grid Size"]].replace(",", " "), r[ix["Block Size"]].replace(",", " ")]
         for c, k in COLS:
@@ -63,7 +64,7 @@ def main(path):
                 if f >= 0.3:
                     st.append("%s=%.1f" % (s, f))
         out.append(" ".join(st))
-        print(",".join(out))
+        w.writerow(out)
 
 
 if __name__ == "__main__":

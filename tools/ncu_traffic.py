@@ -21,10 +21,13 @@ def prof_name(kernel, grid, order):
         return "cnn0_fused_fwd"
     if k.startswith("cnn0_bwd_kernel"):
         return "cnn0_fused_bwd"
-    if k.startswith("conv3x3_tma_kernel<10>"):
-        return "conv3x3_fwd_l1" if order["conv10"] <= 2 else "conv3x3_dgrad_l1"
-    if k.startswith("conv3x3_tma_kernel<8>"):
-        return "conv3x3_fwd_l2" if order["conv8"] <= 2 else "conv3x3_dgrad_l2"
+    if k.startswith("conv3x3_tma_kernel<"):          # <PITCH, HALF>: HALF = the fp16 forward pass, else the data gradient
+        args = k[k.index("<") + 1:k.index(">")].replace("(int)", "").replace("(bool)", "").replace(" ", "").split(",")
+        layer = "l1" if args[0] == "10" else "l2"
+        if len(args) > 1:
+            return ("conv3x3_fwd_" if args[1] in ("1", "true") else "conv3x3_dgrad_") + layer
+        key = "conv10" if args[0] == "10" else "conv8"
+        return ("conv3x3_fwd_" if order[key] <= 2 else "conv3x3_dgrad_") + layer
     if k.startswith("conv_wgrad_tma_kernel<10>"):
         return "conv3x3_wgrad_l1"
     if k.startswith("conv_wgrad_tma_kernel<8>"):
@@ -39,7 +42,8 @@ def prof_name(kernel, grid, order):
             "cnn0_moments_kernel": "cnn0_moments", "bn0_finalize_kernel": "bn0_finalize",
             "bn_bwd_apply_kernel": "bn_bwd_apply", "finish_kernel": "logmel_finish", "clip_max_kernel": "logmel_finish",
             "colsum_batch_kernel": "colsum", "conv_w_image_kernel": "conv_w_prep",
-            "cnn0_bwd_finalize_kernel": "cnn0_bwd_finalize"}.get(k.split("<")[0], k)
+            "cnn0_bwd_finalize_kernel": "cnn0_bwd_finalize", "gemm_tc_kernel": "gemm_tc",
+            "syncbn_allreduce_kernel": "syncbn_allreduce"}.get(k.split("<")[0], k)
 
 
 def main(path):
