@@ -11,16 +11,17 @@ namespace {
 constexpr int kD = 128;        // 2 * hidden
 constexpr int kMaxC = 16;      // class slots
 
-__device__ __forceinline__ void softmax_classes(const float (&ls)[kMaxC], int NC, float (&a_raw)[kMaxC]) {
+template <int KC>
+__device__ __forceinline__ void softmax_classes(const float (&ls)[KC], int NC, float (&a_raw)[KC]) {
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) if (c < NC) mx = fmaxf(mx, ls[c]);
+    for (int c = 0; c < KC; ++c) if (c < NC) mx = fmaxf(mx, ls[c]);
     float sum = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) { a_raw[c] = c < NC ? __expf(ls[c] - mx) : 0.f; sum += a_raw[c]; }
+    for (int c = 0; c < KC; ++c) { a_raw[c] = c < NC ? __expf(ls[c] - mx) : 0.f; sum += a_raw[c]; }
     const float inv = 1.f / sum;
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) a_raw[c] *= inv;
+    for (int c = 0; c < KC; ++c) a_raw[c] *= inv;
 }
 
 __device__ __forceinline__ void load_head_weights(const HeadArgs& a, float* Wd, float* Ws, float* bd, float* bs) {
@@ -69,14 +70,15 @@ __device__ __forceinline__ void stage_rows(const HeadArgs& a, int b, int t0, int
 }
 
 // the kMaxC logits of one head for one staged row: acc[c] = bias[c] + sum_k xm_row[k] W[c][k]
-__device__ __forceinline__ void head_logits(const float* xm_row, const float* W, const float* bias, float (&acc)[kMaxC]) {
+template <int KC>
+__device__ __forceinline__ void head_logits(const float* xm_row, const float* W, const float* bias, float (&acc)[KC]) {
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) acc[c] = bias[c];
+    for (int c = 0; c < KC; ++c) acc[c] = bias[c];
 #pragma unroll 2
     for (int k4 = 0; k4 < kD / 4; ++k4) {
         const float4 v = *reinterpret_cast<const float4*>(xm_row + 4 * k4);
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
+        for (int c = 0; c < KC; ++c) {
             const float4 w = *reinterpret_cast<const float4*>(W + c * kD + 4 * k4);
             acc[c] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[c]))));
         }
@@ -88,6 +90,7 @@ constexpr int kHeadRows = 128;
 constexpr size_t kHeadSmem = (2 * kMaxC * kD + 2 * kMaxC) * sizeof(float) + kHeadRows * sizeof(uint4) +
                              (kHeadRows * kXPitch + kHeadRows * 2 * kMaxC) * sizeof(float);
 
+template <int KC>      // class slots computed: 10 (cfg.crnn_kwargs) or kMaxC
 __global__ void __launch_bounds__(kHeadThreads)
 head_fwd_kernel(HeadArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -105,37 +108,37 @@ head_fwd_kernel(HeadArgs a) {
     if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
     const int r = tid & 127, head = tid >> 7;          // head 0: dense -> strong; head 1: dense_softmax -> attention
     float num = 0.f, den = 0.f;                        // threads 0..NC-1 of the final pass own a class
-    float pn[kMaxC], pd[kMaxC];
+    float pn[KC], pd[KC];
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) { pn[c] = 0.f; pd[c] = 0.f; }
+    for (int c = 0; c < KC; ++c) { pn[c] = 0.f; pd[c] = 0.f; }
     for (int t0 = 0; t0 < a.To; t0 += kHeadRows) {
         const int n_rows = min(kHeadRows, a.To - t0);
         __syncthreads();                               // weights staged / previous chunk consumed
         stage_rows(a, b, t0, n_rows, seed, step, xm, keep_s);
         __syncthreads();
         if (r < n_rows) {
-            float acc[kMaxC];
-            head_logits(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
+            float acc[KC];
+            head_logits<KC>(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
             if (head == 0) {
                 const long long row = (long long)b * a.To + t0 + r;
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) {
+                for (int c = 0; c < KC; ++c) {
                     const float sg = sigmoid_fast(acc[c]);
                     ex[r * 2 * kMaxC + c] = sg;
                     if (c < a.NC) a.strong[row * a.NC + c] = sg;
                 }
             } else {
-                float ar[kMaxC];
-                softmax_classes(acc, a.NC, ar);
+                float ar[KC];
+                softmax_classes<KC>(acc, a.NC, ar);
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) ex[r * 2 * kMaxC + kMaxC + c] = fminf(fmaxf(ar[c], 1e-7f), 1.f);
+                for (int c = 0; c < KC; ++c) ex[r * 2 * kMaxC + kMaxC + c] = fminf(fmaxf(ar[c], 1e-7f), 1.f);
             }
         }
         __syncthreads();
         // attention pooling partial sums: thread (row, head 0) folds its row, then warps reduce per class
         if (head == 0 && r < n_rows) {
 #pragma unroll
-            for (int c = 0; c < kMaxC; ++c) {
+            for (int c = 0; c < KC; ++c) {
                 const float at = ex[r * 2 * kMaxC + kMaxC + c];
                 pn[c] = fmaf(ex[r * 2 * kMaxC + c], at, pn[c]);
                 pd[c] += at;
@@ -143,7 +146,7 @@ head_fwd_kernel(HeadArgs a) {
         }
     }
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
+    for (int c = 0; c < KC; ++c) {
         const float n = warp_sum(pn[c]), d = warp_sum(pd[c]);
         if ((tid & 31) == 0) { red[tid >> 5][c] = n; red[tid >> 5][kMaxC + c] = d; }
     }
@@ -159,6 +162,7 @@ head_fwd_kernel(HeadArgs a) {
 // Backward of the head for one clip per CTA; forward recomputed from the staged rows.  Thread (row, head) owns the
 // logit gradients of its head; d_x needs both heads' gradients of the row (exchanged through shared memory), and the
 // weight gradients are per-thread column sums over the staged chunk.
+template <int KC>
 __global__ void __launch_bounds__(kHeadThreads)
 head_bwd_kernel(HeadArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -176,34 +180,34 @@ head_bwd_kernel(HeadArgs a) {
     if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
     const int r = tid & 127, head = tid >> 7;
     // weight gradients: thread tid owns column k = tid & 127 of head (tid >> 7): 16 accumulators + bias slot
-    float gw[kMaxC];
+    float gw[KC];
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) gw[c] = 0.f;
+    for (int c = 0; c < KC; ++c) gw[c] = 0.f;
     float gb = 0.f;
     for (int t0 = 0; t0 < a.To; t0 += kHeadRows) {
         const int n_rows = min(kHeadRows, a.To - t0);
         __syncthreads();
         stage_rows(a, b, t0, n_rows, seed, step, xm, keep_s);
         __syncthreads();
-        float acc[kMaxC], ar[kMaxC];
+        float acc[KC], ar[KC];
         const bool live = r < n_rows;
         const long long row = (long long)b * a.To + t0 + r;
         if (live) {
-            head_logits(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
+            head_logits<KC>(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
             if (head == 0) {
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) sig_s[r][c] = sigmoid_fast(acc[c]);
+                for (int c = 0; c < KC; ++c) sig_s[r][c] = sigmoid_fast(acc[c]);
             } else {
-                softmax_classes(acc, a.NC, ar);
+                softmax_classes<KC>(acc, a.NC, ar);
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) dl[r * 2 * kMaxC + kMaxC + c] = ar[c];       // parked: head 0 needs `at`
+                for (int c = 0; c < KC; ++c) dl[r * 2 * kMaxC + kMaxC + c] = ar[c];       // parked: head 0 needs `at`
             }
         }
         __syncthreads();
         if (live) {
             if (head == 0) {
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) {
+                for (int c = 0; c < KC; ++c) {
                     float dld = 0.f;
                     if (c < a.NC) {
                         const float sg = sig_s[r][c];
@@ -216,10 +220,10 @@ head_bwd_kernel(HeadArgs a) {
                     acc[c] = dld;
                 }
             } else {
-                float da[kMaxC];
+                float da[KC];
                 float dot = 0.f;
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) {
+                for (int c = 0; c < KC; ++c) {
                     da[c] = 0.f;
                     if (c < a.NC) {
                         const float dwk = __ldg(a.d_weak + b * a.NC + c);
@@ -231,12 +235,12 @@ head_bwd_kernel(HeadArgs a) {
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) acc[c] = c < a.NC ? ar[c] * (da[c] - dot) : 0.f;
+                for (int c = 0; c < KC; ++c) acc[c] = c < a.NC ? ar[c] * (da[c] - dot) : 0.f;
             }
         }
         __syncthreads();                               // every head-0 thread has read its `at` values
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) dl[r * 2 * kMaxC + head * kMaxC + c] = live ? acc[c] : 0.f;
+        for (int c = 0; c < KC; ++c) dl[r * 2 * kMaxC + head * kMaxC + c] = live ? acc[c] : 0.f;
         __syncthreads();
         // d x = mask * 2 * (Wd^T dl_d + Ws^T dl_s): thread (row, head) writes channels 64 head .. 64 head + 63
         if (live) {
@@ -247,7 +251,7 @@ head_bwd_kernel(HeadArgs a) {
             for (int k4 = 16 * head; k4 < 16 * head + 16; ++k4) {
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) {
+                for (int c = 0; c < KC; ++c) {
                     const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
                     const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
                     const float gd = dl_row[c], gs = dl_row[kMaxC + c];
@@ -274,9 +278,9 @@ head_bwd_kernel(HeadArgs a) {
                 const float xv = xm[q * kXPitch + k];
                 const float* dq = dl + q * 2 * kMaxC + head * kMaxC;
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) gw[c] = fmaf(dq[c], xv, gw[c]);
+                for (int c = 0; c < KC; ++c) gw[c] = fmaf(dq[c], xv, gw[c]);
             }
-            if (k < kMaxC)
+            if (k < KC)
                 for (int q = 0; q < n_rows; ++q) gb += dl[q * 2 * kMaxC + head * kMaxC + k];
         }
     }
@@ -285,7 +289,7 @@ head_bwd_kernel(HeadArgs a) {
         float* g_w = head ? a.g_w_soft : a.g_w_dense;
         float* g_b = head ? a.g_b_soft : a.g_b_dense;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c)
+        for (int c = 0; c < KC; ++c)
             if (c < a.NC) atomicAdd(g_w + c * kD + k, gw[c]);
         if (k < a.NC) atomicAdd(g_b + k, gb);
     }
@@ -422,21 +426,25 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
 }  // namespace
 
 int head_kernels_init() {
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
-    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_fwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_bwd_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_fwd_kernel<kMaxC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
+    DCASE_CUDA_CHECK(cudaFuncSetAttribute(head_bwd_kernel<kMaxC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem));
     return DCASE_OK;
 }
 
 int launch_head_fwd(const HeadArgs& a, cudaStream_t s) {
     DCASE_PROF("head_fwd", s);
-    head_fwd_kernel<<<a.B, kHeadThreads, kHeadSmem, s>>>(a);
+    if (a.NC <= 10) head_fwd_kernel<10><<<a.B, kHeadThreads, kHeadSmem, s>>>(a);      // 10 classes: 37 % fewer FMAs / loads than 16 slots
+    else head_fwd_kernel<kMaxC><<<a.B, kHeadThreads, kHeadSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
 
 int launch_head_bwd(const HeadArgs& a, cudaStream_t s) {
     DCASE_PROF("head_bwd", s);
-    head_bwd_kernel<<<a.B, kHeadThreads, kHeadSmem, s>>>(a);
+    if (a.NC <= 10) head_bwd_kernel<10><<<a.B, kHeadThreads, kHeadSmem, s>>>(a);
+    else head_bwd_kernel<kMaxC><<<a.B, kHeadThreads, kHeadSmem, s>>>(a);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }

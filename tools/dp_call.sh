@@ -10,10 +10,15 @@ run() {
     echo "rc=$? $(tail -1 "gpurun_out/dp_$name.log" | cut -c1-900)" >> gpurun_out/dp_call.log
 }
 : > gpurun_out/dp_call.log
-run tests 400 python -u -m pytest -q -m gpu -s --timeout 180 --timeout-method=thread tests/test_gpu_dp.py
+run tests 600 python -u -m pytest -q -m gpu -s --timeout 280 --timeout-method=thread tests/test_gpu_dp.py tests/test_gpu_syncbn.py tests/test_gpu_crnn.py tests/test_gpu_api.py
 for n in "$@"; do
     run "bench_n$n" 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus "$n" --steps 30 --warmup 6
 done
+if [ -n "$SYNCBN_ALSO" ]; then
+    for n in "$@"; do
+        run "bench_syncbn_n$n" 300 env DCASE_SYNC_BN=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus "$n" --steps 30 --warmup 6
+    done
+fi
 if [ -n "$NCCL_ALSO" ]; then
     for n in "$@"; do
         run "bench_nccl_n$n" 300 env DCASE_DP_NCCL=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus "$n" --steps 30 --warmup 6
