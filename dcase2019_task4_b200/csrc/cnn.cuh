@@ -40,12 +40,19 @@ int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w,
 int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
                     DropoutCfg drop, float* out, void* out_h, int num_sms, cudaStream_t s);
 constexpr int kCnn0AccFloats = 128 * 16;   // {U[64][16], S2[64][16]}, zeroed before launch_cnn0_bwd
+// what turns block 0's {U | S2} accumulator into its parameter gradients (n_pix = pixels behind the statistics; the
+// gradients are written x param_grad_scale, see launch_bn_bwd_apply)
+struct Cnn0BwdFinalize {
+    const double* mom;
+    long long n_pix;
+    const float *conv_w, *conv_b;
+    float param_grad_scale;
+    float *g_conv_w, *g_conv_b, *g_gamma, *g_beta, *g_glu_w, *g_glu_b;
+};
+// fin != NULL: the last CTA to finish runs the finalize pass itself (one launch less at the end of the backward chain)
 int launch_cnn0_bwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                    DropoutCfg drop, const float* d_out, float* us, int num_sms, cudaStream_t s);
-int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
-                             const float* fold0, const float* glu_w, const float* us, float param_grad_scale,
-                             float* g_conv_w, float* g_conv_b, float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b,
-                             cudaStream_t s);
+                    DropoutCfg drop, const float* d_out, float* us, const Cnn0BwdFinalize* fin, int num_sms, cudaStream_t s);
+int launch_cnn0_bwd_finalize(const Cnn0BwdFinalize& fin, const float* fold0, const float* glu_w, const float* us, cudaStream_t s);
 int cnn0_kernels_init();
 int launch_glu_pool_fwd(const float* ypre, long long n_pix, int F, const float* glu_img, DropoutCfg drop, float* out,
                         void* out_h /*nullable fp16 copy*/, int num_sms, cudaStream_t s);

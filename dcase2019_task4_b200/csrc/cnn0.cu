@@ -55,6 +55,17 @@ constexpr float kGateUnscale = -0.6931471805599453f;
 #endif
 constexpr float kLinScale = 0.5f * kGateUnscale;      // MMA1 delivers u = (lin + b) / 2 from the pre-scaled ys
 
+// Parameter gradients of the block from the {U | S2} accumulator (cnn0_bwd_finalize): a kernel of its own, or the last CTA
+// of cnn0_bwd_kernel (enabled = 1)
+struct Cnn0FinArgs {
+    int enabled;
+    const double* mom;
+    long long n_pix;
+    const float *w, *b, *glu_w_raw;
+    float pgs;
+    float *g_w, *g_b, *g_gamma, *g_beta, *g_glu_w, *g_glu_b;
+};
+
 struct Cnn0Args {
     const float* x;        // [B][T][64] z-scored log-mel
     int B, T;
@@ -65,7 +76,8 @@ struct Cnn0Args {
     float* out;            // fwd: [B][T/2][16][64], nullable
     void* out_h;           // fwd: the same as fp16 (operand of conv1's forward), nullable
     const float* d_out;    // bwd: grad of out
-    float* us;             // bwd: [128][16] accumulators {U[64][16], S2[64][16]} (zeroed by the caller)
+    float* us;             // bwd: [128][16] accumulators {U[64][16], S2[64][16]} (zeroed by the caller; us[10] = CTA ticket)
+    Cnn0FinArgs fin;       // bwd: the finalize pass, run by the last CTA to finish
 };
 
 __device__ __forceinline__ float ex2_ftz(float x) {
@@ -511,6 +523,9 @@ constexpr int kBwdMiscOff = 16384 + 2 * kBwdGroupBytes;
 constexpr int kBwdMiscGroupFloats = 4 * 66 + 128;          // xs | keep_lo
 constexpr int kBwdSmemBytes = kBwdMiscOff + (64 + 2 * kBwdMiscGroupFloats) * 4 + 6 * 8 + 8;
 
+__device__ __forceinline__ void cnn0_bwd_finalize_body(const Cnn0FinArgs& f, const float* __restrict__ fold0, const float* us, float* sm,
+                                                       int tid, int nt);
+
 __global__ void __launch_bounds__(kBwdThreads, 1)
 cnn0_bwd_kernel(Cnn0Args a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -698,67 +713,83 @@ cnn0_bwd_kernel(Cnn0Args a) {
         for (int j = 0; j < 10; ++j) atomicAdd(a.us + m * 16 + j, sc * v[j]);
     }
     tc::fence_before_sync();
+    __threadfence();                       // this CTA's accumulator atomics are visible before its ticket
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(*tmem_base_s, 512);
+    if (a.fin.enabled) {                   // the last CTA to finish turns the accumulator into the block's parameter gradients
+        __shared__ int is_last;
+        if (tid == 0) is_last = atomicAdd(reinterpret_cast<unsigned int*>(a.us + 10), 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            cnn0_bwd_finalize_body(a.fin, a.fold0, a.us, reinterpret_cast<float*>(smem + 16384), tid, kBwdThreads);   // the operand tiles are dead
+        }
+    }
 }
 
-// One block of 640 threads: {U, S2} -> GLU parameter gradients and S = Wg^T U + S2; then the BatchNorm / conv0 parameter
-// gradients from S and the tap moments, thread (c, k) owning tap k of channel c (the fp64 terms are spread over nine
-// threads per channel: B200's fp64 rate is low and this kernel is the last link of the backward chain before Adam).
-constexpr int kBwdFinThreads = 640;
-__global__ void __launch_bounds__(kBwdFinThreads)
-cnn0_bwd_finalize_kernel(const double* __restrict__ mom, long long n_pix, const float* __restrict__ w,
-                         const float* __restrict__ b, const float* __restrict__ fold0, const float* __restrict__ glu_w,
-                         const float* __restrict__ us, float pgs, float* __restrict__ g_w, float* __restrict__ g_b,
-                         float* __restrict__ g_gamma, float* __restrict__ g_beta, float* __restrict__ g_glu_w,
-                         float* __restrict__ g_glu_b) {
-    __shared__ float U[64][10], S[64][10], W0e[64][10];
-    __shared__ float Wg[64 * 65];                       // [n][c], padded: the S pass walks a column
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 640; i += kBwdFinThreads) {
+// {U, S2} -> GLU parameter gradients and S = Wg^T U + S2; then the BatchNorm / conv0 parameter gradients from S and the
+// tap moments, task (c, k) owning tap k of channel c (the fp64 terms are spread over nine tasks per channel: B200's fp64
+// rate is low and this is the last link of the backward chain before Adam).  `sm`: 6,080 floats of shared memory.
+__device__ __forceinline__ void cnn0_bwd_finalize_body(const Cnn0FinArgs& f, const float* __restrict__ fold0,
+                                                       const float* us, float* sm, int tid, int nt) {
+    float (*U)[10] = reinterpret_cast<float (*)[10]>(sm);
+    float (*S)[10] = reinterpret_cast<float (*)[10]>(sm + 640);
+    float (*W0e)[10] = reinterpret_cast<float (*)[10]>(sm + 1280);
+    float* Wg = sm + 1920;                               // [n][c], pitch 65: the S pass walks a column
+    for (int i = tid; i < 640; i += nt) {
         const int r = i / 10, j = i - r * 10;
-        U[r][j] = us[r * 16 + j];
+        U[r][j] = __ldcg(us + r * 16 + j);               // from L2: other CTAs' atomics
         W0e[r][j] = j < 9 ? fold0[kFold0Wf + j * 64 + r] : fold0[kFold0Bf + r];
     }
-    for (int i = tid; i < 4096; i += kBwdFinThreads) Wg[(i >> 6) * 65 + (i & 63)] = __ldg(glu_w + i);
+    for (int i = tid; i < 4096; i += nt) Wg[(i >> 6) * 65 + (i & 63)] = __ldg(f.glu_w_raw + i);
     __syncthreads();
-    for (int i = tid; i < 4096; i += kBwdFinThreads) {  // dWg[n][k] = sum_j U[n][j] W0e[k][j]
+    for (int i = tid; i < 4096; i += nt) {              // dWg[n][k] = sum_j U[n][j] W0e[k][j]
         const int n = i >> 6, k = i & 63;
-        float s = 0.f;
+        float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 10; ++j) s = fmaf(U[n][j], W0e[k][j], s);
-        g_glu_w[i] = pgs * s;
+        for (int j = 0; j < 10; ++j) acc = fmaf(U[n][j], W0e[k][j], acc);
+        f.g_glu_w[i] = f.pgs * acc;
     }
-    if (tid < 64) g_glu_b[tid] = pgs * U[tid][9];
-    {                                                   // S[c][j] = sum_n Wg[n][c] U[n][j] + S2[c][j]
-        const int c = tid / 10, j = tid - c * 10;
-        float s = us[(64 + c) * 16 + j];
+    if (tid < 64) f.g_glu_b[tid] = f.pgs * U[tid][9];
+    for (int task = tid; task < 640; task += nt) {      // S[c][j] = sum_n Wg[n][c] U[n][j] + S2[c][j]
+        const int c = task / 10, j = task - c * 10;
+        float acc = __ldcg(us + (64 + c) * 16 + j);
 #pragma unroll 8
-        for (int n = 0; n < 64; ++n) s = fmaf(Wg[n * 65 + c], U[n][j], s);
-        S[c][j] = s;
+        for (int n = 0; n < 64; ++n) acc = fmaf(Wg[n * 65 + c], U[n][j], acc);
+        S[c][j] = acc;
     }
     __syncthreads();
-    const int c = tid / 10, k = tid - c * 10;           // k = 9: the channel's gamma / beta / bias thread
-    const double n = (double)n_pix;
-    const double mean = fold0[kFold0Mean + c], invstd = fold0[kFold0Invstd + c], av = fold0[kFold0A + c];
-    const double S1 = S[c][9];                          // sum dY
-    double wG = 0.0;
-    for (int l = 0; l < 9; ++l) wG += (double)w[c * 9 + l] * (double)S[c][l];   // sum dY * (conv output - bias)
-    const double bm = (double)b[c] - mean;
-    const double S2 = invstd * (wG + bm * S1);          // sum dY * xhat
-    if (k == 9) {
-        g_gamma[c] = pgs * (float)S2;
-        g_beta[c] = pgs * (float)S1;
-        g_b[c] = 0.f;                                   // BN cancels the conv bias
-        return;
+    for (int task = tid; task < 640; task += nt) {
+        const int c = task / 10, k = task - c * 10;     // k = 9: the channel's gamma / beta / bias task
+        const double n = (double)f.n_pix;
+        const double mean = fold0[kFold0Mean + c], invstd = fold0[kFold0Invstd + c], av = fold0[kFold0A + c];
+        const double S1 = S[c][9];                      // sum dY
+        double wG = 0.0;
+        for (int l = 0; l < 9; ++l) wG += (double)f.w[c * 9 + l] * (double)S[c][l];   // sum dY * (conv output - bias)
+        const double bm = (double)f.b[c] - mean;
+        const double S2 = invstd * (wG + bm * S1);      // sum dY * xhat
+        if (k == 9) {
+            f.g_gamma[c] = f.pgs * (float)S2;
+            f.g_beta[c] = f.pgs * (float)S1;
+            f.g_b[c] = 0.f;                             // BN cancels the conv bias
+        } else {
+            double sxx = 0.0;                           // sum_p xhat_c * x_k
+            for (int l = 0; l < 9; ++l) {
+                const int lo = l <= k ? l : k, hi = l <= k ? k : l;
+                sxx += (double)f.w[c * 9 + l] * f.mom[9 + lo * 9 - (lo * (lo - 1)) / 2 + (hi - lo)];
+            }
+            sxx = invstd * (sxx + bm * f.mom[k]);
+            f.g_w[c * 9 + k] = f.pgs * (float)(av * ((double)S[c][k] - (S1 / n) * f.mom[k] - (S2 / n) * sxx));
+        }
     }
-    double sxx = 0.0;                                   // sum_p xhat_c * x_k
-    for (int l = 0; l < 9; ++l) {
-        const int lo = l <= k ? l : k, hi = l <= k ? k : l;
-        sxx += (double)w[c * 9 + l] * mom[9 + lo * 9 - (lo * (lo - 1)) / 2 + (hi - lo)];
-    }
-    sxx = invstd * (sxx + bm * mom[k]);
-    g_w[c * 9 + k] = pgs * (float)(av * ((double)S[c][k] - (S1 / n) * mom[k] - (S2 / n) * sxx));
+}
+
+// the same as a kernel of its own (SyncBN: the accumulator crosses the ranks between cnn0_bwd_kernel and this)
+constexpr int kBwdFinThreads = 640;
+__global__ void __launch_bounds__(kBwdFinThreads)
+cnn0_bwd_finalize_kernel(Cnn0FinArgs f, const float* __restrict__ fold0, const float* __restrict__ us) {
+    __shared__ float sm[6080];
+    cnn0_bwd_finalize_body(f, fold0, us, sm, threadIdx.x, kBwdFinThreads);
 }
 
 }  // namespace
@@ -782,10 +813,13 @@ int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const floa
 }
 
 int launch_cnn0_bwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                    DropoutCfg drop, const float* d_out, float* us, int num_sms, cudaStream_t s) {
+                    DropoutCfg drop, const float* d_out, float* us, const Cnn0BwdFinalize* fin, int num_sms, cudaStream_t s) {
     DCASE_PROF("cnn0_fused_bwd", s);
     Cnn0Args a{};
     a.x = x; a.B = B; a.T = T; a.fold0 = fold0; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.d_out = d_out; a.us = us;
+    if (fin)
+        a.fin = Cnn0FinArgs{1, fin->mom, fin->n_pix, fin->conv_w, fin->conv_b, glu_w, fin->param_grad_scale, fin->g_conv_w,
+                            fin->g_conv_b, fin->g_gamma, fin->g_beta, fin->g_glu_w, fin->g_glu_b};
     const long long n_tiles = (long long)B * T / 2;
     const long long grid = (n_tiles + 1) / 2 < num_sms ? (n_tiles + 1) / 2 : num_sms;
     cnn0_bwd_kernel<<<(int)grid, kBwdThreads, kBwdSmemBytes, s>>>(a);
@@ -793,13 +827,11 @@ int launch_cnn0_bwd(const float* x, int B, int T, const float* fold0, const floa
     return DCASE_OK;
 }
 
-int launch_cnn0_bwd_finalize(const double* mom, long long n_pix, const float* conv_w, const float* conv_b,
-                             const float* fold0, const float* glu_w, const float* us, float param_grad_scale,
-                             float* g_conv_w, float* g_conv_b, float* g_gamma, float* g_beta, float* g_glu_w, float* g_glu_b,
-                             cudaStream_t s) {
+int launch_cnn0_bwd_finalize(const Cnn0BwdFinalize& fin, const float* fold0, const float* glu_w, const float* us, cudaStream_t s) {
     DCASE_PROF("cnn0_bwd_finalize", s);
-    cnn0_bwd_finalize_kernel<<<1, kBwdFinThreads, 0, s>>>(mom, n_pix, conv_w, conv_b, fold0, glu_w, us, param_grad_scale, g_conv_w, g_conv_b, g_gamma,
-                                             g_beta, g_glu_w, g_glu_b);
+    const Cnn0FinArgs f{1, fin.mom, fin.n_pix, fin.conv_w, fin.conv_b, glu_w, fin.param_grad_scale, fin.g_conv_w, fin.g_conv_b,
+                        fin.g_gamma, fin.g_beta, fin.g_glu_w, fin.g_glu_b};
+    cnn0_bwd_finalize_kernel<<<1, kBwdFinThreads, 0, s>>>(f, fold0, us);
     DCASE_LAUNCH_CHECK();
     return DCASE_OK;
 }
