@@ -508,9 +508,11 @@ int dcase_bigru_forward(dcase_ctx* ctx, const float* x, int B, int To, const flo
     return DCASE_OK;
 }
 
-int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, const float* params, int flags,
-                        uint64_t seed, uint32_t step, int model_id, const void* scalars, const float* d_strong,
-                        const float* d_weak, const float* weak, void* ws, float* grads, void* stream_) {
+// fused_loss: the mean-teacher losses and their gradients are computed by the first phase of head_bwd (dcase_mt_fwd_bwd)
+static int crnn_backward_impl(dcase_ctx* ctx, const float* x, int B, int T, int NC, const float* params, int flags,
+                              uint64_t seed, uint32_t step, int model_id, const void* scalars, const float* d_strong,
+                              const float* d_weak, const float* weak, void* ws, float* grads, const LossArgs* fused_loss,
+                              void* stream_) {
     cudaStream_t s = (cudaStream_t)stream_;
     DCASE_REQUIRE(ctx && x && params && d_strong && d_weak && weak && ws && grads, "null argument");
     DCASE_TRY(check_shape(B, T, NC));
@@ -540,6 +542,7 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
     h.d_strong = d_strong; h.d_weak = d_weak; h.d_x = wsp<float>(ws, L, "d_rnn1");
     h.g_w_dense = grads + o.dense_w; h.g_b_dense = grads + o.dense_b;
     h.g_w_soft = grads + o.soft_w; h.g_b_soft = grads + o.soft_b;
+    if (fused_loss) { h.fused_loss = 1; h.loss = *fused_loss; }
     DCASE_TRY(launch_head_bwd(h, s));
 
     // ---- BiGRU BPTT, layer 1 then layer 0 ----
@@ -638,10 +641,16 @@ int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, co
     return DCASE_OK;
 }
 
-int dcase_mt_loss(dcase_ctx* ctx, const float* strong_s, const float* weak_s, const float* strong_t,
-                  const float* weak_t, const float* target, int B, int To, int NC, int weak_lo, int weak_hi,
-                  int strong_lo, int strong_hi, float cons_weight, const void* scalars, float* meters,
-                  float* d_strong, float* d_weak, void* stream_) {
+int dcase_crnn_backward(dcase_ctx* ctx, const float* x, int B, int T, int NC, const float* params, int flags,
+                        uint64_t seed, uint32_t step, int model_id, const void* scalars, const float* d_strong,
+                        const float* d_weak, const float* weak, void* ws, float* grads, void* stream_) {
+    return crnn_backward_impl(ctx, x, B, T, NC, params, flags, seed, step, model_id, scalars, d_strong, d_weak, weak, ws, grads,
+                              nullptr, stream_);
+}
+
+static int fill_loss_args(dcase_ctx* ctx, const float* strong_s, const float* weak_s, const float* strong_t, const float* weak_t,
+                          const float* target, int B, int To, int NC, int weak_lo, int weak_hi, int strong_lo, int strong_hi,
+                          float cons_weight, const void* scalars, float* meters, float* d_strong, float* d_weak, LossArgs* out) {
     DCASE_REQUIRE(ctx && strong_s && weak_s && target && meters && d_strong && d_weak, "null argument");
     DCASE_REQUIRE((strong_t == nullptr) == (weak_t == nullptr), "teacher outputs must both be given or both be NULL");
     DCASE_REQUIRE(B >= 1 && To >= 1 && NC >= 1 && NC <= 16, "bad shape");
@@ -653,6 +662,17 @@ int dcase_mt_loss(dcase_ctx* ctx, const float* strong_s, const float* weak_s, co
     a.d_strong = d_strong; a.d_weak = d_weak;
     a.partials = ctx->d_loss_scratch;
     a.ticket = reinterpret_cast<unsigned int*>(ctx->d_loss_scratch + kLossMaxCtas * 8);
+    *out = a;
+    return DCASE_OK;
+}
+
+int dcase_mt_loss(dcase_ctx* ctx, const float* strong_s, const float* weak_s, const float* strong_t,
+                  const float* weak_t, const float* target, int B, int To, int NC, int weak_lo, int weak_hi,
+                  int strong_lo, int strong_hi, float cons_weight, const void* scalars, float* meters,
+                  float* d_strong, float* d_weak, void* stream_) {
+    LossArgs a{};
+    DCASE_TRY(fill_loss_args(ctx, strong_s, weak_s, strong_t, weak_t, target, B, To, NC, weak_lo, weak_hi, strong_lo, strong_hi,
+                             cons_weight, scalars, meters, d_strong, d_weak, &a));
     return launch_mt_loss(a, (cudaStream_t)stream_);
 }
 
@@ -691,12 +711,15 @@ int dcase_mt_fwd_bwd(dcase_ctx* ctx, const dcase_mt_args* a, void* stream) {
                                 a->step, 0, a->scalars, a->strong_s, a->weak_s, a->ws_s, a->mom_s, stream));
     if (a->after_forward_event) DCASE_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a->after_forward_event, s));
     if (a->x_teacher) DCASE_CUDA_CHECK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    DCASE_TRY(dcase_mt_loss(ctx, a->strong_s, a->weak_s, a->x_teacher ? a->strong_t : nullptr,
-                            a->x_teacher ? a->weak_t : nullptr, a->target, a->B, To, a->n_class, a->weak_lo, a->weak_hi,
-                            a->strong_lo, a->strong_hi, a->cons_weight, a->scalars, a->meters, a->d_strong, a->d_weak,
-                            stream));
-    DCASE_TRY(dcase_crnn_backward(ctx, a->x_student, a->B, a->T, a->n_class, a->params_s, a->flags, a->seed, a->step, 0,
-                                  a->scalars, a->d_strong, a->d_weak, a->weak_s, a->ws_s, a->grads, stream));
+    // the losses run as the first phase of the backward's head kernel (one launch less between the forwards and the backward)
+    LossArgs la{};
+    DCASE_TRY(fill_loss_args(ctx, a->strong_s, a->weak_s, a->x_teacher ? a->strong_t : nullptr, a->x_teacher ? a->weak_t : nullptr,
+                             a->target, a->B, To, a->n_class, a->weak_lo, a->weak_hi, a->strong_lo, a->strong_hi, a->cons_weight,
+                             a->scalars, a->meters, a->d_strong, a->d_weak, &la));
+    const bool fuse = a->B <= kLossMaxCtas;
+    if (!fuse) DCASE_TRY(launch_mt_loss(la, s));
+    DCASE_TRY(crnn_backward_impl(ctx, a->x_student, a->B, a->T, a->n_class, a->params_s, a->flags, a->seed, a->step, 0,
+                                 a->scalars, a->d_strong, a->d_weak, a->weak_s, a->ws_s, a->grads, fuse ? &la : nullptr, stream));
     return DCASE_OK;
 }
 

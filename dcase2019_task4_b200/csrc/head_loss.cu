@@ -159,153 +159,16 @@ head_fwd_kernel(HeadArgs a) {
     }
 }
 
-// Backward of the head for one clip per CTA; forward recomputed from the staged rows.  Thread (row, head) owns the
-// logit gradients of its head; d_x needs both heads' gradients of the row (exchanged through shared memory), and the
-// weight gradients are per-thread column sums over the staged chunk.
-template <int KC>
-__global__ void __launch_bounds__(kHeadThreads)
-head_bwd_kernel(HeadArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    float* Wd = smem;
-    float* Ws = Wd + kMaxC * kD;
-    float* bd = Ws + kMaxC * kD;
-    float* bs = bd + kMaxC;
-    uint4* keep_s = reinterpret_cast<uint4*>(bs + kMaxC);
-    float* xm = reinterpret_cast<float*>(keep_s + kHeadRows);
-    float* dl = xm + kHeadRows * kXPitch;              // [row][0..15] dense logit grads, [16..31] softmax logit grads
-    __shared__ float sig_s[kHeadRows][kMaxC];          // sigmoid(dense) of the chunk (softmax branch needs s - weak)
-    const int tid = threadIdx.x, b = blockIdx.x;
-    load_head_weights(a, Wd, Ws, bd, bs);
-    uint64_t seed = a.seed; uint32_t step = a.step;
-    if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
-    const int r = tid & 127, head = tid >> 7;
-    // weight gradients: thread tid owns column k = tid & 127 of head (tid >> 7): 16 accumulators + bias slot
-    float gw[KC];
-#pragma unroll
-    for (int c = 0; c < KC; ++c) gw[c] = 0.f;
-    float gb = 0.f;
-    for (int t0 = 0; t0 < a.To; t0 += kHeadRows) {
-        const int n_rows = min(kHeadRows, a.To - t0);
-        __syncthreads();
-        stage_rows(a, b, t0, n_rows, seed, step, xm, keep_s);
-        __syncthreads();
-        float acc[KC], ar[KC];
-        const bool live = r < n_rows;
-        const long long row = (long long)b * a.To + t0 + r;
-        if (live) {
-            head_logits<KC>(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
-            if (head == 0) {
-#pragma unroll
-                for (int c = 0; c < KC; ++c) sig_s[r][c] = sigmoid_fast(acc[c]);
-            } else {
-                softmax_classes<KC>(acc, a.NC, ar);
-#pragma unroll
-                for (int c = 0; c < KC; ++c) dl[r * 2 * kMaxC + kMaxC + c] = ar[c];       // parked: head 0 needs `at`
-            }
-        }
-        __syncthreads();
-        if (live) {
-            if (head == 0) {
-#pragma unroll
-                for (int c = 0; c < KC; ++c) {
-                    float dld = 0.f;
-                    if (c < a.NC) {
-                        const float sg = sig_s[r][c];
-                        const float at = fminf(fmaxf(dl[r * 2 * kMaxC + kMaxC + c], 1e-7f), 1.f);
-                        const float dwk = __ldg(a.d_weak + b * a.NC + c);
-                        const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
-                        const float ds = __ldg(a.d_strong + row * a.NC + c) + dwk * at * inv_den;
-                        dld = ds * sg * (1.f - sg);
-                    }
-                    acc[c] = dld;
-                }
-            } else {
-                float da[KC];
-                float dot = 0.f;
-#pragma unroll
-                for (int c = 0; c < KC; ++c) {
-                    da[c] = 0.f;
-                    if (c < a.NC) {
-                        const float dwk = __ldg(a.d_weak + b * a.NC + c);
-                        const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
-                        const float wk = __ldg(a.weak + b * a.NC + c);
-                        const bool pass = ar[c] >= 1e-7f && ar[c] <= 1.f;   // clamp passes gradient inside [min, max]
-                        da[c] = pass ? dwk * (sig_s[r][c] - wk) * inv_den : 0.f;
-                        dot = fmaf(da[c], ar[c], dot);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < KC; ++c) acc[c] = c < a.NC ? ar[c] * (da[c] - dot) : 0.f;
-            }
-        }
-        __syncthreads();                               // every head-0 thread has read its `at` values
-#pragma unroll
-        for (int c = 0; c < KC; ++c) dl[r * 2 * kMaxC + head * kMaxC + c] = live ? acc[c] : 0.f;
-        __syncthreads();
-        // d x = mask * 2 * (Wd^T dl_d + Ws^T dl_s): thread (row, head) writes channels 64 head .. 64 head + 63
-        if (live) {
-            const uint4 kw4 = a.drop ? keep_s[r] : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            const float* dl_row = dl + r * 2 * kMaxC;
-            float4* dx = reinterpret_cast<float4*>(a.d_x + row * kD);
-#pragma unroll 2
-            for (int k4 = 16 * head; k4 < 16 * head + 16; ++k4) {
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int c = 0; c < KC; ++c) {
-                    const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
-                    const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
-                    const float gd = dl_row[c], gs = dl_row[kMaxC + c];
-                    o.x = fmaf(gd, wd.x, fmaf(gs, ws.x, o.x));
-                    o.y = fmaf(gd, wd.y, fmaf(gs, ws.y, o.y));
-                    o.z = fmaf(gd, wd.z, fmaf(gs, ws.z, o.z));
-                    o.w = fmaf(gd, wd.w, fmaf(gs, ws.w, o.w));
-                }
-                if (a.drop) {
-                    const uint32_t kw = k4 < 8 ? kw4.x : (k4 < 16 ? kw4.y : (k4 < 24 ? kw4.z : kw4.w));
-                    const uint32_t bits = kw >> ((4 * k4) & 31);
-                    o.x = (bits & 1u) ? 2.f * o.x : 0.f;
-                    o.y = (bits & 2u) ? 2.f * o.y : 0.f;
-                    o.z = (bits & 4u) ? 2.f * o.z : 0.f;
-                    o.w = (bits & 8u) ? 2.f * o.w : 0.f;
-                }
-                dx[k4] = o;
-            }
-        }
-        // weight gradients of the chunk: column k of head (tid >> 7)
-        {
-            const int k = tid & 127;
-            for (int q = 0; q < n_rows; ++q) {
-                const float xv = xm[q * kXPitch + k];
-                const float* dq = dl + q * 2 * kMaxC + head * kMaxC;
-#pragma unroll
-                for (int c = 0; c < KC; ++c) gw[c] = fmaf(dq[c], xv, gw[c]);
-            }
-            if (k < KC)
-                for (int q = 0; q < n_rows; ++q) gb += dl[q * 2 * kMaxC + head * kMaxC + k];
-        }
-    }
-    {
-        const int k = tid & 127;
-        float* g_w = head ? a.g_w_soft : a.g_w_dense;
-        float* g_b = head ? a.g_b_soft : a.g_b_dense;
-#pragma unroll
-        for (int c = 0; c < KC; ++c)
-            if (c < a.NC) atomicAdd(g_w + c * kD + k, gw[c]);
-        if (k < a.NC) atomicAdd(g_b + k, gb);
-    }
-}
-
 __device__ __forceinline__ float bce_term(float p, float y) {
     return -(y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(log1pf(-p), -100.f));
 }
 __device__ __forceinline__ float bce_grad(float p, float y) { return (p - y) / fmaxf((1.f - p) * p, 1e-12f); }
 
-// One CTA per clip (grid-stride over clips): element-wise gradients + per-CTA partial sums; the last CTA to
-// finish (atomic ticket) adds the partials in CTA order, so the meters do not depend on the schedule.
-__global__ void __launch_bounds__(256)
-mt_loss_kernel(LossArgs a) {
-    __shared__ float red[8][6];
-    __shared__ bool is_last;
+// One CTA (256 threads) per clip, grid-stride over clips: element-wise gradients + per-CTA partial sums; the last CTA to
+// finish (atomic ticket) adds the partials in CTA order, so the meters do not depend on the schedule.  A device function:
+// the stand-alone kernel below, or the first phase of head_bwd_kernel (HeadArgs::loss), whose CTA b then consumes the
+// gradients of clip b it has just written.
+__device__ __forceinline__ void mt_loss_body(const LossArgs& a, float (*red)[6], bool* is_last_p) {
     const int tid = threadIdx.x;
     const float cw = a.sc ? a.sc->cons_weight : a.cons_weight;
     const bool has_t = a.strong_t != nullptr;
@@ -379,9 +242,9 @@ mt_loss_kernel(LossArgs a) {
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    if (tid == 0) *is_last_p = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (!is_last) return;
+    if (!*is_last_p) return;
     __threadfence();
     if (tid < 32) {
         float s = 0.f;
@@ -400,6 +263,155 @@ mt_loss_kernel(LossArgs a) {
             a.meters[7] = cw;
             *a.ticket = 0u;                                  // ready for the next launch
         }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mt_loss_kernel(LossArgs a) {
+    __shared__ float red[8][6];
+    __shared__ bool is_last;
+    mt_loss_body(a, red, &is_last);
+}
+
+// Backward of the head for one clip per CTA; forward recomputed from the staged rows.  Thread (row, head) owns the
+// logit gradients of its head; d_x needs both heads' gradients of the row (exchanged through shared memory), and the
+// weight gradients are per-thread column sums over the staged chunk.
+template <int KC>
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_kernel(HeadArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* Wd = smem;
+    float* Ws = Wd + kMaxC * kD;
+    float* bd = Ws + kMaxC * kD;
+    float* bs = bd + kMaxC;
+    uint4* keep_s = reinterpret_cast<uint4*>(bs + kMaxC);
+    float* xm = reinterpret_cast<float*>(keep_s + kHeadRows);
+    float* dl = xm + kHeadRows * kXPitch;              // [row][0..15] dense logit grads, [16..31] softmax logit grads
+    __shared__ float sig_s[kHeadRows][kMaxC];          // sigmoid(dense) of the chunk (softmax branch needs s - weak)
+    const int tid = threadIdx.x, b = blockIdx.x;
+    if (a.fused_loss) {                                // the losses and d Loss / d outputs of clip b first (main.py:95-145)
+        __shared__ float loss_red[8][6];
+        __shared__ bool loss_last;
+        mt_loss_body(a.loss, loss_red, &loss_last);
+        __syncthreads();                               // d_strong / d_weak of clip b, written by this CTA, are visible to it
+    }
+    load_head_weights(a, Wd, Ws, bd, bs);
+    uint64_t seed = a.seed; uint32_t step = a.step;
+    if (a.sc) { seed = a.sc->seed; step = a.sc->step; }
+    const int r = tid & 127, head = tid >> 7;
+    // weight gradients: thread tid owns column k = tid & 127 of head (tid >> 7): 16 accumulators + bias slot
+    float gw[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) gw[c] = 0.f;
+    float gb = 0.f;
+    for (int t0 = 0; t0 < a.To; t0 += kHeadRows) {
+        const int n_rows = min(kHeadRows, a.To - t0);
+        __syncthreads();
+        stage_rows(a, b, t0, n_rows, seed, step, xm, keep_s);
+        __syncthreads();
+        float acc[KC], ar[KC];
+        const bool live = r < n_rows;
+        const long long row = (long long)b * a.To + t0 + r;
+        if (live) {
+            head_logits<KC>(xm + r * kXPitch, head ? Ws : Wd, head ? bs : bd, acc);
+            if (head == 0) {
+#pragma unroll
+                for (int c = 0; c < KC; ++c) sig_s[r][c] = sigmoid_fast(acc[c]);
+            } else {
+                softmax_classes<KC>(acc, a.NC, ar);
+#pragma unroll
+                for (int c = 0; c < KC; ++c) dl[r * 2 * kMaxC + kMaxC + c] = ar[c];       // parked: head 0 needs `at`
+            }
+        }
+        __syncthreads();
+        if (live) {
+            if (head == 0) {
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    float dld = 0.f;
+                    if (c < a.NC) {
+                        const float sg = sig_s[r][c];
+                        const float at = fminf(fmaxf(dl[r * 2 * kMaxC + kMaxC + c], 1e-7f), 1.f);
+                        const float dwk = a.d_weak[b * a.NC + c];
+                        const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
+                        const float ds = a.d_strong[row * a.NC + c] + dwk * at * inv_den;
+                        dld = ds * sg * (1.f - sg);
+                    }
+                    acc[c] = dld;
+                }
+            } else {
+                float da[KC];
+                float dot = 0.f;
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    da[c] = 0.f;
+                    if (c < a.NC) {
+                        const float dwk = a.d_weak[b * a.NC + c];
+                        const float inv_den = 1.f / __ldg(a.den + b * a.NC + c);
+                        const float wk = __ldg(a.weak + b * a.NC + c);
+                        const bool pass = ar[c] >= 1e-7f && ar[c] <= 1.f;   // clamp passes gradient inside [min, max]
+                        da[c] = pass ? dwk * (sig_s[r][c] - wk) * inv_den : 0.f;
+                        dot = fmaf(da[c], ar[c], dot);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < KC; ++c) acc[c] = c < a.NC ? ar[c] * (da[c] - dot) : 0.f;
+            }
+        }
+        __syncthreads();                               // every head-0 thread has read its `at` values
+#pragma unroll
+        for (int c = 0; c < KC; ++c) dl[r * 2 * kMaxC + head * kMaxC + c] = live ? acc[c] : 0.f;
+        __syncthreads();
+        // d x = mask * 2 * (Wd^T dl_d + Ws^T dl_s): thread (row, head) writes channels 64 head .. 64 head + 63
+        if (live) {
+            const uint4 kw4 = a.drop ? keep_s[r] : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            const float* dl_row = dl + r * 2 * kMaxC;
+            float4* dx = reinterpret_cast<float4*>(a.d_x + row * kD);
+#pragma unroll 2
+            for (int k4 = 16 * head; k4 < 16 * head + 16; ++k4) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    const float4 wd = *reinterpret_cast<const float4*>(Wd + c * kD + 4 * k4);
+                    const float4 ws = *reinterpret_cast<const float4*>(Ws + c * kD + 4 * k4);
+                    const float gd = dl_row[c], gs = dl_row[kMaxC + c];
+                    o.x = fmaf(gd, wd.x, fmaf(gs, ws.x, o.x));
+                    o.y = fmaf(gd, wd.y, fmaf(gs, ws.y, o.y));
+                    o.z = fmaf(gd, wd.z, fmaf(gs, ws.z, o.z));
+                    o.w = fmaf(gd, wd.w, fmaf(gs, ws.w, o.w));
+                }
+                if (a.drop) {
+                    const uint32_t kw = k4 < 8 ? kw4.x : (k4 < 16 ? kw4.y : (k4 < 24 ? kw4.z : kw4.w));
+                    const uint32_t bits = kw >> ((4 * k4) & 31);
+                    o.x = (bits & 1u) ? 2.f * o.x : 0.f;
+                    o.y = (bits & 2u) ? 2.f * o.y : 0.f;
+                    o.z = (bits & 4u) ? 2.f * o.z : 0.f;
+                    o.w = (bits & 8u) ? 2.f * o.w : 0.f;
+                }
+                dx[k4] = o;
+            }
+        }
+        // weight gradients of the chunk: column k of head (tid >> 7)
+        {
+            const int k = tid & 127;
+            for (int q = 0; q < n_rows; ++q) {
+                const float xv = xm[q * kXPitch + k];
+                const float* dq = dl + q * 2 * kMaxC + head * kMaxC;
+#pragma unroll
+                for (int c = 0; c < KC; ++c) gw[c] = fmaf(dq[c], xv, gw[c]);
+            }
+            if (k < KC)
+                for (int q = 0; q < n_rows; ++q) gb += dl[q * 2 * kMaxC + head * kMaxC + k];
+        }
+    }
+    {
+        const int k = tid & 127;
+        float* g_w = head ? a.g_w_soft : a.g_w_dense;
+        float* g_b = head ? a.g_b_soft : a.g_b_dense;
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            if (c < a.NC) atomicAdd(g_w + c * kD + k, gw[c]);
+        if (k < a.NC) atomicAdd(g_b + k, gb);
     }
 }
 

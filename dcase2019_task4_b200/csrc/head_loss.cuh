@@ -3,6 +3,24 @@
 #include <cuda_runtime.h>
 #include "common.cuh"
 
+struct LossArgs {
+    const float* strong_s;
+    const float* weak_s;
+    const float* strong_t;   // nullable: no teacher (main_simple_CRNN.py)
+    const float* weak_t;
+    const float* target;     // [B][To][NC]
+    int B, To, NC;
+    int weak_lo, weak_hi;    // weak_mask = slice(weak_lo, weak_hi); empty = None
+    int strong_lo, strong_hi;
+    float cons_weight;
+    const DcaseStepScalars* sc;
+    float* meters;           // [8]
+    float* partials;         // [kLossMaxCtas][8] per-CTA partial sums (context scratch)
+    unsigned int* ticket;    // completion counter (context scratch, zero between launches)
+    float* d_strong;
+    float* d_weak;
+};
+
 struct HeadArgs {
     const float* x;          // [B*To][128] BiGRU output
     const float* w_dense;    // [NC][128]
@@ -26,24 +44,10 @@ struct HeadArgs {
     float* g_b_dense;
     float* g_w_soft;
     float* g_b_soft;
-};
-
-struct LossArgs {
-    const float* strong_s;
-    const float* weak_s;
-    const float* strong_t;   // nullable: no teacher (main_simple_CRNN.py)
-    const float* weak_t;
-    const float* target;     // [B][To][NC]
-    int B, To, NC;
-    int weak_lo, weak_hi;    // weak_mask = slice(weak_lo, weak_hi); empty = None
-    int strong_lo, strong_hi;
-    float cons_weight;
-    const DcaseStepScalars* sc;
-    float* meters;           // [8]
-    float* partials;         // [kLossMaxCtas][8] per-CTA partial sums (context scratch)
-    unsigned int* ticket;    // completion counter (context scratch, zero between launches)
-    float* d_strong;
-    float* d_weak;
+    // backward, optional: the loss kernel's work as the first phase of head_bwd (grid = B <= kLossMaxCtas CTAs; CTA b then
+    // consumes the gradients of clip b it has just written: d_strong / d_weak above must equal loss.d_strong / loss.d_weak)
+    int fused_loss;
+    LossArgs loss;
 };
 
 constexpr int kLossMaxCtas = 1024;

@@ -220,6 +220,50 @@ def test_full_size_eval_and_train_step_properties(K, cuda_device):
     assert not torch.equal(a1, a3)
 
 
+def test_cnn0_input_moments_match_numpy_and_feed_the_same_forward(K, cuda_device):
+    """``dcase_cnn0_input_moments``: the 9 tap sums + 45 second moments of the zero-padded 3 x 3 neighbourhoods of x, the
+    only thing block 0's BatchNorm batch statistics (models/CNN.py:49) need from the data; a forward that is handed them
+    (``dcase_mt_args.mom_s``, the pipelined engine) must equal one that computes them itself."""
+    B, T = 3, 72
+    x = _inputs(B, T, 5)
+    mom = K.cnn0_input_moments(x.to(cuda_device)).cpu().numpy()
+    xp = np.pad(x[:, 0].double().numpy(), ((0, 0), (1, 1), (1, 1)))
+    taps = np.stack([xp[:, dy:dy + T, dx:dx + 64] for dy in range(3) for dx in range(3)], axis=-1).reshape(-1, 9)
+    want = list(taps.sum(0))
+    for k in range(9):
+        for l in range(k, 9):
+            want.append(float((taps[:, k] * taps[:, l]).sum()))
+    want = np.asarray(want)
+    err = np.abs(mom[:54] - want).max() / np.abs(want).max()
+    print(f"tap moments: max rel err {err:.2e}")
+    assert err <= 1e-5                              # fp32 partial sums per thread, fp64 from the block level on
+    # the engine's two routes through block 0 (moments inside the forward / handed in) give the same step
+    import dcase2019_task4_b200.config as cfg
+    from dcase2019_task4_b200 import main as bmain
+    from dcase2019_task4_b200.models.CRNN import CRNN
+    outs = []
+    for handed in (False, True):
+        torch.manual_seed(3)
+        m, t = CRNN(**cfg.crnn_kwargs), CRNN(**cfg.crnn_kwargs)
+        for p_ in t.parameters():
+            p_.detach_()
+        m, t = m.train().cuda(), t.train().cuda()
+        m._rng_seed, m._rng_step = 77, 0
+        opt = torch.optim.Adam(m.parameters(), lr=0.001, betas=(0.9, 0.999))
+        eng = bmain.MeanTeacherEngine(m, opt, t, slice(1), slice(2, 3), B, T, use_graph=False)
+        xs, xt = x[:, 0].to(cuda_device).contiguous(), (x[:, 0] * 0.9 + 0.05).to(cuda_device).contiguous()
+        tgt = (torch.rand(B, T // 8, 10, generator=torch.Generator().manual_seed(1)) < 0.2).float().to(cuda_device)
+        tgt[1] = -1
+        if handed:
+            eng._step_moms = torch.stack([K.cnn0_input_moments(xs), K.cnn0_input_moments(xt)])
+        eng.step(xs, xt, tgt, 0.5, 1, check=False)
+        eng._step_moms = None
+        torch.cuda.synchronize()
+        outs.append((eng.strong_s.clone(), eng.weak_s.clone(), m.flat_bn_running().clone(), t.flat_bn_running().clone()))
+    for a, b in zip(*outs):
+        assert H.maxerr(a.cpu(), b.cpu()) <= 2e-6   # forward quantities only (the fp64 atomics of the moments land in a different order)
+
+
 def test_sequence_longer_than_the_resident_gru_fails_loudly(K, cuda_device):
     """The GRU kernels keep a sequence's operands in shared memory (T/8 <= 136 output frames, DESIGN.md section 4);
     a longer input must raise, not silently fall back."""
