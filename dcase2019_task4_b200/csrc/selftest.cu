@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "ctx.h"
 #include "tc.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -13,6 +14,10 @@ namespace {
 //         tensor memory (tc::umma_tf32_tmem_a_elect), both GEMMs issued back to back by one warp
 // mode 3: the same, followed by a third GEMM that overwrites (doubles) the first accumulator once the chained GEMM has
 //         COMPLETED, the order cnn0 uses for the next tile's conv
+// mode 4: D[m][j] = sum_p [A | B][p][m] * A[p][j], m < 128, j < 16, p < 128 with bf16 operands (kind::f16), both MN-major in
+//         the 16-bit SWIZZLE_128B layout: rows = K index p, a 128-byte row = 64 consecutive M / N elements, 16-byte chunk c of
+//         row p at chunk c ^ (p & 7); the two 64-wide M blocks are LBO = 16 KB apart, 8-row K groups SBO = 1 KB apart, one
+//         instruction consumes K = 16 rows (2 KB).  The layout cnn0's backward accumulates its parameter gradients with.
 __global__ void __launch_bounds__(128)
 umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
     extern __shared__ unsigned char smem_raw[];
@@ -23,6 +28,52 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int b_rows = mode == 1 ? 128 : 64;
+    if (mode == 4) {
+        __shared__ uint64_t bar4;
+        // A operand: block 0 = A[p][0..63], block 1 = B[p][0..63]; B operand: A[p][0..15] in the first 32 bytes of its row
+        unsigned char* e_s = smem + 32768;
+        for (int blk = 0; blk < 2; ++blk) {
+            const float* src = (blk ? B : A) + tid * 64;
+            for (int c = 0; c < 8; ++c) {
+                __nv_bfloat162 h[4];
+                for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(src[8 * c + 2 * e], src[8 * c + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(a_s + blk * 16384 + tc::sw128_chunk(tid, c)) = *reinterpret_cast<uint4*>(h);
+            }
+        }
+        for (int c = 0; c < 8; ++c) {
+            __nv_bfloat162 h[4];
+            for (int e = 0; e < 4; ++e)
+                h[e] = c < 2 ? __floats2bfloat162_rn(A[tid * 64 + 8 * c + 2 * e], A[tid * 64 + 8 * c + 2 * e + 1]) : __floats2bfloat162_rn(0.f, 0.f);
+            *reinterpret_cast<uint4*>(e_s + tc::sw128_chunk(tid, c)) = *reinterpret_cast<uint4*>(h);
+        }
+        if (tid == 0) { tc::mbar_init(&bar4, 1); tc::fence_mbar_init(); }
+        if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
+        tc::fence_proxy_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        const uint32_t tm = tmem_base_s;
+        const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+        if (warp_u == 0) {
+            constexpr uint32_t idesc = tc::idesc_bf16(128, 16, 1, 1);
+            const uint32_t a_lo = tc::desc_lo(tc::smem_u32(a_s), 16384), e_lo = tc::desc_lo(tc::smem_u32(e_s), 16384);
+            const uint32_t hi = tc::desc_hi(1024, 2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                tc::umma_f16_elect(tm, a_lo + (j * 2048 >> 4), hi, e_lo + (j * 2048 >> 4), hi, idesc, j > 0 ? 1u : 0u);
+            tc::umma_commit_elect(&bar4);
+        }
+        tc::mbar_wait(&bar4, 0);
+        tc::fence_after_sync();
+        float v[16];
+        tc::tmem_ld16(tm + ((uint32_t)(warp * 32) << 16), v);
+        tc::tmem_ld_wait();
+        for (int c = 0; c < 64; ++c) D[tid * 64 + c] = c < 16 ? v[c] : 0.f;
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc(tm, 128);
+        return;
+    }
     // fill operands (thread = row)
     for (int c = 0; c < 16; ++c) {
         const float4 v = *reinterpret_cast<const float4*>(A + tid * 64 + 4 * c);
@@ -101,7 +152,7 @@ umma_selftest_kernel(int mode, const float* __restrict__ A, const float* __restr
 
 extern "C" int dcase_selftest_umma(dcase_ctx* ctx, int mode, const float* A, const float* B, float* D, void* stream) {
     DCASE_REQUIRE(ctx && A && B && D, "null argument");
-    DCASE_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 .. 3");
+    DCASE_REQUIRE(mode >= 0 && mode <= 4, "mode must be 0 .. 4");
     static bool attr_set = false;
     if (!attr_set) {
         DCASE_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66560));

@@ -132,6 +132,11 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, i
            ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with bf16 operands (a_format = b_format = 1)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+    return idesc_f16(M, N, a_mn_major, b_mn_major) | (1u << 7) | (1u << 10);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

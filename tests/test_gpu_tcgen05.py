@@ -94,3 +94,17 @@ def test_umma_a_operand_from_tensor_memory(cuda_device, mode):
     err = float((D.double() - ref).abs().max())
     print(f"TMEM-A chained GEMM: err vs tf32-truncated ref {err:.3e} (max |ref| {float(ref.abs().max()):.3e})")
     assert err <= 2e-3 * float(ref.abs().max())
+
+
+def test_umma_bf16_mnmajor_m128_n16(cuda_device):
+    """kind::f16 with bf16 operands, both MN-major in the 16-bit SWIZZLE_128B layout, M = 128 as two 64-wide blocks (LBO),
+    N = 16, K = 128 in eight K = 16 instructions: the accumulating GEMM of cnn0's backward."""
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(128, 64, generator=g).to(cuda_device)
+    B = torch.randn(128, 64, generator=g).to(cuda_device)
+    raw = _run(4, A, B)[:, :16]                                     # [128 lanes = m][16 columns = j]
+    Ab, Bb = A.bfloat16().double(), B.bfloat16().double()
+    ref = torch.cat([Ab, Bb], 1).t() @ Ab[:, :16]                   # [128 m][16 j]
+    err = float((raw.double() - ref).abs().max())
+    print(f"bf16 MN-major M=128 N=16: err vs bf16-rounded ref {err:.3e} (max |ref| {float(ref.abs().max()):.3e})")
+    assert err <= 1e-4 * float(ref.abs().max())                     # exact products, fp32 accumulation
