@@ -56,11 +56,13 @@ def kernel_flops_per_launch(name, B):
     L = LAYER_FLOPS_PER_CLIP
     table = {
         "cnn0_fused_fwd": L["conv0"] + L["glu0"],
-        "cnn0_fused_bwd": L["conv0"] + 3 * L["glu0"] + L["conv0"],   # recompute + dgate GEMM + GLU wgrad + conv wgrad
+        # backward kernels: 2 x the forward FLOPs of what they differentiate ("student bwd (2x)"); the forward
+        # that cnn0_bwd and glu_pool_bwd RECOMPUTE is not algorithmic work and is not counted
+        "cnn0_fused_bwd": 2 * (L["conv0"] + L["glu0"]),
         "conv3x3_fwd_l1": L["conv1"], "conv3x3_dgrad_l1": L["conv1"], "conv3x3_wgrad_l1": L["conv1"],
         "conv3x3_fwd_l2": L["conv2"], "conv3x3_dgrad_l2": L["conv2"], "conv3x3_wgrad_l2": L["conv2"],
-        "glu_pool_fwd_l1": L["glu1"], "glu_pool_bwd_l1": 3 * L["glu1"],
-        "glu_pool_fwd_l2": L["glu2"], "glu_pool_bwd_l2": 3 * L["glu2"],
+        "glu_pool_fwd_l1": L["glu1"], "glu_pool_bwd_l1": 2 * L["glu1"],
+        "glu_pool_fwd_l2": L["glu2"], "glu_pool_bwd_l2": 2 * L["glu2"],
     }
     return table.get(name, 0.0) * B
 
