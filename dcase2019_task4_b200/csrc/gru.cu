@@ -253,7 +253,7 @@ gru_fwd_kernel(GruFwdArgs a) {
         const float r = sigmoid_ftz(gi_r + gh_r), z = sigmoid_ftz(gi_z + gh_z);
         const float n = tanh_ftz(fmaf(r, ghn, gi_n));
         const float hn = fmaf(z, h_own - n, n);          // (1 - z) n + z h
-        sts32(h_nxt, hn);                                // all four lanes of the quad write the same value
+        if (q == 0) sts32(h_nxt, hn);                    // every lane of the quad holds the same value: one writes (racecheck-clean)
         const float va = fmaf(ma0, hn, fmaf(ma1, z, fmaf(ma2, ghn, ma3 * h_own)));
         const float vb = q == 0 ? r : n;
         if (store_a) pa[off_a] = va;
@@ -302,8 +302,7 @@ gru_bwd_kernel(GruBwdArgs a) {
     const int t_first = dir ? 0 : T - 1;
     const int row0 = b * T + t_first;
     // outputs of lane q: q0 -> dgi[i], dgh[i] = drp; q1 -> dgi[H+i], dgh[H+i] = dzp; q2 -> dgh[2H+i] = dghn;
-    // q3 -> dgi[2H+i] = dn.  Lanes 0..2 also publish their value in dgs for the W_hh^T product (lane 3 writes a
-    // spare slot).
+    // q3 -> dgi[2H+i] = dn.  Lanes 0..2 also publish their value in dgs for the W_hh^T product.
     const int jg = q == 3 ? 2 * H + i : q * H + i;             // gate row written by this lane
     int off_g = (dir * BT + row0) * 3 * H + jg;
     const int inc_g = dstep * 3 * H;
@@ -330,7 +329,7 @@ gru_bwd_kernel(GruBwdArgs a) {
         const float v = fmaf(m0, drp, fmaf(m1, dzp, fmaf(m2, dghn, m3 * dn)));
         if (q != 2) dgi_p[off_g] = v;
         if (q != 3) dgh_p[off_g] = v;
-        sts32(dg_w + which, v);
+        if (q != 3) sts32(dg_w + which, v);          // lane 3's value (dn) is not part of dgh
         off_g += inc_g;
         __syncthreads();
         u64 s0 = 0ull, s1 = 0ull;
