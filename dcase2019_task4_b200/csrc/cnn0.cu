@@ -313,7 +313,8 @@ __device__ __forceinline__ uint32_t zrow_base(uint32_t region, int p) { return r
 __device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scale, float* __restrict__ out_tile,
                                           uint2* __restrict__ out_tile_h) {
     const int w = tid >> 4, c4 = tid & 15;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint64_t acc01 = pk(0.f, 0.f), acc23 = acc01;     // packed fp32 sums (FADD2: half the adds)
+    const uint64_t one2 = pk(1.f, 1.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int p = 4 * w + j;                      // frame 0; frame 1 is 64 rows = 8192 bytes further (same p & 7)
@@ -323,9 +324,13 @@ __device__ __forceinline__ void pool_tile(uint32_t z_region, int tid, float scal
             uint32_t v0, v1;
             asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(addr + tr * 8192) : "memory");
             const float2 a = unpack_half2(v0), b = unpack_half2(v1);
-            acc.x += a.x; acc.y += a.y; acc.z += b.x; acc.w += b.y;
+            acc01 = fma2(pk(a.x, a.y), one2, acc01);
+            acc23 = fma2(pk(b.x, b.y), one2, acc23);
         }
     }
+    float4 acc;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(acc01));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(acc23));
     const float4 o = make_float4(scale * acc.x, scale * acc.y, scale * acc.z, scale * acc.w);
     if (out_tile)                                          // operand of the weight-gradient MMAs: rounded to tf32
         *reinterpret_cast<float4*>(out_tile + w * 64 + 4 * c4) =
