@@ -232,6 +232,57 @@ def test_segment_based_metric_and_empty_files():
     assert em.get_event_list_current_file(ref, "b.wav") == []
 
 
+def _random_event_files(draw_rng, n_files, labels):
+    files = []
+    for _ in range(n_files):
+        ref, est = [], []
+        for _ in range(draw_rng.integers(0, 6)):
+            on = float(np.round(draw_rng.uniform(0, 8), 2))
+            ref.append((labels[draw_rng.integers(len(labels))], on, on + float(np.round(draw_rng.uniform(0.1, 4), 2))))
+        for lab, on, off in ref:                                   # system events: jittered copies, misses, extras
+            u = draw_rng.uniform()
+            if u < 0.7:
+                est.append((lab, max(0.0, on + float(np.round(draw_rng.normal(0, 0.15), 2))),      # onsets are frame times: >= 0
+                            off + float(np.round(draw_rng.normal(0, 0.4), 2))))
+            if u > 0.85:
+                est.append((lab, on + 0.05, off - 0.05))               # a second candidate for the same reference event
+        for _ in range(draw_rng.integers(0, 3)):
+            on = float(np.round(draw_rng.uniform(0, 8), 2))
+            est.append((labels[draw_rng.integers(len(labels))], on, on + float(np.round(draw_rng.uniform(0.1, 3), 2))))
+        files.append((ref, [(l, a, max(b, a + 0.01)) for l, a, b in est]))
+    return files
+
+
+def test_event_and_segment_metrics_match_the_bruteforce_oracle_on_random_event_lists():
+    """evaluation_measures.py:124-182 through an independent restatement of sed_eval's published algorithm
+    (oracle/sed_metrics.py: exhaustive optimal matching, explicit segment loops): 300 random multi-file cases."""
+    from dcase2019_task4_b200 import evaluation_measures as em
+    from oracle import sed_metrics as osed
+    rng = np.random.default_rng(20191)
+    labels = ["Dog", "Speech", "Cat"]
+    for case in range(300):
+        files = _random_event_files(rng, int(rng.integers(1, 4)), labels)
+        rows_r, rows_e = [], []
+        for i, (ref, est) in enumerate(files):
+            name = "f%d.wav" % i
+            rows_r += [[name, l, a, b] for l, a, b in ref] or [[name, np.nan, np.nan, np.nan]]   # tsv convention: no event
+            rows_e += [[name, l, a, b] for l, a, b in est]
+        ref_df = _events(rows_r)
+        est_df = _events(rows_e) if rows_e else _events([["none.wav", np.nan, np.nan, np.nan]])
+        used = sorted({l for ref, est in files for l, _, _ in list(ref) + list(est)})
+        got_e = em.event_based_evaluation_df(ref_df, est_df).results()
+        got_s = em.segment_based_evaluation_df(ref_df, est_df, time_resolution=1.0).results()
+        want_e, want_s = osed.event_based(files, used), osed.segment_based(files, used)
+        for got, want in ((got_e, want_e), (got_s, want_s)):
+            assert got["overall"]["count"] == want["overall"]["count"], (case, got["overall"], want["overall"])
+            for l in used:
+                assert got["class_wise"][l]["count"] == want["class_wise"][l]["count"], (case, l)
+            for k in ("f_measure", "precision", "recall"):
+                assert abs(got["overall"]["f_measure"][k] - want["overall"]["f_measure"][k]) < 1e-12
+                if used:
+                    assert abs(got["class_wise_average"]["f_measure"][k] - want["class_wise_average"]["f_measure"][k]) < 1e-12
+
+
 def test_checkpoint_dict_matches_reference_layout(tmp_path):
     """main.py:293-309 / :335-356 / TestModel.py:26-40: same keys, nested model state dicts, loadable on CPU."""
     from dcase2019_task4_b200 import main as bmain
