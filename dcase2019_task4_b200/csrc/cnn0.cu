@@ -42,7 +42,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 //     accumulator at the end of the backward (DL and D2 only feed that linear reduction).
 //   DCASE_GATE_TANH (default): ys = y / 2, a = tanh.approx(ys);  otherwise ys = -log2(e) y, a = 2 rcp(1 + ex2(ys)) - 1.
 // tanh.approx.f32 has a relative error of up to 2^-11 (|dg| <= 2.4e-4); measured effect on the frame posteriors:
-// tests/test_gpu_fullsize.py prints it, tools/precision_modes.py models it.
+// tests/test_gpu_fullsize.py prints it, tests/scripts/precision_modes.py models it.
 #ifndef DCASE_GATE_TANH
 #define DCASE_GATE_TANH 1
 #endif
