@@ -532,7 +532,11 @@ glu_pool_bwd_tma_kernel(const __grid_constant__ CUtensorMap in_k_map, const __gr
             tc::fence_proxy_async();
             mbar_arrive(dy_ready);
         }
-        // ---- read-out: affine fix-ups of the reductions over v, then atomics ----
+        // ---- read-out: affine fix-ups of the reductions over v, staged in shared memory (the operand tiles are dead), then
+        //      COALESCED 16-byte reductions: a warp instruction adds four full 128-byte lines.  148 CTAs add into the same
+        //      4,288 floats: as scalar atomics from threads that own a row each (stride 256 B) every line received ~4,700
+        //      serialised transactions and the tail cost more than the kernel's tile loop (round 2, measured).
+        float* outs = reinterpret_cast<float*>(smem + kBQ2);      // [64][64] dWg | [64] db_g | [64] sum dY | [64] sum dY xhat (Q2: read by G3 only)
         if (any && warp < 4) {
             BWAIT(g45_done, (it - 1) & 1, 10);                // last commit: every MMA of the CTA has completed
             tc::fence_after_sync();
@@ -543,7 +547,7 @@ glu_pool_bwd_tma_kernel(const __grid_constant__ CUtensorMap in_k_map, const __gr
             tc::tmem_ld16(tmem + 192 + lane_base, v);             // D3 columns 64..79: col 64 = sum_p DL[p][n]
             tc::tmem_ld_wait();
             const float dbg = kTruncComp * v[0];
-            if (own) atomicAdd(a.g_glu_b + m, dbg);
+            if (own) outs[4096 + m] = dbg;
 #pragma unroll 1
             for (int j0 = 0; j0 < 64; j0 += 16) {                 // dWg[n][k] = a_k (DL^T v)[n][k] + s_k db_g[n]
                 tc::tmem_ld16(tmem + 128 + j0 + lane_base, v);
@@ -551,7 +555,7 @@ glu_pool_bwd_tma_kernel(const __grid_constant__ CUtensorMap in_k_map, const __gr
                 if (own) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        atomicAdd(a.g_glu_w + m * 64 + j0 + j, fmaf(__ldg(a.bn + kBnScale + j0 + j), c2 * v[j], __ldg(a.bn + kBnShift + j0 + j) * dbg));
+                        outs[m * 64 + j0 + j] = fmaf(__ldg(a.bn + kBnScale + j0 + j), c2 * v[j], __ldg(a.bn + kBnShift + j0 + j) * dbg);
                 }
             }
             tc::tmem_ld16(tmem + 208 + lane_base, v);
@@ -566,10 +570,19 @@ glu_pool_bwd_tma_kernel(const __grid_constant__ CUtensorMap in_k_map, const __gr
                 for (int j = 0; j < 16; ++j) diag = (j0 + j == m) ? v[j] : diag;
             }
             if (own) {
-                atomicAdd(a.s12 + m, s1);
+                outs[4160 + m] = s1;
                 // sum dY xhat, xhat = (v - mean) invstd
-                atomicAdd(a.s12 + 64 + m, (c2 * diag - __ldg(a.bn + kBnMean + m) * s1) * __ldg(a.bn + kBnInvstd + m));
+                outs[4224 + m] = (c2 * diag - __ldg(a.bn + kBnMean + m) * s1) * __ldg(a.bn + kBnInvstd + m);
             }
+            tc::fence_before_sync();
+            bar_sync_named(2, 128);                               // warps 0..3: the staged results are complete
+            auto red4 = [](float* dst, const float* src) {
+                const float4 x = *reinterpret_cast<const float4*>(src);
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+            };
+            for (int i = tid; i < 1024; i += 128) red4(a.g_glu_w + 4 * i, outs + 4 * i);
+            if (tid < 16) red4(a.g_glu_b + 4 * tid, outs + 4096 + 4 * tid);
+            else if (tid < 48) red4(a.s12 + 4 * (tid - 16), outs + 4160 + 4 * (tid - 16));
         }
     }
     tc::fence_before_sync();
