@@ -132,6 +132,7 @@ WsLayout ws_layout(int B, int T, int NC) {
     const size_t n0 = (size_t)B * (T / 2) * 16 * 64;   // out0 / ypre1 elements
     const size_t n1 = (size_t)B * (T / 4) * 4 * 64;    // out1 / ypre2
     add("mom0", 56, sizeof(double));        // 54 tap moments + completion ticket of the moments kernel
+    add("tile_ctr", 16);                    // tile counters of the dynamically scheduled block-0 kernels
     add("stats1", 128, sizeof(double));
     add("stats2", 128, sizeof(double));
     add("fold0", kFold0Size);
@@ -381,7 +382,7 @@ static int crnn_forward_impl(dcase_ctx* ctx, const float* x, int B, int T, int N
     const bool keep_f32 = model_id == 0;
     float* out0 = wsp<float>(ws, L, "out0");
     DCASE_TRY(launch_cnn0_fwd(x, B, T, fold0, params + o.glu_w[0], params + o.glu_b[0], drop(0), keep_f32 ? out0 : nullptr,
-                              wsp<void>(ws, L, "out0_h"), sms, s));
+                              wsp<void>(ws, L, "out0_h"), wsp<unsigned int>(ws, L, "tile_ctr"), sms, s));
 
     // ---- CNN blocks 1, 2 ----
     const char* names[3][7] = {{}, {"wprep1_h", "wprep1_d", "ypre1", "stats1", "bn1", "out1", "gluimg1"},

@@ -38,7 +38,8 @@ int launch_bn0_finalize(const double* mom, long long n_pix, const float* conv_w,
 // out (fp32, tf32-rounded: operand of the backward's weight-gradient MMAs) and out_h (fp16: operand of the next block's
 // forward conv) are both optional
 int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                    DropoutCfg drop, float* out, void* out_h, int num_sms, cudaStream_t s);
+                    DropoutCfg drop, float* out, void* out_h, unsigned int* tile_ctr /*4 bytes of scratch*/, int num_sms,
+                    cudaStream_t s);
 constexpr int kCnn0AccFloats = 128 * 16;   // {U[64][16], S2[64][16]}, zeroed before launch_cnn0_bwd
 // what turns block 0's {U | S2} accumulator into its parameter gradients (n_pix = pixels behind the statistics; the
 // gradients are written x param_grad_scale, see launch_bn_bwd_apply)

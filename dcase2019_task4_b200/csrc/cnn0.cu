@@ -75,6 +75,7 @@ struct Cnn0Args {
     DropoutCfg drop;
     float* out;            // fwd: [B][T/2][16][64], nullable
     void* out_h;           // fwd: the same as fp16 (operand of conv1's forward), nullable
+    unsigned int* tile_ctr; // fwd: tile counter of the dynamic schedule (zeroed by the launcher)
     const float* d_out;    // bwd: grad of out
     float* us;             // bwd: [128][16] accumulators {U[64][16], S2[64][16]} (zeroed by the caller; us[10] = CTA ticket)
     Cnn0FinArgs fin;       // bwd: the finalize pass, run by the last CTA to finish
@@ -292,7 +293,7 @@ __device__ __forceinline__ void require_aligned_smem(const void* p) {
 //                                     xs[4][66] | keep_lo[128] | 2 mbarriers | tmem base
 // TMEM (128 columns, 4 CTAs = all 512): [0,64) y (the next tile's y from barrier A on), [64,128) u = (lin + b) / 2
 constexpr int kFwdWb = 0, kFwdT0 = 16384, kFwdA = 32768, kFwdMisc = 49152;
-constexpr int kFwdSmemBytes = kFwdMisc + 4 * 66 * 4 + 128 * 4 + 2 * 8 + 8;
+constexpr int kFwdSmemBytes = kFwdMisc + 4 * 66 * 4 + 128 * 4 + 2 * 8 + 8 + 16;
 constexpr int kFwdThreads = 256;
 constexpr int kFwdCtasPerSm = 4;
 
@@ -349,6 +350,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
     uint32_t* keep_lo = reinterpret_cast<uint32_t*>(xs + 4 * 66);
     uint64_t* bars = reinterpret_cast<uint64_t*>(keep_lo + 128);     // [0] MMA0, [1] MMA1
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2);
+    int* tq = reinterpret_cast<int*>(tmem_base_s + 1);               // [3] tile indices claimed by thread 0 (dynamic schedule)
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
     const int row = tid & 127, half = tid >> 7;
@@ -360,9 +362,18 @@ cnn0_fwd_kernel(Cnn0Args a) {
     if (warp == 0) tc::tmem_alloc(tmem_base_s, 128);
     uint64_t seed = a.drop.seed; uint32_t step = a.drop.step;
     if (a.drop.sc) { seed = a.drop.sc->seed; step = a.drop.sc->step; }
-    const long long n_tiles = (long long)a.B * a.T / 2;
-    const long long stride = gridDim.x;
-    long long cur = blockIdx.x;
+    // Tiles are handed out DYNAMICALLY: a CTA's first tile is its block index, every further one comes from a global
+    // counter.  The block scheduler needs ~16 us to start the grid's 592 CTAs (globaltimer: the fourth CTA of an SM starts
+    // 11-16 us after the first) and the other model's kernels free SMs at their own pace, so with a static split the CTAs
+    // that started last set the kernel's duration while the early ones had finished 30 us before.  The pipeline looks two
+    // tiles ahead (operand rows of `nxt`, prefetched x rows of `nxt2`), so thread 0 claims the tile after those at the top of
+    // every iteration and publishes it through shared memory before barrier A.
+    const int n_tiles = (int)((long long)a.B * a.T / 2);
+    int cur = blockIdx.x, nxt, nxt2;
+    if (tid == 0) {
+        tq[0] = (int)gridDim.x + (int)atomicAdd(a.tile_ctr, 1u);
+        tq[1] = (int)gridDim.x + (int)atomicAdd(a.tile_ctr, 1u);
+    }
     const uint32_t wb_a = tc::smem_u32(Wb), t0_a = tc::smem_u32(T0), a_a = tc::smem_u32(smem + kFwdA);
     const uint32_t t0_rb = krow_base(t0_a, row), z_rb = zrow_base(a_a, row);
     const bool drop = a.drop.enabled != 0;
@@ -372,20 +383,21 @@ cnn0_fwd_kernel(Cnn0Args a) {
     // prologue: operand rows of the first tile and its MMA0; x rows of the second tile in shared memory, of the third in
     // registers
     uint32_t keep_next = 0xffffffffu;       // keep bits (this thread's 32 channels) of the tile whose MMA0 is in flight
-    TilePos pos;                            // position of the tile whose x rows are fetched next
+    TilePos pos;                            // position of the tile whose x rows are fetched
     pos.init(cur, a.T);
-    const int pos_step = (int)(2 * stride);
     {
         XsRegs x0 = xs_prefetch(a.x, pos, a.T, tid);
         xs_commit(x0, xs, tid);
     }
-    pos.advance(pos_step, a.T);
-    XsRegs xr = cur + stride < n_tiles ? xs_prefetch(a.x, pos, a.T, tid) : XsRegs{0.f, 0.f};
     __syncthreads();
     const uint32_t tmem = *tmem_base_s;
+    nxt = tq[0];
+    nxt2 = tq[1];
+    XsRegs xr{0.f, 0.f};
+    if (nxt < n_tiles) { pos.init(nxt, a.T); xr = xs_prefetch(a.x, pos, a.T, tid); }
     if (half == 0) write_taps(xs, row, t0_rb);
     else if (drop) {
-        const uint4 r = philox4x32_10((uint64_t)(cur * kTile + row), a.drop.stream, step, seed);
+        const uint4 r = philox4x32_10((uint64_t)((long long)cur * kTile + row), a.drop.stream, step, seed);
         keep_lo[row] = r.x;
         keep_next = r.y;
     }
@@ -396,13 +408,12 @@ cnn0_fwd_kernel(Cnn0Args a) {
     if (warp == 0) { issue_mma0(tmem, t0_a); tc::umma_commit_elect(&bars[0]); }
     if (drop && half == 0) keep_next = keep_lo[row];
     xs_commit(xr, xs, tid);                 // the second tile's rows (the first tile's have been consumed)
-    pos.advance(pos_step, a.T);
     __syncthreads();
 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph0 = 0, ph1 = 0;
     const float pool_scale = drop ? 0.25f : 0.125f;      // 1/8 window, x2 inverted dropout
-    long long prev = -1;
+    int prev = -1;
 
 #ifdef DCASE_CNN0_TIMING
     long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tt;
@@ -414,8 +425,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
 #define TICK()
 #define TOCK(i)
 #endif
-    for (; cur < n_tiles; cur += stride) {
-        const long long nxt = cur + stride;
+    while (cur < n_tiles) {
         const bool has_next = nxt < n_tiles;
         const uint32_t keep = keep_next;
         TICK();
@@ -426,21 +436,21 @@ cnn0_fwd_kernel(Cnn0Args a) {
             issue_mma1_tmem(tmem + 64, tmem, wb_a, t0_a);      // every thread before barrier C of the previous tile
             tc::umma_commit_elect(&bars[1]);
         }
+        if (tid == 0) tq[2] = nxt2 < n_tiles ? (int)gridDim.x + (int)atomicAdd(a.tile_ctr, 1u) : n_tiles;   // the tile after `nxt2`
         TOCK(0);
         TICK();
-        if (prev >= 0) pool_tile(a_a, tid, pool_scale, out_f ? out_f + prev * 16 * 64 : nullptr, out_h ? out_h + prev * 16 * 16 : nullptr);     // z of `prev`: complete since barrier C
+        if (prev >= 0) pool_tile(a_a, tid, pool_scale, out_f ? out_f + (long long)prev * 16 * 64 : nullptr, out_h ? out_h + (long long)prev * 16 * 16 : nullptr);     // z of `prev`: complete since barrier C
         TOCK(1);
         TICK();
         uint32_t keep_hi_next = 0xffffffffu;
         if (has_next) {
             if (half == 0) write_taps(xs, row, t0_rb);
             else if (drop) {
-                const uint4 r = philox4x32_10((uint64_t)(nxt * kTile + row), a.drop.stream, step, seed);
+                const uint4 r = philox4x32_10((uint64_t)((long long)nxt * kTile + row), a.drop.stream, step, seed);
                 keep_lo[row] = r.x;
                 keep_hi_next = r.y;
             }
-            if (nxt + stride < n_tiles) xr = xs_prefetch(a.x, pos, a.T, tid);
-            pos.advance(pos_step, a.T);
+            if (nxt2 < n_tiles) { pos.init(nxt2, a.T); xr = xs_prefetch(a.x, pos, a.T, tid); }
         }
         TOCK(2);
         TICK();
@@ -455,6 +465,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
         TOCK(3);
         TICK();
         __syncthreads();                          // A: everybody holds its y, has pooled `prev` and written the rows of `nxt`
+        const int nxt3 = tq[2];
         TOCK(4);
         TICK();
         if (warp == 0 && has_next) {
@@ -492,7 +503,7 @@ cnn0_fwd_kernel(Cnn0Args a) {
                              "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
             }
         }
-        if (has_next && nxt + stride < n_tiles) xs_commit(xr, xs, tid);      // rows of the tile after `nxt` (those of `nxt` were consumed before A)
+        if (has_next && nxt2 < n_tiles) xs_commit(xr, xs, tid);      // rows of `nxt2` (those of `nxt` were consumed before A)
         TOCK(6);
         TICK();
         __syncthreads();                          // C: z of `cur` is complete, its u columns are drained
@@ -501,13 +512,14 @@ cnn0_fwd_kernel(Cnn0Args a) {
         ++n_done;
 #endif
         prev = cur;
+        cur = nxt; nxt = nxt2; nxt2 = nxt3;
     }
 #ifdef DCASE_CNN0_TIMING
     if (blockIdx.x == 7 && (tid == 0 || tid == 160))
         printf("cnn0_fwd tid %d: total %lld tiles %d | wait y + mma1 %lld | pool %lld | taps %lld | phase d %lld | sync A %lld | mma0+mask+wait %lld | phase f %lld | sync C %lld\n",
                tid, clock64() - t_begin, n_done, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7]);
 #endif
-    if (prev >= 0) pool_tile(a_a, tid, pool_scale, out_f ? out_f + prev * 16 * 64 : nullptr, out_h ? out_h + prev * 16 * 16 : nullptr);
+    if (prev >= 0) pool_tile(a_a, tid, pool_scale, out_f ? out_f + (long long)prev * 16 * 64 : nullptr, out_h ? out_h + (long long)prev * 16 * 16 : nullptr);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 128);
@@ -806,10 +818,13 @@ int cnn0_kernels_init() {
 }
 
 int launch_cnn0_fwd(const float* x, int B, int T, const float* fold0, const float* glu_w, const float* glu_b,
-                    DropoutCfg drop, float* out, void* out_h, int num_sms, cudaStream_t s) {
+                    DropoutCfg drop, float* out, void* out_h, unsigned int* tile_ctr, int num_sms, cudaStream_t s) {
     DCASE_PROF("cnn0_fused_fwd", s);
+    DCASE_REQUIRE((long long)B * T / 2 < (1ll << 30), "batch too large");
+    DCASE_CUDA_CHECK(cudaMemsetAsync(tile_ctr, 0, sizeof(unsigned int), s));
     Cnn0Args a{};
     a.x = x; a.B = B; a.T = T; a.fold0 = fold0; a.glu_w = glu_w; a.glu_b = glu_b; a.drop = drop; a.out = out; a.out_h = out_h;
+    a.tile_ctr = tile_ctr;
     const long long n_tiles = (long long)B * T / 2;
     const long long grid = n_tiles < (long long)kFwdCtasPerSm * num_sms ? n_tiles : (long long)kFwdCtasPerSm * num_sms;
     cnn0_fwd_kernel<<<(int)grid, kFwdThreads, kFwdSmemBytes, s>>>(a);
