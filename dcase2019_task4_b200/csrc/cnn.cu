@@ -81,7 +81,7 @@ struct Bn0FinalizeArgs {      // training: the LAST block of the moments kernel 
     float *running, *fold0;
 };
 
-constexpr int kMomSeg = 16;
+constexpr int kMomSeg = 18;      // 864 frames = 48 segments per clip: 288 blocks of four strips at B = 24, one wave of two CTAs per SM
 constexpr int kMomPitch = 4 * 65 + 1;      // floats per row of the reduction buffer (4 strips of 64 threads, padded)
 constexpr int kMomSmemBytes = 54 * kMomPitch * 4;
 __global__ void __launch_bounds__(256)
@@ -98,29 +98,32 @@ cnn0_moments_kernel(const float* __restrict__ x, int B, int T, double* __restric
     for (int sg = blockIdx.x * 4 + strip; sg < n_seg; sg += gridDim.x * 4) {
         const int b = sg / segs_per_clip, t0 = (sg - b * segs_per_clip) * kMomSeg;
         const float* xb = x + (long long)b * T * 64 + f;
-        float r0[3], r1[3], r2[3];
-        auto load_row = [&](int t, float (&r)[3]) {
-            const bool tv = t >= 0 && t < T;
+        // all 18 x 3 values of the segment are requested up front (independent loads in flight together): with the rolling
+        // three-row window every iteration waited out an L2 / HBM round trip, 16 of them in a row -- the kernel's 19 us
+        float r[kMomSeg + 2][3];
+#pragma unroll
+        for (int k = 0; k < kMomSeg + 2; ++k) {
+            const int t = t0 - 1 + k;
+            const bool tv = t >= 0 && t < T && k <= (T - t0 < kMomSeg ? T - t0 : kMomSeg) + 1;
             const float* row = xb + (long long)t * 64;
-            r[0] = (tv && f > 0) ? __ldg(row - 1) : 0.f;
-            r[1] = tv ? __ldg(row) : 0.f;
-            r[2] = (tv && f < 63) ? __ldg(row + 1) : 0.f;
-        };
-        load_row(t0 - 1, r0);
-        load_row(t0, r1);
-        const int t_end = min(t0 + kMomSeg, T);
-        for (int t = t0; t < t_end; ++t) {
-            load_row(t + 1, r2);
-            const float tap[9] = {r0[0], r0[1], r0[2], r1[0], r1[1], r1[2], r2[0], r2[1], r2[2]};   // k = (dy+1)*3 + (dx+1)
-            int i = 9;
+            r[k][0] = (tv && f > 0) ? __ldg(row - 1) : 0.f;
+            r[k][1] = tv ? __ldg(row) : 0.f;
+            r[k][2] = (tv && f < 63) ? __ldg(row + 1) : 0.f;
+        }
+        const int n_rows = T - t0 < kMomSeg ? T - t0 : kMomSeg;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                acc[k] += tap[k];
+        for (int k = 0; k < kMomSeg; ++k) {
+            if (k < n_rows) {
+                const float tap[9] = {r[k][0], r[k][1], r[k][2], r[k + 1][0], r[k + 1][1], r[k + 1][2],
+                                      r[k + 2][0], r[k + 2][1], r[k + 2][2]};                        // k = (dy+1)*3 + (dx+1)
+                int i = 9;
 #pragma unroll
-                for (int l = k; l < 9; ++l) { acc[i] = fmaf(tap[k], tap[l], acc[i]); ++i; }
+                for (int a = 0; a < 9; ++a) {
+                    acc[a] += tap[a];
+#pragma unroll
+                    for (int l = a; l < 9; ++l) { acc[i] = fmaf(tap[a], tap[l], acc[i]); ++i; }
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
         }
     }
     // Block reduction through shared memory: every thread parks its 54 partials (conflict-free, transposed), then thread
@@ -291,7 +294,7 @@ int launch_cnn0_moments(const float* x, int B, int T, double* mom, const float* 
     const long long n_seg = (long long)B * ((T + kMomSeg - 1) / kMomSeg);
     DCASE_REQUIRE(n_seg < (1ll << 30), "batch too large");
     long long blocks = (n_seg + 3) / 4;
-    if (blocks > num_sms * 4) blocks = num_sms * 4;
+    if (blocks > num_sms * 2) blocks = num_sms * 2;      // 127 registers: two CTAs per SM, one wave
     Bn0FinalizeArgs fin{(long long)B * T * 64, conv_w, conv_b, gamma, beta, running, fold0};
     cnn0_moments_kernel<<<(int)blocks, 256, kMomSmemBytes, s>>>(x, B, T, mom, fin);
     DCASE_LAUNCH_CHECK();
