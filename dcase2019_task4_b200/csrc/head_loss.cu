@@ -10,6 +10,8 @@ namespace {
 
 constexpr int kD = 128;        // 2 * hidden
 constexpr int kMaxC = 16;      // class slots
+constexpr int kHeadThreads = 256;
+constexpr int kHeadRows = 128;    // rows of a clip staged per pass
 
 template <int KC>
 __device__ __forceinline__ void softmax_classes(const float (&ls)[KC], int NC, float (&a_raw)[KC]) {
@@ -25,10 +27,20 @@ __device__ __forceinline__ void softmax_classes(const float (&ls)[KC], int NC, f
 }
 
 __device__ __forceinline__ void load_head_weights(const HeadArgs& a, float* Wd, float* Ws, float* bd, float* bs) {
-    for (int i = threadIdx.x; i < kMaxC * kD; i += blockDim.x) {
+    // all 16 loads of a thread are requested before the first is stored: as a rolled loop every iteration waited out an L2
+    // round trip (kHeadThreads = 256 threads, kMaxC * kD = 2048 floats per matrix)
+    float wd[kMaxC * kD / kHeadThreads], wsv[kMaxC * kD / kHeadThreads];
+#pragma unroll
+    for (int k = 0; k < kMaxC * kD / kHeadThreads; ++k) {
+        const int i = threadIdx.x + k * kHeadThreads;
         const bool ok = i < a.NC * kD;
-        Wd[i] = ok ? __ldg(a.w_dense + i) : 0.f;
-        Ws[i] = ok ? __ldg(a.w_soft + i) : 0.f;
+        wd[k] = ok ? __ldg(a.w_dense + i) : 0.f;
+        wsv[k] = ok ? __ldg(a.w_soft + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxC * kD / kHeadThreads; ++k) {
+        Wd[threadIdx.x + k * kHeadThreads] = wd[k];
+        Ws[threadIdx.x + k * kHeadThreads] = wsv[k];
     }
     if (threadIdx.x < kMaxC) {
         bd[threadIdx.x] = threadIdx.x < a.NC ? __ldg(a.b_dense + threadIdx.x) : 0.f;
@@ -44,7 +56,6 @@ __device__ __forceinline__ void load_head_weights(const HeadArgs& a, float* Wd, 
 // reads and 2560 serial FMAs per thread.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kXPitch = 132;
-constexpr int kHeadThreads = 256;
 
 // x rows [t0, t0 + n_rows) of clip b -> xm[r][kXPitch] with inverted dropout (keep bits from Philox, one call per row)
 __device__ __forceinline__ void stage_rows(const HeadArgs& a, int b, int t0, int n_rows, uint64_t seed, uint32_t step, float* xm,
@@ -53,9 +64,19 @@ __device__ __forceinline__ void stage_rows(const HeadArgs& a, int b, int t0, int
     if (a.drop && tid < n_rows) keep_s[tid] = philox4x32_10((uint64_t)((long long)b * a.To + t0 + tid), a.stream, step, seed);
     if (a.drop) __syncthreads();
     const float4* src = reinterpret_cast<const float4*>(a.x + ((long long)b * a.To + t0) * kD);
-    for (int i = tid; i < n_rows * (kD / 4); i += kHeadThreads) {
+    constexpr int kIters = kHeadRows * (kD / 4) / kHeadThreads;      // 16: every load is in flight before the first use
+    float4 vv[kIters];
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+        const int i = tid + k * kHeadThreads;
+        vv[k] = i < n_rows * (kD / 4) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kIters; ++k) {
+        const int i = tid + k * kHeadThreads;
+        if (i >= n_rows * (kD / 4)) break;
         const int r = i >> 5, k4 = i & 31;
-        float4 v = __ldg(src + i);
+        float4 v = vv[k];
         if (a.drop) {
             const uint4 kw4 = keep_s[r];
             const uint32_t kw = k4 < 8 ? kw4.x : (k4 < 16 ? kw4.y : (k4 < 24 ? kw4.z : kw4.w));
@@ -86,7 +107,6 @@ __device__ __forceinline__ void head_logits(const float* xm_row, const float* W,
 }
 
 // dynamic smem: Wd, Ws [16][128] | bd, bs [16] | keep [128] uint4 | xm [128][132] | ex [128][2 * 16]
-constexpr int kHeadRows = 128;
 constexpr size_t kHeadSmem = (2 * kMaxC * kD + 2 * kMaxC) * sizeof(float) + kHeadRows * sizeof(uint4) +
                              (kHeadRows * kXPitch + kHeadRows * 2 * kMaxC) * sizeof(float);
 
