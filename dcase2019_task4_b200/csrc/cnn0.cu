@@ -758,7 +758,13 @@ __device__ __forceinline__ void cnn0_bwd_finalize_body(const Cnn0FinArgs& f, con
         U[r][j] = __ldcg(us + r * 16 + j);               // from L2: other CTAs' atomics
         W0e[r][j] = j < 9 ? fold0[kFold0Wf + j * 64 + r] : fold0[kFold0Bf + r];
     }
-    for (int i = tid; i < 4096; i += nt) Wg[(i >> 6) * 65 + (i & 63)] = __ldg(f.glu_w_raw + i);
+    for (int i0 = 0; i0 < 4096; i0 += 8 * nt) {         // eight loads in flight per thread (this runs in ONE CTA, on the chain)
+        float w8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = i0 + tid + k * nt; w8[k] = i < 4096 ? __ldg(f.glu_w_raw + i) : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = i0 + tid + k * nt; if (i < 4096) Wg[(i >> 6) * 65 + (i & 63)] = w8[k]; }
+    }
     __syncthreads();
     for (int i = tid; i < 4096; i += nt) {              // dWg[n][k] = sum_j U[n][j] W0e[k][j]
         const int n = i >> 6, k = i & 63;

@@ -204,22 +204,38 @@ __device__ __forceinline__ void mt_loss_body(const LossArgs& a, float (*red)[6],
         const bool in_strong = b >= a.strong_lo && b < a.strong_hi;
         const bool in_weak = b >= a.weak_lo && b < a.weak_hi;
         const long long base = (long long)b * per_clip;
-        for (int i = tid; i < per_clip; i += 256) {
+        // the clip's elements in passes of up to 8 x 256: every load of a pass is requested before the first logarithm
+        // (as a rolled loop each iteration waited out its own L2 round trips)
+        for (int i0 = 0; i0 < per_clip; i0 += 8 * 256) {
+            float ps[8], ys[8], ts[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + tid + 256 * k;
+                const bool ok = i < per_clip;
+                ps[k] = ok ? a.strong_s[base + i] : 0.5f;
+                ys[k] = ok && in_strong ? a.target[base + i] : 0.f;
+                ts[k] = ok && has_t ? a.strong_t[base + i] : 0.5f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + tid + 256 * k;
+                if (i >= per_clip) break;
             const long long e = base + i;
-            const float p = a.strong_s[e];
+            const float p = ps[k];
             float d = 0.f;
             if (in_strong) {
-                const float y = a.target[e];
+                const float y = ys[k];
                 s_bce += bce_term(p, y);
-                if (has_t) s_bce_t += bce_term(a.strong_t[e], y);
+                if (has_t) s_bce_t += bce_term(ts[k], y);
                 d = bce_grad(p, y) * inv_ns;
             }
             if (has_t) {
-                const float diff = p - a.strong_t[e];
+                const float diff = p - ts[k];
                 s_cons = fmaf(diff, diff, s_cons);
                 d = fmaf(cs_scale, diff, d);
             }
             a.d_strong[e] = d;
+            }
         }
         // weak outputs of the clip: 16 lanes per class scan the clip's targets (target.max(-2), main.py:95)
         const int c = tid >> 4, l = tid & 15;
