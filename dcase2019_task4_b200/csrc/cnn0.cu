@@ -187,9 +187,20 @@ __device__ __forceinline__ void write_taps(const float* xs, int row, uint32_t t0
 
 // Wg[n][k] -> K-major SW128 B operand (two blocks of 64 rows), rounded to tf32 after the truncation compensation
 __device__ __forceinline__ void stage_wg(const float* __restrict__ glu_w, unsigned char* Wb, int t, int nt) {
-    for (int i = t; i < 4096; i += nt) {
-        const int n = i >> 6, k = i & 63;
-        *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kLinScale * kTruncComp * __ldg(glu_w + i));
+    // eight loads in flight per thread: as a rolled loop each of the 8-16 iterations waited out an L2 round trip, 5-10 us of
+    // prologue in every one of the grid's CTAs (%globaltimer, round 2)
+    for (int i0 = 0; i0 < 4096; i0 += 8 * nt) {
+        float w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int i = i0 + t + j * nt; w8[j] = i < 4096 ? __ldg(glu_w + i) : 0.f; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = i0 + t + j * nt;
+            if (i < 4096) {
+                const int n = i >> 6, k = i & 63;
+                *reinterpret_cast<float*>(Wb + (k >> 5) * 8192 + tc::sw128_off(n, k & 31)) = tc::tf32_rn(kLinScale * kTruncComp * w8[j]);
+            }
+        }
     }
 }
 
