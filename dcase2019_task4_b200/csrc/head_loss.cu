@@ -242,8 +242,18 @@ __device__ __forceinline__ void mt_loss_body(const LossArgs& a, float (*red)[6],
         if (c < a.NC) {
             const int e = b * a.NC + c;
             float y = -INFINITY;
-            if (in_weak)
-                for (int t = l; t < a.To; t += 16) y = fmaxf(y, a.target[base + (long long)t * a.NC + c]);
+            if (in_weak) {                      // passes of eight loads in flight (a rolled loop waited out an L2 round trip each)
+                for (int t0 = l; t0 < a.To; t0 += 8 * 16) {
+                    float yy[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int t = t0 + 16 * k;
+                        yy[k] = t < a.To ? a.target[base + (long long)t * a.NC + c] : -INFINITY;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) y = fmaxf(y, yy[k]);
+                }
+            }
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, o));
             if (l == 0) {
