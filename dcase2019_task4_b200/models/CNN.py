@@ -7,6 +7,8 @@ reference.  The arithmetic does not run through these torch modules: ``CRNN.forw
 slab to the sm_100a kernels.  Only the configuration ``cfg.crnn_kwargs`` selects (config.py:53-58) is in scope;
 the relu / leakyrelu / ContextGating branches (CNN.py:50-57) raise.
 """
+from collections import OrderedDict
+
 import torch
 import torch.nn as nn
 
@@ -39,17 +41,17 @@ class CNN(nn.Module):
             raise NotImplementedError("dropout must be 0 or 0.5 (one Philox bit per element)")
         self.nb_filters = nb_filters
         self.conv_dropout = conv_dropout
-        cnn = nn.Sequential()
-        for i in range(len(nb_filters)):
-            nIn = n_in_channel if i == 0 else nb_filters[i - 1]
-            nOut = nb_filters[i]
-            cnn.add_module('conv{0}'.format(i), nn.Conv2d(nIn, nOut, kernel_size[i], stride[i], padding[i]))
-            cnn.add_module('batchnorm{0}'.format(i), nn.BatchNorm2d(nOut, eps=0.001, momentum=0.99))
-            cnn.add_module('glu{0}'.format(i), GLU(nOut))
+        # the reference's child names, in its registration order (CNN.py:40-62): they are the state_dict keys
+        layers = OrderedDict()
+        widths = [n_in_channel] + list(nb_filters)
+        for i, (c_in, c_out) in enumerate(zip(widths[:-1], widths[1:])):
+            layers["conv%d" % i] = nn.Conv2d(c_in, c_out, kernel_size[i], stride[i], padding[i])
+            layers["batchnorm%d" % i] = nn.BatchNorm2d(c_out, eps=1e-3, momentum=0.99)
+            layers["glu%d" % i] = GLU(c_out)
             if conv_dropout is not None:
-                cnn.add_module('dropout{0}'.format(i), nn.Dropout(conv_dropout))
-            cnn.add_module('pooling{0}'.format(i), nn.AvgPool2d(pooling[i]))
-        self.cnn = cnn
+                layers["dropout%d" % i] = nn.Dropout(conv_dropout)
+            layers["pooling%d" % i] = nn.AvgPool2d(pooling[i])
+        self.cnn = nn.Sequential(layers)
 
     def load(self, filename=None, parameters=None):
         if filename is not None:
